@@ -1,0 +1,5 @@
+# the reference star-imports attacks, verifiers, uncertainty, probverification
+# (deepbayes/analyzers/__init__.py:1-4); only the hot-path callers are built here.
+from .verifiers import *  # noqa: F401,F403
+from .uncertainty import *  # noqa: F401,F403
+from . import verifiers, uncertainty  # noqa: F401

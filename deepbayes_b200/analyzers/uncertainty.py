@@ -1,0 +1,40 @@
+"""deepbayes/analyzers/uncertainty.py on the fused moments: the reference stacks n
+single-sample predictions in host memory (:18-22) and reduces them (:33-35); the device
+epilogue already holds sum p and sum p^2, so one predict_moments pass gives the same numbers.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def variational_uncertainty(model, input, num_samples=35):
+    """uncertainty.py:15-36: epistemic = E[p^2] - E[p]^2, aleatoric = E[p(1-p)] = E[p] - E[p^2]."""
+    if getattr(model, "det", False) or not hasattr(model, "predict_moments"):
+        p = np.asarray(model.predict(input, n=1))
+        return p ** 2 - p ** 2, p * (1 - p)
+    m1, m2 = model.predict_moments(input, n=num_samples)
+    return m2 - m1 ** 2, m1 - m2
+
+
+def predictive_entropy(model, input, num_models=35):
+    """uncertainty.py:42-51."""
+    y_pred = np.asarray(model.predict(input, n=num_models)) + 0.001
+    entropy = [-1 * np.sum(i * np.log(i)) for i in y_pred]
+    return list(np.nan_to_num(entropy))
+
+
+def likelihood_ratio(model, input_indist, input_outdist, labels=-1, num_models=35):
+    """uncertainty.py:57-71."""
+    indist_pred = np.asarray(model.predict(input_indist, n=num_models))
+    outdist_pred = np.asarray(model.predict(input_outdist, n=num_models))
+    in_like = np.asarray([np.max(p) for p in indist_pred])
+    out_like = np.asarray([np.max(p) for p in outdist_pred])
+    return np.mean(out_like) / np.mean(in_like)
+
+
+def auroc(model, input, labels, num_samples=35):
+    """uncertainty.py:78-82."""
+    from sklearn.metrics import roc_auc_score
+    y_pred = np.asarray(model.predict(input, n=num_samples))
+    y_pred = y_pred.reshape(-1, y_pred.shape[-1])
+    return roc_auc_score(labels, y_pred, average='macro', multi_class="ovr")

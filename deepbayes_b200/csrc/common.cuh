@@ -1,0 +1,101 @@
+// Shared device/host helpers for the deepbayes_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+
+namespace dbx {
+
+extern thread_local std::string g_err;
+extern std::atomic<long long> g_launches;
+
+int set_err(const char* fmt, ...);
+
+#define DBX_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::dbx::set_err("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define DBX_CHECK(cond, ...)                         \
+  do {                                               \
+    if (!(cond)) return ::dbx::set_err(__VA_ARGS__); \
+  } while (0)
+
+// every kernel launch goes through this so `gpu_launches` is a count, not a guess
+#define DBX_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                     \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
+    ::dbx::g_launches.fetch_add(1, std::memory_order_relaxed);             \
+    DBX_CUDA(cudaGetLastError());                                          \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  counter = (blk lo, blk hi, sample lo, sample hi),
+// key = (seed lo, seed hi); block blk yields the noise of flat elements 4*blk .. 4*blk+3.
+// ---------------------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// Box-Muller on two 32-bit words: u1 = (a+1)*2^-32 in (0,1], u2 = b*2^-32 in [0,1).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  // (a + 1) * 2^-32 computed so that it never rounds to 0 and never exceeds 1
+  const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 2.3283064365386963e-10f);
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float rad = sqrtf(-2.0f * __logf(fminf(u1, 1.0f)));
+  float sn, cs;
+  __sincosf(6.283185307179586f * (u2 - 0.5f), &sn, &cs);  // angle in [-pi, pi)
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t sample, uint64_t blk, float z[4]) {
+  Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)sample, (uint32_t)(sample >> 32),
+                            (uint32_t)seed, (uint32_t)(seed >> 32));
+  box_muller(r.x, r.y, z[0], z[1]);
+  box_muller(r.z, r.w, z[2], z[3]);
+}
+
+// tf.math.softplus with TensorFlow's CPU thresholds.
+__device__ __forceinline__ float softplus_tf(float x) {
+  const float thr = -13.942385f;  // ln(FLT_EPSILON) + 2
+  if (x > -thr) return x;
+  const float ex = expf(x);
+  if (x < thr) return ex;
+  return log1pf(ex);
+}
+
+__device__ __forceinline__ float apply_act(int act, float z) {
+  switch (act) {
+    case 1: return fmaxf(z, 0.f);
+    case 3: return tanhf(z);
+    case 4: return 1.f / (1.f + expf(-z));
+    default: return z;  // linear; softmax is applied by the accumulation kernels
+  }
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+}  // namespace dbx

@@ -1,0 +1,814 @@
+// deepbayes_b200 engine: model plan, generic sm_100a kernels (every layer kind, fp32 and
+// bf16 storage) and the C ABI of include/deepbayes_b200.h.  The tcgen05 fast path for MLPs
+// lives in fused_mlp.cu and is tried first by dbx_predict / dbx_count_predicate.
+//
+// Reference behaviour restated here (paths relative to the reference checkout):
+//   sampling      deepbayes/posteriormodel.py:60-79, optimizers/optimizer.py:197-202,
+//                 optimizers/bayesbybackprop.py:50-56,176-181
+//   MC predictive deepbayes/posteriormodel.py:81-101 (probs), :114-139 (logits)
+//   forward       Keras Sequential Dense/Conv2D/MaxPool/Flatten (third-party)
+//   predicate     deepbayes/analyzers/verifiers.py:537-557, 563-653
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include "engine.h"
+
+namespace dbx {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+static int g_last_path = 0;
+
+int set_err(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_open = nullptr;
+
+void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_prof_open);
+  cudaEventRecord(g_prof_open, st);
+}
+void prof_end(cudaStream_t st, double flops) {
+  if (!g_prof_on || !g_prof_open) return;
+  ProfRec r; r.a = g_prof_open; r.flops = flops; g_prof_open = nullptr;
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, st);
+  g_prof.push_back(r);
+}
+
+int ensure_ws(Workspace& w, size_t bytes) {
+  if (w.bytes >= bytes) return 0;
+  if (w.ptr) DBX_CUDA(cudaFree(w.ptr));
+  w.ptr = nullptr; w.bytes = 0;
+  DBX_CUDA(cudaMalloc(&w.ptr, bytes));
+  w.bytes = bytes;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------------------
+
+// W_s = mu + (inflate*sigma)*eps_s, written as fp32 in flat Keras order.
+// One thread = one Philox block = 4 consecutive elements of one sample.
+__global__ void sample_f32_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
+                                  const float* __restrict__ eps, float inflate, uint64_t seed, int64_t s0,
+                                  int64_t n, int64_t P, int unfused, float* __restrict__ W,
+                                  float* __restrict__ eps_out) {
+  const int64_t nblk = (P + 3) >> 2;
+  const int64_t total = n * nblk;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = t / nblk, blk = t - s * nblk;
+    const int64_t j0 = blk << 2;
+    float z[4];
+    if (eps == nullptr) philox_normal4(seed, (uint64_t)(s0 + s), (uint64_t)blk, z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t j = j0 + i;
+      if (j < P) {
+        const float e = eps ? eps[s * P + j] : z[i];
+        const float sc = inflate * sigma[j];
+        const float w = unfused ? __fadd_rn(mu[j], __fmul_rn(sc, e)) : fmaf(sc, e, mu[j]);
+        W[s * P + j] = w;
+        if (eps_out) eps_out[s * P + j] = e;
+      }
+    }
+  }
+}
+
+// Same draw, scattered into the bf16 device layout (kernels -> padded bf16 rows, biases ->
+// fp32 side array).  src != nullptr converts stored samples instead (rows idx[s] / j0+s).
+__global__ void sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
+                                   const float* __restrict__ eps, float inflate, uint64_t seed, int64_t s0,
+                                   int64_t n, int64_t P, const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                   int64_t j0row, TensorTable tab, __nv_bfloat16* __restrict__ W16, int64_t P16,
+                                   float* __restrict__ B32, int64_t PB) {
+  const int64_t nblk = (P + 3) >> 2;
+  const int64_t total = n * nblk;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = t / nblk, blk = t - s * nblk;
+    const int64_t j0 = blk << 2;
+    float w[4];
+    if (src) {
+      const int64_t row = idx ? (int64_t)idx[s] : (j0row + s);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = (j0 + i < P) ? src[row * P + j0 + i] : 0.f;
+    } else {
+      float z[4];
+      if (eps == nullptr) philox_normal4(seed, (uint64_t)(s0 + s), (uint64_t)blk, z);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t j = j0 + i;
+        if (j < P) {
+          const float e = eps ? eps[s * P + j] : z[i];
+          w[i] = fmaf(inflate * sigma[j], e, mu[j]);
+        } else w[i] = 0.f;
+      }
+    }
+    int ti = 0;
+    while (ti + 1 < tab.n && j0 >= tab.src_off[ti] + tab.size[ti]) ++ti;
+    const int64_t rel = j0 - tab.src_off[ti];
+    if (!tab.is_bias[ti] && tab.cols_pad[ti] == tab.cols[ti] && rel + 4 <= tab.size[ti]) {
+      // fast path: 4 elements of an unpadded kernel tensor -> one 8-byte store
+      __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(w[2], w[3]);
+      uint2 v;
+      v.x = *reinterpret_cast<uint32_t*>(&lo);
+      v.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(W16 + s * P16 + tab.dst_off[ti] + rel) = v;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t j = j0 + i;
+        if (j >= P) break;
+        while (ti + 1 < tab.n && j >= tab.src_off[ti] + tab.size[ti]) ++ti;
+        const int64_t r = j - tab.src_off[ti];
+        if (tab.is_bias[ti]) {
+          B32[s * PB + tab.dst_off[ti] + r] = w[i];
+        } else {
+          const int64_t row = r / tab.cols[ti], col = r - row * tab.cols[ti];
+          W16[s * P16 + tab.dst_off[ti] + row * tab.cols_pad[ti] + col] = __float2bfloat16_rn(w[i]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void softplus_kernel(const float* __restrict__ rho, float* __restrict__ sigma, int64_t P) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < P; j += (int64_t)gridDim.x * blockDim.x)
+    sigma[j] = softplus_tf(rho[j]);
+}
+
+__global__ void philox_raw_kernel(uint64_t seed, uint64_t s, int64_t P, uint32_t* __restrict__ out) {
+  const int64_t nblk = (P + 3) >> 2;
+  for (int64_t blk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; blk < nblk; blk += (int64_t)gridDim.x * blockDim.x) {
+    Philox4 r = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)s, (uint32_t)(s >> 32),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+    for (int i = 0; i < 4; ++i)
+      if (blk * 4 + i < P) out[blk * 4 + i] = v[i];
+  }
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t nelem) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nelem; j += (int64_t)gridDim.x * blockDim.x)
+    out[j] = from_f32<T>(in[j]);
+}
+
+// Batched Dense: out[s] = act(A[s] (M x K) * W[s] (K x N) + b[s]).  CUDA-core FFMA, fp32
+// accumulation in ascending-k order.  64x64x16 tiles, 4x4 outputs per thread.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256)
+dense_kernel(const T* __restrict__ A, int64_t a_sstride, const T* __restrict__ Wbase, int64_t w_sstride,
+             const int32_t* __restrict__ rows, int64_t row0, int64_t w_off, int ldw,
+             const float* __restrict__ Bbase, int64_t b_sstride, int64_t b_off,
+             TO* __restrict__ out, int64_t o_sstride, int M, int N, int K, int act) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int s = blockIdx.z;
+  const int64_t wrow = rows ? (int64_t)rows[s] : (row0 + s);
+  const T* Ap = A + (int64_t)s * a_sstride;
+  const T* Wp = Wbase + wrow * w_sstride + w_off;
+  const float* bp = Bbase + wrow * b_sstride + b_off;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  float acc[4][4] = {};
+  const int ar = t >> 2, ak = (t & 3) << 2;   // A tile: row ar, k ak..ak+3
+  const int wk = t >> 4, wn = (t & 15) << 2;  // W tile: k wk, n wn..wn+3
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gm = m0 + ar, gk = k0 + ak + i;
+      As[ak + i][ar] = (gm < M && gk < K) ? to_f32<T>(Ap[(int64_t)gm * K + gk]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gk = k0 + wk, gn = n0 + wn + i;
+      Ws[wk][wn + i] = (gk < K && gn < N) ? to_f32<T>(Wp[(int64_t)gk * ldw + gn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  TO* op = out + (int64_t)s * o_sstride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) op[(int64_t)gm * N + gn] = from_f32<TO>(apply_act(act, acc[i][j] + bp[gn]));
+    }
+  }
+}
+
+// Batched direct Conv2D, NHWC x HWIO -> NHWC (one thread per output element, co fastest).
+template <typename T, typename TO>
+__global__ void conv2d_kernel(const T* __restrict__ A, int64_t a_sstride, const T* __restrict__ Wbase,
+                              int64_t w_sstride, const int32_t* __restrict__ rows, int64_t row0, int64_t w_off,
+                              int ldw, const float* __restrict__ Bbase, int64_t b_sstride, int64_t b_off,
+                              TO* __restrict__ out, int64_t o_sstride, int NB, int H, int Wd, int Cin, int Ho,
+                              int Wo, int Cout, int kh, int kw, int sh, int sw, int pt, int pl, int act) {
+  const int s = blockIdx.y;
+  const int64_t wrow = rows ? (int64_t)rows[s] : (row0 + s);
+  const T* Ap = A + (int64_t)s * a_sstride;
+  const T* Wp = Wbase + wrow * w_sstride + w_off;
+  const float* bp = Bbase + wrow * b_sstride + b_off;
+  TO* op = out + (int64_t)s * o_sstride;
+  const int64_t total = (int64_t)NB * Ho * Wo * Cout;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(o % Cout);
+    int64_t r = o / Cout;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int nb = (int)(r / Ho);
+    float acc = 0.f;
+    for (int i = 0; i < kh; ++i) {
+      const int hi = ho * sh + i - pt;
+      if (hi < 0 || hi >= H) continue;
+      for (int j = 0; j < kw; ++j) {
+        const int wi = wo * sw + j - pl;
+        if (wi < 0 || wi >= Wd) continue;
+        const T* ap = Ap + (((int64_t)nb * H + hi) * Wd + wi) * Cin;
+        const T* wp = Wp + ((int64_t)(i * kw + j) * Cin) * ldw + co;
+        for (int c = 0; c < Cin; ++c) acc = fmaf(to_f32<T>(ap[c]), to_f32<T>(wp[(int64_t)c * ldw]), acc);
+      }
+    }
+    op[o] = from_f32<TO>(apply_act(act, acc + bp[co]));
+  }
+}
+
+template <typename T>
+__global__ void maxpool_kernel(const T* __restrict__ A, int64_t a_sstride, T* __restrict__ out, int64_t o_sstride,
+                               int NB, int H, int Wd, int C, int Ho, int Wo, int ph, int pw, int sh, int sw) {
+  const int s = blockIdx.y;
+  const T* Ap = A + (int64_t)s * a_sstride;
+  T* op = out + (int64_t)s * o_sstride;
+  const int64_t total = (int64_t)NB * Ho * Wo * C;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(o % C);
+    int64_t r = o / C;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int nb = (int)(r / Ho);
+    float m = -INFINITY;
+    for (int i = 0; i < ph; ++i)
+      for (int j = 0; j < pw; ++j)
+        m = fmaxf(m, to_f32<T>(Ap[(((int64_t)nb * H + ho * sh + i) * Wd + wo * sw + j) * C + c]));
+    op[o] = from_f32<T>(m);
+  }
+}
+
+// Sample-ordered accumulation of the model output over the chunk's samples:
+//   sum1[b,c] (+)= sum_s w_s * f_s[b,c],  sum2 likewise with f^2  (posteriormodel.py:95-100).
+// logits [ns,B,C] fp32 are the last layer's pre-activation values.
+__global__ void accum_kernel(const float* __restrict__ logits, int ns, int64_t B, int C, int act, int out_kind,
+                             const float* __restrict__ wts, int overwrite, float* __restrict__ sum1,
+                             float* __restrict__ sum2) {
+  const int64_t total = B * C;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = o / C;
+    const int c = (int)(o - b * C);
+    float a1 = overwrite ? 0.f : sum1[o];
+    float a2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
+    for (int s = 0; s < ns; ++s) {
+      const float* z = logits + ((int64_t)s * B + b) * C;
+      float p;
+      if (out_kind == DBX_OUT_LOGITS) p = z[c];
+      else if (act == DBX_ACT_SOFTMAX) {
+        float m = z[0];
+        for (int j = 1; j < C; ++j) m = fmaxf(m, z[j]);
+        float den = 0.f;
+        for (int j = 0; j < C; ++j) den += expf(z[j] - m);
+        p = expf(z[c] - m) / den;
+      } else p = apply_act(act, z[c]);
+      const float w = wts ? wts[s] : 1.f;
+      if (wts) { a1 = fmaf(w, p, a1); a2 = fmaf(w, p * p, a2); }
+      else { a1 += p; a2 = fmaf(p, p, a2); }
+    }
+    sum1[o] = a1;
+    if (sum2) sum2[o] = a2;
+  }
+}
+
+// flags[s,k] = (argmax_c logits[s,k,:] == labels[k]) (first maximum, like np.argmax).
+__global__ void count_kernel(const float* __restrict__ logits, int ns, int64_t K, int C,
+                             const int32_t* __restrict__ labels, uint8_t* __restrict__ flags,
+                             unsigned long long* __restrict__ counts) {
+  const int64_t total = (int64_t)ns * K;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = o % K;
+    const float* z = logits + o * C;
+    int best = 0;
+    float bv = z[0];
+    for (int j = 1; j < C; ++j)
+      if (z[j] > bv) { bv = z[j]; best = j; }
+    const int ok = (best == labels[k]);
+    if (flags) flags[o] = (uint8_t)ok;
+    if (ok) atomicAdd(counts + k, 1ULL);
+  }
+}
+
+__global__ void act_rows_kernel(int act, float* __restrict__ x, int64_t rows, int64_t cols) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float* z = x + r * cols;
+    if (act == DBX_ACT_SOFTMAX) {
+      float m = z[0];
+      for (int64_t j = 1; j < cols; ++j) m = fmaxf(m, z[j]);
+      float den = 0.f;
+      for (int64_t j = 0; j < cols; ++j) den += expf(z[j] - m);
+      for (int64_t j = 0; j < cols; ++j) z[j] = expf(z[j] - m) / den;
+    } else {
+      for (int64_t j = 0; j < cols; ++j) z[j] = apply_act(act, z[j]);
+    }
+  }
+}
+
+__global__ void finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2, float inv_n,
+                                int64_t total, float* __restrict__ mean, float* __restrict__ var) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const float m = s1[o] * inv_n;
+    mean[o] = m;
+    if (var) var[o] = s2[o] * inv_n - m * m;
+  }
+}
+
+__global__ void zero_u64_kernel(unsigned long long* p, int64_t n) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) p[o] = 0ULL;
+}
+
+static inline int grid_for(int64_t total, int block = 256) {
+  int64_t g = cdiv(total, block);
+  return (int)std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 16);
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic executor (all layer kinds; T = storage type of weights/activations)
+// ---------------------------------------------------------------------------------------
+
+static size_t ws_budget_bytes() {
+  const char* e = getenv("DBX_WS_MB");
+  size_t mb = e ? (size_t)atoll(e) : 2048;
+  return mb << 20;
+}
+
+template <typename T>
+static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
+                       cudaStream_t st) {
+  constexpr bool kBf16 = !std::is_same<T, float>::value;
+  const int64_t C = m->out_feat;
+  // per-sample workspace bytes
+  const size_t act_b = (size_t)B * m->max_feat * sizeof(T);
+  const size_t w_b = kBf16 ? ((size_t)m->P16 * 2 + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
+  const size_t per = 2 * act_b + w_b + (size_t)B * C * 4 + 256;
+  const size_t xin_b = kBf16 ? round_up((size_t)B * m->in_feat * 2, 256) : 0;
+  int64_t ns = (int64_t)std::max<size_t>(1, (ws_budget_bytes() - std::min(ws_budget_bytes(), xin_b)) / per);
+  ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
+  if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 1024)) return 1;
+  char* p = (char*)m->ws.ptr;
+  T* xin = (T*)p; p += xin_b;
+  T* act0 = (T*)p; p += round_up((size_t)ns * act_b, 256);
+  T* act1 = (T*)p; p += round_up((size_t)ns * act_b, 256);
+  float* logits = (float*)p; p += round_up((size_t)ns * B * C * 4, 256);
+  T* Wc = (T*)p;
+  float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * m->P16 * 2, 256)) : nullptr;
+
+  const T* x_in;
+  if (kBf16) {
+    DBX_LAUNCH(cast_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, xin, B * m->in_feat);
+    x_in = xin;
+  } else x_in = (const T*)x_dev;
+
+  if (sink.kind == 1 && !sink.accumulate)
+    DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, sink.counts, B);
+
+  for (int64_t c0 = 0; c0 < n; c0 += ns) {
+    const int nc = (int)std::min<int64_t>(ns, n - c0);
+    // ---- weights of this chunk
+    const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
+    const float* Bbase; int64_t b_sstride;
+    if (kBf16) {
+      const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
+      DBX_LAUNCH(sample_bf16_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma,
+                 src.eps ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int64_t)nc, m->P,
+                 src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0,
+                 m->table, (__nv_bfloat16*)Wc, m->P16, B32, m->PB);
+      Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
+    } else if (src.stored) {
+      Wbase = (const T*)m->slab; w_sstride = m->P; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
+      Bbase = m->slab; b_sstride = m->P;
+    } else {
+      const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
+      DBX_LAUNCH(sample_f32_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma,
+                 src.eps ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int64_t)nc, m->P,
+                 src.unfused ? 1 : 0, (float*)Wc, (float*)nullptr);
+      Wbase = Wc; w_sstride = m->P; Bbase = (const float*)Wc; b_sstride = m->P;
+    }
+    // ---- layers
+    const T* cur = x_in; int64_t cur_ss = 0;  // layer-0 input is shared by all samples
+    T* bufs[2] = {act0, act1}; int bi = 0;
+    for (int li = 0; li < (int)m->layers.size(); ++li) {
+      const Layer& L = m->layers[li];
+      if (L.kind == DBX_FLATTEN) continue;
+      const bool last = (li == m->last_weighted);
+      const int64_t woff = kBf16 ? L.w16_off : L.w_off;
+      const int64_t boff = kBf16 ? L.b32_off : L.b_off;
+      const int ldw = (int)(kBf16 ? L.w_cols_pad : L.w_cols);
+      const int act = last ? DBX_ACT_LINEAR : L.act;  // last activation applied by the sink
+      if (L.has_w) prof_begin(st);
+      if (L.kind == DBX_DENSE) {
+        dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), (unsigned)nc);
+        if (last) {
+          DBX_LAUNCH((dense_kernel<T, float>), grid, 256, 0, st, cur, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw,
+                     Bbase, b_sstride, boff, logits, B * C, (int)B, L.units, (int)L.in_feat, act);
+        } else {
+          DBX_LAUNCH((dense_kernel<T, T>), grid, 256, 0, st, cur, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw,
+                     Bbase, b_sstride, boff, bufs[bi], B * L.out_feat, (int)B, L.units, (int)L.in_feat, act);
+        }
+      } else if (L.kind == DBX_CONV2D) {
+        dim3 grid((unsigned)grid_for(B * L.out_feat), (unsigned)nc);
+        if (last) {
+          DBX_LAUNCH((conv2d_kernel<T, float>), grid, 256, 0, st, cur, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw,
+                     Bbase, b_sstride, boff, logits, B * C, (int)B, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.out_c,
+                     L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l, act);
+        } else {
+          DBX_LAUNCH((conv2d_kernel<T, T>), grid, 256, 0, st, cur, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw,
+                     Bbase, b_sstride, boff, bufs[bi], B * L.out_feat, (int)B, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w,
+                     L.out_c, L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l, act);
+        }
+      } else if (L.kind == DBX_MAXPOOL2D) {
+        dim3 grid((unsigned)grid_for(B * L.out_feat), (unsigned)nc);
+        DBX_LAUNCH(maxpool_kernel<T>, grid, 256, 0, st, cur, cur_ss, bufs[bi], B * L.out_feat, (int)B, L.in_h, L.in_w,
+                   L.in_c, L.out_h, L.out_w, L.kh, L.kw, L.sh, L.sw);
+      }
+      if (L.has_w)
+        prof_end(st, 2.0 * (double)L.w_rows * L.w_cols * (L.kind == DBX_CONV2D ? (double)L.out_h * L.out_w : 1.0) * (double)B * nc);
+      if (last) break;
+      cur = bufs[bi]; cur_ss = B * L.out_feat; bi ^= 1;
+    }
+    // ---- sink
+    const int act_last = m->layers[m->last_weighted].act;
+    if (sink.kind == 0) {
+      const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
+      DBX_LAUNCH(accum_kernel, grid_for(B * C), 256, 0, st, logits, nc, B, (int)C, act_last, sink.out_kind,
+                 sink.wts ? sink.wts + c0 : nullptr, overwrite, sink.sum1, sink.sum2);
+    } else {
+      DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, logits, nc, B, (int)C, sink.labels,
+                 sink.flags ? sink.flags + c0 * B : nullptr, sink.counts);
+    }
+  }
+  return 0;
+}
+
+static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink, int mode,
+               cudaStream_t st) {
+  DBX_CHECK(B > 0 && n > 0, "B and n must be positive (B=%lld n=%lld)", (long long)B, (long long)n);
+  DBX_CHECK(src.stored ? (m->slab != nullptr) : m->have_gaussian,
+            src.stored ? "no stored-sample slab set (dbx_set_samples)" : "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(m->device));
+  g_last_path = 0;
+  if (mode == DBX_MODE_BF16) {
+    const char* nf = getenv("DBX_NO_FUSED");
+    if (!(nf && nf[0] == '1')) {
+      const int r = fused_mlp_run(m, x_dev, B, n, src, sink, st);
+      if (r < 0) return 1;
+      if (r == 1) { g_last_path = 1; return 0; }
+    }
+    return run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
+  }
+  DBX_CHECK(mode == DBX_MODE_FP32, "unknown mode %d", mode);
+  return run_generic<float>(m, x_dev, B, n, src, sink, st);
+}
+
+}  // namespace dbx
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+using namespace dbx;
+
+extern "C" {
+
+const char* dbx_last_error(void) { return g_err.c_str(); }
+int dbx_version(void) { return 100; }
+int64_t dbx_launch_count(void) { return (int64_t)g_launches.load(); }
+int dbx_last_path(void) { return g_last_path; }
+
+int dbx_profile(int enable) {
+  g_prof_on = enable != 0;
+  if (!g_prof_on) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+  }
+  return 0;
+}
+
+int dbx_profile_read(double* ms_total, double* flops_total, int64_t* launches) {
+  double ms = 0, fl = 0;
+  for (auto& r : g_prof) {
+    DBX_CUDA(cudaEventSynchronize(r.b));
+    float t = 0;
+    DBX_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; fl += r.flops;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  if (ms_total) *ms_total = ms;
+  if (flops_total) *flops_total = fl;
+  if (launches) *launches = (int64_t)g_prof.size();
+  g_prof.clear();
+  return 0;
+}
+
+int dbx_create(const dbx_layer_desc* layers, int32_t n_layers, const int32_t* input_shape, int32_t input_rank,
+               int32_t device, dbx_handle* out) {
+  DBX_CHECK(layers && n_layers > 0 && input_shape && out, "dbx_create: null argument");
+  DBX_CHECK(input_rank == 1 || input_rank == 3, "input_rank must be 1 ({K}) or 3 ({H,W,C}), got %d", input_rank);
+  int ndev = 0;
+  DBX_CUDA(cudaGetDeviceCount(&ndev));
+  DBX_CHECK(device >= 0 && device < ndev, "device %d not available (%d CUDA devices)", device, ndev);
+  DBX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DBX_CUDA(cudaGetDeviceProperties(&prop, device));
+  DBX_CHECK(prop.major == 10, "deepbayes_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+  dbx_model* m = new dbx_model();
+  m->device = device;
+  int h = 0, w = 0, c = 0;
+  int64_t feat = 0;
+  bool spatial = (input_rank == 3);
+  if (spatial) { h = input_shape[0]; w = input_shape[1]; c = input_shape[2]; feat = (int64_t)h * w * c; }
+  else feat = input_shape[0];
+  m->in_feat = feat; m->max_feat = feat;
+  int64_t off = 0, off16 = 0, offb = 0;
+  m->table.n = 0; m->is_mlp = true;
+  for (int i = 0; i < n_layers; ++i) {
+    const dbx_layer_desc& d = layers[i];
+    Layer L;
+    L.kind = d.kind; L.act = d.activation; L.units = d.units; L.kh = d.kh; L.kw = d.kw;
+    L.sh = d.sh > 0 ? d.sh : 1; L.sw = d.sw > 0 ? d.sw : 1; L.pad = d.padding;
+    L.in_feat = feat; L.in_h = h; L.in_w = w; L.in_c = c;
+    if (d.kind == DBX_DENSE) {
+      if (spatial) { delete m; return set_err("layer %d: Dense after a spatial layer needs a Flatten first", i); }
+      L.has_w = true; L.w_rows = feat; L.w_cols = d.units; L.out_feat = d.units;
+    } else if (d.kind == DBX_CONV2D) {
+      if (!spatial) { delete m; return set_err("layer %d: Conv2D needs an {H,W,C} input", i); }
+      m->is_mlp = false;
+      L.has_w = true; L.w_rows = (int64_t)d.kh * d.kw * c; L.w_cols = d.units;
+      if (d.padding == DBX_PAD_SAME) {
+        L.out_h = (h + L.sh - 1) / L.sh; L.out_w = (w + L.sw - 1) / L.sw;
+        const int ph = std::max((L.out_h - 1) * L.sh + d.kh - h, 0), pw = std::max((L.out_w - 1) * L.sw + d.kw - w, 0);
+        L.pad_t = ph / 2; L.pad_l = pw / 2;
+      } else { L.out_h = (h - d.kh) / L.sh + 1; L.out_w = (w - d.kw) / L.sw + 1; }
+      L.out_c = d.units; L.out_feat = (int64_t)L.out_h * L.out_w * L.out_c;
+      h = L.out_h; w = L.out_w; c = L.out_c;
+    } else if (d.kind == DBX_MAXPOOL2D) {
+      if (!spatial) { delete m; return set_err("layer %d: MaxPool2D needs an {H,W,C} input", i); }
+      m->is_mlp = false;
+      L.out_h = (h - d.kh) / L.sh + 1; L.out_w = (w - d.kw) / L.sw + 1; L.out_c = c;
+      L.out_feat = (int64_t)L.out_h * L.out_w * c;
+      h = L.out_h; w = L.out_w;
+    } else if (d.kind == DBX_FLATTEN) {
+      L.out_feat = feat; spatial = false; h = w = c = 0;
+    } else { delete m; return set_err("layer %d: unknown kind %d", i, d.kind); }
+    if (L.out_feat <= 0) { delete m; return set_err("layer %d: empty output", i); }
+    if (L.has_w) {
+      if (m->table.n + 2 > DBX_MAX_TENSORS) { delete m; return set_err("too many weight tensors"); }
+      L.w_off = off; off += L.w_rows * L.w_cols;
+      L.b_off = off; off += L.w_cols;
+      L.w_cols_pad = round_up(L.w_cols, 8);
+      L.w16_off = off16; off16 += round_up(L.w_rows * L.w_cols_pad, 64);
+      L.b32_off = offb; offb += round_up(L.w_cols, 4);
+      TensorTable& T = m->table;
+      T.src_off[T.n] = L.w_off; T.size[T.n] = L.w_rows * L.w_cols; T.dst_off[T.n] = L.w16_off;
+      T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols_pad; T.is_bias[T.n] = 0; ++T.n;
+      T.src_off[T.n] = L.b_off; T.size[T.n] = L.w_cols; T.dst_off[T.n] = L.b32_off;
+      T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols; T.is_bias[T.n] = 1; ++T.n;
+      m->flops += 2 * L.w_rows * L.w_cols * (L.kind == DBX_CONV2D ? (int64_t)L.out_h * L.out_w : 1);
+      m->last_weighted = i;
+    }
+    feat = L.out_feat;
+    m->max_feat = std::max(m->max_feat, feat);
+    m->layers.push_back(L);
+  }
+  if (m->last_weighted < 0) { delete m; return set_err("model has no weighted layer"); }
+  for (int i = m->last_weighted + 1; i < n_layers; ++i)
+    if (m->layers[i].kind != DBX_FLATTEN) { delete m; return set_err("layers after the last weighted layer are not supported"); }
+  m->P = off; m->P16 = off16; m->PB = offb; m->out_feat = m->layers[m->last_weighted].out_feat;
+  if (cudaMalloc(&m->mu, (size_t)m->P * 4) != cudaSuccess || cudaMalloc(&m->sigma, (size_t)m->P * 4) != cudaSuccess) {
+    delete m; return set_err("cudaMalloc of posterior buffers failed");
+  }
+  *out = m;
+  return 0;
+}
+
+int dbx_destroy(dbx_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  fused_mlp_free(h);
+  cudaFree(h->mu); cudaFree(h->sigma); cudaFree(h->ws.ptr); cudaFree(h->fused_ws.ptr);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  cudaFree(h->d_x); cudaFree(h->d_s1); cudaFree(h->d_s2);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int dbx_param_count(dbx_handle h, int64_t* P) { DBX_CHECK(h && P, "null argument"); *P = h->P; return 0; }
+int dbx_output_dim(dbx_handle h, int64_t* C) { DBX_CHECK(h && C, "null argument"); *C = h->out_feat; return 0; }
+int dbx_input_dim(dbx_handle h, int64_t* K) { DBX_CHECK(h && K, "null argument"); *K = h->in_feat; return 0; }
+int dbx_flops_per_forward(dbx_handle h, int64_t* f) { DBX_CHECK(h && f, "null argument"); *f = h->flops; return 0; }
+
+int dbx_set_gaussian(dbx_handle h, const float* mu, const float* sigma, int64_t P, int32_t on_device, void* stream) {
+  DBX_CHECK(h && mu && sigma, "null argument");
+  DBX_CHECK(P == h->P, "parameter count mismatch: model has %lld, got %lld", (long long)h->P, (long long)P);
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  DBX_CUDA(cudaMemcpyAsync(h->mu, mu, (size_t)P * 4, k, st));
+  DBX_CUDA(cudaMemcpyAsync(h->sigma, sigma, (size_t)P * 4, k, st));
+  if (!on_device) DBX_CUDA(cudaStreamSynchronize(st));
+  h->have_gaussian = true;
+  return 0;
+}
+
+int dbx_set_gaussian_rho(dbx_handle h, const float* mu, const float* rho, int64_t P, int32_t on_device, void* stream) {
+  if (dbx_set_gaussian(h, mu, rho, P, on_device, stream)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  DBX_LAUNCH(softplus_kernel, grid_for(P), 256, 0, st, h->sigma, h->sigma, P);
+  return 0;
+}
+
+int dbx_get_gaussian(dbx_handle h, float* mu_host, float* sigma_host, int64_t P, void* stream) {
+  DBX_CHECK(h && h->have_gaussian, "no Gaussian posterior set");
+  DBX_CHECK(P == h->P, "parameter count mismatch");
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mu_host) DBX_CUDA(cudaMemcpyAsync(mu_host, h->mu, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+  if (sigma_host) DBX_CUDA(cudaMemcpyAsync(sigma_host, h->sigma, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+  DBX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dbx_set_samples(dbx_handle h, const float* slab_dev, int64_t S, int64_t P) {
+  DBX_CHECK(h && slab_dev && S > 0, "null/empty slab");
+  DBX_CHECK(P == h->P, "parameter count mismatch: model has %lld, slab rows have %lld", (long long)h->P, (long long)P);
+  h->slab = slab_dev; h->S = S;
+  return 0;
+}
+
+int dbx_sample(dbx_handle h, uint64_t seed, int64_t s0, int64_t n, const float* eps_dev, float inflate,
+               float* W_out_dev, float* eps_out_dev, void* stream) {
+  DBX_CHECK(h && W_out_dev && n > 0, "null argument");
+  DBX_CHECK(h->have_gaussian, "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DBX_LAUNCH(sample_f32_kernel, grid_for(n * ((h->P + 3) / 4)), 256, 0, st, h->mu, h->sigma, eps_dev, inflate, seed, s0,
+             n, h->P, 0, W_out_dev, eps_out_dev);
+  return 0;
+}
+
+int dbx_predict(dbx_handle h, const float* x_dev, int64_t B, int64_t n, uint64_t seed, int64_t s0, const float* eps_dev,
+                float inflate, int32_t mode, int32_t out_kind, int32_t accumulate, float* sum1_dev, float* sum2_dev,
+                void* stream) {
+  DBX_CHECK(h && x_dev && sum1_dev, "null argument");
+  Source src; src.eps = eps_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  Sink sink; sink.kind = 0; sink.out_kind = out_kind; sink.accumulate = accumulate; sink.sum1 = sum1_dev; sink.sum2 = sum2_dev;
+  return run(h, x_dev, B, n, src, sink, mode, (cudaStream_t)stream);
+}
+
+int dbx_predict_stored(dbx_handle h, const float* x_dev, int64_t B, int64_t j0, int64_t n, const int32_t* idx_dev,
+                       const float* wts_dev, int32_t mode, int32_t out_kind, int32_t accumulate, float* sum1_dev,
+                       float* sum2_dev, void* stream) {
+  DBX_CHECK(h && x_dev && sum1_dev, "null argument");
+  DBX_CHECK(idx_dev || (j0 >= 0 && j0 + n <= h->S), "stored-sample range [%lld,%lld) outside [0,%lld)", (long long)j0,
+            (long long)(j0 + n), (long long)h->S);
+  Source src; src.stored = true; src.j0 = j0; src.idx = idx_dev;
+  Sink sink; sink.kind = 0; sink.out_kind = out_kind; sink.accumulate = accumulate; sink.sum1 = sum1_dev; sink.sum2 = sum2_dev;
+  sink.wts = wts_dev;
+  return run(h, x_dev, B, n, src, sink, mode, (cudaStream_t)stream);
+}
+
+int dbx_forward_one(dbx_handle h, const float* x_dev, int64_t B, const float* W_dev, int32_t mode, int32_t out_kind,
+                    float* out_dev, void* stream) {
+  DBX_CHECK(h && x_dev && W_dev && out_dev, "null argument");
+  // a single explicit weight vector is a stored-sample posterior with S = 1
+  const float* keep = h->slab; const int64_t keepS = h->S;
+  h->slab = W_dev; h->S = 1;
+  Source src; src.stored = true; src.j0 = 0;
+  Sink sink; sink.kind = 0; sink.out_kind = out_kind; sink.sum1 = out_dev;
+  const int r = run(h, x_dev, B, 1, src, sink, mode, (cudaStream_t)stream);
+  h->slab = keep; h->S = keepS;
+  return r;
+}
+
+int dbx_bbb_forward(dbx_handle h, const float* x_dev, int64_t B, uint64_t seed, int64_t step, const float* eps_dev,
+                    int32_t mode, float* out_dev, float* W_out_dev, float* eps_out_dev, void* stream) {
+  DBX_CHECK(h && x_dev && out_dev, "null argument");
+  DBX_CHECK(h->have_gaussian, "no posterior set (dbx_set_gaussian_rho)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (W_out_dev || eps_out_dev) {
+    // the caller wants the sampled weights / noise_used: materialise once, forward with them
+    float* Wtmp = W_out_dev;
+    Workspace tmp;
+    if (!Wtmp) { if (ensure_ws(tmp, (size_t)h->P * 4)) return 1; Wtmp = (float*)tmp.ptr; }
+    DBX_LAUNCH(sample_f32_kernel, grid_for((h->P + 3) / 4), 256, 0, st, h->mu, h->sigma, eps_dev, 1.0f, seed, step,
+               (int64_t)1, h->P, 1, Wtmp, eps_out_dev);
+    const int r = dbx_forward_one(h, x_dev, B, Wtmp, mode, DBX_OUT_PROBS, out_dev, stream);
+    if (tmp.ptr) { cudaStreamSynchronize(st); cudaFree(tmp.ptr); }
+    return r;
+  }
+  Source src; src.eps = eps_dev; src.inflate = 1.f; src.seed = seed; src.s0 = step; src.unfused = true;
+  Sink sink; sink.kind = 0; sink.out_kind = DBX_OUT_PROBS; sink.sum1 = out_dev;
+  return run(h, x_dev, B, 1, src, sink, mode, st);
+}
+
+int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32_t* labels_dev, int64_t n, uint64_t seed,
+                        int64_t s0, const float* eps_dev, float inflate, int32_t mode, int32_t accumulate,
+                        uint8_t* flags_dev, int64_t* counts_dev, void* stream) {
+  DBX_CHECK(h && x_dev && labels_dev && counts_dev, "null argument");
+  Source src; src.eps = eps_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  Sink sink; sink.kind = 1; sink.accumulate = accumulate; sink.labels = labels_dev; sink.flags = flags_dev;
+  sink.counts = (unsigned long long*)counts_dev;
+  return run(h, x_dev, K, n, src, sink, mode, (cudaStream_t)stream);
+}
+
+int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, uint64_t seed, int64_t s0, float inflate,
+                     int32_t mode, int32_t out_kind, float* mean_host, float* var_host) {
+  DBX_CHECK(h && x_host && mean_host, "null argument");
+  DBX_CUDA(cudaSetDevice(h->device));
+  if (!h->own_stream) DBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = h->own_stream;
+  const size_t xb = (size_t)B * h->in_feat * 4, ob = (size_t)B * h->out_feat * 4;
+  if (h->h_pin_bytes < xb + 2 * ob) {
+    if (h->h_pin) DBX_CUDA(cudaFreeHost(h->h_pin));
+    h->h_pin = nullptr; h->h_pin_bytes = 0;
+    DBX_CUDA(cudaMallocHost(&h->h_pin, xb + 2 * ob));
+    h->h_pin_bytes = xb + 2 * ob;
+  }
+  if (h->d_x_bytes < xb) {
+    cudaFree(h->d_x); h->d_x = nullptr; h->d_x_bytes = 0;
+    DBX_CUDA(cudaMalloc(&h->d_x, xb)); h->d_x_bytes = xb;
+  }
+  if (h->d_s_bytes < ob) {
+    cudaFree(h->d_s1); cudaFree(h->d_s2); h->d_s1 = h->d_s2 = nullptr; h->d_s_bytes = 0;
+    DBX_CUDA(cudaMalloc(&h->d_s1, ob)); DBX_CUDA(cudaMalloc(&h->d_s2, ob)); h->d_s_bytes = ob;
+  }
+  memcpy(h->h_pin, x_host, xb);
+  DBX_CUDA(cudaMemcpyAsync(h->d_x, h->h_pin, xb, cudaMemcpyHostToDevice, st));
+  if (dbx_predict(h, h->d_x, B, n, seed, s0, nullptr, inflate, mode, out_kind, 0, h->d_s1, var_host ? h->d_s2 : nullptr, st))
+    return 1;
+  DBX_LAUNCH(finalize_kernel, grid_for(B * h->out_feat), 256, 0, st, h->d_s1, var_host ? h->d_s2 : nullptr,
+             1.0f / (float)n, B * h->out_feat, h->d_s1, var_host ? h->d_s2 : nullptr);
+  float* om = (float*)((char*)h->h_pin + xb);
+  float* ov = (float*)((char*)h->h_pin + xb + ob);
+  DBX_CUDA(cudaMemcpyAsync(om, h->d_s1, ob, cudaMemcpyDeviceToHost, st));
+  if (var_host) DBX_CUDA(cudaMemcpyAsync(ov, h->d_s2, ob, cudaMemcpyDeviceToHost, st));
+  DBX_CUDA(cudaStreamSynchronize(st));
+  memcpy(mean_host, om, ob);
+  if (var_host) memcpy(var_host, ov, ob);
+  return 0;
+}
+
+int dbx_activation(int32_t act, float* x_dev, int64_t rows, int64_t cols, void* stream) {
+  DBX_CHECK(x_dev && rows > 0 && cols > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DBX_LAUNCH(act_rows_kernel, grid_for(rows), 256, 0, st, act, x_dev, rows, cols);
+  return 0;
+}
+
+int dbx_philox_raw(uint64_t seed, int64_t s, int64_t P, uint32_t* out_dev, void* stream) {
+  DBX_CHECK(out_dev && P > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DBX_LAUNCH(philox_raw_kernel, grid_for((P + 3) / 4), 256, 0, st, seed, (uint64_t)s, P, out_dev);
+  return 0;
+}
+
+}  // extern "C"

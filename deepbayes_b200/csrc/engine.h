@@ -1,0 +1,99 @@
+// Internal model / plan structures shared by engine.cu (generic kernels + C ABI) and
+// fused_mlp.cu (tcgen05 fast path).  Not part of the public ABI.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "../../include/deepbayes_b200.h"
+
+namespace dbx {
+
+struct Layer {
+  int kind = 0, act = 0, units = 0, kh = 0, kw = 0, sh = 1, sw = 1, pad = 0;
+  int in_h = 0, in_w = 0, in_c = 0, out_h = 0, out_w = 0, out_c = 0, pad_t = 0, pad_l = 0;
+  int64_t in_feat = 0, out_feat = 0;
+  bool has_w = false;
+  // GEMM view of the kernel tensor: [w_rows (=fan_in or kh*kw*cin), w_cols (=units)] row-major
+  int64_t w_rows = 0, w_cols = 0;
+  int64_t w_off = 0, b_off = 0;      // offsets in the flat fp32 Keras-order vector
+  int64_t w16_off = 0, w_cols_pad = 0;  // offsets / row pitch in the padded bf16 weight layout
+  int64_t b32_off = 0;               // offset in the fp32 bias side-array used by bf16 mode
+};
+
+// One entry per Keras tensor, used by the sampling / conversion kernels to scatter the flat
+// Keras-order element index into the bf16 device layout.
+#define DBX_MAX_TENSORS 32
+struct TensorTable {
+  int n;
+  int64_t src_off[DBX_MAX_TENSORS];   // start in flat Keras order
+  int64_t size[DBX_MAX_TENSORS];
+  int64_t dst_off[DBX_MAX_TENSORS];   // start in bf16 weight layout (kernels) or bias array (biases)
+  int32_t cols[DBX_MAX_TENSORS];
+  int32_t cols_pad[DBX_MAX_TENSORS];
+  int32_t is_bias[DBX_MAX_TENSORS];
+};
+
+struct Workspace {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace dbx
+
+struct dbx_model {
+  int device = 0;
+  std::vector<dbx::Layer> layers;
+  int last_weighted = -1;
+  int64_t P = 0, in_feat = 0, out_feat = 0, flops = 0;
+  int64_t P16 = 0;   // elements of the padded bf16 weight layout (kernels only)
+  int64_t PB = 0;    // elements of the fp32 bias side-array
+  int64_t max_feat = 0;
+  bool is_mlp = false;  // only Dense layers (flatten tolerated)
+  dbx::TensorTable table;
+  float* mu = nullptr;
+  float* sigma = nullptr;
+  bool have_gaussian = false;
+  const float* slab = nullptr;
+  int64_t S = 0;
+  dbx::Workspace ws;        // generic-path workspace
+  dbx::Workspace fused_ws;  // fused-path workspace
+  // host-call staging (dbx_predict_host)
+  float* h_pin = nullptr; size_t h_pin_bytes = 0;
+  float* d_x = nullptr; size_t d_x_bytes = 0;
+  float* d_s1 = nullptr; float* d_s2 = nullptr; size_t d_s_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  void* fused_state = nullptr;  // owned by fused_mlp.cu
+};
+
+namespace dbx {
+
+// Where the per-sample weights come from.
+struct Source {
+  bool stored = false;
+  // gaussian
+  const float* eps = nullptr; float inflate = 1.f; uint64_t seed = 0; int64_t s0 = 0; bool unfused = false;
+  // stored
+  int64_t j0 = 0; const int32_t* idx = nullptr;
+};
+
+// What happens to each sample's output.
+struct Sink {
+  int kind = 0;  // 0 accumulate moments, 1 count predicate
+  int out_kind = 0; int accumulate = 0;
+  float* sum1 = nullptr; float* sum2 = nullptr; const float* wts = nullptr;
+  const int32_t* labels = nullptr; uint8_t* flags = nullptr; unsigned long long* counts = nullptr;
+};
+
+int ensure_ws(Workspace& w, size_t bytes);
+
+// Optional timing of the dominant (GEMM-carrying) kernel with CUDA events on the launching
+// stream -- read by bench.py for the roofline line (dbx_profile / dbx_profile_read).
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st, double flops);
+
+// fused_mlp.cu: returns 1 if the tcgen05 fused path handled the request, 0 if the shape is
+// not supported by it (caller uses the generic kernels), <0 on error.
+int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
+                  cudaStream_t st);
+void fused_mlp_free(dbx_model* m);
+
+}  // namespace dbx

@@ -1,0 +1,253 @@
+"""Host-side wrapper of one C-ABI handle: owns the device-resident posterior and exposes the
+hot-path calls with torch tensors as device memory (torch is plumbing here: allocation,
+streams, torch.distributed -- every FLOP is issued by libdeepbayes_b200.so)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.DbxError("deepbayes_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.cuda.current_device()
+    return torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def flatten_weights(ws: Sequence[np.ndarray]) -> np.ndarray:
+    return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws]) if len(ws) else np.zeros(0, np.float32)
+
+
+def device_activation(name: str, x):
+    """``layer.activation(x)`` on the device (verifiers.py:552-555 calls it on small arrays)."""
+    torch = _torch()
+    dev = _require_cuda()
+    lib = _lib.load()
+    a = np.asarray(x, dtype=np.float32)
+    if a.size == 0:
+        return a.copy()
+    cols = a.shape[-1] if a.ndim else 1
+    t = torch.from_numpy(np.ascontiguousarray(a).reshape(-1, cols)).to(dev)
+    _lib.check(lib.dbx_activation(_lib.ACT[name], _ptr(t), t.shape[0], t.shape[1], _stream()))
+    return t.cpu().numpy().reshape(a.shape)
+
+
+class Engine:
+    """One model plan + its device-resident posterior."""
+
+    def __init__(self, model, device=None):
+        self.lib = _lib.load()
+        self.torch = _torch()
+        self.device = _require_cuda(device)
+        self.model = model
+        descs = []
+        for l in model.layers:
+            d = _lib.LayerDesc()
+            d.activation = _lib.ACT[l.activation.name]
+            if l.kind == "dense":
+                d.kind, d.units = _lib.DENSE, l.units
+            elif l.kind == "conv2d":
+                d.kind, d.units = _lib.CONV2D, l.filters
+                d.kh, d.kw = l.kernel_size
+                d.sh, d.sw = l.strides
+                d.padding = _lib.PAD[l.padding]
+            elif l.kind == "maxpool2d":
+                d.kind = _lib.MAXPOOL2D
+                d.kh, d.kw = l.pool_size
+                d.sh, d.sw = l.strides
+            elif l.kind == "flatten":
+                d.kind = _lib.FLATTEN
+            else:
+                raise ValueError(l.kind)
+            descs.append(d)
+        arr = (_lib.LayerDesc * len(descs))(*descs)
+        shp = tuple(int(v) for v in model.feature_shape)
+        ishape = (C.c_int32 * len(shp))(*shp)
+        h = C.c_void_p()
+        _lib.check(self.lib.dbx_create(arr, len(descs), ishape, len(shp), self.device.index or 0, C.byref(h)))
+        self.h = h
+        v = C.c_int64()
+        _lib.check(self.lib.dbx_param_count(h, C.byref(v))); self.P = v.value
+        _lib.check(self.lib.dbx_output_dim(h, C.byref(v))); self.C = v.value
+        _lib.check(self.lib.dbx_input_dim(h, C.byref(v))); self.K = v.value
+        _lib.check(self.lib.dbx_flops_per_forward(h, C.byref(v))); self.flops_per_forward = v.value
+        self._slab = None
+        self._pin = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.dbx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- helpers ----------------------------------------------------------------------
+    def _dev_f32(self, a):
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.float32).contiguous()
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        if a.nbytes < (1 << 16):
+            return torch.from_numpy(a).to(self.device)
+        # large host arrays go through a cached pinned staging buffer (async H2D)
+        if self._pin is None or self._pin.numel() < a.size:
+            self._pin = torch.empty(a.size, dtype=torch.float32, pin_memory=True)
+        stage = self._pin[:a.size]
+        stage.numpy()[:] = a.reshape(-1)
+        return stage.to(self.device, non_blocking=True).reshape(a.shape)
+
+    def _as_flat(self, a):
+        if isinstance(a, self.torch.Tensor):
+            return a.reshape(-1)
+        if isinstance(a, (list, tuple)) or (isinstance(a, np.ndarray) and a.dtype == object):
+            return flatten_weights(list(a))
+        return np.asarray(a, dtype=np.float32).reshape(-1)
+
+    def _x2d(self, x):
+        t = self._dev_f32(x)
+        if t.numel() % self.K != 0:
+            raise ValueError("input with %d elements is not a multiple of the model input dim %d" % (t.numel(), self.K))
+        return t.reshape(-1, self.K)
+
+    # ---- posterior --------------------------------------------------------------------
+    def set_gaussian(self, mu, sigma, rho=False):
+        mu_t = self._dev_f32(self._as_flat(mu)).reshape(-1)
+        sg_t = self._dev_f32(self._as_flat(sigma)).reshape(-1)
+        if mu_t.numel() != self.P or sg_t.numel() != self.P:
+            raise ValueError("posterior has %d / %d parameters, model needs %d" % (mu_t.numel(), sg_t.numel(), self.P))
+        fn = self.lib.dbx_set_gaussian_rho if rho else self.lib.dbx_set_gaussian
+        _lib.check(fn(self.h, _ptr(mu_t), _ptr(sg_t), self.P, 1, _stream()))
+        self.torch.cuda.current_stream().synchronize()
+
+    def get_gaussian(self):
+        mu = np.empty(self.P, np.float32)
+        sg = np.empty(self.P, np.float32)
+        _lib.check(self.lib.dbx_get_gaussian(self.h, mu.ctypes.data_as(C.c_void_p), sg.ctypes.data_as(C.c_void_p), self.P, _stream()))
+        return mu, sg
+
+    def set_samples(self, slab):
+        """slab: [S,P] fp32 (numpy or torch); kept alive here, borrowed by the library."""
+        t = self._dev_f32(slab)
+        if t.ndim != 2 or t.shape[1] != self.P:
+            raise ValueError("slab must be [S,%d], got %r" % (self.P, tuple(t.shape)))
+        self._slab = t
+        _lib.check(self.lib.dbx_set_samples(self.h, _ptr(t), t.shape[0], t.shape[1]))
+
+    # ---- hot path ---------------------------------------------------------------------
+    def sample(self, n=1, seed=0, s0=0, eps=None, inflate=1.0, return_eps=False):
+        torch = self.torch
+        W = torch.empty((n, self.P), dtype=torch.float32, device=self.device)
+        e = None if eps is None else self._dev_f32(eps).reshape(n, self.P)
+        eo = torch.empty_like(W) if return_eps else None
+        _lib.check(self.lib.dbx_sample(self.h, seed, s0, n, _ptr(e), float(inflate), _ptr(W), _ptr(eo), _stream()))
+        return (W, eo) if return_eps else W
+
+    def predict_sums(self, x, n, seed=0, s0=0, eps=None, inflate=1.0, mode="bf16", out_kind="probs", second_moment=False,
+                     out=None):
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        s1 = out[0] if out is not None else torch.empty((B, self.C), dtype=torch.float32, device=self.device)
+        s2 = (out[1] if out is not None else torch.empty_like(s1)) if second_moment else None
+        e = None if eps is None else self._dev_f32(eps).reshape(n, self.P)
+        _lib.check(self.lib.dbx_predict(self.h, _ptr(xt), B, n, seed, s0, _ptr(e), float(inflate), _lib.MODE[mode],
+                                        _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, 0, _ptr(s1), _ptr(s2),
+                                        _stream()))
+        return s1, s2
+
+    def predict_stored_sums(self, x, n, j0=0, idx=None, wts=None, mode="fp32", out_kind="probs", second_moment=False):
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        s1 = torch.empty((B, self.C), dtype=torch.float32, device=self.device)
+        s2 = torch.empty_like(s1) if second_moment else None
+        it = None if idx is None else torch.as_tensor(np.asarray(idx, dtype=np.int32)).to(self.device)
+        wt = None if wts is None else self._dev_f32(wts).reshape(-1)
+        _lib.check(self.lib.dbx_predict_stored(self.h, _ptr(xt), B, j0, n, _ptr(it), _ptr(wt), _lib.MODE[mode],
+                                               _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, 0, _ptr(s1),
+                                               _ptr(s2), _stream()))
+        return s1, s2
+
+    def forward_device(self, x, W, mode="fp32", out_kind="probs"):
+        torch = self.torch
+        xt = self._x2d(x)
+        Wt = self._dev_f32(W).reshape(-1)
+        if Wt.numel() != self.P:
+            raise ValueError("weight vector has %d elements, model needs %d" % (Wt.numel(), self.P))
+        out = torch.empty((xt.shape[0], self.C), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dbx_forward_one(self.h, _ptr(xt), xt.shape[0], _ptr(Wt), _lib.MODE[mode],
+                                            _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, _ptr(out), _stream()))
+        return out
+
+    def forward(self, x, weights, mode="fp32", out_kind="probs"):
+        """numpy in / numpy out single forward, output shaped like Keras would."""
+        _, oshape = self.model.rows_and_outshape(np.asarray(x))
+        out = self.forward_device(np.asarray(x, dtype=np.float32), flatten_weights(weights), mode, out_kind)
+        return out.cpu().numpy().reshape(oshape)
+
+    def bbb_forward(self, x, seed=0, step=0, eps=None, mode="fp32", return_weights=False):
+        torch = self.torch
+        xt = self._x2d(x)
+        out = torch.empty((xt.shape[0], self.C), dtype=torch.float32, device=self.device)
+        e = None if eps is None else self._dev_f32(eps).reshape(-1)
+        W = torch.empty(self.P, dtype=torch.float32, device=self.device) if return_weights else None
+        eo = torch.empty(self.P, dtype=torch.float32, device=self.device) if return_weights else None
+        _lib.check(self.lib.dbx_bbb_forward(self.h, _ptr(xt), xt.shape[0], seed, step, _ptr(e), _lib.MODE[mode], _ptr(out),
+                                            _ptr(W), _ptr(eo), _stream()))
+        return (out, W, eo) if return_weights else out
+
+    def count_predicate(self, x, labels, n, seed=0, s0=0, eps=None, inflate=1.0, mode="bf16", return_flags=False):
+        torch = self.torch
+        xt = self._x2d(x)
+        K = xt.shape[0]
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1)).to(self.device)
+        if lab.numel() != K:
+            raise ValueError("need one label per input row (%d rows, %d labels)" % (K, lab.numel()))
+        counts = torch.zeros(K, dtype=torch.int64, device=self.device)
+        flags = torch.empty((n, K), dtype=torch.uint8, device=self.device) if return_flags else None
+        e = None if eps is None else self._dev_f32(eps).reshape(n, self.P)
+        _lib.check(self.lib.dbx_count_predicate(self.h, _ptr(xt), K, _ptr(lab), n, seed, s0, _ptr(e), float(inflate),
+                                                _lib.MODE[mode], 0, _ptr(flags), _ptr(counts), _stream()))
+        return (counts, flags) if return_flags else counts
+
+    def predict_host(self, x: np.ndarray, n, seed=0, s0=0, inflate=1.0, mode="bf16", out_kind="probs", variance=False):
+        """Host buffers in, host buffers out: the H2D copy of x and the D2H copy of the mean
+        happen inside the C call (this is the bench's `e2e` path)."""
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.float32)).reshape(-1, self.K)
+        B = a.shape[0]
+        mean = np.empty((B, self.C), np.float32)
+        var = np.empty((B, self.C), np.float32) if variance else None
+        _lib.check(self.lib.dbx_predict_host(
+            self.h, a.ctypes.data_as(C.c_void_p), B, n, seed, s0, float(inflate), _lib.MODE[mode],
+            _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, mean.ctypes.data_as(C.c_void_p),
+            None if var is None else var.ctypes.data_as(C.c_void_p)))
+        return (mean, var) if variance else mean
+
+    def philox_raw(self, seed, s, P):
+        torch = self.torch
+        out = torch.empty(P, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.dbx_philox_raw(seed, s, P, _ptr(out), _stream()))
+        return out.cpu().numpy().view(np.uint32)
+
+    def last_path(self) -> str:
+        return "fused_tcgen05" if self.lib.dbx_last_path() == 1 else "generic"

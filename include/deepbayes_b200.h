@@ -1,0 +1,160 @@
+/*
+ * deepbayes_b200 -- C ABI of the B200 (sm_100a) posterior-predictive engine.
+ *
+ * The reference (matthewwicker/deepbayes) has no FFI layer: its boundary is the Python object
+ * protocol the analyzers rely on (deepbayes/analyzers/attacks.py:2-7).  This header declares
+ * the entry points a binding for that protocol needs; each cites the reference code it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dbx_last_error() gives text.
+ *   - pointers named *_dev are CUDA device pointers on the handle's device, *_host are host
+ *     pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - parameters are ONE flat fp32 vector of P elements in Keras tensor order
+ *     [W0,b0,W1,b1,...], each tensor C-contiguous (Dense kernel (fan_in,fan_out); Conv2D
+ *     kernel HWIO); activations are row-major [rows, features] / NHWC.
+ *   - posterior sample ids are global (s0 + local index): results do not depend on how the
+ *     samples are split over calls or over GPUs.
+ *   - no CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef DEEPBAYES_B200_H
+#define DEEPBAYES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct dbx_model* dbx_handle;
+
+enum { DBX_DENSE = 0, DBX_CONV2D = 1, DBX_MAXPOOL2D = 2, DBX_FLATTEN = 3 };
+enum { DBX_ACT_LINEAR = 0, DBX_ACT_RELU = 1, DBX_ACT_SOFTMAX = 2, DBX_ACT_TANH = 3, DBX_ACT_SIGMOID = 4 };
+enum { DBX_PAD_VALID = 0, DBX_PAD_SAME = 1 };
+/* arithmetic mode: FP32 = fp32 FFMA everywhere (parity <=1e-5 rel); BF16 = bf16 GEMM
+ * operands on tcgen05 tensor cores, fp32 accumulate / bias / softmax / sample sums. */
+enum { DBX_MODE_FP32 = 0, DBX_MODE_BF16 = 1 };
+/* what is accumulated over samples: the model output (softmax probabilities when the last
+ * layer is softmax; posteriormodel.py:81-101) or the pre-activation logits (:114-139). */
+enum { DBX_OUT_PROBS = 0, DBX_OUT_LOGITS = 1 };
+
+/* One Keras layer (the subset the reference's forward touches). */
+typedef struct {
+  int32_t kind;       /* DBX_DENSE ... */
+  int32_t activation; /* DBX_ACT_* */
+  int32_t units;      /* Dense: fan_out; Conv2D: filters */
+  int32_t kh, kw;     /* Conv2D kernel, MaxPool window */
+  int32_t sh, sw;     /* strides */
+  int32_t padding;    /* DBX_PAD_* */
+} dbx_layer_desc;
+
+const char* dbx_last_error(void);
+int dbx_version(void);
+
+/* Build the forward plan for a Keras Sequential (replaces tf.keras.models.load_model at
+ * posteriormodel.py:37,50 / the `keras_model` argument of Optimizer.compile,
+ * optimizer.py:33-40).  input_shape = per-row feature shape: {K} for Dense-first models,
+ * {H,W,C} for Conv2D-first models. */
+int dbx_create(const dbx_layer_desc* layers, int32_t n_layers, const int32_t* input_shape,
+               int32_t input_rank, int32_t device, dbx_handle* out);
+int dbx_destroy(dbx_handle h);
+int dbx_param_count(dbx_handle h, int64_t* P);
+int dbx_output_dim(dbx_handle h, int64_t* C);
+int dbx_input_dim(dbx_handle h, int64_t* K);
+/* algorithmic FLOPs of one (posterior sample x input row) forward: 2*sum(fan_in*fan_out). */
+int dbx_flops_per_forward(dbx_handle h, int64_t* flops);
+
+/* Gaussian posterior (posteriormodel.py:40-41; optimizer.py:51-52).  `sigma` is the array
+ * the reference passes as `scale=` to np.random.normal, i.e. var.npy used AS A STD
+ * (posteriormodel.py:74-75).  Copies P floats each; on_device selects the pointer kind. */
+int dbx_set_gaussian(dbx_handle h, const float* mu, const float* sigma, int64_t P, int32_t on_device, void* stream);
+/* Bayes-by-Backprop parameterisation: sigma = softplus(rho) computed on the device with
+ * TensorFlow's thresholds (bayesbybackprop.py:22-23,54; optimizer.py:286). */
+int dbx_set_gaussian_rho(dbx_handle h, const float* mu, const float* rho, int64_t P, int32_t on_device, void* stream);
+/* Read back the device-resident mu / sigma (e.g. to write var.npy, bayesbybackprop.py:187-191). */
+int dbx_get_gaussian(dbx_handle h, float* mu_host, float* sigma_host, int64_t P, void* stream);
+
+/* Stored-sample posterior (hmc.py:308-322, posteriormodel.py:46-54,77-78): slab_dev is an
+ * HBM-resident [S,P] fp32 matrix, one stored weight sample per row (borrowed, not copied). */
+int dbx_set_samples(dbx_handle h, const float* slab_dev, int64_t S, int64_t P);
+
+/* W_s = mu + (inflate*sigma) * eps_s for s in [s0, s0+n)  (posteriormodel.py:60-79,
+ * optimizer.py:197-202, bayesbybackprop.py:176-181).  eps_dev: injected noise [n,P] fp32 or
+ * NULL -> in-register Philox4x32-10 + Box-Muller keyed by (seed, sample id, element).
+ * W_out_dev: [n,P] fp32.  eps_out_dev (optional, [n,P]) receives the noise that was used
+ * (`noise_used`, bayesbybackprop.py:57). */
+int dbx_sample(dbx_handle h, uint64_t seed, int64_t s0, int64_t n, const float* eps_dev, float inflate,
+               float* W_out_dev, float* eps_out_dev, void* stream);
+
+/* Monte-Carlo posterior predictive, Gaussian posterior (posteriormodel.py:81-101,114-139):
+ *   sum1[b,c]  = sum_{s in [s0,s0+n)} f(x_b ; W_s)      (fp32, accumulated in sample order)
+ *   sum2[b,c]  = sum_s f(...)^2                           (optional, uncertainty.py:33-35)
+ * x_dev [B,K] fp32.  The caller divides by float(n) (after the all-reduce when sharded).
+ * accumulate != 0 adds into sum1/sum2 instead of overwriting. */
+int dbx_predict(dbx_handle h, const float* x_dev, int64_t B, int64_t n, uint64_t seed, int64_t s0,
+                const float* eps_dev, float inflate, int32_t mode, int32_t out_kind, int32_t accumulate,
+                float* sum1_dev, float* sum2_dev, void* stream);
+
+/* Same loop over the stored-sample posterior: visit rows idx[j] of the slab with weight
+ * wts[j] (idx_dev NULL -> rows j0..j0+n-1; wts_dev NULL -> weight 1).  The MC draw
+ * with replacement ~ freq (posteriormodel.py:77) is idx = draws, wts = NULL; the deterministic
+ * expectation sum_i freq_i f(W_i) (probverification.py:619-650) is idx = NULL, wts = freq. */
+int dbx_predict_stored(dbx_handle h, const float* x_dev, int64_t B, int64_t j0, int64_t n,
+                       const int32_t* idx_dev, const float* wts_dev, int32_t mode, int32_t out_kind,
+                       int32_t accumulate, float* sum1_dev, float* sum2_dev, void* stream);
+
+/* One forward with explicit weights W_dev [P] (PosteriorModel._predict, posteriormodel.py:
+ * 112-113; det=True predict :92-93; Optimizer.predict optimizer.py:293-298).  out [B,C]. */
+int dbx_forward_one(dbx_handle h, const float* x_dev, int64_t B, const float* W_dev, int32_t mode,
+                    int32_t out_kind, float* out_dev, void* stream);
+
+/* Bayes-by-Backprop sampling + forward of one step (bayesbybackprop.py:46-65): draws (or takes)
+ * eps, forms W = mu + softplus(rho)*eps, forwards the mini-batch.  W_out_dev / eps_out_dev
+ * (optional, [P]) return the sampled weights and `noise_used`. */
+int dbx_bbb_forward(dbx_handle h, const float* x_dev, int64_t B, uint64_t seed, int64_t step,
+                    const float* eps_dev, int32_t mode, float* out_dev, float* W_out_dev,
+                    float* eps_out_dev, void* stream);
+
+/* Statistical-verification outer loop (verifiers.py:537-557, 563-653 with the tutorial
+ * predicate argmax == label): for each posterior sample s and each of the K fixed inputs,
+ * flag = (argmax_c logits_s(x_k) == labels[k]).  flags_dev [n,K] uint8 (optional);
+ * counts_dev [K] int64 (+= number of successes; zeroed first unless accumulate). */
+int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32_t* labels_dev, int64_t n,
+                        uint64_t seed, int64_t s0, const float* eps_dev, float inflate, int32_t mode,
+                        int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream);
+
+/* Host-buffer form of dbx_predict, the call PosteriorModel.predict(x, n) binds to: copies x
+ * (host, [B,K] fp32) to the device, runs the loop, writes mean = sum1/n ([B,C]) and, if
+ * var_host != NULL, the per-class variance sum2/n - mean^2 back to host memory. */
+int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, uint64_t seed, int64_t s0,
+                     float inflate, int32_t mode, int32_t out_kind, float* mean_host, float* var_host);
+
+/* Elementwise activation on a device buffer [rows, cols] (model.layers[-1].activation(...),
+ * verifiers.py:552-555). */
+int dbx_activation(int32_t act, float* x_dev, int64_t rows, int64_t cols, void* stream);
+
+/* Raw Philox4x32-10 words for sample id s, elements [0,P) (bit-exactness test hook). */
+int dbx_philox_raw(uint64_t seed, int64_t s, int64_t P, uint32_t* out_dev, void* stream);
+
+/* Number of kernel launches issued by this library since process start (bench `gpu_launches`). */
+int64_t dbx_launch_count(void);
+/* Time the dominant (GEMM-carrying) kernel of every call with CUDA events on the launching
+ * stream while enabled; dbx_profile_read synchronises, returns the summed device time (ms),
+ * the algorithmic FLOPs those launches carried and their count, and clears the record. */
+int dbx_profile(int enable);
+int dbx_profile_read(double* ms_total, double* flops_total, int64_t* launches);
+/* 1 if the tcgen05 fused MLP kernel served the last dbx_predict/dbx_count_predicate call. */
+int dbx_last_path(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPBAYES_B200_H */

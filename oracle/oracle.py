@@ -1,0 +1,571 @@
+"""CPU oracle for the deepbayes posterior-predictive hot path.
+
+*** TEST INFRASTRUCTURE ONLY ***
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may import this module.  The product (``deepbayes_b200``) never does: it
+calls the sm_100a CUDA library through the C ABI and fails loudly when that library is missing.
+
+What this is: a loop-faithful NumPy restatement of the reference's algorithm for the path
+named by BASELINE.json ``north_star`` (Monte-Carlo posterior predictive + Bayes-by-Backprop
+reparameterised forward).  Every function cites the reference lines it follows
+(paths relative to /root/reference).
+
+Parity status: the reference ships NO tests and NO known-answer vectors for this path and it
+cannot be imported here as-is (TensorFlow / Keras / TFP are not installed, there is no
+network).  The oracle is therefore pinned two ways, both weaker than a real golden vector:
+  (1) ``tests/golden/make_reference_fixtures.py`` executes the reference's OWN source files
+      (posteriormodel.py, optimizers/optimizer.py, optimizers/bayesbybackprop.py, loaded
+      unmodified from /root/reference) on top of a NumPy stand-in for the handful of TF leaf
+      ops they call; the committed outputs pin the reference's control flow (RNG consumption
+      order, var-used-as-std, fp32 running sum, /float(n), softplus(rho) ...).
+  (2) the two saved posteriors under Tutorials/PosteriorModels pin real inputs (mu, sigma,
+      architecture).
+The third-party arithmetic itself (TensorFlow's Eigen matmul rounding, tf.random.normal's
+bit stream) is NOT pinned by anything the reference holds: **parity unpinned** for those,
+as DESIGN.md says.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Layer descriptors (mirror of the Keras Sequential pieces the reference touches, a12)
+# --------------------------------------------------------------------------------------
+
+
+class Dense:
+    """Keras Dense: y = act(x @ W + b) on the last axis (posteriormodel.py:98 via model())."""
+
+    def __init__(self, fan_in: int, units: int, activation: str = "linear"):
+        self.kind = "dense"
+        self.fan_in, self.units, self.activation = int(fan_in), int(units), activation
+
+    def weight_shapes(self):
+        return [(self.fan_in, self.units), (self.units,)]
+
+
+class Conv2D:
+    """Keras Conv2D, NHWC activations / HWIO kernel (verifiers.py:11-21 uses
+    tf.nn.convolution, stride 1 VALID; strides / SAME are restated for completeness)."""
+
+    def __init__(self, kh, kw, cin, cout, activation="linear", strides=(1, 1), padding="valid"):
+        self.kind = "conv2d"
+        self.kh, self.kw, self.cin, self.cout = int(kh), int(kw), int(cin), int(cout)
+        self.activation = activation
+        self.strides = (int(strides[0]), int(strides[1]))
+        self.padding = padding.lower()
+
+    def weight_shapes(self):
+        return [(self.kh, self.kw, self.cin, self.cout), (self.cout,)]
+
+
+class MaxPool2D:
+    def __init__(self, pool=(2, 2), strides=None):
+        self.kind = "maxpool2d"
+        self.pool = (int(pool[0]), int(pool[1]))
+        self.strides = self.pool if strides is None else (int(strides[0]), int(strides[1]))
+
+    def weight_shapes(self):
+        return []
+
+
+class Flatten:
+    def __init__(self):
+        self.kind = "flatten"
+
+    def weight_shapes(self):
+        return []
+
+
+def mlp(dims: Sequence[int], hidden_act="relu", out_act="softmax") -> list:
+    """784-512-512-10 style MLP as used by BASELINE.json configs 1/2/3/5."""
+    layers = []
+    for i in range(len(dims) - 1):
+        act = out_act if i == len(dims) - 2 else hidden_act
+        layers.append(Dense(dims[i], dims[i + 1], act))
+    return layers
+
+
+def cnn_cfg4() -> list:
+    """BASELINE config 4 architecture as fixed in SURVEY.md section 8(d)."""
+    return [
+        Conv2D(3, 3, 3, 32, "relu"),
+        Conv2D(3, 3, 32, 64, "relu"),
+        MaxPool2D((2, 2)),
+        Flatten(),
+        Dense(12544, 128, "relu"),
+        Dense(128, 10, "softmax"),
+    ]
+
+
+def weight_shapes(layers) -> list:
+    out = []
+    for l in layers:
+        out.extend(l.weight_shapes())
+    return out
+
+
+def param_count(layers) -> int:
+    return int(sum(int(np.prod(s)) for s in weight_shapes(layers)))
+
+
+def flops_per_forward(layers, input_shape=None) -> int:
+    """Algorithmic FLOPs of one (sample x input row) forward, SURVEY.md 8(d)."""
+    f = 0
+    shape = tuple(input_shape) if input_shape is not None else None
+    for l in layers:
+        if l.kind == "dense":
+            f += 2 * l.fan_in * l.units
+            shape = (l.units,)
+        elif l.kind == "conv2d":
+            ho, wo = _conv_out_hw(shape[0], shape[1], l)
+            f += 2 * l.kh * l.kw * l.cin * l.cout * ho * wo
+            shape = (ho, wo, l.cout)
+        elif l.kind == "maxpool2d":
+            shape = ((shape[0] - l.pool[0]) // l.strides[0] + 1, (shape[1] - l.pool[1]) // l.strides[1] + 1, shape[2])
+        elif l.kind == "flatten":
+            shape = (int(np.prod(shape)),)
+    return int(f)
+
+
+# --------------------------------------------------------------------------------------
+# Leaf arithmetic (third-party ops restated: a12, a13)
+# --------------------------------------------------------------------------------------
+
+_SOFTPLUS_THR = np.float32(np.log(np.finfo(np.float32).eps) + 2.0)  # ~ -13.9424
+
+
+def softplus(x, dtype=np.float32):
+    """tf.math.softplus as called at bayesbybackprop.py:22-23,54,180,189.
+    TF's CPU functor: x if x > -thr; exp(x) if x < thr; else log1p(exp(x)); thr = ln(eps)+2."""
+    x = np.asarray(x, dtype=dtype)
+    thr = dtype(_SOFTPLUS_THR)
+    with np.errstate(over="ignore"):
+        ex = np.exp(x)
+        mid = np.log1p(ex)
+    return np.where(x > -thr, x, np.where(x < thr, ex, mid)).astype(dtype)
+
+
+def inverse_softplus(std, dtype=np.float32):
+    """rho = log(exp(std) - 1), bayesbybackprop.py:39-40 and optimizer.py:286."""
+    std = np.asarray(std, dtype=dtype)
+    return np.log(np.exp(std) - dtype(1)).astype(dtype)
+
+
+def _act(name: str, z: np.ndarray) -> np.ndarray:
+    if name in ("linear", None):
+        return z
+    if name == "relu":
+        return np.maximum(z, z.dtype.type(0))
+    if name == "tanh":
+        return np.tanh(z)
+    if name == "sigmoid":
+        return (1 / (1 + np.exp(-z))).astype(z.dtype)
+    if name == "softmax":
+        m = z.max(axis=-1, keepdims=True)
+        e = np.exp(z - m)
+        return (e / e.sum(axis=-1, keepdims=True)).astype(z.dtype)
+    raise ValueError("unknown activation %r" % (name,))
+
+
+def _conv_out_hw(h, w, l):
+    if l.padding == "same":
+        return -(-h // l.strides[0]), -(-w // l.strides[1])
+    return (h - l.kh) // l.strides[0] + 1, (w - l.kw) // l.strides[1] + 1
+
+
+def _conv2d(x, k, l):
+    """NHWC x HWIO -> NHWC, via im2col + matmul in x.dtype."""
+    n, h, w, c = x.shape
+    ho, wo = _conv_out_hw(h, w, l)
+    sh, sw = l.strides
+    if l.padding == "same":
+        ph = max((ho - 1) * sh + l.kh - h, 0)
+        pw = max((wo - 1) * sw + l.kw - w, 0)
+        x = np.pad(x, ((0, 0), (ph // 2, ph - ph // 2), (pw // 2, pw - pw // 2), (0, 0)))
+    cols = np.empty((n, ho, wo, l.kh, l.kw, c), dtype=x.dtype)
+    for i in range(l.kh):
+        for j in range(l.kw):
+            cols[:, :, :, i, j, :] = x[:, i:i + sh * ho:sh, j:j + sw * wo:sw, :]
+    y = cols.reshape(n * ho * wo, l.kh * l.kw * c) @ k.reshape(l.kh * l.kw * c, l.cout)
+    return y.reshape(n, ho, wo, l.cout)
+
+
+def _maxpool(x, l):
+    n, h, w, c = x.shape
+    ho = (h - l.pool[0]) // l.strides[0] + 1
+    wo = (w - l.pool[1]) // l.strides[1] + 1
+    out = np.full((n, ho, wo, c), -np.inf, dtype=x.dtype)
+    for i in range(l.pool[0]):
+        for j in range(l.pool[1]):
+            out = np.maximum(out, x[:, i:i + l.strides[0] * ho:l.strides[0], j:j + l.strides[1] * wo:l.strides[1], :])
+    return out
+
+
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even fp32 -> bf16 -> fp32 (what cvt.rn.bf16.f32 does)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    out = r.astype(np.uint32).view(np.float32)
+    return np.where(np.isnan(a), a, out).reshape(a.shape)
+
+
+def forward(layers, weights, x, dtype=np.float32, out="probs", bf16=False):
+    """One forward pass of the Keras Sequential with explicit weights (a12; call sites
+    posteriormodel.py:93,98,100,113; bayesbybackprop.py:65).  ``out='logits'`` stops before
+    the last activation (posteriormodel.py:128-134).  ``bf16=True`` emulates the GPU's bf16
+    mode: GEMM operands (weights and layer inputs) rounded to bf16, fp32 accumulation, fp32
+    bias / activation / softmax."""
+    h = np.asarray(x).astype(dtype)
+    wi = 0
+    nl = len(layers)
+    last_weighted = max(i for i, l in enumerate(layers) if l.kind in ("dense", "conv2d"))
+    for i, l in enumerate(layers):
+        if l.kind == "dense":
+            W = np.asarray(weights[wi]).astype(dtype)
+            b = np.asarray(weights[wi + 1]).astype(dtype)
+            wi += 2
+            if bf16:
+                z = bf16_round(h) @ bf16_round(W) + b
+            else:
+                z = h @ W + b
+        elif l.kind == "conv2d":
+            W = np.asarray(weights[wi]).astype(dtype)
+            b = np.asarray(weights[wi + 1]).astype(dtype)
+            wi += 2
+            if bf16:
+                z = _conv2d(bf16_round(h), bf16_round(W), l) + b
+            else:
+                z = _conv2d(h, W, l) + b
+        elif l.kind == "maxpool2d":
+            h = _maxpool(h, l)
+            continue
+        elif l.kind == "flatten":
+            h = h.reshape(h.shape[0], -1)
+            continue
+        else:
+            raise ValueError(l.kind)
+        if i == last_weighted and out == "logits":
+            return z
+        h = _act(l.activation, z)
+    return h
+
+
+# --------------------------------------------------------------------------------------
+# Sampling (a2, a6, a8, a9)
+# --------------------------------------------------------------------------------------
+
+
+def sample_gaussian(mean, std, eps, inflate=1.0, order="f64"):
+    """W = mean + (inflate*std) * eps with eps injected.
+    posteriormodel.py:74-75 / optimizer.py:200-201: ``np.random.normal(loc=mean_i,
+    scale=inflate*var_i)`` -- the stored ``var`` array is used AS A STANDARD DEVIATION and the
+    draw is formed in float64 then cast to fp32 by set_weights (order='f64').
+    bayesbybackprop.py:52-56 forms it entirely in fp32 (order='f32')."""
+    out = []
+    for m, s, e in zip(mean, std, eps):
+        if order == "f64":
+            w = np.asarray(m, np.float64) + (np.float64(inflate) * np.asarray(s, np.float64)) * np.asarray(e, np.float64)
+        else:
+            w = np.asarray(m, np.float32) + (np.float32(inflate) * np.asarray(s, np.float32)) * np.asarray(e, np.float32)
+        out.append(w.astype(np.float32))
+    return out
+
+
+def sample_reference_rng(mean, std, inflate=1.0):
+    """Exactly what the reference executes (global NumPy RNG, tensor order W0,b0,W1,b1,...):
+    posteriormodel.py:70-75."""
+    return [np.random.normal(loc=mean[i], scale=inflate * std[i]) for i in range(len(mean))]
+
+
+def draw_stored_index(freq):
+    """posteriormodel.py:77: np.random.choice(range(S), p=frequency)."""
+    return int(np.random.choice(range(len(freq)), p=freq))
+
+
+# --------------------------------------------------------------------------------------
+# predict / predict_logits (a3, a4)
+# --------------------------------------------------------------------------------------
+
+
+def predict(layers, mean, std, x, n, eps=None, inflate=1.0, out="probs", bf16=False, order="f64"):
+    """PosteriorModel.predict (posteriormodel.py:81-101) / predict_logits (:114-139):
+    fp32 running sum over samples in sample order, then ``/ float(n)``.
+    ``eps``: list (len n) of per-tensor arrays; None -> reference RNG (np.random.normal)."""
+    acc = None
+    for s in range(n):
+        if eps is None:
+            w = [np.asarray(t, np.float32) for t in sample_reference_rng(mean, std, inflate)]
+        else:
+            w = sample_gaussian(mean, std, eps[s], inflate, order)
+        y = forward(layers, w, x, np.float32, out, bf16)
+        acc = y if acc is None else acc + y  # posteriormodel.py:97-100
+    return (acc / np.float32(float(n))).astype(np.float32)  # :101
+
+
+def predict_moments(layers, mean, std, x, n, eps, inflate=1.0, bf16=False, order="f64"):
+    """Sum p and sum p^2 over samples (uncertainty.py:15-36 consumes per-sample predictions;
+    the GPU epilogue emits the two running sums instead of the [n,B,C] stack)."""
+    s1 = s2 = None
+    for s in range(n):
+        w = sample_gaussian(mean, std, eps[s], inflate, order)
+        y = forward(layers, w, x, np.float32, "probs", bf16)
+        s1 = y if s1 is None else s1 + y
+        s2 = y * y if s2 is None else s2 + y * y
+    return s1, s2
+
+
+def variational_uncertainty(per_sample_preds):
+    """uncertainty.py:33-35."""
+    p_hat = np.asarray(per_sample_preds)
+    epistemic = np.mean(p_hat ** 2, axis=0) - np.mean(p_hat, axis=0) ** 2
+    aleatoric = np.mean(p_hat * (1 - p_hat), axis=0)
+    return epistemic, aleatoric
+
+
+def predict_stored(layers, samples, x, idx, weights=None, out="probs", bf16=False):
+    """Sample-based posterior (HMC/SGHMC store, hmc.py:308-322).  ``idx`` = the stored-sample
+    indices visited in order (posteriormodel.py:77-78 draws them with replacement ~ freq);
+    ``weights`` = per-visit weights (1 for the MC loop; freq_i for the deterministic
+    expectation sum_i freq_i f(W_i) used by probverification.py:619-650).  Returns the SUM."""
+    acc = None
+    for j, i in enumerate(idx):
+        y = forward(layers, samples[i], x, np.float32, out, bf16)
+        if weights is not None:
+            y = y * np.float32(weights[j])
+        acc = y if acc is None else acc + y
+    return acc
+
+
+def normalise_freq(freq):
+    """posteriormodel.py:52-54."""
+    freq = np.asarray(freq, dtype=np.float64)
+    return freq / np.sum(freq)
+
+
+# --------------------------------------------------------------------------------------
+# Bayes-by-Backprop (a7, a8, a9, a10)
+# --------------------------------------------------------------------------------------
+
+
+def bbb_forward(layers, mean, rho, eps, x, bf16=False):
+    """bayesbybackprop.py:50-65: w = mean + softplus(rho) * noise (fp32), forward.
+    Returns (predictions, sampled_weights)."""
+    w = []
+    for m, r, e in zip(mean, rho, eps):
+        w.append((np.asarray(m, np.float32) + softplus(r) * np.asarray(e, np.float32)).astype(np.float32))
+    return forward(layers, w, x, np.float32, "probs", bf16), w
+
+
+def implicit_prior(layers, inflate_prior=1.0):
+    """optimizer.py:204-228: zero mean, std = sqrt(inflate_prior / fan_in), fan_in =
+    prod(shape[:-1]) for conv kernels, bias gets its kernel's std."""
+    mean, var = [], []
+    for l in layers:
+        shp = l.weight_shapes()
+        if not shp:
+            continue
+        sha, b_sha = shp
+        nin = int(np.prod(sha[:-1])) if len(sha) > 2 else sha[0]
+        std = math.sqrt(inflate_prior / nin)
+        mean += [np.zeros(sha, np.float32), np.zeros(b_sha, np.float32)]
+        var += [np.ones(sha, np.float32) * np.float32(std), np.ones(b_sha, np.float32) * np.float32(std)]
+    return mean, var
+
+
+def prior_generator(layers, means, vars_, inflate_prior=1.0):
+    """optimizer.py:230-257."""
+    if type(means) == int and type(vars_) == int and (means < 0 or vars_ < 0):
+        return implicit_prior(layers, inflate_prior)
+    shapes = weight_shapes(layers)
+    if type(means) in (int, float):
+        means = [0.0 if means == -1 else means] * len(shapes)
+    if type(vars_) in (int, float):
+        vars_ = [0.0 if vars_ == -1 else vars_] * len(shapes)
+    m, v = [], []
+    for i, s in enumerate(shapes):
+        pi = i // 2  # optimizer.py:251 floor(index/2)
+        m.append(np.ones(s, np.float32) * np.float32(means[pi]))
+        v.append(np.ones(s, np.float32) * np.float32(vars_[pi]))
+    return m, v
+
+
+# --------------------------------------------------------------------------------------
+# Statistical verification outer loop (a15)
+# --------------------------------------------------------------------------------------
+
+
+def okamoto_bound(epsilon, delta):
+    """verifiers.py:517-518."""
+    return (-1 * .5) * math.log(float(delta) / 2) * (1.0 / (epsilon ** 2))
+
+
+def chernoff_n(confidence=0.95, delta=0.3):
+    """verifiers.py:542-543 / :579-580."""
+    epsilon = 1 - confidence
+    return math.ceil((1 / (2 * epsilon ** 2)) * math.log(2 / delta))
+
+
+def absolute_massart_halting(succ, trials, I, epsilon, delta, alpha):
+    """verifiers.py:521-532."""
+    if I[0] < 0.5 and I[1] > 0.5:
+        return -1
+    elif I[1] < 0.5:
+        val = I[1]
+        h = (9 / 2.0) * (((3 * val + epsilon) * (3 * (1 - val) - epsilon)) ** (-1))
+        return math.ceil((h * (epsilon ** 2)) ** (-1) * math.log((delta - alpha) ** (-1)))
+    elif I[0] >= 0.5:
+        val = I[0]
+        h = (9 / 2.0) * (((3 * (1 - val) + epsilon) * ((3 * val) + epsilon)) ** (-1))
+        return math.ceil((h * (epsilon ** 2)) ** (-1) * math.log((delta - alpha) ** (-1)))
+
+
+def clopper_pearson(successes, trials, alpha=0.05):
+    """statsmodels.stats.proportion.proportion_confint(method='beta') as called at
+    verifiers.py:636 (third-party, restated from its published definition), with the NaN
+    handling of verifiers.py:637-640."""
+    from scipy.stats import beta
+
+    lb = beta.ppf(alpha / 2, successes, trials - successes + 1)
+    ub = beta.ppf(1 - alpha / 2, successes + 1, trials - successes)
+    lb = 0.0 if math.isnan(lb) else float(lb)
+    ub = 1.0 if math.isnan(ub) else float(ub)
+    return lb, ub
+
+
+def count_predicate(layers, mean, std, x, labels, n, eps, inflate=1.0, bf16=False, order="f64"):
+    """BASELINE config 5 restated: per posterior sample, forward the K fixed (pre-perturbed)
+    inputs and apply the tutorial predicate ``argmax == TRUE_VALUE`` (verifiers.py:628-634
+    with the notebook's predicate); returns flags [n,K] uint8 and counts [K]."""
+    K = np.asarray(x).shape[0]
+    flags = np.zeros((n, K), np.uint8)
+    for s in range(n):
+        w = sample_gaussian(mean, std, eps[s], inflate, order)
+        z = forward(layers, w, x, np.float32, "logits", bf16).reshape(K, -1)
+        flags[s] = (np.argmax(z, axis=-1) == np.asarray(labels).reshape(K)).astype(np.uint8)
+    return flags, flags.sum(axis=0).astype(np.int64)
+
+
+def massart_loop(flags_1d, confidence=0.95, delta=0.3, alpha=0.05):
+    """The sequential halting logic of massart_bound_check (verifiers.py:578-653) applied to
+    a pre-computed 0/1 success sequence (one entry per posterior sample, in order).
+    Returns (successes/iterations, iterations)."""
+    epsilon = 1 - confidence
+    chernoff_bound = chernoff_n(confidence, delta)
+    successes, iterations = 0.0, 0.0
+    halting_bound = chernoff_bound
+    while iterations <= halting_bound:
+        successes += float(flags_1d[int(iterations)])
+        iterations += 1
+        lb, ub = clopper_pearson(successes, iterations)
+        hb = absolute_massart_halting(successes, iterations, [lb, ub], epsilon, delta, alpha)
+        halting_bound = chernoff_bound if hb == -1 else min(hb, chernoff_bound)
+    return successes / iterations, iterations
+
+
+# --------------------------------------------------------------------------------------
+# Philox4x32-10 counter RNG (the product's in-kernel generator, restated for bit checks)
+# --------------------------------------------------------------------------------------
+
+_PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PH_W0, _PH_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., SC'11) on arrays: ctr [..,4] uint32, key [..,2] uint32."""
+    c = [np.asarray(ctr[..., i], np.uint32).copy() for i in range(4)]
+    k0 = np.asarray(key[..., 0], np.uint32).copy()
+    k1 = np.asarray(key[..., 1], np.uint32).copy()
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = _PH_M0 * c[0].astype(np.uint64)
+            p1 = _PH_M1 * c[2].astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+            c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+            k0 = (k0 + _PH_W0).astype(np.uint32)
+            k1 = (k1 + _PH_W1).astype(np.uint32)
+    return np.stack(c, axis=-1)
+
+
+def philox_normals(seed: int, sample: int, P: int) -> np.ndarray:
+    """The eps stream the CUDA library generates for posterior sample ``sample``:
+    element j (flat Keras order over all tensors) comes from Philox block j//4, lane j%4;
+    counter = (j//4 lo, j//4 hi, sample lo, sample hi), key = (seed lo, seed hi);
+    lanes (0,1) and (2,3) feed one Box-Muller each:
+      u1 = (r_a + 1) * 2^-32 in (0,1], u2 = r_b * 2^-32 in [0,1),
+      z_a = sqrt(-2 ln u1) cos(2 pi (u2-1/2)), z_b = sqrt(-2 ln u1) sin(2 pi (u2-1/2))
+    (angle kept in [-pi, pi) where the GPU's fast sincos is most accurate)."""
+    nb = (P + 3) // 4
+    blk = np.arange(nb, dtype=np.uint64)
+    ctr = np.stack([
+        (blk & np.uint64(0xFFFFFFFF)).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
+        np.full(nb, sample & 0xFFFFFFFF, np.uint32), np.full(nb, (sample >> 32) & 0xFFFFFFFF, np.uint32)], axis=-1)
+    key = np.stack([np.full(nb, seed & 0xFFFFFFFF, np.uint32), np.full(nb, (seed >> 32) & 0xFFFFFFFF, np.uint32)], axis=-1)
+    r = philox4x32_10(ctr, key).astype(np.float64)
+    z = np.empty((nb, 4), np.float64)
+    for a, b in ((0, 1), (2, 3)):
+        u1 = (r[:, a] + 1.0) * 2.0 ** -32
+        u2 = r[:, b] * 2.0 ** -32
+        rad = np.sqrt(-2.0 * np.log(u1))
+        z[:, a] = rad * np.cos(2 * np.pi * (u2 - 0.5))
+        z[:, b] = rad * np.sin(2 * np.pi * (u2 - 0.5))
+    return z.reshape(-1)[:P].astype(np.float32)
+
+
+def philox_raw(seed: int, sample: int, P: int) -> np.ndarray:
+    """Raw uint32 outputs matching philox_normals' blocks (bit-exact check of the kernel)."""
+    nb = (P + 3) // 4
+    blk = np.arange(nb, dtype=np.uint64)
+    ctr = np.stack([
+        (blk & np.uint64(0xFFFFFFFF)).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
+        np.full(nb, sample & 0xFFFFFFFF, np.uint32), np.full(nb, (sample >> 32) & 0xFFFFFFFF, np.uint32)], axis=-1)
+    key = np.stack([np.full(nb, seed & 0xFFFFFFFF, np.uint32), np.full(nb, (seed >> 32) & 0xFFFFFFFF, np.uint32)], axis=-1)
+    return philox4x32_10(ctr, key).reshape(-1)[:P]
+
+
+# --------------------------------------------------------------------------------------
+# Helpers shared by tests / bench (synthetic inputs of SURVEY.md 8(d))
+# --------------------------------------------------------------------------------------
+
+
+def split_flat(layers, flat):
+    out, o = [], 0
+    for s in weight_shapes(layers):
+        k = int(np.prod(s))
+        out.append(np.asarray(flat[o:o + k]).reshape(s))
+        o += k
+    return out
+
+
+def flatten_list(tensors):
+    return np.concatenate([np.asarray(t, np.float32).reshape(-1) for t in tensors])
+
+
+def synthetic_posterior(layers, seed=1, sigma_scale=0.1):
+    """mu ~ N(0, 1/fan_in) (biases too), sigma = sigma_scale/sqrt(fan_in) per layer."""
+    g = np.random.Generator(np.random.Philox(seed))
+    mean, std = [], []
+    for l in layers:
+        shp = l.weight_shapes()
+        if not shp:
+            continue
+        fan_in = int(np.prod(shp[0][:-1]))
+        for s in shp:
+            mean.append((g.standard_normal(s) / math.sqrt(fan_in)).astype(np.float32))
+            std.append(np.full(s, sigma_scale / math.sqrt(fan_in), np.float32))
+    return mean, std
+
+
+def synthetic_eps(layers, n, seed=2):
+    g = np.random.Generator(np.random.Philox(seed))
+    return [[g.standard_normal(s).astype(np.float32) for s in weight_shapes(layers)] for _ in range(n)]
+
+
+def synthetic_x(shape, seed=0):
+    g = np.random.Generator(np.random.Philox(seed))
+    return g.random(shape, dtype=np.float32)

@@ -1,0 +1,368 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (deepbayes_b200.engine.Engine is
+a thin ctypes shim), against the CPU oracle on identical seeded inputs with the oracle's eps
+tensors injected, and against the committed golden outputs.
+
+Tolerances (BASELINE.json north_star): fp32 mode <= 1e-5 relative; bf16 mode <= 2e-2 absolute
+on predictive probabilities; argmax of the predictive mean identical."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+FP32_RTOL, FP32_ATOL = 1e-5, 2e-7
+BF16_ATOL = 2e-2
+
+
+def _model_for(name, c):
+    import deepbayes_b200 as db
+    L = c["layers"]
+    layers = []
+    first = True
+    for l in L:
+        kw = {"input_shape": c["in_shape"]} if first else {}
+        if l.kind == "dense":
+            layers.append(db.Dense(l.units, activation=l.activation, **kw))
+        elif l.kind == "conv2d":
+            layers.append(db.Conv2D(l.cout, (l.kh, l.kw), l.strides, l.padding, l.activation, **kw))
+        elif l.kind == "maxpool2d":
+            layers.append(db.MaxPooling2D(l.pool, l.strides))
+        else:
+            layers.append(db.Flatten())
+        first = False
+    return db.Sequential(layers)
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "oracle_cases.npz"))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            from deepbayes_b200.engine import Engine
+            c = cases.case_inputs(name)
+            m = _model_for(name, c)
+            eng = Engine(m)
+            eng.set_gaussian(c["mean"], c["std"])
+            from oracle import oracle as o
+            c["eps_flat"] = np.stack([o.flatten_list(e) for e in c["eps"]])
+            cache[name] = (c, m, eng)
+        return cache[name]
+    return get
+
+
+def test_native_library_is_loaded():
+    from deepbayes_b200 import _lib
+    _lib.load()
+    assert any("libdeepbayes_b200.so" in l for l in open("/proc/self/maps").read().splitlines())
+
+
+def test_philox_bit_exact_and_normals(oracle):
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    m = db.Sequential([db.Dense(7, activation="relu", input_shape=(13,)), db.Dense(3, activation="softmax")])
+    eng = Engine(m)
+    for seed, s in ((0, 0), (12345678901234, 7), (2 ** 63 + 5, 2 ** 33 + 1)):
+        got = eng.philox_raw(seed, s, 1001)
+        np.testing.assert_array_equal(got, oracle.philox_raw(seed, s, 1001))
+    P = eng.P
+    eng.set_gaussian([np.zeros(s, np.float32) for s in m.weight_shapes()], [np.ones(s, np.float32) for s in m.weight_shapes()])
+    W = eng.sample(3, seed=99, s0=5).cpu().numpy()  # mu=0, sigma=1 -> W is the eps stream itself
+    for i in range(3):
+        np.testing.assert_allclose(W[i], oracle.philox_normals(99, 5 + i, P), rtol=0, atol=5e-6)
+    # same global sample id -> same draw, independent of the call split
+    np.testing.assert_array_equal(eng.sample(1, seed=99, s0=6).cpu().numpy()[0], W[1])
+
+
+def test_philox_statistics(oracle):
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    m = db.Sequential([db.Dense(512, activation="relu", input_shape=(784,)), db.Dense(10, activation="softmax")])
+    eng = Engine(m)
+    eng.set_gaussian([np.zeros(s, np.float32) for s in m.weight_shapes()], [np.ones(s, np.float32) for s in m.weight_shapes()])
+    z = eng.sample(8, seed=3, s0=0).cpu().numpy().astype(np.float64).reshape(-1)
+    assert abs(z.mean()) < 2e-3 and abs(z.std() - 1) < 2e-3
+    assert abs((z ** 3).mean()) < 1e-2 and abs((z ** 4).mean() - 3) < 2e-2
+    assert np.abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 2e-3
+
+
+@pytest.mark.parametrize("name", cases.NAMES)
+def test_sample_matches_oracle(ctx, golden, oracle, name):
+    c, m, eng = ctx(name)
+    W = eng.sample(c["n"], eps=c["eps_flat"]).cpu().numpy()
+    want = np.stack([oracle.flatten_list(oracle.sample_gaussian(c["mean"], c["std"], e)) for e in c["eps"]])
+    # fmaf(sigma, eps, mu) vs the reference's float64 form then fp32 cast: <= 1 ulp (double rounding)
+    np.testing.assert_allclose(W, want, rtol=1.2e-7, atol=1e-12)
+    assert (W == want).mean() > 0.999
+    np.testing.assert_allclose(W[:, ::cases.w_stride(c["layers"])], golden[name + "/sample_w"], rtol=1.2e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", cases.NAMES)
+def test_predict_fp32(ctx, golden, oracle, name):
+    c, m, eng = ctx(name)
+    n = c["n"]
+    s1, s2 = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="fp32", second_moment=True)
+    got = (s1 / float(n)).cpu().numpy()
+    want = oracle.predict(c["layers"], c["mean"], c["std"], c["x"], n, c["eps"])
+    np.testing.assert_allclose(got, want, rtol=FP32_RTOL, atol=FP32_ATOL)
+    np.testing.assert_allclose(got, golden[name + "/predict_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
+    np.testing.assert_allclose(s1.cpu().numpy(), golden[name + "/sum1_fp32"], rtol=FP32_RTOL, atol=n * FP32_ATOL)
+    np.testing.assert_allclose(s2.cpu().numpy(), golden[name + "/sum2_fp32"], rtol=2 * FP32_RTOL, atol=n * FP32_ATOL)
+    assert eng.last_path() == "generic"
+    lg, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="fp32", out_kind="logits")
+    np.testing.assert_allclose((lg / float(n)).cpu().numpy(), golden[name + "/predict_logits_fp32"], rtol=FP32_RTOL, atol=2e-6)
+    inf, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="fp32", inflate=2.0)
+    np.testing.assert_allclose((inf / float(n)).cpu().numpy(), golden[name + "/predict_inflate2_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
+
+
+@pytest.mark.parametrize("name", cases.NAMES)
+@pytest.mark.parametrize("fused", [True, False])
+def test_predict_bf16(ctx, golden, oracle, name, fused, monkeypatch):
+    c, m, eng = ctx(name)
+    monkeypatch.setenv("DBX_NO_FUSED", "0" if fused else "1")
+    n = c["n"]
+    s1, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="bf16")
+    got = (s1 / float(n)).cpu().numpy()
+    want_bf = golden[name + "/predict_bf16"]   # oracle with bf16-rounded GEMM operands
+    want_32 = golden[name + "/predict_fp32"]
+    assert np.abs(got - want_32).max() <= BF16_ATOL
+    # against the bf16-emulating oracle only accumulation order differs
+    np.testing.assert_allclose(got, want_bf, rtol=0, atol=2e-3)
+    if c["layers"][-1].activation == "softmax":
+        margin = np.sort(want_32, axis=-1)
+        clear = (margin[:, -1] - margin[:, -2]) > 2 * BF16_ATOL
+        assert (got.argmax(-1) == want_32.argmax(-1))[clear].all()
+        assert (got.argmax(-1) == want_bf.argmax(-1)).all(), "argmax differs from the bf16 oracle"
+
+
+@pytest.mark.parametrize("name", ["mlp_small", "mlp_cfg2", "cnn_small"])
+def test_stored_posterior(ctx, golden, oracle, name):
+    c, m, eng = ctx(name)
+    n = c["n"]
+    samples = [oracle.sample_gaussian(c["mean"], c["std"], e) for e in c["eps"]]
+    slab = np.stack([oracle.flatten_list(s) for s in samples])
+    eng.set_samples(slab)
+    freq = oracle.normalise_freq(np.arange(1, n + 1)).astype(np.float32)
+    s1, _ = eng.predict_stored_sums(c["x"], n, j0=0, wts=freq, mode="fp32")
+    np.testing.assert_allclose(s1.cpu().numpy(), golden[name + "/stored_expect_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
+    idx = [(3 * j + 1) % n for j in range(2 * n)]
+    s1, _ = eng.predict_stored_sums(c["x"], len(idx), idx=idx, mode="fp32")
+    np.testing.assert_allclose((s1 / float(len(idx))).cpu().numpy(), golden[name + "/stored_mc_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
+    s1b, _ = eng.predict_stored_sums(c["x"], len(idx), idx=idx, mode="bf16")
+    assert np.abs((s1b / float(len(idx))).cpu().numpy() - golden[name + "/stored_mc_fp32"]).max() <= BF16_ATOL
+    # range check: asking past the slab fails loudly
+    from deepbayes_b200._lib import DbxError
+    with pytest.raises(DbxError):
+        eng.predict_stored_sums(c["x"], n + 1, j0=0, mode="fp32")
+
+
+@pytest.mark.parametrize("name", ["mlp_small", "mlp_cfg1", "cnn_small"])
+def test_bbb_forward(ctx, golden, oracle, name):
+    c, m, eng = ctx(name)
+    rho = [oracle.inverse_softplus(s) for s in c["std"]]
+    eng.set_gaussian(c["mean"], rho, rho=True)
+    try:
+        out, W, noise = eng.bbb_forward(c["x"], eps=c["eps_flat"][0], mode="fp32", return_weights=True)
+        want, w = oracle.bbb_forward(c["layers"], c["mean"], rho, c["eps"][0], c["x"])
+        # W = mean + softplus(rho)*eps formed in fp32 in the reference's order: device softplus vs numpy <= 2 ulp
+        np.testing.assert_allclose(W.cpu().numpy(), oracle.flatten_list(w), rtol=3e-7, atol=1e-9)
+        np.testing.assert_array_equal(noise.cpu().numpy(), c["eps_flat"][0])
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=FP32_RTOL, atol=FP32_ATOL)
+        np.testing.assert_allclose(out.cpu().numpy(), golden[name + "/bbb_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
+        out2 = eng.bbb_forward(c["x"], eps=c["eps_flat"][0], mode="fp32")
+        np.testing.assert_allclose(out2.cpu().numpy(), out.cpu().numpy(), rtol=1e-6, atol=1e-7)
+        mu, sg = eng.get_gaussian()
+        np.testing.assert_allclose(sg, oracle.flatten_list([oracle.softplus(r) for r in rho]), rtol=3e-7)
+    finally:
+        eng.set_gaussian(c["mean"], c["std"])
+
+
+@pytest.mark.parametrize("name", ["mlp_small", "mlp_cfg2", "cnn_small"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_count_predicate(ctx, golden, oracle, name, mode):
+    c, m, eng = ctx(name)
+    counts, flags = eng.count_predicate(c["x"], c["labels"], c["n"], eps=c["eps_flat"], mode=mode, return_flags=True)
+    flags, counts = flags.cpu().numpy(), counts.cpu().numpy()
+    np.testing.assert_array_equal(counts, flags.sum(0))
+    if mode == "fp32":
+        want_flags = golden[name + "/flags"]
+    else:
+        want_flags, _ = oracle.count_predicate(c["layers"], c["mean"], c["std"], c["x"], c["labels"], c["n"], c["eps"], bf16=True)
+    # bit-exact except where the top-2 logits are within rounding of each other
+    assert (flags != want_flags).mean() <= (0.0 if mode == "fp32" else 0.02)
+
+
+def test_edge_cases(oracle):
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    from deepbayes_b200._lib import DbxError
+    m = db.Sequential([db.Dense(3, activation="softmax", input_shape=(5,))])
+    eng = Engine(m)
+    with pytest.raises(DbxError):  # posterior not set
+        eng.predict_sums(np.zeros((1, 5), np.float32), 1, mode="fp32")
+    L = oracle.mlp([5, 3])
+    mean, std = oracle.synthetic_posterior(L, seed=1)
+    eng.set_gaussian(mean, std)
+    with pytest.raises(ValueError):
+        eng.set_gaussian(mean[:1], std[:1])
+    # B = 1, n = 1, single layer
+    x = oracle.synthetic_x((1, 5), seed=2)
+    eps = oracle.synthetic_eps(L, 1, seed=3)
+    s1, _ = eng.predict_sums(x, 1, eps=oracle.flatten_list(eps[0])[None], mode="fp32")
+    np.testing.assert_allclose(s1.cpu().numpy(), oracle.predict(L, mean, std, x, 1, eps), rtol=FP32_RTOL, atol=FP32_ATOL)
+    # sigma = 0 -> every sample equals the deterministic forward, for any seed
+    eng.set_gaussian(mean, [np.zeros_like(s) for s in std])
+    s1, s2 = eng.predict_sums(x, 9, seed=77, mode="fp32", second_moment=True)
+    det = oracle.forward(L, mean, x)
+    np.testing.assert_allclose((s1 / 9.0).cpu().numpy(), det, rtol=FP32_RTOL, atol=FP32_ATOL)
+    np.testing.assert_allclose((s2 / 9.0).cpu().numpy(), det ** 2, rtol=3e-5, atol=FP32_ATOL)
+    with pytest.raises(DbxError):
+        eng.predict_sums(x, 0, mode="fp32")
+
+
+def test_sample_split_independence(ctx):
+    """Global sample ids: n samples in one call == the same ids split over two calls (this is
+    what makes the multi-GPU shard sum independent of G)."""
+    c, m, eng = ctx("mlp_cfg1")
+    for mode, tol in (("fp32", 1e-6), ("bf16", 1e-6)):
+        a, _ = eng.predict_sums(c["x"], 10, seed=5, s0=100, mode=mode)
+        b1, _ = eng.predict_sums(c["x"], 4, seed=5, s0=100, mode=mode)
+        b2, _ = eng.predict_sums(c["x"], 6, seed=5, s0=104, mode=mode)
+        np.testing.assert_allclose(a.cpu().numpy(), (b1 + b2).cpu().numpy(), rtol=1e-5, atol=tol)
+    cnt = eng.count_predicate(c["x"], c["labels"], 64, seed=5, s0=0, mode="bf16").cpu().numpy()
+    c1 = eng.count_predicate(c["x"], c["labels"], 24, seed=5, s0=0, mode="bf16").cpu().numpy()
+    c2 = eng.count_predicate(c["x"], c["labels"], 40, seed=5, s0=24, mode="bf16").cpu().numpy()
+    np.testing.assert_array_equal(cnt, c1 + c2)
+
+
+def test_mc_converges_to_oracle_mc(ctx, oracle):
+    """Philox path (no injected eps): the MC mean over many samples agrees with the oracle's
+    MC mean over its own RNG to within the Monte-Carlo standard error."""
+    c, m, eng = ctx("mlp_small")
+    n = 4096
+    s1, s2 = eng.predict_sums(c["x"], n, seed=11, mode="fp32", second_moment=True)
+    mean = (s1 / n).cpu().numpy()
+    var = np.maximum((s2 / n).cpu().numpy() - mean ** 2, 0)
+    eps = oracle.synthetic_eps(c["layers"], 512, seed=99)
+    ref = oracle.predict(c["layers"], c["mean"], c["std"], c["x"], 512, eps)
+    se = np.sqrt(var / n + var / 512) + 1e-4
+    assert (np.abs(mean - ref) < 6 * se).all()
+
+
+def test_posterior_model_api(golden_dir, oracle):
+    """Drop-in surface on the reference's own saved posterior (loaded from its TF pickles)."""
+    import deepbayes_b200 as db
+    p = os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior")
+    L = oracle.mlp([784, 128, 10])
+    x = oracle.synthetic_x((6, 1, 784), seed=0).astype(np.float64)  # tutorials pass float64 (B,1,784)
+    np.random.seed(0)
+    pm = db.PosteriorModel(p, mode="fp32")
+    assert pm.det is False and pm.sample_based is False and pm.input_upper == np.inf
+    out = pm.predict(x, n=35)
+    assert out.shape == (6, 1, 10) and out.dtype == np.float32
+    det = oracle.forward(L, pm.posterior_mean, x.reshape(6, 784)).reshape(6, 1, 10)
+    assert np.abs(out - det).max() < 2e-3 and np.allclose(out.sum(-1), 1, rtol=1e-5)
+    # predict leaves the model holding the last sample (posteriormodel.py:96); sample() does not touch it
+    w_after = pm.model.get_weights()
+    assert not np.array_equal(w_after[0], pm.posterior_mean[0])
+    assert np.abs(w_after[0] - pm.posterior_mean[0]).max() < 6 * pm.posterior_var[0].max()
+    s = pm.sample()
+    assert [a.shape for a in s] == [(784, 128), (128,), (128, 10), (10,)]
+    np.testing.assert_array_equal(pm.model.get_weights()[0], w_after[0])
+    np.testing.assert_allclose(pm._predict(x), oracle.forward(L, w_after, x.reshape(6, 784)).reshape(6, 1, 10), rtol=FP32_RTOL, atol=FP32_ATOL)
+    lg = pm.predict_logits(x, n=5)
+    assert lg.shape == (6, 1, 10) and np.abs(lg - oracle.forward(L, pm.posterior_mean, x.reshape(6, 784), out="logits").reshape(6, 1, 10)).max() < 0.05
+    wl = pm.model.get_weights()
+    nb = pm._predict_logits(x)  # reference bug kept: no bias
+    np.testing.assert_allclose(nb, oracle.forward(L, wl[:-1] + [np.zeros_like(wl[-1])], x.reshape(6, 784), out="logits").reshape(6, 1, 10), rtol=1e-5, atol=2e-6)
+    # deterministic mode short-circuits (posteriormodel.py:42-43,92-93)
+    pd = db.PosteriorModel(p, deterministic=True, mode="fp32")
+    np.testing.assert_allclose(pd.predict(x, n=50), det, rtol=FP32_RTOL, atol=FP32_ATOL)
+    np.testing.assert_array_equal(pd.sample()[0], pd.posterior_mean[0])
+    # bf16 default mode agrees within the stated tolerance, argmax identical
+    pb = db.PosteriorModel(p, seed=pm.seed)
+    ob = pb.predict(x, n=35)
+    assert np.abs(ob - out).max() < BF16_ATOL and (ob.argmax(-1) == out.argmax(-1)).all()
+    # analyzers on top
+    ep, al = db.analyzers.variational_uncertainty(pm, x, num_samples=64)
+    assert ep.shape == (6, 1, 10) and (ep > -1e-6).all() and (al > -1e-6).all()
+    assert len(db.analyzers.predictive_entropy(pm, x, num_models=8)) == 6
+
+
+def test_sample_based_posterior_model(tmp_path, oracle):
+    import deepbayes_b200 as db
+    L = oracle.mlp([20, 16, 4])
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=0.5)
+    m = db.Sequential([db.Dense(16, activation="relu", input_shape=(20,)), db.Dense(4, activation="softmax")])
+    hmc = db.optimizers.HamiltonianMonteCarlo().compile(m, None)
+    hmc.posterior_mean = mean
+    samples = [oracle.sample_gaussian(mean, std, e) for e in oracle.synthetic_eps(L, 6, seed=2)]
+    for i, s in enumerate(samples):
+        hmc.record(s, multiplicity=i + 1)
+    hmc.save(str(tmp_path / "hmc"))
+    pm = db.PosteriorModel(str(tmp_path / "hmc"), mode="fp32")
+    assert pm.sample_based and pm.num_post_samps == 6 and abs(pm.frequency.sum() - 1) < 1e-12
+    x = oracle.synthetic_x((5, 20), seed=3)
+    np.random.seed(42)
+    got = pm.predict(x, n=40)
+    np.random.seed(42)
+    idx = np.random.choice(6, size=40, p=pm.frequency)
+    want = oracle.predict_stored(L, samples, x, list(idx)) / np.float32(40.0)
+    np.testing.assert_allclose(got, want, rtol=FP32_RTOL, atol=FP32_ATOL)
+    np.testing.assert_array_equal(pm.model.get_weights()[0], samples[idx[-1]][0])
+
+
+def test_bbb_optimizer_api(oracle):
+    import deepbayes_b200 as db
+    L = oracle.mlp([30, 24, 10])
+    m = db.Sequential([db.Dense(24, activation="relu", input_shape=(30,)), db.Dense(10, activation="softmax")])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=16, seed=4)
+    x = oracle.synthetic_x((16, 30), seed=0)
+    eps = oracle.synthetic_eps(L, 1, seed=1)[0]
+    pred, ws, noise = opt.forward_sample(x, eps=eps, return_weights=True)
+    want, w = oracle.bbb_forward(L, opt.posterior_mean, opt.posterior_var, eps, x)
+    np.testing.assert_allclose(pred, want, rtol=FP32_RTOL, atol=FP32_ATOL)
+    for a, b in zip(ws, w):
+        np.testing.assert_allclose(a, b, rtol=3e-7, atol=1e-9)
+    np.testing.assert_array_equal(m.get_weights()[0], ws[0])         # step leaves the sample in the model (:59)
+    np.testing.assert_allclose(opt.predict(x), want, rtol=FP32_RTOL, atol=FP32_ATOL)  # single forward, no sampling (:293-298)
+    s = opt.sample()
+    sd = np.sqrt(1 / 30.0)
+    assert abs(np.std(s[0]) - sd) < 0.1 * sd                          # N(0, softplus(rho)) = N(0, prior std)
+    p2 = opt.forward_sample(x)                                        # Philox noise
+    assert p2.shape == (16, 10) and np.allclose(p2.sum(-1), 1, rtol=1e-5)
+
+
+def test_statistical_verification(ctx, oracle):
+    import deepbayes_b200 as db
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "posteriors", "VOGN_MNIST_Posterior")
+    pm = db.PosteriorModel(p, mode="fp32", seed=3)
+    x = oracle.synthetic_x((4, 784), seed=0)
+    cls = pm.predict(x, n=16).argmax(-1)
+    res = db.analyzers.statistical_robustness(pm, x, cls, return_flags=True)
+    assert res["n"] == 380 and res["flags"].shape == (380, 4)
+    assert (res["p"] > 0.9).all()
+    frac, iters, _ = db.analyzers.massart_bound_check(pm, x[:1], 0.0, cls=int(cls[0]), adv=x[:1])
+    flags = np.ones(1000, np.uint8)
+    want_frac, want_iters = oracle.massart_loop(flags)
+    if frac == 1.0:
+        assert iters == want_iters
+
+
+def test_predict_host_e2e(ctx, oracle):
+    c, m, eng = ctx("mlp_cfg1")
+    mean = eng.predict_host(c["x"], 8, seed=21, s0=0, mode="fp32")
+    s1, _ = eng.predict_sums(c["x"], 8, seed=21, s0=0, mode="fp32")
+    np.testing.assert_allclose(mean, (s1 / 8.0).cpu().numpy(), rtol=1e-6, atol=1e-7)
+    mean2, var2 = eng.predict_host(c["x"], 8, seed=21, s0=0, mode="bf16", variance=True)
+    assert np.abs(mean2 - mean).max() < BF16_ATOL and (var2 > -1e-6).all()

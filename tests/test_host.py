@@ -1,0 +1,134 @@
+"""CPU tests of the host-side mirror of the reference interface (no CUDA calls)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import deepbayes_b200 as db
+from deepbayes_b200 import _lib, formats, distributed as dd
+from deepbayes_b200.analyzers import verifiers
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 20 and set(names) == set(_lib._SIGS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.dbx_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = db.Sequential([db.Dense(4, activation="softmax", input_shape=(3,))])
+    with pytest.raises(_lib.DbxError):
+        m(np.zeros((2, 3), np.float32))
+
+
+def test_sequential_json_roundtrip_and_keras_arch(golden_dir):
+    m = db.Sequential([db.Conv2D(8, 3, activation="relu", input_shape=(14, 14, 3)), db.MaxPooling2D(2), db.Flatten(),
+                       db.Dense(10, activation="softmax")])
+    assert m.weight_shapes() == [(3, 3, 3, 8), (8,), (6 * 6 * 8, 10), (10,)]
+    m2 = db.model_from_json(m.to_json())
+    assert m2.weight_shapes() == m.weight_shapes() and [l.kind for l in m2.layers] == [l.kind for l in m.layers]
+    with open(os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior", "arch.json")) as f:
+        k = db.model_from_json(f.read())
+    assert k.input_shape == (1, 784) and k.feature_shape == (784,)
+    assert [l.activation.name for l in k.layers] == ["relu", "softmax"]
+    rows, oshape = k.rows_and_outshape(np.zeros((5, 1, 784)))
+    assert rows == 5 and oshape == (5, 1, 10)  # Appendix A.8
+    ws = k.get_weights()
+    k.set_weights([w + 1 for w in ws])
+    np.testing.assert_array_equal(k.layers[1].get_weights()[1], ws[3] + 1)
+    with pytest.raises(ValueError):
+        k.set_weights(ws[:-1])
+
+
+def test_compile_priors_match_oracle(oracle):
+    L = oracle.cnn_cfg4()
+    m = db.Sequential([db.Conv2D(32, 3, activation="relu", input_shape=(32, 32, 3)), db.Conv2D(64, 3, activation="relu"),
+                       db.MaxPooling2D(2), db.Flatten(), db.Dense(128, activation="relu"), db.Dense(10, activation="softmax")])
+    assert m.count_params() == 1626442
+    opt = db.optimizers.BayesByBackprop().compile(m, None, inflate_prior=2.0, epochs=10)
+    assert opt.epochs == 11  # linear_schedule default adds one epoch (optimizer.py:77-79)
+    pm, pv = oracle.implicit_prior(L, 2.0)
+    for a, b in zip(opt.prior_mean, pm):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(opt.prior_var, pv):
+        np.testing.assert_array_equal(a, b)
+    # posterior mean starts at the prior mean (zeros), rho = log(exp(std)-1)  (bayesbybackprop.py:39-40)
+    assert all((a == 0).all() for a in opt.posterior_mean)
+    for r, v in zip(opt.posterior_var, pv):
+        np.testing.assert_allclose(r, oracle.inverse_softplus(v), rtol=1e-6)
+    # explicit scalar priors: element floor(i/2) per tensor (optimizer.py:250-256)
+    opt2 = db.optimizers.StochasticGradientDescent().compile(m, None, prior_mean=0.5, prior_var=0.25)
+    om, ov = oracle.prior_generator(L, 0.5, 0.25)
+    for a, b in zip(opt2.prior_var, ov):
+        np.testing.assert_array_equal(a, b)
+    assert opt2.input_upper == math.inf and opt2.det is False and opt2.classes == 10
+
+
+def test_formats_roundtrip(tmp_path, oracle):
+    L = oracle.mlp([6, 5, 3])
+    mean, std = oracle.synthetic_posterior(L, seed=1)
+    m = db.Sequential([db.Dense(5, activation="relu", input_shape=(6,)), db.Dense(3, activation="softmax")])
+    p = str(tmp_path / "g")
+    formats.save_gaussian_posterior(p, m, mean, std, {"input_upper": 1.0, "input_lower": 0.0, "N": 7})
+    assert formats.is_gaussian_dir(p)
+    for a, b in zip(formats.load_tensor_list(p + "/mean.npy"), mean):
+        np.testing.assert_array_equal(a, b)
+    assert formats.load_info(p)["input_upper"] == 1.0
+    assert formats.load_arch(p).weight_shapes() == m.weight_shapes()
+    # HMC layout (hmc.py:308-322) + packed slab
+    samples = [oracle.sample_gaussian(mean, std, e) for e in oracle.synthetic_eps(L, 4, seed=2)]
+    q = str(tmp_path / "h")
+    formats.save_sample_posterior(q, m, mean, samples, [3, 1, 2, 2])
+    assert not formats.is_gaussian_dir(q) and formats.count_samples(q) == 4
+    slab = formats.load_slab(q, oracle.param_count(L))
+    np.testing.assert_array_equal(slab[2], oracle.flatten_list(samples[2]))
+    os.remove(q + "/slab.npy")
+    np.testing.assert_array_equal(formats.load_slab(q, oracle.param_count(L)), slab)
+    assert formats.load_info(q)["input_lower"] == -math.inf  # Appendix A.2
+
+
+def test_optimizer_save_formats(tmp_path, oracle):
+    m = db.Sequential([db.Dense(5, activation="relu", input_shape=(6,)), db.Dense(3, activation="softmax")])
+    bbb = db.optimizers.BayesByBackprop().compile(m, None)
+    bbb.save(str(tmp_path / "bbb"))
+    var = formats.load_tensor_list(str(tmp_path / "bbb" / "var.npy"))
+    np.testing.assert_allclose(var[0], math.sqrt(1 / 6), rtol=1e-5)  # softplus(rho) round-trips to the prior std
+    assert not os.path.exists(str(tmp_path / "bbb" / "info.pkl"))     # bayesbybackprop.py:184-195 writes none
+    sgd = db.optimizers.StochasticGradientDescent().compile(m, None)
+    sgd.save(str(tmp_path / "sgd"))
+    info = formats.load_info(str(tmp_path / "sgd"))
+    assert info["epochs"] == 11 and info["classes"] == 10 and "input_upper" in info
+    hmc = db.optimizers.HamiltonianMonteCarlo().compile(m, None)
+    for i in range(3):
+        hmc.record([w + i for w in m.get_weights()], multiplicity=i + 1)
+    hmc.save(str(tmp_path / "hmc"))
+    np.testing.assert_array_equal(np.load(str(tmp_path / "hmc" / "freq.npy")), [1, 2, 3])
+    assert formats.count_samples(str(tmp_path / "hmc")) == 3
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 1024, 100000):
+        for G in (1, 2, 3, 8):
+            parts = [dd.shard_range(n, r, G) for r in range(G)]
+            assert sum(c for _, c in parts) == n
+            assert parts[0][0] == 0 and all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(G - 1))
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_massart_helpers_match_oracle(oracle):
+    assert verifiers.chernoff_sample_bound(0.95, 0.3) == oracle.chernoff_n(0.95, 0.3) == 380
+    assert verifiers.okamoto_bound(0.05, 0.3) == oracle.okamoto_bound(0.05, 0.3)
+    for succ, tr in ((5, 5), (0, 9), (40, 50), (3, 50)):
+        I = list(verifiers.proportion_confint_beta(succ, tr))
+        I = [0.0 if math.isnan(I[0]) else I[0], 1.0 if math.isnan(I[1]) else I[1]]
+        assert tuple(I) == oracle.clopper_pearson(succ, tr)
+        assert verifiers.absolute_massart_halting(succ, tr, I, 0.05, 0.3, 0.05) == \
+            oracle.absolute_massart_halting(succ, tr, I, 0.05, 0.3, 0.05)

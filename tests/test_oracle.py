@@ -1,0 +1,149 @@
+"""CPU tests: the oracle against closed forms, known-answer vectors and the committed golden
+outputs ('what the new repo must supply itself')."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+
+def test_philox_known_answers(oracle):
+    # Random123 kat_vectors for philox4x32-10
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for c, k, want in kat:
+        got = oracle.philox4x32_10(np.array([c], np.uint32), np.array([k], np.uint32))[0]
+        assert [int(v) for v in got] == want
+
+
+def test_philox_normals_moments(oracle):
+    z = oracle.philox_normals(123, 5, 400000).astype(np.float64)
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+    assert abs((z ** 3).mean()) < 2e-2 and abs((z ** 4).mean() - 3) < 5e-2
+    # different sample ids / seeds give different streams
+    assert not np.allclose(z[:100], oracle.philox_normals(123, 6, 100))
+    assert not np.allclose(z[:100], oracle.philox_normals(124, 5, 100))
+
+
+def test_softplus_thresholds(oracle):
+    x = np.array([-80, -20, -13.95, -13.9, -1, 0, 1, 13.9, 13.95, 20, 100], np.float32)
+    y = oracle.softplus(x)
+    ref = np.log1p(np.exp(x.astype(np.float64)))
+    np.testing.assert_allclose(y, ref, rtol=2e-6, atol=0)
+    assert y[-1] == np.float32(100) and y[0] == np.exp(np.float32(-80))
+    s = np.array([1e-3, 0.05, 0.5, 2.0], np.float32)
+    np.testing.assert_allclose(oracle.softplus(oracle.inverse_softplus(s)), s, rtol=2e-4)
+
+
+def test_sigma_zero_is_deterministic(oracle):
+    L = oracle.mlp([20, 16, 5])
+    mean, std = oracle.synthetic_posterior(L, seed=3)
+    std0 = [np.zeros_like(s) for s in std]
+    x = oracle.synthetic_x((7, 20), seed=4)
+    eps = oracle.synthetic_eps(L, 5, seed=5)
+    got = oracle.predict(L, mean, std0, x, 5, eps)
+    np.testing.assert_allclose(got, oracle.forward(L, mean, x), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(got.sum(-1), 1, rtol=1e-5)
+
+
+def test_predict_equals_explicit_loop(oracle):
+    L = oracle.mlp([12, 9, 4])
+    mean, std = oracle.synthetic_posterior(L, seed=3, sigma_scale=0.5)
+    x = oracle.synthetic_x((6, 12), seed=4)
+    eps = oracle.synthetic_eps(L, 4, seed=5)
+    acc = np.zeros((6, 4), np.float32)
+    for e in eps:
+        w = [m.astype(np.float64) + s.astype(np.float64) * ee.astype(np.float64) for m, s, ee in zip(mean, std, e)]
+        acc += oracle.forward(L, [t.astype(np.float32) for t in w], x)
+    np.testing.assert_array_equal(oracle.predict(L, mean, std, x, 4, eps), acc / np.float32(4.0))
+
+
+def test_fp32_vs_fp64_forward(oracle):
+    c = cases.case_inputs("mlp_cfg2")
+    w = oracle.sample_gaussian(c["mean"], c["std"], c["eps"][0])
+    y32 = oracle.forward(c["layers"], w, c["x"], np.float32)
+    y64 = oracle.forward(c["layers"], w, c["x"], np.float64)
+    np.testing.assert_allclose(y32, y64, rtol=2e-5, atol=1e-7)
+
+
+def test_bf16_round(oracle):
+    import torch
+    a = np.random.Generator(np.random.Philox(0)).standard_normal(10000).astype(np.float32)
+    a[:4] = [0.0, -0.0, 1.0000001e-38, 3.3895314e38]
+    want = torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+    np.testing.assert_array_equal(oracle.bf16_round(a), want)
+
+
+def test_conv_against_torch(oracle):
+    import torch
+    g = np.random.Generator(np.random.Philox(1))
+    x = g.standard_normal((2, 9, 8, 3)).astype(np.float32)
+    for strides, padding in (((1, 1), "valid"), ((2, 2), "same"), ((1, 2), "same")):
+        l = oracle.Conv2D(3, 3, 3, 5, "linear", strides, padding)
+        k = g.standard_normal((3, 3, 3, 5)).astype(np.float32)
+        got = oracle._conv2d(x, k, l)
+        xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+        kt = torch.from_numpy(k).permute(3, 2, 0, 1)
+        if padding == "same":
+            ho, wo = -(-9 // strides[0]), -(-8 // strides[1])
+            ph = max((ho - 1) * strides[0] + 3 - 9, 0); pw = max((wo - 1) * strides[1] + 3 - 8, 0)
+            xt = torch.nn.functional.pad(xt, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+        want = torch.nn.functional.conv2d(xt, kt, stride=strides).permute(0, 2, 3, 1).numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_flops_and_params(oracle):
+    assert oracle.param_count(oracle.mlp([784, 512, 10])) == 407050
+    assert oracle.param_count(oracle.mlp([784, 512, 512, 10])) == 669706
+    assert oracle.flops_per_forward(oracle.mlp([784, 512, 512, 10])) == 1337344
+    assert oracle.param_count(oracle.cnn_cfg4()) == 1626442
+    assert oracle.param_count(oracle.mlp([784, 1024, 1024, 10])) == 1863690
+
+
+def test_chernoff_and_massart(oracle):
+    assert oracle.chernoff_n(0.95, 0.3) == 380
+    assert oracle.chernoff_n(0.995, 0.01) == 105967
+    assert abs(oracle.okamoto_bound(0.05, 0.3) - 379.42) < 0.01
+    assert oracle.absolute_massart_halting(1, 2, [0.2, 0.8], 0.05, 0.3, 0.05) == -1
+    flags = np.ones(1000, np.uint8)
+    frac, iters = oracle.massart_loop(flags)
+    assert frac == 1.0 and iters < 380  # all-success sequence halts before the Chernoff bound
+    lb, ub = oracle.clopper_pearson(0.0, 1.0)
+    assert lb == 0.0 and 0.9 < ub <= 1.0
+
+
+@pytest.mark.parametrize("name", cases.NAMES)
+def test_oracle_matches_committed_golden(oracle, golden_dir, name):
+    blob = np.load(os.path.join(golden_dir, "oracle_cases.npz"))
+    exp = cases.expected(name)
+    for k, v in exp.items():
+        want = blob["%s/%s" % (name, k)]
+        if v.dtype.kind in "iu":
+            np.testing.assert_array_equal(v, want)
+        else:  # BLAS builds may reorder sums; everything else is bit-stable
+            np.testing.assert_allclose(v, want, rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+def test_fixture_posteriors_load_and_predict(oracle, golden_dir):
+    from deepbayes_b200 import formats
+    for d in ("VOGN_MNIST_Posterior", "Robust_MNIST_Posterior"):
+        p = os.path.join(golden_dir, "posteriors", d)
+        mean = formats.load_tensor_list(os.path.join(p, "mean.npy"))
+        var = formats.load_tensor_list(os.path.join(p, "var.npy"))
+        assert [m.shape for m in mean] == [(784, 128), (128,), (128, 10), (10,)]
+        assert all(np.isfinite(v).all() and (v > 0).all() for v in var)
+        assert abs(float(var[0].mean()) - 4.666e-4) < 2e-6  # = 1/(N*s), N=60000 (blrvi.py:175)
+        info = formats.load_info(p)
+        assert info["input_upper"] == np.inf and info["N"] == 60000
+        L = oracle.mlp([784, 128, 10])
+        x = oracle.synthetic_x((8, 784), seed=0)
+        eps = oracle.synthetic_eps(L, 35, seed=2)
+        mc = oracle.predict(L, mean, var, x, 35, eps)
+        det = oracle.forward(L, mean, x)
+        np.testing.assert_allclose(mc.sum(-1), 1.0, rtol=1e-5)
+        assert np.abs(mc - det).max() < 2e-3  # sigma ~ 4.7e-4: MC mean hugs the deterministic forward
