@@ -264,8 +264,9 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            t1 = cpu_reference_pass(1, B)
-            n_ref = int(max(2, min(64, round(15.0 / max(t1, 1e-3)))))
+            cpu_reference_pass(1, B)  # warm the BLAS threads
+            t1 = cpu_reference_pass(2, B) / 2
+            n_ref = int(max(2, min(1024, round(15.0 / max(t1, 1e-3)))))
             dt = cpu_reference_pass(n_ref, B)
             cpu = {"value": n_ref * B / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d of %d posterior samples x all %d rows (%.1f s); NumPy port of posteriormodel.py:81-101, "

@@ -175,7 +175,7 @@ def test_bbb_forward(ctx, golden, oracle, name):
         out, W, noise = eng.bbb_forward(c["x"], eps=c["eps_flat"][0], mode="fp32", return_weights=True)
         want, w = oracle.bbb_forward(c["layers"], c["mean"], rho, c["eps"][0], c["x"])
         # W = mean + softplus(rho)*eps formed in fp32 in the reference's order: device softplus vs numpy <= 2 ulp
-        np.testing.assert_allclose(W.cpu().numpy(), oracle.flatten_list(w), rtol=3e-7, atol=1e-9)
+        np.testing.assert_allclose(W.cpu().numpy(), oracle.flatten_list(w), rtol=3e-7, atol=6e-8)
         np.testing.assert_array_equal(noise.cpu().numpy(), c["eps_flat"][0])
         np.testing.assert_allclose(out.cpu().numpy(), want, rtol=FP32_RTOL, atol=FP32_ATOL)
         np.testing.assert_allclose(out.cpu().numpy(), golden[name + "/bbb_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
@@ -333,7 +333,7 @@ def test_bbb_optimizer_api(oracle):
     want, w = oracle.bbb_forward(L, opt.posterior_mean, opt.posterior_var, eps, x)
     np.testing.assert_allclose(pred, want, rtol=FP32_RTOL, atol=FP32_ATOL)
     for a, b in zip(ws, w):
-        np.testing.assert_allclose(a, b, rtol=3e-7, atol=1e-9)
+        np.testing.assert_allclose(a, b, rtol=3e-7, atol=6e-8)
     np.testing.assert_array_equal(m.get_weights()[0], ws[0])         # step leaves the sample in the model (:59)
     np.testing.assert_allclose(opt.predict(x), want, rtol=FP32_RTOL, atol=FP32_ATOL)  # single forward, no sampling (:293-298)
     s = opt.sample()
