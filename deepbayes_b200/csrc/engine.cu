@@ -373,6 +373,15 @@ static inline int grid_for(int64_t total, int block = 256) {
 // Generic executor (all layer kinds; T = storage type of weights/activations)
 // ---------------------------------------------------------------------------------------
 
+int launch_sample_bf16(dbx_model* m, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16, float* B32, cudaStream_t st) {
+  const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
+  DBX_LAUNCH(sample_bf16_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma,
+             (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int64_t)nc, m->P,
+             src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, m->table, W16,
+             m->P16, B32, m->PB);
+  return 0;
+}
+
 static size_t ws_budget_bytes() {
   const char* e = getenv("DBX_WS_MB");
   size_t mb = e ? (size_t)atoll(e) : 2048;
@@ -415,11 +424,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
     const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
     const float* Bbase; int64_t b_sstride;
     if (kBf16) {
-      const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
-      DBX_LAUNCH(sample_bf16_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma,
-                 src.eps ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int64_t)nc, m->P,
-                 src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0,
-                 m->table, (__nv_bfloat16*)Wc, m->P16, B32, m->PB);
+      if (launch_sample_bf16(m, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
       Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
     } else if (src.stored) {
       Wbase = (const T*)m->slab; w_sstride = m->P; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;

@@ -90,6 +90,11 @@ int ensure_ws(Workspace& w, size_t bytes);
 void prof_begin(cudaStream_t st);
 void prof_end(cudaStream_t st, double flops);
 
+// Materialise the chunk's per-sample weights in the bf16 device layout (kernels -> W16 [nc,P16]
+// padded bf16, biases -> B32 [nc,PB] fp32): Gaussian draw (injected eps or Philox) or conversion
+// of stored samples.  Defined in engine.cu.
+int launch_sample_bf16(dbx_model* m, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16, float* B32, cudaStream_t st);
+
 // fused_mlp.cu: returns 1 if the tcgen05 fused path handled the request, 0 if the shape is
 // not supported by it (caller uses the generic kernels), <0 on error.
 int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,

@@ -1,6 +1,636 @@
-// placeholder: replaced by the tcgen05 fused MLP kernel
+// Fused Bayesian-MLP posterior-predictive kernel for sm_100a (tcgen05 / TMEM / TMA).
+//
+// One launch evaluates a chunk of `ns` posterior samples for all B input rows of an MLP
+//     x[K0] -> Dense(H, relu) [-> Dense(H, relu)] -> Dense(C <= 16, softmax | linear)
+// (BASELINE configs 1, 2, 5: 784-512-10 and 784-512-512-10).  The per-sample weights W_s were
+// materialised just before by sample_bf16_kernel (Philox + mu/sigma transform) in Keras layout,
+// bf16, and are streamed with TMA; activations never leave the SM:
+//
+//   unit = (posterior sample s, 128-row tile m).  Per unit, in one CTA:
+//     L1  : X tile (smem, K-major SW128)  x  W1_s (smem, MN-major SW128)  -> fp32 acc in TMEM
+//           two N=256 chunks -> TMEM regions R0=[0,256), R1=[256,512)
+//     E1  : epilogue warps: acc + b1, relu, pack bf16x2 IN PLACE -> R[0:128) (next A operand)
+//     L2  : A = packed H1 straight from TMEM (tcgen05.mma .ts), W2_s from smem, four N=128
+//           chunks into the freed halves R0[128:256) / R1[128:256)
+//     E2  : acc + b2, relu, pack in place -> buf[0:64)
+//     L3  : per chunk, A = packed H2 chunk (TMEM), W3_s (smem, no-swizzle, N=16) -> 16 cols,
+//           drained to registers and summed over chunks
+//     fin : + b3, softmax (fp32), running sum of p and p^2 over this CTA's samples in registers
+//   (posteriormodel.py:94-101: per-sample logits / probabilities never reach HBM.)
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue
+// (one thread per accumulator row).  CTAs of a cluster work on the same sample and adjacent row
+// tiles, so every weight box is fetched from L2 once per cluster and multicast.
+//
+// Work split: units are flattened [tile-group q][sample s] and cut into contiguous ranges, one
+// per cluster; a CTA keeps its running sums in registers while q stays the same and writes one
+// partial block per (cluster, segment); finish_kernel adds the partials in sample order, so
+// results are deterministic (no float atomics).
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include "engine.h"
+#include "tc05.cuh"
+
 namespace dbx {
-int fused_mlp_run(dbx_model*, const float*, int64_t, int64_t, const Source&, const Sink&, cudaStream_t) { return 0; }
-void fused_mlp_free(dbx_model*) {}
+
+using namespace tc05;
+
+constexpr int kStages = 4;
+constexpr int kStageBytes = 49152;           // X block 16 KB + weight blocks 32 KB
+constexpr int kXBytes = 16384;
+constexpr int kBlkBytes = 8192;              // one [64 n x 64 k] MN-major weight box
+constexpr int kW3Bytes = 16384;              // [H<=512 x 16] bf16, no-swizzle core-matrix layout
+constexpr int kBiasFloats = 1056;            // b1 | b2 | b3 (each padded to 4 floats)
+constexpr int kThreads = 192;
+constexpr int kMaxC = 16;
+
+struct FusedParams {
+  int K0, H, NH, C, B, ns, CM;
+  long long U;                 // units in this launch = Q * ns
+  int Q;                       // tile groups (CM row tiles each)
+  int NC;                      // clusters
+  int maxseg;
+  int sink_kind, out_kind, act_last, want_sum2;
+  const float* bias;           // [ns, PB] fp32
+  long long PB;
+  int b1_off, b2_off, b3_off;  // offsets inside one sample's bias row
+  const float* wts;            // [ns] or null
+  const int32_t* labels;       // [B] (count sink)
+  uint8_t* flags;              // [ns, B] or null
+  unsigned long long* counts;  // [B]
+  float* partial;              // [NC][maxseg][CM*128][2][16]
+};
+
+struct __align__(8) Barriers {
+  uint64_t full[kStages], empty[kStages];
+  uint64_t w3_full, w3_empty;
+  uint64_t bias_full[2], bias_empty[2];
+  uint64_t acc_full[2], act1_ready[2];
+  uint64_t acc2_full[2], act2_ready[2];
+  uint64_t l3_full[2], l3_drained[2];
+  uint32_t tmem_slot;
+};
+
+extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
+
+template <int CM>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
+                 const FusedParams p) {
+  uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  const uint32_t s_w3 = s_stage + kStages * kStageBytes;
+  float* bias_smem = (float*)(smem + kStages * kStageBytes + kW3Bytes);
+  const uint32_t s_bias = smem_u32(bias_smem);
+  Barriers* bars = (Barriers*)(smem + kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = (CM > 1) ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CM;
+  constexpr uint16_t kMask = (uint16_t)((1u << CM) - 1);
+
+  const int H = p.H, NH = p.NH, K0 = p.K0;
+  const int n_l1 = (H + 255) / 256;             // L1 chunks (N = 256, last may be 128)
+  const int n_l2 = (NH == 2) ? H / 128 : 0;     // L2 chunks (N = 128)
+  const int kb1 = (K0 + 63) / 64;               // k-blocks of layer 1
+  const int l2_stages = H / 128;                // 2 k-blocks per stage
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), CM); }
+    mbar_init(smem_u32(&bars->w3_full), 1); mbar_init(smem_u32(&bars->w3_empty), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->bias_full[i]), 1); mbar_init(smem_u32(&bars->bias_empty[i]), 128);
+      mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->act1_ready[i]), 128);
+      mbar_init(smem_u32(&bars->acc2_full[i]), 1); mbar_init(smem_u32(&bars->act2_ready[i]), 128);
+      mbar_init(smem_u32(&bars->l3_full[i]), 1); mbar_init(smem_u32(&bars->l3_drained[i]), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2); prefetch_tmap(&tmW3); }
+  fence_before_sync();
+  __syncthreads();
+  if (CM > 1) cluster_sync();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  const long long u0 = ((long long)cluster_id * p.U) / p.NC;
+  const long long u1 = ((long long)(cluster_id + 1) * p.U) / p.NC;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      uint32_t w3_n = 0, unit_n = 0;
+      for (long long u = u0; u < u1; ++u, ++unit_n) {
+        const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
+        const int m0 = (q * CM + (int)rank) * 128;
+        // biases of this sample -> bias buffer (unit parity)
+        {
+          const uint32_t b = unit_n & 1;
+          mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
+          mbar_expect_tx(smem_u32(&bars->bias_full[b]), (uint32_t)(p.PB * 4));
+          bulk_load(s_bias + b * kBiasFloats * 4, p.bias + (long long)s * p.PB, (uint32_t)(p.PB * 4), smem_u32(&bars->bias_full[b]));
+        }
+        for (int c = 0; c < n_l1; ++c) {
+          const int ncols = min(256, H - c * 256);
+          const int nblk = ncols / 64;
+          for (int kb = 0; kb < kb1; ++kb, ++it) {
+            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+            const uint32_t fb = smem_u32(&bars->full[st]);
+            const uint32_t base = s_stage + st * kStageBytes;
+            mbar_expect_tx(fb, kXBytes + nblk * kBlkBytes);
+            tma_load_2d(base, &tmX, fb, kb * 64, m0);
+            for (int nb = 0; nb < nblk; ++nb) {
+              if (CM == 1) tma_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s);
+              else if ((nb % CM) == (int)rank)
+                tma_load_3d_mc(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s, kMask);
+            }
+          }
+          if (c == 0) {
+            // W3 of this sample (single buffer): the MMA warp releases it after the previous
+            // unit's last L3 partial, which it force-issues right after L1 chunk 0.
+            mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
+            const uint32_t wf = smem_u32(&bars->w3_full);
+            mbar_expect_tx(wf, (uint32_t)(H * 32));
+            for (int nb = 0; nb < 2; ++nb)
+              for (int k0 = 0; k0 < H; k0 += 256)
+                tma_load_3d(s_w3 + nb * (H * 16) + k0 * 16, &tmW3, wf, nb * 8, k0, s);
+            ++w3_n;
+          }
+        }
+        for (int j = 0; j < n_l2; ++j) {
+          for (int sg = 0; sg < l2_stages; ++sg, ++it) {
+            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+            const uint32_t fb = smem_u32(&bars->full[st]);
+            const uint32_t base = s_stage + st * kStageBytes + kXBytes;
+            mbar_expect_tx(fb, 4 * kBlkBytes);
+            for (int bx = 0; bx < 4; ++bx) {  // (k-block kblk, n-block nb)
+              const int kblk = bx >> 1, nb = bx & 1;
+              const int kabs = sg * 2 + kblk;
+              if (CM == 1) tma_load_3d(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s);
+              else if ((bx % CM) == (int)rank)
+                tma_load_3d_mc(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s, kMask);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      uint32_t ph_act1[2] = {0, 0}, ph_act2[2] = {0, 0};
+      uint32_t l3_issued[2] = {0, 0}, l3_waited[2] = {0, 0};
+      uint32_t w3_n = 0;
+      // pending L3 partials (FIFO, at most 2 outstanding)
+      struct Pend { int buf; uint32_t a, d, woff; int ksteps; int last; int kind; };
+      Pend pend[4];
+      int pn = 0;
+      const uint32_t idesc_l3 = make_idesc_bf16(128, 16, 0, 1);
+      const uint32_t idesc_l2 = make_idesc_bf16(128, 128, 0, 1);
+
+      auto issue_l3 = [&](const Pend& e) {
+        for (int kk = 0; kk < e.ksteps; ++kk) {
+          const uint64_t bdesc = make_smem_desc(s_w3 + e.woff + kk * 256, 128, (uint32_t)(H * 16), SW_NONE);
+          mma_ts(e.d, e.a + kk * 8, bdesc, idesc_l3, kk > 0);
+        }
+        mma_commit(smem_u32(&bars->l3_full[e.buf]));
+        ++l3_issued[e.buf];
+        if (e.last) mma_commit(smem_u32(&bars->w3_empty));
+      };
+      // try (or force) to issue the oldest pending L3 partial; returns true if one was issued
+      auto pump = [&](bool force) -> bool {
+        if (pn == 0) return false;
+        const Pend e = pend[0];
+        const uint32_t bar = smem_u32(e.kind == 1 ? &bars->act1_ready[e.buf] : &bars->act2_ready[e.buf]);
+        uint32_t& ph = (e.kind == 1) ? ph_act1[e.buf] : ph_act2[e.buf];
+        if (force) mbar_wait(bar, ph & 1);
+        else if (!mbar_try_wait(bar, ph & 1)) return false;
+        ++ph;
+        fence_after_sync();
+        issue_l3(e);
+        for (int i = 1; i < pn; ++i) pend[i - 1] = pend[i];
+        --pn;
+        return true;
+      };
+      auto flush_all = [&]() { while (pump(true)) {} };
+      // issue every pending partial up to the last one that touches buffer b
+      auto flush_buf = [&](int b) {
+        int last = -1;
+        for (int i = 0; i < pn; ++i) if (pend[i].buf == b) last = i;
+        for (int i = 0; i <= last; ++i) pump(true);
+      };
+      auto wait_drained = [&](int b) {
+        while (l3_waited[b] < l3_issued[b]) { mbar_wait(smem_u32(&bars->l3_drained[b]), l3_waited[b] & 1); ++l3_waited[b]; }
+        fence_after_sync();
+      };
+
+      for (long long u = u0; u < u1; ++u) {
+        // ---------------- layer 1 (SS): X tile x W1 chunk -> region c
+        for (int c = 0; c < n_l1; ++c) {
+          const int ncols = min(256, H - c * 256);
+          const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 1);
+          const uint32_t dreg = tmem + c * 256;
+          if (c == 1) flush_all();        // everything that still reads region 1 / W3 of the previous unit
+          // region c must be free: its previous L3 partial drained
+          if (c == 0) flush_buf(0);
+          wait_drained(c);
+          for (int kb = 0; kb < kb1; ++kb, ++it) {
+            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(smem_u32(&bars->full[st]), ph);
+            fence_after_sync();
+            const uint32_t base = s_stage + st * kStageBytes;
+            const int ksteps = min(4, (K0 - kb * 64 + 15) / 16);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t adesc = make_smem_desc(base + kk * 32, 16, 1024, SW_128B);
+              const uint64_t bdesc = make_smem_desc(base + kXBytes + kk * 2048, kBlkBytes, 1024, SW_128B);
+              mma_ss(dreg, adesc, bdesc, idesc, (kb | kk) > 0);
+            }
+            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
+            pump(false);
+          }
+          mma_commit(smem_u32(&bars->acc_full[c]));
+          if (c == 0) {
+            flush_all();  // releases W3 of the previous unit (the producer waits for it here)
+            mbar_wait(smem_u32(&bars->w3_full), w3_n & 1);
+            ++w3_n;
+          }
+          if (NH == 1) {
+            // output layer straight from H1 chunk c
+            Pend e; e.buf = c; e.a = tmem + c * 256; e.d = tmem + c * 256 + 128; e.woff = (uint32_t)(c * 256 * 16);
+            e.ksteps = ncols / 16; e.last = (c == n_l1 - 1); e.kind = 1;
+            pend[pn++] = e;
+          }
+        }
+        // ---------------- layer 2 (TS): packed H1 (TMEM) x W2 chunk -> buffer j&1
+        for (int j = 0; j < n_l2; ++j) {
+          const int b = j & 1;
+          const uint32_t dbuf = tmem + b * 256 + 128;
+          // buffer b must be free: force its pending L3 partial out and wait for the drain
+          flush_buf(b);
+          wait_drained(b);
+          for (int sg = 0; sg < l2_stages; ++sg, ++it) {
+            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+            // the A operand of k-blocks [2sg, 2sg+1] lives in region (k*64)/256
+            const int reg = (sg * 128) / 256;
+            if (j == 0 && (sg * 128) % 256 == 0) {  // first touch of region `reg` in this unit
+              mbar_wait(smem_u32(&bars->act1_ready[reg]), ph_act1[reg] & 1);
+              ++ph_act1[reg];
+            }
+            mbar_wait(smem_u32(&bars->full[st]), ph);
+            fence_after_sync();
+            const uint32_t base = s_stage + st * kStageBytes + kXBytes;
+            for (int kblk = 0; kblk < 2; ++kblk) {
+              const int kabs = sg * 2 + kblk;                  // 64-wide k-block index
+              const uint32_t a0 = tmem + (uint32_t)((kabs * 64) / 256) * 256 + (uint32_t)(((kabs * 64) % 256) / 2);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t bdesc = make_smem_desc(base + kblk * 2 * kBlkBytes + kk * 2048, kBlkBytes, 1024, SW_128B);
+                mma_ts(dbuf, a0 + kk * 8, bdesc, idesc_l2, (kabs | kk) > 0);
+              }
+            }
+            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
+            pump(false);
+          }
+          mma_commit(smem_u32(&bars->acc2_full[b]));
+          Pend e; e.buf = b; e.a = dbuf; e.d = dbuf + 64; e.woff = (uint32_t)(j * 128 * 16); e.ksteps = 8;
+          e.last = (j == n_l2 - 1); e.kind = 2;
+          pend[pn++] = e;
+        }
+      }
+      flush_all();
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int g = warp & 3;                       // TMEM lane group this warp may access
+    const int row = g * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    uint32_t ph_acc[2] = {0, 0}, ph_acc2[2] = {0, 0}, ph_l3[2] = {0, 0};
+    uint32_t unit_n = 0;
+    float acc1[kMaxC], acc2[kMaxC];
+#pragma unroll
+    for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+    unsigned int cnt = 0;
+    int cur_q = (u0 < u1) ? (int)(u0 / p.ns) : -1;
+    const int q_first = cur_q;
+
+    auto flush_segment = [&](int q) {
+      const int seg = q - q_first;
+      const int grow = (q * CM + (int)rank) * 128 + row;
+      if (p.sink_kind == 0) {
+        float* dst = p.partial + ((((long long)cluster_id * p.maxseg + seg) * CM + rank) * 128 + row) * 32;
+#pragma unroll
+        for (int i = 0; i < kMaxC; i += 4) {
+          *reinterpret_cast<float4*>(dst + i) = make_float4(acc1[i], acc1[i + 1], acc1[i + 2], acc1[i + 3]);
+          *reinterpret_cast<float4*>(dst + 16 + i) = make_float4(acc2[i], acc2[i + 1], acc2[i + 2], acc2[i + 3]);
+        }
+      } else if (grow < p.B && cnt) {
+        atomicAdd(p.counts + grow, (unsigned long long)cnt);
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+      cnt = 0;
+    };
+
+    // pack one accumulator chunk: fp32 cols [0,ncols) at `src` (+bias, relu) -> bf16x2 cols [0,ncols/2)
+    auto pack_chunk = [&](uint32_t src, int ncols, const float* bias) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(src + c0, v);
+        wait_ld();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * i);
+          const float lo = fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f);
+          const float hi = fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f);
+          w[i] = pack_bf16x2(lo, hi);
+        }
+        tmem_st16(src + c0 / 2, w);
+      }
+      wait_st();
+      fence_before_sync();
+    };
+
+    for (long long u = u0; u < u1; ++u, ++unit_n) {
+      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
+      if (q != cur_q) { flush_segment(cur_q); cur_q = q; }
+      const uint32_t bb = unit_n & 1;
+      const float* bias = bias_smem + bb * kBiasFloats;
+      mbar_wait(smem_u32(&bars->bias_full[bb]), (unit_n >> 1) & 1);
+      float logit[kMaxC];
+#pragma unroll
+      for (int i = 0; i < kMaxC; ++i) logit[i] = 0.f;
+
+      auto drain_l3 = [&](int b, uint32_t daddr) {
+        mbar_wait(smem_u32(&bars->l3_full[b]), ph_l3[b] & 1);
+        ++ph_l3[b];
+        fence_after_sync();
+        uint32_t v[16];
+        tmem_ld16(daddr, v);
+        wait_ld();
+        fence_before_sync();
+        mbar_arrive(smem_u32(&bars->l3_drained[b]));
+#pragma unroll
+        for (int i = 0; i < kMaxC; ++i) logit[i] += __uint_as_float(v[i]);
+      };
+
+      for (int c = 0; c < n_l1; ++c) {
+        const int ncols = min(256, H - c * 256);
+        mbar_wait(smem_u32(&bars->acc_full[c]), ph_acc[c] & 1);
+        ++ph_acc[c];
+        fence_after_sync();
+        pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
+        mbar_arrive(smem_u32(&bars->act1_ready[c]));
+        if (NH == 1) drain_l3(c, tmem + lane_base + c * 256 + 128);
+      }
+      for (int j = 0; j < n_l2; ++j) {
+        const int b = j & 1;
+        mbar_wait(smem_u32(&bars->acc2_full[b]), ph_acc2[b] & 1);
+        ++ph_acc2[b];
+        fence_after_sync();
+        pack_chunk(tmem + lane_base + b * 256 + 128, 128, bias + p.b2_off + j * 128);
+        mbar_arrive(smem_u32(&bars->act2_ready[b]));
+        drain_l3(b, tmem + lane_base + b * 256 + 128 + 64);
+      }
+      // ---------------- output: + b3, softmax / linear, running sums over this CTA's samples
+      const float* b3 = bias + p.b3_off;
+      float z[kMaxC];
+#pragma unroll
+      for (int i = 0; i < kMaxC; ++i) z[i] = (i < p.C) ? logit[i] + b3[i] : -INFINITY;
+      mbar_arrive(smem_u32(&bars->bias_empty[bb]));
+      const int grow = (q * CM + (int)rank) * 128 + row;
+      if (p.sink_kind == 0) {
+        const float w = p.wts ? p.wts[s] : 1.f;
+        if (p.out_kind == DBX_OUT_LOGITS) {
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) if (i < p.C) { acc1[i] = fmaf(w, z[i], acc1[i]); acc2[i] = fmaf(w * z[i], z[i], acc2[i]); }
+        } else if (p.act_last == DBX_ACT_SOFTMAX) {
+          float mx = z[0];
+#pragma unroll
+          for (int i = 1; i < kMaxC; ++i) mx = fmaxf(mx, z[i]);
+          float e[kMaxC], den = 0.f;
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) { e[i] = (i < p.C) ? expf(z[i] - mx) : 0.f; den += e[i]; }
+          const float inv = 1.f / den;
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) { const float pr = e[i] * inv; acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) if (i < p.C) { const float pr = apply_act(p.act_last, z[i]); acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
+        }
+      } else {
+        int best = 0; float bv = z[0];
+#pragma unroll
+        for (int i = 1; i < kMaxC; ++i) if (z[i] > bv) { bv = z[i]; best = i; }
+        if (grow < p.B) {
+          const int ok = (best == p.labels[grow]);
+          if (p.flags) p.flags[(long long)s * p.B + grow] = (uint8_t)ok;
+          cnt += ok;
+        }
+      }
+    }
+    if (cur_q >= 0) flush_segment(cur_q);
+  }
+
+  // teardown: nobody may exit while a peer can still multicast into / arrive on this CTA
+  fence_before_sync();
+  __syncthreads();
+  if (CM > 1) cluster_sync();
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
+
+// Adds the per-(cluster, segment) partial sums in sample order.
+__global__ void finish_kernel(const float* __restrict__ partial, int NC, int maxseg, int CM, long long U, int ns, int B,
+                              int C, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
+  const long long total = (long long)B * C;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(o / C), c = (int)(o - (long long)b * C);
+    const int tile = b / 128, row = b % 128, q = tile / CM, rank = tile % CM;
+    float a1 = overwrite ? 0.f : sum1[o];
+    float a2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
+    const long long lo = (long long)q * ns, hi = lo + ns;
+    for (int k = 0; k < NC; ++k) {
+      const long long u0 = ((long long)k * U) / NC, u1 = ((long long)(k + 1) * U) / NC;
+      if (u1 <= lo || u0 >= hi || u0 >= u1) continue;
+      const int seg = q - (int)(u0 / ns);
+      const float* src = partial + ((((long long)k * maxseg + seg) * CM + rank) * 128 + row) * 32;
+      a1 += src[c];
+      a2 += src[16 + c];
+    }
+    sum1[o] = a1;
+    if (sum2) sum2[o] = a2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int K,
+                                      int Kp) {
+  const int64_t total = rows * Kp;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = o / Kp; const int k = (int)(o - r * Kp);
+    out[o] = __float2bfloat16_rn(k < K ? in[r * K + k] : 0.f);
+  }
+}
+__global__ void zero_counts_kernel(unsigned long long* p, int64_t n) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) p[o] = 0ULL;
+}
+
+struct FusedState {
+  int num_sms = 0;
+  bool attr_set[9] = {};
+};
+
+static bool shape_supported(const dbx_model* m) {
+  if (!m->is_mlp) return false;
+  std::vector<const Layer*> dl;
+  for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
+  if (dl.size() != 2 && dl.size() != 3) return false;
+  const int H = dl[0]->units;
+  if (H % 128 != 0 || H > 512 || H < 128) return false;
+  if (dl.size() == 3 && dl[1]->units != H) return false;
+  for (size_t i = 0; i + 1 < dl.size(); ++i) if (dl[i]->act != DBX_ACT_RELU) return false;
+  if (dl.back()->units > kMaxC) return false;
+  if (m->in_feat < 16) return false;
+  return true;
+}
+
+template <int CM>
+static int launch_fused(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
+                        const FusedParams& p, int smem, cudaStream_t st) {
+  DBX_CUDA(cudaFuncSetAttribute(fused_mlp_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.NC * CM));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp_kernel<CM>, tmX, tmW1, tmW2, tmW3, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+static inline int grid_for2(int64_t total, int block = 256) {
+  return (int)std::min<int64_t>(std::max<int64_t>(cdiv(total, block), 1), 148 * 16);
+}
+
+int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
+                  cudaStream_t st) {
+  if (!shape_supported(m)) return 0;
+  if (!get_encode_fn()) return 0;
+  FusedState* fs = (FusedState*)m->fused_state;
+  if (!fs) {
+    fs = new FusedState();
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete fs; return -1; }
+    fs->num_sms = prop.multiProcessorCount;
+    m->fused_state = fs;
+  }
+  std::vector<const Layer*> dl;
+  for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
+  const int NH = (int)dl.size() - 1, H = dl[0]->units, K0 = (int)m->in_feat, C = (int)m->out_feat;
+  const Layer* Lout = dl.back();
+
+  int CM = 1;
+  if (const char* e = getenv("DBX_FUSED_CM")) CM = atoi(e);
+  if (CM != 1 && CM != 2 && CM != 4) CM = 1;
+  const int T = (int)cdiv(B, 128);
+  const int Q = (int)cdiv(T, CM);
+  int64_t ns_max = 256;
+  if (const char* e = getenv("DBX_FUSED_NS")) ns_max = std::max(1, atoi(e));
+  const int64_t ns = std::min<int64_t>(n, ns_max);
+
+  // ---- workspace: X bf16 | W16 [ns,P16] | B32 [ns,PB] | partials
+  const int K0p = (int)round_up(K0, 8);
+  const size_t x_b = round_up((size_t)B * K0p * 2, 1024);
+  const size_t w_b = round_up((size_t)ns * m->P16 * 2, 1024);
+  const size_t b_b = round_up((size_t)ns * m->PB * 4, 1024);
+  const int NCmax = std::max(1, fs->num_sms / CM);
+  const int maxseg = (int)cdiv(Q, NCmax) + 2;
+  const size_t part_b = round_up((size_t)NCmax * maxseg * CM * 128 * 32 * 4, 1024);
+  const size_t need = x_b + w_b + b_b + part_b;
+  if (m->fused_ws.bytes < need) {
+    if (ensure_ws(m->fused_ws, need)) return -1;
+    if (cudaMemsetAsync(m->fused_ws.ptr, 0, need, st) != cudaSuccess) return -1;  // pad columns stay zero
+  }
+  char* wp = (char*)m->fused_ws.ptr;
+  __nv_bfloat16* X16 = (__nv_bfloat16*)wp; wp += x_b;
+  __nv_bfloat16* W16 = (__nv_bfloat16*)wp; wp += w_b;
+  float* B32 = (float*)wp; wp += b_b;
+  float* partial = (float*)wp;
+
+  cast_rows_bf16_kernel<<<grid_for2(B * K0p), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
+  g_launches.fetch_add(1);
+  if (cudaGetLastError() != cudaSuccess) { set_err("cast launch failed"); return -1; }
+
+  // ---- tensor maps
+  CUtensorMap tmX, tmW1, tmW2, tmW3;
+  {
+    uint64_t d[2] = {(uint64_t)K0, (uint64_t)B}, s[1] = {(uint64_t)K0p * 2};
+    uint32_t b[2] = {64, 128};
+    if (!make_tmap_bf16(&tmX, X16, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
+  }
+  auto make_w = [&](CUtensorMap* tm, const Layer* L, uint32_t bn, uint32_t bk, CUtensorMapSwizzle swz) {
+    uint64_t d[3] = {(uint64_t)L->w_cols_pad, (uint64_t)L->w_rows, (uint64_t)ns};
+    uint64_t s[2] = {(uint64_t)L->w_cols_pad * 2, (uint64_t)m->P16 * 2};
+    uint32_t b[3] = {bn, bk, 1};
+    return make_tmap_bf16(tm, W16 + L->w16_off, 3, d, s, b, swz);
+  };
+  if (!make_w(&tmW1, dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
+  if (!make_w(&tmW2, NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
+  if (!make_w(&tmW3, Lout, 8, (uint32_t)std::min(256, H), CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
+
+  const int smem = kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024;
+
+  if (sink.kind == 1 && !sink.accumulate) {
+    zero_counts_kernel<<<grid_for2(B), 256, 0, st>>>(sink.counts, B);
+    g_launches.fetch_add(1);
+  }
+
+  for (int64_t c0 = 0; c0 < n; c0 += ns) {
+    const int nc = (int)std::min<int64_t>(ns, n - c0);
+    if (launch_sample_bf16(m, src, c0, nc, W16, B32, st)) return -1;
+
+    FusedParams p = {};
+    p.K0 = K0; p.H = H; p.NH = NH; p.C = C; p.B = (int)B; p.ns = nc; p.CM = CM;
+    p.Q = Q; p.U = (long long)Q * nc;
+    p.NC = (int)std::min<long long>(NCmax, std::max<long long>(1, p.U));
+    p.maxseg = maxseg;
+    p.sink_kind = sink.kind; p.out_kind = sink.out_kind; p.act_last = Lout->act; p.want_sum2 = sink.sum2 != nullptr;
+    p.bias = B32; p.PB = m->PB;
+    p.b1_off = (int)dl[0]->b32_off; p.b2_off = (int)(NH == 2 ? dl[1]->b32_off : 0); p.b3_off = (int)Lout->b32_off;
+    p.wts = sink.wts ? sink.wts + c0 : nullptr;
+    p.labels = sink.labels; p.flags = sink.flags ? sink.flags + c0 * B : nullptr; p.counts = sink.counts;
+    p.partial = partial;
+    prof_begin(st);
+    int rc = 0;
+    if (CM == 1) rc = launch_fused<1>(tmX, tmW1, tmW2, tmW3, p, smem, st);
+    else if (CM == 2) rc = launch_fused<2>(tmX, tmW1, tmW2, tmW3, p, smem, st);
+    else rc = launch_fused<4>(tmX, tmW1, tmW2, tmW3, p, smem, st);
+    if (rc) return -1;
+    prof_end(st, (double)m->flops * (double)B * nc);
+    if (sink.kind == 0) {
+      const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
+      finish_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.NC, maxseg, CM, p.U, nc, (int)B, C, overwrite, sink.sum1,
+                                                       sink.sum2);
+      g_launches.fetch_add(1);
+      if (cudaGetLastError() != cudaSuccess) { set_err("finish launch failed"); return -1; }
+    }
+  }
+  return 1;
+}
+
+void fused_mlp_free(dbx_model* m) {
+  if (m->fused_state) { delete (FusedState*)m->fused_state; m->fused_state = nullptr; }
+}
+
+}  // namespace dbx

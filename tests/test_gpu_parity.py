@@ -133,6 +133,8 @@ def test_predict_bf16(ctx, golden, oracle, name, fused, monkeypatch):
     n = c["n"]
     s1, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="bf16")
     got = (s1 / float(n)).cpu().numpy()
+    fusable = name in ("mlp_cfg1", "mlp_cfg2")
+    assert eng.last_path() == ("fused_tcgen05" if (fused and fusable) else "generic")
     want_bf = golden[name + "/predict_bf16"]   # oracle with bf16-rounded GEMM operands
     want_32 = golden[name + "/predict_fp32"]
     assert np.abs(got - want_32).max() <= BF16_ATOL
