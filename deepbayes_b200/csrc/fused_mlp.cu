@@ -121,54 +121,68 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      uint32_t it = 0;
-      uint32_t w3_n = 0, unit_n = 0;
-      for (long long u = u0; u < u1; ++u, ++unit_n) {
-        const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
-        const int m0 = (q * CM + (int)rank) * 128;
-        // biases of this sample -> bias buffer (unit parity)
-        {
-          const uint32_t b = unit_n & 1;
-          mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
+    // The whole warp runs the loop with warp-uniform values (so addresses / descriptors live
+    // in uniform registers); one elected lane issues the copies.
+    uint32_t it = 0;
+    uint32_t w3_n = 0, unit_n = 0;
+    for (long long u = u0; u < u1; ++u, ++unit_n) {
+      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
+      const int m0 = (q * CM + (int)rank) * 128;
+      {
+        const uint32_t b = unit_n & 1;
+        mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(smem_u32(&bars->bias_full[b]), (uint32_t)(p.PB * 4));
           bulk_load(s_bias + b * kBiasFloats * 4, p.bias + (long long)s * p.PB, (uint32_t)(p.PB * 4), smem_u32(&bars->bias_full[b]));
         }
-        for (int c = 0; c < n_l1; ++c) {
-          const int ncols = min(256, H - c * 256);
-          const int nblk = ncols / 64;
-          for (int kb = 0; kb < kb1; ++kb, ++it) {
-            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        __syncwarp();
+      }
+      for (int c = 0; c < n_l1; ++c) {
+        const int ncols = min(256, H - c * 256);
+        const int nblk = ncols / 64;
+        for (int kb = 0; kb < kb1; ++kb, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
             const uint32_t base = s_stage + st * kStageBytes;
             mbar_expect_tx(fb, kXBytes + nblk * kBlkBytes);
             tma_load_2d(base, &tmX, fb, kb * 64, m0);
-            for (int nb = 0; nb < nblk; ++nb) {
-              if (CM == 1) tma_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s);
-              else if ((nb % CM) == (int)rank)
-                tma_load_3d_mc(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s, kMask);
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+              if (nb < nblk) {
+                if (CM == 1) tma_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s);
+                else if ((nb % CM) == (int)rank)
+                  tma_load_3d_mc(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s, kMask);
+              }
             }
           }
-          if (c == 0) {
-            // W3 of this sample (single buffer): the MMA warp releases it after the previous
-            // unit's last L3 partial, which it force-issues right after L1 chunk 0.
-            mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
+          __syncwarp();
+        }
+        if (c == 0) {
+          // W3 of this sample (single buffer): the MMA warp releases it after the previous
+          // unit's last L3 partial, which it force-issues right after L1 chunk 0.
+          mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
+          if (elect_one()) {
             const uint32_t wf = smem_u32(&bars->w3_full);
             mbar_expect_tx(wf, (uint32_t)(H * 32));
             for (int nb = 0; nb < 2; ++nb)
               for (int k0 = 0; k0 < H; k0 += 256)
                 tma_load_3d(s_w3 + nb * (H * 16) + k0 * 16, &tmW3, wf, nb * 8, k0, s);
-            ++w3_n;
           }
+          __syncwarp();
+          ++w3_n;
         }
-        for (int j = 0; j < n_l2; ++j) {
-          for (int sg = 0; sg < l2_stages; ++sg, ++it) {
-            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      }
+      for (int j = 0; j < n_l2; ++j) {
+        for (int sg = 0; sg < l2_stages; ++sg, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
             const uint32_t base = s_stage + st * kStageBytes + kXBytes;
             mbar_expect_tx(fb, 4 * kBlkBytes);
+#pragma unroll
             for (int bx = 0; bx < 4; ++bx) {  // (k-block kblk, n-block nb)
               const int kblk = bx >> 1, nb = bx & 1;
               const int kabs = sg * 2 + kblk;
@@ -177,133 +191,136 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 tma_load_3d_mc(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s, kMask);
             }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      uint32_t it = 0;
-      uint32_t ph_act1[2] = {0, 0}, ph_act2[2] = {0, 0};
-      uint32_t l3_issued[2] = {0, 0}, l3_waited[2] = {0, 0};
-      uint32_t w3_n = 0;
-      // pending L3 partials (FIFO, at most 2 outstanding)
-      struct Pend { int buf; uint32_t a, d, woff; int ksteps; int last; int kind; };
-      Pend pend[4];
-      int pn = 0;
-      const uint32_t idesc_l3 = make_idesc_bf16(128, 16, 0, 1);
-      const uint32_t idesc_l2 = make_idesc_bf16(128, 128, 0, 1);
+    // Warp-uniform control flow; one elected lane issues tcgen05.mma / commit.
+    uint32_t it = 0;
+    uint32_t ph_act1_0 = 0, ph_act1_1 = 0, ph_act2_0 = 0, ph_act2_1 = 0;
+    uint32_t l3_issued0 = 0, l3_issued1 = 0, l3_waited0 = 0, l3_waited1 = 0;
+    uint32_t w3_n = 0;
+    // pending L3 partials: FIFO of at most 2 entries, kept in scalars
+    // entry = (buf, a_tmem, d_tmem, w3 byte offset, ksteps, last-of-unit, kind 1|2)
+    int pn = 0;
+    int pb0 = 0, pk0 = 0, pl0 = 0, pkind0 = 0; uint32_t pa0 = 0, pd0 = 0, pw0 = 0;
+    int pb1 = 0, pk1 = 0, pl1 = 0, pkind1 = 0; uint32_t pa1 = 0, pd1 = 0, pw1 = 0;
+    const uint32_t idesc_l3 = make_idesc_bf16(128, 16, 0, 1);
+    const uint32_t idesc_l2 = make_idesc_bf16(128, 128, 0, 1);
+    const uint64_t w3desc0 = make_smem_desc(s_w3, 128, (uint32_t)(H * 16), SW_NONE);
 
-      auto issue_l3 = [&](const Pend& e) {
-        for (int kk = 0; kk < e.ksteps; ++kk) {
-          const uint64_t bdesc = make_smem_desc(s_w3 + e.woff + kk * 256, 128, (uint32_t)(H * 16), SW_NONE);
-          mma_ts(e.d, e.a + kk * 8, bdesc, idesc_l3, kk > 0);
-        }
-        mma_commit(smem_u32(&bars->l3_full[e.buf]));
-        ++l3_issued[e.buf];
-        if (e.last) mma_commit(smem_u32(&bars->w3_empty));
-      };
-      // try (or force) to issue the oldest pending L3 partial; returns true if one was issued
-      auto pump = [&](bool force) -> bool {
-        if (pn == 0) return false;
-        const Pend e = pend[0];
-        const uint32_t bar = smem_u32(e.kind == 1 ? &bars->act1_ready[e.buf] : &bars->act2_ready[e.buf]);
-        uint32_t& ph = (e.kind == 1) ? ph_act1[e.buf] : ph_act2[e.buf];
-        if (force) mbar_wait(bar, ph & 1);
-        else if (!mbar_try_wait(bar, ph & 1)) return false;
-        ++ph;
-        fence_after_sync();
-        issue_l3(e);
-        for (int i = 1; i < pn; ++i) pend[i - 1] = pend[i];
-        --pn;
-        return true;
-      };
-      auto flush_all = [&]() { while (pump(true)) {} };
-      // issue every pending partial up to the last one that touches buffer b
-      auto flush_buf = [&](int b) {
-        int last = -1;
-        for (int i = 0; i < pn; ++i) if (pend[i].buf == b) last = i;
-        for (int i = 0; i <= last; ++i) pump(true);
-      };
-      auto wait_drained = [&](int b) {
-        while (l3_waited[b] < l3_issued[b]) { mbar_wait(smem_u32(&bars->l3_drained[b]), l3_waited[b] & 1); ++l3_waited[b]; }
-        fence_after_sync();
-      };
-
-      for (long long u = u0; u < u1; ++u) {
-        // ---------------- layer 1 (SS): X tile x W1 chunk -> region c
-        for (int c = 0; c < n_l1; ++c) {
-          const int ncols = min(256, H - c * 256);
-          const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 1);
-          const uint32_t dreg = tmem + c * 256;
-          if (c == 1) flush_all();        // everything that still reads region 1 / W3 of the previous unit
-          // region c must be free: its previous L3 partial drained
-          if (c == 0) flush_buf(0);
-          wait_drained(c);
-          for (int kb = 0; kb < kb1; ++kb, ++it) {
-            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-            mbar_wait(smem_u32(&bars->full[st]), ph);
-            fence_after_sync();
-            const uint32_t base = s_stage + st * kStageBytes;
-            const int ksteps = min(4, (K0 - kb * 64 + 15) / 16);
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t adesc = make_smem_desc(base + kk * 32, 16, 1024, SW_128B);
-              const uint64_t bdesc = make_smem_desc(base + kXBytes + kk * 2048, kBlkBytes, 1024, SW_128B);
-              mma_ss(dreg, adesc, bdesc, idesc, (kb | kk) > 0);
-            }
-            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
-            pump(false);
-          }
-          mma_commit(smem_u32(&bars->acc_full[c]));
-          if (c == 0) {
-            flush_all();  // releases W3 of the previous unit (the producer waits for it here)
-            mbar_wait(smem_u32(&bars->w3_full), w3_n & 1);
-            ++w3_n;
-          }
-          if (NH == 1) {
-            // output layer straight from H1 chunk c
-            Pend e; e.buf = c; e.a = tmem + c * 256; e.d = tmem + c * 256 + 128; e.woff = (uint32_t)(c * 256 * 16);
-            e.ksteps = ncols / 16; e.last = (c == n_l1 - 1); e.kind = 1;
-            pend[pn++] = e;
-          }
-        }
-        // ---------------- layer 2 (TS): packed H1 (TMEM) x W2 chunk -> buffer j&1
-        for (int j = 0; j < n_l2; ++j) {
-          const int b = j & 1;
-          const uint32_t dbuf = tmem + b * 256 + 128;
-          // buffer b must be free: force its pending L3 partial out and wait for the drain
-          flush_buf(b);
-          wait_drained(b);
-          for (int sg = 0; sg < l2_stages; ++sg, ++it) {
-            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-            // the A operand of k-blocks [2sg, 2sg+1] lives in region (k*64)/256
-            const int reg = (sg * 128) / 256;
-            if (j == 0 && (sg * 128) % 256 == 0) {  // first touch of region `reg` in this unit
-              mbar_wait(smem_u32(&bars->act1_ready[reg]), ph_act1[reg] & 1);
-              ++ph_act1[reg];
-            }
-            mbar_wait(smem_u32(&bars->full[st]), ph);
-            fence_after_sync();
-            const uint32_t base = s_stage + st * kStageBytes + kXBytes;
-            for (int kblk = 0; kblk < 2; ++kblk) {
-              const int kabs = sg * 2 + kblk;                  // 64-wide k-block index
-              const uint32_t a0 = tmem + (uint32_t)((kabs * 64) / 256) * 256 + (uint32_t)(((kabs * 64) % 256) / 2);
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t bdesc = make_smem_desc(base + kblk * 2 * kBlkBytes + kk * 2048, kBlkBytes, 1024, SW_128B);
-                mma_ts(dbuf, a0 + kk * 8, bdesc, idesc_l2, (kabs | kk) > 0);
-              }
-            }
-            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
-            pump(false);
-          }
-          mma_commit(smem_u32(&bars->acc2_full[b]));
-          Pend e; e.buf = b; e.a = dbuf; e.d = dbuf + 64; e.woff = (uint32_t)(j * 128 * 16); e.ksteps = 8;
-          e.last = (j == n_l2 - 1); e.kind = 2;
-          pend[pn++] = e;
-        }
+    // try (or force) to issue the oldest pending L3 partial; returns true if one was issued
+    auto pump = [&](bool force) -> bool {
+      if (pn == 0) return false;
+      const uint32_t bar = smem_u32(pkind0 == 1 ? &bars->act1_ready[pb0] : &bars->act2_ready[pb0]);
+      uint32_t ph;
+      if (pkind0 == 1) ph = pb0 ? ph_act1_1 : ph_act1_0; else ph = pb0 ? ph_act2_1 : ph_act2_0;
+      if (force) mbar_wait(bar, ph & 1);
+      else if (!mbar_try_wait(bar, ph & 1)) return false;
+      if (pkind0 == 1) { if (pb0) ++ph_act1_1; else ++ph_act1_0; } else { if (pb0) ++ph_act2_1; else ++ph_act2_0; }
+      fence_after_sync();
+      if (elect_one()) {
+        const uint64_t bd = w3desc0 + (uint64_t)(pw0 >> 4);
+        for (int kk = 0; kk < pk0; ++kk) mma_ts(pd0, pa0 + kk * 8, bd + (uint64_t)(kk * 16), idesc_l3, kk > 0);
+        mma_commit(smem_u32(&bars->l3_full[pb0]));
+        if (pl0) mma_commit(smem_u32(&bars->w3_empty));
       }
-      flush_all();
+      __syncwarp();
+      if (pb0) ++l3_issued1; else ++l3_issued0;
+      pb0 = pb1; pk0 = pk1; pl0 = pl1; pkind0 = pkind1; pa0 = pa1; pd0 = pd1; pw0 = pw1;
+      --pn;
+      return true;
+    };
+    auto push = [&](int buf, uint32_t a, uint32_t d, uint32_t woff, int ksteps, int last, int kind) {
+      if (pn == 0) { pb0 = buf; pa0 = a; pd0 = d; pw0 = woff; pk0 = ksteps; pl0 = last; pkind0 = kind; }
+      else { pb1 = buf; pa1 = a; pd1 = d; pw1 = woff; pk1 = ksteps; pl1 = last; pkind1 = kind; }
+      ++pn;
+    };
+    auto flush_all = [&]() { while (pump(true)) {} };
+    // issue every pending partial up to the last one that touches buffer b
+    auto flush_buf = [&](int b) {
+      if (pn == 2 && pb1 == b) { pump(true); pump(true); }
+      else if (pn >= 1 && pb0 == b) pump(true);
+    };
+    auto wait_drained = [&](int b) {
+      if (b == 0) { while (l3_waited0 < l3_issued0) { mbar_wait(smem_u32(&bars->l3_drained[0]), l3_waited0 & 1); ++l3_waited0; } }
+      else { while (l3_waited1 < l3_issued1) { mbar_wait(smem_u32(&bars->l3_drained[1]), l3_waited1 & 1); ++l3_waited1; } }
+      fence_after_sync();
+    };
+
+    for (long long u = u0; u < u1; ++u) {
+      // ---------------- layer 1 (SS): X tile x W1 chunk -> region c
+      for (int c = 0; c < n_l1; ++c) {
+        const int ncols = min(256, H - c * 256);
+        const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 1);
+        const uint32_t dreg = tmem + c * 256;
+        if (c == 1) flush_all();        // everything that still reads region 1 / W3 of the previous unit
+        else flush_buf(0);
+        wait_drained(c);                // region c is free once its last L3 partial was drained
+        for (int kb = 0; kb < kb1; ++kb, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(smem_u32(&bars->full[st]), ph);
+          fence_after_sync();
+          const int ksteps = min(4, (K0 - kb * 64 + 15) / 16);
+          if (elect_one()) {
+            const uint32_t base = s_stage + st * kStageBytes;
+            const uint64_t adesc = make_smem_desc(base, 16, 1024, SW_128B);
+            const uint64_t bdesc = make_smem_desc(base + kXBytes, kBlkBytes, 1024, SW_128B);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              if (kk < ksteps) mma_ss(dreg, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 128), idesc, (kb | kk) > 0);
+            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
+          }
+          __syncwarp();
+          pump(false);
+        }
+        if (elect_one()) mma_commit(smem_u32(&bars->acc_full[c]));
+        __syncwarp();
+        if (c == 0) {
+          flush_all();  // releases W3 of the previous unit (the producer waits for it here)
+          mbar_wait(smem_u32(&bars->w3_full), w3_n & 1);
+          ++w3_n;
+        }
+        if (NH == 1)  // output layer straight from H1 chunk c
+          push(c, tmem + c * 256, tmem + c * 256 + 128, (uint32_t)(c * 256 * 16), ncols / 16, c == n_l1 - 1, 1);
+      }
+      // ---------------- layer 2 (TS): packed H1 (TMEM) x W2 chunk -> buffer j&1
+      for (int j = 0; j < n_l2; ++j) {
+        const int b = j & 1;
+        const uint32_t dbuf = tmem + b * 256 + 128;
+        flush_buf(b);      // buffer b must be free: force its pending L3 partial out ...
+        wait_drained(b);   // ... and wait until the epilogue drained it
+        for (int sg = 0; sg < l2_stages; ++sg, ++it) {
+          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+          // the A operand of k-blocks [2sg, 2sg+1] lives in region (sg*128)/256
+          if (j == 0 && (sg * 128) % 256 == 0) {  // first touch of that region in this unit
+            if ((sg * 128) / 256 == 0) { mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
+            else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
+          }
+          mbar_wait(smem_u32(&bars->full[st]), ph);
+          fence_after_sync();
+          if (elect_one()) {
+            const uint32_t base = s_stage + st * kStageBytes + kXBytes;
+            const uint64_t bdesc = make_smem_desc(base, kBlkBytes, 1024, SW_128B);
+            const int kabs0 = sg * 2;                        // first 64-wide k-block of this stage
+            const uint32_t a0 = tmem + (uint32_t)((kabs0 * 64) / 256) * 256 + (uint32_t)(((kabs0 * 64) % 256) / 2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk; consecutive 16-wide k-steps are 8 TMEM columns apart
+              mma_ts(dbuf, a0 + i * 8, bdesc + (uint64_t)((i >> 2) * (2 * kBlkBytes / 16) + (i & 3) * 128), idesc_l2,
+                     (sg | i) > 0);
+            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
+          }
+          __syncwarp();
+          pump(false);
+        }
+        if (elect_one()) mma_commit(smem_u32(&bars->acc2_full[b]));
+        __syncwarp();
+        push(b, dbuf, dbuf + 64, (uint32_t)(j * 128 * 16), 8, j == n_l2 - 1, 2);
+      }
     }
+    flush_all();
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     const int g = warp & 3;                       // TMEM lane group this warp may access
