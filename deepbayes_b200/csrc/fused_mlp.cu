@@ -46,7 +46,7 @@ constexpr int kThreads = 192;
 constexpr int kMaxC = 16;
 
 struct FusedParams {
-  int K0, H, NH, C, B, ns, CM;
+  int K0, H, NH, C, B, ns, CM, mc;
   long long U;                 // units in this launch = Q * ns
   int Q;                       // tile groups (CM row tiles each)
   int NC;                      // clusters
@@ -98,7 +98,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int l2_stages = H / 128;                // 2 k-blocks per stage
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), CM); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), p.mc ? CM : 1); }
     mbar_init(smem_u32(&bars->w3_full), 1); mbar_init(smem_u32(&bars->w3_empty), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->bias_full[i]), 1); mbar_init(smem_u32(&bars->bias_empty[i]), 128);
@@ -151,7 +151,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
               if (nb < nblk) {
-                if (CM == 1) tma_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s);
+                if (CM == 1 || !p.mc) tma_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s);
                 else if ((nb % CM) == (int)rank)
                   tma_load_3d_mc(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s, kMask);
               }
@@ -167,7 +167,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t wf = smem_u32(&bars->w3_full);
             mbar_expect_tx(wf, (uint32_t)(H * 32));
             for (int nb = 0; nb < 2; ++nb)
-              for (int k0 = 0; k0 < H; k0 += 256)
+              for (int k0 = 0; k0 < H; k0 += 128)   // boxes of [8 n x 128 k] = 2 KB
                 tma_load_3d(s_w3 + nb * (H * 16) + k0 * 16, &tmW3, wf, nb * 8, k0, s);
           }
           __syncwarp();
@@ -186,7 +186,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int bx = 0; bx < 4; ++bx) {  // (k-block kblk, n-block nb)
               const int kblk = bx >> 1, nb = bx & 1;
               const int kabs = sg * 2 + kblk;
-              if (CM == 1) tma_load_3d(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s);
+              if (CM == 1 || !p.mc) tma_load_3d(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s);
               else if ((bx % CM) == (int)rank)
                 tma_load_3d_mc(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s, kMask);
             }
@@ -195,10 +195,29 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
     }
+    // producer tail: peers' MMA warps still arrive (multicast commit) on this CTA's `empty`
+    // barriers for the last ring pass; do not let the CTA exit before those have landed.
+    if (CM > 1 && p.mc) {
+      for (int k = 0; k < kStages; ++k, ++it) {
+        const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      }
+    }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     // Warp-uniform control flow; one elected lane issues tcgen05.mma / commit.
-    uint32_t it = 0;
+    // running pipeline-stage state (no div/mod, no descriptor rebuilds in the hot loop)
+    uint32_t st_i = 0, st_ph = 0;
+    const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+    // NB: inside a cluster the shared-window address carries the CTA rank in its upper bits
+    // (rank 1: 0x01000400); matrix descriptors take the CTA-local 18-bit offset only.
+    const uint32_t a16_0 = (s_stage & 0x3FFFF) >> 4;
+    uint32_t st_full = full0, st_empty = empty0, st_a16 = a16_0;   // stage base address >> 4
+    auto advance = [&]() {
+      if (++st_i == kStages) { st_i = 0; st_ph ^= 1; st_full = full0; st_empty = empty0; st_a16 = a16_0; }
+      else { st_full += 8; st_empty += 8; st_a16 += kStageBytes >> 4; }
+    };
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, version 1, SWIZZLE_128B
     uint32_t ph_act1_0 = 0, ph_act1_1 = 0, ph_act2_0 = 0, ph_act2_1 = 0;
     uint32_t l3_issued0 = 0, l3_issued1 = 0, l3_waited0 = 0, l3_waited1 = 0;
     uint32_t w3_n = 0;
@@ -259,21 +278,25 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (c == 1) flush_all();        // everything that still reads region 1 / W3 of the previous unit
         else flush_buf(0);
         wait_drained(c);                // region c is free once its last L3 partial was drained
-        for (int kb = 0; kb < kb1; ++kb, ++it) {
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(smem_u32(&bars->full[st]), ph);
+        for (int kb = 0; kb < kb1; ++kb) {
+          mbar_wait(st_full, st_ph);
           fence_after_sync();
-          const int ksteps = min(4, (K0 - kb * 64 + 15) / 16);
           if (elect_one()) {
-            const uint32_t base = s_stage + st * kStageBytes;
-            const uint64_t adesc = make_smem_desc(base, 16, 1024, SW_128B);
-            const uint64_t bdesc = make_smem_desc(base + kXBytes, kBlkBytes, 1024, SW_128B);
+            const uint32_t a_lo = st_a16 | (1u << 16);                               // A: X block, K-major
+            const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);  // B: LBO = n-block stride
+            if (kb + 1 < kb1 || (K0 & 63) == 0) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              if (kk < ksteps) mma_ss(dreg, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 128), idesc, (kb | kk) > 0);
-            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
+              for (int kk = 0; kk < 4; ++kk)
+                mma_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+            } else {
+              const int ksteps = ((K0 & 63) + 15) >> 4;
+              for (int kk = 0; kk < ksteps; ++kk)
+                mma_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+            }
+            if (CM == 1 || !p.mc) mma_commit(st_empty); else mma_commit_mc(st_empty, kMask);
           }
           __syncwarp();
+          advance();
           pump(false);
         }
         if (elect_one()) mma_commit(smem_u32(&bars->acc_full[c]));
@@ -292,27 +315,26 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t dbuf = tmem + b * 256 + 128;
         flush_buf(b);      // buffer b must be free: force its pending L3 partial out ...
         wait_drained(b);   // ... and wait until the epilogue drained it
-        for (int sg = 0; sg < l2_stages; ++sg, ++it) {
-          const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+        for (int sg = 0; sg < l2_stages; ++sg) {
           // the A operand of k-blocks [2sg, 2sg+1] lives in region (sg*128)/256
-          if (j == 0 && (sg * 128) % 256 == 0) {  // first touch of that region in this unit
-            if ((sg * 128) / 256 == 0) { mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
+          if (j == 0 && (sg & 1) == 0) {  // first touch of that region in this unit
+            if ((sg >> 1) == 0) { mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
             else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
           }
-          mbar_wait(smem_u32(&bars->full[st]), ph);
+          mbar_wait(st_full, st_ph);
           fence_after_sync();
           if (elect_one()) {
-            const uint32_t base = s_stage + st * kStageBytes + kXBytes;
-            const uint64_t bdesc = make_smem_desc(base, kBlkBytes, 1024, SW_128B);
-            const int kabs0 = sg * 2;                        // first 64-wide k-block of this stage
-            const uint32_t a0 = tmem + (uint32_t)((kabs0 * 64) / 256) * 256 + (uint32_t)(((kabs0 * 64) % 256) / 2);
+            const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
+            // 128 consecutive k of packed H1: region sg>>1, packed column (sg&1)*64
+            const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
 #pragma unroll
             for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk; consecutive 16-wide k-steps are 8 TMEM columns apart
-              mma_ts(dbuf, a0 + i * 8, bdesc + (uint64_t)((i >> 2) * (2 * kBlkBytes / 16) + (i & 3) * 128), idesc_l2,
-                     (sg | i) > 0);
-            if (CM == 1) mma_commit(smem_u32(&bars->empty[st])); else mma_commit_mc(smem_u32(&bars->empty[st]), kMask);
+              mma_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (2 * kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2,
+                        (sg | i) > 0);
+            if (CM == 1 || !p.mc) mma_commit(st_empty); else mma_commit_mc(st_empty, kMask);
           }
           __syncwarp();
+          advance();
           pump(false);
         }
         if (elect_one()) mma_commit(smem_u32(&bars->acc2_full[b]));
@@ -604,7 +626,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   };
   if (!make_w(&tmW1, dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
   if (!make_w(&tmW2, NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
-  if (!make_w(&tmW3, Lout, 8, (uint32_t)std::min(256, H), CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
+  if (!make_w(&tmW3, Lout, 8, 128, CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
 
   const int smem = kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024;
 
@@ -619,6 +641,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
 
     FusedParams p = {};
     p.K0 = K0; p.H = H; p.NH = NH; p.C = C; p.B = (int)B; p.ns = nc; p.CM = CM;
+    p.mc = 1; if (const char* e = getenv("DBX_FUSED_MC")) p.mc = atoi(e);
     p.Q = Q; p.U = (long long)Q * nc;
     p.NC = (int)std::min<long long>(NCmax, std::max<long long>(1, p.U));
     p.maxseg = maxseg;

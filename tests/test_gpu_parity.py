@@ -247,6 +247,47 @@ def test_sample_split_independence(ctx):
     np.testing.assert_array_equal(cnt, c1 + c2)
 
 
+@pytest.mark.parametrize("cm", ["1", "2", "4"])
+@pytest.mark.parametrize("dims,B,n", [([784, 512, 512, 10], 1000, 70), ([784, 512, 10], 700, 33), ([784, 128, 10], 300, 20),
+                                       ([100, 256, 256, 7], 513, 40), ([784, 384, 384, 10], 260, 12)])
+def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n):
+    """The tcgen05 fused kernel (cluster multicast widths 1/2/4, ragged row tiles, several chunks
+    and work segments) against the plain CUDA-core bf16 path on the same Philox draws: both round
+    the GEMM operands to bf16 and accumulate in fp32, so they agree to accumulation order."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    L = oracle.mlp(dims)
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    eng = Engine(db.Sequential(layers))
+    mean, std = oracle.synthetic_posterior(L, seed=5, sigma_scale=0.5)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=6)
+    monkeypatch.setenv("DBX_NO_FUSED", "1")
+    g1, g2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
+    assert eng.last_path() == "generic"
+    monkeypatch.setenv("DBX_NO_FUSED", "0")
+    monkeypatch.setenv("DBX_FUSED_CM", cm)
+    monkeypatch.setenv("DBX_FUSED_NS", "16")   # several chunks -> accumulate path of finish_kernel
+    for rep in range(3):
+        f1, f2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
+        assert eng.last_path() == "fused_tcgen05"
+        np.testing.assert_allclose((f1 / n).cpu().numpy(), (g1 / n).cpu().numpy(), rtol=0, atol=1.5e-3)
+        np.testing.assert_allclose((f2 / n).cpu().numpy(), (g2 / n).cpu().numpy(), rtol=0, atol=1.5e-3)
+        if rep == 0:
+            first = f1.clone()
+        else:  # deterministic: bit-identical run to run
+            assert bool((f1 == first).all())
+    lab = np.random.Generator(np.random.Philox(1)).integers(0, dims[-1], size=B).astype(np.int32)
+    cf, ff = eng.count_predicate(x, lab, n, seed=17, s0=3, mode="bf16", return_flags=True)
+    monkeypatch.setenv("DBX_NO_FUSED", "1")
+    cg, fg = eng.count_predicate(x, lab, n, seed=17, s0=3, mode="bf16", return_flags=True)
+    assert (ff != fg).float().mean().item() < 5e-3
+    np.testing.assert_array_equal(cf.cpu().numpy(), ff.sum(0).cpu().numpy())
+
+
 def test_mc_converges_to_oracle_mc(ctx, oracle):
     """Philox path (no injected eps): the MC mean over many samples agrees with the oracle's
     MC mean over its own RNG to within the Monte-Carlo standard error."""
