@@ -91,56 +91,62 @@ __global__ void sample_f32_kernel(const float* __restrict__ mu, const float* __r
 
 // Same draw, scattered into the bf16 device layout (kernels -> padded bf16 rows, biases ->
 // fp32 side array).  src != nullptr converts stored samples instead (rows idx[s] / j0+s).
-__global__ void sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
-                                   const float* __restrict__ eps, float inflate, uint64_t seed, int64_t s0,
-                                   int64_t n, int64_t P, const float* __restrict__ src, const int32_t* __restrict__ idx,
-                                   int64_t j0row, TensorTable tab, __nv_bfloat16* __restrict__ W16, int64_t P16,
-                                   float* __restrict__ B32, int64_t PB) {
-  const int64_t nblk = (P + 3) >> 2;
-  const int64_t total = n * nblk;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = t / nblk, blk = t - s * nblk;
-    const int64_t j0 = blk << 2;
+// grid = (blocks over Philox blocks, samples); one thread = 4 consecutive flat elements.
+__global__ void __launch_bounds__(256)
+sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
+                   float inflate, uint64_t seed, int64_t s0, int P, const float* __restrict__ src,
+                   const int32_t* __restrict__ idx, int64_t j0row, const TensorTable tab,
+                   __nv_bfloat16* __restrict__ W16, int64_t P16, float* __restrict__ B32, int64_t PB) {
+  const int s = blockIdx.y;
+  const int nblk = (P + 3) >> 2;
+  const uint64_t sample = (uint64_t)(s0 + s);
+  const float* srow = src ? src + (idx ? (int64_t)idx[s] : (j0row + s)) * (int64_t)P : nullptr;
+  const float* erow = eps ? eps + (int64_t)s * P : nullptr;
+  __nv_bfloat16* wrow = W16 + (int64_t)s * P16;
+  float* brow = B32 + (int64_t)s * PB;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x) {
+    const int j0 = blk << 2;
+    const bool full4 = (j0 + 4 <= P);
     float w[4];
-    if (src) {
-      const int64_t row = idx ? (int64_t)idx[s] : (j0row + s);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = (j0 + i < P) ? src[row * P + j0 + i] : 0.f;
+    if (srow) {
+      if (full4 && (P & 3) == 0) { const float4 v = *reinterpret_cast<const float4*>(srow + j0); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+      else { for (int i = 0; i < 4; ++i) w[i] = (j0 + i < P) ? srow[j0 + i] : 0.f; }
     } else {
       float z[4];
-      if (eps == nullptr) philox_normal4(seed, (uint64_t)(s0 + s), (uint64_t)blk, z);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t j = j0 + i;
-        if (j < P) {
-          const float e = eps ? eps[s * P + j] : z[i];
-          w[i] = fmaf(inflate * sigma[j], e, mu[j]);
-        } else w[i] = 0.f;
+      if (erow == nullptr) philox_normal4(seed, sample, (uint64_t)blk, z);
+      else { for (int i = 0; i < 4; ++i) z[i] = (j0 + i < P) ? erow[j0 + i] : 0.f; }
+      if (full4) {
+        const float4 m4 = *reinterpret_cast<const float4*>(mu + j0);
+        const float4 s4 = *reinterpret_cast<const float4*>(sigma + j0);
+        w[0] = fmaf(inflate * s4.x, z[0], m4.x); w[1] = fmaf(inflate * s4.y, z[1], m4.y);
+        w[2] = fmaf(inflate * s4.z, z[2], m4.z); w[3] = fmaf(inflate * s4.w, z[3], m4.w);
+      } else {
+        for (int i = 0; i < 4; ++i) w[i] = (j0 + i < P) ? fmaf(inflate * sigma[j0 + i], z[i], mu[j0 + i]) : 0.f;
       }
     }
+    // which tensor holds element j0 (branch-free count over the <=16 table entries)
     int ti = 0;
-    while (ti + 1 < tab.n && j0 >= tab.src_off[ti] + tab.size[ti]) ++ti;
-    const int64_t rel = j0 - tab.src_off[ti];
-    if (!tab.is_bias[ti] && tab.cols_pad[ti] == tab.cols[ti] && rel + 4 <= tab.size[ti]) {
-      // fast path: 4 elements of an unpadded kernel tensor -> one 8-byte store
-      __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(w[2], w[3]);
-      uint2 v;
-      v.x = *reinterpret_cast<uint32_t*>(&lo);
-      v.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(W16 + s * P16 + tab.dst_off[ti] + rel) = v;
-    } else {
 #pragma unroll
+    for (int i = 0; i < DBX_MAX_TENSORS - 1; ++i) ti += (i + 1 < tab.n && j0 >= tab.src_off[i] + tab.size[i]) ? 1 : 0;
+    const int rel = j0 - tab.src_off[ti];
+    if (!tab.is_bias[ti] && !tab.blocked8[ti] && tab.cols_pad[ti] == tab.cols[ti] && rel + 4 <= tab.size[ti]) {
+      // fast path: 4 elements of an unpadded kernel tensor -> one 8-byte store
+      uint2 v;
+      v.x = tc_pack_bf16x2(w[0], w[1]);
+      v.y = tc_pack_bf16x2(w[2], w[3]);
+      *reinterpret_cast<uint2*>(wrow + tab.dst_off[ti] + rel) = v;
+    } else {
       for (int i = 0; i < 4; ++i) {
-        const int64_t j = j0 + i;
+        const int j = j0 + i;
         if (j >= P) break;
         while (ti + 1 < tab.n && j >= tab.src_off[ti] + tab.size[ti]) ++ti;
-        const int64_t r = j - tab.src_off[ti];
+        const int r = j - tab.src_off[ti];
         if (tab.is_bias[ti]) {
-          B32[s * PB + tab.dst_off[ti] + r] = w[i];
+          brow[tab.dst_off[ti] + r] = w[i];
         } else {
-          const int64_t row = r / tab.cols[ti], col = r - row * tab.cols[ti];
-          W16[s * P16 + tab.dst_off[ti] + row * tab.cols_pad[ti] + col] = __float2bfloat16_rn(w[i]);
+          const int row = r / tab.cols[ti], col = r - row * tab.cols[ti];
+          const int d = tab.blocked8[ti] ? (((col >> 3) * tab.rows[ti] + row) * 8 + (col & 7)) : (row * tab.cols_pad[ti] + col);
+          wrow[tab.dst_off[ti] + d] = __float2bfloat16_rn(w[i]);
         }
       }
     }
@@ -373,11 +379,14 @@ static inline int grid_for(int64_t total, int block = 256) {
 // Generic executor (all layer kinds; T = storage type of weights/activations)
 // ---------------------------------------------------------------------------------------
 
-int launch_sample_bf16(dbx_model* m, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16, float* B32, cudaStream_t st) {
-  const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
-  DBX_LAUNCH(sample_bf16_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma,
-             (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int64_t)nc, m->P,
-             src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, m->table, W16,
+int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
+                       float* B32, cudaStream_t st) {
+  const int nblk = (int)((m->P + 3) / 4);
+  // 2 Philox blocks per thread keeps ~1300 CTAs x nc in flight without a long grid-stride tail
+  dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(nblk, 256), 148 * 4)), (unsigned)nc);
+  DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
+             (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
+             src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, tab, W16,
              m->P16, B32, m->PB);
   return 0;
 }
@@ -424,7 +433,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
     const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
     const float* Bbase; int64_t b_sstride;
     if (kBf16) {
-      if (launch_sample_bf16(m, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
+      if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
       Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
     } else if (src.stored) {
       Wbase = (const T*)m->slab; w_sstride = m->P; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
@@ -572,6 +581,7 @@ int dbx_create(const dbx_layer_desc* layers, int32_t n_layers, const int32_t* in
   else feat = input_shape[0];
   m->in_feat = feat; m->max_feat = feat;
   int64_t off = 0, off16 = 0, offb = 0;
+  memset(&m->table, 0, sizeof m->table);
   m->table.n = 0; m->is_mlp = true;
   for (int i = 0; i < n_layers; ++i) {
     const dbx_layer_desc& d = layers[i];
@@ -611,10 +621,12 @@ int dbx_create(const dbx_layer_desc* layers, int32_t n_layers, const int32_t* in
       L.w16_off = off16; off16 += round_up(L.w_rows * L.w_cols_pad, 64);
       L.b32_off = offb; offb += round_up(L.w_cols, 4);
       TensorTable& T = m->table;
-      T.src_off[T.n] = L.w_off; T.size[T.n] = L.w_rows * L.w_cols; T.dst_off[T.n] = L.w16_off;
-      T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols_pad; T.is_bias[T.n] = 0; ++T.n;
-      T.src_off[T.n] = L.b_off; T.size[T.n] = L.w_cols; T.dst_off[T.n] = L.b32_off;
-      T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols; T.is_bias[T.n] = 1; ++T.n;
+      T.src_off[T.n] = (int32_t)L.w_off; T.size[T.n] = (int32_t)(L.w_rows * L.w_cols); T.dst_off[T.n] = (int32_t)L.w16_off;
+      T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols_pad; T.rows[T.n] = (int)L.w_rows;
+      T.is_bias[T.n] = 0; T.blocked8[T.n] = 0; ++T.n;
+      T.src_off[T.n] = (int32_t)L.b_off; T.size[T.n] = (int32_t)L.w_cols; T.dst_off[T.n] = (int32_t)L.b32_off;
+      T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols; T.rows[T.n] = 1;
+      T.is_bias[T.n] = 1; T.blocked8[T.n] = 0; ++T.n;
       m->flops += 2 * L.w_rows * L.w_cols * (L.kind == DBX_CONV2D ? (int64_t)L.out_h * L.out_w : 1);
       m->last_weighted = i;
     }
@@ -625,6 +637,7 @@ int dbx_create(const dbx_layer_desc* layers, int32_t n_layers, const int32_t* in
   if (m->last_weighted < 0) { delete m; return set_err("model has no weighted layer"); }
   for (int i = m->last_weighted + 1; i < n_layers; ++i)
     if (m->layers[i].kind != DBX_FLATTEN) { delete m; return set_err("layers after the last weighted layer are not supported"); }
+  if (off >= (1ll << 31) - 8 || off16 >= (1ll << 31) - 8) { delete m; return set_err("model too large (> 2^31 parameters)"); }
   m->P = off; m->P16 = off16; m->PB = offb; m->out_feat = m->layers[m->last_weighted].out_feat;
   if (cudaMalloc(&m->mu, (size_t)m->P * 4) != cudaSuccess || cudaMalloc(&m->sigma, (size_t)m->P * 4) != cudaSuccess) {
     delete m; return set_err("cudaMalloc of posterior buffers failed");

@@ -21,15 +21,19 @@ struct Layer {
 
 // One entry per Keras tensor, used by the sampling / conversion kernels to scatter the flat
 // Keras-order element index into the bf16 device layout.
-#define DBX_MAX_TENSORS 32
+#define DBX_MAX_TENSORS 16
 struct TensorTable {
   int n;
-  int64_t src_off[DBX_MAX_TENSORS];   // start in flat Keras order
-  int64_t size[DBX_MAX_TENSORS];
-  int64_t dst_off[DBX_MAX_TENSORS];   // start in bf16 weight layout (kernels) or bias array (biases)
+  int32_t src_off[DBX_MAX_TENSORS];   // start in flat Keras order
+  int32_t size[DBX_MAX_TENSORS];
+  int32_t dst_off[DBX_MAX_TENSORS];   // start in bf16 weight layout (kernels) or bias array (biases)
   int32_t cols[DBX_MAX_TENSORS];
   int32_t cols_pad[DBX_MAX_TENSORS];
-  int32_t is_bias[DBX_MAX_TENSORS];
+  int32_t rows[DBX_MAX_TENSORS];
+  int8_t is_bias[DBX_MAX_TENSORS];
+  // blocked8: element (k, n) of a kernel tensor goes to dst_off + ((n>>3)*rows + k)*8 + (n&7): the
+  // tcgen05 no-swizzle core-matrix order, so the fused kernel fetches it with ONE bulk copy
+  int8_t blocked8[DBX_MAX_TENSORS];
 };
 
 struct Workspace {
@@ -93,7 +97,8 @@ void prof_end(cudaStream_t st, double flops);
 // Materialise the chunk's per-sample weights in the bf16 device layout (kernels -> W16 [nc,P16]
 // padded bf16, biases -> B32 [nc,PB] fp32): Gaussian draw (injected eps or Philox) or conversion
 // of stored samples.  Defined in engine.cu.
-int launch_sample_bf16(dbx_model* m, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16, float* B32, cudaStream_t st);
+int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
+                       float* B32, cudaStream_t st);
 
 // fused_mlp.cu: returns 1 if the tcgen05 fused path handled the request, 0 if the shape is
 // not supported by it (caller uses the generic kernels), <0 on error.

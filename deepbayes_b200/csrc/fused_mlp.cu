@@ -60,6 +60,9 @@ struct FusedParams {
   uint8_t* flags;              // [ns, B] or null
   unsigned long long* counts;  // [B]
   float* partial;              // [NC][maxseg][CM*128][2][16]
+  const __nv_bfloat16* w3;     // last-layer kernels of the chunk, blocked8 layout: sample s at w3 + s*P16
+  long long P16; int w3_bytes;
+  long long* trace;            // debug timeline of block 0 (null in production): [0]=count, then (id, clock) pairs
 };
 
 struct __align__(8) Barriers {
@@ -74,6 +77,16 @@ struct __align__(8) Barriers {
 
 extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
 
+// debug timeline (block 0 only): each traced warp appends (id, clock) to its own lane of the
+// buffer with a private counter -- no atomics, so the probe costs a clock read and two stores.
+#define DBX_TRACE(id)                                                                         \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n < 2600) { \
+      long long* _t = p.trace + 1 + (threadIdx.x >> 5) * 5200 + 2 * trace_n;                  \
+      _t[0] = (id); _t[1] = clock64(); ++trace_n;                                             \
+    }                                                                                         \
+  } while (0)
+
 template <int CM>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -87,6 +100,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   Barriers* bars = (Barriers*)(smem + kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int trace_n = 0;
   const uint32_t rank = (CM > 1) ? cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CM;
   constexpr uint16_t kMask = (uint16_t)((1u << CM) - 1);
@@ -165,10 +179,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
           if (elect_one()) {
             const uint32_t wf = smem_u32(&bars->w3_full);
-            mbar_expect_tx(wf, (uint32_t)(H * 32));
-            for (int nb = 0; nb < 2; ++nb)
-              for (int k0 = 0; k0 < H; k0 += 128)   // boxes of [8 n x 128 k] = 2 KB
-                tma_load_3d(s_w3 + nb * (H * 16) + k0 * 16, &tmW3, wf, nb * 8, k0, s);
+            mbar_expect_tx(wf, (uint32_t)p.w3_bytes);
+            bulk_load(s_w3, p.w3 + (long long)s * p.P16, (uint32_t)p.w3_bytes, wf);   // already in core-matrix order
           }
           __syncwarp();
           ++w3_n;
@@ -240,6 +252,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       else if (!mbar_try_wait(bar, ph & 1)) return false;
       if (pkind0 == 1) { if (pb0) ++ph_act1_1; else ++ph_act1_0; } else { if (pb0) ++ph_act2_1; else ++ph_act2_0; }
       fence_after_sync();
+      DBX_TRACE(140);
       if (elect_one()) {
         const uint64_t bd = w3desc0 + (uint64_t)(pw0 >> 4);
         for (int kk = 0; kk < pk0; ++kk) mma_ts(pd0, pa0 + kk * 8, bd + (uint64_t)(kk * 16), idesc_l3, kk > 0);
@@ -278,6 +291,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (c == 1) flush_all();        // everything that still reads region 1 / W3 of the previous unit
         else flush_buf(0);
         wait_drained(c);                // region c is free once its last L3 partial was drained
+        DBX_TRACE(100 + c);
         for (int kb = 0; kb < kb1; ++kb) {
           mbar_wait(st_full, st_ph);
           fence_after_sync();
@@ -301,6 +315,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (elect_one()) mma_commit(smem_u32(&bars->acc_full[c]));
         __syncwarp();
+        DBX_TRACE(110 + c);
         if (c == 0) {
           flush_all();  // releases W3 of the previous unit (the producer waits for it here)
           mbar_wait(smem_u32(&bars->w3_full), w3_n & 1);
@@ -315,6 +330,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t dbuf = tmem + b * 256 + 128;
         flush_buf(b);      // buffer b must be free: force its pending L3 partial out ...
         wait_drained(b);   // ... and wait until the epilogue drained it
+        DBX_TRACE(120 + j);
         for (int sg = 0; sg < l2_stages; ++sg) {
           // the A operand of k-blocks [2sg, 2sg+1] lives in region (sg*128)/256
           if (j == 0 && (sg & 1) == 0) {  // first touch of that region in this unit
@@ -339,6 +355,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (elect_one()) mma_commit(smem_u32(&bars->acc2_full[b]));
         __syncwarp();
+        DBX_TRACE(130 + j);
         push(b, dbuf, dbuf + 64, (uint32_t)(j * 128 * 16), 8, j == n_l2 - 1, 2);
       }
     }
@@ -423,8 +440,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(smem_u32(&bars->acc_full[c]), ph_acc[c] & 1);
         ++ph_acc[c];
         fence_after_sync();
+        if (warp == 2) DBX_TRACE(200 + c);
         pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
         mbar_arrive(smem_u32(&bars->act1_ready[c]));
+        if (warp == 2) DBX_TRACE(210 + c);
         if (NH == 1) drain_l3(c, tmem + lane_base + c * 256 + 128);
       }
       for (int j = 0; j < n_l2; ++j) {
@@ -432,9 +451,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(smem_u32(&bars->acc2_full[b]), ph_acc2[b] & 1);
         ++ph_acc2[b];
         fence_after_sync();
+        if (warp == 2) DBX_TRACE(220 + j);
         pack_chunk(tmem + lane_base + b * 256 + 128, 128, bias + p.b2_off + j * 128);
         mbar_arrive(smem_u32(&bars->act2_ready[b]));
+        if (warp == 2) DBX_TRACE(230 + j);
         drain_l3(b, tmem + lane_base + b * 256 + 128 + 64);
+        if (warp == 2) DBX_TRACE(240 + j);
       }
       // ---------------- output: + b3, softmax / linear, running sums over this CTA's samples
       const float* b3 = bias + p.b3_off;
@@ -520,6 +542,8 @@ __global__ void cast_rows_bf16_kernel(const float* __restrict__ in, __nv_bfloat1
 __global__ void zero_counts_kernel(unsigned long long* p, int64_t n) {
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) p[o] = 0ULL;
 }
+
+long long* g_trace_buf = nullptr;
 
 struct FusedState {
   int num_sms = 0;
@@ -626,7 +650,12 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   };
   if (!make_w(&tmW1, dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
   if (!make_w(&tmW2, NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
-  if (!make_w(&tmW3, Lout, 8, 128, CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
+  tmW3 = tmW2;  // unused: W3 is fetched with a plain bulk copy (blocked8 layout)
+
+  // the last layer's kernel goes out in tcgen05 core-matrix order (one bulk copy per sample)
+  TensorTable tab = m->table;
+  for (int i = 0; i < tab.n; ++i)
+    if (!tab.is_bias[i] && tab.src_off[i] == (int32_t)Lout->w_off) tab.blocked8[i] = 1;
 
   const int smem = kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024;
 
@@ -637,7 +666,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
 
   for (int64_t c0 = 0; c0 < n; c0 += ns) {
     const int nc = (int)std::min<int64_t>(ns, n - c0);
-    if (launch_sample_bf16(m, src, c0, nc, W16, B32, st)) return -1;
+    if (launch_sample_bf16(m, tab, src, c0, nc, W16, B32, st)) return -1;
 
     FusedParams p = {};
     p.K0 = K0; p.H = H; p.NH = NH; p.C = C; p.B = (int)B; p.ns = nc; p.CM = CM;
@@ -651,6 +680,9 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     p.wts = sink.wts ? sink.wts + c0 : nullptr;
     p.labels = sink.labels; p.flags = sink.flags ? sink.flags + c0 * B : nullptr; p.counts = sink.counts;
     p.partial = partial;
+    p.w3 = W16 + Lout->w16_off; p.P16 = m->P16; p.w3_bytes = (int)(Lout->w_rows * Lout->w_cols_pad * 2);
+    p.trace = nullptr;
+    if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
     prof_begin(st);
     int rc = 0;
     if (CM == 1) rc = launch_fused<1>(tmX, tmW1, tmW2, tmW3, p, smem, st);
@@ -667,6 +699,22 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     }
   }
   return 1;
+}
+
+// debug: copy the timeline of the last traced launch to the host (count, then (id, clock) pairs)
+extern "C" __attribute__((visibility("default"))) int dbx_debug_trace(long long* out, int max_pairs) {
+  if (!g_trace_buf) return 0;
+  cudaDeviceSynchronize();
+  static long long host[31208];
+  cudaMemcpy(host, g_trace_buf, sizeof host, cudaMemcpyDeviceToHost);
+  int cnt = 0;
+  for (int w = 0; w < 6; ++w)
+    for (int i = 0; i < 2600 && cnt < max_pairs; ++i) {
+      const long long* e = host + 1 + w * 5200 + 2 * i;
+      if (e[1] == 0) break;
+      out[2 * cnt] = e[0]; out[2 * cnt + 1] = e[1]; ++cnt;
+    }
+  return cnt;
 }
 
 void fused_mlp_free(dbx_model* m) {
