@@ -95,7 +95,7 @@ __global__ void sample_f32_kernel(const float* __restrict__ mu, const float* __r
 __global__ void __launch_bounds__(256)
 sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
                    float inflate, uint64_t seed, int64_t s0, int P, const float* __restrict__ src,
-                   const int32_t* __restrict__ idx, int64_t j0row, const TensorTable tab,
+                   const int32_t* __restrict__ idx, int64_t j0row, const TensorTable tab, const BlockRanges rg,
                    __nv_bfloat16* __restrict__ W16, int64_t P16, float* __restrict__ B32, int64_t PB) {
   const int s = blockIdx.y;
   const int nblk = (P + 3) >> 2;
@@ -104,7 +104,11 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
   const float* erow = eps ? eps + (int64_t)s * P : nullptr;
   __nv_bfloat16* wrow = W16 + (int64_t)s * P16;
   float* brow = B32 + (int64_t)s * PB;
-  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x) {
+  (void)nblk;
+  for (int ri = 0; ri < rg.n; ++ri) {
+  int tfirst = 0;
+  for (int blk = rg.lo[ri] + blockIdx.x * blockDim.x + threadIdx.x; blk - (int)threadIdx.x < rg.hi[ri]; blk += gridDim.x * blockDim.x) {
+    if (blk >= rg.hi[ri]) continue;
     const int j0 = blk << 2;
     const bool full4 = (j0 + 4 <= P);
     float w[4];
@@ -124,10 +128,14 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
         for (int i = 0; i < 4; ++i) w[i] = (j0 + i < P) ? fmaf(inflate * sigma[j0 + i], z[i], mu[j0 + i]) : 0.f;
       }
     }
-    // which tensor holds element j0 (branch-free count over the <=16 table entries)
-    int ti = 0;
-#pragma unroll
-    for (int i = 0; i < DBX_MAX_TENSORS - 1; ++i) ti += (i + 1 < tab.n && j0 >= tab.src_off[i] + tab.size[i]) ? 1 : 0;
+    // which tensor holds element j0: the 1024 elements of this block iteration usually sit in
+    // one tensor (block-uniform test), otherwise count the tensor ends below j0
+    const int jb = (blk - (int)threadIdx.x) << 2;
+    int ti = tfirst;
+    while (ti + 1 < tab.n && jb >= tab.src_end[ti]) ++ti;   // uniform: advances rarely
+    tfirst = ti;
+    if (jb + 1024 > tab.src_end[ti])
+      for (int i = ti; i + 1 < tab.n; ++i) ti += (j0 >= tab.src_end[i]) ? 1 : 0;
     const int rel = j0 - tab.src_off[ti];
     if (!tab.is_bias[ti] && !tab.blocked8[ti] && tab.cols_pad[ti] == tab.cols[ti] && rel + 4 <= tab.size[ti]) {
       // fast path: 4 elements of an unpadded kernel tensor -> one 8-byte store
@@ -139,7 +147,7 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
       for (int i = 0; i < 4; ++i) {
         const int j = j0 + i;
         if (j >= P) break;
-        while (ti + 1 < tab.n && j >= tab.src_off[ti] + tab.size[ti]) ++ti;
+        while (ti + 1 < tab.n && j >= tab.src_end[ti]) ++ti;
         const int r = j - tab.src_off[ti];
         if (tab.is_bias[ti]) {
           brow[tab.dst_off[ti] + r] = w[i];
@@ -150,6 +158,28 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
         }
       }
     }
+  }
+  }
+}
+
+// Fast path for one large, unpadded kernel tensor whose flat range is 4-aligned: Philox block ->
+// 4 normals -> W = mu + sigma*eps -> one 8-byte bf16 store.  No table, no division.
+__global__ void __launch_bounds__(256)
+sample_bf16_fast_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, float inflate, uint64_t seed,
+                        int64_t s0, int blk_lo, int blk_hi, int dst_delta, __nv_bfloat16* __restrict__ W16,
+                        int64_t P16) {
+  const uint64_t sample = (uint64_t)(s0 + blockIdx.y);
+  __nv_bfloat16* wrow = W16 + (int64_t)blockIdx.y * P16 + dst_delta;   // dst index = flat index + dst_delta
+  for (int blk = blk_lo + blockIdx.x * blockDim.x + threadIdx.x; blk < blk_hi; blk += gridDim.x * blockDim.x) {
+    float z[4];
+    philox_normal4(seed, sample, (uint64_t)blk, z);
+    const int j0 = blk << 2;
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + j0));
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sigma + j0));
+    uint2 v;
+    v.x = tc_pack_bf16x2(fmaf(inflate * s4.x, z[0], m4.x), fmaf(inflate * s4.y, z[1], m4.y));
+    v.y = tc_pack_bf16x2(fmaf(inflate * s4.z, z[2], m4.z), fmaf(inflate * s4.w, z[3], m4.w));
+    *reinterpret_cast<uint2*>(wrow + j0) = v;
   }
 }
 
@@ -382,12 +412,33 @@ static inline int grid_for(int64_t total, int block = 256) {
 int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
                        float* B32, cudaStream_t st) {
   const int nblk = (int)((m->P + 3) / 4);
-  // 2 Philox blocks per thread keeps ~1300 CTAs x nc in flight without a long grid-stride tail
-  dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(nblk, 256), 148 * 4)), (unsigned)nc);
-  DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
-             (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
-             src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, tab, W16,
-             m->P16, B32, m->PB);
+  BlockRanges rg; rg.n = 0;
+  const bool philox = !src.stored && !src.eps;
+  int cursor = 0;  // first Philox block not yet covered
+  if (philox) {
+    for (int i = 0; i < tab.n; ++i) {
+      const bool fast = !tab.is_bias[i] && !tab.blocked8[i] && tab.cols_pad[i] == tab.cols[i] && tab.size[i] >= 65536 &&
+                        ((tab.dst_off[i] - tab.src_off[i]) & 3) == 0;
+      if (!fast) continue;
+      const int lo = (tab.src_off[i] + 3) >> 2, hi = tab.src_end[i] >> 2;   // whole Philox blocks inside the tensor
+      if (hi <= lo || rg.n + 2 > DBX_MAX_RANGES) continue;
+      if (lo > cursor) { rg.lo[rg.n] = cursor; rg.hi[rg.n] = lo; ++rg.n; }
+      dim3 grid((unsigned)std::min<int64_t>(cdiv(hi - lo, 256), 148 * 4), (unsigned)nc);
+      DBX_LAUNCH(sample_bf16_fast_kernel, grid, 256, 0, st, m->mu, m->sigma, src.inflate, src.seed, src.s0 + c0, lo, hi,
+                 tab.dst_off[i] - tab.src_off[i], W16, m->P16);
+      cursor = hi;
+    }
+  }
+  if (cursor < nblk) { rg.lo[rg.n] = cursor; rg.hi[rg.n] = nblk; ++rg.n; }
+  if (rg.n > 0) {
+    int64_t most = 0;
+    for (int i = 0; i < rg.n; ++i) most = std::max<int64_t>(most, rg.hi[i] - rg.lo[i]);
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(most, 256), 148 * 4)), (unsigned)nc);
+    DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
+               (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
+               src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, tab, rg, W16,
+               m->P16, B32, m->PB);
+  }
   return 0;
 }
 
@@ -622,9 +673,11 @@ int dbx_create(const dbx_layer_desc* layers, int32_t n_layers, const int32_t* in
       L.b32_off = offb; offb += round_up(L.w_cols, 4);
       TensorTable& T = m->table;
       T.src_off[T.n] = (int32_t)L.w_off; T.size[T.n] = (int32_t)(L.w_rows * L.w_cols); T.dst_off[T.n] = (int32_t)L.w16_off;
+      T.src_end[T.n] = T.src_off[T.n] + T.size[T.n];
       T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols_pad; T.rows[T.n] = (int)L.w_rows;
       T.is_bias[T.n] = 0; T.blocked8[T.n] = 0; ++T.n;
       T.src_off[T.n] = (int32_t)L.b_off; T.size[T.n] = (int32_t)L.w_cols; T.dst_off[T.n] = (int32_t)L.b32_off;
+      T.src_end[T.n] = T.src_off[T.n] + T.size[T.n];
       T.cols[T.n] = (int)L.w_cols; T.cols_pad[T.n] = (int)L.w_cols; T.rows[T.n] = 1;
       T.is_bias[T.n] = 1; T.blocked8[T.n] = 0; ++T.n;
       m->flops += 2 * L.w_rows * L.w_cols * (L.kind == DBX_CONV2D ? (int64_t)L.out_h * L.out_w : 1);

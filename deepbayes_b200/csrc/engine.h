@@ -25,6 +25,7 @@ struct Layer {
 struct TensorTable {
   int n;
   int32_t src_off[DBX_MAX_TENSORS];   // start in flat Keras order
+  int32_t src_end[DBX_MAX_TENSORS];   // src_off + size
   int32_t size[DBX_MAX_TENSORS];
   int32_t dst_off[DBX_MAX_TENSORS];   // start in bf16 weight layout (kernels) or bias array (biases)
   int32_t cols[DBX_MAX_TENSORS];
@@ -34,6 +35,13 @@ struct TensorTable {
   // blocked8: element (k, n) of a kernel tensor goes to dst_off + ((n>>3)*rows + k)*8 + (n&7): the
   // tcgen05 no-swizzle core-matrix order, so the fused kernel fetches it with ONE bulk copy
   int8_t blocked8[DBX_MAX_TENSORS];
+};
+
+// Philox-block ranges [lo, hi) handled by the general sampling kernel
+#define DBX_MAX_RANGES 12
+struct BlockRanges {
+  int n;
+  int32_t lo[DBX_MAX_RANGES], hi[DBX_MAX_RANGES];
 };
 
 struct Workspace {

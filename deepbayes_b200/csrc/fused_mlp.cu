@@ -547,7 +547,9 @@ long long* g_trace_buf = nullptr;
 
 struct FusedState {
   int num_sms = 0;
-  bool attr_set[9] = {};
+  // weight sampling of chunk c+1 runs on a side stream while chunk c is in the fused kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_entry = nullptr, ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
 };
 
 static bool shape_supported(const dbx_model* m) {
@@ -596,6 +598,12 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete fs; return -1; }
     fs->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&fs->side, cudaStreamNonBlocking) != cudaSuccess) { delete fs; return -1; }
+    cudaEventCreateWithFlags(&fs->ev_entry, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&fs->ev_sampled[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&fs->ev_consumed[i], cudaEventDisableTiming);
+    }
     m->fused_state = fs;
   }
   std::vector<const Layer*> dl;
@@ -620,15 +628,15 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   const int NCmax = std::max(1, fs->num_sms / CM);
   const int maxseg = (int)cdiv(Q, NCmax) + 2;
   const size_t part_b = round_up((size_t)NCmax * maxseg * CM * 128 * 32 * 4, 1024);
-  const size_t need = x_b + w_b + b_b + part_b;
+  const size_t need = x_b + 2 * (w_b + b_b) + part_b;
   if (m->fused_ws.bytes < need) {
     if (ensure_ws(m->fused_ws, need)) return -1;
     if (cudaMemsetAsync(m->fused_ws.ptr, 0, need, st) != cudaSuccess) return -1;  // pad columns stay zero
   }
   char* wp = (char*)m->fused_ws.ptr;
   __nv_bfloat16* X16 = (__nv_bfloat16*)wp; wp += x_b;
-  __nv_bfloat16* W16 = (__nv_bfloat16*)wp; wp += w_b;
-  float* B32 = (float*)wp; wp += b_b;
+  __nv_bfloat16* W16buf[2]; float* B32buf[2];
+  for (int i = 0; i < 2; ++i) { W16buf[i] = (__nv_bfloat16*)wp; wp += w_b; B32buf[i] = (float*)wp; wp += b_b; }
   float* partial = (float*)wp;
 
   cast_rows_bf16_kernel<<<grid_for2(B * K0p), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
@@ -642,16 +650,18 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     uint32_t b[2] = {64, 128};
     if (!make_tmap_bf16(&tmX, X16, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
   }
-  auto make_w = [&](CUtensorMap* tm, const Layer* L, uint32_t bn, uint32_t bk, CUtensorMapSwizzle swz) {
-    uint64_t d[3] = {(uint64_t)L->w_cols_pad, (uint64_t)L->w_rows, (uint64_t)ns};
-    uint64_t s[2] = {(uint64_t)L->w_cols_pad * 2, (uint64_t)m->P16 * 2};
-    uint32_t b[3] = {bn, bk, 1};
-    return make_tmap_bf16(tm, W16 + L->w16_off, 3, d, s, b, swz);
-  };
-  if (!make_w(&tmW1, dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
-  if (!make_w(&tmW2, NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
-  tmW3 = tmW2;  // unused: W3 is fetched with a plain bulk copy (blocked8 layout)
-
+  CUtensorMap tmW1b[2], tmW2b[2];
+  for (int i = 0; i < 2; ++i) {
+    auto make_w = [&](CUtensorMap* tm, const Layer* L, uint32_t bn, uint32_t bk, CUtensorMapSwizzle swz) {
+      uint64_t d[3] = {(uint64_t)L->w_cols_pad, (uint64_t)L->w_rows, (uint64_t)ns};
+      uint64_t sb[2] = {(uint64_t)L->w_cols_pad * 2, (uint64_t)m->P16 * 2};
+      uint32_t b[3] = {bn, bk, 1};
+      return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 3, d, sb, b, swz);
+    };
+    if (!make_w(&tmW1b[i], dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
+    if (!make_w(&tmW2b[i], NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
+  }
+  (void)tmW1; (void)tmW2; (void)tmW3;
   // the last layer's kernel goes out in tcgen05 core-matrix order (one bulk copy per sample)
   TensorTable tab = m->table;
   for (int i = 0; i < tab.n; ++i)
@@ -664,9 +674,34 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     g_launches.fetch_add(1);
   }
 
-  for (int64_t c0 = 0; c0 < n; c0 += ns) {
+  // overlap: sampling runs one chunk ahead on the side stream (env DBX_FUSED_OVERLAP=0 disables)
+  bool overlap = true;
+  if (const char* e = getenv("DBX_FUSED_OVERLAP")) overlap = atoi(e) != 0;
+  cudaStream_t sst = overlap ? fs->side : st;
+  if (overlap) {
+    if (cudaEventRecord(fs->ev_entry, st) != cudaSuccess || cudaStreamWaitEvent(sst, fs->ev_entry, 0) != cudaSuccess) return -1;
+  }
+  const int64_t nchunks = cdiv(n, ns);
+  auto sample_chunk = [&](int64_t ci) -> int {
+    const int b = (int)(ci & 1);
+    const int64_t c0 = ci * ns;
     const int nc = (int)std::min<int64_t>(ns, n - c0);
-    if (launch_sample_bf16(m, tab, src, c0, nc, W16, B32, st)) return -1;
+    if (overlap && ci >= 2 && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
+    if (launch_sample_bf16(m, tab, src, c0, nc, W16buf[b], B32buf[b], sst)) return -1;
+    if (overlap && cudaEventRecord(fs->ev_sampled[b], sst) != cudaSuccess) return -1;
+    return 0;
+  };
+  if (sample_chunk(0)) return -1;
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t c0 = ci * ns;
+    const int bsel = (int)(ci & 1);
+    const int nc = (int)std::min<int64_t>(ns, n - c0);
+    if (ci + 1 < nchunks && sample_chunk(ci + 1)) return -1;   // next chunk's weights, concurrently
+    if (overlap && cudaStreamWaitEvent(st, fs->ev_sampled[bsel], 0) != cudaSuccess) return -1;
+    __nv_bfloat16* W16 = W16buf[bsel];
+    float* B32 = B32buf[bsel];
+    const CUtensorMap& tmW1c = tmW1b[bsel];
+    const CUtensorMap& tmW2c = tmW2b[bsel];
 
     FusedParams p = {};
     p.K0 = K0; p.H = H; p.NH = NH; p.C = C; p.B = (int)B; p.ns = nc; p.CM = CM;
@@ -685,9 +720,9 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
     prof_begin(st);
     int rc = 0;
-    if (CM == 1) rc = launch_fused<1>(tmX, tmW1, tmW2, tmW3, p, smem, st);
-    else if (CM == 2) rc = launch_fused<2>(tmX, tmW1, tmW2, tmW3, p, smem, st);
-    else rc = launch_fused<4>(tmX, tmW1, tmW2, tmW3, p, smem, st);
+    if (CM == 1) rc = launch_fused<1>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
+    else if (CM == 2) rc = launch_fused<2>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
+    else rc = launch_fused<4>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     if (rc) return -1;
     prof_end(st, (double)m->flops * (double)B * nc);
     if (sink.kind == 0) {
@@ -697,6 +732,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
       g_launches.fetch_add(1);
       if (cudaGetLastError() != cudaSuccess) { set_err("finish launch failed"); return -1; }
     }
+    if (overlap && cudaEventRecord(fs->ev_consumed[bsel], st) != cudaSuccess) return -1;
   }
   return 1;
 }
@@ -718,7 +754,13 @@ extern "C" __attribute__((visibility("default"))) int dbx_debug_trace(long long*
 }
 
 void fused_mlp_free(dbx_model* m) {
-  if (m->fused_state) { delete (FusedState*)m->fused_state; m->fused_state = nullptr; }
+  if (m->fused_state) {
+    FusedState* fs = (FusedState*)m->fused_state;
+    if (fs->side) cudaStreamDestroy(fs->side);
+    if (fs->ev_entry) cudaEventDestroy(fs->ev_entry);
+    for (int i = 0; i < 2; ++i) { if (fs->ev_sampled[i]) cudaEventDestroy(fs->ev_sampled[i]); if (fs->ev_consumed[i]) cudaEventDestroy(fs->ev_consumed[i]); }
+    delete fs; m->fused_state = nullptr;
+  }
 }
 
 }  // namespace dbx
