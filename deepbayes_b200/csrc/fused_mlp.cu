@@ -515,9 +515,13 @@ __global__ void finish_kernel(const float* __restrict__ partial, int NC, int max
     float a1 = overwrite ? 0.f : sum1[o];
     float a2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
     const long long lo = (long long)q * ns, hi = lo + ns;
-    for (int k = 0; k < NC; ++k) {
+    // clusters whose unit range [k*U/NC, (k+1)*U/NC) meets [lo, hi): a handful, found directly
+    int k0 = (int)((lo * NC) / U);
+    while (k0 > 0 && ((long long)k0 * U) / NC > lo) --k0;
+    for (int k = k0; k < NC; ++k) {
       const long long u0 = ((long long)k * U) / NC, u1 = ((long long)(k + 1) * U) / NC;
-      if (u1 <= lo || u0 >= hi || u0 >= u1) continue;
+      if (u0 >= hi) break;
+      if (u1 <= lo || u0 >= u1) continue;
       const int seg = q - (int)(u0 / ns);
       const float* src = partial + ((((long long)k * maxseg + seg) * CM + rank) * 128 + row) * 32;
       a1 += src[c];

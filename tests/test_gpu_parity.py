@@ -409,3 +409,37 @@ def test_predict_host_e2e(ctx, oracle):
     np.testing.assert_allclose(mean, (s1 / 8.0).cpu().numpy(), rtol=1e-6, atol=1e-7)
     mean2, var2 = eng.predict_host(c["x"], 8, seed=21, s0=0, mode="bf16", variance=True)
     assert np.abs(mean2 - mean).max() < BF16_ATOL and (var2 > -1e-6).all()
+
+
+def test_reference_run_vectors(golden_dir, oracle):
+    """CUDA path against the outputs of the reference's own source (tests/golden/reference_run.npz),
+    with the reference's global-RNG draws injected as eps."""
+    import deepbayes_b200 as db
+    ref = np.load(os.path.join(golden_dir, "reference_run.npz"))
+    p = os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior")
+    pm = db.PosteriorModel(p, mode="fp32")
+    x = oracle.synthetic_x((6, 1, 784), seed=0).astype(np.float64)
+    np.random.seed(20240601)
+    eps = np.stack([np.concatenate([np.random.standard_normal(t.shape).reshape(-1) for t in pm.posterior_mean]) for _ in range(7)])
+    s1, _ = pm._engine.predict_sums(x, 7, eps=eps.astype(np.float32), mode="fp32")
+    np.testing.assert_allclose((s1 / 7.0).cpu().numpy().reshape(6, 1, 10), ref["pm_predict_n7"], rtol=FP32_RTOL, atol=FP32_ATOL)
+    sl, _ = pm._engine.predict_sums(x, 5, eps=eps[:5].astype(np.float32), mode="fp32", out_kind="logits")
+    np.testing.assert_allclose((sl / 5.0).cpu().numpy().reshape(6, 1, 10), ref["pm_predict_logits_n5"], rtol=FP32_RTOL, atol=3e-6)
+    W = pm._engine.sample(1, eps=eps[6:7].astype(np.float32)).cpu().numpy()[0]
+    o1 = 784 * 128 + 128
+    np.testing.assert_allclose(W[o1:o1 + 1280].reshape(128, 10), ref["pm_weights_after_predict_W1"], rtol=1.2e-7, atol=1e-12)
+    pd = db.PosteriorModel(p, deterministic=True, mode="fp32")
+    np.testing.assert_allclose(pd.predict(x, n=50), ref["pm_det_predict"], rtol=FP32_RTOL, atol=FP32_ATOL)
+    pm.model.set_weights(pm.posterior_mean)
+    np.testing.assert_allclose(pm._predict_logits(x), ref["pm__predict_logits_nobias"], rtol=FP32_RTOL, atol=3e-6)
+    # Bayes-by-Backprop: compile + the sampling/forward half of step with the reference's noise
+    m = db.Sequential([db.Dense(24, activation="relu", input_shape=(30,)), db.Dense(10, activation="softmax")])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=16, inflate_prior=2.0)
+    assert opt.epochs == int(ref["bbb_epochs_after_compile"][0])
+    for i in range(4):
+        np.testing.assert_array_equal(opt.prior_var[i], ref["bbb_prior_var_%d" % i])
+        np.testing.assert_allclose(opt.posterior_var[i], ref["bbb_rho_%d" % i], rtol=1e-6)
+    noise = [ref["bbb_step_noise_%d" % i] for i in range(4)]
+    pred, ws, _ = opt.forward_sample(oracle.synthetic_x((16, 30), seed=3), eps=noise, return_weights=True)
+    np.testing.assert_allclose(pred, ref["bbb_step_predictions"], rtol=FP32_RTOL, atol=FP32_ATOL)
+    np.testing.assert_allclose(ws[0], ref["bbb_step_model_W0"], rtol=3e-7, atol=6e-8)

@@ -147,3 +147,77 @@ def test_fixture_posteriors_load_and_predict(oracle, golden_dir):
         det = oracle.forward(L, mean, x)
         np.testing.assert_allclose(mc.sum(-1), 1.0, rtol=1e-5)
         assert np.abs(mc - det).max() < 2e-3  # sigma ~ 4.7e-4: MC mean hugs the deterministic forward
+
+
+# ---------------------------------------------------------------------------------------
+# The oracle against outputs of the REFERENCE'S OWN source files (executed unmodified on a NumPy
+# stand-in for TensorFlow by tests/golden/make_reference_fixtures.py; seeds in that script).
+# ---------------------------------------------------------------------------------------
+SEED_PM, SEED_BBB = 20240601, 777
+
+
+def _vogn(golden_dir):
+    from deepbayes_b200 import formats
+    p = os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior")
+    return (formats.load_tensor_list(os.path.join(p, "mean.npy")), formats.load_tensor_list(os.path.join(p, "var.npy")))
+
+
+def test_legacy_normal_is_loc_plus_scale_times_standard_normal():
+    """np.random.normal(loc=array, scale=array) consumes the global stream exactly like
+    loc + scale * standard_normal(shape): this is what lets eps be injected."""
+    loc = np.linspace(-1, 1, 35).reshape(5, 7).astype(np.float32)
+    scale = np.linspace(0.1, 2, 35).reshape(5, 7).astype(np.float32)
+    np.random.seed(5)
+    a = np.random.normal(loc=loc, scale=scale)
+    np.random.seed(5)
+    b = loc + scale * np.random.standard_normal(loc.shape)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_oracle_matches_reference_posteriormodel_run(oracle, golden_dir):
+    ref = np.load(os.path.join(golden_dir, "reference_run.npz"))
+    mean, var = _vogn(golden_dir)
+    L = oracle.mlp([784, 128, 10])
+    x = oracle.synthetic_x((6, 1, 784), seed=0).astype(np.float64).reshape(6, 784)
+    # predict(x, n=7): same global-RNG consumption order as posteriormodel.py:94-101
+    np.random.seed(SEED_PM)
+    got = oracle.predict(L, mean, var, x, 7, eps=None)
+    np.testing.assert_allclose(got.reshape(6, 1, 10), ref["pm_predict_n7"], rtol=5e-6, atol=1e-8)
+    # ... which is also what the eps-injection form computes
+    np.random.seed(SEED_PM)
+    eps = [[np.random.standard_normal(t.shape) for t in mean] for _ in range(7)]
+    np.testing.assert_allclose(oracle.predict(L, mean, var, x, 7, eps).reshape(6, 1, 10), ref["pm_predict_n7"], rtol=5e-6, atol=1e-8)
+    # predict leaves the LAST sample in the model (posteriormodel.py:96)
+    last = oracle.sample_gaussian(mean, var, eps[6])
+    np.testing.assert_array_equal(last[2], ref["pm_weights_after_predict_W1"])
+    np.random.seed(SEED_PM)
+    lg = oracle.predict(L, mean, var, x, 5, eps=None, out="logits")
+    np.testing.assert_allclose(lg.reshape(6, 1, 10), ref["pm_predict_logits_n5"], rtol=5e-6, atol=1e-6)
+    # sample(inflate=2): var used as a std, float64 result
+    np.random.seed(SEED_PM)
+    s = oracle.sample_reference_rng(mean, var, inflate=2.0)
+    np.testing.assert_array_equal(s[1], ref["pm_sample_inflate2_b0"])
+    assert bool(ref["pm_sample_dtype_is_f64"][0]) and s[0].dtype == np.float64
+    np.testing.assert_allclose(oracle.forward(L, mean, x).reshape(6, 1, 10), ref["pm_det_predict"], rtol=5e-6, atol=1e-8)  # 3-D vs 2-D matmul path in BLAS
+    nb = oracle.forward(L, mean[:-1] + [np.zeros_like(mean[-1])], x, out="logits")
+    np.testing.assert_allclose(nb.reshape(6, 1, 10), ref["pm__predict_logits_nobias"], rtol=5e-6, atol=1e-6)
+
+
+def test_oracle_matches_reference_bbb_run(oracle, golden_dir):
+    ref = np.load(os.path.join(golden_dir, "reference_run.npz"))
+    L = oracle.mlp([30, 24, 10])
+    assert int(ref["bbb_epochs_after_compile"][0]) == 11
+    pm, pv = oracle.implicit_prior(L, 2.0)
+    rho = [oracle.inverse_softplus(v) for v in pv]
+    for i in range(4):
+        np.testing.assert_array_equal(pm[i], ref["bbb_prior_mean_%d" % i])
+        np.testing.assert_array_equal(pv[i], ref["bbb_prior_var_%d" % i])
+        np.testing.assert_allclose(rho[i], ref["bbb_rho_%d" % i], rtol=1e-6)
+    noise = [ref["bbb_step_noise_%d" % i] for i in range(4)]
+    xb = oracle.synthetic_x((16, 30), seed=3)
+    pred, w = oracle.bbb_forward(L, pm, rho, noise, xb)
+    np.testing.assert_allclose(pred, ref["bbb_step_predictions"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(w[0], ref["bbb_step_model_W0"], rtol=1e-6, atol=1e-8)
+    np.random.seed(SEED_BBB)
+    s0 = np.random.normal(loc=pm[0], scale=oracle.softplus(rho[0]))
+    np.testing.assert_allclose(s0, ref["bbb_sample_W0"], rtol=1e-6, atol=1e-9)
