@@ -559,6 +559,12 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
             src.stored ? "no stored-sample slab set (dbx_set_samples)" : "no Gaussian posterior set (dbx_set_gaussian)");
   DBX_CUDA(cudaSetDevice(m->device));
   g_last_path = 0;
+  DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
+  {
+    const int r = stream_mlp_run(m, x_dev, B, n, src, sink, st);
+    if (r < 0) return 1;
+    if (r == 1) { g_last_path = 2; return 0; }
+  }
   if (mode == DBX_MODE_BF16) {
     const char* nf = getenv("DBX_NO_FUSED");
     if (!(nf && nf[0] == '1')) {

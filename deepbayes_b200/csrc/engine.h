@@ -114,4 +114,8 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
                   cudaStream_t st);
 void fused_mlp_free(dbx_model* m);
 
+// stream_mlp.cu: small-batch (B <= 16) streaming path, fp32 FFMA, weights read / generated once.
+int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
+                   cudaStream_t st);
+
 }  // namespace dbx

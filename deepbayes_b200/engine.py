@@ -250,4 +250,4 @@ class Engine:
         return out.cpu().numpy().view(np.uint32)
 
     def last_path(self) -> str:
-        return "fused_tcgen05" if self.lib.dbx_last_path() == 1 else "generic"
+        return {0: "generic", 1: "fused_tcgen05", 2: "stream"}[self.lib.dbx_last_path()]

@@ -118,7 +118,7 @@ def test_predict_fp32(ctx, golden, oracle, name):
     np.testing.assert_allclose(got, golden[name + "/predict_fp32"], rtol=FP32_RTOL, atol=FP32_ATOL)
     np.testing.assert_allclose(s1.cpu().numpy(), golden[name + "/sum1_fp32"], rtol=FP32_RTOL, atol=n * FP32_ATOL)
     np.testing.assert_allclose(s2.cpu().numpy(), golden[name + "/sum2_fp32"], rtol=2 * FP32_RTOL, atol=n * FP32_ATOL)
-    assert eng.last_path() == "generic"
+    assert eng.last_path() == ("stream" if (c["B"] <= 16 and name != "cnn_small") else "generic")
     lg, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="fp32", out_kind="logits")
     np.testing.assert_allclose((lg / float(n)).cpu().numpy(), golden[name + "/predict_logits_fp32"], rtol=FP32_RTOL, atol=2e-6)
     inf, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="fp32", inflate=2.0)
@@ -134,7 +134,8 @@ def test_predict_bf16(ctx, golden, oracle, name, fused, monkeypatch):
     s1, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="bf16")
     got = (s1 / float(n)).cpu().numpy()
     fusable = name in ("mlp_cfg1", "mlp_cfg2")
-    assert eng.last_path() == ("fused_tcgen05" if (fused and fusable) else "generic")
+    small = c["B"] <= 16 and name != "cnn_small"      # small batches take the fp32 streaming kernel in any mode
+    assert eng.last_path() == ("stream" if small else "fused_tcgen05" if (fused and fusable) else "generic")
     want_bf = golden[name + "/predict_bf16"]   # oracle with bf16-rounded GEMM operands
     want_32 = golden[name + "/predict_fp32"]
     assert np.abs(got - want_32).max() <= BF16_ATOL
@@ -286,6 +287,54 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     cg, fg = eng.count_predicate(x, lab, n, seed=17, s0=3, mode="bf16", return_flags=True)
     assert (ff != fg).float().mean().item() < 5e-3
     np.testing.assert_array_equal(cf.cpu().numpy(), ff.sum(0).cpu().numpy())
+
+
+@pytest.mark.parametrize("dims,B", [([784, 1024, 1024, 10], 16), ([784, 1024, 1024, 10], 1), ([784, 512, 10], 5),
+                                    ([37, 50, 10], 7), ([13, 24, 16, 3], 9), ([64, 40, 12], 2)])
+def test_stream_vs_generic_device_crosscheck(oracle, monkeypatch, dims, B):
+    """Small-batch streaming kernel (weights read / generated once, fp32) against the generic fp32
+    kernels: Philox draws, injected eps, stored samples with index list and weights, count sink."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    L = oracle.mlp(dims)
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    eng = Engine(db.Sequential(layers))
+    mean, std = oracle.synthetic_posterior(L, seed=5, sigma_scale=0.5)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=6)
+    n = 23
+    eps = np.random.Generator(np.random.Philox(4)).standard_normal((n, eng.P)).astype(np.float32)
+    slab = eng.sample(9, seed=3, s0=0)
+    eng.set_samples(slab)
+    idx = [(5 * j + 2) % 9 for j in range(n)]
+    wts = np.linspace(0.1, 1.0, 9).astype(np.float32)
+    lab = np.random.Generator(np.random.Philox(1)).integers(0, dims[-1], size=B).astype(np.int32)
+    res = {}
+    for tag, env in (("generic", "1"), ("stream", "0")):
+        monkeypatch.setenv("DBX_NO_STREAM", env)
+        monkeypatch.setenv("DBX_NO_FUSED", "1")
+        r = {}
+        r["philox"] = eng.predict_sums(x, n, seed=17, s0=3, mode="fp32", second_moment=True)
+        assert eng.last_path() == tag
+        r["eps"] = eng.predict_sums(x, n, eps=eps, mode="fp32", out_kind="logits", second_moment=True)
+        r["stored_idx"] = eng.predict_stored_sums(x, n, idx=idx, mode="fp32", second_moment=True)
+        r["stored_wts"] = eng.predict_stored_sums(x, 9, j0=0, wts=wts, mode="fp32", second_moment=True)
+        r["count"] = eng.count_predicate(x, lab, n, seed=17, s0=3, mode="fp32", return_flags=True)
+        assert eng.last_path() == tag
+        res[tag] = r
+    for k in ("philox", "eps", "stored_idx", "stored_wts"):
+        for a, b in zip(res["stream"][k], res["generic"][k]):
+            np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5, atol=2e-5 if k == "eps" else 2e-6)
+    assert (res["stream"]["count"][1] != res["generic"]["count"][1]).float().mean().item() < 0.02
+    np.testing.assert_array_equal(res["stream"]["count"][0].cpu().numpy(), res["stream"]["count"][1].sum(0).cpu().numpy())
+    # bf16 mode at small B is served by the same fp32 streaming kernel
+    monkeypatch.setenv("DBX_NO_STREAM", "0")
+    b1, _ = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16")
+    assert eng.last_path() == "stream"
+    np.testing.assert_array_equal(b1.cpu().numpy(), res["stream"]["philox"][0].cpu().numpy())
 
 
 def test_mc_converges_to_oracle_mc(ctx, oracle):
