@@ -42,13 +42,14 @@ struct StreamParams {
 };
 
 // 4 consecutive weights starting at flat index j (j % 4 == 0, aligned source rows)
+template <int SRC>
 __device__ __forceinline__ float4 load_w4(const StreamParams& p, const float* __restrict__ srow, const float* __restrict__ erow,
                                           unsigned long long sample, int j) {
-  if (p.stored) return __ldcs(reinterpret_cast<const float4*>(srow + j));   // streaming: read once
+  if (SRC == 0) return __ldcs(reinterpret_cast<const float4*>(srow + j));   // streaming: read once
   const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.mu + j));
   const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.sigma + j));
   float z[4];
-  if (erow) { const float4 e4 = __ldcs(reinterpret_cast<const float4*>(erow + j)); z[0] = e4.x; z[1] = e4.y; z[2] = e4.z; z[3] = e4.w; }
+  if (SRC == 2) { const float4 e4 = __ldcs(reinterpret_cast<const float4*>(erow + j)); z[0] = e4.x; z[1] = e4.y; z[2] = e4.z; z[3] = e4.w; }
   else philox_normal4(p.seed, sample, (unsigned long long)(j >> 2), z);
   float4 w;
   if (p.unfused) {
@@ -62,11 +63,12 @@ __device__ __forceinline__ float4 load_w4(const StreamParams& p, const float* __
 }
 
 // one weight at flat index j (any alignment)
+template <int SRC>
 __device__ __forceinline__ float load_w1(const StreamParams& p, const float* __restrict__ srow, const float* __restrict__ erow,
                                          unsigned long long sample, int j) {
-  if (p.stored) return __ldcs(srow + j);
+  if (SRC == 0) return __ldcs(srow + j);
   float e;
-  if (erow) e = erow[j];
+  if (SRC == 2) e = erow[j];
   else { float z[4]; philox_normal4(p.seed, sample, (unsigned long long)(j >> 2), z); e = z[j & 3]; }
   const float sc = p.inflate * p.sigma[j];
   return p.unfused ? __fadd_rn(p.mu[j], __fmul_rn(sc, e)) : fmaf(sc, e, p.mu[j]);
@@ -74,8 +76,8 @@ __device__ __forceinline__ float load_w1(const StreamParams& p, const float* __r
 
 extern __shared__ __align__(16) float stream_smem[];
 
-template <int BT>
-__global__ void __launch_bounds__(kStreamThreads)
+template <int BT, int SRC>
+__global__ void __launch_bounds__(kStreamThreads, (BT <= 2 ? 3 : 2))
 stream_mlp_kernel(const StreamParams p) {
   float* xs = stream_smem;                       // [in_feat][BT]   (input, shared by all samples)
   float* hA = xs + (size_t)p.in_feat * BT;       // [maxw][BT]
@@ -109,23 +111,35 @@ stream_mlp_kernel(const StreamParams p) {
             for (int b = 0; b < BT; ++b) { a[b][0] = a[b][1] = a[b][2] = a[b][3] = 0.f; }
             const int col = g << 2;
             int k = 0;
-            for (; k + 8 <= L.K; k += 8) {
-              float4 w[8];
+            constexpr int U = (SRC == 0 && BT <= 2) ? 12 : 8;   // independent 128-bit loads in flight per thread
+            for (; k + U <= L.K; k += U) {
+              float4 w[U];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) w[u] = load_w4(p, srow, erow, sample, L.w_off + (k + u) * L.N + col);
+              for (int u = 0; u < U; ++u) w[u] = load_w4<SRC>(p, srow, erow, sample, L.w_off + (k + u) * L.N + col);
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
+              for (int u = 0; u < U; ++u) {
                 const float* hk = hin + (size_t)(k + u) * BT;
+                float hv[BT];
+                if (BT >= 4) {   // activations are [feature][BT]: one 128-bit broadcast load per 4 rows
+#pragma unroll
+                  for (int b4 = 0; b4 < BT / 4; ++b4) {
+                    const float4 h4 = *reinterpret_cast<const float4*>(hk + 4 * b4);
+                    hv[4 * b4] = h4.x; hv[4 * b4 + 1] = h4.y; hv[4 * b4 + 2] = h4.z; hv[4 * b4 + 3] = h4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int b = 0; b < BT; ++b) hv[b] = hk[b];
+                }
 #pragma unroll
                 for (int b = 0; b < BT; ++b) {
-                  const float h = hk[b];
+                  const float h = hv[b];
                   a[b][0] = fmaf(h, w[u].x, a[b][0]); a[b][1] = fmaf(h, w[u].y, a[b][1]);
                   a[b][2] = fmaf(h, w[u].z, a[b][2]); a[b][3] = fmaf(h, w[u].w, a[b][3]);
                 }
               }
             }
             for (; k < L.K; ++k) {
-              const float4 w = load_w4(p, srow, erow, sample, L.w_off + k * L.N + col);
+              const float4 w = load_w4<SRC>(p, srow, erow, sample, L.w_off + k * L.N + col);
               const float* hk = hin + (size_t)k * BT;
 #pragma unroll
               for (int b = 0; b < BT; ++b) {
@@ -134,7 +148,7 @@ stream_mlp_kernel(const StreamParams p) {
                 a[b][2] = fmaf(h, w.z, a[b][2]); a[b][3] = fmaf(h, w.w, a[b][3]);
               }
             }
-            const float4 bias = load_w4(p, srow, erow, sample, L.b_off + col);
+            const float4 bias = load_w4<SRC>(p, srow, erow, sample, L.b_off + col);
             const float bb[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -148,12 +162,12 @@ stream_mlp_kernel(const StreamParams p) {
 #pragma unroll
             for (int b = 0; b < BT; ++b) a[b] = 0.f;
             for (int k = 0; k < L.K; ++k) {
-              const float w = load_w1(p, srow, erow, sample, L.w_off + k * L.N + col);
+              const float w = load_w1<SRC>(p, srow, erow, sample, L.w_off + k * L.N + col);
               const float* hk = hin + (size_t)k * BT;
 #pragma unroll
               for (int b = 0; b < BT; ++b) a[b] = fmaf(hk[b], w, a[b]);
             }
-            const float bias = load_w1(p, srow, erow, sample, L.b_off + col);
+            const float bias = load_w1<SRC>(p, srow, erow, sample, L.b_off + col);
 #pragma unroll
             for (int b = 0; b < BT; ++b) hout[(size_t)col * BT + b] = apply_act(act, a[b] + bias);
           }
@@ -176,7 +190,7 @@ stream_mlp_kernel(const StreamParams p) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               if (c < L.N) {   // consecutive threads read consecutive rows: the warp's loads are contiguous
-                const float w = load_w1(p, srow, erow, sample, L.w_off + k * L.N + c);
+                const float w = load_w1<SRC>(p, srow, erow, sample, L.w_off + k * L.N + c);
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) a[bb][c] = fmaf(h[bb], w, a[bb][c]);
               }
@@ -202,7 +216,7 @@ stream_mlp_kernel(const StreamParams p) {
               float v = 0.f;
 #pragma unroll
               for (int w = 0; w < kStreamThreads / 32; ++w) v += red[w][bb][c];
-              const float bias = load_w1(p, srow, erow, sample, L.b_off + c);
+              const float bias = load_w1<SRC>(p, srow, erow, sample, L.b_off + c);
               hout[(size_t)c * BT + b0 + bb] = apply_act(act, v + bias);
             }
           }
@@ -272,13 +286,25 @@ __global__ void stream_zero_counts(unsigned long long* p, int n) {
   if (o < n) p[o] = 0ULL;
 }
 
-template <int BT>
-static int launch_stream(const StreamParams& p, int grid, size_t smem, cudaStream_t st) {
-  DBX_CUDA(cudaFuncSetAttribute(stream_mlp_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  stream_mlp_kernel<BT><<<grid, kStreamThreads, smem, st>>>(p);
+template <int BT, int SRC>
+static int launch_stream2(StreamParams& p, int num_sms, size_t smem, cudaStream_t st, int* grid_out) {
+  DBX_CUDA(cudaFuncSetAttribute(stream_mlp_kernel<BT, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  DBX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_mlp_kernel<BT, SRC>, kStreamThreads, smem));
+  per_sm = std::max(per_sm, 1);
+  // one resident wave; if there are fewer samples than that, one CTA per sample
+  const int grid = (int)std::min<long long>(p.n, (long long)num_sms * per_sm);
+  *grid_out = grid;
+  stream_mlp_kernel<BT, SRC><<<grid, kStreamThreads, smem, st>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   DBX_CUDA(cudaGetLastError());
   return 0;
+}
+template <int BT>
+static int launch_stream(StreamParams& p, int num_sms, size_t smem, cudaStream_t st, int* grid_out) {
+  if (p.stored) return launch_stream2<BT, 0>(p, num_sms, smem, st, grid_out);
+  if (p.eps) return launch_stream2<BT, 2>(p, num_sms, smem, st, grid_out);
+  return launch_stream2<BT, 1>(p, num_sms, smem, st, grid_out);
 }
 
 // returns 1 if handled, 0 if the shape is not for this path, <0 on error
@@ -306,12 +332,10 @@ int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const
   const int C = (int)m->out_feat;
   const size_t smem = ((size_t)m->in_feat * BT + 2 * (size_t)maxw * BT + 2 * (size_t)BT * C) * sizeof(float);
   if (smem > 200 * 1024) return 0;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) return -1;
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem + 9216, 1)));
-  const int grid = (int)std::min<int64_t>(n, (int64_t)prop.multiProcessorCount * per_sm);
-  // workspace for per-CTA partials
-  const size_t part_b = (size_t)grid * 2 * BT * C * sizeof(float);
+  static int num_sms = 0;
+  if (!num_sms && cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess) return -1;
+  // workspace for per-CTA partials (upper bound: 8 CTAs per SM)
+  const size_t part_b = (size_t)num_sms * 8 * 2 * BT * C * sizeof(float);
   if (ensure_ws(m->ws, std::max<size_t>(part_b, 256))) return -1;
   p.nlayers = nl; p.B = (int)B; p.C = C; p.in_feat = (int)m->in_feat; p.maxw = maxw; p.n = n; p.P = m->P;
   p.stored = src.stored ? 1 : 0; p.slab = m->slab; p.idx = src.idx; p.j0 = src.j0;
@@ -327,12 +351,13 @@ int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const
   }
   prof_begin(st);
   int rc = 0;
+  int grid = 1;
   switch (BT) {
-    case 1: rc = launch_stream<1>(p, grid, smem, st); break;
-    case 2: rc = launch_stream<2>(p, grid, smem, st); break;
-    case 4: rc = launch_stream<4>(p, grid, smem, st); break;
-    case 8: rc = launch_stream<8>(p, grid, smem, st); break;
-    default: rc = launch_stream<16>(p, grid, smem, st); break;
+    case 1: rc = launch_stream<1>(p, num_sms, smem, st, &grid); break;
+    case 2: rc = launch_stream<2>(p, num_sms, smem, st, &grid); break;
+    case 4: rc = launch_stream<4>(p, num_sms, smem, st, &grid); break;
+    case 8: rc = launch_stream<8>(p, num_sms, smem, st, &grid); break;
+    default: rc = launch_stream<16>(p, num_sms, smem, st, &grid); break;
   }
   if (rc) return -1;
   prof_end(st, (double)m->flops * (double)B * (double)n);

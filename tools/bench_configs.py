@@ -1,0 +1,117 @@
+"""Measure the other BASELINE.json configs (1, 3, 4, 5) on one B200 and print one JSON line each.
+Usage: python tools/bench_configs.py [--configs 1,3,4,5] [--stored 2000]"""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import deepbayes_b200 as db
+from deepbayes_b200 import _lib
+from deepbayes_b200.engine import Engine
+from oracle import oracle as o
+
+PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else \
+    {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def timeit(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def mlp_engine(dims):
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    eng = Engine(db.Sequential(layers))
+    mean, std = o.synthetic_posterior(o.mlp(dims), seed=1)
+    eng.set_gaussian(mean, std)
+    return eng
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def cfg1():
+    eng = mlp_engine([784, 512, 10])
+    for B in (10000, 128, 1):
+        x = torch.from_numpy(o.synthetic_x((B, 784), seed=0)).cuda()
+        n = 100
+        ms = timeit(lambda: eng.predict_sums(x, n, seed=1, mode="bf16", second_moment=True))
+        fl = eng.flops_per_forward * B * n / (ms * 1e-3) / 1e12
+        emit(config="1: BBB MLP 784-512-10, n=100", B=B, ms=ms, value=B * n / (ms * 1e-3), unit="forwards/s", path=eng.last_path(),
+             tflops=fl, frac_of_bf16_burst=fl / PEAKS["bf16_tflops"])
+
+
+def cfg3(S):
+    eng = mlp_engine([784, 1024, 1024, 10])
+    P = eng.P
+    slab = torch.empty((S, P), dtype=torch.float32, device="cuda")
+    for s0 in range(0, S, 256):   # synthetic stored samples = Gaussian draws, written straight into the slab
+        nc = min(256, S - s0)
+        slab[s0:s0 + nc] = eng.sample(nc, seed=7, s0=s0)
+    eng.set_samples(slab)
+    freq = torch.full((S,), 1.0 / S, device="cuda")
+    for B in (1, 8, 16, 64):
+        x = torch.from_numpy(o.synthetic_x((B, 784), seed=0)).cuda()
+        lib = _lib.load()
+        ms = timeit(lambda: eng.predict_stored_sums(x, S, j0=0, wts=freq, mode="bf16", second_moment=True), warm=1, reps=3)
+        gbs = 4.0 * P * S / (ms * 1e-3) / 1e9
+        emit(config="3: HMC stored posterior, MLP 784-1024-1024-10, %d stored fp32 samples resident in HBM (%.1f GB)" % (S, 4e-9 * P * S),
+             B=B, ms=ms, value=S * B / (ms * 1e-3), unit="forwards/s", samples_per_s=S / (ms * 1e-3), path=eng.last_path(),
+             roofline={"bound": "hbm", "achieved": gbs, "peak": PEAKS["hbm_gbs"], "unit": "GB/s", "frac": gbs / PEAKS["hbm_gbs"],
+                       "algorithmic_bytes_per_sample": 4 * P})
+    del slab
+
+
+def cfg4():
+    m = db.Sequential([db.Conv2D(32, 3, activation="relu", input_shape=(32, 32, 3)), db.Conv2D(64, 3, activation="relu"),
+                       db.MaxPooling2D(2), db.Flatten(), db.Dense(128, activation="relu"), db.Dense(10, activation="softmax")])
+    eng = Engine(m)
+    mean, std = o.synthetic_posterior(o.cnn_cfg4(), seed=1)
+    eng.set_gaussian(mean, std)
+    B, n = 256, 256
+    x = torch.from_numpy(o.synthetic_x((B, 32, 32, 3), seed=0)).cuda()
+    ms = timeit(lambda: eng.predict_sums(x, n, seed=1, mode="bf16"), warm=1, reps=2)
+    fl = eng.flops_per_forward * B * n / (ms * 1e-3) / 1e12
+    emit(config="4: Bayesian CNN conv32-conv64-pool-dense128-dense10, CIFAR-10 shape, n=256", B=B, ms=ms,
+         value=B * n / (ms * 1e-3), unit="forwards/s", path=eng.last_path(), tflops=fl, frac_of_bf16_burst=fl / PEAKS["bf16_tflops"],
+         note="generic direct-conv kernels (CUDA cores); implicit-GEMM tcgen05 conv is the next step")
+
+
+def cfg5():
+    eng = mlp_engine([784, 512, 512, 10])
+    K, n = 128, 100000
+    g = np.random.Generator(np.random.Philox(3))
+    x0 = o.synthetic_x((K, 784), seed=0)
+    xadv = np.clip(x0 + g.uniform(-0.1, 0.1, x0.shape).astype(np.float32), 0, 1)
+    x = torch.from_numpy(xadv).cuda()
+    lab = g.integers(0, 10, size=K).astype(np.int32)
+    ms = timeit(lambda: eng.count_predicate(x, lab, n, seed=5, mode="bf16"), warm=1, reps=2)
+    fl = eng.flops_per_forward * K * n / (ms * 1e-3) / 1e12
+    emit(config="5: Chernoff-bound MC, 100k posterior samples x 128 perturbed inputs, MLP 784-512-512-10", B=K, ms=ms,
+         value=K * n / (ms * 1e-3), unit="forwards/s", samples_per_s=n / (ms * 1e-3), path=eng.last_path(), tflops=fl,
+         frac_of_bf16_burst=fl / PEAKS["bf16_tflops"])
+    for K1 in (1,):
+        ms = timeit(lambda: eng.count_predicate(x[:K1], lab[:K1], n, seed=5, mode="bf16"), warm=1, reps=2)
+        emit(config="5b: massart-style loop, 100k posterior samples x 1 input", B=K1, ms=ms, samples_per_s=n / (ms * 1e-3),
+             path=eng.last_path(), note="weights formed in registers from Philox, never materialised")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,3,4,5")
+    ap.add_argument("--stored", type=int, default=2000)
+    a = ap.parse_args()
+    for c in a.configs.split(","):
+        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5}[c]()
