@@ -505,6 +505,419 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// =======================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster own rows [0,128) and
+// [128,256) of a 256-row unit; ONE tcgen05.mma issued by the leader drives both SMs' tensor
+// cores, and each CTA's shared memory holds only HALF of every weight tile (N/2 columns).  That
+// halves the per-SM shared-memory operand traffic (8 KB instead of 12 KB per layer-1 MMA), which
+// is what limits the single-CTA SS MMA to ~77 % of the tensor peak (tools/mma_rate.cu).
+// Same TMEM plan, same epilogue and same work split as fused_mlp_kernel<2>.
+// =======================================================================================
+constexpr int k2Stages = 6;
+constexpr int k2StageBytes = 32768;   // X block 16 KB + this CTA's half of the weight block 16 KB
+
+struct __align__(8) Barriers2 {
+  uint64_t full[k2Stages], empty[k2Stages];
+  uint64_t w3_full, w3_empty;
+  uint64_t bias_full[2], bias_empty[2];
+  uint64_t acc_full[2], act1_ready[2];
+  uint64_t acc2_full[2], act2_ready[2];
+  uint64_t l3_full[2], l3_drained[2];
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
+                  const FusedParams p) {
+  constexpr int CM = 2;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  const uint32_t s_w3 = s_stage + k2Stages * k2StageBytes;
+  float* bias_smem = (float*)(smem + k2Stages * k2StageBytes + kW3Bytes / 2);
+  const uint32_t s_bias = smem_u32(bias_smem);
+  Barriers2* bars = (Barriers2*)(smem + k2Stages * k2StageBytes + kW3Bytes / 2 + 2 * kBiasFloats * 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int trace_n = 0;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int cluster_id = blockIdx.x / CM;
+  constexpr uint16_t kBoth = 0x3;
+
+  const int H = p.H, NH = p.NH, K0 = p.K0;
+  const int n_l1 = (H + 255) / 256;
+  const int n_l2 = (NH == 2) ? H / 128 : 0;
+  const int kb1 = (K0 + 63) / 64;
+  const int l2_stages = H / 128;                // 2 k-blocks per stage
+
+  if (tid == 0) {
+    for (int i = 0; i < k2Stages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    mbar_init(smem_u32(&bars->w3_full), 1); mbar_init(smem_u32(&bars->w3_empty), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->bias_full[i]), 1); mbar_init(smem_u32(&bars->bias_empty[i]), 128);
+      mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->act1_ready[i]), 256);   // both CTAs' epilogues
+      mbar_init(smem_u32(&bars->acc2_full[i]), 1); mbar_init(smem_u32(&bars->act2_ready[i]), 256);
+      mbar_init(smem_u32(&bars->l3_full[i]), 1); mbar_init(smem_u32(&bars->l3_drained[i]), 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2<512>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2); prefetch_tmap(&tmW3); }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  const long long u0 = ((long long)cluster_id * p.U) / p.NC;
+  const long long u1 = ((long long)(cluster_id + 1) * p.U) / p.NC;
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs) ===========================
+    // Every copy lands in the issuing CTA's smem and signals the LEADER's `full` barrier; only
+    // the leader arms it (expect_tx of the pair's total bytes).
+    uint32_t it = 0, w3_n = 0, unit_n = 0;
+    for (long long u = u0; u < u1; ++u, ++unit_n) {
+      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
+      const int m0 = (q * CM + (int)rank) * 128;
+      {
+        const uint32_t b = unit_n & 1;
+        mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(&bars->bias_full[b]), (uint32_t)(p.PB * 4));
+          bulk_load(s_bias + b * kBiasFloats * 4, p.bias + (long long)s * p.PB, (uint32_t)(p.PB * 4), smem_u32(&bars->bias_full[b]));
+        }
+        __syncwarp();
+      }
+      for (int c = 0; c < n_l1; ++c) {
+        const int ncols = min(256, H - c * 256);
+        const int nhalf = ncols / 128;            // n-blocks (64 cols) per CTA
+        for (int kb = 0; kb < kb1; ++kb, ++it) {
+          const uint32_t st = it % k2Stages, ph = (it / k2Stages) & 1;
+          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&bars->full[st]);
+            const uint32_t base = s_stage + st * k2StageBytes;
+            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)(kXBytes + nhalf * kBlkBytes));
+            tma2_load_2d(base, &tmX, fb, kb * 64, m0);
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+              if (nb < nhalf)
+                tma2_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + ((int)rank * nhalf + nb) * 64, kb * 64, s);
+          }
+          __syncwarp();
+        }
+        if (c == 0) {
+          mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
+          if (elect_one()) {
+            const uint32_t wf = smem_u32(&bars->w3_full);
+            if (leader) mbar_expect_tx(wf, 2u * (uint32_t)(H * 16));
+            // this CTA's 8 output columns = core-matrix n-block `rank` of the blocked8 layout
+            tma2_load_3d(s_w3, &tmW3, wf, 0, (int)rank * (H / 8), s);
+          }
+          __syncwarp();
+          ++w3_n;
+        }
+      }
+      for (int j = 0; j < n_l2; ++j) {
+        for (int sg = 0; sg < l2_stages; ++sg, ++it) {
+          const uint32_t st = it % k2Stages, ph = (it / k2Stages) & 1;
+          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&bars->full[st]);
+            const uint32_t base = s_stage + st * k2StageBytes + kXBytes;
+            if (leader) mbar_expect_tx(fb, 2u * 2u * kBlkBytes);
+#pragma unroll
+            for (int kblk = 0; kblk < 2; ++kblk)   // this CTA's 64 of the chunk's 128 columns, two 64-wide k-blocks
+              tma2_load_3d(base + kblk * kBlkBytes, &tmW2, fb, j * 128 + (int)rank * 64, (sg * 2 + kblk) * 64, s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    for (int k = 0; k < k2Stages; ++k, ++it) {   // tail: the leader's last commits must have landed here
+      const uint32_t st = it % k2Stages, ph = (it / k2Stages) & 1;
+      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (leader) {
+      uint32_t st_i = 0, st_ph = 0;
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t a16_0 = (s_stage & 0x3FFFF) >> 4;
+      uint32_t st_full = full0, st_empty = empty0, st_a16 = a16_0;
+      auto advance = [&]() {
+        if (++st_i == k2Stages) { st_i = 0; st_ph ^= 1; st_full = full0; st_empty = empty0; st_a16 = a16_0; }
+        else { st_full += 8; st_empty += 8; st_a16 += k2StageBytes >> 4; }
+      };
+      constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+      uint32_t ph_act1_0 = 0, ph_act1_1 = 0, ph_act2_0 = 0, ph_act2_1 = 0;
+      uint32_t l3_issued0 = 0, l3_issued1 = 0, l3_waited0 = 0, l3_waited1 = 0;
+      uint32_t w3_n = 0;
+      int pn = 0;
+      int pb0 = 0, pk0 = 0, pl0 = 0, pkind0 = 0; uint32_t pa0 = 0, pd0 = 0, pw0 = 0;
+      int pb1 = 0, pk1 = 0, pl1 = 0, pkind1 = 0; uint32_t pa1 = 0, pd1 = 0, pw1 = 0;
+      const uint32_t idesc_l3 = make_idesc_bf16(256, 16, 0, 1);
+      const uint32_t idesc_l2 = make_idesc_bf16(256, 128, 0, 1);
+      // W3: one 8-column core-matrix block per CTA, k-groups 128 B apart
+      const uint64_t w3desc0 = make_smem_desc(s_w3, 128, (uint32_t)(H * 16), SW_NONE);
+
+      auto pump = [&](bool force) -> bool {
+        if (pn == 0) return false;
+        const uint32_t bar = smem_u32(pkind0 == 1 ? &bars->act1_ready[pb0] : &bars->act2_ready[pb0]);
+        uint32_t ph;
+        if (pkind0 == 1) ph = pb0 ? ph_act1_1 : ph_act1_0; else ph = pb0 ? ph_act2_1 : ph_act2_0;
+        if (force) mbar_wait_cluster(bar, ph & 1);
+        else if (!mbar_try_wait_cluster(bar, ph & 1)) return false;
+        if (pkind0 == 1) { if (pb0) ++ph_act1_1; else ++ph_act1_0; } else { if (pb0) ++ph_act2_1; else ++ph_act2_0; }
+        fence_after_sync();
+        DBX_TRACE(140);
+        if (elect_one()) {
+          const uint64_t bd = w3desc0 + (uint64_t)(pw0 >> 4);
+          for (int kk = 0; kk < pk0; ++kk) {
+            const uint64_t d = bd + (uint64_t)(kk * 16);
+            mma2_ts_lh(pd0, pa0 + kk * 8, (uint32_t)d, (uint32_t)(d >> 32), idesc_l3, kk > 0);
+          }
+          mma2_commit_mc(smem_u32(&bars->l3_full[pb0]), kBoth);
+          if (pl0) mma2_commit_mc(smem_u32(&bars->w3_empty), kBoth);
+        }
+        __syncwarp();
+        if (pb0) ++l3_issued1; else ++l3_issued0;
+        pb0 = pb1; pk0 = pk1; pl0 = pl1; pkind0 = pkind1; pa0 = pa1; pd0 = pd1; pw0 = pw1;
+        --pn;
+        return true;
+      };
+      auto push = [&](int buf, uint32_t a, uint32_t d, uint32_t woff, int ksteps, int last, int kind) {
+        if (pn == 0) { pb0 = buf; pa0 = a; pd0 = d; pw0 = woff; pk0 = ksteps; pl0 = last; pkind0 = kind; }
+        else { pb1 = buf; pa1 = a; pd1 = d; pw1 = woff; pk1 = ksteps; pl1 = last; pkind1 = kind; }
+        ++pn;
+      };
+      auto flush_all = [&]() { while (pump(true)) {} };
+      auto flush_buf = [&](int b) {
+        if (pn == 2 && pb1 == b) { pump(true); pump(true); }
+        else if (pn >= 1 && pb0 == b) pump(true);
+      };
+      auto wait_drained = [&](int b) {
+        if (b == 0) { while (l3_waited0 < l3_issued0) { mbar_wait_cluster(smem_u32(&bars->l3_drained[0]), l3_waited0 & 1); ++l3_waited0; } }
+        else { while (l3_waited1 < l3_issued1) { mbar_wait_cluster(smem_u32(&bars->l3_drained[1]), l3_waited1 & 1); ++l3_waited1; } }
+        fence_after_sync();
+      };
+
+      for (long long u = u0; u < u1; ++u) {
+        for (int c = 0; c < n_l1; ++c) {
+          const int ncols = min(256, H - c * 256);
+          const uint32_t idesc = make_idesc_bf16(256, ncols, 0, 1);
+          const uint32_t dreg = tmem + c * 256;
+          if (c == 1) flush_all(); else flush_buf(0);
+          wait_drained(c);
+          DBX_TRACE(100 + c);
+          for (int kb = 0; kb < kb1; ++kb) {
+            mbar_wait(st_full, st_ph);
+            fence_after_sync();
+            if (elect_one()) {
+              const uint32_t a_lo = st_a16 | (1u << 16);
+              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
+              if (kb + 1 < kb1 || (K0 & 63) == 0) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  mma2_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+              } else {
+                const int ksteps = ((K0 & 63) + 15) >> 4;
+                for (int kk = 0; kk < ksteps; ++kk)
+                  mma2_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+              }
+              mma2_commit_mc(st_empty, kBoth);
+            }
+            __syncwarp();
+            advance();
+            pump(false);
+          }
+          if (elect_one()) mma2_commit_mc(smem_u32(&bars->acc_full[c]), kBoth);
+          __syncwarp();
+          DBX_TRACE(110 + c);
+          if (c == 0) {
+            flush_all();
+            mbar_wait(smem_u32(&bars->w3_full), w3_n & 1);
+            ++w3_n;
+          }
+          if (NH == 1)
+            push(c, tmem + c * 256, tmem + c * 256 + 128, (uint32_t)(c * 256 * 16), ncols / 16, c == n_l1 - 1, 1);
+        }
+        for (int j = 0; j < n_l2; ++j) {
+          const int b = j & 1;
+          const uint32_t dbuf = tmem + b * 256 + 128;
+          flush_buf(b);
+          wait_drained(b);
+          DBX_TRACE(120 + j);
+          for (int sg = 0; sg < l2_stages; ++sg) {
+            if (j == 0 && (sg & 1) == 0) {
+              if ((sg >> 1) == 0) { mbar_wait_cluster(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
+              else { mbar_wait_cluster(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
+            }
+            mbar_wait(st_full, st_ph);
+            fence_after_sync();
+            if (elect_one()) {
+              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
+              const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
+                mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (sg | i) > 0);
+              mma2_commit_mc(st_empty, kBoth);
+            }
+            __syncwarp();
+            advance();
+            pump(false);
+          }
+          if (elect_one()) mma2_commit_mc(smem_u32(&bars->acc2_full[b]), kBoth);
+          __syncwarp();
+          DBX_TRACE(130 + j);
+          push(b, dbuf, dbuf + 64, (uint32_t)(j * 128 * 16), 8, j == n_l2 - 1, 2);
+        }
+      }
+      flush_all();
+    }
+  } else {
+    // =========================== epilogue (warps 2..5, both CTAs) ===========================
+    const int g = warp & 3;
+    const int row = g * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    uint32_t ph_acc[2] = {0, 0}, ph_acc2[2] = {0, 0}, ph_l3[2] = {0, 0};
+    uint32_t unit_n = 0;
+    float acc1[kMaxC], acc2[kMaxC];
+#pragma unroll
+    for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+    unsigned int cnt = 0;
+    int cur_q = (u0 < u1) ? (int)(u0 / p.ns) : -1;
+    const int q_first = cur_q;
+
+    auto flush_segment = [&](int q) {
+      const int seg = q - q_first;
+      const int grow = (q * CM + (int)rank) * 128 + row;
+      if (p.sink_kind == 0) {
+        float* dst = p.partial + ((((long long)cluster_id * p.maxseg + seg) * CM + rank) * 128 + row) * 32;
+#pragma unroll
+        for (int i = 0; i < kMaxC; i += 4) {
+          *reinterpret_cast<float4*>(dst + i) = make_float4(acc1[i], acc1[i + 1], acc1[i + 2], acc1[i + 3]);
+          *reinterpret_cast<float4*>(dst + 16 + i) = make_float4(acc2[i], acc2[i + 1], acc2[i + 2], acc2[i + 3]);
+        }
+      } else if (grow < p.B && cnt) {
+        atomicAdd(p.counts + grow, (unsigned long long)cnt);
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
+      cnt = 0;
+    };
+    auto pack_chunk = [&](uint32_t src, int ncols, const float* bias) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(src + c0, v);
+        wait_ld();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * i);
+          const float lo = fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f);
+          const float hi = fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f);
+          w[i] = pack_bf16x2(lo, hi);
+        }
+        tmem_st16(src + c0 / 2, w);
+      }
+      wait_st();
+      fence_before_sync();
+    };
+
+    for (long long u = u0; u < u1; ++u, ++unit_n) {
+      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
+      if (q != cur_q) { flush_segment(cur_q); cur_q = q; }
+      const uint32_t bb = unit_n & 1;
+      const float* bias = bias_smem + bb * kBiasFloats;
+      mbar_wait(smem_u32(&bars->bias_full[bb]), (unit_n >> 1) & 1);
+      float logit[kMaxC];
+#pragma unroll
+      for (int i = 0; i < kMaxC; ++i) logit[i] = 0.f;
+
+      auto drain_l3 = [&](int b, uint32_t daddr) {
+        mbar_wait(smem_u32(&bars->l3_full[b]), ph_l3[b] & 1);
+        ++ph_l3[b];
+        fence_after_sync();
+        uint32_t v[16];
+        tmem_ld16(daddr, v);
+        wait_ld();
+        fence_before_sync();
+        mbar_arrive_cluster(smem_u32(&bars->l3_drained[b]), 0);   // the leader's MMA warp waits for both CTAs
+#pragma unroll
+        for (int i = 0; i < kMaxC; ++i) logit[i] += __uint_as_float(v[i]);
+      };
+
+      for (int c = 0; c < n_l1; ++c) {
+        const int ncols = min(256, H - c * 256);
+        mbar_wait(smem_u32(&bars->acc_full[c]), ph_acc[c] & 1);
+        ++ph_acc[c];
+        fence_after_sync();
+        if (warp == 2) DBX_TRACE(200 + c);
+        pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
+        mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
+        if (warp == 2) DBX_TRACE(210 + c);
+        if (NH == 1) drain_l3(c, tmem + lane_base + c * 256 + 128);
+      }
+      for (int j = 0; j < n_l2; ++j) {
+        const int b = j & 1;
+        mbar_wait(smem_u32(&bars->acc2_full[b]), ph_acc2[b] & 1);
+        ++ph_acc2[b];
+        fence_after_sync();
+        if (warp == 2) DBX_TRACE(220 + j);
+        pack_chunk(tmem + lane_base + b * 256 + 128, 128, bias + p.b2_off + j * 128);
+        mbar_arrive_cluster(smem_u32(&bars->act2_ready[b]), 0);
+        if (warp == 2) DBX_TRACE(230 + j);
+        drain_l3(b, tmem + lane_base + b * 256 + 128 + 64);
+        if (warp == 2) DBX_TRACE(240 + j);
+      }
+      const float* b3 = bias + p.b3_off;
+      float z[kMaxC];
+#pragma unroll
+      for (int i = 0; i < kMaxC; ++i) z[i] = (i < p.C) ? logit[i] + b3[i] : -INFINITY;
+      mbar_arrive(smem_u32(&bars->bias_empty[bb]));
+      const int grow = (q * CM + (int)rank) * 128 + row;
+      if (p.sink_kind == 0) {
+        const float w = p.wts ? p.wts[s] : 1.f;
+        if (p.out_kind == DBX_OUT_LOGITS) {
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) if (i < p.C) { acc1[i] = fmaf(w, z[i], acc1[i]); acc2[i] = fmaf(w * z[i], z[i], acc2[i]); }
+        } else if (p.act_last == DBX_ACT_SOFTMAX) {
+          float mx = z[0];
+#pragma unroll
+          for (int i = 1; i < kMaxC; ++i) mx = fmaxf(mx, z[i]);
+          float e[kMaxC], den = 0.f;
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) { e[i] = (i < p.C) ? expf(z[i] - mx) : 0.f; den += e[i]; }
+          const float inv = 1.f / den;
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) { const float pr = e[i] * inv; acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) if (i < p.C) { const float pr = apply_act(p.act_last, z[i]); acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
+        }
+      } else {
+        int best = 0; float bv = z[0];
+#pragma unroll
+        for (int i = 1; i < kMaxC; ++i) if (z[i] > bv) { bv = z[i]; best = i; }
+        if (grow < p.B) {
+          const int ok = (best == p.labels[grow]);
+          if (p.flags) p.flags[(long long)s * p.B + grow] = (uint8_t)ok;
+          cnt += ok;
+        }
+      }
+    }
+    if (cur_q >= 0) flush_segment(cur_q);
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) tmem_dealloc2<512>(tmem);
+}
+
 // Adds the per-(cluster, segment) partial sums in sample order.
 __global__ void finish_kernel(const float* __restrict__ partial, int NC, int maxseg, int CM, long long U, int ns, int B,
                               int C, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
@@ -588,6 +1001,23 @@ static int launch_fused(const CUtensorMap& tmX, const CUtensorMap& tmW1, const C
   return 0;
 }
 
+static int launch_fused2(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
+                         const FusedParams& p, int smem, cudaStream_t st) {
+  DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.NC * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel, tmX, tmW1, tmW2, tmW3, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 static inline int grid_for2(int64_t total, int block = 256) {
   return (int)std::min<int64_t>(std::max<int64_t>(cdiv(total, block), 1), 148 * 16);
 }
@@ -618,6 +1048,9 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   int CM = 1;
   if (const char* e = getenv("DBX_FUSED_CM")) CM = atoi(e);
   if (CM != 1 && CM != 2 && CM != 4) CM = 1;
+  bool two_cta = false;   // cta_group::2 kernel (CTA pairs)
+  if (const char* e = getenv("DBX_FUSED_2CTA")) two_cta = atoi(e) != 0;
+  if (two_cta) CM = 2;
   const int T = (int)cdiv(B, 128);
   const int Q = (int)cdiv(T, CM);
   int64_t ns_max = 256;
@@ -666,12 +1099,21 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     if (!make_w(&tmW2b[i], NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
   }
   (void)tmW1; (void)tmW2; (void)tmW3;
+  CUtensorMap tmW3b[2];
+  for (int i = 0; i < 2; ++i) {
+    // last layer's kernel in blocked8 order viewed as rows of 64 bf16: CTA r of a pair fetches rows [r*H/8, (r+1)*H/8)
+    uint64_t d[3] = {64, (uint64_t)(Lout->w_rows * Lout->w_cols_pad / 64), (uint64_t)ns};
+    uint64_t sb[2] = {128, (uint64_t)m->P16 * 2};
+    uint32_t b[3] = {64, (uint32_t)(H / 8), 1};
+    if (!make_tmap_bf16(&tmW3b[i], W16buf[i] + Lout->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
+  }
   // the last layer's kernel goes out in tcgen05 core-matrix order (one bulk copy per sample)
   TensorTable tab = m->table;
   for (int i = 0; i < tab.n; ++i)
     if (!tab.is_bias[i] && tab.src_off[i] == (int32_t)Lout->w_off) tab.blocked8[i] = 1;
 
-  const int smem = kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024;
+  const int smem = two_cta ? (k2Stages * k2StageBytes + kW3Bytes / 2 + 2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024)
+                           : (kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024);
 
   if (sink.kind == 1 && !sink.accumulate) {
     zero_counts_kernel<<<grid_for2(B), 256, 0, st>>>(sink.counts, B);
@@ -724,7 +1166,8 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
     prof_begin(st);
     int rc = 0;
-    if (CM == 1) rc = launch_fused<1>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
+    if (two_cta) rc = launch_fused2(tmX, tmW1c, tmW2c, tmW3b[bsel], p, smem, st);
+    else if (CM == 1) rc = launch_fused<1>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     else if (CM == 2) rc = launch_fused<2>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     else rc = launch_fused<4>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     if (rc) return -1;

@@ -40,11 +40,12 @@ def run(dims, B, n, cm, ns):
 
 if __name__ == "__main__":
     d2 = [784, 512, 512, 10]
-    for mc in (0, 1):
-        os.environ["DBX_FUSED_MC"] = str(mc)
-        print("==== MC", mc)
-        for cm in (2, 4):
-            run(d2, 1024, 1, cm, 16)
-            run(d2, 1000, 70, cm, 16)
-            run([784, 512, 10], 700, 33, cm, 8)
-
+    os.environ["DBX_FUSED_2CTA"] = sys.argv[1] if len(sys.argv) > 1 else "1"
+    run(d2, 256, 1, 2, 16)
+    run(d2, 1024, 16, 2, 16)
+    run(d2, 1000, 70, 2, 16)
+    run([784, 512, 10], 700, 33, 2, 8)
+    run([784, 128, 10], 300, 20, 2, 8)
+    run([100, 256, 256, 7], 513, 40, 2, 16)
+    run([784, 384, 384, 10], 260, 12, 2, 16)
+    run(d2, 4096, 256, 2, 128)
