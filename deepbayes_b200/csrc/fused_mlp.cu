@@ -556,9 +556,9 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_init(smem_u32(&bars->w3_full), 1); mbar_init(smem_u32(&bars->w3_empty), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->bias_full[i]), 1); mbar_init(smem_u32(&bars->bias_empty[i]), 128);
-      mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->act1_ready[i]), 256);   // both CTAs' epilogues
-      mbar_init(smem_u32(&bars->acc2_full[i]), 1); mbar_init(smem_u32(&bars->act2_ready[i]), 256);
-      mbar_init(smem_u32(&bars->l3_full[i]), 1); mbar_init(smem_u32(&bars->l3_drained[i]), 256);
+      mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->act1_ready[i]), 8);   // one arrival per epilogue warp of both CTAs
+      mbar_init(smem_u32(&bars->acc2_full[i]), 1); mbar_init(smem_u32(&bars->act2_ready[i]), 8);
+      mbar_init(smem_u32(&bars->l3_full[i]), 1); mbar_init(smem_u32(&bars->l3_drained[i]), 8);
     }
     fence_mbar_init();
   }
@@ -668,8 +668,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t bar = smem_u32(pkind0 == 1 ? &bars->act1_ready[pb0] : &bars->act2_ready[pb0]);
         uint32_t ph;
         if (pkind0 == 1) ph = pb0 ? ph_act1_1 : ph_act1_0; else ph = pb0 ? ph_act2_1 : ph_act2_0;
-        if (force) mbar_wait_cluster(bar, ph & 1);
-        else if (!mbar_try_wait_cluster(bar, ph & 1)) return false;
+        if (force) mbar_wait(bar, ph & 1);
+        else if (!mbar_try_wait(bar, ph & 1)) return false;
         if (pkind0 == 1) { if (pb0) ++ph_act1_1; else ++ph_act1_0; } else { if (pb0) ++ph_act2_1; else ++ph_act2_0; }
         fence_after_sync();
         DBX_TRACE(140);
@@ -699,8 +699,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         else if (pn >= 1 && pb0 == b) pump(true);
       };
       auto wait_drained = [&](int b) {
-        if (b == 0) { while (l3_waited0 < l3_issued0) { mbar_wait_cluster(smem_u32(&bars->l3_drained[0]), l3_waited0 & 1); ++l3_waited0; } }
-        else { while (l3_waited1 < l3_issued1) { mbar_wait_cluster(smem_u32(&bars->l3_drained[1]), l3_waited1 & 1); ++l3_waited1; } }
+        if (b == 0) { while (l3_waited0 < l3_issued0) { mbar_wait(smem_u32(&bars->l3_drained[0]), l3_waited0 & 1); ++l3_waited0; } }
+        else { while (l3_waited1 < l3_issued1) { mbar_wait(smem_u32(&bars->l3_drained[1]), l3_waited1 & 1); ++l3_waited1; } }
         fence_after_sync();
       };
 
@@ -752,11 +752,13 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           DBX_TRACE(120 + j);
           for (int sg = 0; sg < l2_stages; ++sg) {
             if (j == 0 && (sg & 1) == 0) {
-              if ((sg >> 1) == 0) { mbar_wait_cluster(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
-              else { mbar_wait_cluster(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
+              if ((sg >> 1) == 0) { mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
+              else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
             }
+            DBX_TRACE(160);
             mbar_wait(st_full, st_ph);
             fence_after_sync();
+            DBX_TRACE(161);
             if (elect_one()) {
               const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
               const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
@@ -845,7 +847,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_ld16(daddr, v);
         wait_ld();
         fence_before_sync();
-        mbar_arrive_cluster(smem_u32(&bars->l3_drained[b]), 0);   // the leader's MMA warp waits for both CTAs
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->l3_drained[b]), 0);   // the leader's MMA warp waits for both CTAs
 #pragma unroll
         for (int i = 0; i < kMaxC; ++i) logit[i] += __uint_as_float(v[i]);
       };
@@ -857,7 +860,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         fence_after_sync();
         if (warp == 2) DBX_TRACE(200 + c);
         pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
-        mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
         if (warp == 2) DBX_TRACE(210 + c);
         if (NH == 1) drain_l3(c, tmem + lane_base + c * 256 + 128);
       }
@@ -868,7 +872,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         fence_after_sync();
         if (warp == 2) DBX_TRACE(220 + j);
         pack_chunk(tmem + lane_base + b * 256 + 128, 128, bias + p.b2_off + j * 128);
-        mbar_arrive_cluster(smem_u32(&bars->act2_ready[b]), 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act2_ready[b]), 0);
         if (warp == 2) DBX_TRACE(230 + j);
         drain_l3(b, tmem + lane_base + b * 256 + 128 + 64);
         if (warp == 2) DBX_TRACE(240 + j);
