@@ -149,8 +149,13 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
         if (j >= P) break;
         while (ti + 1 < tab.n && j >= tab.src_end[ti]) ++ti;
         const int r = j - tab.src_off[ti];
-        if (tab.is_bias[ti]) {
+        if (tab.is_bias[ti] == 1) {
           brow[tab.dst_off[ti] + r] = w[i];
+        } else if (tab.is_bias[ti] == 2) {
+          // output-layer kernel kept as fp32 rows of 12 (bf16-rounded values) next to the biases: the
+          // CTA-pair kernel applies it with FFMA in the epilogue
+          const int row = r / tab.cols[ti], col = r - row * tab.cols[ti];
+          brow[tab.dst_off[ti] + row * 12 + col] = __bfloat162float(__float2bfloat16_rn(w[i]));
         } else {
           const int row = r / tab.cols[ti], col = r - row * tab.cols[ti];
           const int d = tab.blocked8[ti] ? (((col >> 3) * tab.rows[ti] + row) * 8 + (col & 7)) : (row * tab.cols_pad[ti] + col);
@@ -410,7 +415,8 @@ static inline int grid_for(int64_t total, int block = 256) {
 // ---------------------------------------------------------------------------------------
 
 int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
-                       float* B32, cudaStream_t st) {
+                       float* B32, cudaStream_t st, int64_t pb_stride) {
+  if (pb_stride <= 0) pb_stride = m->PB;
   const int nblk = (int)((m->P + 3) / 4);
   BlockRanges rg; rg.n = 0;
   const bool philox = !src.stored && !src.eps;
@@ -437,7 +443,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
     DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
                (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
                src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, tab, rg, W16,
-               m->P16, B32, m->PB);
+               m->P16, B32, pb_stride);
   }
   return 0;
 }

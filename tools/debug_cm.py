@@ -40,7 +40,7 @@ def run(dims, B, n, cm, ns):
 
 if __name__ == "__main__":
     d2 = [784, 512, 512, 10]
-    os.environ["DBX_FUSED_2CTA"] = sys.argv[1] if len(sys.argv) > 1 else "1"
+    os.environ["DBX_FUSED_KERNEL"] = sys.argv[1] if len(sys.argv) > 1 else "3"
     run(d2, 256, 1, 2, 16)
     run(d2, 1024, 16, 2, 16)
     run(d2, 1000, 70, 2, 16)
