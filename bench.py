@@ -33,6 +33,20 @@ METRIC = "posterior-sample x input forwards/sec"
 UNIT = "forwards/s"
 
 
+def _ncu_traffic():
+    """DRAM bytes (read + write) of ONE fused-kernel launch from the committed ncu --set full capture."""
+    f = os.path.join(ROOT, "profiles", "r1_ncu_fused_pair_summary.txt")
+    try:
+        tot = 0.0
+        for line in open(f):
+            parts = line.split()
+            if parts and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(parts[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[parts[2]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -252,11 +266,15 @@ def main():
         tf_achieved = (pfl.value / (pms.value * 1e-3)) / 1e12 if pms.value > 0 else None
         peak_tf = float(peaks["bf16_tflops_sustained"]) if args.mode == "bf16" else None
         roof = {
-            "bound": "tensor", "kernel": "fused_mlp_tcgen05" if path == "fused_tcgen05" else "dense_kernel (generic FFMA)",
+            "bound": "tensor",
+            "kernel": "fused_mlp2_kernel (tcgen05 cta_group::2, TMA, TMEM-resident activations)" if path == "fused_tcgen05" else "dense_kernel (generic FFMA)",
             "achieved": tf_achieved, "peak": peak_tf, "peak_burst": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
             "frac": (tf_achieved / peak_tf) if (tf_achieved and peak_tf) else None,
             "frac_of_burst": (tf_achieved / float(peaks["bf16_tflops"])) if tf_achieved else None,
-            "peak_source": peak_src + " (sustained figure: kernel timed inside a long step)", "traffic": None,
+            "peak_source": peak_src + " (sustained figure: kernel timed inside a long step)",
+            "traffic": _ncu_traffic() if path == "fused_tcgen05" else None,
+            "traffic_note": "DRAM read+write bytes of one launch (256 samples x 4096 rows) from profiles/r1_ncu_fused_pair_summary.txt; "
+                            "algorithmic bytes of that launch: 256 * 1.34 MB sampled bf16 weights + 6.4 MB inputs",
             "kernel_ms_per_step": pms.value / args.steps, "kernel_launches_per_step": pn.value / args.steps,
             "algorithmic_flops_per_forward": flops_fwd,
             "whole_step_frac_of_burst_peak": (forwards * flops_fwd / (ms * 1e-3)) / 1e12 / float(peaks["bf16_tflops"]),

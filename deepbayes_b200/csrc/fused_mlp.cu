@@ -1488,9 +1488,10 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   int CM = 1;
   if (const char* e = getenv("DBX_FUSED_CM")) CM = atoi(e);
   if (CM != 1 && CM != 2 && CM != 4) CM = 1;
-  // kernel variant: 1 = single-CTA (clusters only multicast), 2 = CTA pair with tensor-core output layer,
-  // 3 = CTA pair with FFMA output layer in two epilogue warpgroups (default when C <= 12)
-  int variant = (C <= kW3Pitch) ? 3 : 1;
+  // kernel variant: 1 = single-CTA (clusters only multicast); 2 = CTA pair (cta_group::2), output layer on the
+  // tensor cores -- the default; 3 = CTA pair with the output layer on FFMA in two epilogue warpgroups (kept as
+  // a measured negative result: broadcasting W3 to every row-thread is shared-memory-bandwidth bound)
+  int variant = 2;
   if (const char* e = getenv("DBX_FUSED_KERNEL")) variant = atoi(e);
   if (const char* e = getenv("DBX_FUSED_2CTA")) variant = atoi(e) ? 2 : 1;
   if (variant == 3 && C > kW3Pitch) variant = 1;

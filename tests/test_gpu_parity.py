@@ -248,7 +248,7 @@ def test_sample_split_independence(ctx):
     np.testing.assert_array_equal(cnt, c1 + c2)
 
 
-@pytest.mark.parametrize("cm", ["1", "2", "4"])
+@pytest.mark.parametrize("cm", ["1", "2", "4", "pair", "pair_ffma"])
 @pytest.mark.parametrize("dims,B,n", [([784, 512, 512, 10], 1000, 70), ([784, 512, 10], 700, 33), ([784, 128, 10], 300, 20),
                                        ([100, 256, 256, 7], 513, 40), ([784, 384, 384, 10], 260, 12)])
 def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n):
@@ -270,7 +270,11 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     g1, g2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
     assert eng.last_path() == "generic"
     monkeypatch.setenv("DBX_NO_FUSED", "0")
-    monkeypatch.setenv("DBX_FUSED_CM", cm)
+    if cm.startswith("pair"):   # cta_group::2 kernels (the default is "pair")
+        monkeypatch.setenv("DBX_FUSED_KERNEL", "2" if cm == "pair" else "3")
+    else:
+        monkeypatch.setenv("DBX_FUSED_KERNEL", "1")
+        monkeypatch.setenv("DBX_FUSED_CM", cm)
     monkeypatch.setenv("DBX_FUSED_NS", "16")   # several chunks -> accumulate path of finish_kernel
     for rep in range(3):
         f1, f2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
