@@ -175,16 +175,32 @@ sample_bf16_fast_kernel(const float* __restrict__ mu, const float* __restrict__ 
                         int64_t P16) {
   const uint64_t sample = (uint64_t)(s0 + blockIdx.y);
   __nv_bfloat16* wrow = W16 + (int64_t)blockIdx.y * P16 + dst_delta;   // dst index = flat index + dst_delta
-  for (int blk = blk_lo + blockIdx.x * blockDim.x + threadIdx.x; blk < blk_hi; blk += gridDim.x * blockDim.x) {
-    float z[4];
+  // two Philox blocks (8 consecutive weights) per thread and iteration: two independent Philox /
+  // Box-Muller chains in flight per thread
+  const int npair = (blk_hi - blk_lo + 1) >> 1;
+  for (int pi = blockIdx.x * blockDim.x + threadIdx.x; pi < npair; pi += gridDim.x * blockDim.x) {
+    const int blk = blk_lo + 2 * pi;
+    const bool two = (blk + 1 < blk_hi);
+    float z[8];
     philox_normal4(seed, sample, (uint64_t)blk, z);
+    philox_normal4(seed, sample, (uint64_t)(blk + 1), z + 4);
     const int j0 = blk << 2;
-    const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu + j0));
-    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sigma + j0));
-    uint2 v;
-    v.x = tc_pack_bf16x2(fmaf(inflate * s4.x, z[0], m4.x), fmaf(inflate * s4.y, z[1], m4.y));
-    v.y = tc_pack_bf16x2(fmaf(inflate * s4.z, z[2], m4.z), fmaf(inflate * s4.w, z[3], m4.w));
-    *reinterpret_cast<uint2*>(wrow + j0) = v;
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + j0));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(sigma + j0));
+    uint2 v0;
+    v0.x = tc_pack_bf16x2(fmaf(inflate * g0.x, z[0], m0.x), fmaf(inflate * g0.y, z[1], m0.y));
+    v0.y = tc_pack_bf16x2(fmaf(inflate * g0.z, z[2], m0.z), fmaf(inflate * g0.w, z[3], m0.w));
+    if (two) {
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(mu + j0 + 4));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(sigma + j0 + 4));
+      uint2 v1;
+      v1.x = tc_pack_bf16x2(fmaf(inflate * g1.x, z[4], m1.x), fmaf(inflate * g1.y, z[5], m1.y));
+      v1.y = tc_pack_bf16x2(fmaf(inflate * g1.z, z[6], m1.z), fmaf(inflate * g1.w, z[7], m1.w));
+      if ((((uintptr_t)(wrow + j0)) & 15) == 0) *reinterpret_cast<uint4*>(wrow + j0) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+      else { *reinterpret_cast<uint2*>(wrow + j0) = v0; *reinterpret_cast<uint2*>(wrow + j0 + 4) = v1; }
+    } else {
+      *reinterpret_cast<uint2*>(wrow + j0) = v0;
+    }
   }
 }
 
@@ -429,7 +445,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
       const int lo = (tab.src_off[i] + 3) >> 2, hi = tab.src_end[i] >> 2;   // whole Philox blocks inside the tensor
       if (hi <= lo || rg.n + 2 > DBX_MAX_RANGES) continue;
       if (lo > cursor) { rg.lo[rg.n] = cursor; rg.hi[rg.n] = lo; ++rg.n; }
-      dim3 grid((unsigned)std::min<int64_t>(cdiv(hi - lo, 256), 148 * 4), (unsigned)nc);
+      dim3 grid((unsigned)std::min<int64_t>(cdiv((hi - lo + 1) / 2, 256), 148 * 4), (unsigned)nc);
       DBX_LAUNCH(sample_bf16_fast_kernel, grid, 256, 0, st, m->mu, m->sigma, src.inflate, src.seed, src.s0 + c0, lo, hi,
                  tab.dst_off[i] - tab.src_off[i], W16, m->P16);
       cursor = hi;
@@ -719,6 +735,7 @@ int dbx_destroy(dbx_handle h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaFree(h->d_x); cudaFree(h->d_s1); cudaFree(h->d_s2);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev_posterior) cudaEventDestroy(h->ev_posterior);
   delete h;
   return 0;
 }
@@ -737,6 +754,8 @@ int dbx_set_gaussian(dbx_handle h, const float* mu, const float* sigma, int64_t 
   DBX_CUDA(cudaMemcpyAsync(h->mu, mu, (size_t)P * 4, k, st));
   DBX_CUDA(cudaMemcpyAsync(h->sigma, sigma, (size_t)P * 4, k, st));
   if (!on_device) DBX_CUDA(cudaStreamSynchronize(st));
+  if (!h->ev_posterior) DBX_CUDA(cudaEventCreateWithFlags(&h->ev_posterior, cudaEventDisableTiming));
+  DBX_CUDA(cudaEventRecord(h->ev_posterior, st));
   h->have_gaussian = true;
   return 0;
 }
@@ -745,6 +764,7 @@ int dbx_set_gaussian_rho(dbx_handle h, const float* mu, const float* rho, int64_
   if (dbx_set_gaussian(h, mu, rho, P, on_device, stream)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   DBX_LAUNCH(softplus_kernel, grid_for(P), 256, 0, st, h->sigma, h->sigma, P);
+  DBX_CUDA(cudaEventRecord(h->ev_posterior, st));
   return 0;
 }
 

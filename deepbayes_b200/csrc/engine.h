@@ -64,6 +64,7 @@ struct dbx_model {
   float* mu = nullptr;
   float* sigma = nullptr;
   bool have_gaussian = false;
+  cudaEvent_t ev_posterior = nullptr;   // recorded after the last upload of mu / sigma (side streams wait on it)
   const float* slab = nullptr;
   int64_t S = 0;
   dbx::Workspace ws;        // generic-path workspace

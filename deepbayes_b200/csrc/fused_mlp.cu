@@ -1389,6 +1389,7 @@ struct FusedState {
   int num_sms = 0;
   // weight sampling of chunk c+1 runs on a side stream while chunk c is in the fused kernel
   cudaStream_t side = nullptr;
+  bool used = false;   // ev_entry holds the end of the previous call's device work
   cudaEvent_t ev_entry = nullptr, ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
 };
 
@@ -1579,7 +1580,16 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   if (const char* e = getenv("DBX_FUSED_OVERLAP")) overlap = atoi(e) != 0;
   cudaStream_t sst = overlap ? fs->side : st;
   if (overlap) {
-    if (cudaEventRecord(fs->ev_entry, st) != cudaSuccess || cudaStreamWaitEvent(sst, fs->ev_entry, 0) != cudaSuccess) return -1;
+    // Sampling does not depend on this call's input, only on the previous call having finished with the weight
+    // buffers: wait for the event recorded at the END of the previous call, so the first chunk is drawn while the
+    // caller's H2D copy of x (enqueued on `st` just before this call) is still in flight.
+    if (fs->used && cudaStreamWaitEvent(sst, fs->ev_entry, 0) != cudaSuccess) return -1;
+    if (m->ev_posterior && cudaStreamWaitEvent(sst, m->ev_posterior, 0) != cudaSuccess) return -1;
+    if (src.stored || src.eps) {   // slab / injected eps may have been produced on `st` just before this call
+      static thread_local cudaEvent_t ev_in = nullptr;
+      if (!ev_in) cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+      if (cudaEventRecord(ev_in, st) != cudaSuccess || cudaStreamWaitEvent(sst, ev_in, 0) != cudaSuccess) return -1;
+    }
   }
   const int64_t nchunks = cdiv(n, ns);
   auto sample_chunk = [&](int64_t ci) -> int {
@@ -1636,6 +1646,8 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     }
     if (overlap && cudaEventRecord(fs->ev_consumed[bsel], st) != cudaSuccess) return -1;
   }
+  if (cudaEventRecord(fs->ev_entry, st) != cudaSuccess) return -1;
+  fs->used = true;
   return 1;
 }
 
