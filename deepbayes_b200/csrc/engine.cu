@@ -20,6 +20,7 @@ namespace dbx {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 static int g_last_path = 0;
+static bool g_used_tc = false;
 
 int set_err(const char* fmt, ...) {
   char buf[1024];
@@ -478,11 +479,18 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   // per-sample workspace bytes
   const size_t act_b = (size_t)B * m->max_feat * sizeof(T);
   const size_t w_b = kBf16 ? ((size_t)m->P16 * 2 + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
-  const size_t per = 2 * act_b + w_b + (size_t)B * C * 4 + 256;
+  // bf16 mode: Conv2D layers run as im2col + tcgen05 GEMM and need a column buffer
+  size_t col_b = 0;
+  bool use_tc = kBf16;
+  if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') use_tc = false;
+  if (use_tc)
+    for (auto& L : m->layers)
+      if (L.kind == DBX_CONV2D) col_b = std::max(col_b, (size_t)B * L.out_h * L.out_w * round_up(L.w_rows, 8) * 2);
+  const size_t per = 2 * act_b + w_b + (size_t)B * C * 4 + col_b + 256;
   const size_t xin_b = kBf16 ? round_up((size_t)B * m->in_feat * 2, 256) : 0;
   int64_t ns = (int64_t)std::max<size_t>(1, (ws_budget_bytes() - std::min(ws_budget_bytes(), xin_b)) / per);
   ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
-  if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 1024)) return 1;
+  if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 8192)) return 1;
   char* p = (char*)m->ws.ptr;
   T* xin = (T*)p; p += xin_b;
   T* act0 = (T*)p; p += round_up((size_t)ns * act_b, 256);
@@ -490,6 +498,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   float* logits = (float*)p; p += round_up((size_t)ns * B * C * 4, 256);
   T* Wc = (T*)p;
   float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * m->P16 * 2, 256)) : nullptr;
+  __nv_bfloat16* colbuf = (__nv_bfloat16*)(p + round_up((size_t)ns * w_b, 256) + 512);
 
   const T* x_in;
   if (kBf16) {
@@ -530,7 +539,30 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
       const int ldw = (int)(kBf16 ? L.w_cols_pad : L.w_cols);
       const int act = last ? DBX_ACT_LINEAR : L.act;  // last activation applied by the sink
       if (L.has_w) prof_begin(st);
-      if (L.kind == DBX_DENSE) {
+      bool done_tc = false;
+      if (kBf16 && use_tc && L.has_w && (last || L.units % 8 == 0)) {
+        // tensor-core path: per-sample GEMM on tcgen05 (Dense directly, Conv2D through im2col)
+        const __nv_bfloat16* A16 = (const __nv_bfloat16*)cur;
+        const int shared = (cur_ss == 0) ? 1 : 0;
+        if (L.kind == DBX_DENSE && L.in_feat % 8 == 0) {
+          done_tc = dense_tc_launch(A16, cur_ss, (int)L.in_feat, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc,
+                                    (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff, act,
+                                    last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units, last ? logits : nullptr,
+                                    B * C, st) == 0;
+        } else if (L.kind == DBX_CONV2D) {
+          const int Kp = (int)round_up(L.w_rows, 8);
+          const long long Mrows = (long long)B * L.out_h * L.out_w;
+          const long long col_ss = shared ? 0 : Mrows * Kp;
+          if (im2col_launch(A16, cur_ss, colbuf, col_ss, shared ? 1 : nc, (int)B, L, Kp, st) == 0)
+            done_tc = dense_tc_launch(colbuf, col_ss, Kp, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc,
+                                      (int)Mrows, L.units, (int)L.w_rows, Bbase, b_sstride, boff, act,
+                                      last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units,
+                                      last ? logits : nullptr, B * C, st) == 0;
+        }
+        if (done_tc) g_used_tc = true;
+      }
+      if (done_tc) {
+      } else if (L.kind == DBX_DENSE) {
         dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), (unsigned)nc);
         if (last) {
           DBX_LAUNCH((dense_kernel<T, float>), grid, 256, 0, st, cur, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw,
@@ -580,7 +612,7 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
   DBX_CHECK(src.stored ? (m->slab != nullptr) : m->have_gaussian,
             src.stored ? "no stored-sample slab set (dbx_set_samples)" : "no Gaussian posterior set (dbx_set_gaussian)");
   DBX_CUDA(cudaSetDevice(m->device));
-  g_last_path = 0;
+  g_last_path = 0; g_used_tc = false;
   DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
   {
     const int r = stream_mlp_run(m, x_dev, B, n, src, sink, st);
@@ -594,7 +626,9 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
       if (r < 0) return 1;
       if (r == 1) { g_last_path = 1; return 0; }
     }
-    return run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
+    const int rg = run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
+    if (g_used_tc) g_last_path = 3;
+    return rg;
   }
   DBX_CHECK(mode == DBX_MODE_FP32, "unknown mode %d", mode);
   return run_generic<float>(m, x_dev, B, n, src, sink, st);

@@ -115,6 +115,14 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
                   cudaStream_t st);
 void fused_mlp_free(dbx_model* m);
 
+// gemm_tc.cu: one layer of every sample of a chunk on tcgen05 (generic bf16 path); return 0 on success
+int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const __nv_bfloat16* Wbase,
+                    long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride,
+                    long long b_off, int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32,
+                    long long o32_sstride, cudaStream_t st);
+int im2col_launch(const __nv_bfloat16* in, long long in_sstride, __nv_bfloat16* out, long long out_sstride, int ns, int NB,
+                  const Layer& L, int Kp, cudaStream_t st);
+
 // stream_mlp.cu: small-batch (B <= 16) streaming path, fp32 FFMA, weights read / generated once.
 int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
                    cudaStream_t st);

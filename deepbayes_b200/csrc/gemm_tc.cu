@@ -1,0 +1,216 @@
+// Batched per-sample GEMM on tcgen05 for the GENERIC bf16 path: one Dense layer (or an im2col'd
+// Conv2D) of every posterior sample of a chunk,
+//     Y[s] = act( A[s] (M x K, bf16, K-major)  *  W_s (K x N, bf16, Keras (fan_in, fan_out) layout)  + b_s )
+// for models the fused MLP kernel does not cover (hidden width > 512, more than two hidden layers,
+// convolutions).  Classic Blackwell GEMM structure: TMA producer warp, one MMA-issuing warp
+// (tcgen05.mma, accumulator in TMEM), four epilogue warps (tcgen05.ld -> bias + activation ->
+// bf16 / fp32 stores).  One CTA per (128-row tile, <=256-column tile, sample).
+#include <algorithm>
+#include <cstdlib>
+#include "engine.h"
+#include "tc05.cuh"
+
+namespace dbx {
+
+using namespace tc05;
+
+constexpr int kGStages = 4;
+constexpr int kGStageBytes = 49152;   // A block [128 x 64] 16 KB + W blocks up to [64 x 256] 32 KB
+constexpr int kGThreads = 192;
+
+struct GemmParams {
+  int M, N, K, NT;          // NT = columns handled per CTA (multiple of 64, <= 256)
+  int a_shared;             // A is the same for every sample (layer 0)
+  const float* bias; long long b_sstride; long long b_off;
+  const int32_t* rows; long long row0;      // sample -> weight-row indirection of the bias array (chunk-local rows here)
+  int act;
+  __nv_bfloat16* out16; long long o16_sstride; int ld16;    // bf16 output [s][M][ld16] (next layer's A) or null
+  float* out32; long long o32_sstride;                      // fp32 output [s][M][N] (logits of the last layer) or null
+};
+
+struct __align__(8) GBarriers {
+  uint64_t full[kGStages], empty[kGStages];
+  uint64_t acc_full;
+  uint32_t tmem_slot;
+};
+
+extern __shared__ __align__(1024) uint8_t gemm_smem_raw[];
+
+__global__ void __launch_bounds__(kGThreads, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  GBarriers* bars = (GBarriers*)(smem + kGStages * kGStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * p.NT, m0 = blockIdx.y * 128, s = blockIdx.z;
+  const int nt = min(p.NT, ((p.N - n0 + 63) / 64) * 64);     // columns of this tile, multiple of 64
+  const int nblk = nt / 64;
+  const int kb_n = (p.K + 63) / 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < kGStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const uint32_t st = kb % kGStages, ph = (kb / kGStages) & 1;
+      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&bars->full[st]);
+        const uint32_t base = s_stage + st * kGStageBytes;
+        mbar_expect_tx(fb, 16384 + nblk * 8192);
+        if (p.a_shared) tma_load_2d(base, &tmA, fb, kb * 64, m0);
+        else tma_load_3d(base, &tmA, fb, kb * 64, m0, s);
+        for (int nb = 0; nb < nblk; ++nb) tma_load_3d(base + 16384 + nb * 8192, &tmW, fb, n0 + nb * 64, kb * 64, s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = make_idesc_bf16(128, nt, 0, 1);
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const uint32_t st = kb % kGStages, ph = (kb / kGStages) & 1;
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a16 = ((s_stage + st * kGStageBytes) & 0x3FFFF) >> 4;
+        const uint32_t a_lo = a16 | (1u << 16);
+        const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
+        const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+        for (int kk = 0; kk < ksteps; ++kk)
+          mma_ss_lh(tmem, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+        mma_commit(smem_u32(&bars->empty[st]));
+        if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int g = warp & 3;
+    const int row = g * 32 + lane;
+    const int gm = m0 + row;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    const long long brow = p.rows ? (long long)p.rows[s] : (p.row0 + s);
+    const float* bias = p.bias + brow * p.b_sstride + p.b_off;
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    fence_after_sync();
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_base + c0, v);
+      wait_ld();
+      if (gm < p.M) {
+        if (p.out16) {
+          __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0 + c0;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {   // 8 bf16 = 16 bytes per store
+            const int c = n0 + c0 + q4 * 8;
+            if (c + 8 <= p.N) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                   apply_act(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+              *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              for (int i = 0; i < 8; ++i)
+                if (c + i < p.N) dst[q4 * 8 + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q4 * 8 + i]) + bias[c + i]));
+            }
+          }
+        } else {
+          float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = n0 + c0 + i;
+            if (c < p.N) dst[c] = apply_act(p.act, __uint_as_float(v[i]) + bias[c]);
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// NHWC bf16 activations -> im2col rows [n*Ho*Wo][kh*kw*C (padded to Kp)] so that Conv2D becomes the GEMM above
+// (same (kh, kw, cin) ordering as the HWIO kernel flattened to [kh*kw*cin, cout]).
+__global__ void im2col_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long in_sstride, __nv_bfloat16* __restrict__ out,
+                                   long long out_sstride, int NB, int H, int Wd, int C, int Ho, int Wo, int kh, int kw,
+                                   int sh, int sw, int pt, int pl, int Kp) {
+  const int s = blockIdx.y;
+  const __nv_bfloat16* ip = in + (long long)s * in_sstride;
+  __nv_bfloat16* op = out + (long long)s * out_sstride;
+  const long long total = (long long)NB * Ho * Wo * Kp;
+  const int K = kh * kw * C;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(o % Kp);
+    long long r = o / Kp;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (k < K) {
+      const int c = k % C; const int t = k / C; const int j = t % kw, i = t / kw;
+      const int wo = (int)(r % Wo); long long r2 = r / Wo;
+      const int ho = (int)(r2 % Ho); const int nb = (int)(r2 / Ho);
+      const int hi = ho * sh + i - pt, wi = wo * sw + j - pl;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < Wd) v = ip[(((long long)nb * H + hi) * Wd + wi) * C + c];
+    }
+    op[o] = v;
+  }
+}
+
+static bool g_tc_ok = true;
+
+// Launch one layer.  A: bf16 [ns or 1][M][lda] (lda % 8 == 0).  W16 chunk layout as produced by sample_bf16_kernel.
+int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const __nv_bfloat16* Wbase,
+                    long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride,
+                    long long b_off, int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32,
+                    long long o32_sstride, cudaStream_t st) {
+  if (!g_tc_ok || !get_encode_fn()) return 1;
+  CUtensorMap tmA, tmW;
+  if (a_shared) {
+    uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, sb[1] = {(uint64_t)lda * 2};
+    uint32_t b[2] = {64, 128};
+    if (!make_tmap_bf16(&tmA, (void*)A, 2, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else {
+    uint64_t d[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)lda * 2, (uint64_t)a_sstride * 2};
+    uint32_t b[3] = {64, 128, 1};
+    if (!make_tmap_bf16(&tmA, (void*)A, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t d[3] = {(uint64_t)N, (uint64_t)K, (uint64_t)ns}, sb[2] = {(uint64_t)ldw * 2, (uint64_t)w_sstride_elems * 2};
+    uint32_t b[3] = {64, 64, 1};
+    if (!make_tmap_bf16(&tmW, (void*)Wbase, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.NT = (int)std::min<int64_t>(256, round_up(N, 64));
+  p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
+  p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
+  const int smem = kGStages * kGStageBytes + (int)sizeof(GBarriers) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { g_tc_ok = false; return 1; }
+    attr_done = true;
+  }
+  dim3 grid((unsigned)cdiv(N, p.NT), (unsigned)cdiv(M, 128), (unsigned)ns);
+  dense_tc_kernel<<<grid, kGThreads, smem, st>>>(tmA, tmW, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int im2col_launch(const __nv_bfloat16* in, long long in_sstride, __nv_bfloat16* out, long long out_sstride, int ns, int NB,
+                  const Layer& L, int Kp, cudaStream_t st) {
+  const long long total = (long long)NB * L.out_h * L.out_w * Kp;
+  dim3 grid((unsigned)std::min<long long>(std::max<long long>(cdiv(total, 256), 1), 148 * 32), (unsigned)ns);
+  im2col_bf16_kernel<<<grid, 256, 0, st>>>(in, in_sstride, out, out_sstride, NB, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w,
+                                           L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l, Kp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace dbx

@@ -250,4 +250,4 @@ class Engine:
         return out.cpu().numpy().view(np.uint32)
 
     def last_path(self) -> str:
-        return {0: "generic", 1: "fused_tcgen05", 2: "stream"}[self.lib.dbx_last_path()]
+        return {0: "generic", 1: "fused_tcgen05", 2: "stream", 3: "generic_tc"}[self.lib.dbx_last_path()]

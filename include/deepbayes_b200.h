@@ -147,7 +147,8 @@ int64_t dbx_launch_count(void);
  * the algorithmic FLOPs those launches carried and their count, and clears the record. */
 int dbx_profile(int enable);
 int dbx_profile_read(double* ms_total, double* flops_total, int64_t* launches);
-/* which kernels served the last compute call: 0 generic, 1 fused tcgen05 MLP, 2 small-batch streaming. */
+/* which kernels served the last compute call: 0 generic (CUDA cores), 1 fused tcgen05 MLP,
+ * 2 small-batch streaming, 3 generic with per-layer tcgen05 GEMMs (bf16 mode). */
 int dbx_last_path(void);
 
 #if defined(__GNUC__)

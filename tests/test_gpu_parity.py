@@ -135,7 +135,8 @@ def test_predict_bf16(ctx, golden, oracle, name, fused, monkeypatch):
     got = (s1 / float(n)).cpu().numpy()
     fusable = name in ("mlp_cfg1", "mlp_cfg2")
     small = c["B"] <= 16 and name != "cnn_small"      # small batches take the fp32 streaming kernel in any mode
-    assert eng.last_path() == ("stream" if small else "fused_tcgen05" if (fused and fusable) else "generic")
+    want = ("stream",) if small else ("fused_tcgen05",) if (fused and fusable) else ("generic", "generic_tc")
+    assert eng.last_path() in want
     want_bf = golden[name + "/predict_bf16"]   # oracle with bf16-rounded GEMM operands
     want_32 = golden[name + "/predict_fp32"]
     assert np.abs(got - want_32).max() <= BF16_ATOL
@@ -267,8 +268,13 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     eng.set_gaussian(mean, std)
     x = oracle.synthetic_x((B, dims[0]), seed=6)
     monkeypatch.setenv("DBX_NO_FUSED", "1")
+    monkeypatch.setenv("DBX_NO_TC", "1")     # reference = plain CUDA-core bf16 kernels
     g1, g2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
     assert eng.last_path() == "generic"
+    monkeypatch.setenv("DBX_NO_TC", "0")
+    t1, t2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)   # per-layer tcgen05 GEMMs
+    assert eng.last_path() == "generic_tc"   # at least the hidden layers are GEMM-eligible (widths % 8 == 0)
+    np.testing.assert_allclose((t1 / n).cpu().numpy(), (g1 / n).cpu().numpy(), rtol=0, atol=1.5e-3)
     monkeypatch.setenv("DBX_NO_FUSED", "0")
     if cm.startswith("pair"):   # cta_group::2 kernels (the default is "pair")
         monkeypatch.setenv("DBX_FUSED_KERNEL", "2" if cm == "pair" else "3")
