@@ -164,6 +164,30 @@ __global__ void im2col_bf16_kernel(const __nv_bfloat16* __restrict__ in, long lo
   }
 }
 
+// Same gather for C % 8 == 0 (and Kp == kh*kw*C): one thread moves 8 channels = 16 bytes.
+__global__ void im2col_bf16_vec8_kernel(const __nv_bfloat16* __restrict__ in, long long in_sstride,
+                                        __nv_bfloat16* __restrict__ out, long long out_sstride, int NB, int H, int Wd, int C,
+                                        int Ho, int Wo, int kh, int kw, int sh, int sw, int pt, int pl) {
+  const int s = blockIdx.y;
+  const uint4* ip = reinterpret_cast<const uint4*>(in + (long long)s * in_sstride);
+  uint4* op = reinterpret_cast<uint4*>(out + (long long)s * out_sstride);
+  const int C8 = C >> 3, taps = kh * kw;
+  const int K8 = taps * C8;                               // 16-byte groups per im2col row
+  const long long total = (long long)NB * Ho * Wo * K8;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int k8 = (int)(o % K8);
+    const long long r = o / K8;
+    const int c8 = k8 % C8, t = k8 / C8;
+    const int j = t % kw, i = t / kw;
+    const int wo = (int)(r % Wo); const long long r2 = r / Wo;
+    const int ho = (int)(r2 % Ho); const int nb = (int)(r2 / Ho);
+    const int hi = ho * sh + i - pt, wi = wo * sw + j - pl;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < Wd) v = __ldg(ip + (((long long)nb * H + hi) * Wd + wi) * C8 + c8);
+    op[o] = v;
+  }
+}
+
 static bool g_tc_ok = true;
 
 // Launch one layer.  A: bf16 [ns or 1][M][lda] (lda % 8 == 0).  W16 chunk layout as produced by sample_bf16_kernel.
@@ -205,6 +229,14 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
 
 int im2col_launch(const __nv_bfloat16* in, long long in_sstride, __nv_bfloat16* out, long long out_sstride, int ns, int NB,
                   const Layer& L, int Kp, cudaStream_t st) {
+  if (L.in_c % 8 == 0 && Kp == L.kh * L.kw * L.in_c && (in_sstride % 8) == 0 && (out_sstride % 8) == 0) {
+    const long long total8 = (long long)NB * L.out_h * L.out_w * (Kp / 8);
+    dim3 grid8((unsigned)std::min<long long>(std::max<long long>(cdiv(total8, 256), 1), 148 * 32), (unsigned)ns);
+    im2col_bf16_vec8_kernel<<<grid8, 256, 0, st>>>(in, in_sstride, out, out_sstride, NB, L.in_h, L.in_w, L.in_c, L.out_h,
+                                                   L.out_w, L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
   const long long total = (long long)NB * L.out_h * L.out_w * Kp;
   dim3 grid((unsigned)std::min<long long>(std::max<long long>(cdiv(total, 256), 1), 148 * 32), (unsigned)ns);
   im2col_bf16_kernel<<<grid, 256, 0, st>>>(in, in_sstride, out, out_sstride, NB, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w,
