@@ -1496,6 +1496,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   if (const char* e = getenv("DBX_FUSED_KERNEL")) variant = atoi(e);
   if (const char* e = getenv("DBX_FUSED_2CTA")) variant = atoi(e) ? 2 : 1;
   if (variant == 3 && C > kW3Pitch) variant = 1;
+  if (variant >= 2 && B <= 128 && !getenv("DBX_FUSED_KERNEL")) variant = 1;   // a single 128-row tile: a CTA pair would idle its second half
   if (variant < 1 || variant > 3) variant = 1;
   const bool two_cta = variant >= 2;
   if (two_cta) CM = 2;

@@ -86,7 +86,7 @@ def cfg4():
     fl = eng.flops_per_forward * B * n / (ms * 1e-3) / 1e12
     emit(config="4: Bayesian CNN conv32-conv64-pool-dense128-dense10, CIFAR-10 shape, n=256", B=B, ms=ms,
          value=B * n / (ms * 1e-3), unit="forwards/s", path=eng.last_path(), tflops=fl, frac_of_bf16_burst=fl / PEAKS["bf16_tflops"],
-         note="generic direct-conv kernels (CUDA cores); implicit-GEMM tcgen05 conv is the next step")
+         note="generic bf16 path: Conv2D = im2col + per-sample tcgen05 GEMM (dense_tc_kernel), Dense = dense_tc_kernel; an implicit-GEMM conv would remove the im2col round trip")
 
 
 def cfg5():
