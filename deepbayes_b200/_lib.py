@@ -49,6 +49,7 @@ _SIGS = {
     "dbx_set_gaussian_rho": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "dbx_get_gaussian": (C.c_int, [_p, _p, _p, _i64, _p]),
     "dbx_set_samples": (C.c_int, [_p, _p, _i64, _i64]),
+    "dbx_set_samples_strided": (C.c_int, [_p, _p, _i64, _i64, _i64]),
     "dbx_sample": (C.c_int, [_p, _u64, _i64, _i64, _p, _f, _p, _p, _p]),
     "dbx_predict": (C.c_int, [_p, _p, _i64, _i64, _u64, _i64, _p, _f, _i32, _i32, _i32, _p, _p, _p]),
     "dbx_predict_stored": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _i32, _i32, _i32, _p, _p, _p]),

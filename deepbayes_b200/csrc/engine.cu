@@ -96,12 +96,12 @@ __global__ void sample_f32_kernel(const float* __restrict__ mu, const float* __r
 __global__ void __launch_bounds__(256)
 sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
                    float inflate, uint64_t seed, int64_t s0, int P, const float* __restrict__ src,
-                   const int32_t* __restrict__ idx, int64_t j0row, const TensorTable tab, const BlockRanges rg,
+                   const int32_t* __restrict__ idx, int64_t j0row, int64_t src_stride, const TensorTable tab, const BlockRanges rg,
                    __nv_bfloat16* __restrict__ W16, int64_t P16, float* __restrict__ B32, int64_t PB) {
   const int s = blockIdx.y;
   const int nblk = (P + 3) >> 2;
   const uint64_t sample = (uint64_t)(s0 + s);
-  const float* srow = src ? src + (idx ? (int64_t)idx[s] : (j0row + s)) * (int64_t)P : nullptr;
+  const float* srow = src ? src + (idx ? (int64_t)idx[s] : (j0row + s)) * src_stride : nullptr;
   const float* erow = eps ? eps + (int64_t)s * P : nullptr;
   __nv_bfloat16* wrow = W16 + (int64_t)s * P16;
   float* brow = B32 + (int64_t)s * PB;
@@ -114,7 +114,7 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
     const bool full4 = (j0 + 4 <= P);
     float w[4];
     if (srow) {
-      if (full4 && (P & 3) == 0) { const float4 v = *reinterpret_cast<const float4*>(srow + j0); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+      if (full4 && (src_stride & 3) == 0) { const float4 v = *reinterpret_cast<const float4*>(srow + j0); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
       else { for (int i = 0; i < 4; ++i) w[i] = (j0 + i < P) ? srow[j0 + i] : 0.f; }
     } else {
       float z[4];
@@ -459,7 +459,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
     dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(most, 256), 148 * 4)), (unsigned)nc);
     DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
                (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
-               src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, tab, rg, W16,
+               src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, m->slab_stride, tab, rg, W16,
                m->P16, B32, pb_stride);
   }
   return 0;
@@ -518,8 +518,8 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
       if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
       Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
     } else if (src.stored) {
-      Wbase = (const T*)m->slab; w_sstride = m->P; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
-      Bbase = m->slab; b_sstride = m->P;
+      Wbase = (const T*)m->slab; w_sstride = m->slab_stride; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
+      Bbase = m->slab; b_sstride = m->slab_stride;
     } else {
       const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
       DBX_LAUNCH(sample_f32_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma,
@@ -816,7 +816,14 @@ int dbx_get_gaussian(dbx_handle h, float* mu_host, float* sigma_host, int64_t P,
 int dbx_set_samples(dbx_handle h, const float* slab_dev, int64_t S, int64_t P) {
   DBX_CHECK(h && slab_dev && S > 0, "null/empty slab");
   DBX_CHECK(P == h->P, "parameter count mismatch: model has %lld, slab rows have %lld", (long long)h->P, (long long)P);
-  h->slab = slab_dev; h->S = S;
+  h->slab = slab_dev; h->S = S; h->slab_stride = P;
+  return 0;
+}
+
+int dbx_set_samples_strided(dbx_handle h, const float* slab_dev, int64_t S, int64_t P, int64_t row_stride) {
+  if (dbx_set_samples(h, slab_dev, S, P)) return 1;
+  DBX_CHECK(row_stride >= P, "row_stride %lld < P %lld", (long long)row_stride, (long long)P);
+  h->slab_stride = row_stride;
   return 0;
 }
 
@@ -856,12 +863,12 @@ int dbx_forward_one(dbx_handle h, const float* x_dev, int64_t B, const float* W_
                     float* out_dev, void* stream) {
   DBX_CHECK(h && x_dev && W_dev && out_dev, "null argument");
   // a single explicit weight vector is a stored-sample posterior with S = 1
-  const float* keep = h->slab; const int64_t keepS = h->S;
-  h->slab = W_dev; h->S = 1;
+  const float* keep = h->slab; const int64_t keepS = h->S, keepStride = h->slab_stride;
+  h->slab = W_dev; h->S = 1; h->slab_stride = h->P;
   Source src; src.stored = true; src.j0 = 0;
   Sink sink; sink.kind = 0; sink.out_kind = out_kind; sink.sum1 = out_dev;
   const int r = run(h, x_dev, B, 1, src, sink, mode, (cudaStream_t)stream);
-  h->slab = keep; h->S = keepS;
+  h->slab = keep; h->S = keepS; h->slab_stride = keepStride;
   return r;
 }
 

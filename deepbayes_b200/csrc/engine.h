@@ -67,6 +67,7 @@ struct dbx_model {
   cudaEvent_t ev_posterior = nullptr;   // recorded after the last upload of mu / sigma (side streams wait on it)
   const float* slab = nullptr;
   int64_t S = 0;
+  int64_t slab_stride = 0;   // elements between stored samples (>= P; a multiple of 4 enables 128-bit loads)
   dbx::Workspace ws;        // generic-path workspace
   dbx::Workspace fused_ws;  // fused-path workspace
   // host-call staging (dbx_predict_host)

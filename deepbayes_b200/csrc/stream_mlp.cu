@@ -27,7 +27,7 @@ struct StreamParams {
   int nlayers, B, C, in_feat, maxw;
   StreamLayer L[kStreamMaxLayers];
   long long n;                 // samples in this call
-  long long P;
+  long long P; long long slab_stride;
   // source
   int stored;
   const float* slab; const int32_t* idx; long long j0;          // stored
@@ -94,7 +94,7 @@ stream_mlp_kernel(const StreamParams p) {
 
   for (long long si = blockIdx.x; si < p.n; si += gridDim.x) {
     const unsigned long long sample = (unsigned long long)(p.s0 + si);
-    const float* srow = p.stored ? p.slab + (p.idx ? (long long)p.idx[si] : (p.j0 + si)) * p.P : nullptr;
+    const float* srow = p.stored ? p.slab + (p.idx ? (long long)p.idx[si] : (p.j0 + si)) * p.slab_stride : nullptr;
     const float* erow = (!p.stored && p.eps) ? p.eps + si * p.P : nullptr;
     const float* hin = xs;
     float* hout = hA;
@@ -323,7 +323,7 @@ int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const
     S.K = (int)L.w_rows; S.N = (int)L.w_cols; S.act = L.act; S.w_off = (int)L.w_off; S.b_off = (int)L.b_off;
     // 128-bit loads need 4-aligned rows / offsets (and, for slab rows, P % 4 == 0)
     S.vec_ok = (S.N % 4 == 0) && (S.w_off % 4 == 0) && (S.b_off % 4 == 0) &&
-               (!(src.stored || src.eps) || (m->P % 4 == 0));   // slab / eps rows start at multiples of P
+               (src.stored ? (m->slab_stride % 4 == 0) : (!src.eps || m->P % 4 == 0));   // slab / eps row starts
     maxw = std::max(maxw, S.N);
   }
   if (nl == 0) return 0;
@@ -338,7 +338,7 @@ int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const
   const size_t part_b = (size_t)num_sms * 8 * 2 * BT * C * sizeof(float);
   if (ensure_ws(m->ws, std::max<size_t>(part_b, 256))) return -1;
   p.nlayers = nl; p.B = (int)B; p.C = C; p.in_feat = (int)m->in_feat; p.maxw = maxw; p.n = n; p.P = m->P;
-  p.stored = src.stored ? 1 : 0; p.slab = m->slab; p.idx = src.idx; p.j0 = src.j0;
+  p.stored = src.stored ? 1 : 0; p.slab = m->slab; p.slab_stride = m->slab_stride; p.idx = src.idx; p.j0 = src.j0;
   p.mu = m->mu; p.sigma = m->sigma; p.eps = src.eps; p.inflate = src.inflate; p.seed = src.seed; p.s0 = src.s0;
   p.unfused = src.unfused ? 1 : 0;
   p.x = x_dev;

@@ -150,8 +150,13 @@ class Engine:
         t = self._dev_f32(slab)
         if t.ndim != 2 or t.shape[1] != self.P:
             raise ValueError("slab must be [S,%d], got %r" % (self.P, tuple(t.shape)))
+        pitch = (self.P + 3) // 4 * 4          # 16-byte aligned rows -> 128-bit streaming loads
+        if pitch != self.P:
+            padded = self.torch.zeros((t.shape[0], pitch), dtype=self.torch.float32, device=self.device)
+            padded[:, :self.P] = t
+            t = padded
         self._slab = t
-        _lib.check(self.lib.dbx_set_samples(self.h, _ptr(t), t.shape[0], t.shape[1]))
+        _lib.check(self.lib.dbx_set_samples_strided(self.h, _ptr(t), t.shape[0], self.P, pitch))
 
     # ---- hot path ---------------------------------------------------------------------
     def sample(self, n=1, seed=0, s0=0, eps=None, inflate=1.0, return_eps=False):

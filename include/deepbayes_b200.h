@@ -81,6 +81,9 @@ int dbx_get_gaussian(dbx_handle h, float* mu_host, float* sigma_host, int64_t P,
 /* Stored-sample posterior (hmc.py:308-322, posteriormodel.py:46-54,77-78): slab_dev is an
  * HBM-resident [S,P] fp32 matrix, one stored weight sample per row (borrowed, not copied). */
 int dbx_set_samples(dbx_handle h, const float* slab_dev, int64_t S, int64_t P);
+/* Same with an explicit row pitch (elements, >= P): a pitch that is a multiple of 4 keeps every stored sample
+ * 16-byte aligned, which lets the streaming kernel use 128-bit loads. */
+int dbx_set_samples_strided(dbx_handle h, const float* slab_dev, int64_t S, int64_t P, int64_t row_stride);
 
 /* W_s = mu + (inflate*sigma) * eps_s for s in [s0, s0+n)  (posteriormodel.py:60-79,
  * optimizer.py:197-202, bayesbybackprop.py:176-181).  eps_dev: injected noise [n,P] fp32 or
