@@ -63,6 +63,8 @@ struct FusedParams {
   int w3f_off;                 // v3: floats of (b1|b2|b3) per sample = offset of the fp32 [H][12] output-layer kernel
   const __nv_bfloat16* w3;     // last-layer kernels of the chunk, blocked8 layout: sample s at w3 + s*P16
   long long P16; int w3_bytes;
+  int order;                   // v4: 0 = [q][s] contiguous ranges, 1 = [s][q] round-robin with running sums in `partial`
+  unsigned long long* visited; // v4 order 1: per cluster, bit q set when the cluster wrote its (cluster, q) slice
   long long* trace;            // debug timeline of block 0 (null in production): [0]=count, then (id, clock) pairs
 };
 
@@ -571,16 +573,24 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   fence_after_sync();
   const uint32_t tmem = bars->tmem_slot;
 
-  const long long u0 = ((long long)cluster_id * p.U) / p.NC;
-  const long long u1 = ((long long)(cluster_id + 1) * p.U) / p.NC;
+  // this cluster's units: order 0 = a contiguous range of the [q][s] flattening,
+  //                       order 1 = cluster_id, cluster_id + NC, ... of the [s][q] flattening (see fused_mlp4.cuh)
+  const long long u0 = p.order ? (long long)cluster_id : ((long long)cluster_id * p.U) / p.NC;
+  const long long u1 = p.order ? p.U : ((long long)(cluster_id + 1) * p.U) / p.NC;
+  const long long u_step = p.order ? (long long)p.NC : 1;
+  auto decode = [&](long long u, int& q, int& s) {
+    if (p.order) { s = (int)(u / p.Q); q = (int)(u - (long long)s * p.Q); }
+    else { q = (int)(u / p.ns); s = (int)(u - (long long)q * p.ns); }
+  };
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ===========================
     // Every copy lands in the issuing CTA's smem and signals the LEADER's `full` barrier; only
     // the leader arms it (expect_tx of the pair's total bytes).
     uint32_t it = 0, w3_n = 0, unit_n = 0;
-    for (long long u = u0; u < u1; ++u, ++unit_n) {
-      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
+    for (long long u = u0; u < u1; u += u_step, ++unit_n) {
+      int q, s;
+      decode(u, q, s);
       const int m0 = (q * CM + (int)rank) * 128;
       {
         const uint32_t b = unit_n & 1;
@@ -705,7 +715,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         fence_after_sync();
       };
 
-      for (long long u = u0; u < u1; ++u) {
+      for (long long u = u0; u < u1; u += u_step) {
         for (int c = 0; c < n_l1; ++c) {
           const int ncols = min(256, H - c * 256);
           const uint32_t idesc = make_idesc_bf16(256, ncols, 0, 1);
@@ -791,8 +801,10 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
     for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
     unsigned int cnt = 0;
-    int cur_q = (u0 < u1) ? (int)(u0 / p.ns) : -1;
+    int cur_q = -1;
+    if (u0 < u1) { int s_first; decode(u0, cur_q, s_first); }
     const int q_first = cur_q;
+    unsigned long long visited = 0ull;
 
     auto flush_segment = [&](int q) {
       const int seg = q - q_first;
@@ -830,9 +842,10 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       fence_before_sync();
     };
 
-    for (long long u = u0; u < u1; ++u, ++unit_n) {
-      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
-      if (q != cur_q) { flush_segment(cur_q); cur_q = q; }
+    for (long long u = u0; u < u1; u += u_step, ++unit_n) {
+      int q, s;
+      decode(u, q, s);
+      if (!p.order && q != cur_q) { flush_segment(cur_q); cur_q = q; }
       const uint32_t bb = unit_n & 1;
       const float* bias = bias_smem + bb * kBiasFloats;
       mbar_wait(smem_u32(&bars->bias_full[bb]), (unit_n >> 1) & 1);
@@ -887,22 +900,46 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int grow = (q * CM + (int)rank) * 128 + row;
       if (p.sink_kind == 0) {
         const float w = p.wts ? p.wts[s] : 1.f;
+        float pr[kMaxC];
         if (p.out_kind == DBX_OUT_LOGITS) {
 #pragma unroll
-          for (int i = 0; i < kMaxC; ++i) if (i < p.C) { acc1[i] = fmaf(w, z[i], acc1[i]); acc2[i] = fmaf(w * z[i], z[i], acc2[i]); }
+          for (int i = 0; i < kMaxC; ++i) pr[i] = (i < p.C) ? z[i] : 0.f;
         } else if (p.act_last == DBX_ACT_SOFTMAX) {
           float mx = z[0];
 #pragma unroll
           for (int i = 1; i < kMaxC; ++i) mx = fmaxf(mx, z[i]);
-          float e[kMaxC], den = 0.f;
+          float den = 0.f;
 #pragma unroll
-          for (int i = 0; i < kMaxC; ++i) { e[i] = (i < p.C) ? expf(z[i] - mx) : 0.f; den += e[i]; }
+          for (int i = 0; i < kMaxC; ++i) { pr[i] = (i < p.C) ? expf(z[i] - mx) : 0.f; den += pr[i]; }
           const float inv = 1.f / den;
 #pragma unroll
-          for (int i = 0; i < kMaxC; ++i) { const float pr = e[i] * inv; acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
+          for (int i = 0; i < kMaxC; ++i) pr[i] *= inv;
         } else {
 #pragma unroll
-          for (int i = 0; i < kMaxC; ++i) if (i < p.C) { const float pr = apply_act(p.act_last, z[i]); acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
+          for (int i = 0; i < kMaxC; ++i) pr[i] = (i < p.C) ? apply_act(p.act_last, z[i]) : 0.f;
+        }
+        if (!p.order) {
+#pragma unroll
+          for (int i = 0; i < kMaxC; ++i) { acc1[i] = fmaf(w, pr[i], acc1[i]); acc2[i] = fmaf(w * pr[i], pr[i], acc2[i]); }
+        } else {
+          // running sums of (cluster, q) live in global memory (L2 resident); only this thread touches this row
+          float* dst = p.partial + ((((long long)cluster_id * p.Q + q) * CM + rank) * 128 + row) * 32;
+          const bool first = !((visited >> q) & 1ull);
+          visited |= 1ull << q;
+#pragma unroll
+          for (int i = 0; i < kMaxC; i += 4) {
+            if (i < p.C) {
+              float4 o = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(dst + i);
+              o.x = fmaf(w, pr[i], o.x); o.y = fmaf(w, pr[i + 1], o.y); o.z = fmaf(w, pr[i + 2], o.z); o.w = fmaf(w, pr[i + 3], o.w);
+              *reinterpret_cast<float4*>(dst + i) = o;
+              if (p.want_sum2) {
+                float4 o2 = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(dst + 16 + i);
+                o2.x = fmaf(w * pr[i], pr[i], o2.x); o2.y = fmaf(w * pr[i + 1], pr[i + 1], o2.y);
+                o2.z = fmaf(w * pr[i + 2], pr[i + 2], o2.z); o2.w = fmaf(w * pr[i + 3], pr[i + 3], o2.w);
+                *reinterpret_cast<float4*>(dst + 16 + i) = o2;
+              }
+            }
+          }
         }
       } else {
         int best = 0; float bv = z[0];
@@ -911,11 +948,13 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (grow < p.B) {
           const int ok = (best == p.labels[grow]);
           if (p.flags) p.flags[(long long)s * p.B + grow] = (uint8_t)ok;
-          cnt += ok;
+          if (!p.order) cnt += ok;
+          else if (ok) atomicAdd(p.counts + grow, 1ull);
         }
       }
     }
-    if (cur_q >= 0) flush_segment(cur_q);
+    if (!p.order && cur_q >= 0) flush_segment(cur_q);
+    if (p.order && p.visited && tid == 64 && rank == 0) p.visited[cluster_id] = visited;
   }
 
   fence_before_sync();
@@ -1341,6 +1380,8 @@ fused_mlp3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1) tmem_dealloc2<512>(tmem);
 }
 
+#include "fused_mlp4.cuh"
+
 // Adds the per-(cluster, segment) partial sums in sample order.
 __global__ void finish_kernel(const float* __restrict__ partial, int NC, int maxseg, int CM, long long U, int ns, int B,
                               int C, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
@@ -1459,6 +1500,23 @@ static int launch_fused3(const CUtensorMap& tmX, const CUtensorMap& tmW1, const 
   return 0;
 }
 
+static int launch_fused4(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
+                         const FusedParams& p, cudaStream_t st) {
+  DBX_CUDA(cudaFuncSetAttribute(fused_mlp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k4SmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.NC * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)k4SmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp4_kernel, tmX, tmW1, tmW2, tmW3, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 static inline int grid_for2(int64_t total, int block = 256) {
   return (int)std::min<int64_t>(std::max<int64_t>(cdiv(total, block), 1), 148 * 16);
 }
@@ -1497,7 +1555,8 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   if (const char* e = getenv("DBX_FUSED_2CTA")) variant = atoi(e) ? 2 : 1;
   if (variant == 3 && C > kW3Pitch) variant = 1;
   if (variant >= 2 && B <= 128 && !getenv("DBX_FUSED_KERNEL")) variant = 1;   // a single 128-row tile: a CTA pair would idle its second half
-  if (variant < 1 || variant > 3) variant = 1;
+  if (variant < 1 || variant > 4) variant = 1;
+  if (variant == 4 && !(NH == 2 && H == k4H)) variant = 2;   // v4 is the 2-hidden-layer H = 512 kernel
   const bool two_cta = variant >= 2;
   if (two_cta) CM = 2;
   // v3 keeps the output-layer kernel as fp32 [H][12] behind the biases of each sample
@@ -1516,7 +1575,12 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   const size_t b_b = round_up((size_t)ns * PBx * 4, 1024);
   const int NCmax = std::max(1, fs->num_sms / CM);
   const int maxseg = (int)cdiv(Q, NCmax) + 2;
-  const size_t part_b = round_up((size_t)NCmax * maxseg * CM * 128 * 32 * 4, 1024);
+  // v4 work order: 1 = [s][q] round-robin (L2-friendly), needs Q <= 64 for the visited mask
+  const bool order_ok = (variant == 2 || variant == 4) && Q <= 64;
+  int order = order_ok ? 1 : 0;
+  if (const char* e = getenv("DBX_FUSED_ORDER")) order = (order_ok && atoi(e) != 0) ? 1 : 0;
+  const size_t part_b = round_up(std::max((size_t)NCmax * maxseg * CM * 128 * 32 * 4,
+                                          order ? (size_t)NCmax * Q * CM * 128 * 32 * 4 + (size_t)NCmax * 8 : (size_t)0), 1024);
   const size_t need = x_b + 2 * (w_b + b_b) + part_b;
   if (m->fused_ws.bytes < need) {
     if (ensure_ws(m->fused_ws, need)) return -1;
@@ -1536,8 +1600,8 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   CUtensorMap tmX, tmW1, tmW2, tmW3;
   {
     uint64_t d[2] = {(uint64_t)K0, (uint64_t)B}, s[1] = {(uint64_t)K0p * 2};
-    uint32_t b[2] = {64, 128};
-    if (!make_tmap_bf16(&tmX, X16, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
+    uint32_t b[2] = {variant == 4 ? 32u : 64u, 128};
+    if (!make_tmap_bf16(&tmX, X16, 2, d, s, b, variant == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
   }
   CUtensorMap tmW1b[2], tmW2b[2];
   for (int i = 0; i < 2; ++i) {
@@ -1547,8 +1611,9 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
       uint32_t b[3] = {bn, bk, 1};
       return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 3, d, sb, b, swz);
     };
-    if (!make_w(&tmW1b[i], dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
-    if (!make_w(&tmW2b[i], NH == 2 ? dl[1] : dl[0], 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
+    const uint32_t bk = variant == 4 ? 32 : 64;
+    if (!make_w(&tmW1b[i], dl[0], 64, bk, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
+    if (!make_w(&tmW2b[i], NH == 2 ? dl[1] : dl[0], 64, bk, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
   }
   (void)tmW1; (void)tmW2; (void)tmW3;
   CUtensorMap tmW3b[2];
@@ -1627,11 +1692,13 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     p.labels = sink.labels; p.flags = sink.flags ? sink.flags + c0 * B : nullptr; p.counts = sink.counts;
     p.partial = partial;
     p.w3 = W16 + Lout->w16_off; p.P16 = m->P16; p.w3_bytes = (int)(Lout->w_rows * Lout->w_cols_pad * 2);
+    p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
     p.trace = nullptr;
     if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
     prof_begin(st);
     int rc = 0;
-    if (variant == 3) rc = launch_fused3(tmX, tmW1c, tmW2c, p, smem, st);
+    if (variant == 4) rc = launch_fused4(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st);
+    else if (variant == 3) rc = launch_fused3(tmX, tmW1c, tmW2c, p, smem, st);
     else if (two_cta) rc = launch_fused2(tmX, tmW1c, tmW2c, tmW3b[bsel], p, smem, st);
     else if (CM == 1) rc = launch_fused<1>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     else if (CM == 2) rc = launch_fused<2>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
@@ -1640,8 +1707,11 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     prof_end(st, (double)m->flops * (double)B * nc);
     if (sink.kind == 0) {
       const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
-      finish_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.NC, maxseg, CM, p.U, nc, (int)B, C, overwrite, sink.sum1,
-                                                       sink.sum2);
+      if (order)
+        finish4_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.visited, p.NC, Q, CM, (int)B, C, overwrite, sink.sum1, sink.sum2);
+      else
+        finish_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.NC, maxseg, CM, p.U, nc, (int)B, C, overwrite, sink.sum1,
+                                                         sink.sum2);
       g_launches.fetch_add(1);
       if (cudaGetLastError() != cudaSuccess) { set_err("finish launch failed"); return -1; }
     }

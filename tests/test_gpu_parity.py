@@ -249,8 +249,8 @@ def test_sample_split_independence(ctx):
     np.testing.assert_array_equal(cnt, c1 + c2)
 
 
-@pytest.mark.parametrize("cm", ["1", "2", "4", "pair", "pair_ffma"])
-@pytest.mark.parametrize("dims,B,n", [([784, 512, 512, 10], 1000, 70), ([784, 512, 10], 700, 33), ([784, 128, 10], 300, 20),
+@pytest.mark.parametrize("cm", ["1", "2", "4", "pair", "pair_qs", "pair_ffma", "pair_smem", "pair_smem_qs"])
+@pytest.mark.parametrize("dims,B,n", [([784, 512, 512, 10], 1000, 70), ([300, 512, 512, 16], 5000, 9), ([784, 512, 10], 700, 33), ([784, 128, 10], 300, 20),
                                        ([100, 256, 256, 7], 513, 40), ([784, 384, 384, 10], 260, 12)])
 def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n):
     """The tcgen05 fused kernel (cluster multicast widths 1/2/4, ragged row tiles, several chunks
@@ -277,7 +277,9 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     np.testing.assert_allclose((t1 / n).cpu().numpy(), (g1 / n).cpu().numpy(), rtol=0, atol=1.5e-3)
     monkeypatch.setenv("DBX_NO_FUSED", "0")
     if cm.startswith("pair"):   # cta_group::2 kernels (the default is "pair")
-        monkeypatch.setenv("DBX_FUSED_KERNEL", "2" if cm == "pair" else "3")
+        # pair = v2 (H1 in TMEM), pair_ffma = v3, pair_smem = v4 (H1 in smem); default work order [s][q], *_qs = [q][s]
+        monkeypatch.setenv("DBX_FUSED_KERNEL", {"pair": "2", "pair_qs": "2", "pair_ffma": "3", "pair_smem": "4", "pair_smem_qs": "4"}[cm])
+        monkeypatch.setenv("DBX_FUSED_ORDER", "0" if cm.endswith("_qs") else "1")
     else:
         monkeypatch.setenv("DBX_FUSED_KERNEL", "1")
         monkeypatch.setenv("DBX_FUSED_CM", cm)

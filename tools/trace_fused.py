@@ -35,7 +35,17 @@ print("events", n, "units", len(starts))
 if len(starts) > 13:
     a, b = starts[10], starts[11]
     base = ev[a, 1]
+    compact = os.environ.get("TRACE_COMPACT", "1") == "1"
+    wait_acc = 0
     for i in range(a, b):
+        if compact and int(ev[i, 0]) in (150, 160):
+            continue
+        if compact and int(ev[i, 0]) in (151, 161):
+            wait_acc += ev[i, 1] - ev[i - 1, 1]
+            continue
+        if wait_acc:
+            print("                    (stage waits since last line: %d cycles)" % wait_acc)
+            wait_acc = 0
         print("%8d  +%6d  %s" % (ev[i, 1] - base, ev[i, 1] - ev[i - 1, 1], names.get(int(ev[i, 0]), str(ev[i, 0]))))
     per = (ev[starts[-1], 1] - ev[starts[5], 1]) / (len(starts) - 1 - 5)
     print("cycles per unit (steady):", per)
