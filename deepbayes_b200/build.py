@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for s in SOURCES:
         obj = os.path.join(HERE, "lib", s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("DBX_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)

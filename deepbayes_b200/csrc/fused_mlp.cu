@@ -65,6 +65,7 @@ struct FusedParams {
   long long P16; int w3_bytes;
   int order;                   // v4: 0 = [q][s] contiguous ranges, 1 = [s][q] round-robin with running sums in `partial`
   unsigned long long* visited; // v4 order 1: per cluster, bit q set when the cluster wrote its (cluster, q) slice
+  unsigned trace_only;            // 0 = all probes, else up to four probe ids, one per byte (a probe costs ~180 cycles on the warp that takes it)
   long long* trace;            // debug timeline of block 0 (null in production): [0]=count, then (id, clock) pairs
 };
 
@@ -80,11 +81,21 @@ struct __align__(8) Barriers {
 
 extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
 
+// After the wait on a TMA stage's `full` barrier the MMA warp needs no tcgen05 fence: the mbarrier completion
+// already orders the async-proxy writes before the MMA's operand reads, and tcgen05.fence::after_thread_sync is only
+// for ordering against OTHER threads' tcgen05 work (the epilogue barriers keep theirs).  -DDBX_STAGE_FENCE_ON=1
+// restores the per-stage fence for A/B measurements.
+#if defined(DBX_STAGE_FENCE_ON) && DBX_STAGE_FENCE_ON
+#define DBX_STAGE_FENCE() fence_after_sync()
+#else
+#define DBX_STAGE_FENCE() do {} while (0)
+#endif
+
 // debug timeline (block 0 only): each traced warp appends (id, clock) to its own lane of the
 // buffer with a private counter -- no atomics, so the probe costs a clock read and two stores.
 #define DBX_TRACE(id)                                                                         \
   do {                                                                                        \
-    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n < 2600) { \
+    if (p.trace != nullptr && (p.trace_only == 0 || (p.trace_only & 0xFF) == (id) || ((p.trace_only >> 8) & 0xFF) == (id) || ((p.trace_only >> 16) & 0xFF) == (id) || ((p.trace_only >> 24) & 0xFF) == (id)) && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_n < 2600) { \
       long long* _t = p.trace + 1 + (threadIdx.x >> 5) * 5200 + 2 * trace_n;                  \
       _t[0] = (id); _t[1] = clock64(); ++trace_n;                                             \
     }                                                                                         \
@@ -252,7 +263,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t ph;
       if (pkind0 == 1) ph = pb0 ? ph_act1_1 : ph_act1_0; else ph = pb0 ? ph_act2_1 : ph_act2_0;
       if (force) mbar_wait(bar, ph & 1);
-      else if (!mbar_try_wait(bar, ph & 1)) return false;
+      else if (!mbar_test_wait(bar, ph & 1)) return false;   // must not block: the next stage's MMAs are waiting to be issued
       if (pkind0 == 1) { if (pb0) ++ph_act1_1; else ++ph_act1_0; } else { if (pb0) ++ph_act2_1; else ++ph_act2_0; }
       fence_after_sync();
       DBX_TRACE(140);
@@ -297,7 +308,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         DBX_TRACE(100 + c);
         for (int kb = 0; kb < kb1; ++kb) {
           mbar_wait(st_full, st_ph);
-          fence_after_sync();
+          DBX_STAGE_FENCE();
           if (elect_one()) {
             const uint32_t a_lo = st_a16 | (1u << 16);                               // A: X block, K-major
             const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);  // B: LBO = n-block stride
@@ -341,7 +352,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
           }
           mbar_wait(st_full, st_ph);
-          fence_after_sync();
+          DBX_STAGE_FENCE();
           if (elect_one()) {
             const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
             // 128 consecutive k of packed H1: region sg>>1, packed column (sg&1)*64
@@ -516,7 +527,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // is what limits the single-CTA SS MMA to ~77 % of the tensor peak (tools/mma_rate.cu).
 // Same TMEM plan, same epilogue and same work split as fused_mlp_kernel<2>.
 // =======================================================================================
-constexpr int k2Stages = 6;
+#ifndef DBX_K2STAGES
+#define DBX_K2STAGES 6
+#endif
+constexpr int k2Stages = DBX_K2STAGES;
+constexpr int k2StagesS1 = 4;         // S1 variant: 64 KB of the ring hold the second half of H1
+constexpr int k2H1Bytes = 65536;
 constexpr int k2StageBytes = 32768;   // X block 16 KB + this CTA's half of the weight block 16 KB
 
 struct __align__(8) Barriers2 {
@@ -529,6 +545,12 @@ struct __align__(8) Barriers2 {
   uint32_t tmem_slot;
 };
 
+// S1 = true (opt-in experiment; two hidden layers, H > 256): the second half of H1 (layer-1 chunk 1) is packed into
+// SHARED memory (K-major SWIZZLE_128B, 64 KB) instead of TMEM, and the layer-2 MMAs over k >= 256 read it as an SS
+// operand; the 64 KB come out of the TMA ring (4 stages instead of 6; measured cost of the shorter ring: 1 %).
+// Built to test whether the TMEM read port limits layer 2 -- it does not (tools/mma_rate2.cu: tcgen05.ld streams do
+// not slow .ts MMAs), and the SS form is the slower MMA, so this is a measured negative result.
+template <bool S1>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
@@ -536,10 +558,14 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int CM = 2;
   uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  const uint32_t s_w3 = s_stage + k2Stages * k2StageBytes;
-  float* bias_smem = (float*)(smem + k2Stages * k2StageBytes + kW3Bytes / 2);
+  constexpr int NST = S1 ? k2StagesS1 : k2Stages;
+  constexpr int kH1Smem = S1 ? k2H1Bytes : 0;
+  uint8_t* h1_smem = smem + NST * k2StageBytes;
+  const uint32_t s_h1 = s_stage + NST * k2StageBytes;
+  const uint32_t s_w3 = s_h1 + kH1Smem;
+  float* bias_smem = (float*)(h1_smem + kH1Smem + kW3Bytes / 2);
   const uint32_t s_bias = smem_u32(bias_smem);
-  Barriers2* bars = (Barriers2*)(smem + k2Stages * k2StageBytes + kW3Bytes / 2 + 2 * kBiasFloats * 4);
+  Barriers2* bars = (Barriers2*)((uint8_t*)bias_smem + 2 * kBiasFloats * 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int trace_n = 0;
@@ -555,7 +581,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int l2_stages = H / 128;                // 2 k-blocks per stage
 
   if (tid == 0) {
-    for (int i = 0; i < k2Stages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->w3_full), 1); mbar_init(smem_u32(&bars->w3_empty), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->bias_full[i]), 1); mbar_init(smem_u32(&bars->bias_empty[i]), 128);
@@ -605,7 +631,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int ncols = min(256, H - c * 256);
         const int nhalf = ncols / 128;            // n-blocks (64 cols) per CTA
         for (int kb = 0; kb < kb1; ++kb, ++it) {
-          const uint32_t st = it % k2Stages, ph = (it / k2Stages) & 1;
+          const uint32_t st = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
           if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
@@ -633,7 +659,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       for (int j = 0; j < n_l2; ++j) {
         for (int sg = 0; sg < l2_stages; ++sg, ++it) {
-          const uint32_t st = it % k2Stages, ph = (it / k2Stages) & 1;
+          const uint32_t st = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
           if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
@@ -647,8 +673,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
     }
-    for (int k = 0; k < k2Stages; ++k, ++it) {   // tail: the leader's last commits must have landed here
-      const uint32_t st = it % k2Stages, ph = (it / k2Stages) & 1;
+    for (int k = 0; k < NST; ++k, ++it) {   // tail: the leader's last commits must have landed here
+      const uint32_t st = it % NST, ph = (it / NST) & 1;
       mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
     }
   } else if (warp == 1) {
@@ -659,7 +685,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t a16_0 = (s_stage & 0x3FFFF) >> 4;
       uint32_t st_full = full0, st_empty = empty0, st_a16 = a16_0;
       auto advance = [&]() {
-        if (++st_i == k2Stages) { st_i = 0; st_ph ^= 1; st_full = full0; st_empty = empty0; st_a16 = a16_0; }
+        if (++st_i == NST) { st_i = 0; st_ph ^= 1; st_full = full0; st_empty = empty0; st_a16 = a16_0; }
         else { st_full += 8; st_empty += 8; st_a16 += k2StageBytes >> 4; }
       };
       constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -673,6 +699,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t idesc_l2 = make_idesc_bf16(256, 128, 0, 1);
       // W3: one 8-column core-matrix block per CTA, k-groups 128 B apart
       const uint64_t w3desc0 = make_smem_desc(s_w3, 128, (uint32_t)(H * 16), SW_NONE);
+      const uint32_t h1_16 = (s_h1 & 0x3FFFF) >> 4;
 
       auto pump = [&](bool force) -> bool {
         if (pn == 0) return false;
@@ -680,7 +707,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint32_t ph;
         if (pkind0 == 1) ph = pb0 ? ph_act1_1 : ph_act1_0; else ph = pb0 ? ph_act2_1 : ph_act2_0;
         if (force) mbar_wait(bar, ph & 1);
-        else if (!mbar_try_wait(bar, ph & 1)) return false;
+        else if (!mbar_test_wait(bar, ph & 1)) return false;   // must not block: the next stage's MMAs are waiting to be issued
         if (pkind0 == 1) { if (pb0) ++ph_act1_1; else ++ph_act1_0; } else { if (pb0) ++ph_act2_1; else ++ph_act2_0; }
         fence_after_sync();
         DBX_TRACE(140);
@@ -725,7 +752,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           DBX_TRACE(100 + c);
           for (int kb = 0; kb < kb1; ++kb) {
             mbar_wait(st_full, st_ph);
-            fence_after_sync();
+            DBX_STAGE_FENCE();
             if (elect_one()) {
               const uint32_t a_lo = st_a16 | (1u << 16);
               const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
@@ -755,35 +782,68 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (NH == 1)
             push(c, tmem + c * 256, tmem + c * 256 + 128, (uint32_t)(c * 256 * 16), ncols / 16, c == n_l1 - 1, 1);
         }
+        // Layer 2.  tools/mma_rate2.cu: a .ts N=128 pair MMA takes 73.5 cycles when the MMAs are issued back to back,
+        // but ANY pause of the issuing thread between groups of 8 (20 cycles are enough) costs ~330 extra cycles per
+        // group -- the tensor pipe restarts -- which is what the per-stage bookkeeping (barrier wait, commit, pump)
+        // used to do four times per chunk.  So a whole chunk (chunk 0: each half, because its second half needs the
+        // epilogue of layer-1 chunk 1) is issued as ONE block: wait for all its TMA stages first, then 32 MMAs and
+        // their commits without anything in between.
         for (int j = 0; j < n_l2; ++j) {
           const int b = j & 1;
           const uint32_t dbuf = tmem + b * 256 + 128;
           flush_buf(b);
           wait_drained(b);
           DBX_TRACE(120 + j);
-          for (int sg = 0; sg < l2_stages; ++sg) {
-            if (j == 0 && (sg & 1) == 0) {
-              if ((sg >> 1) == 0) { mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
-              else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
+          int sg = 0;
+          while (sg < l2_stages) {
+            int nsg = l2_stages;
+            if (j == 0) {
+              if (sg == 0) {
+                mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0;
+                nsg = min(2, l2_stages);
+              } else {
+                if (S1) mbar_wait_cluster(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1);   // peer's smem stores
+                else mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1);
+                ++ph_act1_1;
+                nsg = l2_stages - sg;
+              }
+              fence_after_sync();
             }
-            DBX_TRACE(160);
-            mbar_wait(st_full, st_ph);
-            fence_after_sync();
-            DBX_TRACE(161);
+            {   // every stage of the block has landed (normally long ago: the producer runs ahead)
+              uint32_t f = st_full, i2 = st_i, ph = st_ph;
+              for (int t = 0; t < nsg; ++t) {
+                mbar_wait(f, ph);
+                if (++i2 == NST) { i2 = 0; ph ^= 1; f = full0; } else f += 8;
+              }
+            }
             if (elect_one()) {
-              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
-              const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
+              uint32_t e = st_empty, a16 = st_a16, i2 = st_i;
+              for (int t = 0; t < nsg; ++t) {
+                const int g = sg + t;
+                const uint32_t b_lo = (a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
+                if (S1 && g >= 2) {
+                  // k >= 256: A = H1 chunk 1 in shared memory, 64-wide k-block (g - 2) * 2 + kblk, 32 B per k-step
+                  const uint32_t a_lo = (h1_16 + (uint32_t)(g - 2) * (2u * 16384u >> 4)) | (1u << 16);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
-                mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (sg | i) > 0);
-              mma2_commit_mc(st_empty, kBoth);
+                  for (int i = 0; i < 8; ++i)
+                    mma2_ss_lh(dbuf, a_lo + (i >> 2) * (16384u >> 4) + (i & 3) * 2, kDescHi128,
+                               b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, 1);
+                } else {
+                  const uint32_t a0 = tmem + (uint32_t)(g >> 1) * 256 + (uint32_t)(g & 1) * 64;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
+                    mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (g | i) > 0);
+                }
+                mma2_commit_mc(e, kBoth);
+                if (++i2 == NST) { i2 = 0; e = empty0; a16 = a16_0; } else { e += 8; a16 += k2StageBytes >> 4; }
+              }
+              if (sg + nsg == l2_stages) mma2_commit_mc(smem_u32(&bars->acc2_full[b]), kBoth);
             }
             __syncwarp();
-            advance();
+            for (int t = 0; t < nsg; ++t) advance();
+            sg += nsg;
             pump(false);
           }
-          if (elect_one()) mma2_commit_mc(smem_u32(&bars->acc2_full[b]), kBoth);
-          __syncwarp();
           DBX_TRACE(130 + j);
           push(b, dbuf, dbuf + 64, (uint32_t)(j * 128 * 16), 8, j == n_l2 - 1, 2);
         }
@@ -842,6 +902,33 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       fence_before_sync();
     };
 
+    // S1: relu(acc + b) -> bf16 -> this row of the H1 chunk-1 operand in shared memory (8-row groups of 1024 B,
+    // 128 B per row, 16-byte chunks XOR-swizzled by row & 7 = SWIZZLE_128B K-major)
+    uint8_t* h1_row = h1_smem + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+    auto store_h1 = [&](uint32_t src, int ncols, const float* bias) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(src + c0, v);
+        wait_ld();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * i);
+          const float lo = fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f);
+          const float hi = fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f);
+          w[i] = pack_bf16x2(lo, hi);
+        }
+        uint8_t* blk = h1_row + (c0 >> 6) * 16384;
+        const int j0 = (c0 & 63) >> 3;            // first 16-byte chunk (0 or 4)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(blk + (((j0 + i) ^ sw) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      fence_before_sync();
+    };
+
     for (long long u = u0; u < u1; u += u_step, ++unit_n) {
       int q, s;
       decode(u, q, s);
@@ -873,9 +960,15 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++ph_acc[c];
         fence_after_sync();
         if (warp == 2) DBX_TRACE(200 + c);
-        pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
+        if (S1 && c == 1) {
+          store_h1(tmem + lane_base + 256, ncols, bias + p.b1_off + 256);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_release(smem_u32(&bars->act1_ready[1]), 0);
+        } else {
+          pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
+        }
         if (warp == 2) DBX_TRACE(210 + c);
         if (NH == 1) drain_l3(c, tmem + lane_base + c * 256 + 128);
       }
@@ -1134,7 +1227,7 @@ fused_mlp3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           DBX_TRACE(100 + c);
           for (int kb = 0; kb < kb1; ++kb) {
             mbar_wait(st_full, st_ph);
-            fence_after_sync();
+            DBX_STAGE_FENCE();
             if (elect_one()) {
               const uint32_t a_lo = st_a16 | (1u << 16);
               const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
@@ -1168,7 +1261,7 @@ fused_mlp3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
             }
             mbar_wait(st_full, st_ph);
-            fence_after_sync();
+            DBX_STAGE_FENCE();
             if (elect_one()) {
               const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
               const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
@@ -1466,9 +1559,12 @@ static int launch_fused(const CUtensorMap& tmX, const CUtensorMap& tmW1, const C
   return 0;
 }
 
+template <bool S1>
 static int launch_fused2(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
-                         const FusedParams& p, int smem, cudaStream_t st) {
-  DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                         const FusedParams& p, cudaStream_t st) {
+  constexpr int smem = (S1 ? k2StagesS1 * k2StageBytes + k2H1Bytes : k2Stages * k2StageBytes) + kW3Bytes / 2 +
+                       2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024;
+  DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<S1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.NC * 2));
   cfg.blockDim = dim3(kThreads);
@@ -1478,7 +1574,7 @@ static int launch_fused2(const CUtensorMap& tmX, const CUtensorMap& tmW1, const 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel, tmX, tmW1, tmW2, tmW3, p));
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<S1>, tmX, tmW1, tmW2, tmW3, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -1558,6 +1654,10 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   if (variant < 1 || variant > 4) variant = 1;
   if (variant == 4 && !(NH == 2 && H == k4H)) variant = 2;   // v4 is the 2-hidden-layer H = 512 kernel
   const bool two_cta = variant >= 2;
+  // v2 only, opt-in (DBX_FUSED_H1SMEM=1): second half of H1 in shared memory.  Measured slower (5.84 vs 5.59 ms per
+  // config-2 step): the SS N=128 pair MMA costs 106 cycles against 73.5 for the .ts form (tools/mma_rate2.cu).
+  bool h1_smem = false;
+  if (const char* e = getenv("DBX_FUSED_H1SMEM")) h1_smem = variant == 2 && NH == 2 && H > 256 && atoi(e) != 0;
   if (two_cta) CM = 2;
   // v3 keeps the output-layer kernel as fp32 [H][12] behind the biases of each sample
   const int64_t pbs = round_up(m->PB, 4);
@@ -1693,13 +1793,15 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     p.partial = partial;
     p.w3 = W16 + Lout->w16_off; p.P16 = m->P16; p.w3_bytes = (int)(Lout->w_rows * Lout->w_cols_pad * 2);
     p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
-    p.trace = nullptr;
+    p.trace = nullptr; p.trace_only = 0;
+    if (const char* e = getenv("DBX_FUSED_TRACE_ONLY")) p.trace_only = (unsigned)strtoul(e, nullptr, 10);
     if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
     prof_begin(st);
     int rc = 0;
     if (variant == 4) rc = launch_fused4(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st);
     else if (variant == 3) rc = launch_fused3(tmX, tmW1c, tmW2c, p, smem, st);
-    else if (two_cta) rc = launch_fused2(tmX, tmW1c, tmW2c, tmW3b[bsel], p, smem, st);
+    else if (two_cta) rc = h1_smem ? launch_fused2<true>(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st)
+                             : launch_fused2<false>(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st);
     else if (CM == 1) rc = launch_fused<1>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     else if (CM == 2) rc = launch_fused<2>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
     else rc = launch_fused<4>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);

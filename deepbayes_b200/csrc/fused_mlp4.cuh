@@ -45,14 +45,6 @@ struct __align__(8) Barriers4 {
 
 constexpr int k4SmemBytes = k4Stages * k4StageBytes + k4H1Bytes + kW3Bytes / 2 + 2 * kBiasFloats * 4 + (int)sizeof(Barriers4) + 1024;
 
-// release at cluster scope: the peer's generic-proxy smem writes (H1) must be visible to the
-// tensor core reads the leader triggers after it sees this arrival
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
@@ -200,7 +192,7 @@ fused_mlp4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t bar = smem_u32(&bars->act2_ready[b]);
         const uint32_t ph = b ? ph_act2_1 : ph_act2_0;
         if (force) mbar_wait(bar, ph & 1);
-        else if (!mbar_try_wait(bar, ph & 1)) return false;
+        else if (!mbar_test_wait(bar, ph & 1)) return false;   // must not block: the next stage's MMAs are waiting to be issued
         if (b) ++ph_act2_1; else ++ph_act2_0;
         fence_after_sync();
         DBX_TRACE(140);
@@ -242,7 +234,7 @@ fused_mlp4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           DBX_TRACE(100 + c);
           for (int kb = 0; kb < kb1; ++kb) {
             mbar_wait(st_full, st_ph);
-            fence_after_sync();
+            DBX_STAGE_FENCE();
             if (elect_one()) {
               const uint32_t a_lo = st_a16 | (1u << 16);
               const uint32_t b_lo = (st_a16 + (k4XBytes >> 4)) | ((k4BlkBytes >> 4) << 16);
@@ -272,7 +264,7 @@ fused_mlp4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (j == 0 && kb == 0) { mbar_wait_cluster(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
             if (j == 0 && kb == kL2Stages / 2) { mbar_wait_cluster(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
             mbar_wait(st_full, st_ph);
-            fence_after_sync();
+            DBX_STAGE_FENCE();
             if (elect_one()) {
               // 32-wide k-block kb = half (kb & 1) of the 64-wide H1 block kb >> 1
               const uint32_t a_lo = (h1_16 + (uint32_t)(kb >> 1) * (16384u >> 4) + (uint32_t)(kb & 1) * 4u) | (1u << 16);

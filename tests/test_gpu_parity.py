@@ -249,7 +249,7 @@ def test_sample_split_independence(ctx):
     np.testing.assert_array_equal(cnt, c1 + c2)
 
 
-@pytest.mark.parametrize("cm", ["1", "2", "4", "pair", "pair_qs", "pair_ffma", "pair_smem", "pair_smem_qs"])
+@pytest.mark.parametrize("cm", ["1", "2", "4", "pair", "pair_qs", "pair_h1half", "pair_ffma", "pair_smem", "pair_smem_qs"])
 @pytest.mark.parametrize("dims,B,n", [([784, 512, 512, 10], 1000, 70), ([300, 512, 512, 16], 5000, 9), ([784, 512, 10], 700, 33), ([784, 128, 10], 300, 20),
                                        ([100, 256, 256, 7], 513, 40), ([784, 384, 384, 10], 260, 12)])
 def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n):
@@ -277,8 +277,10 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     np.testing.assert_allclose((t1 / n).cpu().numpy(), (g1 / n).cpu().numpy(), rtol=0, atol=1.5e-3)
     monkeypatch.setenv("DBX_NO_FUSED", "0")
     if cm.startswith("pair"):   # cta_group::2 kernels (the default is "pair")
-        # pair = v2 (H1 in TMEM), pair_ffma = v3, pair_smem = v4 (H1 in smem); default work order [s][q], *_qs = [q][s]
-        monkeypatch.setenv("DBX_FUSED_KERNEL", {"pair": "2", "pair_qs": "2", "pair_ffma": "3", "pair_smem": "4", "pair_smem_qs": "4"}[cm])
+        # pair = v2 (the default: H1 packed in TMEM), pair_h1half = v2 with the second half of H1 in smem, pair_ffma = v3,
+        # pair_smem = v4 (all of H1 in smem); default work order [s][q], *_qs = [q][s]
+        monkeypatch.setenv("DBX_FUSED_KERNEL", {"pair": "2", "pair_qs": "2", "pair_h1half": "2", "pair_ffma": "3", "pair_smem": "4", "pair_smem_qs": "4"}[cm])
+        monkeypatch.setenv("DBX_FUSED_H1SMEM", "1" if cm == "pair_h1half" else "0")
         monkeypatch.setenv("DBX_FUSED_ORDER", "0" if cm.endswith("_qs") else "1")
     else:
         monkeypatch.setenv("DBX_FUSED_KERNEL", "1")

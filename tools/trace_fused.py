@@ -32,6 +32,23 @@ for j in range(4):
 # print units 10..12 (steady state)
 starts = [i for i in range(n) if ev[i, 0] == 100]
 print("events", n, "units", len(starts))
+if os.environ.get("DBX_FUSED_TRACE_ONLY"):
+    ids = sorted(set(int(v) for v in ev[:, 0]))
+    # median offset of every selected probe from the preceding probe 100 of the same unit
+    for pid in ids:
+        if pid == 100:
+            continue
+        offs = []
+        for a, b in zip(starts[5:-1], starts[6:]):
+            for i in range(a + 1, b):
+                if ev[i, 0] == pid:
+                    offs.append(ev[i, 1] - ev[a, 1])
+                    break
+        if offs:
+            print("probe %d: median offset from unit start %.0f" % (pid, np.median(offs)))
+    d = np.diff(ev[starts, 1])
+    print("cycles per unit with a single probe per unit: median %.0f  mean %.0f  min %d  max %d" % (np.median(d), d.mean(), d.min(), d.max()))
+    sys.exit(0)
 if len(starts) > 13:
     a, b = starts[10], starts[11]
     base = ev[a, 1]
