@@ -63,6 +63,7 @@ struct FusedParams {
   int w3f_off;                 // v3: floats of (b1|b2|b3) per sample = offset of the fp32 [H][12] output-layer kernel
   const __nv_bfloat16* w3;     // last-layer kernels of the chunk, blocked8 layout: sample s at w3 + s*P16
   long long P16; int w3_bytes;
+  int chunk;                   // index of this launch within the call (order 1 keeps its running sums across launches)
   int order;                   // v4: 0 = [q][s] contiguous ranges, 1 = [s][q] round-robin with running sums in `partial`
   unsigned long long* visited; // v4 order 1: per cluster, bit q set when the cluster wrote its (cluster, q) slice
   unsigned trace_only;            // 0 = all probes, else up to four probe ids, one per byte (a probe costs ~180 cycles on the warp that takes it)
@@ -864,7 +865,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int cur_q = -1;
     if (u0 < u1) { int s_first; decode(u0, cur_q, s_first); }
     const int q_first = cur_q;
-    unsigned long long visited = 0ull;
+    // order 1: the (cluster, q) slices persist over the chunk launches of one call; finish4_kernel runs once at the end
+    unsigned long long visited = (p.order && p.chunk > 0 && p.visited) ? p.visited[cluster_id] : 0ull;
 
     auto flush_segment = [&](int q) {
       const int seg = q - q_first;
@@ -1758,6 +1760,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     }
   }
   const int64_t nchunks = cdiv(n, ns);
+  int nc_first = 1;
   auto sample_chunk = [&](int64_t ci) -> int {
     const int b = (int)(ci & 1);
     const int64_t c0 = ci * ns;
@@ -1792,7 +1795,7 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     p.labels = sink.labels; p.flags = sink.flags ? sink.flags + c0 * B : nullptr; p.counts = sink.counts;
     p.partial = partial;
     p.w3 = W16 + Lout->w16_off; p.P16 = m->P16; p.w3_bytes = (int)(Lout->w_rows * Lout->w_cols_pad * 2);
-    p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
+    p.chunk = (int)ci; p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
     p.trace = nullptr; p.trace_only = 0;
     if (const char* e = getenv("DBX_FUSED_TRACE_ONLY")) p.trace_only = (unsigned)strtoul(e, nullptr, 10);
     if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
@@ -1809,12 +1812,18 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
     prof_end(st, (double)m->flops * (double)B * nc);
     if (sink.kind == 0) {
       const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
-      if (order)
-        finish4_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.visited, p.NC, Q, CM, (int)B, C, overwrite, sink.sum1, sink.sum2);
-      else
+      if (order) {
+        if (ci == 0) nc_first = p.NC;
+        if (ci + 1 == nchunks) {   // the slices carried the sums of every chunk
+          finish4_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.visited, nc_first, Q, CM, (int)B, C, sink.accumulate ? 0 : 1,
+                                                           sink.sum1, sink.sum2);
+          g_launches.fetch_add(1);
+        }
+      } else {
         finish_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.NC, maxseg, CM, p.U, nc, (int)B, C, overwrite, sink.sum1,
                                                          sink.sum2);
-      g_launches.fetch_add(1);
+        g_launches.fetch_add(1);
+      }
       if (cudaGetLastError() != cudaSuccess) { set_err("finish launch failed"); return -1; }
     }
     if (overlap && cudaEventRecord(fs->ev_consumed[bsel], st) != cudaSuccess) return -1;

@@ -297,7 +297,7 @@ fused_mlp4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
     unsigned int cnt = 0;
     int cur_q = -1, q_first = -1;
-    unsigned long long visited = 0ull;
+    unsigned long long visited = (p.order && p.chunk > 0 && p.visited) ? p.visited[cluster_id] : 0ull;   // slices persist over a call's launches
     if (u_begin < u_end) { int s0; decode(u_begin, cur_q, s0); q_first = cur_q; }
     // this thread's row inside an H1 k-block: 8-row groups of 1024 B, 128 B per row, 16-byte chunks XOR-swizzled by (row & 7)
     uint8_t* h1_row = h1_smem + (row >> 3) * 1024 + (row & 7) * 128;
