@@ -475,6 +475,87 @@ _PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _PH_W0, _PH_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 
 
+# ---------------------------------------------------------------------------------------
+# Interval bound propagation over sampled weights
+# ---------------------------------------------------------------------------------------
+def propagate_interval(W, b, x_l, x_u, marg=0.0, b_marg=0.0):
+    """One Dense layer on an interval, centre/radius form in float64 (verifiers.py:23-41):
+    h_mu = x_mu W, x_rad = x_r |W|, W_rad = |x_mu| W_r, Quad = |x_r| |W_r|;
+    h_u = h_mu + x_rad + W_rad + Quad + (b + b_marg), h_l = h_mu - x_rad - W_rad - Quad + (b - b_marg).
+    (x_u + x_l)/2 and (x_u - x_l)/2 are formed in the dtype of the incoming bounds and THEN cast (:26-27)."""
+    x_l, x_u = np.asarray(x_l), np.asarray(x_u)
+    x_mu = ((x_u + x_l) / 2).astype(np.float64)
+    x_r = ((x_u - x_l) / 2).astype(np.float64)
+    W_mu = np.asarray(W).astype(np.float64)
+    W_r = np.zeros_like(W_mu) if np.isscalar(marg) and marg == 0 else np.broadcast_to(np.asarray(marg, np.float64), W_mu.shape)
+    b_u = (np.asarray(b) + b_marg).astype(np.float64)
+    b_l = (np.asarray(b) - b_marg).astype(np.float64)
+    h_mu = x_mu @ W_mu
+    x_rad = x_r @ np.abs(W_mu)
+    W_rad = np.abs(x_mu) @ W_r
+    quad = np.abs(x_r) @ np.abs(W_r)
+    h_u = h_mu + x_rad + W_rad + quad + b_u
+    h_l = h_mu - x_rad - W_rad - quad + b_l
+    return h_l, h_u
+
+
+def ibp_forward(layers, weights, x, eps, predict=False):
+    """`IBP(model, inp, weights, eps, predict)` (verifiers.py:68-95) for Dense / weightless layers:
+    input box clip(x -+ eps, 0, 1) (predict=False) or x -+ eps; every Dense through
+    propagate_interval; the layer's activation on both bounds, except that with predict=False
+    the LAST layer's activation is skipped (:90-91), i.e. the result is a logit interval.
+    Returns (h_l, h_u) float64."""
+    x = np.asarray(x)
+    if not predict:
+        h_u = np.clip(x + eps, 0.0, 1.0)
+        h_l = np.clip(x - eps, 0.0, 1.0)
+    else:
+        h_u, h_l = x + eps, x - eps
+    wi = 0
+    for i, l in enumerate(layers):
+        if l.kind == "flatten":
+            h_u, h_l = h_u.reshape(h_u.shape[0], -1), h_l.reshape(h_l.shape[0], -1)
+            continue
+        if l.kind != "dense":
+            raise NotImplementedError("oracle IBP covers Dense / Flatten (propagate_conv2d, verifiers.py:11-21, is not restated)")
+        h_l, h_u = propagate_interval(weights[wi], weights[wi + 1], h_l, h_u)
+        wi += 2
+        if (not predict) and i >= len(layers) - 1:
+            continue
+        h_l, h_u = _act(l.activation, h_l), _act(l.activation, h_u)
+    return h_l, h_u
+
+
+def worst_case_logits(logit_l, logit_u, cls, depth=None):
+    """v1 * logit_l + v2 * logit_u with v1 = one_hot(cls), v2 = 1 - v1 (verifiers.py:549-552, :590-593):
+    the true class takes its lower bound, every other class its upper bound."""
+    logit_l, logit_u = np.asarray(logit_l), np.asarray(logit_u)
+    C = logit_l.shape[-1] if depth is None else depth
+    v1 = np.eye(C, dtype=logit_l.dtype)[np.asarray(cls).reshape(-1)]
+    v1 = v1.reshape(logit_l.shape[:-1] + (C,)) if v1.shape[0] != 1 else np.broadcast_to(v1[0], logit_l.shape)
+    return (1 - v1) * logit_u + v1 * logit_l
+
+
+def chernoff_verification(layers, mean, std, x, eps, cls, n, noise, inflate=1.0, order="f64"):
+    """`chernoff_bound_verification` (verifiers.py:537-557) with the weight noise injected: for each of
+    the n posterior samples, IBP logits on the eps-ball, worst case w.r.t. cls, the last layer's
+    activation, and the SUM over samples (the reference returns the running sum, not the mean).
+    Also returns the per-sample predicate argmax(worst case) == cls that massart_bound_check
+    (:588-634, verify=True, classification=True) counts."""
+    last_act = layers[-1].activation
+    total = None
+    flags = []
+    for s in range(n):
+        w = sample_gaussian(mean, std, noise[s], inflate, order)
+        lo, hi = ibp_forward(layers, w, x, eps, predict=False)
+        wc = worst_case_logits(lo, hi, cls)
+        sm = _act(last_act, wc)
+        total = sm if total is None else total + sm
+        flags.append(np.argmax(wc, axis=-1) == np.asarray(cls).reshape(-1))
+    return total, np.asarray(flags)
+
+
+
 def philox4x32_10(ctr, key):
     """Philox4x32-10 (Salmon et al., SC'11) on arrays: ctr [..,4] uint32, key [..,2] uint32."""
     c = [np.asarray(ctr[..., i], np.uint32).copy() for i in range(4)]

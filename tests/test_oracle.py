@@ -221,3 +221,56 @@ def test_oracle_matches_reference_bbb_run(oracle, golden_dir):
     np.random.seed(SEED_BBB)
     s0 = np.random.normal(loc=pm[0], scale=oracle.softplus(rho[0]))
     np.testing.assert_allclose(s0, ref["bbb_sample_W0"], rtol=1e-6, atol=1e-9)
+
+
+SEED_IBP = 424242
+
+
+def test_oracle_matches_reference_ibp_run(oracle, golden_dir):
+    """oracle.ibp_forward / chernoff_verification against the outputs of the reference's own
+    verifiers.IBP / chernoff_bound_verification (tests/golden/make_reference_ibp_fixtures.py)."""
+    ref = np.load(os.path.join(golden_dir, "reference_ibp.npz"))
+    mean, var = _vogn(golden_dir)
+    L = oracle.mlp([784, 128, 10])
+    x, eps = ref["x"], float(ref["eps"][0])
+    lo, hi = oracle.ibp_forward(L, [np.asarray(t, np.float32) for t in mean], x, eps, predict=False)
+    np.testing.assert_allclose(lo, ref["ibp_mean_l"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(hi, ref["ibp_mean_u"], rtol=1e-12, atol=1e-12)
+    assert (lo <= hi).all()
+    det = oracle.forward(L, mean, x, dtype=np.float64, out="logits")
+    assert (lo <= det + 1e-9).all() and (det <= hi + 1e-9).all()        # the interval contains the nominal logits
+    lo, hi = oracle.ibp_forward(L, [np.asarray(t, np.float32) for t in mean], x, eps, predict=True)
+    np.testing.assert_allclose(lo, ref["ibp_mean_predict_l"], rtol=1e-6, atol=1e-9)   # softmax on the bounds, fp32 in the stand-in
+    np.testing.assert_allclose(hi, ref["ibp_mean_predict_u"], rtol=1e-6, atol=1e-9)
+    # one sampled weight set: the reference draws with the global RNG, Keras stores fp32
+    np.random.seed(SEED_IBP)
+    w = [np.asarray(t, np.float32) for t in oracle.sample_reference_rng(mean, var)]
+    np.testing.assert_array_equal(w[2], ref["ibp_sample_W1"])
+    lo, hi = oracle.ibp_forward(L, w, x, eps)
+    np.testing.assert_allclose(lo, ref["ibp_sample_l"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(hi, ref["ibp_sample_u"], rtol=1e-12, atol=1e-12)
+    # chernoff_bound_verification: 16 samples, running SUM of softmax(worst case)
+    n, cls = int(ref["chernoff_n"][0]), int(ref["chernoff_cls"][0])
+    assert n == 16
+    np.random.seed(SEED_IBP)
+    noise = [[np.random.standard_normal(t.shape) for t in mean] for _ in range(n)]
+    total, flags = oracle.chernoff_verification(L, mean, var, x[:1], eps, [cls], n, noise)
+    np.testing.assert_allclose(total, ref["chernoff_sum"], rtol=2e-6, atol=1e-7)
+    assert flags.shape == (n, 1)
+
+
+def test_ibp_interval_properties(oracle):
+    """Size-independent properties: eps = 0 collapses the interval onto the plain forward; the
+    interval widens monotonically with eps; worst-case logits pick lower/upper by class."""
+    L = oracle.mlp([30, 24, 16, 7])
+    mean, std = oracle.synthetic_posterior(L, seed=4, sigma_scale=0.5)
+    x = oracle.synthetic_x((5, 30), seed=1)
+    lo0, hi0 = oracle.ibp_forward(L, mean, x, 0.0)
+    np.testing.assert_allclose(lo0, hi0, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(lo0, oracle.forward(L, mean, x, dtype=np.float64, out="logits"), rtol=1e-6, atol=1e-6)
+    lo1, hi1 = oracle.ibp_forward(L, mean, x, 0.01)
+    lo2, hi2 = oracle.ibp_forward(L, mean, x, 0.05)
+    assert (lo2 <= lo1 + 1e-12).all() and (hi1 <= hi2 + 1e-12).all()
+    wc = oracle.worst_case_logits(lo1, hi1, [0, 1, 2, 3, 4])
+    for r in range(5):
+        assert wc[r, r] == lo1[r, r] and (np.delete(wc[r], r) == np.delete(hi1[r], r)).all()
