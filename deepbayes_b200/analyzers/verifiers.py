@@ -45,6 +45,15 @@ def chernoff_sample_bound(confidence=0.95, delta=0.3):
     return math.ceil((1 / (2 * epsilon ** 2)) * math.log(2 / delta))
 
 
+def _mode_of(model, override=None):
+    """Arithmetic mode of the device path: PosteriorModel.mode / Optimizer.compute_mode (an optimizer's own
+    `.mode` is the reference's "classification" / "regression" switch, optimizer.py:60)."""
+    for m in (override, getattr(model, "compute_mode", None), getattr(model, "mode", None)):
+        if m in ("bf16", "fp32"):
+            return m
+    return "bf16"
+
+
 def _engine_of(model):
     eng = model.engine() if callable(getattr(model, "engine", None)) else getattr(model, "_engine", None)
     if eng is None:
@@ -60,7 +69,7 @@ def statistical_robustness(model, adv_inputs, labels, n=None, confidence=0.95, d
     counts, n, interval=Clopper-Pearson per input[, flags])."""
     eng = _engine_of(model)
     n = chernoff_sample_bound(confidence, delta) if n is None else int(n)
-    mode = mode or getattr(model, "mode", getattr(model, "compute_mode", "bf16"))
+    mode = _mode_of(model, mode)
     s0 = model._take_ids(n)
     res = eng.count_predicate(adv_inputs, labels, n, model.seed, s0, None, 1.0, mode, return_flags)
     counts = (res[0] if return_flags else res).cpu().numpy()
@@ -71,18 +80,54 @@ def statistical_robustness(model, adv_inputs, labels, n=None, confidence=0.95, d
     return out
 
 
-def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
-    """verifiers.py:563-653 with verify=False semantics: each iteration draws one posterior
-    sample, evaluates the worst-case input and applies the predicate; the loop stops at the
-    Massart halting bound (or the Chernoff bound).  The device evaluates the 0/1 outcomes for
-    whole blocks of samples at once and the halting rule walks them in order, so the result
-    equals the sequential loop on the same sample sequence.
+def _flat(weights):
+    return np.concatenate([np.asarray(w, np.float32).ravel() for w in weights])
 
-    Differences from the reference, stated: the perturbed input is supplied by the caller
-    (``adv=`` kwarg, default ``inp`` itself; FGSM is SURVEY.md 8(f) rank 3), the predicate is
-    ``argmax == cls`` (``cls=`` kwarg; the tutorials' predicate), and verify=True (IBP) is
-    not built.  Returns (successes/iterations, iterations, mean/iterations) like :653 (mean
-    is zero unless chernoff override, as in the reference)."""
+
+def IBP(model, inp, weights, eps, predict=False):
+    """`IBP(model, inp, weights, eps, predict=False)` (verifiers.py:68-95) on the device: the logit interval
+    (h_l, h_u) of the eps-ball around ``inp`` (clipped to [0,1]) under the explicit weight list ``weights``.
+    predict=True (un-clipped box, last activation applied to the bounds) is the regression branch and is not built.
+    Dense / Flatten models; fp32 arithmetic (the reference uses float64)."""
+    if predict:
+        raise NotImplementedError("IBP(predict=True) (verifiers.py:73-74, :92-94) is not built")
+    eng = _engine_of(model)
+    a = np.asarray(inp, np.float32)
+    lo, hi = eng.ibp_one(a.reshape(-1, eng.K), eps, _flat(weights), mode="fp32")
+    shape = a.shape[:-1] + (eng.C,)
+    return lo.cpu().numpy().reshape(shape), hi.cpu().numpy().reshape(shape)
+
+
+def chernoff_bound_verification(model, inp, eps, cls, **kwargs):
+    """`chernoff_bound_verification` (verifiers.py:537-557): n = ceil(ln(2/delta) / (2 (1-confidence)^2)) posterior
+    samples; for each, IBP logits of the eps-ball, worst case w.r.t. ``cls`` (lower bound of the true class, upper
+    bound of the others), the last layer's activation; returns the SUM over samples, like the reference (:556-557).
+    ``inp`` may hold several rows, with one class per row (the reference takes one input).  All n samples run in one
+    device call; kwarg mode="fp32"|"bf16" (default: the model's)."""
+    delta = kwargs.get('delta', 0.3)
+    confidence = kwargs.get('confidence', 0.95)
+    eng = _engine_of(model)
+    n = chernoff_sample_bound(confidence, delta)
+    mode = _mode_of(model, kwargs.get('mode'))
+    a = np.asarray(inp, np.float32)
+    x2 = a.reshape(-1, eng.K)
+    labels = np.broadcast_to(np.asarray(cls, np.int32).reshape(-1), (x2.shape[0],))
+    s0 = model._take_ids(n)
+    out = eng.ibp_predict(x2, eps, labels, n, model.seed, s0, None, 1.0, mode, want=("worst",))
+    return out["worst"].cpu().numpy().reshape(a.shape[:-1] + (eng.C,))
+
+
+def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
+    """verifiers.py:563-653: each iteration draws one posterior sample, evaluates the worst case and applies the
+    predicate; the loop stops at the Massart halting bound (or the Chernoff bound).  The device evaluates the 0/1
+    outcomes for whole blocks of samples at once and the halting rule walks them in order, so the result equals the
+    sequential loop on the same sample sequence.
+
+    verify=True, classification=True (:588-603): the worst case comes from IBP over the eps-ball (`dbx_ibp_predict`).
+    verify=False (:622-625): the perturbed input is supplied by the caller (``adv=`` kwarg, default ``inp`` itself;
+    FGSM is SURVEY.md 8(f) rank 3).  In both cases the predicate is ``argmax == cls`` (``cls=`` kwarg; the tutorials'
+    predicate).  Returns (successes/iterations, iterations, mean/iterations) like :653 (mean is zero unless chernoff
+    override, as in the reference)."""
     delta = kwargs.get('delta', 0.3)
     alpha = kwargs.get('alpha', 0.05)
     confidence = kwargs.get('confidence', 0.95)
@@ -90,12 +135,12 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
     cls = kwargs.get('cls', None)
     adv = kwargs.get('adv', inp)
     block = int(kwargs.get('block', 4096))
-    if verify:
-        raise NotImplementedError("verify=True needs the IBP forward (verifiers.py:23-95), SURVEY.md 8(f) rank 1")
+    if verify and not kwargs.get('classification', False):
+        raise NotImplementedError("verify=True for regression (verifiers.py:605-620, IBP predict=True) is not built")
     if cls is None:
         raise ValueError("pass cls=<true class>: the device predicate is argmax == cls")
     eng = _engine_of(model)
-    mode = getattr(model, "mode", getattr(model, "compute_mode", "bf16"))
+    mode = _mode_of(model, kwargs.get('mode'))
     epsilon = 1 - confidence
     chernoff_bound = math.ceil((1 / (2 * epsilon ** 2)) * math.log(2 / delta))
     successes, iterations = 0.0, 0.0
@@ -106,7 +151,11 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
     while not done:
         nb = int(min(block, chernoff_bound + 1 - iterations))
         s0 = model._take_ids(nb)
-        _, fl = eng.count_predicate(np.asarray(adv).reshape(1, -1), [int(cls)], nb, model.seed, s0, None, 1.0, mode, True)
+        if verify:
+            fl = eng.ibp_predict(np.asarray(inp).reshape(1, -1), eps, [int(cls)], nb, model.seed, s0, None, 1.0, mode,
+                                 want=(), return_flags=True)["flags"]
+        else:
+            _, fl = eng.count_predicate(np.asarray(adv).reshape(1, -1), [int(cls)], nb, model.seed, s0, None, 1.0, mode, True)
         flags = fl.cpu().numpy().reshape(-1)
         pos = 0
         while pos < len(flags):

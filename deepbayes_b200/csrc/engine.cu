@@ -618,6 +618,10 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   return 0;
 }
 
+}  // namespace dbx
+#include "ibp.cuh"
+namespace dbx {
+
 static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink, int mode,
                cudaStream_t st) {
   DBX_CHECK(B > 0 && n > 0, "B and n must be positive (B=%lld n=%lld)", (long long)B, (long long)n);
@@ -914,6 +918,40 @@ int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32
   Sink sink; sink.kind = 1; sink.accumulate = accumulate; sink.labels = labels_dev; sink.flags = flags_dev;
   sink.counts = (unsigned long long*)counts_dev;
   return run(h, x_dev, K, n, src, sink, mode, (cudaStream_t)stream);
+}
+
+int dbx_ibp_predict(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const int32_t* labels_dev, int64_t n,
+                    uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, int32_t mode,
+                    int32_t accumulate, float* sum_worst_dev, float* sum_lower_dev, float* sum_upper_dev, uint8_t* flags_dev,
+                    int64_t* counts_dev, void* stream) {
+  DBX_CHECK(h && x_dev, "null argument");
+  DBX_CHECK(B > 0 && n > 0, "B and n must be positive (B=%lld n=%lld)", (long long)B, (long long)n);
+  DBX_CHECK(eps >= 0.f, "eps must be >= 0");
+  DBX_CHECK(labels_dev || (!sum_worst_dev && !counts_dev), "worst-case outputs need the class labels");
+  DBX_CHECK(sum_worst_dev || sum_lower_dev || sum_upper_dev || counts_dev, "no output requested");
+  DBX_CHECK(!flags_dev || counts_dev, "flags need counts");
+  Source src; src.stored = stored != 0; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0; src.j0 = j0;
+  DBX_CHECK(src.stored ? (h->slab != nullptr && j0 >= 0 && j0 + n <= h->S) : h->have_gaussian,
+            src.stored ? "stored rows out of range / no slab set" : "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  IbpSink sink; sink.labels = labels_dev; sink.sum_worst = sum_worst_dev; sink.sum_lower = sum_lower_dev; sink.sum_upper = sum_upper_dev;
+  sink.counts = (unsigned long long*)counts_dev; sink.flags = flags_dev; sink.accumulate = accumulate;
+  g_last_path = 0; g_used_tc = false;
+  int rc;
+  if (mode == DBX_MODE_BF16) { rc = run_ibp<__nv_bfloat16>(h, x_dev, B, eps, clip01, n, src, sink, (cudaStream_t)stream); if (g_used_tc) g_last_path = 3; }
+  else { DBX_CHECK(mode == DBX_MODE_FP32, "unknown mode %d", mode); rc = run_ibp<float>(h, x_dev, B, eps, clip01, n, src, sink, (cudaStream_t)stream); }
+  return rc;
+}
+
+int dbx_ibp_one(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const float* W_dev, int32_t mode,
+                float* lower_dev, float* upper_dev, void* stream) {
+  DBX_CHECK(h && x_dev && W_dev && lower_dev && upper_dev, "null argument");
+  const float* keep = h->slab; const int64_t keepS = h->S, keepStride = h->slab_stride;
+  h->slab = W_dev; h->S = 1; h->slab_stride = h->P;
+  const int rc = dbx_ibp_predict(h, x_dev, B, eps, clip01, nullptr, 1, 0, 0, nullptr, 1.f, 1, 0, mode, 0, nullptr, lower_dev, upper_dev,
+                                 nullptr, nullptr, stream);
+  h->slab = keep; h->S = keepS; h->slab_stride = keepStride;
+  return rc;
 }
 
 int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, uint64_t seed, int64_t s0, float inflate,

@@ -235,6 +235,48 @@ class Engine:
                                                 _lib.MODE[mode], 0, _ptr(flags), _ptr(counts), _stream()))
         return (counts, flags) if return_flags else counts
 
+    def ibp_predict(self, x, eps, labels=None, n=1, seed=0, s0=0, noise=None, inflate=1.0, mode="bf16", clip=True,
+                    stored=False, j0=0, want=("worst",), return_flags=False):
+        """Interval bound propagation over n posterior samples (verifiers.py:23-41, 68-95, 537-557, 588-634).
+        ``want`` picks the outputs: "worst" = sum over samples of softmax(worst-case logits) [B,C], "lower" /
+        "upper" = sums of the logit bounds [B,C], "counts" = per input, the number of samples whose worst case
+        still has argmax == label (with return_flags also the [n,B] 0/1 flags).  Returns a dict of device tensors."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        lab = None
+        if labels is not None:
+            lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1)).to(self.device)
+            if lab.numel() != B:
+                raise ValueError("need one label per input row (%d rows, %d labels)" % (B, lab.numel()))
+        z = lambda: torch.zeros((B, self.C), dtype=torch.float32, device=self.device)   # noqa: E731
+        out = {k: z() for k in ("worst", "lower", "upper") if k in want}
+        counts = torch.zeros(B, dtype=torch.int64, device=self.device) if ("counts" in want or return_flags) else None
+        flags = torch.empty((n, B), dtype=torch.uint8, device=self.device) if return_flags else None
+        e = None if noise is None else self._dev_f32(noise).reshape(n, self.P)
+        _lib.check(self.lib.dbx_ibp_predict(self.h, _ptr(xt), B, float(eps), 1 if clip else 0, _ptr(lab), n, seed, s0, _ptr(e),
+                                            float(inflate), 1 if stored else 0, j0, _lib.MODE[mode], 0, _ptr(out.get("worst")),
+                                            _ptr(out.get("lower")), _ptr(out.get("upper")), _ptr(flags), _ptr(counts), _stream()))
+        if counts is not None:
+            out["counts"] = counts
+        if flags is not None:
+            out["flags"] = flags
+        return out
+
+    def ibp_one(self, x, eps, weights_flat, mode="fp32", clip=True):
+        """`IBP(model, inp, weights, eps)` with explicit weights (verifiers.py:68-95): (lower, upper) logits [B,C]."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        w = self._dev_f32(weights_flat).reshape(-1)
+        if w.numel() != self.P:
+            raise ValueError("need %d weights, got %d" % (self.P, w.numel()))
+        lo = torch.empty((B, self.C), dtype=torch.float32, device=self.device)
+        hi = torch.empty_like(lo)
+        _lib.check(self.lib.dbx_ibp_one(self.h, _ptr(xt), B, float(eps), 1 if clip else 0, _ptr(w), _lib.MODE[mode], _ptr(lo), _ptr(hi),
+                                        _stream()))
+        return lo, hi
+
     def predict_host(self, x: np.ndarray, n, seed=0, s0=0, inflate=1.0, mode="bf16", out_kind="probs", variance=False):
         """Host buffers in, host buffers out: the H2D copy of x and the D2H copy of the mean
         happen inside the C call (this is the bench's `e2e` path)."""

@@ -130,6 +130,21 @@ int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32
                         uint64_t seed, int64_t s0, const float* eps_dev, float inflate, int32_t mode,
                         int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream);
 
+/* Interval bound propagation over posterior samples (deepbayes/analyzers/verifiers.py: propagate_interval :23-41,
+ * IBP :68-95, and its per-sample use in chernoff_bound_verification :537-557 / massart_bound_check :588-634).
+ * For each of the n samples (Gaussian: global ids s0.., optional injected noise [n,P]; stored != 0: slab rows j0..)
+ * the input box clip(x -+ eps, 0, 1) (clip01 = 0: x -+ eps) goes through the Dense layers in centre/radius form;
+ * outputs, all optional: sum over samples of softmax(worst case) [B,C] (worst case = lower logit of labels[b], upper
+ * logit of every other class), of the lower / upper logits [B,C], and per input the number of samples (and the
+ * per-sample flags [n,B]) whose worst case still has argmax == labels[b].  Dense / Flatten models only. */
+int dbx_ibp_predict(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const int32_t* labels_dev, int64_t n,
+                    uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, int32_t mode,
+                    int32_t accumulate, float* sum_worst_dev, float* sum_lower_dev, float* sum_upper_dev, uint8_t* flags_dev,
+                    int64_t* counts_dev, void* stream);
+/* `IBP(model, inp, weights, eps)` with one explicit flat weight vector (verifiers.py:68-95): logit bounds [B,C]. */
+int dbx_ibp_one(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const float* W_dev, int32_t mode,
+                float* lower_dev, float* upper_dev, void* stream);
+
 /* Host-buffer form of dbx_predict, the call PosteriorModel.predict(x, n) binds to: copies x
  * (host, [B,K] fp32) to the device, runs the loop, writes mean = sum1/n ([B,C]) and, if
  * var_host != NULL, the per-class variance sum2/n - mean^2 back to host memory. */

@@ -506,3 +506,121 @@ def test_reference_run_vectors(golden_dir, oracle):
     pred, ws, _ = opt.forward_sample(oracle.synthetic_x((16, 30), seed=3), eps=noise, return_weights=True)
     np.testing.assert_allclose(pred, ref["bbb_step_predictions"], rtol=FP32_RTOL, atol=FP32_ATOL)
     np.testing.assert_allclose(ws[0], ref["bbb_step_model_W0"], rtol=3e-7, atol=6e-8)
+
+
+# ---------------------------------------------------------------------------------------
+# Interval bound propagation over sampled weights
+# ---------------------------------------------------------------------------------------
+def _mlp_engine(dims, oracle, seed=4, sigma_scale=0.5):
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    L = oracle.mlp(dims)
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    eng = Engine(db.Sequential(layers))
+    mean, std = oracle.synthetic_posterior(L, seed=seed, sigma_scale=sigma_scale)
+    eng.set_gaussian(mean, std)
+    return L, eng, mean, std
+
+
+@pytest.mark.parametrize("dims,B,n", [([30, 24, 16, 7], 5, 6), ([784, 128, 10], 9, 4), ([100, 72, 40, 10], 70, 3)])
+def test_ibp_fp32_matches_oracle(oracle, dims, B, n):
+    """dbx_ibp_predict (fp32 mode, injected weight noise) against oracle.ibp_forward / chernoff_verification,
+    the float64 restatement pinned on the reference's own verifiers.IBP run."""
+    L, eng, mean, std = _mlp_engine(dims, oracle)
+    x = oracle.synthetic_x((B, dims[0]), seed=1)
+    labels = np.random.Generator(np.random.Philox(3)).integers(0, dims[-1], size=B).astype(np.int32)
+    noise = oracle.synthetic_eps(L, n, seed=2)
+    nf = np.stack([oracle.flatten_list(e) for e in noise])
+    eps = 0.01
+    out = eng.ibp_predict(x, eps, labels, n, noise=nf, mode="fp32", want=("worst", "lower", "upper", "counts"), return_flags=True)
+    want_l = np.zeros((B, dims[-1])); want_u = np.zeros((B, dims[-1]))
+    for s in range(n):
+        w = oracle.sample_gaussian(mean, std, noise[s], order="f32")
+        lo, hi = oracle.ibp_forward(L, w, x, eps)
+        want_l += lo; want_u += hi
+    scale = max(np.abs(want_l).max(), np.abs(want_u).max())
+    np.testing.assert_allclose(out["lower"].cpu().numpy(), want_l, rtol=1e-5, atol=2e-6 * scale)
+    np.testing.assert_allclose(out["upper"].cpu().numpy(), want_u, rtol=1e-5, atol=2e-6 * scale)
+    total, flags = oracle.chernoff_verification(L, mean, std, x, eps, labels, n, noise, order="f32")
+    np.testing.assert_allclose(out["worst"].cpu().numpy(), total, rtol=2e-5, atol=1e-6)
+    np.testing.assert_array_equal(out["flags"].cpu().numpy().astype(bool), flags)
+    np.testing.assert_array_equal(out["counts"].cpu().numpy(), flags.sum(0))
+    assert (out["lower"] <= out["upper"]).all()
+
+
+def test_ibp_matches_reference_run(oracle, golden_dir):
+    """The CUDA path against the committed outputs of the reference's own verifiers.IBP and
+    chernoff_bound_verification on the VOGN tutorial posterior (tests/golden/reference_ibp.npz)."""
+    import deepbayes_b200 as db
+    from deepbayes_b200 import formats
+    from deepbayes_b200.analyzers import verifiers
+    ref = np.load(os.path.join(golden_dir, "reference_ibp.npz"))
+    pm = db.PosteriorModel(os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior"), mode="fp32")
+    x, eps = ref["x"], float(ref["eps"][0])
+    lo, hi = verifiers.IBP(pm, x, pm.posterior_mean, eps)
+    np.testing.assert_allclose(lo, ref["ibp_mean_l"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(hi, ref["ibp_mean_u"], rtol=1e-5, atol=2e-5)
+    # chernoff_bound_verification: the reference's noise (global NumPy RNG, seed 424242) injected
+    n, cls = int(ref["chernoff_n"][0]), int(ref["chernoff_cls"][0])
+    mean = formats.load_tensor_list(os.path.join(pm.path_to_model, "mean.npy"))
+    np.random.seed(424242)
+    noise = np.stack([np.concatenate([np.random.standard_normal(t.shape).ravel() for t in mean]) for _ in range(n)]).astype(np.float32)
+    out = verifiers._engine_of(pm).ibp_predict(x[:1], eps, [cls], n, noise=noise, mode="fp32", want=("worst",))
+    np.testing.assert_allclose(out["worst"].cpu().numpy(), ref["chernoff_sum"], rtol=1e-4, atol=1e-5)
+    # API shape and sample count of the drop-in function (device Philox noise: same distribution, other draws)
+    got = verifiers.chernoff_bound_verification(pm, x[:1], eps, cls, confidence=0.75, delta=0.3)
+    assert got.shape == (1, 10) and abs(got.sum() - n) < 1e-3
+    with pytest.raises(NotImplementedError):
+        verifiers.IBP(pm, x, pm.posterior_mean, eps, predict=True)
+
+
+def test_ibp_properties_and_bf16(oracle, monkeypatch):
+    """eps = 0 collapses the interval onto the plain forward; the bf16 tensor-core back end agrees with the
+    bf16 CUDA-core back end and stays within the bf16 tolerance of fp32; stored-sample source; Massart loop."""
+    dims, B, n = [784, 256, 256, 10], 200, 12
+    L, eng, mean, std = _mlp_engine(dims, oracle, sigma_scale=0.3)
+    x = oracle.synthetic_x((B, dims[0]), seed=6)
+    labels = np.random.Generator(np.random.Philox(8)).integers(0, 10, size=B).astype(np.int32)
+    z = eng.ibp_predict(x, 0.0, labels, n, seed=5, mode="fp32", want=("lower", "upper"))
+    np.testing.assert_allclose(z["lower"].cpu().numpy(), z["upper"].cpu().numpy(), rtol=0, atol=1e-4)
+    lg, _ = eng.predict_sums(x, n, seed=5, mode="fp32", out_kind="logits")
+    np.testing.assert_allclose(z["lower"].cpu().numpy(), lg.cpu().numpy(), rtol=1e-4, atol=1e-3)
+    eps = 0.004
+    f = eng.ibp_predict(x, eps, labels, n, seed=5, mode="fp32", want=("worst", "lower", "upper", "counts"))
+    monkeypatch.setenv("DBX_NO_TC", "1")
+    c = eng.ibp_predict(x, eps, labels, n, seed=5, mode="bf16", want=("worst", "lower", "upper", "counts"))
+    assert eng.last_path() == "generic"
+    monkeypatch.setenv("DBX_NO_TC", "0")
+    t = eng.ibp_predict(x, eps, labels, n, seed=5, mode="bf16", want=("worst", "lower", "upper", "counts"))
+    assert eng.last_path() == "generic_tc"
+    for k in ("lower", "upper"):
+        np.testing.assert_allclose(t[k].cpu().numpy() / n, c[k].cpu().numpy() / n, rtol=0, atol=3e-3)
+        np.testing.assert_allclose(t[k].cpu().numpy() / n, f[k].cpu().numpy() / n, rtol=0, atol=8e-2)
+    np.testing.assert_allclose(t["worst"].cpu().numpy() / n, f["worst"].cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
+    assert (t["lower"] <= t["upper"]).all()
+    assert np.abs(t["counts"].cpu().numpy() - f["counts"].cpu().numpy()).max() <= 2
+    # wider ball -> wider interval
+    f2 = eng.ibp_predict(x, 2 * eps, labels, n, seed=5, mode="fp32", want=("lower", "upper"))
+    assert (f2["lower"] <= f["lower"] + 1e-4).all() and (f["upper"] <= f2["upper"] + 1e-4).all()
+    # stored-sample source: rows of a slab drawn with the same ids give the same bounds
+    slab = eng.sample(n, seed=5, s0=0)
+    eng.set_samples(slab)
+    s = eng.ibp_predict(x, eps, labels, n, mode="fp32", stored=True, want=("lower", "upper"))
+    np.testing.assert_allclose(s["lower"].cpu().numpy(), f["lower"].cpu().numpy(), rtol=1e-6, atol=1e-5)
+
+
+def test_massart_with_ibp(tmp_path, oracle):
+    import deepbayes_b200 as db
+    from deepbayes_b200.analyzers import verifiers
+    L = oracle.mlp([784, 128, 10])
+    m = db.Sequential([db.Dense(128, activation="relu", input_shape=(784,)), db.Dense(10, activation="softmax")])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=16, inflate_prior=1.0)
+    x = oracle.synthetic_x((1, 784), seed=9)
+    cls = int(np.argmax(opt.predict(x)))
+    p, it, _ = verifiers.massart_bound_check(opt, x, 1e-4, None, cls=cls, verify=True, classification=True, confidence=0.8, delta=0.3)
+    assert 0.0 <= p <= 1.0 and 1 <= it <= verifiers.chernoff_sample_bound(0.8, 0.3) + 1
+    with pytest.raises(NotImplementedError):
+        verifiers.massart_bound_check(opt, x, 1e-4, None, cls=cls, verify=True, classification=False)
