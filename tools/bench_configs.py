@@ -106,6 +106,14 @@ def cfg5():
         ms = timeit(lambda: eng.count_predicate(x[:K1], lab[:K1], n, seed=5, mode="bf16"), warm=1, reps=2)
         emit(config="5b: massart-style loop, 100k posterior samples x 1 input", B=K1, ms=ms, samples_per_s=n / (ms * 1e-3),
              path=eng.last_path(), note="weights formed in registers from Philox, never materialised")
+    # 5c: the same loop with verify=True -- IBP over the eps-ball for every posterior sample
+    n2 = 10000
+    for mode in ("bf16", "fp32"):
+        ms = timeit(lambda: eng.ibp_predict(x, 0.01, lab, n2, seed=5, mode=mode, want=("worst", "counts")), warm=1, reps=2)
+        fl = 2 * 1337344 * K * n2 / (ms * 1e-3) / 1e12          # centre and radius products
+        emit(config="5c: Chernoff-bound MC with IBP (verify=True), 10k posterior samples x 128 eps-balls, MLP 784-512-512-10",
+             B=K, mode=mode, ms=ms, value=K * n2 / (ms * 1e-3), unit="interval forwards/s", samples_per_s=n2 / (ms * 1e-3),
+             path=eng.last_path(), tflops=fl)
 
 
 if __name__ == "__main__":
