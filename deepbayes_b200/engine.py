@@ -105,7 +105,7 @@ class Engine:
     def _dev_f32(self, a):
         torch = self.torch
         if isinstance(a, torch.Tensor):
-            return a.to(device=self.device, dtype=torch.float32).contiguous()
+            return a.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()   # async when the source is pinned
         a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
         if a.nbytes < (1 << 16):
             return torch.from_numpy(a).to(self.device)
