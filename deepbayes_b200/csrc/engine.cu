@@ -444,7 +444,7 @@ static inline int grid_for(int64_t total, int block = 256) {
 // ---------------------------------------------------------------------------------------
 
 int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
-                       float* B32, cudaStream_t st, int64_t pb_stride) {
+                       float* B32, cudaStream_t st, int64_t pb_stride, const bool* skip) {
   if (pb_stride <= 0) pb_stride = m->PB;
   const int nblk = (int)((m->P + 3) / 4);
   BlockRanges rg; rg.n = 0;
@@ -461,6 +461,17 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
       dim3 grid((unsigned)std::min<int64_t>(cdiv((hi - lo + 1) / 2, 256), 148 * 4), (unsigned)cdiv(nc, kSamplesPerThread));
       DBX_LAUNCH(sample_bf16_fast_kernel, grid, 256, 0, st, m->mu, m->sigma, src.inflate, src.seed, src.s0 + c0, nc, lo, hi,
                  tab.dst_off[i] - tab.src_off[i], W16, m->P16);
+      cursor = hi;
+    }
+  }
+  if (skip) {
+    // tensors somebody else consumes in their original form (stored fp32 kernels read by dense_tc_f32w_kernel): leave
+    // their interior Philox blocks out
+    for (int i = 0; i < tab.n; ++i) {
+      if (!skip[i]) continue;
+      const int lo = (tab.src_off[i] + 3) >> 2, hi = tab.src_end[i] >> 2;
+      if (hi <= lo || lo < cursor || rg.n + 2 > DBX_MAX_RANGES) continue;
+      if (lo > cursor) { rg.lo[rg.n] = cursor; rg.hi[rg.n] = lo; ++rg.n; }
       cursor = hi;
     }
   }
@@ -521,13 +532,29 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   if (sink.kind == 1 && !sink.accumulate)
     DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, sink.counts, B);
 
+  // Stored posteriors in bf16 mode: large Dense kernels are NOT copied to bf16 first -- dense_tc_f32w_kernel reads them
+  // from the fp32 slab by TMA and rounds them inside the SM (gemm_tc.cu).  DBX_NO_F32W=1 restores the two-pass path.
+  bool skip_tensor[DBX_MAX_TENSORS] = {};
+  bool layer_f32w[64] = {};
+  bool any_f32w = false;
+  if (kBf16 && use_tc && src.stored && m->layers.size() <= 64 && !(getenv("DBX_NO_F32W") && getenv("DBX_NO_F32W")[0] == '1')) {
+    for (int li = 0; li < (int)m->layers.size(); ++li) {
+      const Layer& L = m->layers[li];
+      if (L.kind != DBX_DENSE || !L.has_w) continue;
+      if ((L.in_feat & 7) || (L.w_cols & 3) || (L.w_off & 3) || (m->slab_stride & 3) || ((uintptr_t)m->slab & 15)) continue;
+      if ((int64_t)L.w_rows * L.w_cols < 65536 || !(li == m->last_weighted || L.units % 8 == 0)) continue;
+      for (int ti = 0; ti < m->table.n; ++ti)
+        if (!m->table.is_bias[ti] && m->table.src_off[ti] == (int32_t)L.w_off) { skip_tensor[ti] = true; layer_f32w[li] = true; any_f32w = true; }
+    }
+  }
+
   for (int64_t c0 = 0; c0 < n; c0 += ns) {
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     // ---- weights of this chunk
     const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
     const float* Bbase; int64_t b_sstride;
     if (kBf16) {
-      if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
+      if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st, 0, any_f32w ? skip_tensor : nullptr)) return 1;
       Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
     } else if (src.stored) {
       Wbase = (const T*)m->slab; w_sstride = m->slab_stride; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
@@ -556,7 +583,15 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
         // tensor-core path: per-sample GEMM on tcgen05 (Dense directly, Conv2D through im2col)
         const __nv_bfloat16* A16 = (const __nv_bfloat16*)cur;
         const int shared = (cur_ss == 0) ? 1 : 0;
-        if (L.kind == DBX_DENSE && L.in_feat % 8 == 0) {
+        if (L.kind == DBX_DENSE && layer_f32w[li]) {
+          if (dense_tc_f32w_launch(A16, cur_ss, (int)L.in_feat, shared, m->slab, m->slab_stride, m->S, L.w_off,
+                                   src.idx ? src.idx + c0 : nullptr, src.j0 + c0, nc, (int)B, L.units, (int)L.in_feat, Bbase, b_sstride,
+                                   boff, act, last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units,
+                                   last ? logits : nullptr, B * C, st)) {
+            set_err("dense_tc_f32w launch failed"); return 1;
+          }
+          done_tc = true;
+        } else if (L.kind == DBX_DENSE && L.in_feat % 8 == 0) {
           done_tc = dense_tc_launch(A16, cur_ss, (int)L.in_feat, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc,
                                     (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff, act,
                                     last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units, last ? logits : nullptr,

@@ -108,7 +108,7 @@ void prof_end(cudaStream_t st, double flops);
 // padded bf16, biases -> B32 [nc,PB] fp32): Gaussian draw (injected eps or Philox) or conversion
 // of stored samples.  Defined in engine.cu.
 int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
-                       float* B32, cudaStream_t st, int64_t pb_stride = 0);
+                       float* B32, cudaStream_t st, int64_t pb_stride = 0, const bool* skip = nullptr);
 
 // fused_mlp.cu: returns 1 if the tcgen05 fused path handled the request, 0 if the shape is
 // not supported by it (caller uses the generic kernels), <0 on error.
@@ -121,6 +121,10 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
                     long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride,
                     long long b_off, int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32,
                     long long o32_sstride, cudaStream_t st);
+int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const float* slab, long long slab_stride,
+                         long long slab_rows, long long w_off, const int32_t* w_rows, long long w_row0, int ns, int M, int N, int K,
+                         const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
+                         long long o16_sstride, int ld16, float* out32, long long o32_sstride, cudaStream_t st);
 int im2col_launch(const __nv_bfloat16* in, long long in_sstride, __nv_bfloat16* out, long long out_sstride, int ns, int NB,
                   const Layer& L, int Kp, cudaStream_t st);
 

@@ -624,3 +624,33 @@ def test_massart_with_ibp(tmp_path, oracle):
     assert 0.0 <= p <= 1.0 and 1 <= it <= verifiers.chernoff_sample_bound(0.8, 0.3) + 1
     with pytest.raises(NotImplementedError):
         verifiers.massart_bound_check(opt, x, 1e-4, None, cls=cls, verify=True, classification=False)
+
+
+@pytest.mark.parametrize("dims,B,S", [([784, 1024, 1024, 10], 64, 20), ([200, 512, 384, 12], 150, 9), ([784, 640, 10], 40, 7)])
+def test_stored_posterior_f32_slab_on_tensor_cores(oracle, monkeypatch, dims, B, S):
+    """Stored posteriors at B > 16 in bf16 mode: dense_tc_f32w_kernel reads the Dense kernels from the fp32 slab by TMA and
+    rounds them to bf16 inside the SM.  Same arithmetic as the two-pass path (bf16 copy of the slab chunk, then
+    dense_tc_kernel), so the two agree to accumulation order; both stay within the bf16 tolerance of the fp32 mode."""
+    L, eng, mean, std = _mlp_engine(dims, oracle, sigma_scale=0.5)
+    slab = eng.sample(S, seed=3, s0=0)
+    eng.set_samples(slab)
+    x = oracle.synthetic_x((B, dims[0]), seed=2)
+    g = np.random.Generator(np.random.Philox(5))
+    idx = g.integers(0, S, size=2 * S).astype(np.int32)
+    wts = g.uniform(0.5, 1.5, size=2 * S).astype(np.float32)
+    f1, f2 = eng.predict_stored_sums(x, 2 * S, idx=idx, wts=wts, mode="fp32", second_moment=True)
+    t1, t2 = eng.predict_stored_sums(x, 2 * S, idx=idx, wts=wts, mode="bf16", second_moment=True)
+    assert eng.last_path() == "generic_tc"
+    monkeypatch.setenv("DBX_NO_F32W", "1")
+    c1, c2 = eng.predict_stored_sums(x, 2 * S, idx=idx, wts=wts, mode="bf16", second_moment=True)
+    monkeypatch.setenv("DBX_NO_F32W", "0")
+    tot = float(wts.sum())
+    np.testing.assert_allclose(t1.cpu().numpy() / tot, c1.cpu().numpy() / tot, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(t2.cpu().numpy() / tot, c2.cpu().numpy() / tot, rtol=0, atol=2e-4)
+    np.testing.assert_allclose(t1.cpu().numpy() / tot, f1.cpu().numpy() / tot, rtol=0, atol=BF16_ATOL)
+    assert (t1.argmax(1) == f1.argmax(1)).float().mean().item() > 0.97
+    # contiguous rows j0.. (no index list)
+    a1, _ = eng.predict_stored_sums(x, S - 2, j0=2, mode="bf16")
+    monkeypatch.setenv("DBX_NO_F32W", "1")
+    b1, _ = eng.predict_stored_sums(x, S - 2, j0=2, mode="bf16")
+    np.testing.assert_allclose(a1.cpu().numpy() / (S - 2), b1.cpu().numpy() / (S - 2), rtol=0, atol=2e-4)
