@@ -359,6 +359,18 @@ __global__ void maxpool_kernel(const T* __restrict__ A, int64_t a_sstride, T* __
 // Sample-ordered accumulation of the model output over the chunk's samples:
 //   sum1[b,c] (+)= sum_s w_s * f_s[b,c],  sum2 likewise with f^2  (posteriormodel.py:95-100).
 // logits [ns,B,C] fp32 are the last layer's pre-activation values.
+__device__ __forceinline__ float accum_value(const float* __restrict__ z, int c, int C, int act, int out_kind) {
+  if (out_kind == DBX_OUT_LOGITS) return z[c];
+  if (act == DBX_ACT_SOFTMAX) {
+    float m = z[0];
+    for (int j = 1; j < C; ++j) m = fmaxf(m, z[j]);
+    float den = 0.f;
+    for (int j = 0; j < C; ++j) den += expf(z[j] - m);
+    return expf(z[c] - m) / den;
+  }
+  return apply_act(act, z[c]);
+}
+
 __global__ void accum_kernel(const float* __restrict__ logits, int ns, int64_t B, int C, int act, int out_kind,
                              const float* __restrict__ wts, int overwrite, float* __restrict__ sum1,
                              float* __restrict__ sum2) {
@@ -369,16 +381,7 @@ __global__ void accum_kernel(const float* __restrict__ logits, int ns, int64_t B
     float a1 = overwrite ? 0.f : sum1[o];
     float a2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
     for (int s = 0; s < ns; ++s) {
-      const float* z = logits + ((int64_t)s * B + b) * C;
-      float p;
-      if (out_kind == DBX_OUT_LOGITS) p = z[c];
-      else if (act == DBX_ACT_SOFTMAX) {
-        float m = z[0];
-        for (int j = 1; j < C; ++j) m = fmaxf(m, z[j]);
-        float den = 0.f;
-        for (int j = 0; j < C; ++j) den += expf(z[j] - m);
-        p = expf(z[c] - m) / den;
-      } else p = apply_act(act, z[c]);
+      const float p = accum_value(logits + ((int64_t)s * B + b) * C, c, C, act, out_kind);
       const float w = wts ? wts[s] : 1.f;
       if (wts) { a1 = fmaf(w, p, a1); a2 = fmaf(w, p * p, a2); }
       else { a1 += p; a2 = fmaf(p, p, a2); }
@@ -386,6 +389,49 @@ __global__ void accum_kernel(const float* __restrict__ logits, int ns, int64_t B
     sum1[o] = a1;
     if (sum2) sum2[o] = a2;
   }
+}
+
+// Few outputs, many samples (small batches): one WARP per output element; lane l sums the contiguous sample range
+// [l*ns/32, (l+1)*ns/32) in order and lane 0 adds the 32 partial sums in lane order -- deterministic, and 32x the
+// parallelism of the kernel above (which left a B=64, C=10 call with 640 busy threads for 256 samples).
+__global__ void __launch_bounds__(256)
+accum_warp_kernel(const float* __restrict__ logits, int ns, int64_t B, int C, int act, int out_kind,
+                  const float* __restrict__ wts, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
+  const int64_t total = B * C;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t o = warp0; o < total; o += nwarps) {
+    const int64_t b = o / C;
+    const int c = (int)(o - b * C);
+    const int s_lo = (int)(((int64_t)lane * ns) / 32), s_hi = (int)(((int64_t)(lane + 1) * ns) / 32);
+    float a1 = 0.f, a2 = 0.f;
+    for (int s = s_lo; s < s_hi; ++s) {
+      const float p = accum_value(logits + ((int64_t)s * B + b) * C, c, C, act, out_kind);
+      const float w = wts ? wts[s] : 1.f;
+      if (wts) { a1 = fmaf(w, p, a1); a2 = fmaf(w, p * p, a2); }
+      else { a1 += p; a2 = fmaf(p, p, a2); }
+    }
+    float t1 = overwrite ? 0.f : sum1[o];
+    float t2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
+    for (int l = 0; l < 32; ++l) {
+      t1 += __shfl_sync(0xffffffffu, a1, l);
+      t2 += __shfl_sync(0xffffffffu, a2, l);
+    }
+    if (lane == 0) { sum1[o] = t1; if (sum2) sum2[o] = t2; }
+  }
+}
+
+static inline void launch_accum(const float* logits, int ns, int64_t B, int C, int act, int out_kind, const float* wts, int overwrite,
+                                float* sum1, float* sum2, cudaStream_t st) {
+  if (B * C <= 8192 && ns >= 64) {
+    const int64_t threads = B * C * 32;
+    accum_warp_kernel<<<(unsigned)std::min<int64_t>(cdiv(threads, 256), 148 * 8), 256, 0, st>>>(logits, ns, B, C, act, out_kind, wts,
+                                                                                               overwrite, sum1, sum2);
+  } else {
+    accum_kernel<<<(unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(B * C, 256), 1), 148 * 16), 256, 0, st>>>(
+        logits, ns, B, C, act, out_kind, wts, overwrite, sum1, sum2);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 // flags[s,k] = (argmax_c logits[s,k,:] == labels[k]) (first maximum, like np.argmax).
@@ -643,8 +689,8 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
     const int act_last = m->layers[m->last_weighted].act;
     if (sink.kind == 0) {
       const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
-      DBX_LAUNCH(accum_kernel, grid_for(B * C), 256, 0, st, logits, nc, B, (int)C, act_last, sink.out_kind,
-                 sink.wts ? sink.wts + c0 : nullptr, overwrite, sink.sum1, sink.sum2);
+      launch_accum(logits, nc, B, (int)C, act_last, sink.out_kind, sink.wts ? sink.wts + c0 : nullptr, overwrite, sink.sum1, sink.sum2, st);
+      DBX_CUDA(cudaGetLastError());
     } else {
       DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, logits, nc, B, (int)C, sink.labels,
                  sink.flags ? sink.flags + c0 * B : nullptr, sink.counts);

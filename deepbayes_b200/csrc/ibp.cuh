@@ -249,14 +249,11 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     const int act_last = m->layers[m->last_weighted].act;
     const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
     if (sink.sum_worst)
-      DBX_LAUNCH(accum_kernel, grid_for(B * C), 256, 0, st, worst, nc, B, (int)C, act_last, DBX_OUT_PROBS, (const float*)nullptr,
-                 overwrite, sink.sum_worst, (float*)nullptr);
+      launch_accum(worst, nc, B, (int)C, act_last, DBX_OUT_PROBS, nullptr, overwrite, sink.sum_worst, nullptr, st);
     if (sink.sum_lower)
-      DBX_LAUNCH(accum_kernel, grid_for(B * C), 256, 0, st, lower, nc, B, (int)C, act_last, DBX_OUT_LOGITS, (const float*)nullptr,
-                 overwrite, sink.sum_lower, (float*)nullptr);
+      launch_accum(lower, nc, B, (int)C, act_last, DBX_OUT_LOGITS, nullptr, overwrite, sink.sum_lower, nullptr, st);
     if (sink.sum_upper)
-      DBX_LAUNCH(accum_kernel, grid_for(B * C), 256, 0, st, upper, nc, B, (int)C, act_last, DBX_OUT_LOGITS, (const float*)nullptr,
-                 overwrite, sink.sum_upper, (float*)nullptr);
+      launch_accum(upper, nc, B, (int)C, act_last, DBX_OUT_LOGITS, nullptr, overwrite, sink.sum_upper, nullptr, st);
     if (sink.counts)
       DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, worst, nc, B, (int)C, sink.labels,
                  sink.flags ? sink.flags + c0 * B : nullptr, sink.counts);
