@@ -148,28 +148,34 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // pass wrote a bf16 copy of the slab chunk to HBM and the GEMM read it back, 2x the algorithmic bytes.)
 //   warp 0     TMA producer: W block [64 k x 64 n] fp32 -> landing ring (3 x 16 KB); A block [128 x 64] bf16 -> operand ring
 //   warps 2-5  converter: landing block -> bf16, MN-major SWIZZLE_128B layout (row k: 128 B, 16-byte chunk c at c ^ (k & 7))
-//              -> operand ring (2 x 24 KB); afterwards the epilogue (bias, activation, stores)
-//   warp 1     MMA issuer (M = 128, N = 64, four K = 16 steps per block), accumulator in 64 TMEM columns
-// 97 KB of shared memory per CTA -> two CTAs per SM, so one CTA's prologue / epilogue overlaps the other's stream.
+//              -> operand ring (2 x 24 KB)
+//   warp 1     MMA issuer (M = 128, N = 64, four K = 16 steps per block), two 64-column accumulators in TMEM
+//   warps 6-9  epilogue of tile i (bias, activation, stores) while the main loop of tile i+1 runs
+// 97 KB of shared memory per CTA -> two persistent CTAs per SM.
 // =======================================================================================
 constexpr int kFLand = 3, kFOp = 2;
 constexpr int kFLandBytes = 16384;   // [64 k][64 n] fp32, as TMA delivers it (no swizzle, 256 B rows)
 constexpr int kFOpBytes = 24576;     // A block 16 KB + converted W block 8 KB
 constexpr int kFNT = 64;
+constexpr int kFThreads = 320;       // producer, issuer, 4 converter warps, 4 epilogue warps
 
 struct __align__(8) FBarriers {
   uint64_t land_full[kFLand], land_empty[kFLand];
   uint64_t op_full[kFOp], op_empty[kFOp];
-  uint64_t acc_full;
+  uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
 
 struct FGemmParams {
   GemmParams g;
   const int32_t* w_rows; long long w_row0;   // sample -> slab row (third TMA coordinate)
+  int ns, tiles_n, tiles_m;
 };
 
-__global__ void __launch_bounds__(kGThreads, 2)
+// PERSISTENT: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened (sample, m tile, n tile)
+// list (n fastest: CTAs running side by side read neighbouring 256-byte segments of the same slab rows), and all three
+// rings run across tile boundaries, so the HBM stream never drains between tiles.
+__global__ void __launch_bounds__(kFThreads, 2)
 dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const FGemmParams fp) {
   const GemmParams& p = fp.g;
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -178,16 +184,21 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t s_op = s_land + kFLand * kFLandBytes;
   FBarriers* bars = (FBarriers*)(op_smem + kFOp * kFOpBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * kFNT, m0 = blockIdx.y * 128, s = blockIdx.z;
   const int kb_n = (p.K + 63) / 64;
+  const long long total = (long long)fp.ns * fp.tiles_m * fp.tiles_n;
+  auto decode = [&](long long t, int& n0, int& m0, int& s) {
+    const int nt = (int)(t % fp.tiles_n);
+    const long long r = t / fp.tiles_n;
+    n0 = nt * kFNT; m0 = (int)(r % fp.tiles_m) * 128; s = (int)(r / fp.tiles_m);
+  };
 
   if (tid == 0) {
     for (int i = 0; i < kFLand; ++i) { mbar_init(smem_u32(&bars->land_full[i]), 1); mbar_init(smem_u32(&bars->land_empty[i]), 4); }
     for (int i = 0; i < kFOp; ++i) { mbar_init(smem_u32(&bars->op_full[i]), 1 + 4); mbar_init(smem_u32(&bars->op_empty[i]), 1); }
-    mbar_init(smem_u32(&bars->acc_full), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<64>(smem_u32(&bars->tmem_slot));
+  if (warp == 1) tmem_alloc<128>(smem_u32(&bars->tmem_slot));
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
   fence_before_sync();
   __syncthreads();
@@ -195,110 +206,140 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem = bars->tmem_slot;
 
   if (warp == 0) {
-    // the fp32 weight blocks (the bulk of the bytes) are requested kFLand blocks ahead of their conversion; the small A
-    // blocks follow the operand ring
-    const int wrow = (int)(fp.w_rows ? (long long)fp.w_rows[s] : (fp.w_row0 + s));
-    auto issue_w = [&](int k2) {
-      const uint32_t l = k2 % kFLand, lph = (k2 / kFLand) & 1;
+    // ---- TMA producer.  The fp32 weight blocks (the bulk of the bytes) are requested kFLand blocks ahead of their
+    // conversion, across tile boundaries; the small A blocks follow the operand ring.
+    long long wt = blockIdx.x; int wkb = 0; uint32_t wg = 0;       // cursor of the next weight block to request
+    int wn0 = 0, wm0 = 0, ws = 0, wrow = 0;
+    auto w_setup = [&]() {
+      if (wt < total) { decode(wt, wn0, wm0, ws); wrow = (int)(fp.w_rows ? (long long)fp.w_rows[ws] : (fp.w_row0 + ws)); }
+    };
+    auto issue_w = [&]() {
+      const uint32_t l = wg % kFLand, lph = (wg / kFLand) & 1;
       mbar_wait(smem_u32(&bars->land_empty[l]), lph ^ 1);
       if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->land_full[l]);
         mbar_expect_tx(fb, kFLandBytes);
-        tma_load_3d(s_land + l * kFLandBytes, &tmW, fb, n0, k2 * 64, wrow);
+        tma_load_3d(s_land + l * kFLandBytes, &tmW, fb, wn0, wkb * 64, wrow);
       }
       __syncwarp();
+      ++wg;
+      if (++wkb == kb_n) { wkb = 0; wt += gridDim.x; w_setup(); }
     };
-    int wk = 0;
-    for (; wk < kFLand && wk < kb_n; ++wk) issue_w(wk);
-    for (int kb = 0; kb < kb_n; ++kb) {
-      const uint32_t o = kb % kFOp, oph = (kb / kFOp) & 1;
-      mbar_wait(smem_u32(&bars->op_empty[o]), oph ^ 1);
-      if (elect_one()) {
-        const uint32_t fb = smem_u32(&bars->op_full[o]);
-        mbar_expect_tx(fb, 16384);
-        if (p.a_shared) tma_load_2d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0);
-        else tma_load_3d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0, s);
+    w_setup();
+    for (int i = 0; i < kFLand && wt < total; ++i) issue_w();
+    uint32_t g = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t o = g % kFOp, oph = (g / kFOp) & 1;
+        mbar_wait(smem_u32(&bars->op_empty[o]), oph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->op_full[o]);
+          mbar_expect_tx(fb, 16384);
+          if (p.a_shared) tma_load_2d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0);
+          else tma_load_3d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0, s);
+        }
+        __syncwarp();
+        if (wt < total) issue_w();
       }
-      __syncwarp();
-      if (wk < kb_n) { issue_w(wk); ++wk; }
     }
   } else if (warp == 1) {
+    // ---- MMA issuer
     constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t idesc = make_idesc_bf16(128, kFNT, 0, 1);
-    for (int kb = 0; kb < kb_n; ++kb) {
-      const uint32_t o = kb % kFOp, oph = (kb / kFOp) & 1;
-      mbar_wait(smem_u32(&bars->op_full[o]), oph);
+    uint32_t g = 0, it = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
       fence_after_sync();
-      if (elect_one()) {
-        const uint32_t a16 = ((s_op + o * kFOpBytes) & 0x3FFFF) >> 4;
-        const uint32_t a_lo = a16 | (1u << 16);
-        const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
-        const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
-        for (int kk = 0; kk < ksteps; ++kk)
-          mma_ss_lh(tmem, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
-        mma_commit(smem_u32(&bars->op_empty[o]));
-        if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full));
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t o = g % kFOp, oph = (g / kFOp) & 1;
+        mbar_wait(smem_u32(&bars->op_full[o]), oph);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a16 = ((s_op + o * kFOpBytes) & 0x3FFFF) >> 4;
+          const uint32_t a_lo = a16 | (1u << 16);
+          const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
+          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+          for (int kk = 0; kk < ksteps; ++kk)
+            mma_ss_lh(tmem + ab * kFNT, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+          mma_commit(smem_u32(&bars->op_empty[o]));
+          if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
+        }
+        __syncwarp();
       }
-      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ---- converter: landed fp32 block -> bf16 B operand (row k = 128 B, 16-byte chunk c stored at c ^ (k & 7))
+    const int tc = tid - 64;                      // 0..127
+    uint32_t g = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t l = g % kFLand, lph = (g / kFLand) & 1, o = g % kFOp, oph = (g / kFOp) & 1;
+        mbar_wait(smem_u32(&bars->land_full[l]), lph);
+        mbar_wait(smem_u32(&bars->op_empty[o]), oph ^ 1);
+        const uint8_t* src = smem + l * kFLandBytes;
+        uint8_t* dst = op_smem + o * kFOpBytes + 16384;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = i * 128 + tc;
+          const int k = u >> 3, c = u & 7;        // row k, 16-byte bf16 chunk c = columns 8c..8c+7
+          const float4 a = *reinterpret_cast<const float4*>(src + k * 256 + c * 32);
+          const float4 b = *reinterpret_cast<const float4*>(src + k * 256 + c * 32 + 16);
+          const uint4 v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+          *reinterpret_cast<uint4*>(dst + (k >> 3) * 1024 + (k & 7) * 128 + ((c ^ (k & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(smem_u32(&bars->op_full[o])); mbar_arrive(smem_u32(&bars->land_empty[l])); }
+      }
     }
   } else {
-    // ---- converter
-    const int tc = tid - 64;                      // 0..127
-    for (int kb = 0; kb < kb_n; ++kb) {
-      const uint32_t l = kb % kFLand, lph = (kb / kFLand) & 1, o = kb % kFOp, oph = (kb / kFOp) & 1;
-      mbar_wait(smem_u32(&bars->land_full[l]), lph);
-      mbar_wait(smem_u32(&bars->op_empty[o]), oph ^ 1);
-      const uint8_t* src = smem + l * kFLandBytes;
-      uint8_t* dst = op_smem + o * kFOpBytes + 16384;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int u = it * 128 + tc;
-        const int k = u >> 3, c = u & 7;          // row k, 16-byte bf16 chunk c = columns 8c..8c+7
-        const float4 a = *reinterpret_cast<const float4*>(src + k * 256 + c * 32);
-        const float4 b = *reinterpret_cast<const float4*>(src + k * 256 + c * 32 + 16);
-        const uint4 v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-        *reinterpret_cast<uint4*>(dst + (k >> 3) * 1024 + (k & 7) * 128 + ((c ^ (k & 7)) << 4)) = v;
-      }
-      fence_proxy_async_smem();                   // generic-proxy stores -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(smem_u32(&bars->op_full[o])); mbar_arrive(smem_u32(&bars->land_empty[l])); }
-    }
-    // ---- epilogue
-    const int g = warp & 3;
-    const int row = g * 32 + lane;
-    const int gm = m0 + row;
-    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
-    const long long brow = p.rows ? (long long)p.rows[s] : (p.row0 + s);
-    const float* bias = p.bias + brow * p.b_sstride + p.b_off;
-    mbar_wait(smem_u32(&bars->acc_full), 0);
-    fence_after_sync();
-    for (int c0 = 0; c0 < kFNT; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem + lane_base + c0, v);
+    // ---- epilogue (warps 6..9 own TMEM lane quadrants 2, 3, 0, 1)
+    const int gq = warp & 3;
+    const int row = gq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int gm = m0 + row;
+      const uint32_t ab = it & 1;
+      const long long brow = p.rows ? (long long)p.rows[s] : (p.row0 + s);
+      const float* bias = p.bias + brow * p.b_sstride + p.b_off;
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+      uint32_t v[kFNT];
+      tmem_ld32(tmem + lane_base + ab * kFNT, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem + lane_base + ab * kFNT + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       wait_ld();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));   // the accumulator is in registers: the next tile may start
       if (gm < p.M) {
         if (p.out16) {
-          __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0 + c0;
+          __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int c = n0 + c0 + q4 * 8;
+          for (int q8 = 0; q8 < kFNT / 8; ++q8) {
+            const int c = n0 + q8 * 8;
             if (c + 8 <= p.N) {
               uint32_t w[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + bias[c + 2 * i]),
-                                   apply_act(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
-              *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                   apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+              *reinterpret_cast<uint4*>(dst + q8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
               for (int i = 0; i < 8; ++i)
-                if (c + i < p.N) dst[q4 * 8 + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q4 * 8 + i]) + bias[c + i]));
+                if (c + i < p.N) dst[q8 * 8 + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
             }
           }
         } else {
           float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = n0 + c0 + i;
+          for (int i = 0; i < kFNT; ++i) {
+            const int c = n0 + i;
             if (c < p.N) dst[c] = apply_act(p.act, __uint_as_float(v[i]) + bias[c]);
           }
         }
@@ -307,7 +348,7 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<64>(tmem);
+  if (warp == 1) tmem_dealloc<128>(tmem);
 }
 
 // NHWC bf16 activations -> im2col rows [n*Ho*Wo][kh*kw*C (padded to Kp)] so that Conv2D becomes the GEMM above
@@ -428,14 +469,19 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
   p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
   fp.w_rows = w_rows; fp.w_row0 = w_row0;
+  fp.ns = ns; fp.tiles_n = (int)cdiv(N, kFNT); fp.tiles_m = (int)cdiv(M, 128);
   const int smem = kFLand * kFLandBytes + kFOp * kFOpBytes + (int)sizeof(FBarriers) + 1024;
   static bool attr_done = false;
+  static int num_sms = 0;
   if (!attr_done) {
     if (cudaFuncSetAttribute(dense_tc_f32w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
     attr_done = true;
   }
-  dim3 grid((unsigned)cdiv(N, kFNT), (unsigned)cdiv(M, 128), (unsigned)ns);
-  dense_tc_f32w_kernel<<<grid, kGThreads, smem, st>>>(tmA, tmW, fp);
+  const long long total = (long long)ns * fp.tiles_m * fp.tiles_n;
+  dim3 grid((unsigned)std::min<long long>(total, 2LL * num_sms));   // two resident CTAs per SM
+  dense_tc_f32w_kernel<<<grid, kFThreads, smem, st>>>(tmA, tmW, fp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
