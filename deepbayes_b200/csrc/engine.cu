@@ -540,6 +540,25 @@ static size_t ws_budget_bytes() {
   return mb << 20;
 }
 
+// Can dense_tc_f32w_kernel take this layer's kernel straight from the fp32 slab?  (16-byte TMA strides and offsets; small
+// kernels are not worth a launch of their own.)  DBX_NO_F32W=1 restores the two-pass path.
+static bool f32w_layer_ok(const dbx_model* m, int li) {
+  if (const char* e = getenv("DBX_NO_F32W")) if (e[0] == '1') return false;
+  if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') return false;
+  const Layer& L = m->layers[li];
+  if (L.kind != DBX_DENSE || !L.has_w || !m->slab) return false;
+  if ((L.in_feat & 7) || (L.w_cols & 3) || (L.w_off & 3) || (m->slab_stride & 3) || ((uintptr_t)m->slab & 15)) return false;
+  return (int64_t)L.w_rows * L.w_cols >= 65536 && (li == m->last_weighted || L.units % 8 == 0);
+}
+// ... and do those layers hold most of the model (then the tensor-core path streams the slab at B > 8 faster than the
+// FFMA streaming kernel, which is compute-bound beyond 8 rows)
+static bool f32w_model_ok(const dbx_model* m) {
+  int64_t covered = 0;
+  for (int li = 0; li < (int)m->layers.size() && li < 64; ++li)
+    if (f32w_layer_ok(m, li)) covered += (int64_t)m->layers[li].w_rows * m->layers[li].w_cols;
+  return covered * 10 >= m->P * 9;
+}
+
 template <typename T>
 static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
                        cudaStream_t st) {
@@ -556,7 +575,10 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
     for (auto& L : m->layers)
       if (L.kind == DBX_CONV2D) col_b = std::max(col_b, (size_t)B * L.out_h * L.out_w * round_up(L.w_rows, 8) * 2);
   const size_t per = 2 * act_b + w_b + (size_t)B * C * 4 + col_b + 256;
-  const size_t xin_b = kBf16 ? round_up((size_t)B * m->in_feat * 2, 256) : 0;
+  // the bf16 copy of x exists kXRep times when stored posteriors go through dense_tc_f32w_kernel (see its launcher)
+  constexpr int kXRep = 32;
+  const size_t xin1_b = kBf16 ? round_up((size_t)B * m->in_feat * 2, 256) : 0;
+  const size_t xin_b = xin1_b * ((kBf16 && src.stored) ? kXRep : 1);
   int64_t ns = (int64_t)std::max<size_t>(1, (ws_budget_bytes() - std::min(ws_budget_bytes(), xin_b)) / per);
   ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
   if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 8192)) return 1;
@@ -573,6 +595,9 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   if (kBf16) {
     DBX_LAUNCH(cast_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, xin, B * m->in_feat);
     x_in = xin;
+    if (src.stored)
+      for (int r = 1; r < kXRep; ++r)
+        DBX_CUDA(cudaMemcpyAsync((char*)xin + (size_t)r * xin1_b, xin, (size_t)B * m->in_feat * 2, cudaMemcpyDeviceToDevice, st));
   } else x_in = (const T*)x_dev;
 
   if (sink.kind == 1 && !sink.accumulate)
@@ -583,12 +608,10 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   bool skip_tensor[DBX_MAX_TENSORS] = {};
   bool layer_f32w[64] = {};
   bool any_f32w = false;
-  if (kBf16 && use_tc && src.stored && m->layers.size() <= 64 && !(getenv("DBX_NO_F32W") && getenv("DBX_NO_F32W")[0] == '1')) {
+  if (kBf16 && use_tc && src.stored && m->layers.size() <= 64) {
     for (int li = 0; li < (int)m->layers.size(); ++li) {
+      if (!f32w_layer_ok(m, li)) continue;
       const Layer& L = m->layers[li];
-      if (L.kind != DBX_DENSE || !L.has_w) continue;
-      if ((L.in_feat & 7) || (L.w_cols & 3) || (L.w_off & 3) || (m->slab_stride & 3) || ((uintptr_t)m->slab & 15)) continue;
-      if ((int64_t)L.w_rows * L.w_cols < 65536 || !(li == m->last_weighted || L.units % 8 == 0)) continue;
       for (int ti = 0; ti < m->table.n; ++ti)
         if (!m->table.is_bias[ti] && m->table.src_off[ti] == (int32_t)L.w_off) { skip_tensor[ti] = true; layer_f32w[li] = true; any_f32w = true; }
     }
@@ -630,7 +653,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
         const __nv_bfloat16* A16 = (const __nv_bfloat16*)cur;
         const int shared = (cur_ss == 0) ? 1 : 0;
         if (L.kind == DBX_DENSE && layer_f32w[li]) {
-          if (dense_tc_f32w_launch(A16, cur_ss, (int)L.in_feat, shared, m->slab, m->slab_stride, m->S, L.w_off,
+          if (dense_tc_f32w_launch(A16, shared ? (long long)(xin1_b / 2) : cur_ss, (int)L.in_feat, shared ? kXRep : 0, m->slab, m->slab_stride, m->S, L.w_off,
                                    src.idx ? src.idx + c0 : nullptr, src.j0 + c0, nc, (int)B, L.units, (int)L.in_feat, Bbase, b_sstride,
                                    boff, act, last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units,
                                    last ? logits : nullptr, B * C, st)) {
@@ -711,7 +734,7 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
   DBX_CUDA(cudaSetDevice(m->device));
   g_last_path = 0; g_used_tc = false;
   DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
-  {
+  if (!(mode == DBX_MODE_BF16 && src.stored && B > 8 && f32w_model_ok(m))) {
     const int r = stream_mlp_run(m, x_dev, B, n, src, sink, st);
     if (r < 0) return 1;
     if (r == 1) { g_last_path = 2; return 0; }

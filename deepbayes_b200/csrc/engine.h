@@ -121,7 +121,7 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
                     long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride,
                     long long b_off, int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32,
                     long long o32_sstride, cudaStream_t st);
-int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const float* slab, long long slab_stride,
+int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_rep, const float* slab, long long slab_stride,
                          long long slab_rows, long long w_off, const int32_t* w_rows, long long w_row0, int ns, int M, int N, int K,
                          const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
                          long long o16_sstride, int ld16, float* out32, long long o32_sstride, cudaStream_t st);

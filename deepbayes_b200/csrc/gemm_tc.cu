@@ -170,6 +170,7 @@ struct FGemmParams {
   GemmParams g;
   const int32_t* w_rows; long long w_row0;   // sample -> slab row (third TMA coordinate)
   int ns, tiles_n, tiles_m;
+  int a_rep;                                 // > 0: A is the same for every sample and exists a_rep times (copy s % a_rep is read)
 };
 
 // PERSISTENT: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened (sample, m tile, n tile)
@@ -237,8 +238,7 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->op_full[o]);
           mbar_expect_tx(fb, 16384);
-          if (p.a_shared) tma_load_2d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0);
-          else tma_load_3d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0, s);
+          tma_load_3d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0, fp.a_rep ? s % fp.a_rep : s);
         }
         __syncwarp();
         if (wt < total) issue_w();
@@ -442,19 +442,17 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
 // Launch one Dense layer whose weights are rows of the fp32 stored-sample slab: W element (k, n) of sample s is
 // slab[(w_rows ? w_rows[s] : w_row0 + s) * slab_stride + w_off + k * N + n].  Needs N % 4 == 0, w_off % 4 == 0,
 // slab_stride % 4 == 0 (16-byte TMA strides); returns 1 when not applicable so the caller can fall back.
-int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const float* slab, long long slab_stride,
+int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_rep, const float* slab, long long slab_stride,
                          long long slab_rows, long long w_off, const int32_t* w_rows, long long w_row0, int ns, int M, int N, int K,
                          const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
                          long long o16_sstride, int ld16, float* out32, long long o32_sstride, cudaStream_t st) {
   if (!g_tc_ok || !get_encode_fn()) return 1;
   if ((N & 3) || (w_off & 3) || (slab_stride & 3) || (lda & 7) || ((uintptr_t)slab & 15)) return 1;
   CUtensorMap tmA, tmW;
-  if (a_shared) {
-    uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, sb[1] = {(uint64_t)lda * 2};
-    uint32_t b[2] = {64, 128};
-    if (!make_tmap_bf16(&tmA, (void*)A, 2, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-  } else {
-    uint64_t d[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)lda * 2, (uint64_t)a_sstride * 2};
+  {
+    // a_rep > 0: the layer input is shared by all samples and replicated a_rep times a_sstride apart, so that the CTAs
+    // of different samples do not all pull the same L2 lines; a_rep == 0: one input per sample
+    uint64_t d[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(a_rep ? a_rep : ns)}, sb[2] = {(uint64_t)lda * 2, (uint64_t)a_sstride * 2};
     uint32_t b[3] = {64, 128, 1};
     if (!make_tmap_bf16(&tmA, (void*)A, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
@@ -466,8 +464,9 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
   FGemmParams fp = {};
   GemmParams& p = fp.g;
   p.M = M; p.N = N; p.K = K; p.NT = kFNT;
-  p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
+  p.a_shared = a_rep ? 1 : 0; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
+  fp.a_rep = a_rep;
   fp.w_rows = w_rows; fp.w_row0 = w_row0;
   fp.ns = ns; fp.tiles_n = (int)cdiv(N, kFNT); fp.tiles_m = (int)cdiv(M, 128);
   const int smem = kFLand * kFLandBytes + kFOp * kFOpBytes + (int)sizeof(FBarriers) + 1024;
