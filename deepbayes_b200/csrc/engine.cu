@@ -391,42 +391,70 @@ __global__ void accum_kernel(const float* __restrict__ logits, int ns, int64_t B
   }
 }
 
-// Few outputs, many samples (small batches): one WARP per output element; lane l sums the contiguous sample range
-// [l*ns/32, (l+1)*ns/32) in order and lane 0 adds the 32 partial sums in lane order -- deterministic, and 32x the
-// parallelism of the kernel above (which left a B=64, C=10 call with 640 busy threads for 256 samples).
+// One BLOCK per input row b (C <= 32): thread t takes the contiguous sample range [t*ns/256, (t+1)*ns/256), evaluates the
+// last activation ONCE per (sample, row) for all C classes and keeps C running sums in registers; the 256 partial sums
+// are combined by a fixed shuffle tree and a fixed-order pass over the 8 warps -- deterministic.  (The element-per-thread
+// kernel above recomputes the softmax C times and, at B = 64, left a 256-sample chunk to 640 threads: 224 us.)
+constexpr int kAccumMaxC = 32;
 __global__ void __launch_bounds__(256)
-accum_warp_kernel(const float* __restrict__ logits, int ns, int64_t B, int C, int act, int out_kind,
-                  const float* __restrict__ wts, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
-  const int64_t total = B * C;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t o = warp0; o < total; o += nwarps) {
-    const int64_t b = o / C;
-    const int c = (int)(o - b * C);
-    const int s_lo = (int)(((int64_t)lane * ns) / 32), s_hi = (int)(((int64_t)(lane + 1) * ns) / 32);
-    float a1 = 0.f, a2 = 0.f;
-    for (int s = s_lo; s < s_hi; ++s) {
-      const float p = accum_value(logits + ((int64_t)s * B + b) * C, c, C, act, out_kind);
-      const float w = wts ? wts[s] : 1.f;
-      if (wts) { a1 = fmaf(w, p, a1); a2 = fmaf(w, p * p, a2); }
-      else { a1 += p; a2 = fmaf(p, p, a2); }
+accum_block_kernel(const float* __restrict__ logits, int ns, int64_t B, int C, int act, int out_kind,
+                   const float* __restrict__ wts, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
+  __shared__ float part[8][2][kAccumMaxC];
+  const int64_t b = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int s_lo = (int)(((int64_t)t * ns) / 256), s_hi = (int)(((int64_t)(t + 1) * ns) / 256);
+  float a1[kAccumMaxC], a2[kAccumMaxC];
+#pragma unroll
+  for (int c = 0; c < kAccumMaxC; ++c) { a1[c] = 0.f; a2[c] = 0.f; }
+  for (int s = s_lo; s < s_hi; ++s) {
+    const float* z = logits + ((int64_t)s * B + b) * C;
+    float v[kAccumMaxC];
+#pragma unroll
+    for (int c = 0; c < kAccumMaxC; ++c) v[c] = (c < C) ? z[c] : -INFINITY;
+    if (out_kind != DBX_OUT_LOGITS) {
+      if (act == DBX_ACT_SOFTMAX) {
+        float m = v[0];
+#pragma unroll
+        for (int c = 1; c < kAccumMaxC; ++c) m = fmaxf(m, v[c]);
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < kAccumMaxC; ++c) { v[c] = (c < C) ? expf(v[c] - m) : 0.f; den += v[c]; }
+#pragma unroll
+        for (int c = 0; c < kAccumMaxC; ++c) v[c] = v[c] / den;
+      } else {
+#pragma unroll
+        for (int c = 0; c < kAccumMaxC; ++c) v[c] = (c < C) ? apply_act(act, v[c]) : 0.f;
+      }
     }
+    const float w = wts ? wts[s] : 1.f;
+#pragma unroll
+    for (int c = 0; c < kAccumMaxC; ++c)
+      if (c < C) { a1[c] = fmaf(w, v[c], a1[c]); a2[c] = fmaf(w * v[c], v[c], a2[c]); }
+  }
+#pragma unroll
+  for (int c = 0; c < kAccumMaxC; ++c) {
+    if (c < C) {
+      float x1 = a1[c], x2 = a2[c];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) { x1 += __shfl_down_sync(0xffffffffu, x1, d); x2 += __shfl_down_sync(0xffffffffu, x2, d); }
+      if (lane == 0) { part[warp][0][c] = x1; part[warp][1][c] = x2; }
+    }
+  }
+  __syncthreads();
+  if (t < C) {
+    const int64_t o = b * C + t;
     float t1 = overwrite ? 0.f : sum1[o];
     float t2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
-    for (int l = 0; l < 32; ++l) {
-      t1 += __shfl_sync(0xffffffffu, a1, l);
-      t2 += __shfl_sync(0xffffffffu, a2, l);
-    }
-    if (lane == 0) { sum1[o] = t1; if (sum2) sum2[o] = t2; }
+    for (int w8 = 0; w8 < 8; ++w8) { t1 += part[w8][0][t]; t2 += part[w8][1][t]; }
+    sum1[o] = t1;
+    if (sum2) sum2[o] = t2;
   }
 }
 
 static inline void launch_accum(const float* logits, int ns, int64_t B, int C, int act, int out_kind, const float* wts, int overwrite,
                                 float* sum1, float* sum2, cudaStream_t st) {
-  if (B * C <= 8192 && ns >= 64) {
-    const int64_t threads = B * C * 32;
-    accum_warp_kernel<<<(unsigned)std::min<int64_t>(cdiv(threads, 256), 148 * 8), 256, 0, st>>>(logits, ns, B, C, act, out_kind, wts,
-                                                                                               overwrite, sum1, sum2);
+  if (C <= kAccumMaxC && ns >= 32 && B <= 65535 * 16) {
+    accum_block_kernel<<<(unsigned)B, 256, 0, st>>>(logits, ns, B, C, act, out_kind, wts, overwrite, sum1, sum2);
   } else {
     accum_kernel<<<(unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(B * C, 256), 1), 148 * 16), 256, 0, st>>>(
         logits, ns, B, C, act, out_kind, wts, overwrite, sum1, sum2);

@@ -62,7 +62,7 @@ def cfg3(S):
         slab[s0:s0 + nc] = eng.sample(nc, seed=7, s0=s0)
     eng.set_samples(slab)
     freq = torch.full((S,), 1.0 / S, device="cuda")
-    for B in (1, 8, 16, 64):
+    for B in (1, 8, 16, 64, 128, 512):
         x = torch.from_numpy(o.synthetic_x((B, 784), seed=0)).cuda()
         lib = _lib.load()
         ms = timeit(lambda: eng.predict_stored_sums(x, S, j0=0, wts=freq, mode="bf16", second_moment=True), warm=1, reps=3)
