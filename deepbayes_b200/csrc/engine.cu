@@ -356,6 +356,35 @@ __global__ void maxpool_kernel(const T* __restrict__ A, int64_t a_sstride, T* __
   }
 }
 
+// bf16, C % 8 == 0: one thread = 8 channels (16-byte loads / stores, packed bf16x2 max)
+__global__ void maxpool_bf16_vec8_kernel(const __nv_bfloat16* __restrict__ A, int64_t a_sstride, __nv_bfloat16* __restrict__ out,
+                                         int64_t o_sstride, int NB, int H, int Wd, int C, int Ho, int Wo, int ph, int pw, int sh,
+                                         int sw) {
+  const int s = blockIdx.y;
+  const uint4* Ap = reinterpret_cast<const uint4*>(A + (int64_t)s * a_sstride);
+  uint4* op = reinterpret_cast<uint4*>(out + (int64_t)s * o_sstride);
+  const int C8 = C >> 3;
+  const int64_t total = (int64_t)NB * Ho * Wo * C8;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(o % C8);
+    int64_t r = o / C8;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int nb = (int)(r / Ho);
+    __nv_bfloat162 m[4];
+    bool first = true;
+    for (int i = 0; i < ph; ++i)
+      for (int j = 0; j < pw; ++j) {
+        const uint4 v = __ldg(Ap + (((int64_t)nb * H + ho * sh + i) * Wd + wo * sw + j) * C8 + c8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = first ? h[q] : __hmax2(m[q], h[q]);
+        first = false;
+      }
+    op[o] = *reinterpret_cast<const uint4*>(m);
+  }
+}
+
 // Sample-ordered accumulation of the model output over the chunk's samples:
 //   sum1[b,c] (+)= sum_s w_s * f_s[b,c],  sum2 likewise with f^2  (posteriormodel.py:95-100).
 // logits [ns,B,C] fp32 are the last layer's pre-activation values.
@@ -727,9 +756,15 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
                      L.out_c, L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l, act);
         }
       } else if (L.kind == DBX_MAXPOOL2D) {
-        dim3 grid((unsigned)grid_for(B * L.out_feat), (unsigned)nc);
-        DBX_LAUNCH(maxpool_kernel<T>, grid, 256, 0, st, cur, cur_ss, bufs[bi], B * L.out_feat, (int)B, L.in_h, L.in_w,
-                   L.in_c, L.out_h, L.out_w, L.kh, L.kw, L.sh, L.sw);
+        if (kBf16 && L.in_c % 8 == 0 && cur_ss % 8 == 0 && (B * L.out_feat) % 8 == 0) {
+          dim3 grid((unsigned)grid_for(B * L.out_feat / 8), (unsigned)nc);
+          DBX_LAUNCH(maxpool_bf16_vec8_kernel, grid, 256, 0, st, (const __nv_bfloat16*)cur, cur_ss, (__nv_bfloat16*)bufs[bi],
+                     B * L.out_feat, (int)B, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.kh, L.kw, L.sh, L.sw);
+        } else {
+          dim3 grid((unsigned)grid_for(B * L.out_feat), (unsigned)nc);
+          DBX_LAUNCH(maxpool_kernel<T>, grid, 256, 0, st, cur, cur_ss, bufs[bi], B * L.out_feat, (int)B, L.in_h, L.in_w,
+                     L.in_c, L.out_h, L.out_w, L.kh, L.kw, L.sh, L.sw);
+        }
       }
       if (L.has_w)
         prof_end(st, 2.0 * (double)L.w_rows * L.w_cols * (L.kind == DBX_CONV2D ? (double)L.out_h * L.out_w : 1.0) * (double)B * nc);

@@ -15,7 +15,6 @@ namespace dbx {
 using namespace tc05;
 
 constexpr int kGStages = 4;
-constexpr int kGStageBytes = 49152;   // A block [128 x 64] 16 KB + W blocks up to [64 x 256] 32 KB
 constexpr int kGThreads = 192;
 
 struct GemmParams {
@@ -36,11 +35,17 @@ struct __align__(8) GBarriers {
 
 extern __shared__ __align__(1024) uint8_t gemm_smem_raw[];
 
-__global__ void __launch_bounds__(kGThreads, 1)
+// kNTMax = widest column tile of the launch (64 / 128 / 256): it fixes the stage size (A block 16 KB + kNTMax/64 weight
+// blocks of 8 KB) and the TMEM allocation, so narrow layers (conv kernels with 32 / 64 output channels) run 3-4 CTAs
+// per SM instead of one -- their tiles have 1-5 k-blocks, and a lone CTA per SM spent most of its life in the prologue.
+template <int kNTMax>
+__global__ void __launch_bounds__(kGThreads, kNTMax == 256 ? 1 : (kNTMax == 128 ? 2 : 3))
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  constexpr int kStageB = 16384 + (kNTMax / 64) * 8192;
+  constexpr int kSt = kNTMax == 64 ? 3 : kGStages;            // 3 x 24 KB: three CTAs of a narrow layer fit one SM
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  GBarriers* bars = (GBarriers*)(smem + kGStages * kGStageBytes);
+  GBarriers* bars = (GBarriers*)(smem + kSt * kStageB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * p.NT, m0 = blockIdx.y * 128, s = blockIdx.z;
   const int nt = min(p.NT, ((p.N - n0 + 63) / 64) * 64);     // columns of this tile, multiple of 64
@@ -48,11 +53,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kb_n = (p.K + 63) / 64;
 
   if (tid == 0) {
-    for (int i = 0; i < kGStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < kSt; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->acc_full), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem_slot));
+  if (warp == 1) tmem_alloc<kNTMax>(smem_u32(&bars->tmem_slot));
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
   fence_before_sync();
   __syncthreads();
@@ -61,11 +66,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     for (int kb = 0; kb < kb_n; ++kb) {
-      const uint32_t st = kb % kGStages, ph = (kb / kGStages) & 1;
+      const uint32_t st = kb % kSt, ph = (kb / kSt) & 1;
       mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
       if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->full[st]);
-        const uint32_t base = s_stage + st * kGStageBytes;
+        const uint32_t base = s_stage + st * kStageB;
         mbar_expect_tx(fb, 16384 + nblk * 8192);
         if (p.a_shared) tma_load_2d(base, &tmA, fb, kb * 64, m0);
         else tma_load_3d(base, &tmA, fb, kb * 64, m0, s);
@@ -77,11 +82,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t idesc = make_idesc_bf16(128, nt, 0, 1);
     for (int kb = 0; kb < kb_n; ++kb) {
-      const uint32_t st = kb % kGStages, ph = (kb / kGStages) & 1;
+      const uint32_t st = kb % kSt, ph = (kb / kSt) & 1;
       mbar_wait(smem_u32(&bars->full[st]), ph);
       fence_after_sync();
       if (elect_one()) {
-        const uint32_t a16 = ((s_stage + st * kGStageBytes) & 0x3FFFF) >> 4;
+        const uint32_t a16 = ((s_stage + st * kStageB) & 0x3FFFF) >> 4;
         const uint32_t a_lo = a16 | (1u << 16);
         const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
         const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
@@ -136,7 +141,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<kNTMax>(tmem);
 }
 
 
@@ -427,14 +432,18 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
   p.M = M; p.N = N; p.K = K; p.NT = (int)std::min<int64_t>(256, round_up(N, 64));
   p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
-  const int smem = kGStages * kGStageBytes + (int)sizeof(GBarriers) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { g_tc_ok = false; return 1; }
-    attr_done = true;
-  }
   dim3 grid((unsigned)cdiv(N, p.NT), (unsigned)cdiv(M, 128), (unsigned)ns);
-  dense_tc_kernel<<<grid, kGThreads, smem, st>>>(tmA, tmW, p);
+  auto go = [&](auto kern, int ntmax) -> int {
+    const int smem = (ntmax == 64 ? 3 : kGStages) * (16384 + (ntmax / 64) * 8192) + (int)sizeof(GBarriers) + 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { g_tc_ok = false; return 1; }
+    kern<<<grid, kGThreads, smem, st>>>(tmA, tmW, p);
+    return 0;
+  };
+  int rc;
+  if (p.NT <= 64) rc = go(dense_tc_kernel<64>, 64);
+  else if (p.NT <= 128) rc = go(dense_tc_kernel<128>, 128);
+  else rc = go(dense_tc_kernel<256>, 256);
+  if (rc) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
