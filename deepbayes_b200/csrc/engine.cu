@@ -722,6 +722,10 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
                                     (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff, act,
                                     last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units, last ? logits : nullptr,
                                     B * C, st) == 0;
+        } else if (L.kind == DBX_CONV2D && !last && !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1') &&
+                   conv_tc_launch(A16, cur_ss, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L, Bbase, b_sstride,
+                                  boff, act, (__nv_bfloat16*)bufs[bi], B * L.out_feat, st) == 0) {
+          done_tc = true;      // direct convolution: per-tap TMA boxes of the NHWC input, no im2col matrix
         } else if (L.kind == DBX_CONV2D) {
           const int Kp = (int)round_up(L.w_rows, 8);
           const long long Mrows = (long long)B * L.out_h * L.out_w;

@@ -356,6 +356,160 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) tmem_dealloc<128>(tmem);
 }
 
+
+// =======================================================================================
+// Direct Conv2D (stride 1, Cin in {16, 32, 64}) on tcgen05 -- no im2col matrix.  A tile = R output rows x Wo output
+// columns of one image (R * Wo <= 128 accumulator rows); for filter tap (i, j) the A operand is the box
+// [Cin, Wo, R] of the NHWC input at (j - pad_l, ho0 + i - pad_t), which TMA delivers as R*Wo rows of Cin channels
+// (out-of-range coordinates -- SAME padding -- arrive as zeros), and the B operand is rows [tap*Cin, (tap+1)*Cin) of
+// the sample's HWIO kernel.  K loop = kh*kw taps x Cin/16 MMAs.  Persistent CTAs (tile list = sample x image x row
+// group), two TMEM accumulators, epilogue (bias, activation, NHWC bf16 stores) overlapped with the next tile.
+// Before: the conv input was expanded to an im2col matrix in HBM (115 MB per sample for config 4's second conv) and
+// read back by the GEMM.
+// =======================================================================================
+constexpr int kCStages = 6;
+constexpr int kCThreads = 192;
+
+struct ConvParams {
+  int NB, Ho, Wo, Cin, Cout, kh, kw, pad_t, pad_l, R, tiles_per_img, ns, a_shared, act;
+  const float* bias; long long b_sstride, b_off;
+  __nv_bfloat16* out; long long o_sstride;
+};
+
+struct __align__(8) CBarriers {
+  uint64_t full[kCStages], empty[kCStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(kCThreads, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  const int cin_b = p.Cin * 2;                        // bytes per A row = swizzle span (32 / 64 / 128)
+  const int a_bytes = 128 * cin_b;                    // A slot (R*Wo <= 128 rows are written)
+  const int nblk = (p.Cout + 63) / 64;                // 64-column weight blocks, each Cin rows of 128 B
+  const int stage_b = a_bytes + nblk * p.Cin * 128;
+  CBarriers* bars = (CBarriers*)(smem + kCStages * stage_b);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int taps = p.kh * p.kw;
+  const long long total = (long long)p.ns * p.NB * p.tiles_per_img;
+  const int NT = nblk * 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < kCStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  auto decode = [&](long long t, int& ho0, int& nb, int& s) {
+    const int rg = (int)(t % p.tiles_per_img);
+    const long long r = t / p.tiles_per_img;
+    ho0 = rg * p.R; nb = (int)(r % p.NB); s = (int)(r / p.NB);
+  };
+
+  if (warp == 0) {
+    uint32_t g = 0;
+    const uint32_t tx = (uint32_t)(p.R * p.Wo * cin_b + nblk * p.Cin * 128);
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+      int ho0, nb, s;
+      decode(t, ho0, nb, s);
+      for (int tap = 0; tap < taps; ++tap, ++g) {
+        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          const uint32_t base = s_stage + st * stage_b;
+          const int i = tap / p.kw, j = tap - i * p.kw;
+          mbar_expect_tx(fb, tx);
+          tma_load_5d(base, &tmA, fb, 0, j - p.pad_l, ho0 + i - p.pad_t, nb, p.a_shared ? 0 : s);
+          for (int b = 0; b < nblk; ++b) tma_load_3d(base + a_bytes + b * p.Cin * 128, &tmW, fb, b * 64, tap * p.Cin, s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // A: K-major rows of cin_b bytes, 8-row groups cin_b*8 apart, swizzle span = cin_b.  B: MN-major SWIZZLE_128B.
+    const uint32_t swz = cin_b == 128 ? 2u : (cin_b == 64 ? 4u : 6u);
+    const uint32_t a_hi = ((uint32_t)(cin_b * 8) >> 4) | (1u << 14) | (swz << 29);
+    constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = make_idesc_bf16(128, NT, 0, 1);
+    const int ksteps = p.Cin / 16;
+    uint32_t g = 0, it = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
+      fence_after_sync();
+      for (int tap = 0; tap < taps; ++tap, ++g) {
+        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        mbar_wait(smem_u32(&bars->full[st]), ph);
+        if (elect_one()) {
+          const uint32_t a16 = ((s_stage + st * stage_b) & 0x3FFFF) >> 4;
+          const uint32_t a_lo = a16 | (1u << 16);
+          const uint32_t b_lo = (a16 + (uint32_t)(a_bytes >> 4)) | ((uint32_t)((p.Cin * 128) >> 4) << 16);
+          for (int kk = 0; kk < ksteps; ++kk)
+            mma_ss_lh(tmem + ab * 128, a_lo + kk * 2, a_hi, b_lo + kk * 128, b_hi, idesc, (tap | kk) > 0);
+          mma_commit(smem_u32(&bars->empty[st]));
+          if (tap == taps - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int gq = warp & 3;
+    const int row = gq * 32 + lane;                  // accumulator row = output pixel r * Wo + wo of the tile
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    const int r = row / p.Wo, wo = row - r * p.Wo;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      int ho0, nb, s;
+      decode(t, ho0, nb, s);
+      const uint32_t ab = it & 1;
+      const float* bias = p.bias + (long long)s * p.b_sstride + p.b_off;
+      const bool valid = r < p.R && ho0 + r < p.Ho;
+      __nv_bfloat16* dst = p.out + (long long)s * p.o_sstride + ((((long long)nb * p.Ho + ho0 + r) * p.Wo + wo) * p.Cout);
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + ab * 128 + c0, v);
+        wait_ld();
+        if (c0 + 32 >= NT) {   // everything is in registers: hand the accumulator back before the stores
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+        }
+        if (valid) {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const int c = c0 + q8 * 8;
+            if (c + 8 <= p.Cout) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                   apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+              *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              for (int i = 0; i < 8; ++i)
+                if (c + i < p.Cout) dst[c + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
 // NHWC bf16 activations -> im2col rows [n*Ho*Wo][kh*kw*C (padded to Kp)] so that Conv2D becomes the GEMM above
 // (same (kh, kw, cin) ordering as the HWIO kernel flattened to [kh*kw*cin, cout]).
 __global__ void im2col_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long in_sstride, __nv_bfloat16* __restrict__ out,
@@ -490,6 +644,52 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
   const long long total = (long long)ns * fp.tiles_m * fp.tiles_n;
   dim3 grid((unsigned)std::min<long long>(total, 2LL * num_sms));   // two resident CTAs per SM
   dense_tc_f32w_kernel<<<grid, kFThreads, smem, st>>>(tmA, tmW, fp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Direct convolution launch.  in: bf16 NHWC [ns or 1][NB][H][W][Cin]; W16: the sample's HWIO kernel as [kh*kw*Cin][ldw] bf16
+// rows; out: bf16 NHWC [ns][NB][Ho][Wo][Cout].  Returns 1 when the layer is outside the kernel's scope (the caller then
+// uses im2col + dense_tc_kernel).
+int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared, const __nv_bfloat16* W16, long long w_sstride_elems,
+                   int ldw, int ns, int NB, const Layer& L, const float* bias, long long b_sstride, long long b_off, int act,
+                   __nv_bfloat16* out, long long o_sstride, cudaStream_t st) {
+  if (!g_tc_ok || !get_encode_fn()) return 1;
+  const int Cin = L.in_c, Cout = L.out_c, Wo = L.out_w, Ho = L.out_h;
+  if (L.sh != 1 || L.sw != 1 || !(Cin == 16 || Cin == 32 || Cin == 64) || Cout > 128 || (Cout & 7) || Wo > 128 || Wo < 1) return 1;
+  if ((in_sstride & 7) || (o_sstride & 7) || (ldw & 7) || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return 1;
+  const int R = std::min(128 / Wo, Ho);
+  const int nblk = (Cout + 63) / 64;
+  const int stage_b = 128 * Cin * 2 + nblk * Cin * 128;
+  const int smem = kCStages * stage_b + (int)sizeof(CBarriers) + 1024;
+  if (smem > 110 * 1024) return 1;
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t d[5] = {(uint64_t)Cin, (uint64_t)L.in_w, (uint64_t)L.in_h, (uint64_t)NB, (uint64_t)(in_shared ? 1 : ns)};
+    uint64_t sb[4] = {(uint64_t)Cin * 2, (uint64_t)L.in_w * Cin * 2, (uint64_t)L.in_h * L.in_w * Cin * 2,
+                      (uint64_t)(in_shared ? (long long)NB * L.in_h * L.in_w * Cin : in_sstride) * 2};
+    uint32_t b[5] = {(uint32_t)Cin, (uint32_t)Wo, (uint32_t)R, 1, 1};
+    const CUtensorMapSwizzle swz = Cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (Cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (!make_tmap_bf16(&tmA, (void*)in, 5, d, sb, b, swz)) return 1;
+  }
+  {
+    uint64_t d[3] = {(uint64_t)ldw, (uint64_t)L.w_rows, (uint64_t)ns}, sb[2] = {(uint64_t)ldw * 2, (uint64_t)w_sstride_elems * 2};
+    uint32_t b[3] = {64, (uint32_t)Cin, 1};
+    if (!make_tmap_bf16(&tmW, (void*)W16, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  ConvParams p = {};
+  p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.kh = L.kh; p.kw = L.kw; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
+  p.R = R; p.tiles_per_img = (int)cdiv(Ho, R); p.ns = ns; p.a_shared = in_shared; p.act = act;
+  p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.out = out; p.o_sstride = o_sstride;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+  }
+  if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  const long long total = (long long)ns * NB * p.tiles_per_img;
+  dim3 grid((unsigned)std::min<long long>(total, 2LL * num_sms));
+  conv_tc_kernel<<<grid, kCThreads, smem, st>>>(tmA, tmW, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -654,3 +654,38 @@ def test_stored_posterior_f32_slab_on_tensor_cores(oracle, monkeypatch, dims, B,
     monkeypatch.setenv("DBX_NO_F32W", "1")
     b1, _ = eng.predict_stored_sums(x, S - 2, j0=2, mode="bf16")
     np.testing.assert_allclose(a1.cpu().numpy() / (S - 2), b1.cpu().numpy() / (S - 2), rtol=0, atol=2e-4)
+
+
+def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
+    """conv_tc_kernel (per-tap TMA boxes of the NHWC input, no im2col matrix) against the im2col + GEMM path on the same
+    sampled weights, and against the fp32 mode: VALID and SAME padding, Cin = 16 / 32 / 64, ragged row groups, Cout
+    that is not a multiple of 64."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    m = db.Sequential([db.Conv2D(16, 3, activation="relu", input_shape=(13, 11, 3)),          # Cin = 3: im2col path
+                       db.Conv2D(32, 3, padding="same", activation="relu"),                   # Cin = 16, SAME
+                       db.Conv2D(64, (2, 3), activation="tanh"),                              # Cin = 32, VALID, 2x3 taps
+                       db.Conv2D(24, 3, padding="same", activation="relu"),                   # Cin = 64, Cout = 24
+                       db.MaxPooling2D(2), db.Flatten(), db.Dense(10, activation="softmax")])
+    eng = Engine(m)
+    g = np.random.Generator(np.random.Philox(21))
+    mu = (g.standard_normal(eng.P) * 0.08).astype(np.float32)
+    sg = np.full(eng.P, 0.01, np.float32)
+    eng.set_gaussian(mu, sg)
+    B, n = 37, 5
+    x = oracle.synthetic_x((B, 13, 11, 3), seed=4)
+    f1, _ = eng.predict_sums(x, n, seed=9, mode="fp32")
+    d1, d2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
+    assert eng.last_path() == "generic_tc"
+    launches_direct = _lib_launches()
+    monkeypatch.setenv("DBX_NO_DIRECT_CONV", "1")
+    i1, i2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
+    np.testing.assert_allclose(d1.cpu().numpy() / n, i1.cpu().numpy() / n, rtol=0, atol=1.5e-3)
+    np.testing.assert_allclose(d2.cpu().numpy() / n, i2.cpu().numpy() / n, rtol=0, atol=1.5e-3)
+    np.testing.assert_allclose(d1.cpu().numpy() / n, f1.cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
+    assert _lib_launches() - launches_direct > 0
+
+
+def _lib_launches():
+    from deepbayes_b200 import _lib
+    return _lib.launch_count()
