@@ -628,19 +628,31 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   size_t col_b = 0;
   bool use_tc = kBf16;
   if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') use_tc = false;
+  // (not the layers conv_tc_kernel takes directly; a conv on the call's input, which every sample shares, needs ONE
+  // column matrix per call, built before the chunk loop)
+  const bool direct_conv = !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1');
+  size_t col0_b = 0;
+  int first_w = -1;
+  for (int li = 0; li < (int)m->layers.size(); ++li) if (m->layers[li].has_w) { first_w = li; break; }
   if (use_tc)
-    for (auto& L : m->layers)
-      if (L.kind == DBX_CONV2D) col_b = std::max(col_b, (size_t)B * L.out_h * L.out_w * round_up(L.w_rows, 8) * 2);
+    for (int li = 0; li < (int)m->layers.size(); ++li) {
+      const Layer& L = m->layers[li];
+      if (L.kind != DBX_CONV2D || (direct_conv && li != m->last_weighted && conv_tc_eligible(L))) continue;
+      const size_t b = round_up((size_t)B * L.out_h * L.out_w * round_up(L.w_rows, 8) * 2, 256);
+      if (li == first_w) col0_b = b; else col_b = std::max(col_b, b);
+    }
   const size_t per = 2 * act_b + w_b + (size_t)B * C * 4 + col_b + 256;
   // the bf16 copy of x exists kXRep times when stored posteriors go through dense_tc_f32w_kernel (see its launcher)
   constexpr int kXRep = 32;
   const size_t xin1_b = kBf16 ? round_up((size_t)B * m->in_feat * 2, 256) : 0;
-  const size_t xin_b = xin1_b * ((kBf16 && src.stored) ? kXRep : 1);
+  const size_t xin_b = xin1_b * ((kBf16 && src.stored) ? kXRep : 1) + col0_b;
   int64_t ns = (int64_t)std::max<size_t>(1, (ws_budget_bytes() - std::min(ws_budget_bytes(), xin_b)) / per);
   ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
   if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 8192)) return 1;
   char* p = (char*)m->ws.ptr;
-  T* xin = (T*)p; p += xin_b;
+  T* xin = (T*)p; p += xin_b - col0_b;
+  __nv_bfloat16* col0 = (__nv_bfloat16*)p; p += col0_b;
+  bool col0_done = false;
   T* act0 = (T*)p; p += round_up((size_t)ns * act_b, 256);
   T* act1 = (T*)p; p += round_up((size_t)ns * act_b, 256);
   float* logits = (float*)p; p += round_up((size_t)ns * B * C * 4, 256);
@@ -730,8 +742,12 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
           const int Kp = (int)round_up(L.w_rows, 8);
           const long long Mrows = (long long)B * L.out_h * L.out_w;
           const long long col_ss = shared ? 0 : Mrows * Kp;
-          if (im2col_launch(A16, cur_ss, colbuf, col_ss, shared ? 1 : nc, (int)B, L, Kp, st) == 0)
-            done_tc = dense_tc_launch(colbuf, col_ss, Kp, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc,
+          __nv_bfloat16* cb = (shared && li == first_w && col0_b) ? col0 : colbuf;
+          bool col_ok = true;
+          if (!(cb == col0 && col0_done)) col_ok = im2col_launch(A16, cur_ss, cb, col_ss, shared ? 1 : nc, (int)B, L, Kp, st) == 0;
+          if (cb == col0 && col_ok) col0_done = true;      // the input is the same for every chunk of this call
+          if (col_ok)
+            done_tc = dense_tc_launch(cb, col_ss, Kp, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc,
                                       (int)Mrows, L.units, (int)L.w_rows, Bbase, b_sstride, boff, act,
                                       last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units,
                                       last ? logits : nullptr, B * C, st) == 0;

@@ -372,6 +372,7 @@ constexpr int kCThreads = 192;
 
 struct ConvParams {
   int NB, Ho, Wo, Cin, Cout, kh, kw, pad_t, pad_l, R, tiles_per_img, ns, a_shared, act;
+  int w_res;   // the whole kernel tensor of a sample stays in shared memory while the CTA works on that sample
   const float* bias; long long b_sstride, b_off;
   __nv_bfloat16* out; long long o_sstride;
 };
@@ -379,6 +380,7 @@ struct ConvParams {
 struct __align__(8) CBarriers {
   uint64_t full[kCStages], empty[kCStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t w_full;
   uint32_t tmem_slot;
 };
 
@@ -389,16 +391,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int cin_b = p.Cin * 2;                        // bytes per A row = swizzle span (32 / 64 / 128)
   const int a_bytes = 128 * cin_b;                    // A slot (R*Wo <= 128 rows are written)
   const int nblk = (p.Cout + 63) / 64;                // 64-column weight blocks, each Cin rows of 128 B
-  const int stage_b = a_bytes + nblk * p.Cin * 128;
-  CBarriers* bars = (CBarriers*)(smem + kCStages * stage_b);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int w_tap_b = nblk * p.Cin * 128;             // one tap's weight rows
   const int taps = p.kh * p.kw;
+  // w_res: [all taps' weights][A stages]; otherwise every stage carries its tap's weights behind the A block.  (With
+  // per-tap weight loads every CTA of the GPU re-read the same few KB of the current sample's kernel for every tile.)
+  const int w_res_b = p.w_res ? taps * w_tap_b : 0;
+  const int stage_b = a_bytes + (p.w_res ? 0 : w_tap_b);
+  const uint32_t s_wres = s_stage;
+  const uint32_t s_ring = s_stage + w_res_b;
+  CBarriers* bars = (CBarriers*)(smem + w_res_b + kCStages * stage_b);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = (long long)p.ns * p.NB * p.tiles_per_img;
   const int NT = nblk * 64;
 
   if (tid == 0) {
     for (int i = 0; i < kCStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    mbar_init(smem_u32(&bars->w_full), 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(smem_u32(&bars->tmem_slot));
@@ -416,20 +425,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     uint32_t g = 0;
-    const uint32_t tx = (uint32_t)(p.R * p.Wo * cin_b + nblk * p.Cin * 128);
+    const uint32_t tx = (uint32_t)(p.R * p.Wo * cin_b + (p.w_res ? 0 : w_tap_b));
+    int cur_s = -1;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
       int ho0, nb, s;
       decode(t, ho0, nb, s);
+      if (p.w_res && s != cur_s) {
+        // new sample: every MMA that read the old weights has retired once the last tap's commit has arrived
+        if (g > 0) mbar_wait(smem_u32(&bars->empty[(g - 1) % kCStages]), ((g - 1) / kCStages) & 1);
+        if (elect_one()) {
+          const uint32_t wf = smem_u32(&bars->w_full);
+          mbar_expect_tx(wf, (uint32_t)w_res_b);
+          for (int tap = 0; tap < taps; ++tap)
+            for (int b = 0; b < nblk; ++b) tma_load_3d(s_wres + tap * w_tap_b + b * p.Cin * 128, &tmW, wf, b * 64, tap * p.Cin, s);
+        }
+        __syncwarp();
+        cur_s = s;
+      }
       for (int tap = 0; tap < taps; ++tap, ++g) {
         const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->full[st]);
-          const uint32_t base = s_stage + st * stage_b;
+          const uint32_t base = s_ring + st * stage_b;
           const int i = tap / p.kw, j = tap - i * p.kw;
           mbar_expect_tx(fb, tx);
           tma_load_5d(base, &tmA, fb, 0, j - p.pad_l, ho0 + i - p.pad_t, nb, p.a_shared ? 0 : s);
-          for (int b = 0; b < nblk; ++b) tma_load_3d(base + a_bytes + b * p.Cin * 128, &tmW, fb, b * 64, tap * p.Cin, s);
+          if (!p.w_res)
+            for (int b = 0; b < nblk; ++b) tma_load_3d(base + a_bytes + b * p.Cin * 128, &tmW, fb, b * 64, tap * p.Cin, s);
         }
         __syncwarp();
       }
@@ -441,18 +464,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t idesc = make_idesc_bf16(128, NT, 0, 1);
     const int ksteps = p.Cin / 16;
-    uint32_t g = 0, it = 0;
+    uint32_t g = 0, it = 0, w_n = 0;
+    int cur_s = -1;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const uint32_t ab = it & 1;
+      if (p.w_res) {
+        int ho0, nb, s;
+        decode(t, ho0, nb, s);
+        if (s != cur_s) { mbar_wait(smem_u32(&bars->w_full), w_n & 1); ++w_n; cur_s = s; }
+      }
       mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
       fence_after_sync();
       for (int tap = 0; tap < taps; ++tap, ++g) {
         const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
         mbar_wait(smem_u32(&bars->full[st]), ph);
         if (elect_one()) {
-          const uint32_t a16 = ((s_stage + st * stage_b) & 0x3FFFF) >> 4;
+          const uint32_t a16 = ((s_ring + st * stage_b) & 0x3FFFF) >> 4;
           const uint32_t a_lo = a16 | (1u << 16);
-          const uint32_t b_lo = (a16 + (uint32_t)(a_bytes >> 4)) | ((uint32_t)((p.Cin * 128) >> 4) << 16);
+          const uint32_t w16 = p.w_res ? (((s_wres + tap * w_tap_b) & 0x3FFFF) >> 4) : (a16 + (uint32_t)(a_bytes >> 4));
+          const uint32_t b_lo = w16 | ((uint32_t)((p.Cin * 128) >> 4) << 16);
           for (int kk = 0; kk < ksteps; ++kk)
             mma_ss_lh(tmem + ab * 128, a_lo + kk * 2, a_hi, b_lo + kk * 128, b_hi, idesc, (tap | kk) > 0);
           mma_commit(smem_u32(&bars->empty[st]));
@@ -648,6 +678,23 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// dynamic shared memory of conv_tc_kernel; the kernel tensor stays resident when it is at most 40 KB
+static int conv_tc_smem(int taps, int Cin, int nblk, int* w_res) {
+  const int w_tap_b = nblk * Cin * 128, a_bytes = 128 * Cin * 2;
+  const int res = taps * w_tap_b <= 40 * 1024 ? 1 : 0;
+  if (w_res) *w_res = res;
+  return (res ? taps * w_tap_b + kCStages * a_bytes : kCStages * (a_bytes + w_tap_b)) + (int)sizeof(CBarriers) + 1024;
+}
+
+// layer-level part of conv_tc_launch's scope test (the executor sizes its im2col buffer with it)
+bool conv_tc_eligible(const Layer& L) {
+  const int Cin = L.in_c, Cout = L.out_c, Wo = L.out_w;
+  if (L.kind != DBX_CONV2D || L.sh != 1 || L.sw != 1 || !(Cin == 16 || Cin == 32 || Cin == 64) || Cout > 128 || (Cout & 7) || Wo > 128 || Wo < 1)
+    return false;
+  const int nblk = (Cout + 63) / 64;
+  return conv_tc_smem(L.kh * L.kw, Cin, nblk, nullptr) <= 110 * 1024;
+}
+
 // Direct convolution launch.  in: bf16 NHWC [ns or 1][NB][H][W][Cin]; W16: the sample's HWIO kernel as [kh*kw*Cin][ldw] bf16
 // rows; out: bf16 NHWC [ns][NB][Ho][Wo][Cout].  Returns 1 when the layer is outside the kernel's scope (the caller then
 // uses im2col + dense_tc_kernel).
@@ -656,13 +703,12 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
                    __nv_bfloat16* out, long long o_sstride, cudaStream_t st) {
   if (!g_tc_ok || !get_encode_fn()) return 1;
   const int Cin = L.in_c, Cout = L.out_c, Wo = L.out_w, Ho = L.out_h;
-  if (L.sh != 1 || L.sw != 1 || !(Cin == 16 || Cin == 32 || Cin == 64) || Cout > 128 || (Cout & 7) || Wo > 128 || Wo < 1) return 1;
+  if (!conv_tc_eligible(L)) return 1;
   if ((in_sstride & 7) || (o_sstride & 7) || (ldw & 7) || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return 1;
   const int R = std::min(128 / Wo, Ho);
   const int nblk = (Cout + 63) / 64;
-  const int stage_b = 128 * Cin * 2 + nblk * Cin * 128;
-  const int smem = kCStages * stage_b + (int)sizeof(CBarriers) + 1024;
-  if (smem > 110 * 1024) return 1;
+  int w_res = 0;
+  const int smem = conv_tc_smem(L.kh * L.kw, Cin, nblk, &w_res);
   CUtensorMap tmA, tmW;
   {
     uint64_t d[5] = {(uint64_t)Cin, (uint64_t)L.in_w, (uint64_t)L.in_h, (uint64_t)NB, (uint64_t)(in_shared ? 1 : ns)};
@@ -679,7 +725,7 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
   }
   ConvParams p = {};
   p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.kh = L.kh; p.kw = L.kw; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
-  p.R = R; p.tiles_per_img = (int)cdiv(Ho, R); p.ns = ns; p.a_shared = in_shared; p.act = act;
+  p.R = R; p.tiles_per_img = (int)cdiv(Ho, R); p.ns = ns; p.a_shared = in_shared; p.act = act; p.w_res = w_res;
   p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.out = out; p.o_sstride = o_sstride;
   static int num_sms = 0;
   if (!num_sms) {
