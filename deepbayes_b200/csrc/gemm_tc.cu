@@ -367,7 +367,10 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // Before: the conv input was expanded to an im2col matrix in HBM (115 MB per sample for config 4's second conv) and
 // read back by the GEMM.
 // =======================================================================================
-constexpr int kCStages = 6;
+#ifndef DBX_CSTAGES
+#define DBX_CSTAGES 6
+#endif
+constexpr int kCStages = DBX_CSTAGES;
 constexpr int kCThreads = 192;
 
 struct ConvParams {
@@ -403,6 +406,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = (long long)p.ns * p.NB * p.tiles_per_img;
   const int NT = nblk * 64;
+  // a CONTIGUOUS range of the (sample, image, row group) list per CTA: it changes sample (= reloads the resident kernel
+  // tensor, draining its pipeline) once or twice per launch, and walks down its images row group by row group, so the
+  // input rows its nine taps share stay in L2
+  const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
 
   if (tid == 0) {
     for (int i = 0; i < kCStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
@@ -427,7 +434,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t g = 0;
     const uint32_t tx = (uint32_t)(p.R * p.Wo * cin_b + (p.w_res ? 0 : w_tap_b));
     int cur_s = -1;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    for (long long t = t_begin; t < t_end; ++t) {
       int ho0, nb, s;
       decode(t, ho0, nb, s);
       if (p.w_res && s != cur_s) {
@@ -466,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ksteps = p.Cin / 16;
     uint32_t g = 0, it = 0, w_n = 0;
     int cur_s = -1;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
       const uint32_t ab = it & 1;
       if (p.w_res) {
         int ho0, nb, s;
@@ -497,7 +504,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
     const int r = row / p.Wo, wo = row - r * p.Wo;
     uint32_t it = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
       int ho0, nb, s;
       decode(t, ho0, nb, s);
       const uint32_t ab = it & 1;
