@@ -35,10 +35,20 @@ struct __align__(8) GBarriers {
 
 extern __shared__ __align__(1024) uint8_t gemm_smem_raw[];
 
+// The epilogues apply the activation to 32-128 values per thread and tile; with the activation as a run-time switch that
+// was a branch per element (the conv kernel's hottest instructions).  kAct: 1 = relu, 0 = linear, -1 = look at `act`.
+template <int kAct>
+__device__ __forceinline__ float act_fixed(int act, float z) {
+  if (kAct == 1) return fmaxf(z, 0.f);
+  if (kAct == 0) return z;
+  return apply_act(act, z);
+}
+static inline int act_class(int act) { return act == DBX_ACT_RELU ? 1 : ((act == DBX_ACT_LINEAR || act == DBX_ACT_SOFTMAX) ? 0 : -1); }
+
 // kNTMax = widest column tile of the launch (64 / 128 / 256): it fixes the stage size (A block 16 KB + kNTMax/64 weight
 // blocks of 8 KB) and the TMEM allocation, so narrow layers (conv kernels with 32 / 64 output channels) run 3-4 CTAs
 // per SM instead of one -- their tiles have 1-5 k-blocks, and a lone CTA per SM spent most of its life in the prologue.
-template <int kNTMax>
+template <int kNTMax, int kAct>
 __global__ void __launch_bounds__(kGThreads, kNTMax == 256 ? 1 : (kNTMax == 128 ? 2 : 3))
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   constexpr int kStageB = 16384 + (kNTMax / 64) * 8192;
@@ -120,12 +130,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               uint32_t w[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + bias[c + 2 * i]),
-                                   apply_act(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                   act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
               *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
               for (int i = 0; i < 8; ++i)
-                if (c + i < p.N) dst[q4 * 8 + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q4 * 8 + i]) + bias[c + i]));
+                if (c + i < p.N) dst[q4 * 8 + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + i]) + bias[c + i]));
             }
           }
         } else {
@@ -133,7 +143,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int c = n0 + c0 + i;
-            if (c < p.N) dst[c] = apply_act(p.act, __uint_as_float(v[i]) + bias[c]);
+            if (c < p.N) dst[c] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + bias[c]);
           }
         }
       }
@@ -181,6 +191,7 @@ struct FGemmParams {
 // PERSISTENT: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened (sample, m tile, n tile)
 // list (n fastest: CTAs running side by side read neighbouring 256-byte segments of the same slab rows), and all three
 // rings run across tile boundaries, so the HBM stream never drains between tiles.
+template <int kAct>
 __global__ void __launch_bounds__(kFThreads, 2)
 dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const FGemmParams fp) {
   const GemmParams& p = fp.g;
@@ -332,12 +343,12 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               uint32_t w[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
-                                   apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                   act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
               *reinterpret_cast<uint4*>(dst + q8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
               for (int i = 0; i < 8; ++i)
-                if (c + i < p.N) dst[q8 * 8 + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
+                if (c + i < p.N) dst[q8 * 8 + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
             }
           }
         } else {
@@ -345,7 +356,7 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int i = 0; i < kFNT; ++i) {
             const int c = n0 + i;
-            if (c < p.N) dst[c] = apply_act(p.act, __uint_as_float(v[i]) + bias[c]);
+            if (c < p.N) dst[c] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + bias[c]);
           }
         }
       }
@@ -375,6 +386,8 @@ constexpr int kCThreads = 192;
 
 struct ConvParams {
   int NB, Ho, Wo, Cin, Cout, kh, kw, pad_t, pad_l, R, tiles_per_img, ns, a_shared, act;
+  int patch;   // one input patch [R+kh-1][Wo+kw-1][Cin] per tile serves all taps (see conv_tc_kernel); implies w_res
+  int PW, base_off;
   int w_res;   // the whole kernel tensor of a sample stays in shared memory while the CTA works on that sample
   const float* bias; long long b_sstride, b_off;
   __nv_bfloat16* out; long long o_sstride;
@@ -387,12 +400,15 @@ struct __align__(8) CBarriers {
   uint32_t tmem_slot;
 };
 
+template <int kAct>
 __global__ void __launch_bounds__(kCThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  __shared__ float s_bias[128];                       // the current sample's bias (epilogue warps refill it per sample)
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
   const int cin_b = p.Cin * 2;                        // bytes per A row = swizzle span (32 / 64 / 128)
-  const int a_bytes = 128 * cin_b;                    // A slot (R*Wo <= 128 rows are written)
+  // patch mode: the slot holds (kh-1)*PW + kw-1 + 128 pixel rows (the last ones are only read for garbage accumulator rows)
+  const int a_bytes = p.patch ? (((p.kh - 1) * p.PW + p.kw - 1 + 128) * cin_b + 1023) / 1024 * 1024 : 128 * cin_b;
   const int nblk = (p.Cout + 63) / 64;                // 64-column weight blocks, each Cin rows of 128 B
   const int w_tap_b = nblk * p.Cin * 128;             // one tap's weight rows
   const int taps = p.kh * p.kw;
@@ -449,6 +465,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         cur_s = s;
       }
+      if (p.patch) {
+        // ONE box per tile: input rows ho0-pad_t .. +R+kh-2, columns -pad_l .. +PW-1 (zeros outside the image); the taps
+        // are address offsets into it.  (Per-tap boxes cost 9 x 112 TMA rows of 64 B per tile, and the TMA row rate, not
+        // bandwidth or latency, bounded the kernel.)
+        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          mbar_expect_tx(fb, (uint32_t)((p.R + p.kh - 1) * p.PW * cin_b));
+          tma_load_5d(s_ring + st * stage_b, &tmA, fb, 0, -p.pad_l, ho0 - p.pad_t, nb, p.a_shared ? 0 : s);
+        }
+        __syncwarp();
+        ++g;
+        continue;
+      }
       for (int tap = 0; tap < taps; ++tap, ++g) {
         const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
@@ -482,6 +513,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
       fence_after_sync();
+      if (p.patch) {
+        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        mbar_wait(smem_u32(&bars->full[st]), ph);
+        if (elect_one()) {
+          const uint32_t base = (s_ring + st * stage_b) & 0x3FFFF;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int i = tap / p.kw, j = tap - i * p.kw;
+            const uint32_t addr = base + (uint32_t)((i * p.PW + j) * cin_b);     // the patch shifted by (i, j) pixels
+            // the swizzle XOR is a function of the absolute shared-memory address (what TMA wrote with), so a start address
+            // shifted by whole pixel rows needs NO base-offset field -- measured: setting it gives wrong results
+            const uint32_t hi = a_hi | (p.base_off ? (((addr >> 7) & 7u) << 17) : 0u);
+            const uint32_t a_lo = (addr >> 4) | (1u << 16);
+            const uint32_t b_lo = (((s_wres + tap * w_tap_b) & 0x3FFFF) >> 4) | ((uint32_t)((p.Cin * 128) >> 4) << 16);
+            for (int kk = 0; kk < ksteps; ++kk)
+              mma_ss_lh(tmem + ab * 128, a_lo + kk * 2, hi, b_lo + kk * 128, b_hi, idesc, (tap | kk) > 0);
+          }
+          mma_commit(smem_u32(&bars->empty[st]));
+          mma_commit(smem_u32(&bars->acc_full[ab]));
+        }
+        __syncwarp();
+        ++g;
+        continue;
+      }
       for (int tap = 0; tap < taps; ++tap, ++g) {
         const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
         mbar_wait(smem_u32(&bars->full[st]), ph);
@@ -502,14 +556,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int gq = warp & 3;
     const int row = gq * 32 + lane;                  // accumulator row = output pixel r * Wo + wo of the tile
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
-    const int r = row / p.Wo, wo = row - r * p.Wo;
+    const int rw = p.patch ? p.PW : p.Wo;          // accumulator rows per output row (patch mode keeps kw-1 garbage columns)
+    const int r = row / rw, wo = row - r * rw;
     uint32_t it = 0;
+    int cur_s = -1;
+    const float* bias = s_bias;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       int ho0, nb, s;
       decode(t, ho0, nb, s);
       const uint32_t ab = it & 1;
-      const float* bias = p.bias + (long long)s * p.b_sstride + p.b_off;
-      const bool valid = r < p.R && ho0 + r < p.Ho;
+      if (s != cur_s) {      // per-column global loads in the epilogue were its longest stall (ncu: long scoreboard)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int te = tid - 64;
+        if (te < p.Cout) s_bias[te] = p.bias[(long long)s * p.b_sstride + p.b_off + te];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_s = s;
+      }
+      const bool valid = r < p.R && wo < p.Wo && ho0 + r < p.Ho;
       __nv_bfloat16* dst = p.out + (long long)s * p.o_sstride + ((((long long)nb * p.Ho + ho0 + r) * p.Wo + wo) * p.Cout);
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
@@ -530,12 +593,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t w[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
-                                   apply_act(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                   act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
               *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
               for (int i = 0; i < 8; ++i)
-                if (c + i < p.Cout) dst[c + i] = __float2bfloat16_rn(apply_act(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
+                if (c + i < p.Cout) dst[c + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
             }
           }
         }
@@ -631,9 +694,12 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
     return 0;
   };
   int rc;
-  if (p.NT <= 64) rc = go(dense_tc_kernel<64>, 64);
-  else if (p.NT <= 128) rc = go(dense_tc_kernel<128>, 128);
-  else rc = go(dense_tc_kernel<256>, 256);
+  const int ka = act_class(act);
+#define DBX_GO(NTM) (ka == 1 ? go(dense_tc_kernel<NTM, 1>, NTM) : ka == 0 ? go(dense_tc_kernel<NTM, 0>, NTM) : go(dense_tc_kernel<NTM, -1>, NTM))
+  if (p.NT <= 64) rc = DBX_GO(64);
+  else if (p.NT <= 128) rc = DBX_GO(128);
+  else rc = DBX_GO(256);
+#undef DBX_GO
   if (rc) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -670,26 +736,38 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
   fp.w_rows = w_rows; fp.w_row0 = w_row0;
   fp.ns = ns; fp.tiles_n = (int)cdiv(N, kFNT); fp.tiles_m = (int)cdiv(M, 128);
   const int smem = kFLand * kFLandBytes + kFOp * kFOpBytes + (int)sizeof(FBarriers) + 1024;
-  static bool attr_done = false;
   static int num_sms = 0;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(dense_tc_f32w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  if (!num_sms) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
-    attr_done = true;
   }
   const long long total = (long long)ns * fp.tiles_m * fp.tiles_n;
   dim3 grid((unsigned)std::min<long long>(total, 2LL * num_sms));   // two resident CTAs per SM
-  dense_tc_f32w_kernel<<<grid, kFThreads, smem, st>>>(tmA, tmW, fp);
+  auto go = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+    kern<<<grid, kFThreads, smem, st>>>(tmA, tmW, fp);
+    return 0;
+  };
+  const int ka = act_class(act);
+  if (ka == 1 ? go(dense_tc_f32w_kernel<1>) : ka == 0 ? go(dense_tc_f32w_kernel<0>) : go(dense_tc_f32w_kernel<-1>)) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// dynamic shared memory of conv_tc_kernel; the kernel tensor stays resident when it is at most 40 KB
-static int conv_tc_smem(int taps, int Cin, int nblk, int* w_res) {
-  const int w_tap_b = nblk * Cin * 128, a_bytes = 128 * Cin * 2;
+// dynamic shared memory of conv_tc_kernel.  The kernel tensor stays resident when it is at most 40 KB; then, if
+// R = 128 / (Wo + kw - 1) >= 1 output rows fit the 128 accumulator rows, one input patch per tile serves all taps.
+static int conv_tc_smem(const Layer& L, int* w_res, int* patch, int* R_out) {
+  const int Cin = L.in_c, taps = L.kh * L.kw, nblk = (L.out_c + 63) / 64;
+  const int w_tap_b = nblk * Cin * 128;
   const int res = taps * w_tap_b <= 40 * 1024 ? 1 : 0;
+  const int PW = L.out_w + L.kw - 1;
+  int pm = (res && PW <= 128) ? 1 : 0;
+  if (const char* e = getenv("DBX_CONV_PATCH")) pm = pm && atoi(e) != 0;
+  const int R = std::min(pm ? 128 / PW : 128 / L.out_w, L.out_h);
+  const int a_bytes = pm ? (((L.kh - 1) * PW + L.kw - 1 + 128) * Cin * 2 + 1023) / 1024 * 1024 : 128 * Cin * 2;
   if (w_res) *w_res = res;
+  if (patch) *patch = pm;
+  if (R_out) *R_out = R;
   return (res ? taps * w_tap_b + kCStages * a_bytes : kCStages * (a_bytes + w_tap_b)) + (int)sizeof(CBarriers) + 1024;
 }
 
@@ -698,8 +776,7 @@ bool conv_tc_eligible(const Layer& L) {
   const int Cin = L.in_c, Cout = L.out_c, Wo = L.out_w;
   if (L.kind != DBX_CONV2D || L.sh != 1 || L.sw != 1 || !(Cin == 16 || Cin == 32 || Cin == 64) || Cout > 128 || (Cout & 7) || Wo > 128 || Wo < 1)
     return false;
-  const int nblk = (Cout + 63) / 64;
-  return conv_tc_smem(L.kh * L.kw, Cin, nblk, nullptr) <= 110 * 1024;
+  return conv_tc_smem(L, nullptr, nullptr, nullptr) <= 110 * 1024;
 }
 
 // Direct convolution launch.  in: bf16 NHWC [ns or 1][NB][H][W][Cin]; W16: the sample's HWIO kernel as [kh*kw*Cin][ldw] bf16
@@ -712,16 +789,15 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
   const int Cin = L.in_c, Cout = L.out_c, Wo = L.out_w, Ho = L.out_h;
   if (!conv_tc_eligible(L)) return 1;
   if ((in_sstride & 7) || (o_sstride & 7) || (ldw & 7) || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return 1;
-  const int R = std::min(128 / Wo, Ho);
-  const int nblk = (Cout + 63) / 64;
-  int w_res = 0;
-  const int smem = conv_tc_smem(L.kh * L.kw, Cin, nblk, &w_res);
+  int w_res = 0, patch = 0, R = 1;
+  const int smem = conv_tc_smem(L, &w_res, &patch, &R);
+  const int PW = Wo + L.kw - 1;
   CUtensorMap tmA, tmW;
   {
     uint64_t d[5] = {(uint64_t)Cin, (uint64_t)L.in_w, (uint64_t)L.in_h, (uint64_t)NB, (uint64_t)(in_shared ? 1 : ns)};
     uint64_t sb[4] = {(uint64_t)Cin * 2, (uint64_t)L.in_w * Cin * 2, (uint64_t)L.in_h * L.in_w * Cin * 2,
                       (uint64_t)(in_shared ? (long long)NB * L.in_h * L.in_w * Cin : in_sstride) * 2};
-    uint32_t b[5] = {(uint32_t)Cin, (uint32_t)Wo, (uint32_t)R, 1, 1};
+    uint32_t b[5] = {(uint32_t)Cin, (uint32_t)(patch ? PW : Wo), (uint32_t)(patch ? R + L.kh - 1 : R), 1, 1};
     const CUtensorMapSwizzle swz = Cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (Cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     if (!make_tmap_bf16(&tmA, (void*)in, 5, d, sb, b, swz)) return 1;
   }
@@ -733,16 +809,23 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
   ConvParams p = {};
   p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.kh = L.kh; p.kw = L.kw; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
   p.R = R; p.tiles_per_img = (int)cdiv(Ho, R); p.ns = ns; p.a_shared = in_shared; p.act = act; p.w_res = w_res;
+  p.patch = patch; p.PW = PW; p.base_off = 0;
+  if (const char* e = getenv("DBX_CONV_BASEOFF")) p.base_off = atoi(e);
   p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.out = out; p.o_sstride = o_sstride;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
   }
-  if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
   const long long total = (long long)ns * NB * p.tiles_per_img;
   dim3 grid((unsigned)std::min<long long>(total, 2LL * num_sms));
-  conv_tc_kernel<<<grid, kCThreads, smem, st>>>(tmA, tmW, p);
+  auto go = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+    kern<<<grid, kCThreads, smem, st>>>(tmA, tmW, p);
+    return 0;
+  };
+  const int ka = act_class(act);
+  if (ka == 1 ? go(conv_tc_kernel<1>) : ka == 0 ? go(conv_tc_kernel<0>) : go(conv_tc_kernel<-1>)) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
