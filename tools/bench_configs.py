@@ -86,7 +86,7 @@ def cfg4():
     fl = eng.flops_per_forward * B * n / (ms * 1e-3) / 1e12
     emit(config="4: Bayesian CNN conv32-conv64-pool-dense128-dense10, CIFAR-10 shape, n=256", B=B, ms=ms,
          value=B * n / (ms * 1e-3), unit="forwards/s", path=eng.last_path(), tflops=fl, frac_of_bf16_burst=fl / PEAKS["bf16_tflops"],
-         note="generic bf16 path: Conv2D = im2col + per-sample tcgen05 GEMM (dense_tc_kernel), Dense = dense_tc_kernel; an implicit-GEMM conv would remove the im2col round trip")
+         note="generic bf16 path: first conv (Cin = 3) = im2col of the shared input (once per call) + dense_tc_kernel; second conv = conv_tc_kernel (direct, per-tile input patch by TMA); Dense = dense_tc_kernel")
 
 
 def cfg5():
