@@ -556,6 +556,116 @@ def chernoff_verification(layers, mean, std, x, eps, cls, n, noise, inflate=1.0,
 
 
 
+# ---------------------------------------------------------------------------------------
+# Bayes-by-Backprop training step
+# ---------------------------------------------------------------------------------------
+_LOG_SQRT_2PI = 0.5 * np.log(2.0 * np.pi)
+
+
+def log_q(x, mu, rho, dtype=np.float64):
+    """losses.py:10-16: sum over tensors of the MEAN over elements of Normal(mu_i, softplus(rho_i)).log_prob(x_i)."""
+    total = dtype(0)
+    for xi, mi, ri in zip(x, mu, rho):
+        sg = softplus(np.asarray(ri, dtype), dtype)
+        z = (np.asarray(xi, dtype) - np.asarray(mi, dtype)) / sg
+        total = total + np.mean(-0.5 * z * z - np.log(sg) - dtype(_LOG_SQRT_2PI))
+    return total
+
+
+def sparse_categorical_crossentropy(labels, probs, dtype=np.float64):
+    """tf.keras.losses.SparseCategoricalCrossentropy() on probabilities: mean over the batch of -log(clip(p[label], 1e-7, 1-1e-7))."""
+    p = np.asarray(probs, dtype)
+    pl = p[np.arange(p.shape[0]), np.asarray(labels).reshape(-1)]
+    return -np.mean(np.log(np.clip(pl, dtype(1e-7), dtype(1 - 1e-7))))
+
+
+def kl_loss(layers, labels, x, W, prior_mean, prior_var, q_mean, q_rho, kl_weight=1.0, dtype=np.float64):
+    """losses.KL_Loss (losses.py:40-45): data_likli + kl_weight * (log_q(W; q_mean, q_rho) - log_q(W; prior_mean, prior_var)),
+    and the KL component.  NOTE the prior goes through the same log_q, i.e. its scale is softplus(prior_var)."""
+    pred = forward(layers, [np.asarray(w, dtype) for w in W], np.asarray(x, dtype), dtype=dtype)
+    data = sparse_categorical_crossentropy(labels, pred, dtype)
+    klc = log_q(W, q_mean, q_rho, dtype) - log_q(W, prior_mean, prior_var, dtype)
+    return data + dtype(kl_weight) * klc, klc, pred
+
+
+def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64):
+    """`BayesByBackprop.step` (bayesbybackprop.py:46-170, robust_train == 0) for Dense MLPs with a softmax output and the
+    sparse categorical cross-entropy, gradients written out by hand (the reference gets them from tf.GradientTape):
+      W = mean + softplus(rho) * noise                                                    (:50-59)
+      weight_gradient = dLoss/dW       (data term + kl_weight * d(log_q - log_prior)/dW)  (:138)
+      mean_gradient   = dLoss/dmean = kl_weight * (W - mean) / (sigma^2 n_i)              (:139)
+      var_gradient    = dLoss/drho  = kl_weight * ((W - mean)^2 / sigma^3 - 1 / sigma) * sigmoid(rho) / n_i   (:140)
+      posti_mean_grad = weight_gradient + mean_gradient                                   (:146)
+      posti_var_grad  = noise / (1 + exp(-rho)) * weight_gradient + var_gradient          (:148-150)
+      new = old - lrate * grad                                                            (:156-163)
+    Returns (new_mean, new_rho, loss, kl_component, predictions, W)."""
+    d = dtype
+    mean = [np.asarray(t, d) for t in mean]
+    rho = [np.asarray(t, d) for t in rho]
+    noise = [np.asarray(t, d) for t in noise]
+    pm = [np.asarray(t, d) for t in prior_mean]
+    ps = [softplus(np.asarray(t, d), d) for t in prior_var]
+    sg = [softplus(r, d) for r in rho]
+    W = [m + s * e for m, s, e in zip(mean, sg, noise)]
+    # forward, keeping the layer inputs
+    acts = [np.asarray(x, d)]
+    dense = [l for l in layers if l.kind == "dense"]
+    if len(dense) != len(layers):
+        raise NotImplementedError("oracle bbb_step covers Dense MLPs")
+    h = acts[0]
+    for li, l in enumerate(dense):
+        z = h @ W[2 * li] + W[2 * li + 1]
+        h = _act(l.activation, z)
+        acts.append(h)
+    pred = acts[-1]
+    B = pred.shape[0]
+    lab = np.asarray(labels).reshape(-1)
+    data = sparse_categorical_crossentropy(lab, pred, d)
+    klc = log_q(W, mean, rho, d) - log_q(W, pm, [np.asarray(t, d) for t in prior_var], d)
+    loss = data + d(kl_weight) * klc
+    # backward of the data term: softmax + mean cross-entropy (the clip is inactive away from p = 1e-7)
+    if dense[-1].activation != "softmax":
+        raise NotImplementedError("oracle bbb_step: softmax output")
+    dz = pred.copy()
+    pl = pred[np.arange(B), lab]
+    active = ((pl > 1e-7) & (pl < 1 - 1e-7)).astype(d)
+    onehot = np.zeros_like(pred)
+    onehot[np.arange(B), lab] = 1
+    dz = (pred - onehot) * active[:, None] / d(B)
+    gW = [None] * len(W)
+    for li in range(len(dense) - 1, -1, -1):
+        a_prev = acts[li]
+        gW[2 * li] = a_prev.T @ dz
+        gW[2 * li + 1] = dz.sum(0)
+        if li > 0:
+            da = dz @ W[2 * li].T
+            name = dense[li - 1].activation
+            a = acts[li]
+            if name == "relu":
+                dz = da * (a > 0)
+            elif name == "tanh":
+                dz = da * (1 - a * a)
+            elif name == "sigmoid":
+                dz = da * a * (1 - a)
+            elif name in ("linear", None):
+                dz = da
+            else:
+                raise NotImplementedError(name)
+    new_mean, new_rho = [], []
+    for i in range(len(W)):
+        n_i = d(W[i].size)
+        sig = 1.0 / (1.0 + np.exp(-rho[i]))
+        wg = gW[i] + d(kl_weight) * (-(W[i] - mean[i]) / (sg[i] ** 2) + (W[i] - pm[i]) / (ps[i] ** 2)) / n_i
+        mg = d(kl_weight) * (W[i] - mean[i]) / (sg[i] ** 2) / n_i
+        vg = d(kl_weight) * (((W[i] - mean[i]) ** 2) / sg[i] ** 3 - 1.0 / sg[i]) * sig / n_i
+        g_mean = wg + mg
+        g_rho = noise[i] * sig * wg + vg
+        new_mean.append(mean[i] - d(lrate) * g_mean)
+        new_rho.append(rho[i] - d(lrate) * g_rho)
+    return new_mean, new_rho, loss, klc, pred, W
+
+
+
 def philox4x32_10(ctr, key):
     """Philox4x32-10 (Salmon et al., SC'11) on arrays: ctr [..,4] uint32, key [..,2] uint32."""
     c = [np.asarray(ctr[..., i], np.uint32).copy() for i in range(4)]

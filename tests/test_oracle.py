@@ -274,3 +274,62 @@ def test_ibp_interval_properties(oracle):
     wc = oracle.worst_case_logits(lo1, hi1, [0, 1, 2, 3, 4])
     for r in range(5):
         assert wc[r, r] == lo1[r, r] and (np.delete(wc[r], r) == np.delete(hi1[r], r)).all()
+
+
+def test_oracle_matches_reference_kl_loss_run(oracle, golden_dir):
+    """oracle.log_q / kl_loss against the reference's own losses.py (log_q, KL_Loss) executed on the stand-in
+    (tests/golden/make_reference_bbb_fixtures.py): same inputs, regenerated from seeds."""
+    ref = np.load(os.path.join(golden_dir, "reference_bbb.npz"))
+    L = oracle.mlp([20, 16, 12, 5])
+    mean, std = oracle.synthetic_posterior(L, seed=3, sigma_scale=2.0)
+    rho = [oracle.inverse_softplus(s) for s in std]
+    pm, pv = oracle.implicit_prior(L, 2.0)
+    noise = oracle.synthetic_eps(L, 1, seed=4)[0]
+    W = oracle.sample_gaussian(mean, std, noise, order="f32")
+    x = oracle.synthetic_x((9, 20), seed=5)
+    labels = ref["labels"]
+    np.testing.assert_allclose(oracle.log_q(W, mean, rho), ref["logq_post"], rtol=2e-6)
+    np.testing.assert_allclose(oracle.log_q(W, pm, pv), ref["logq_prior"], rtol=2e-6)
+    for kw in (1.0, 0.25):
+        loss, klc, pred = oracle.kl_loss(L, labels, x, W, pm, pv, mean, rho, kw)
+        np.testing.assert_allclose(loss, ref["loss_kw%g" % kw], rtol=3e-6)
+        np.testing.assert_allclose(klc, ref["klc_kw%g" % kw], rtol=3e-6)
+    np.testing.assert_allclose(pred, ref["pred"], rtol=2e-5, atol=1e-7)
+
+
+def test_bbb_step_gradients_by_finite_differences(oracle):
+    """The hand-written gradients of oracle.bbb_step against central differences of the (reference-pinned) loss:
+    weight_gradient = dLoss/dW, mean_gradient = dLoss/dmean and var_gradient = dLoss/drho at fixed W -- the three
+    tape.gradient calls of bayesbybackprop.py:138-140 -- combined as in :146-163."""
+    L = oracle.mlp([12, 9, 7, 5])
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    rho = [oracle.inverse_softplus(s, np.float64) for s in std]
+    pm, pv = oracle.implicit_prior(L, 2.0)
+    x = oracle.synthetic_x((6, 12), seed=0)
+    lab = np.array([0, 1, 2, 3, 4, 0])
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr, kw = 0.1, 0.7
+    nm, nr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho, pm, pv, x, lab, noise, lr, kl_weight=kw)
+    mean64 = [np.asarray(m, np.float64) for m in mean]
+
+    def f(W_, m_, r_):
+        return oracle.kl_loss(L, lab, x, W_, pm, pv, m_, r_, kw)[0]
+    assert abs(f(W, mean64, rho) - loss) < 1e-12
+    g = np.random.Generator(np.random.Philox(0))
+    h = 1e-6
+    for i in range(len(W)):
+        for _ in range(3):
+            idx = tuple(g.integers(0, d) for d in W[i].shape)
+
+            def bump(lst, sign):
+                out = [np.array(t, np.float64) for t in lst]
+                out[i][idx] += sign * h
+                return out
+            wg = (f(bump(W, 1), mean64, rho) - f(bump(W, -1), mean64, rho)) / (2 * h)
+            mg = (f(W, bump(mean64, 1), rho) - f(W, bump(mean64, -1), rho)) / (2 * h)
+            vg = (f(W, mean64, bump(rho, 1)) - f(W, mean64, bump(rho, -1))) / (2 * h)
+            sig = 1.0 / (1.0 + np.exp(-rho[i][idx]))
+            g_mean = (mean64[i][idx] - nm[i][idx]) / lr
+            g_rho = (rho[i][idx] - nr[i][idx]) / lr
+            np.testing.assert_allclose(g_mean, wg + mg, rtol=2e-5, atol=2e-8)
+            np.testing.assert_allclose(g_rho, noise[i][idx] * sig * wg + vg, rtol=2e-5, atol=2e-8)
