@@ -807,6 +807,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
 
 }  // namespace dbx
 #include "ibp.cuh"
+#include "train.cuh"
 namespace dbx {
 
 static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink, int mode,
@@ -1095,6 +1096,20 @@ int dbx_bbb_forward(dbx_handle h, const float* x_dev, int64_t B, uint64_t seed, 
   Source src; src.eps = eps_dev; src.inflate = 1.f; src.seed = seed; src.s0 = step; src.unfused = true;
   Sink sink; sink.kind = 0; sink.out_kind = DBX_OUT_PROBS; sink.sum1 = out_dev;
   return run(h, x_dev, B, 1, src, sink, mode, st);
+}
+
+int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                 const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                 float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
+  DBX_CHECK(h && x_dev && labels_dev && mean_dev && rho_dev && prior_mean_dev && prior_var_dev, "null argument");
+  DBX_CHECK(B > 0, "B must be positive");
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (run_bbb_step(h, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
+                   loss_out_dev, probs_out_dev, st))
+    return 1;
+  if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));   // W is the first workspace block
+  return 0;
 }
 
 int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32_t* labels_dev, int64_t n, uint64_t seed,

@@ -235,6 +235,27 @@ class Engine:
                                                 _lib.MODE[mode], 0, _ptr(flags), _ptr(counts), _stream()))
         return (counts, flags) if return_flags else counts
 
+    def bbb_step(self, x, labels, mean_t, rho_t, prior_mean_t, prior_var_t, lrate, kl_weight=1.0, seed=0, step=0, noise=None,
+                 want_probs=True, want_weights=False):
+        """One Bayes-by-Backprop step (bayesbybackprop.py:46-170) updating the flat device tensors ``mean_t`` / ``rho_t`` in
+        place.  Returns dict(loss=[loss, kl] device tensor, probs=[B,C] | None, W=[P] | None)."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1)).to(self.device)
+        if lab.numel() != B:
+            raise ValueError("need one label per input row (%d rows, %d labels)" % (B, lab.numel()))
+        for t in (mean_t, rho_t, prior_mean_t, prior_var_t):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.numel() == self.P and t.is_contiguous()):
+                raise ValueError("parameter vectors must be contiguous fp32 CUDA tensors with %d elements" % self.P)
+        loss = torch.empty(2, dtype=torch.float32, device=self.device)
+        probs = torch.empty((B, self.C), dtype=torch.float32, device=self.device) if want_probs else None
+        W = torch.empty(self.P, dtype=torch.float32, device=self.device) if want_weights else None
+        e = None if noise is None else self._dev_f32(noise).reshape(-1)
+        _lib.check(self.lib.dbx_bbb_step(self.h, _ptr(xt), B, _ptr(lab), _ptr(mean_t), _ptr(rho_t), _ptr(prior_mean_t), _ptr(prior_var_t),
+                                         _ptr(e), seed, step, float(lrate), float(kl_weight), _ptr(loss), _ptr(probs), _ptr(W), _stream()))
+        return {"loss": loss, "probs": probs, "W": W}
+
     def ibp_predict(self, x, eps, labels=None, n=1, seed=0, s0=0, noise=None, inflate=1.0, mode="bf16", clip=True,
                     stored=False, j0=0, want=("worst",), return_flags=False):
         """Interval bound propagation over n posterior samples (verifiers.py:23-41, 68-95, 537-557, 588-634).

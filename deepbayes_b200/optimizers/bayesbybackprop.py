@@ -1,7 +1,7 @@
 """BayesByBackprop -- hot-path part of deepbayes/optimizers/bayesbybackprop.py:
 ``compile`` (:31-44, rho = log(exp(std)-1)), the sampling + forward half of ``step``
 (:46-65, W = mu + softplus(rho)*eps then model(features)), ``sample`` (:176-181) and ``save``
-(:184-195).  The backward / SGD update (:138-170) is the next row.
+(:184-195), and the full training step (:46-170, robust_train == 0) as one device call (`dbx_bbb_step`).
 """
 from __future__ import annotations
 
@@ -48,13 +48,95 @@ class BayesByBackprop(optimizer.Optimizer):
         out = eng.bbb_forward(features, self.seed, step, e, self.compute_mode, False)
         return out.cpu().numpy().reshape(oshape)
 
-    def step(self, features, labels, lrate):
-        raise NotImplementedError(
-            "BayesByBackprop.step: only the sampling + forward half (forward_sample) is built; the "
-            "reparameterised backward and SGD update (bayesbybackprop.py:138-170) are SURVEY.md 8(f) rank 2")
+    # ------------------------------------------------------------------ training
+    def _flat_dev(self, tensors):
+        eng = self.engine()
+        return eng._dev_f32(np.concatenate([np.asarray(t, np.float32).ravel() for t in tensors])).contiguous()
+
+    def _unflat(self, flat):
+        out, o = [], 0
+        for shp in self.model.weight_shapes():
+            k = int(np.prod(shp))
+            out.append(flat[o:o + k].reshape(shp))
+            o += k
+        return out
+
+    def step(self, features, labels, lrate, noise=None, sync=True):
+        """bayesbybackprop.py:46-170 (robust_train == 0) in ONE device call (`dbx_bbb_step`): draw noise, W = mean +
+        softplus(rho) * noise, forward, KL loss (losses.py:40-45) with the sparse categorical cross-entropy as the data
+        term, the reference's three gradients and its SGD update.  ``noise`` (list / flat vector) injects the N(0,1) draw.
+        The parameters live on the device between steps; with sync=True (default) the updated lists are copied back,
+        set on the object and returned like the reference does (:169-170), and the sampled weights are left in the model
+        (:59).  Other data losses / robust_train modes raise NotImplementedError."""
+        if getattr(self, "robust_train", 0) != 0:
+            raise NotImplementedError("robust_train != 0 (bayesbybackprop.py:73-136) needs the IBP / FGSM backward (SURVEY.md 8(f))")
+        name = getattr(self.loss_func, "__name__", type(self.loss_func).__name__).lower() if self.loss_func is not None else "sparse_categorical_crossentropy"
+        if "sparse" not in name or "crossentropy" not in name:
+            raise NotImplementedError("the device step builds the sparse categorical cross-entropy data term only (got %r)" % name)
+        eng = self.engine()
+        key = (id(self.posterior_mean), id(self.posterior_var))
+        if getattr(self, "_train_key", None) != key:      # (re)upload after compile / load / external assignment
+            self._d_mean = self._flat_dev(self.posterior_mean).clone()
+            self._d_rho = self._flat_dev(self.posterior_var).clone()
+            self._d_pm = self._flat_dev(self.prior_mean).clone()
+            self._d_pv = self._flat_dev(self.prior_var).clone()
+        e = None if noise is None else eng._as_flat(noise)
+        res = eng.bbb_step(features, labels, self._d_mean, self._d_rho, self._d_pm, self._d_pv, lrate, self.kl_weight, self.seed,
+                           self._take_ids(1), e, want_probs=True, want_weights=sync)
+        self._last_loss, self._last_probs = res["loss"], res["probs"]
+        if sync:
+            self.posterior_mean = self._unflat(self._d_mean.cpu().numpy())
+            self.posterior_var = self._unflat(self._d_rho.cpu().numpy())
+            self.model.set_weights(self._unflat(res["W"].cpu().numpy()))
+        else:
+            self._dirty = True
+        self._train_key = (id(self.posterior_mean), id(self.posterior_var))
+        return self.posterior_mean, self.posterior_var
+
+    def sync_from_device(self):
+        """Copy the device-resident parameters back into posterior_mean / posterior_var (after steps with sync=False)."""
+        if getattr(self, "_dirty", False):
+            self.posterior_mean = self._unflat(self._d_mean.cpu().numpy())
+            self.posterior_var = self._unflat(self._d_rho.cpu().numpy())
+            self._train_key = (id(self.posterior_mean), id(self.posterior_var))
+            self._dirty = False
 
     def train(self, X_train, y_train, X_test=None, y_test=None, **kwargs):
-        return super().train(X_train, y_train, X_test, y_test, **kwargs)
+        """optimizer.py:100-133: epochs x mini-batches of `step`, learning rate lr / (1 + decay * epoch), Gaussian input
+        noise (input_noise), per-epoch logging of the running loss / accuracy and of the validation pass with the weights
+        the last step left in the model (model_validate, :139-141).  The reference's `shuffle(100)` windowed shuffle is
+        replaced by a seeded permutation per epoch."""
+        X_train = np.asarray(X_train, np.float32)
+        y_train = np.asarray(y_train).reshape(-1)
+        self.N = len(X_train)
+        rng = np.random.Generator(np.random.Philox(self.seed))
+        bs = int(self.batch_size)
+        self.loss_log, self.acc_log, self.val_log = [], [], []
+        for epoch in range(self.epochs):
+            lrate = self.learning_rate * (1 / (1 + self.decay * epoch))
+            perm = rng.permutation(self.N)
+            losses, correct, seen = [], 0, 0
+            starts = list(range(0, self.N, bs))
+            for b0 in starts:
+                idx = perm[b0:b0 + bs]
+                feats = X_train[idx]
+                if getattr(self, "input_noise", 0.0):
+                    feats = feats + rng.normal(0.0, self.input_noise, size=feats.shape).astype(np.float32)
+                self.step(feats, y_train[idx], lrate, sync=(b0 == starts[-1]))   # the epoch's last step leaves its W in the model
+                losses.append(self._last_loss)
+                correct += int((self._last_probs.argmax(1).cpu().numpy() == y_train[idx]).sum())
+                seen += len(idx)
+            loss = float(np.mean([float(l[0]) for l in losses]))
+            acc = correct / max(seen, 1)
+            val_loss = val_acc = float("nan")
+            if X_test is not None and y_test is not None:
+                pv = np.asarray(self.model(np.asarray(X_test, np.float32))).reshape(len(X_test), -1)   # model_validate, :139-141
+                yt = np.asarray(y_test).reshape(-1)
+                val_acc = float((pv.argmax(1) == yt).mean())
+                val_loss = float(-np.mean(np.log(np.clip(pv[np.arange(len(yt)), yt], 1e-7, 1 - 1e-7))))
+            self.loss_log.append(loss); self.acc_log.append(acc); self.val_log.append((val_loss, val_acc))
+            print("Epoch {}, loss: {:.3f}, acc: {:.3f}, val_loss: {:.3f}, val_acc: {:.3f}".format(epoch + 1, loss, acc, val_loss, val_acc))
+        return self
 
     def sample(self):
         """bayesbybackprop.py:176-181: N(mean, scale=softplus(rho)) -- the device holds

@@ -130,6 +130,19 @@ int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32
                         uint64_t seed, int64_t s0, const float* eps_dev, float inflate, int32_t mode,
                         int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream);
 
+/* One Bayes-by-Backprop training step on a mini-batch (deepbayes/optimizers/bayesbybackprop.py:46-170 with
+ * robust_train == 0, losses.py:10-45): noise ~ N(0,1) (Philox keyed by (seed, step), or noise_dev [P]),
+ * W = mean + softplus(rho) * noise, forward, loss = sparse categorical cross-entropy (batch mean, Keras' clip of p to
+ * [1e-7, 1-1e-7]) + kl_weight * (log_q(W; mean, rho) - log_q(W; prior_mean, prior_var)), the three gradients the
+ * reference takes from tf.GradientTape, and the in-place update mean -= lrate * (gW + gmean),
+ * rho -= lrate * (noise * sigmoid(rho) * gW + grho).  All parameter vectors are flat fp32 [P] in Keras order, on the
+ * device, owned by the caller.  Optional outputs: loss_out_dev[2] = (loss, kl component), probs_out_dev [B,C] = the
+ * predictions of this step, W_out_dev [P] = the sampled weights (the reference leaves them in the model, :59).
+ * Dense MLPs with a softmax output; fp32 arithmetic. */
+int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                 const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                 float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
+
 /* Interval bound propagation over posterior samples (deepbayes/analyzers/verifiers.py: propagate_interval :23-41,
  * IBP :68-95, and its per-sample use in chernoff_bound_verification :537-557 / massart_bound_check :588-634).
  * For each of the n samples (Gaussian: global ids s0.., optional injected noise [n,P]; stored != 0: slab rows j0..)

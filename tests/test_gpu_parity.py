@@ -689,3 +689,59 @@ def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
 def _lib_launches():
     from deepbayes_b200 import _lib
     return _lib.launch_count()
+
+
+# ---------------------------------------------------------------------------------------
+# Bayes-by-Backprop training step
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims,B", [([12, 9, 7, 5], 6), ([784, 128, 10], 64), ([100, 72, 40, 10], 37)])
+def test_bbb_step_matches_oracle(oracle, dims, B):
+    """dbx_bbb_step with injected noise against oracle.bbb_step (hand-written gradients, checked by finite differences
+    of the loss that is pinned on a run of the reference's losses.py): updated mean / rho, loss, KL component,
+    predictions, sampled weights."""
+    import deepbayes_b200 as db
+    L = oracle.mlp(dims)
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.7)
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    opt.posterior_mean = [m.copy() for m in mean]
+    opt.posterior_var = [oracle.inverse_softplus(s) for s in std]
+    rho0 = [r.copy() for r in opt.posterior_var]
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    lab = np.random.Generator(np.random.Philox(3)).integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr = 0.1
+    nm, nr = opt.step(x, lab, lr, noise=noise)
+    wm, wr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.7)
+    for i in range(len(nm)):
+        # the step sizes are what is being compared: tolerance relative to the size of the update
+        dm, dr = np.abs(wm[i] - mean[i]).max() + 1e-12, np.abs(wr[i] - rho0[i]).max() + 1e-12
+        np.testing.assert_allclose(nm[i], wm[i], rtol=0, atol=2e-4 * dm + 1e-7)
+        np.testing.assert_allclose(nr[i], wr[i], rtol=0, atol=2e-4 * dr + 1e-7)
+        np.testing.assert_allclose(opt.model.get_weights()[i], W[i], rtol=1e-6, atol=1e-7)
+    got = opt._last_loss.cpu().numpy()
+    np.testing.assert_allclose(got[0], loss, rtol=2e-5)
+    np.testing.assert_allclose(got[1], klc, rtol=2e-5)
+    np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, robust_train=1).step(x, lab, lr)
+
+
+def test_bbb_training_learns(oracle):
+    """End to end: a few epochs of BayesByBackprop.train on a separable synthetic problem drive the loss down and the
+    accuracy up, and the trained posterior predicts through the fused / generic inference path."""
+    import deepbayes_b200 as db
+    g = np.random.Generator(np.random.Philox(11))
+    C, D, N = 4, 20, 2048
+    centers = g.standard_normal((C, D)).astype(np.float32) * 2.0
+    y = g.integers(0, C, size=N)
+    X = (centers[y] + g.standard_normal((N, D)).astype(np.float32) * 0.5).astype(np.float32)
+    m = db.Sequential([db.Dense(32, activation="relu", input_shape=(D,)), db.Dense(C, activation="softmax")])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=128, learning_rate=0.3, epochs=5, inflate_prior=1.0, kl_weight=0.1, seed=5)
+    opt.train(X[:1536], y[:1536], X[1536:], y[1536:])
+    assert opt.loss_log[-1] < opt.loss_log[0] and opt.acc_log[-1] > 0.9 and opt.val_log[-1][1] > 0.85
+    pm = np.asarray(opt.engine().predict_sums(X[1536:], 16, seed=1, mode="fp32")[0].cpu().numpy()) / 16
+    assert (pm.argmax(1) == y[1536:]).mean() > 0.85
