@@ -116,10 +116,32 @@ def cfg5():
              path=eng.last_path(), tflops=fl)
 
 
+def cfg_train():
+    """BBB training throughput: MLP 784-512-10 and 784-512-512-10, mini-batch 128, one `dbx_bbb_step` per step
+    with the parameters resident on the device (sync=False)."""
+    import deepbayes_b200 as db
+    for dims in ([784, 512, 10], [784, 512, 512, 10]):
+        layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+        for h in dims[2:-1]:
+            layers.append(db.Dense(h, activation="relu"))
+        layers.append(db.Dense(dims[-1], activation="softmax"))
+        opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=128, inflate_prior=1.0, seed=3)
+        x = torch.from_numpy(o.synthetic_x((128, 784), seed=0)).cuda()
+        y = np.random.Generator(np.random.Philox(3)).integers(0, 10, size=128)
+        opt.step(x, y, 0.01, sync=False)
+
+        def run():
+            for _ in range(50):
+                opt.step(x, y, 0.01, sync=False)
+        ms = timeit(run, warm=1, reps=3) / 50
+        emit(config="train: BayesByBackprop.step, MLP %s, mini-batch 128, fp32" % "-".join(map(str, dims)), B=128, ms=ms,
+             value=1e3 / ms, unit="steps/s", path="dbx_bbb_step", note="reference: 8.4 ms per sample-forward on CPU (SURVEY section 6); one step = sample + forward + backward + update")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--stored", type=int, default=2000)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5}[c]()
+        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5, "train": cfg_train}[c]()
