@@ -1,0 +1,95 @@
+"""First-order attacks over the posterior -- deepbayes/analyzers/attacks.py: ``gradient_expectation`` (:49-75),
+``FGSM`` (:81-102), ``PGD`` / ``_PGD`` (:133-182) -- with the input gradient evaluated on the device
+(`dbx_input_gradient`): all samples of one ``model.predict`` side by side, forward and backward in fp32.
+
+Scope: Dense MLPs with a softmax output and the sparse categorical cross-entropy (the tutorials' attack loss); order=1.
+As in the reference the model may be a PosteriorModel (its predict() is the mean of 35 sampled forwards, so each
+iteration differentiates through 35 samples) or an optimizer object (predict() = one forward with the model's weights).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .verifiers import _engine_of
+
+_PM_PREDICT_N = 35          # PosteriorModel.predict's default n (posteriormodel.py:81)
+
+
+def _check_loss(loss_fn):
+    name = getattr(loss_fn, "__name__", type(loss_fn).__name__).lower() if loss_fn is not None else "sparse_categorical_crossentropy"
+    if "sparse" not in name or "crossentropy" not in name:
+        raise NotImplementedError("the device input gradient builds the sparse categorical cross-entropy only (got %r)" % name)
+
+
+def _labels_of(model, inp, direction):
+    if type(direction) == int and direction == -1:          # attacks.py:86-91 / :139-144: the model's own prediction
+        return np.argmax(np.asarray(model.predict(inp)).reshape(len(inp), -1), axis=1)
+    d = np.asarray(direction).reshape(-1)
+    return np.broadcast_to(d, (len(inp),)) if d.size == 1 else d
+
+
+def gradient_expectation(model, inp, direction, loss_fn=None, num_models=10):
+    """attacks.py:49-75.  Returns the gradient SUM over the iterations, shaped like ``inp``."""
+    _check_loss(loss_fn)
+    eng = _engine_of(model)
+    a = np.asarray(inp, np.float32)
+    x2 = a.reshape(-1, eng.K)
+    labels = np.asarray(direction).reshape(-1)
+    labels = np.broadcast_to(labels, (x2.shape[0],)) if labels.size == 1 else labels
+    val = num_models
+    n_outer = max(int(num_models), 1)
+    is_pm = hasattr(model, "sample_based")                   # PosteriorModel
+    if getattr(model, "det", False) or (not is_pm and val in (1, -1)):
+        # no sampling: the model's current weights (:57-58); a deterministic PosteriorModel predicts with them too
+        w = np.concatenate([np.asarray(t, np.float32).ravel() for t in model.model.get_weights()])
+        g = eng.input_gradient_one(x2, labels, w)
+        n_eff = 1 if (getattr(model, "det", False) or val == -1) else n_outer
+        return (g * float(n_eff)).cpu().numpy().reshape(a.shape) if n_eff > 1 else g.cpu().numpy().reshape(a.shape)
+    if val == -1:
+        n_outer = 1                                          # :73-74
+    n_inner = _PM_PREDICT_N if is_pm else 1
+    s0 = model._take_ids(n_outer * n_inner)
+    if is_pm and model.sample_based:
+        raise NotImplementedError("gradient_expectation over a sample-based posterior draws stored samples with replacement (posteriormodel.py:77); not built")
+    g = eng.input_gradient(x2, labels, n_outer, n_inner, model.seed, s0)
+    return g.cpu().numpy().reshape(a.shape)
+
+
+def FGSM(model, inp, loss_fn=None, eps=0.1, direction=-1, num_models=1, order=1, samples=1):
+    """attacks.py:81-102 (``samples`` overrides ``num_models``, :82)."""
+    if order != 1:
+        raise NotImplementedError("zeroth-order gradients (attacks.py:17-45) are not built")
+    num_models = samples
+    inp = np.asarray(inp)
+    maxi, mini = inp + eps, inp - eps
+    direc = _labels_of(model, inp, direction)
+    grad = np.sign(gradient_expectation(model, inp, direc, loss_fn, num_models))
+    adv = np.clip(inp + eps * grad, mini, maxi)
+    return np.clip(adv, getattr(model, "input_lower", -np.inf), getattr(model, "input_upper", np.inf))
+
+
+def _PGD(model, inp, loss_fn=None, eps=0.1, direc=-1, step=0.1, num_steps=15, num_models=35, order=1):
+    """attacks.py:133-165: random sign start of size eps/10, num_steps+1 sign-gradient steps of eps/num_steps, final clips."""
+    if order != 1:
+        raise NotImplementedError("zeroth-order gradients (attacks.py:17-45) are not built")
+    inp = np.asarray(inp)
+    direc = _labels_of(model, inp, direc)
+    adv = np.asarray(inp, np.float32)
+    maxi, mini = adv + eps, adv - eps
+    adv = adv + ((eps / 10) * np.sign(np.random.normal(0.0, 1.0, size=adv.shape)))
+    lo, hi = getattr(model, "input_lower", -np.inf), getattr(model, "input_upper", np.inf)
+    adv = np.clip(adv, lo, hi)
+    for _ in range(num_steps + 1):
+        grad = np.sign(gradient_expectation(model, adv, direc, loss_fn, num_models))
+        adv = (adv + grad * (eps / float(num_steps))).astype(np.float32)
+    adv = np.clip(adv, mini, maxi)
+    return np.clip(adv, lo, hi)
+
+
+def PGD(model, inp, loss_fn=None, eps=0.1, direction=-1, step=0.1, num_steps=5, num_models=-1, order=1, restarts=0):
+    """attacks.py:167-177: restarts + 1 runs of _PGD; the single result, or the list of all of them when restarts > 0."""
+    advs = []
+    for _ in range(restarts + 1):
+        adv = _PGD(model, inp, loss_fn, eps, direc=direction, step=step, num_steps=num_steps, num_models=num_models, order=order)
+        advs.append(adv)
+    return adv if restarts == 0 else advs

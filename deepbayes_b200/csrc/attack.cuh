@@ -1,0 +1,169 @@
+// Expected input gradient over posterior samples (included by engine.cu).
+//
+// Reference: deepbayes/analyzers/attacks.py gradient_expectation :49-75 -- for each of num_models iterations,
+// d loss_fn(direction, model.predict(inp)) / d inp by tf.GradientTape, summed.  model.predict of a PosteriorModel is
+// itself the mean of n forward passes under fresh weight samples (posteriormodel.py:81-101), of an optimizer a single
+// forward.  Here, for one iteration with n_inner samples s:
+//     pbar = (1/n) sum_s softmax(f_s(x)),   loss = -(1/B) sum_b log clip(pbar_b[y_b])      (sparse categorical CE)
+//     dLoss/dz_s[b, c] = g_b * p_s[b, y_b] * ([c == y_b] - p_s[b, c]),   g_b = -1 / (B n pbar_b[y_b])
+//     dLoss/dx = sum_s backprop_s(dLoss/dz_s)
+// evaluated with the chunk's samples side by side (fp32, CUDA cores, the sample is the grid's z dimension).
+#pragma once
+
+namespace dbx {
+
+// in place: logits[s][b][:] -> p_s[b][:];  pbar[b][:] = mean over s
+__global__ void softmax_mean_kernel(float* __restrict__ z, int ns, int B, int C, float* __restrict__ pbar) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int c = 0; c < C; ++c) pbar[(int64_t)b * C + c] = 0.f;
+  for (int s = 0; s < ns; ++s) {
+    float* row = z + ((int64_t)s * B + b) * C;
+    float m = row[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(row[c] - m);
+    for (int c = 0; c < C; ++c) { const float p = expf(row[c] - m) / den; row[c] = p; pbar[(int64_t)b * C + c] += p; }
+  }
+  for (int c = 0; c < C; ++c) pbar[(int64_t)b * C + c] /= (float)ns;
+}
+
+// dz[s][b][c] from p_s and pbar (see the header); zero where Keras' clip of pbar[y] to [1e-7, 1-1e-7] is active
+__global__ void ce_mean_upstream_kernel(const float* __restrict__ p, const float* __restrict__ pbar, const int32_t* __restrict__ labels,
+                                        int ns, int B, int C, float* __restrict__ dz) {
+  const int64_t total = (int64_t)ns * B;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(o % B);
+    const int y = labels[b];
+    const float pb = pbar[(int64_t)b * C + y];
+    const float g = (pb > 1e-7f && pb < 1.f - 1e-7f) ? -1.f / ((float)B * (float)ns * pb) : 0.f;
+    const float* ps = p + o * C;
+    const float gy = g * ps[y];
+    for (int c = 0; c < C; ++c) dz[o * C + c] = gy * ((c == y ? 1.f : 0.f) - ps[c]);
+  }
+}
+
+// batched over samples (blockIdx.z): dZprev[s][b, k] = (sum_n dZ[s][b, n] * W_s[k, n]) * act'(Aprev[s][b, k]); aprev == nullptr: no act'
+__global__ void __launch_bounds__(256)
+grad_a_batched_kernel(const float* __restrict__ dZ, int64_t dz_ss, const float* __restrict__ Wbase, int64_t w_ss, int64_t w_off,
+                      const int32_t* __restrict__ rows, int64_t row0, const float* __restrict__ Aprev, int64_t a_ss, int B, int K, int N,
+                      int act, float* __restrict__ out, int64_t o_ss) {
+  __shared__ float Zs[32][33];
+  __shared__ float Ws[32][33];
+  const int s = blockIdx.z;
+  const int64_t wrow = rows ? (int64_t)rows[s] : (row0 + s);
+  const float* dZp = dZ + (int64_t)s * dz_ss;
+  const float* W = Wbase + wrow * w_ss + w_off;
+  const int b0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    for (int i = ty; i < 32; i += 8) {
+      Zs[i][tx] = (b0 + i < B && n0 + tx < N) ? dZp[(int64_t)(b0 + i) * N + n0 + tx] : 0.f;
+      Ws[i][tx] = (k0 + i < K && n0 + tx < N) ? W[(int64_t)(k0 + i) * N + n0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < 32; ++n) {
+      const float w = Ws[tx][n];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(Zs[ty + 8 * r][n], w, acc[r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + ty + 8 * r, k = k0 + tx;
+    if (b < B && k < K) {
+      float d = 1.f;
+      if (Aprev) {
+        const float a = Aprev[(int64_t)s * a_ss + (int64_t)b * K + k];
+        switch (act) {
+          case DBX_ACT_RELU: d = a > 0.f ? 1.f : 0.f; break;
+          case DBX_ACT_TANH: d = 1.f - a * a; break;
+          case DBX_ACT_SIGMOID: d = a * (1.f - a); break;
+          default: d = 1.f;
+        }
+      }
+      out[(int64_t)s * o_ss + (int64_t)b * K + k] = acc[r] * d;
+    }
+  }
+}
+
+// grad[e] (+)= sum_s dx[s][e], in sample order
+__global__ void sum_samples_kernel(const float* __restrict__ dx, int ns, int64_t n, int accumulate, float* __restrict__ grad) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float a = accumulate ? grad[e] : 0.f;
+    for (int s = 0; s < ns; ++s) a += dx[(int64_t)s * n + e];
+    grad[e] = a;
+  }
+}
+
+static int run_input_gradient(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, int64_t n_outer, int64_t n_inner,
+                              const Source& src0, float* grad_dev, cudaStream_t st) {
+  DBX_CHECK(m->is_mlp, "the device input gradient covers Dense MLPs (attacks.py:49-75)");
+  DBX_CHECK(m->layers[m->last_weighted].act == DBX_ACT_SOFTMAX, "the device input gradient needs a softmax output (sparse categorical cross-entropy)");
+  std::vector<const Layer*> dl;
+  for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
+  const int nl = (int)dl.size();
+  const int64_t C = m->out_feat, K0 = m->in_feat;
+  const int nc = (int)n_inner;
+  size_t act_total = 0;
+  for (auto* L : dl) act_total += (size_t)B * L->units * 4;      // per-sample blocks are dense: [s][B][units]
+  const size_t dzb = round_up((size_t)B * std::max<int64_t>(m->max_feat, K0) * 4, 256);
+  const size_t wb = src0.stored ? 0 : (size_t)m->P * 4;
+  const size_t per = act_total + 2 * dzb + wb;
+  const size_t need = (size_t)nc * per + round_up((size_t)B * C * 4, 256) + 8192;
+  DBX_CHECK(need <= ws_budget_bytes() * 2, "n_inner = %d samples need %zu MB of workspace", nc, need >> 20);
+  if (ensure_ws(m->ws, need)) return 1;
+  char* p = (char*)m->ws.ptr;
+  std::vector<float*> acts(nl);
+  std::vector<int64_t> act_ss(nl);
+  for (int i = 0; i < nl; ++i) { acts[i] = (float*)p; act_ss[i] = B * dl[i]->units; p += (size_t)nc * act_ss[i] * 4; }
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+  float* dz[2]; const int64_t dz_ss = (int64_t)(dzb / 4);
+  dz[0] = (float*)p; p += (size_t)nc * dzb; dz[1] = (float*)p; p += (size_t)nc * dzb;
+  float* pbar = (float*)p; p += round_up((size_t)B * C * 4, 256);
+  float* Wc = (float*)p;
+
+  for (int64_t it = 0; it < n_outer; ++it) {
+    Source src = src0;
+    src.s0 = src0.s0 + it * n_inner; src.j0 = src0.j0 + (src0.idx ? 0 : it * n_inner);
+    const float* Wbase; int64_t w_ss; const int32_t* rows = nullptr; int64_t row0 = 0;
+    if (src.stored) { Wbase = m->slab; w_ss = m->slab_stride; rows = src.idx ? src.idx + it * n_inner : nullptr; row0 = src.j0; }
+    else {
+      const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
+      DBX_LAUNCH(sample_f32_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma, src.eps ? src.eps + it * n_inner * m->P : nullptr,
+                 src.inflate, src.seed, src.s0, (int64_t)nc, m->P, 0, Wc, (float*)nullptr);
+      Wbase = Wc; w_ss = m->P;      // sample_f32_kernel writes rows m->P apart
+    }
+    // forward, all samples side by side
+    const float* cur = x_dev; int64_t cur_ss = 0;
+    for (int i = 0; i < nl; ++i) {
+      const Layer& L = *dl[i];
+      dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), (unsigned)nc);
+      DBX_LAUNCH((dense_kernel<float, float>), grid, 256, 0, st, cur, cur_ss, Wbase, w_ss, rows, row0, L.w_off, (int)L.w_cols, Wbase, w_ss,
+                 L.b_off, acts[i], act_ss[i], (int)B, L.units, (int)L.in_feat, i == nl - 1 ? DBX_ACT_LINEAR : L.act);
+      cur = acts[i]; cur_ss = act_ss[i];
+    }
+    float* logits = acts[nl - 1];
+    DBX_LAUNCH(softmax_mean_kernel, (int)cdiv(B, 128), 128, 0, st, logits, nc, (int)B, (int)C, pbar);
+    DBX_LAUNCH(ce_mean_upstream_kernel, grid_for((int64_t)nc * B), 256, 0, st, (const float*)logits, (const float*)pbar, labels_dev, nc, (int)B,
+               (int)C, dz[0]);
+    // backward to the input
+    int zi = 0; int64_t zs = B * C;
+    for (int i = nl - 1; i >= 0; --i) {
+      const Layer& L = *dl[i];
+      const int K = (int)L.in_feat, N = L.units;
+      dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32), (unsigned)nc);
+      const float* aprev = i > 0 ? acts[i - 1] : nullptr;
+      DBX_LAUNCH(grad_a_batched_kernel, ga, 256, 0, st, (const float*)dz[zi], zs, Wbase, w_ss, L.w_off, rows, row0, aprev, i > 0 ? act_ss[i - 1] : 0,
+                 (int)B, K, N, i > 0 ? dl[i - 1]->act : DBX_ACT_LINEAR, dz[zi ^ 1], (int64_t)B * K);
+      zi ^= 1; zs = (int64_t)B * K;
+    }
+    DBX_LAUNCH(sum_samples_kernel, grid_for(B * K0), 256, 0, st, (const float*)dz[zi], nc, B * K0, it > 0 ? 1 : 0, grad_dev);
+  }
+  return 0;
+}
+
+}  // namespace dbx

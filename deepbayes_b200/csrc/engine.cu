@@ -808,6 +808,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
 }  // namespace dbx
 #include "ibp.cuh"
 #include "train.cuh"
+#include "attack.cuh"
 namespace dbx {
 
 static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink, int mode,
@@ -1110,6 +1111,27 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
     return 1;
   if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));   // W is the first workspace block
   return 0;
+}
+
+int dbx_input_gradient(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, int64_t n_outer, int64_t n_inner, uint64_t seed,
+                       int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, float* grad_dev, void* stream) {
+  DBX_CHECK(h && x_dev && labels_dev && grad_dev, "null argument");
+  DBX_CHECK(B > 0 && n_outer > 0 && n_inner > 0 && n_inner <= 4096, "B, n_outer, n_inner must be positive (n_inner <= 4096)");
+  Source src; src.stored = stored != 0; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0; src.j0 = j0;
+  DBX_CHECK(src.stored ? (h->slab != nullptr && j0 >= 0 && j0 + n_outer * n_inner <= h->S) : h->have_gaussian,
+            src.stored ? "stored rows out of range / no slab set" : "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  return run_input_gradient(h, x_dev, B, labels_dev, n_outer, n_inner, src, grad_dev, (cudaStream_t)stream);
+}
+
+int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, const float* W_dev, float* grad_dev,
+                           void* stream) {
+  DBX_CHECK(h && W_dev, "null argument");
+  const float* keep = h->slab; const int64_t keepS = h->S, keepStride = h->slab_stride;
+  h->slab = W_dev; h->S = 1; h->slab_stride = h->P;
+  const int rc = dbx_input_gradient(h, x_dev, B, labels_dev, 1, 1, 0, 0, nullptr, 1.f, 1, 0, grad_dev, stream);
+  h->slab = keep; h->S = keepS; h->slab_stride = keepStride;
+  return rc;
 }
 
 int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32_t* labels_dev, int64_t n, uint64_t seed,

@@ -256,6 +256,30 @@ class Engine:
                                          _ptr(e), seed, step, float(lrate), float(kl_weight), _ptr(loss), _ptr(probs), _ptr(W), _stream()))
         return {"loss": loss, "probs": probs, "W": W}
 
+    def input_gradient(self, x, labels, n_outer=1, n_inner=1, seed=0, s0=0, noise=None, inflate=1.0, stored=False, j0=0):
+        """Sum over n_outer iterations of d CE(labels, mean of n_inner sampled predictions) / d x (attacks.py:49-75): [B,K] device tensor."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
+        if lab.numel() != B:
+            raise ValueError("need one label per input row (%d rows, %d labels)" % (B, lab.numel()))
+        g = torch.empty((B, self.K), dtype=torch.float32, device=self.device)
+        e = None if noise is None else self._dev_f32(noise).reshape(n_outer * n_inner, self.P)
+        _lib.check(self.lib.dbx_input_gradient(self.h, _ptr(xt), B, _ptr(lab), n_outer, n_inner, seed, s0, _ptr(e), float(inflate),
+                                               1 if stored else 0, j0, _ptr(g), _stream()))
+        return g
+
+    def input_gradient_one(self, x, labels, weights_flat):
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
+        w = self._dev_f32(weights_flat).reshape(-1)
+        g = torch.empty((B, self.K), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.dbx_input_gradient_one(self.h, _ptr(xt), B, _ptr(lab), _ptr(w), _ptr(g), _stream()))
+        return g
+
     def ibp_predict(self, x, eps, labels=None, n=1, seed=0, s0=0, noise=None, inflate=1.0, mode="bf16", clip=True,
                     stored=False, j0=0, want=("worst",), return_flags=False):
         """Interval bound propagation over n posterior samples (verifiers.py:23-41, 68-95, 537-557, 588-634).

@@ -143,6 +143,17 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
                  const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                  float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
 
+/* Expected input gradient (deepbayes/analyzers/attacks.py gradient_expectation :49-75): the sum over n_outer iterations
+ * of d CE(labels, mean over n_inner posterior samples of softmax(f_W(x))) / d x, CE = batch-mean sparse categorical
+ * cross-entropy.  n_inner = 35 reproduces a PosteriorModel (its predict() averages 35 samples, posteriormodel.py:81),
+ * n_inner = 1 an optimizer object.  Sample ids s0 + it * n_inner + s (stored != 0: slab rows j0 + ...).  grad_dev [B,K]
+ * fp32.  Dense MLPs with a softmax output. */
+int dbx_input_gradient(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, int64_t n_outer, int64_t n_inner, uint64_t seed,
+                       int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, float* grad_dev, void* stream);
+/* same with one explicit flat weight vector (the det / current-weights branch, attacks.py:57-58) */
+int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, const float* W_dev, float* grad_dev,
+                           void* stream);
+
 /* Interval bound propagation over posterior samples (deepbayes/analyzers/verifiers.py: propagate_interval :23-41,
  * IBP :68-95, and its per-sample use in chernoff_bound_verification :537-557 / massart_bound_check :588-634).
  * For each of the n samples (Gaussian: global ids s0.., optional injected noise [n,P]; stored != 0: slab rows j0..)

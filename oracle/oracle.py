@@ -666,6 +666,65 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
 
 
 
+# ---------------------------------------------------------------------------------------
+# Expected input gradient and the attacks built on it
+# ---------------------------------------------------------------------------------------
+def mean_prediction_loss(layers, weight_sets, x, labels, dtype=np.float64):
+    """loss_fn(direction, model.predict(inp)) of attacks.py:64-65 for a PosteriorModel: the sparse categorical
+    cross-entropy of the MEAN over the given weight sets of the model output (posteriormodel.py:94-101)."""
+    pbar = None
+    for w in weight_sets:
+        p = forward(layers, [np.asarray(t, dtype) for t in w], np.asarray(x, dtype), dtype=dtype)
+        pbar = p if pbar is None else pbar + p
+    pbar = pbar / dtype(len(weight_sets))
+    return sparse_categorical_crossentropy(labels, pbar, dtype), pbar
+
+
+def input_gradient(layers, weight_sets, x, labels, dtype=np.float64):
+    """d mean_prediction_loss / d x by hand (the reference uses tf.GradientTape, attacks.py:60-67) for Dense MLPs with
+    a softmax output: with pbar the mean prediction, dz_s[b, c] = g_b p_s[b, y_b] ([c == y_b] - p_s[b, c]),
+    g_b = -1 / (B n pbar_b[y_b]), back-propagated through each sample's layers and summed over samples."""
+    d = dtype
+    x = np.asarray(x, d)
+    lab = np.asarray(labels).reshape(-1)
+    dense = [l for l in layers if l.kind == "dense"]
+    B, n = x.shape[0], len(weight_sets)
+    fw = []
+    for w in weight_sets:
+        W = [np.asarray(t, d) for t in w]
+        acts = [x]
+        h = x
+        for li, l in enumerate(dense):
+            h = _act(l.activation, h @ W[2 * li] + W[2 * li + 1])
+            acts.append(h)
+        fw.append((W, acts))
+    pbar = sum(a[-1] for _, a in fw) / d(n)
+    py = pbar[np.arange(B), lab]
+    g = np.where((py > 1e-7) & (py < 1 - 1e-7), -1.0 / (B * n * py), 0.0)
+    grad = np.zeros_like(x)
+    for W, acts in fw:
+        p = acts[-1]
+        onehot = np.zeros_like(p)
+        onehot[np.arange(B), lab] = 1
+        dz = (g * p[np.arange(B), lab])[:, None] * (onehot - p)
+        for li in range(len(dense) - 1, -1, -1):
+            da = dz @ W[2 * li].T
+            if li == 0:
+                grad += da
+                break
+            a, name = acts[li], dense[li - 1].activation
+            dz = da * ((a > 0) if name == "relu" else (1 - a * a) if name == "tanh" else a * (1 - a) if name == "sigmoid" else 1.0)
+    return grad
+
+
+def fgsm(x, grad, eps, lower=-np.inf, upper=np.inf):
+    """attacks.py:94-101: adv = clip(clip(x + eps * sign(grad), x - eps, x + eps), input_lower, input_upper)."""
+    x = np.asarray(x)
+    adv = np.clip(x + eps * np.sign(grad), x - eps, x + eps)
+    return np.clip(adv, lower, upper)
+
+
+
 def philox4x32_10(ctr, key):
     """Philox4x32-10 (Salmon et al., SC'11) on arrays: ctr [..,4] uint32, key [..,2] uint32."""
     c = [np.asarray(ctr[..., i], np.uint32).copy() for i in range(4)]

@@ -745,3 +745,46 @@ def test_bbb_training_learns(oracle):
     assert opt.loss_log[-1] < opt.loss_log[0] and opt.acc_log[-1] > 0.9 and opt.val_log[-1][1] > 0.85
     pm = np.asarray(opt.engine().predict_sums(X[1536:], 16, seed=1, mode="fp32")[0].cpu().numpy()) / 16
     assert (pm.argmax(1) == y[1536:]).mean() > 0.85
+
+
+@pytest.mark.parametrize("dims,B,n_outer,n_inner", [([10, 8, 6, 4], 3, 2, 5), ([784, 128, 10], 40, 1, 35), ([100, 72, 40, 10], 33, 3, 1)])
+def test_input_gradient_matches_oracle(oracle, dims, B, n_outer, n_inner):
+    """dbx_input_gradient (injected weight noise) against oracle.input_gradient, summed over the outer iterations."""
+    L, eng, mean, std = _mlp_engine(dims, oracle, seed=2, sigma_scale=2.0)
+    x = oracle.synthetic_x((B, dims[0]), seed=4)
+    lab = np.random.Generator(np.random.Philox(9)).integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, n_outer * n_inner, seed=3)
+    nf = np.stack([oracle.flatten_list(e) for e in noise])
+    got = eng.input_gradient(x, lab, n_outer, n_inner, noise=nf).cpu().numpy()
+    want = np.zeros((B, dims[0]))
+    for it in range(n_outer):
+        ws = [oracle.sample_gaussian(mean, std, noise[it * n_inner + s], order="f32") for s in range(n_inner)]
+        want += oracle.input_gradient(L, ws, x, lab)
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6 * np.abs(want).max())
+    # one explicit weight vector == one stored sample
+    w = oracle.flatten_list(oracle.sample_gaussian(mean, std, noise[0], order="f32")).astype(np.float32)
+    g1 = eng.input_gradient_one(x, lab, w).cpu().numpy()
+    np.testing.assert_allclose(g1, oracle.input_gradient(L, [oracle.split_flat(L, w)], x, lab), rtol=2e-4, atol=2e-6 * np.abs(g1).max() + 1e-12)
+
+
+def test_fgsm_and_pgd_lower_the_true_class_probability(oracle, golden_dir):
+    """FGSM / PGD through the drop-in API on the VOGN tutorial posterior: the adversarial inputs stay in the eps-ball and in
+    [input_lower, input_upper], and the posterior-mean probability of the attacked class goes down."""
+    import deepbayes_b200 as db
+    from deepbayes_b200 import analyzers
+    pm = db.PosteriorModel(os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior"), mode="fp32")
+    x = oracle.synthetic_x((16, 784), seed=12)
+    base = np.asarray(pm.predict(x, n=35)).reshape(16, 10)
+    cls = base.argmax(1)
+    eps = 0.05
+    adv = analyzers.FGSM(pm, x, None, eps, samples=3)
+    assert adv.shape == x.shape and (np.abs(adv - x) <= eps + 1e-6).all()
+    pa = np.asarray(pm.predict(adv, n=35)).reshape(16, 10)
+    assert pa[np.arange(16), cls].mean() < base[np.arange(16), cls].mean() - 1e-3
+    np.random.seed(0)
+    adv2 = analyzers.PGD(pm, x, None, eps, num_steps=3, num_models=2)
+    assert (np.abs(adv2 - x) <= eps + 1e-6).all()
+    p2 = np.asarray(pm.predict(adv2, n=35)).reshape(16, 10)
+    assert p2[np.arange(16), cls].mean() < base[np.arange(16), cls].mean() - 1e-3
+    with pytest.raises(NotImplementedError):
+        analyzers.FGSM(pm, x, None, eps, order=0)

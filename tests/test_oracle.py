@@ -333,3 +333,23 @@ def test_bbb_step_gradients_by_finite_differences(oracle):
             g_rho = (rho[i][idx] - nr[i][idx]) / lr
             np.testing.assert_allclose(g_mean, wg + mg, rtol=2e-5, atol=2e-8)
             np.testing.assert_allclose(g_rho, noise[i][idx] * sig * wg + vg, rtol=2e-5, atol=2e-8)
+
+
+def test_input_gradient_by_finite_differences(oracle):
+    """oracle.input_gradient (hand-written backprop of the mean-prediction cross-entropy, attacks.py:60-67) against central
+    differences of oracle.mean_prediction_loss."""
+    L = oracle.mlp([10, 8, 6, 4])
+    mean, std = oracle.synthetic_posterior(L, seed=2, sigma_scale=2.0)
+    noise = oracle.synthetic_eps(L, 5, seed=3)
+    ws = [oracle.sample_gaussian(mean, std, e) for e in noise]
+    x = oracle.synthetic_x((3, 10), seed=4).astype(np.float64)
+    lab = np.array([1, 3, 0])
+    g = oracle.input_gradient(L, ws, x, lab)
+    h = 1e-6
+    for (b, k) in [(0, 0), (1, 7), (2, 9), (0, 5)]:
+        xp, xm = x.copy(), x.copy()
+        xp[b, k] += h; xm[b, k] -= h
+        fd = (oracle.mean_prediction_loss(L, ws, xp, lab)[0] - oracle.mean_prediction_loss(L, ws, xm, lab)[0]) / (2 * h)
+        np.testing.assert_allclose(g[b, k], fd, rtol=1e-5, atol=1e-9)
+    adv = oracle.fgsm(x, g, 0.05, 0.0, 1.0)
+    assert (np.abs(adv - x) <= 0.05 + 1e-12).all() and adv.min() >= 0 and adv.max() <= 1

@@ -138,10 +138,22 @@ def cfg_train():
              value=1e3 / ms, unit="steps/s", path="dbx_bbb_step", note="reference: 8.4 ms per sample-forward on CPU (SURVEY section 6); one step = sample + forward + backward + update")
 
 
+def cfg_attack():
+    """Expected input gradient: MLP 784-512-512-10, 128 inputs, one FGSM gradient = 10 iterations x 35
+    posterior samples (a PosteriorModel's predict), all on the device."""
+    eng = mlp_engine([784, 512, 512, 10])
+    x = torch.from_numpy(o.synthetic_x((128, 784), seed=0)).cuda()
+    y = np.random.Generator(np.random.Philox(3)).integers(0, 10, size=128)
+    ms = timeit(lambda: eng.input_gradient(x, y, 10, 35, seed=5), warm=1, reps=3)
+    fl = 3 * 1337344 * 128 * 350 / (ms * 1e-3) / 1e12     # forward + backward-data
+    emit(config="attack: gradient_expectation, MLP 784-512-512-10, 128 inputs, num_models=10 x 35 samples", B=128, ms=ms,
+         value=350 * 128 / (ms * 1e-3), unit="sample-input gradients/s", path="dbx_input_gradient", tflops=fl)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--stored", type=int, default=2000)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5, "train": cfg_train}[c]()
+        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5, "train": cfg_train, "attack": cfg_attack}[c]()
