@@ -20,6 +20,11 @@ network).  The oracle is therefore pinned two ways, both weaker than a real gold
       order, var-used-as-std, fp32 running sum, /float(n), softplus(rho) ...).
   (2) the two saved posteriors under Tutorials/PosteriorModels pin real inputs (mu, sigma,
       architecture).
+  (3) the widened rows: make_reference_ibp_fixtures.py runs analyzers/verifiers.py (IBP,
+      chernoff_bound_verification) and make_reference_bbb_fixtures.py runs optimizers/losses.py
+      (log_q, KL_Loss) the same way; the GRADIENTS of bbb_step / input_gradient replace
+      tf.GradientTape, which cannot run on the stand-in, and are checked against finite
+      differences of those pinned losses -- parity unpinned by a reference run for them.
 The third-party arithmetic itself (TensorFlow's Eigen matmul rounding, tf.random.normal's
 bit stream) is NOT pinned by anything the reference holds: **parity unpinned** for those,
 as DESIGN.md says.
