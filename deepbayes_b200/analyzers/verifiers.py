@@ -124,8 +124,11 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
     sequential loop on the same sample sequence.
 
     verify=True, classification=True (:588-603): the worst case comes from IBP over the eps-ball (`dbx_ibp_predict`).
-    verify=False (:622-625): the perturbed input is supplied by the caller (``adv=`` kwarg, default ``inp`` itself;
-    FGSM is SURVEY.md 8(f) rank 3).  In both cases the predicate is ``argmax == cls`` (``cls=`` kwarg; the tutorials'
+    verify=False (:622-625): every posterior sample gets its own FGSM step against that sample's weights, then the sample
+    is evaluated at the adversarial input (`dbx_count_predicate_fgsm`; attack direction = argmax of model.predict(inp), as
+    FGSM's default direction=-1).  For a PosteriorModel the reference's FGSM differentiates through the 35 fresh samples of
+    predict() instead of the iteration's own weights; the per-sample form used here is what it does for an optimizer object.
+    Passing ``adv=`` (a pre-perturbed input) skips the attack.  In all cases the predicate is ``argmax == cls`` (``cls=`` kwarg; the tutorials'
     predicate).  Returns (successes/iterations, iterations, mean/iterations) like :653 (mean is zero unless chernoff
     override, as in the reference)."""
     delta = kwargs.get('delta', 0.3)
@@ -133,7 +136,7 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
     confidence = kwargs.get('confidence', 0.95)
     verify = kwargs.get('verify', False)
     cls = kwargs.get('cls', None)
-    adv = kwargs.get('adv', inp)
+    adv = kwargs.get('adv', None)
     block = int(kwargs.get('block', 4096))
     if verify and not kwargs.get('classification', False):
         raise NotImplementedError("verify=True for regression (verifiers.py:605-620, IBP predict=True) is not built")
@@ -148,12 +151,19 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
     flags = np.zeros(0, np.uint8)
     pos = 0
     done = False
+    direc = None
     while not done:
         nb = int(min(block, chernoff_bound + 1 - iterations))
         s0 = model._take_ids(nb)
         if verify:
             fl = eng.ibp_predict(np.asarray(inp).reshape(1, -1), eps, [int(cls)], nb, model.seed, s0, None, 1.0, mode,
                                  want=(), return_flags=True)["flags"]
+        elif adv is None:
+            if direc is None:
+                direc = int(np.argmax(np.asarray(model.predict(inp)).reshape(-1)))
+            _, fl = eng.count_predicate_fgsm(np.asarray(inp).reshape(1, -1), [direc], [int(cls)], eps, nb, model.seed, s0,
+                                             lower=getattr(model, "input_lower", -np.inf), upper=getattr(model, "input_upper", np.inf),
+                                             return_flags=True)
         else:
             _, fl = eng.count_predicate(np.asarray(adv).reshape(1, -1), [int(cls)], nb, model.seed, s0, None, 1.0, mode, True)
         flags = fl.cpu().numpy().reshape(-1)

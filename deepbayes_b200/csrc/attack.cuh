@@ -166,4 +166,108 @@ static int run_input_gradient(dbx_model* m, const float* x_dev, int64_t B, const
   return 0;
 }
 
+// per-sample upstream gradient (n_inner = 1): dz[s][b][c] = (p_s[b,c] - [c == y_b]) / B, zero where the clip is active; logits -> p in place
+__global__ void softmax_ce_per_sample_kernel(float* __restrict__ z, const int32_t* __restrict__ labels, int ns, int B, int C,
+                                             float* __restrict__ dz) {
+  const int64_t total = (int64_t)ns * B;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(o % B);
+    float* row = z + o * C;
+    float m = row[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(row[c] - m);
+    const int y = labels[b];
+    const float py = expf(row[y] - m) / den;
+    const float active = (py > 1e-7f && py < 1.f - 1e-7f) ? 1.f / (float)B : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(row[c] - m) / den;
+      row[c] = p;
+      dz[o * C + c] = (p - (c == y ? 1.f : 0.f)) * active;
+    }
+  }
+}
+
+// adv[s][e] = clip(clip(x[e] + eps * sign(g[s][e]), x[e] - eps, x[e] + eps), lower, upper)   (attacks.py:94-101), in place over g
+__global__ void fgsm_adv_kernel(const float* __restrict__ x, float* __restrict__ g, int ns, int64_t n, float eps, float lower, float upper) {
+  const int64_t total = (int64_t)ns * n;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const float xe = x[o % n], ge = g[o];
+    const float sgn = ge > 0.f ? 1.f : (ge < 0.f ? -1.f : 0.f);
+    float a = xe + eps * sgn;
+    a = fminf(fmaxf(a, xe - eps), xe + eps);
+    g[o] = fminf(fmaxf(a, lower), upper);
+  }
+}
+
+// massart_bound_check with verify=False (verifiers.py:622-634): for every posterior sample, an FGSM step against THAT
+// sample's weights, then the predicate argmax == label on the sample's output at the adversarial input.
+static int run_count_fgsm(dbx_model* m, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, const int32_t* labels_dev,
+                          float eps, float lower, float upper, int64_t n, const Source& src0, int accumulate, uint8_t* flags_dev,
+                          unsigned long long* counts_dev, cudaStream_t st) {
+  DBX_CHECK(m->is_mlp, "the device FGSM loop covers Dense MLPs");
+  DBX_CHECK(m->layers[m->last_weighted].act == DBX_ACT_SOFTMAX, "the device FGSM loop needs a softmax output");
+  std::vector<const Layer*> dl;
+  for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
+  const int nl = (int)dl.size();
+  const int64_t C = m->out_feat, K0 = m->in_feat;
+  size_t act_total = 0;
+  for (auto* L : dl) act_total += (size_t)B * L->units * 4;
+  const size_t dzb = round_up((size_t)B * std::max<int64_t>(m->max_feat, K0) * 4, 256);
+  const size_t wb = src0.stored ? 0 : (size_t)m->P * 4;
+  const size_t per = act_total + 2 * dzb + wb + 64;
+  int64_t ns = (int64_t)std::max<size_t>(1, ws_budget_bytes() / per);
+  ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
+  if (ensure_ws(m->ws, (size_t)ns * per + 8192)) return 1;
+  char* p = (char*)m->ws.ptr;
+  std::vector<float*> acts(nl);
+  std::vector<int64_t> act_ss(nl);
+  for (int i = 0; i < nl; ++i) { acts[i] = (float*)p; act_ss[i] = B * dl[i]->units; p += (size_t)ns * act_ss[i] * 4; }
+  p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+  float* dz[2];
+  dz[0] = (float*)p; p += (size_t)ns * dzb; dz[1] = (float*)p; p += (size_t)ns * dzb;
+  float* Wc = (float*)p;
+  if (!accumulate) DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, counts_dev, B);
+
+  for (int64_t c0 = 0; c0 < n; c0 += ns) {
+    const int nc = (int)std::min<int64_t>(ns, n - c0);
+    const float* Wbase; int64_t w_ss; const int32_t* rows = nullptr; int64_t row0 = 0;
+    if (src0.stored) { Wbase = m->slab; w_ss = m->slab_stride; rows = src0.idx ? src0.idx + c0 : nullptr; row0 = src0.j0 + c0; }
+    else {
+      const int64_t total = (int64_t)nc * ((m->P + 3) / 4);
+      DBX_LAUNCH(sample_f32_kernel, grid_for(total), 256, 0, st, m->mu, m->sigma, src0.eps ? src0.eps + c0 * m->P : nullptr, src0.inflate,
+                 src0.seed, src0.s0 + c0, (int64_t)nc, m->P, 0, Wc, (float*)nullptr);
+      Wbase = Wc; w_ss = m->P;
+    }
+    auto forward = [&](const float* in, int64_t in_ss) -> int {
+      const float* cur = in; int64_t cur_ss = in_ss;
+      for (int i = 0; i < nl; ++i) {
+        const Layer& L = *dl[i];
+        dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), (unsigned)nc);
+        DBX_LAUNCH((dense_kernel<float, float>), grid, 256, 0, st, cur, cur_ss, Wbase, w_ss, rows, row0, L.w_off, (int)L.w_cols, Wbase, w_ss,
+                   L.b_off, acts[i], act_ss[i], (int)B, L.units, (int)L.in_feat, i == nl - 1 ? DBX_ACT_LINEAR : L.act);
+        cur = acts[i]; cur_ss = act_ss[i];
+      }
+      return 0;
+    };
+    if (forward(x_dev, 0)) return 1;
+    DBX_LAUNCH(softmax_ce_per_sample_kernel, grid_for((int64_t)nc * B), 256, 0, st, acts[nl - 1], attack_labels_dev, nc, (int)B, (int)C, dz[0]);
+    int zi = 0; int64_t zs = B * C;
+    for (int i = nl - 1; i >= 0; --i) {
+      const Layer& L = *dl[i];
+      const int K = (int)L.in_feat, N = L.units;
+      dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32), (unsigned)nc);
+      DBX_LAUNCH(grad_a_batched_kernel, ga, 256, 0, st, (const float*)dz[zi], zs, Wbase, w_ss, L.w_off, rows, row0,
+                 i > 0 ? (const float*)acts[i - 1] : (const float*)nullptr, i > 0 ? act_ss[i - 1] : 0, (int)B, K, N,
+                 i > 0 ? dl[i - 1]->act : DBX_ACT_LINEAR, dz[zi ^ 1], (int64_t)B * K);
+      zi ^= 1; zs = (int64_t)B * K;
+    }
+    DBX_LAUNCH(fgsm_adv_kernel, grid_for((int64_t)nc * B * K0), 256, 0, st, x_dev, dz[zi], nc, B * K0, eps, lower, upper);
+    if (forward(dz[zi], B * K0)) return 1;
+    DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, (const float*)acts[nl - 1], nc, B, (int)C, labels_dev,
+               flags_dev ? flags_dev + c0 * B : nullptr, counts_dev);
+  }
+  return 0;
+}
+
 }  // namespace dbx

@@ -1134,6 +1134,18 @@ int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const in
   return rc;
 }
 
+int dbx_count_predicate_fgsm(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, const int32_t* labels_dev,
+                             float eps, float lower, float upper, int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate,
+                             int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream) {
+  DBX_CHECK(h && x_dev && attack_labels_dev && labels_dev && counts_dev, "null argument");
+  DBX_CHECK(B > 0 && n > 0 && eps >= 0.f, "B, n must be positive and eps >= 0");
+  DBX_CHECK(h->have_gaussian, "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  Source src; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  return run_count_fgsm(h, x_dev, B, attack_labels_dev, labels_dev, eps, lower, upper, n, src, accumulate, flags_dev,
+                        (unsigned long long*)counts_dev, (cudaStream_t)stream);
+}
+
 int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32_t* labels_dev, int64_t n, uint64_t seed,
                         int64_t s0, const float* eps_dev, float inflate, int32_t mode, int32_t accumulate,
                         uint8_t* flags_dev, int64_t* counts_dev, void* stream) {

@@ -280,6 +280,24 @@ class Engine:
         _lib.check(self.lib.dbx_input_gradient_one(self.h, _ptr(xt), B, _ptr(lab), _ptr(w), _ptr(g), _stream()))
         return g
 
+    def count_predicate_fgsm(self, x, attack_labels, labels, eps, n, seed=0, s0=0, noise=None, inflate=1.0, lower=-3.0e38, upper=3.0e38,
+                             return_flags=False):
+        """Per posterior sample: FGSM against that sample, then argmax == label at the adversarial input (verifiers.py:622-634)."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        al = torch.as_tensor(np.asarray(attack_labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
+        if lab.numel() != B or al.numel() != B:
+            raise ValueError("need one label per input row")
+        counts = torch.zeros(B, dtype=torch.int64, device=self.device)
+        flags = torch.empty((n, B), dtype=torch.uint8, device=self.device) if return_flags else None
+        e = None if noise is None else self._dev_f32(noise).reshape(n, self.P)
+        lo = float(max(lower, -3.0e38)); hi = float(min(upper, 3.0e38))
+        _lib.check(self.lib.dbx_count_predicate_fgsm(self.h, _ptr(xt), B, _ptr(al), _ptr(lab), float(eps), lo, hi, n, seed, s0, _ptr(e),
+                                                     float(inflate), 0, _ptr(flags), _ptr(counts), _stream()))
+        return (counts, flags) if return_flags else counts
+
     def ibp_predict(self, x, eps, labels=None, n=1, seed=0, s0=0, noise=None, inflate=1.0, mode="bf16", clip=True,
                     stored=False, j0=0, want=("worst",), return_flags=False):
         """Interval bound propagation over n posterior samples (verifiers.py:23-41, 68-95, 537-557, 588-634).

@@ -154,6 +154,14 @@ int dbx_input_gradient(dbx_handle h, const float* x_dev, int64_t B, const int32_
 int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, const float* W_dev, float* grad_dev,
                            void* stream);
 
+/* massart_bound_check / chernoff loop with verify=False (verifiers.py:588-634, :622-625): for each of the n posterior
+ * samples, an FGSM step (attacks.py:81-102, first order, sparse categorical cross-entropy towards attack_labels) against
+ * THAT sample's weights, then the predicate argmax == labels[b] on the sample's output at the adversarial input.
+ * counts_dev [B] (+ per-sample flags [n,B]).  lower / upper = the model's input_lower / input_upper. */
+int dbx_count_predicate_fgsm(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, const int32_t* labels_dev,
+                             float eps, float lower, float upper, int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate,
+                             int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream);
+
 /* Interval bound propagation over posterior samples (deepbayes/analyzers/verifiers.py: propagate_interval :23-41,
  * IBP :68-95, and its per-sample use in chernoff_bound_verification :537-557 / massart_bound_check :588-634).
  * For each of the n samples (Gaussian: global ids s0.., optional injected noise [n,P]; stored != 0: slab rows j0..)

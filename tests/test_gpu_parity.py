@@ -788,3 +788,42 @@ def test_fgsm_and_pgd_lower_the_true_class_probability(oracle, golden_dir):
     assert p2[np.arange(16), cls].mean() < base[np.arange(16), cls].mean() - 1e-3
     with pytest.raises(NotImplementedError):
         analyzers.FGSM(pm, x, None, eps, order=0)
+
+
+def test_count_predicate_fgsm_matches_oracle(oracle):
+    """dbx_count_predicate_fgsm (injected weight noise): per posterior sample, the FGSM step of attacks.py:94-101 against that
+    sample's weights and the predicate at the adversarial input, against the oracle's input_gradient / fgsm / forward."""
+    dims, B, n = [30, 24, 16, 7], 9, 11
+    L, eng, mean, std = _mlp_engine(dims, oracle, seed=2, sigma_scale=2.0)
+    x = oracle.synthetic_x((B, dims[0]), seed=4)
+    g = np.random.Generator(np.random.Philox(9))
+    direc = g.integers(0, dims[-1], size=B)
+    lab = g.integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, n, seed=3)
+    nf = np.stack([oracle.flatten_list(e) for e in noise])
+    eps = 0.03
+    counts, flags = eng.count_predicate_fgsm(x, direc, lab, eps, n, noise=nf, lower=0.0, upper=1.0, return_flags=True)
+    want = np.zeros((n, B), bool)
+    margin_ok = np.ones((n, B), bool)
+    for s in range(n):
+        w = oracle.sample_gaussian(mean, std, noise[s], order="f32")
+        gr = oracle.input_gradient(L, [w], x, direc)
+        adv = oracle.fgsm(x, gr, eps, 0.0, 1.0)
+        z = oracle.forward(L, w, adv, dtype=np.float64, out="logits")
+        want[s] = z.argmax(1) == lab
+        top2 = np.sort(z, axis=1)[:, -2:]
+        margin_ok[s] = ((top2[:, 1] - top2[:, 0]) > 1e-4) & (np.abs(gr).min(1) > 1e-9)   # ties / zero gradients may flip in fp32
+    got = flags.cpu().numpy().astype(bool)
+    assert (got == want)[margin_ok].all() and margin_ok.mean() > 0.9
+    np.testing.assert_array_equal(counts.cpu().numpy(), got.sum(0))
+
+
+def test_massart_with_device_fgsm(oracle):
+    import deepbayes_b200 as db
+    from deepbayes_b200.analyzers import verifiers
+    m = db.Sequential([db.Dense(64, activation="relu", input_shape=(784,)), db.Dense(10, activation="softmax")])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=16, inflate_prior=1.0)
+    x = oracle.synthetic_x((1, 784), seed=9)
+    cls = int(np.argmax(opt.predict(x)))
+    p, it, _ = verifiers.massart_bound_check(opt, x, 0.01, None, cls=cls, verify=False, confidence=0.8, delta=0.3)
+    assert 0.0 <= p <= 1.0 and 1 <= it <= verifiers.chernoff_sample_bound(0.8, 0.3) + 1
