@@ -1101,13 +1101,14 @@ int dbx_bbb_forward(dbx_handle h, const float* x_dev, int64_t B, uint64_t seed, 
 
 int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                  const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
-                 float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
+                 float lrate, float kl_weight, int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper,
+                 float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
   DBX_CHECK(h && x_dev && labels_dev && mean_dev && rho_dev && prior_mean_dev && prior_var_dev, "null argument");
   DBX_CHECK(B > 0, "B must be positive");
   DBX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (run_bbb_step(h, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
-                   loss_out_dev, probs_out_dev, st))
+                   loss_out_dev, probs_out_dev, robust_mode, epsilon, robust_lambda, in_lower, in_upper, st))
     return 1;
   if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));   // W is the first workspace block
   return 0;

@@ -57,7 +57,7 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_
 
 // dW[k, n] = sum_b A[b, k] * dZ[b, n]   (A: [B, K], dZ: [B, N]); 32x32 tiles, ascending b
 __global__ void __launch_bounds__(256)
-grad_w_kernel(const float* __restrict__ A, const float* __restrict__ dZ, int B, int K, int N, float* __restrict__ dW) {
+grad_w_kernel(const float* __restrict__ A, const float* __restrict__ dZ, int B, int K, int N, float* __restrict__ dW, int accumulate) {
   __shared__ float As[32][33];
   __shared__ float Zs[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -81,17 +81,17 @@ grad_w_kernel(const float* __restrict__ A, const float* __restrict__ dZ, int B, 
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int k = k0 + ty + 8 * r, n = n0 + tx;
-    if (k < K && n < N) dW[(int64_t)k * N + n] = acc[r];
+    if (k < K && n < N) dW[(int64_t)k * N + n] = accumulate ? dW[(int64_t)k * N + n] + acc[r] : acc[r];
   }
 }
 
 // db[n] = sum_b dZ[b, n]
-__global__ void grad_b_kernel(const float* __restrict__ dZ, int B, int N, float* __restrict__ db) {
+__global__ void grad_b_kernel(const float* __restrict__ dZ, int B, int N, float* __restrict__ db, int accumulate) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float a = 0.f;
   for (int b = 0; b < B; ++b) a += dZ[(int64_t)b * N + n];
-  db[n] = a;
+  db[n] = accumulate ? db[n] + a : a;
 }
 
 // dZprev[b, k] = (sum_n dZ[b, n] * W[k, n]) * act'(Aprev[b, k])   (W: [K, N] row-major)
@@ -131,6 +131,56 @@ grad_a_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const f
       }
       dZprev[(int64_t)b * K + k] = acc[r] * d;
     }
+  }
+}
+
+// robust_train == 2 (bayesbybackprop.py:91-101): FGSM against the step's own weights, direction = the predicted class
+// (attacks.py:86-91 with direction = -1): dz_att[b][c] = (p[b][c] - [c == argmax p[b]]) / B
+__global__ void attack_upstream_kernel(const float* __restrict__ logits, int B, int C, float* __restrict__ dz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* z = logits + (int64_t)b * C;
+  int best = 0; float m = z[0];
+  for (int c = 1; c < C; ++c) if (z[c] > m) { m = z[c]; best = c; }
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) den += expf(z[c] - m);
+  const float pb = 1.f / den;
+  const float active = (pb > 1e-7f && pb < 1.f - 1e-7f) ? 1.f / (float)B : 0.f;
+  for (int c = 0; c < C; ++c) dz[(int64_t)b * C + c] = (expf(z[c] - m) / den - (c == best ? 1.f : 0.f)) * active;
+}
+
+__global__ void fgsm_step_kernel(const float* __restrict__ x, const float* __restrict__ g, int64_t n, float eps, float lower, float upper,
+                                 float* __restrict__ adv) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const float xe = x[o], ge = g[o];
+    float a = xe + eps * (ge > 0.f ? 1.f : (ge < 0.f ? -1.f : 0.f));
+    a = fminf(fmaxf(a, xe - eps), xe + eps);
+    adv[o] = fminf(fmaxf(a, lower), upper);
+  }
+}
+
+// output = lambda * p + (1 - lambda) * p' (:94, :101); loss row, and the logit gradients of BOTH passes
+__global__ void mix_ce_kernel(const float* __restrict__ logits, const float* __restrict__ logits_adv, const int32_t* __restrict__ labels, int B,
+                              int C, float lambda, float* __restrict__ probs, float* __restrict__ dz, float* __restrict__ dz_adv,
+                              float* __restrict__ row_loss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* z = logits + (int64_t)b * C;
+  const float* za = logits_adv + (int64_t)b * C;
+  float m = z[0], ma = za[0];
+  for (int c = 1; c < C; ++c) { m = fmaxf(m, z[c]); ma = fmaxf(ma, za[c]); }
+  float den = 0.f, dena = 0.f;
+  for (int c = 0; c < C; ++c) { den += expf(z[c] - m); dena += expf(za[c] - ma); }
+  const int y = labels[b];
+  const float py = expf(z[y] - m) / den, pay = expf(za[y] - ma) / dena;
+  const float oy = lambda * py + (1.f - lambda) * pay;
+  const float g = (oy > 1e-7f && oy < 1.f - 1e-7f) ? -1.f / ((float)B * oy) : 0.f;
+  row_loss[b] = -logf(fminf(fmaxf(oy, 1e-7f), 1.f - 1e-7f));
+  for (int c = 0; c < C; ++c) {
+    const float p = expf(z[c] - m) / den, pa = expf(za[c] - ma) / dena;
+    probs[(int64_t)b * C + c] = p;                                   // train_metric sees `predictions`, :166
+    dz[(int64_t)b * C + c] = lambda * g * py * ((c == y ? 1.f : 0.f) - p);
+    dz_adv[(int64_t)b * C + c] = (1.f - lambda) * g * pay * ((c == y ? 1.f : 0.f) - pa);
   }
 }
 
@@ -190,62 +240,93 @@ __global__ void bbb_loss_kernel(const float* __restrict__ row_loss, int B, const
 
 static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
-                        float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, cudaStream_t st) {
+                        float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
+                        float robust_lambda, float in_lower, float in_upper, cudaStream_t st) {
   DBX_CHECK(m->is_mlp, "the device training step covers Dense MLPs (bayesbybackprop.py:46-170)");
+  DBX_CHECK(robust_mode == 0 || robust_mode == 2, "robust_train %d is not built (0 = standard, 2 = FGSM adversarial training)", robust_mode);
   const Layer& Lout = m->layers[m->last_weighted];
   DBX_CHECK(Lout.act == DBX_ACT_SOFTMAX, "the device training step needs a softmax output (sparse categorical cross-entropy)");
-  const int64_t P = m->P, C = m->out_feat;
-  // workspace: W | noise | gdata | activations of every layer (outputs) | dZ ping-pong | logits | row_loss | partials
+  const int64_t P = m->P, C = m->out_feat, K0 = m->in_feat;
   std::vector<const Layer*> dl;
   for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
   const int nl = (int)dl.size();
+  // workspace: W | noise | gdata | layer outputs (clean pass, adversarial pass) | x_adv | dZ ping-pong | probs | dz_adv | row_loss | partials
   size_t act_total = 0;
   for (auto* L : dl) act_total += round_up((size_t)B * L->units * 4, 256);
-  const size_t pb = round_up((size_t)P * 4, 256), dzb = round_up((size_t)B * m->max_feat * 4, 256);
+  const size_t pb = round_up((size_t)P * 4, 256), dzb = round_up((size_t)B * std::max<int64_t>(m->max_feat, K0) * 4, 256);
+  const size_t xb = round_up((size_t)B * K0 * 4, 256), ob = round_up((size_t)B * C * 4, 256);
   const int ublocks = 148 * 4;
-  const size_t need = 3 * pb + act_total + 2 * dzb + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
+  const size_t need = 3 * pb + 2 * act_total + xb + 2 * dzb + 2 * ob + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
   if (ensure_ws(m->ws, need)) return 1;
   char* p = (char*)m->ws.ptr;
-  float* W = (float*)p; p += pb;
+  float* W = (float*)p; p += pb;            // (dbx_bbb_step copies the sampled weights out of this first block)
   float* noise = (float*)p; p += pb;
   float* gdata = (float*)p; p += pb;
-  std::vector<float*> acts(nl);
+  std::vector<float*> acts(nl), acts_adv(nl);
   for (int i = 0; i < nl; ++i) { acts[i] = (float*)p; p += round_up((size_t)B * dl[i]->units * 4, 256); }
+  for (int i = 0; i < nl; ++i) { acts_adv[i] = (float*)p; p += round_up((size_t)B * dl[i]->units * 4, 256); }
+  float* x_adv = (float*)p; p += xb;
   float* dz[2]; dz[0] = (float*)p; p += dzb; dz[1] = (float*)p; p += dzb;
+  float* probs_scratch = (float*)p; p += ob;
+  float* dz_adv = (float*)p; p += ob;
   float* row_loss = (float*)p; p += round_up((size_t)B * 4, 256);
   float* partial = (float*)p;
+  float* probs = probs_out_dev ? probs_out_dev : probs_scratch;
 
   DBX_LAUNCH(bbb_sample_kernel, grid_for((P + 3) / 4), 256, 0, st, mean_dev, rho_dev, noise_dev, seed, step, P, W, noise);
-  // ---- forward (fp32, layer outputs kept)
-  const float* cur = x_dev;
-  for (int i = 0; i < nl; ++i) {
-    const Layer& L = *dl[i];
-    const bool last = (i == nl - 1);
-    dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), 1);
-    DBX_LAUNCH((dense_kernel<float, float>), grid, 256, 0, st, cur, (int64_t)0, (const float*)W, (int64_t)0, (const int32_t*)nullptr,
-               (int64_t)0, L.w_off, (int)L.w_cols, (const float*)W, (int64_t)0, L.b_off, acts[i], (int64_t)0, (int)B, L.units,
-               (int)L.in_feat, last ? DBX_ACT_LINEAR : L.act);
-    cur = acts[i];
-  }
-  // ---- loss gradient at the logits; acts[nl-1] becomes the probabilities
-  float* probs = probs_out_dev ? probs_out_dev : dz[1];
-  DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, acts[nl - 1], labels_dev, (int)B, (int)C, probs, dz[0], row_loss);
-  // ---- backward
-  int zi = 0;
-  for (int i = nl - 1; i >= 0; --i) {
-    const Layer& L = *dl[i];
-    const float* a_prev = (i == 0) ? x_dev : acts[i - 1];
-    const int K = (int)L.in_feat, N = L.units;
-    dim3 gw((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
-    DBX_LAUNCH(grad_w_kernel, gw, 256, 0, st, a_prev, dz[zi], (int)B, K, N, gdata + L.w_off);
-    DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, dz[zi], (int)B, N, gdata + L.b_off);
-    if (i > 0) {
-      dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32));
-      // dz[1] may hold the probabilities of this call only when the caller did not ask for them; they are dead by now
-      DBX_LAUNCH(grad_a_kernel, ga, 256, 0, st, dz[zi], (const float*)W + L.w_off, a_prev, (int)B, K, N, dl[i - 1]->act, dz[zi ^ 1]);
-      zi ^= 1;
+  // forward with the sampled weights, fp32, layer outputs kept
+  auto forward = [&](const float* in, std::vector<float*>& out) -> int {
+    const float* cur = in;
+    for (int i = 0; i < nl; ++i) {
+      const Layer& L = *dl[i];
+      dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), 1);
+      DBX_LAUNCH((dense_kernel<float, float>), grid, 256, 0, st, cur, (int64_t)0, (const float*)W, (int64_t)0, (const int32_t*)nullptr,
+                 (int64_t)0, L.w_off, (int)L.w_cols, (const float*)W, (int64_t)0, L.b_off, out[i], (int64_t)0, (int)B, L.units,
+                 (int)L.in_feat, i == nl - 1 ? DBX_ACT_LINEAR : L.act);
+      cur = out[i];
     }
+    return 0;
+  };
+  // backward from dz[0] (the gradient at the logits).  to_input: propagate down to dX and return the index of the dz
+  // buffer holding it; otherwise produce the weight / bias gradients into gdata (accumulate: add to what is there)
+  auto backward = [&](const float* in, std::vector<float*>& a, bool to_input, int accumulate) -> int {
+    int zi = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      const Layer& L = *dl[i];
+      const float* a_prev = (i == 0) ? in : a[i - 1];
+      const int K = (int)L.in_feat, N = L.units;
+      if (!to_input) {
+        dim3 gw((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
+        DBX_LAUNCH(grad_w_kernel, gw, 256, 0, st, a_prev, (const float*)dz[zi], (int)B, K, N, gdata + L.w_off, accumulate);
+        DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, accumulate);
+      }
+      if (i > 0 || to_input) {
+        dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32));
+        DBX_LAUNCH(grad_a_kernel, ga, 256, 0, st, (const float*)dz[zi], (const float*)W + L.w_off, a_prev, (int)B, K, N,
+                   i > 0 ? dl[i - 1]->act : DBX_ACT_LINEAR, dz[zi ^ 1]);
+        zi ^= 1;
+      }
+    }
+    return zi;
+  };
+  if (forward(x_dev, acts)) return 1;
+  if (robust_mode == 0) {
+    DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], labels_dev, (int)B, (int)C, probs, dz[0], row_loss);
+    backward(x_dev, acts, false, 0);
+  } else {
+    // robust_train == 2: FGSM against the step's own weights (attacks.py:81-102 with num_models = 1 -> current weights, :57-58)
+    DBX_LAUNCH(attack_upstream_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (int)B, (int)C, dz[0]);
+    const int zi = backward(x_dev, acts, true, 0);
+    DBX_LAUNCH(fgsm_step_kernel, grid_for(B * K0), 256, 0, st, x_dev, (const float*)dz[zi], B * K0, epsilon, in_lower, in_upper, x_adv);
+    if (forward(x_adv, acts_adv)) return 1;
+    // loss on lambda * p + (1 - lambda) * p_adv; logit gradients of both passes
+    DBX_LAUNCH(mix_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (const float*)acts_adv[nl - 1], labels_dev, (int)B, (int)C,
+               robust_lambda, probs, dz[0], dz_adv, row_loss);
+    backward(x_dev, acts, false, 0);
+    DBX_CUDA(cudaMemcpyAsync(dz[0], dz_adv, (size_t)B * C * 4, cudaMemcpyDeviceToDevice, st));
+    backward(x_adv, acts_adv, false, 1);
   }
+  DBX_CUDA(cudaGetLastError());
   // ---- log_q terms + update
   TrainTensors tt; tt.n = m->table.n;
   for (int i = 0; i < tt.n; ++i) { tt.off[i] = m->table.src_off[i]; tt.end[i] = m->table.src_end[i]; }

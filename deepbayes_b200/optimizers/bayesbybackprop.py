@@ -68,8 +68,10 @@ class BayesByBackprop(optimizer.Optimizer):
         The parameters live on the device between steps; with sync=True (default) the updated lists are copied back,
         set on the object and returned like the reference does (:169-170), and the sampled weights are left in the model
         (:59).  Other data losses / robust_train modes raise NotImplementedError."""
-        if getattr(self, "robust_train", 0) != 0:
-            raise NotImplementedError("robust_train != 0 (bayesbybackprop.py:73-136) needs the IBP / FGSM backward (SURVEY.md 8(f))")
+        rt = int(getattr(self, "robust_train", 0))
+        if rt not in (0, 2):
+            raise NotImplementedError("robust_train = %d (bayesbybackprop.py:73-136): only 0 (standard) and 2 (FGSM adversarial training, "
+                                      ":91-101) are built; the IBP modes need a backward through the interval forward" % rt)
         name = getattr(self.loss_func, "__name__", type(self.loss_func).__name__).lower() if self.loss_func is not None else "sparse_categorical_crossentropy"
         if "sparse" not in name or "crossentropy" not in name:
             raise NotImplementedError("the device step builds the sparse categorical cross-entropy data term only (got %r)" % name)
@@ -82,7 +84,9 @@ class BayesByBackprop(optimizer.Optimizer):
             self._d_pv = self._flat_dev(self.prior_var).clone()
         e = None if noise is None else eng._as_flat(noise)
         res = eng.bbb_step(features, labels, self._d_mean, self._d_rho, self._d_pm, self._d_pv, lrate, self.kl_weight, self.seed,
-                           self._take_ids(1), e, want_probs=True, want_weights=sync)
+                           self._take_ids(1), e, want_probs=True, want_weights=sync, robust_mode=rt,
+                           epsilon=float(getattr(self, "epsilon", 0.0)), robust_lambda=float(getattr(self, "robust_lambda", 1.0)),
+                           in_lower=self.input_lower, in_upper=self.input_upper)
         self._last_loss, self._last_probs = res["loss"], res["probs"]
         if sync:
             self.posterior_mean = self._unflat(self._d_mean.cpu().numpy())

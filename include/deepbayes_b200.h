@@ -138,10 +138,14 @@ int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32
  * rho -= lrate * (noise * sigmoid(rho) * gW + grho).  All parameter vectors are flat fp32 [P] in Keras order, on the
  * device, owned by the caller.  Optional outputs: loss_out_dev[2] = (loss, kl component), probs_out_dev [B,C] = the
  * predictions of this step, W_out_dev [P] = the sampled weights (the reference leaves them in the model, :59).
+ * robust_mode = 2 (bayesbybackprop.py:91-101): features_adv = FGSM(features, eps = epsilon) against the step's own
+ * weights towards the predicted class, clipped to [in_lower, in_upper], and the data term is evaluated on
+ * robust_lambda * predictions + (1 - robust_lambda) * model(features_adv); robust_mode = 0 ignores those arguments.
  * Dense MLPs with a softmax output; fp32 arithmetic. */
 int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                  const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
-                 float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
+                 float lrate, float kl_weight, int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper,
+                 float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
 
 /* Expected input gradient (deepbayes/analyzers/attacks.py gradient_expectation :49-75): the sum over n_outer iterations
  * of d CE(labels, mean over n_inner posterior samples of softmax(f_W(x))) / d x, CE = batch-mean sparse categorical

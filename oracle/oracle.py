@@ -593,10 +593,44 @@ def kl_loss(layers, labels, x, W, prior_mean, prior_var, q_mean, q_rho, kl_weigh
     return data + dtype(kl_weight) * klc, klc, pred
 
 
-def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64):
-    """`BayesByBackprop.step` (bayesbybackprop.py:46-170, robust_train == 0) for Dense MLPs with a softmax output and the
-    sparse categorical cross-entropy, gradients written out by hand (the reference gets them from tf.GradientTape):
+def _mlp_forward_acts(dense, W, x):
+    acts, h = [x], x
+    for li, l in enumerate(dense):
+        h = _act(l.activation, h @ W[2 * li] + W[2 * li + 1])
+        acts.append(h)
+    return acts
+
+
+def _mlp_backward_weights(dense, W, acts, dz):
+    """dLoss/dW for every tensor given dLoss/d(logits) = dz; acts[i] = input of layer i, acts[-1] = output."""
+    gW = [None] * len(W)
+    for li in range(len(dense) - 1, -1, -1):
+        gW[2 * li] = acts[li].T @ dz
+        gW[2 * li + 1] = dz.sum(0)
+        if li > 0:
+            da = dz @ W[2 * li].T
+            a, name = acts[li], dense[li - 1].activation
+            if name == "relu":
+                dz = da * (a > 0)
+            elif name == "tanh":
+                dz = da * (1 - a * a)
+            elif name == "sigmoid":
+                dz = da * a * (1 - a)
+            elif name in ("linear", None):
+                dz = da
+            else:
+                raise NotImplementedError(name)
+    return gW
+
+
+def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64,
+             robust_train=0, epsilon=0.0, robust_lambda=1.0, lower=-np.inf, upper=np.inf):
+    """`BayesByBackprop.step` (bayesbybackprop.py:46-170) for Dense MLPs with a softmax output and the sparse categorical
+    cross-entropy, gradients written out by hand (the reference gets them from tf.GradientTape):
       W = mean + softplus(rho) * noise                                                    (:50-59)
+      robust_train == 0: output = model_W(x)                                               (:65-72)
+      robust_train == 2: x_adv = FGSM(x, eps) against W towards argmax model_W(x) (:92, attacks.py:81-102 with the
+                         model's current weights), output = lambda * model_W(x) + (1 - lambda) * model_W(x_adv)   (:93-95)
       weight_gradient = dLoss/dW       (data term + kl_weight * d(log_q - log_prior)/dW)  (:138)
       mean_gradient   = dLoss/dmean = kl_weight * (W - mean) / (sigma^2 n_i)              (:139)
       var_gradient    = dLoss/drho  = kl_weight * ((W - mean)^2 / sigma^3 - 1 / sigma) * sigmoid(rho) / n_i   (:140)
@@ -612,50 +646,41 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
     ps = [softplus(np.asarray(t, d), d) for t in prior_var]
     sg = [softplus(r, d) for r in rho]
     W = [m + s * e for m, s, e in zip(mean, sg, noise)]
-    # forward, keeping the layer inputs
-    acts = [np.asarray(x, d)]
     dense = [l for l in layers if l.kind == "dense"]
     if len(dense) != len(layers):
         raise NotImplementedError("oracle bbb_step covers Dense MLPs")
-    h = acts[0]
-    for li, l in enumerate(dense):
-        z = h @ W[2 * li] + W[2 * li + 1]
-        h = _act(l.activation, z)
-        acts.append(h)
+    if dense[-1].activation != "softmax":
+        raise NotImplementedError("oracle bbb_step: softmax output")
+    x = np.asarray(x, d)
+    acts = _mlp_forward_acts(dense, W, x)
     pred = acts[-1]
     B = pred.shape[0]
     lab = np.asarray(labels).reshape(-1)
-    data = sparse_categorical_crossentropy(lab, pred, d)
-    klc = log_q(W, mean, rho, d) - log_q(W, pm, [np.asarray(t, d) for t in prior_var], d)
-    loss = data + d(kl_weight) * klc
-    # backward of the data term: softmax + mean cross-entropy (the clip is inactive away from p = 1e-7)
-    if dense[-1].activation != "softmax":
-        raise NotImplementedError("oracle bbb_step: softmax output")
-    dz = pred.copy()
-    pl = pred[np.arange(B), lab]
-    active = ((pl > 1e-7) & (pl < 1 - 1e-7)).astype(d)
     onehot = np.zeros_like(pred)
     onehot[np.arange(B), lab] = 1
-    dz = (pred - onehot) * active[:, None] / d(B)
-    gW = [None] * len(W)
-    for li in range(len(dense) - 1, -1, -1):
-        a_prev = acts[li]
-        gW[2 * li] = a_prev.T @ dz
-        gW[2 * li + 1] = dz.sum(0)
-        if li > 0:
-            da = dz @ W[2 * li].T
-            name = dense[li - 1].activation
-            a = acts[li]
-            if name == "relu":
-                dz = da * (a > 0)
-            elif name == "tanh":
-                dz = da * (1 - a * a)
-            elif name == "sigmoid":
-                dz = da * a * (1 - a)
-            elif name in ("linear", None):
-                dz = da
-            else:
-                raise NotImplementedError(name)
+    if robust_train == 0:
+        out = pred
+        pl = out[np.arange(B), lab]
+        active = ((pl > 1e-7) & (pl < 1 - 1e-7)).astype(d)
+        gW = _mlp_backward_weights(dense, W, acts, (pred - onehot) * active[:, None] / d(B))
+    elif robust_train == 2:
+        direc = pred.argmax(1)
+        x_adv = fgsm(x, input_gradient(layers, [W], x, direc, d), epsilon, lower, upper)
+        acts_adv = _mlp_forward_acts(dense, W, x_adv)
+        pa = acts_adv[-1]
+        out = d(robust_lambda) * pred + d(1 - robust_lambda) * pa
+        oy = out[np.arange(B), lab]
+        g = np.where((oy > 1e-7) & (oy < 1 - 1e-7), -1.0 / (B * oy), 0.0)
+        dz = (d(robust_lambda) * g * pred[np.arange(B), lab])[:, None] * (onehot - pred)
+        dza = (d(1 - robust_lambda) * g * pa[np.arange(B), lab])[:, None] * (onehot - pa)
+        g1 = _mlp_backward_weights(dense, W, acts, dz)
+        g2 = _mlp_backward_weights(dense, W, acts_adv, dza)
+        gW = [a + b for a, b in zip(g1, g2)]
+    else:
+        raise NotImplementedError("oracle bbb_step: robust_train 0 and 2")
+    data = sparse_categorical_crossentropy(lab, out, d)
+    klc = log_q(W, mean, rho, d) - log_q(W, pm, [np.asarray(t, d) for t in prior_var], d)
+    loss = data + d(kl_weight) * klc
     new_mean, new_rho = [], []
     for i in range(len(W)):
         n_i = d(W[i].size)
@@ -668,7 +693,6 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
         new_mean.append(mean[i] - d(lrate) * g_mean)
         new_rho.append(rho[i] - d(lrate) * g_rho)
     return new_mean, new_rho, loss, klc, pred, W
-
 
 
 # ---------------------------------------------------------------------------------------

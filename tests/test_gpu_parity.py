@@ -827,3 +827,32 @@ def test_massart_with_device_fgsm(oracle):
     cls = int(np.argmax(opt.predict(x)))
     p, it, _ = verifiers.massart_bound_check(opt, x, 0.01, None, cls=cls, verify=False, confidence=0.8, delta=0.3)
     assert 0.0 <= p <= 1.0 and 1 <= it <= verifiers.chernoff_sample_bound(0.8, 0.3) + 1
+
+
+def test_bbb_step_fgsm_adversarial_training_matches_oracle(oracle):
+    """robust_train = 2 (bayesbybackprop.py:91-101): FGSM against the step's own weights, loss on the mix of clean and
+    adversarial predictions, both backward passes -- device vs oracle with injected noise."""
+    import deepbayes_b200 as db
+    dims, B = [40, 24, 16, 6], 21
+    L = oracle.mlp(dims)
+    layers = [db.Dense(24, activation="relu", input_shape=(40,)), db.Dense(16, activation="relu"), db.Dense(6, activation="softmax")]
+    opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.5,
+                                                  robust_train=2, epsilon=0.05, rob_lam=0.3)
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    opt.posterior_mean = [m.copy() for m in mean]
+    opt.posterior_var = [oracle.inverse_softplus(s) for s in std]
+    rho0 = [r.copy() for r in opt.posterior_var]
+    x = oracle.synthetic_x((B, 40), seed=0)
+    lab = np.random.Generator(np.random.Philox(3)).integers(0, 6, size=B)
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr = 0.1
+    nm, nr = opt.step(x, lab, lr, noise=noise)
+    wm, wr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.5,
+                                                 robust_train=2, epsilon=0.05, robust_lambda=0.3)
+    for i in range(len(nm)):
+        dm, dr = np.abs(wm[i] - mean[i]).max() + 1e-12, np.abs(wr[i] - rho0[i]).max() + 1e-12
+        np.testing.assert_allclose(nm[i], wm[i], rtol=0, atol=5e-4 * dm + 1e-7)
+        np.testing.assert_allclose(nr[i], wr[i], rtol=0, atol=5e-4 * dr + 1e-7)
+    got = opt._last_loss.cpu().numpy()
+    np.testing.assert_allclose(got[0], loss, rtol=5e-5)
+    np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)

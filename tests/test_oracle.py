@@ -353,3 +353,36 @@ def test_input_gradient_by_finite_differences(oracle):
         np.testing.assert_allclose(g[b, k], fd, rtol=1e-5, atol=1e-9)
     adv = oracle.fgsm(x, g, 0.05, 0.0, 1.0)
     assert (np.abs(adv - x) <= 0.05 + 1e-12).all() and adv.min() >= 0 and adv.max() <= 1
+
+
+def test_bbb_step_fgsm_mode_gradient_by_finite_differences(oracle):
+    """robust_train = 2: the adversarial input is a constant for the tape (attacks.FGSM returns a NumPy array), so
+    dLoss/dW is the derivative of CE(y, lambda f_W(x) + (1 - lambda) f_W(x_adv)) at fixed x_adv."""
+    L = oracle.mlp([12, 9, 7, 5])
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    rho = [oracle.inverse_softplus(s, np.float64) for s in std]
+    pm, pv = oracle.implicit_prior(L, 2.0)
+    x = oracle.synthetic_x((6, 12), seed=0).astype(np.float64)
+    lab = np.array([0, 1, 2, 3, 4, 0])
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr, kw, lam, eps = 0.1, 0.7, 0.3, 0.05
+    nm, nr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho, pm, pv, x, lab, noise, lr, kl_weight=kw, robust_train=2, epsilon=eps, robust_lambda=lam)
+    x_adv = oracle.fgsm(x, oracle.input_gradient(L, [W], x, pred.argmax(1)), eps)
+    mean64 = [np.asarray(m, np.float64) for m in mean]
+
+    def f(W_, m_, r_):
+        out = lam * oracle.forward(L, W_, x, dtype=np.float64) + (1 - lam) * oracle.forward(L, W_, x_adv, dtype=np.float64)
+        return oracle.sparse_categorical_crossentropy(lab, out) + kw * (oracle.log_q(W_, m_, r_) - oracle.log_q(W_, pm, pv))
+    assert abs(f(W, mean64, rho) - loss) < 1e-12
+    g = np.random.Generator(np.random.Philox(1))
+    h = 1e-6
+    for i in range(len(W)):
+        idx = tuple(g.integers(0, d) for d in W[i].shape)
+
+        def bump(lst, sign):
+            out = [np.array(t, np.float64) for t in lst]
+            out[i][idx] += sign * h
+            return out
+        wg = (f(bump(W, 1), mean64, rho) - f(bump(W, -1), mean64, rho)) / (2 * h)
+        mg = (f(W, bump(mean64, 1), rho) - f(W, bump(mean64, -1), rho)) / (2 * h)
+        np.testing.assert_allclose((mean64[i][idx] - nm[i][idx]) / lr, wg + mg, rtol=2e-5, atol=2e-8)
