@@ -98,6 +98,21 @@ def IBP(model, inp, weights, eps, predict=False):
     return lo.cpu().numpy().reshape(shape), hi.cpu().numpy().reshape(shape)
 
 
+def IBP_state(model, s0, s1, weights, weight_margin=0, logits=True):
+    """`IBP_state(model, s0, s1, weights, weight_margin, logits=True)` (verifiers.py:97-123; the same function is
+    probverification.IBP_prob, :84-110): logit bounds of the input box [s0, s1] under weights widened by
+    weight_margin * posterior_var (the posterior's scale, used as a std like everywhere in the reference).  Needs a
+    Gaussian posterior on the model; fp32."""
+    eng = _engine_of(model)
+    a0, a1 = np.asarray(s0, np.float32), np.asarray(s1, np.float32)
+    lo, hi = eng.ibp_state(a0.reshape(-1, eng.K), a1.reshape(-1, eng.K), _flat(weights), float(weight_margin))
+    shape = a0.shape[:-1] + (eng.C,)
+    return lo.cpu().numpy().reshape(shape), hi.cpu().numpy().reshape(shape)
+
+
+IBP_prob = IBP_state
+
+
 def chernoff_bound_verification(model, inp, eps, cls, **kwargs):
     """`chernoff_bound_verification` (verifiers.py:537-557): n = ceil(ln(2/delta) / (2 (1-confidence)^2)) posterior
     samples; for each, IBP logits of the eps-ball, worst case w.r.t. ``cls`` (lower bound of the true class, upper

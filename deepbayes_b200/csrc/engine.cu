@@ -1191,6 +1191,21 @@ int dbx_ibp_one(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t 
   return rc;
 }
 
+int dbx_ibp_state(dbx_handle h, const float* lo_dev, const float* hi_dev, int64_t B, const float* W_dev, float weight_margin,
+                  float* lower_dev, float* upper_dev, void* stream) {
+  DBX_CHECK(h && lo_dev && hi_dev && W_dev && lower_dev && upper_dev, "null argument");
+  DBX_CHECK(B > 0 && weight_margin >= 0.f, "B must be positive and weight_margin >= 0");
+  DBX_CUDA(cudaSetDevice(h->device));
+  const float* keep = h->slab; const int64_t keepS = h->S, keepStride = h->slab_stride;
+  h->slab = W_dev; h->S = 1; h->slab_stride = h->P;
+  Source src; src.stored = true; src.j0 = 0;
+  IbpSink sink; sink.sum_lower = lower_dev; sink.sum_upper = upper_dev;
+  g_last_path = 0; g_used_tc = false;
+  const int rc = run_ibp<float>(h, lo_dev, B, 0.f, 0, 1, src, sink, (cudaStream_t)stream, hi_dev, weight_margin);
+  h->slab = keep; h->S = keepS; h->slab_stride = keepStride;
+  return rc;
+}
+
 int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, uint64_t seed, int64_t s0, float inflate,
                      int32_t mode, int32_t out_kind, float* mean_host, float* var_host) {
   DBX_CHECK(h && x_host && mean_host, "null argument");

@@ -26,6 +26,16 @@ __global__ void ibp_input_kernel(const float* __restrict__ x, float eps, int cli
   }
 }
 
+// explicit input box [lo, hi] (IBP_state, verifiers.py:97-99)
+template <typename T>
+__global__ void ibp_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, T* __restrict__ a_mu, T* __restrict__ a_r,
+                               int64_t total) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    a_mu[o] = from_f32<T>((hi[o] + lo[o]) / 2.f);
+    a_r[o] = from_f32<T>((hi[o] - lo[o]) / 2.f);
+  }
+}
+
 // |W16|: the radius product needs the element-wise absolute value of the sampled kernels (sign bits cleared)
 __global__ void abs_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n16) {
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n16; o += (int64_t)gridDim.x * blockDim.x) {
@@ -67,11 +77,16 @@ __global__ void __launch_bounds__(256)
 ibp_dense_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_sstride, const T* __restrict__ Wbase,
                  int64_t w_sstride, const int32_t* __restrict__ rows, int64_t row0, int64_t w_off, int ldw,
                  const float* __restrict__ Bbase, int64_t b_sstride, int64_t b_off, T* __restrict__ n_mu,
-                 T* __restrict__ n_r, int64_t n_sstride, int M, int N, int K, IbpOut o) {
+                 T* __restrict__ n_r, int64_t n_sstride, int M, int N, int K, IbpOut o,
+                 const float* __restrict__ sigma, float margin, int64_t sig_w_off, int64_t sig_b_off) {
+  // margin > 0 (IBP_state, verifiers.py:107-112): weight interval W -+ margin * sigma, bias interval b -+ margin * sigma_b:
+  //   radius += |x_mu| W_r + x_r W_r   (propagate_interval :37-38),  upper += b_marg, lower -= b_marg
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 4];
   __shared__ float Rs[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
+  __shared__ float Ss[BK][BN + 4];
+  const bool marg = margin > 0.f && sigma != nullptr;
   const int s = blockIdx.z;
   const int64_t wrow = rows ? (int64_t)rows[s] : (row0 + s);
   const T* Ap = Amu + (int64_t)s * a_sstride;
@@ -95,6 +110,7 @@ ibp_dense_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_
     for (int i = 0; i < 4; ++i) {
       const int gk = k0 + wk, gn = n0 + wn + i;
       Ws[wk][wn + i] = (gk < K && gn < N) ? to_f32<T>(Wp[(int64_t)gk * ldw + gn]) : 0.f;
+      if (marg) Ss[wk][wn + i] = (gk < K && gn < N) ? margin * sigma[sig_w_off + (int64_t)gk * N + gn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -108,6 +124,12 @@ ibp_dense_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { am[i][j] = fmaf(a[i], w[j], am[i][j]); ar[i][j] = fmaf(r[i], fabsf(w[j]), ar[i][j]); }
+      if (marg) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ar[i][j] = fmaf(fabsf(a[i]) + r[i], Ss[k][tx * 4 + j], ar[i][j]);
+      }
     }
     __syncthreads();
   }
@@ -118,7 +140,7 @@ ibp_dense_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
-      if (gn < N) ibp_store<T>(o, n_mu, n_r, n_sstride, s, gm, gn, N, am[i][j] + bp[gn], ar[i][j]);
+      if (gn < N) ibp_store<T>(o, n_mu, n_r, n_sstride, s, gm, gn, N, am[i][j] + bp[gn], ar[i][j] + (marg ? margin * sigma[sig_b_off + gn] : 0.f));
     }
   }
 }
@@ -143,7 +165,9 @@ struct IbpSink {
 
 template <typename T>
 static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int clip01, int64_t n, const Source& src,
-                   const IbpSink& sink, cudaStream_t st) {
+                   const IbpSink& sink, cudaStream_t st, const float* box_hi_dev = nullptr, float weight_margin = 0.f) {
+  // box_hi_dev != nullptr: x_dev / box_hi_dev are the lower / upper input bounds themselves (IBP_state); weight_margin > 0
+  // widens every weight by margin * sigma (needs the Gaussian posterior's sigma; CUDA-core back end)
   constexpr bool kBf16 = !std::is_same<T, float>::value;
   DBX_CHECK(m->is_mlp, "IBP on the device covers Dense / Flatten models (propagate_conv2d, verifiers.py:11-21, is not built)");
   for (size_t li = 0; li + 1 < m->layers.size(); ++li) {
@@ -152,8 +176,9 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
               "IBP needs monotone element-wise hidden activations (layer %d is softmax)", (int)li);
   }
   const int64_t C = m->out_feat;
-  bool use_tc = kBf16;
+  bool use_tc = kBf16 && !(weight_margin > 0.f);
   if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') use_tc = false;
+  DBX_CHECK(!(weight_margin > 0.f) || (m->have_gaussian && !kBf16), "weight margins need a Gaussian posterior's sigma and the fp32 mode");
   // ---- workspace per sample: 4 activation buffers (centre/radius, ping-pong), fp32 MU/R (tensor-core back end),
   //      lower/upper/worst, weights (+ |W16|)
   const size_t act_b = round_up((size_t)B * m->max_feat * sizeof(T), 256);
@@ -184,7 +209,8 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * w16_b, 256) * (use_tc ? 2 : 1)) : nullptr;
   const int64_t act_ss = (int64_t)(act_b / sizeof(T)), out_ss = B * C;
 
-  DBX_LAUNCH(ibp_input_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, eps, clip01, in_mu, in_r, B * m->in_feat);
+  if (box_hi_dev) DBX_LAUNCH(ibp_box_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, box_hi_dev, in_mu, in_r, B * m->in_feat);
+  else DBX_LAUNCH(ibp_input_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, eps, clip01, in_mu, in_r, B * m->in_feat);
   DBX_CUDA(cudaMemsetAsync(zero_bias, 0, zb_b, st));
   if (sink.counts && !sink.accumulate) DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, sink.counts, B);
 
@@ -239,7 +265,7 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
       if (!done) {
         dim3 grid((unsigned)cdiv(L.units, 64), (unsigned)cdiv(B, 64), (unsigned)nc);
         DBX_LAUNCH(ibp_dense_kernel<T>, grid, 256, 0, st, cur_mu, cur_r, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw, Bbase,
-                   b_sstride, boff, n_mu, n_r, act_ss, (int)B, L.units, (int)L.in_feat, o);
+                   b_sstride, boff, n_mu, n_r, act_ss, (int)B, L.units, (int)L.in_feat, o, (const float*)m->sigma, weight_margin, L.w_off, L.b_off);
       }
       prof_end(st, 4.0 * (double)L.w_rows * L.w_cols * (double)B * nc);
       if (last) break;

@@ -342,6 +342,19 @@ class Engine:
                                         _stream()))
         return lo, hi
 
+    def ibp_state(self, lo, hi, weights_flat, weight_margin=0.0):
+        """`IBP_state` (verifiers.py:97-123): explicit input box, explicit weights, weight margin in units of sigma."""
+        torch = self.torch
+        lt, ht = self._x2d(lo), self._x2d(hi)
+        B = lt.shape[0]
+        w = self._dev_f32(weights_flat).reshape(-1)
+        if w.numel() != self.P or ht.shape != lt.shape:
+            raise ValueError("need %d weights and matching lower / upper inputs" % self.P)
+        lo_o = torch.empty((B, self.C), dtype=torch.float32, device=self.device)
+        hi_o = torch.empty_like(lo_o)
+        _lib.check(self.lib.dbx_ibp_state(self.h, _ptr(lt), _ptr(ht), B, _ptr(w), float(weight_margin), _ptr(lo_o), _ptr(hi_o), _stream()))
+        return lo_o, hi_o
+
     def predict_host(self, x: np.ndarray, n, seed=0, s0=0, inflate=1.0, mode="bf16", out_kind="probs", variance=False):
         """Host buffers in, host buffers out: the H2D copy of x and the D2H copy of the mean
         happen inside the C call (this is the bench's `e2e` path)."""

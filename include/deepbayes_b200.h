@@ -147,6 +147,13 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
                  float lrate, float kl_weight, int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper,
                  float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
 
+/* `IBP_state(model, s0, s1, weights, weight_margin)` (verifiers.py:97-123; probverification.py IBP_prob :84-110): the
+ * input box [lo, hi] itself is given, the weights are one explicit flat vector, and every weight / bias is widened by
+ * weight_margin * sigma (sigma = the Gaussian posterior's scale set with dbx_set_gaussian): the |x_mu| W_r and
+ * |x_r| |W_r| terms of propagate_interval (:37-38).  Logit bounds [B,C]; fp32. */
+int dbx_ibp_state(dbx_handle h, const float* lo_dev, const float* hi_dev, int64_t B, const float* W_dev, float weight_margin,
+                  float* lower_dev, float* upper_dev, void* stream);
+
 /* Expected input gradient (deepbayes/analyzers/attacks.py gradient_expectation :49-75): the sum over n_outer iterations
  * of d CE(labels, mean over n_inner posterior samples of softmax(f_W(x))) / d x, CE = batch-mean sparse categorical
  * cross-entropy.  n_inner = 35 reproduces a PosteriorModel (its predict() averages 35 samples, posteriormodel.py:81),

@@ -492,7 +492,7 @@ def propagate_interval(W, b, x_l, x_u, marg=0.0, b_marg=0.0):
     x_mu = ((x_u + x_l) / 2).astype(np.float64)
     x_r = ((x_u - x_l) / 2).astype(np.float64)
     W_mu = np.asarray(W).astype(np.float64)
-    W_r = np.zeros_like(W_mu) if np.isscalar(marg) and marg == 0 else np.broadcast_to(np.asarray(marg, np.float64), W_mu.shape)
+    W_r = np.zeros_like(W_mu) if (np.isscalar(marg) and marg == 0) else np.broadcast_to(np.asarray(marg, np.float64), W_mu.shape)
     b_u = (np.asarray(b) + b_marg).astype(np.float64)
     b_l = (np.asarray(b) - b_marg).astype(np.float64)
     h_mu = x_mu @ W_mu
@@ -528,6 +528,27 @@ def ibp_forward(layers, weights, x, eps, predict=False):
         if (not predict) and i >= len(layers) - 1:
             continue
         h_l, h_u = _act(l.activation, h_l), _act(l.activation, h_u)
+    return h_l, h_u
+
+
+def ibp_state(layers, weights, s0, s1, sigma, weight_margin=0.0):
+    """`IBP_state(model, s0, s1, weights, weight_margin, logits=True)` (verifiers.py:97-123 = probverification.IBP_prob
+    :84-110): the input box [s0, s1] as given, marg = weight_margin * posterior_var per tensor (:107-110), every Dense
+    through propagate_interval with the |x_mu| W_r and |x_r| |W_r| terms, activation on all but the last layer."""
+    h_l, h_u = np.asarray(s0), np.asarray(s1)
+    wi = 0
+    for i, l in enumerate(layers):
+        if l.kind == "flatten":
+            h_u, h_l = h_u.reshape(h_u.shape[0], -1), h_l.reshape(h_l.shape[0], -1)
+            continue
+        if l.kind != "dense":
+            raise NotImplementedError("oracle IBP covers Dense / Flatten")
+        marg = weight_margin * np.asarray(sigma[wi])          # in sigma's dtype (fp32), like the reference (:109-110)
+        b_marg = weight_margin * np.asarray(sigma[wi + 1])
+        h_l, h_u = propagate_interval(weights[wi], weights[wi + 1], h_l, h_u, marg=marg, b_marg=b_marg)
+        wi += 2
+        if i < len(layers) - 1:
+            h_l, h_u = _act(l.activation, h_l), _act(l.activation, h_u)
     return h_l, h_u
 
 

@@ -77,6 +77,11 @@ def main():
     total = verifiers.chernoff_bound_verification(pm, x1, eps, cls, confidence=0.75, delta=0.3)
     out["chernoff_sum"], out["chernoff_cls"] = np.asarray(total), np.asarray([cls])
     out["chernoff_n"] = np.asarray([int(np.ceil((1 / (2 * 0.25 ** 2)) * np.log(2 / 0.3)))])
+    # ---- IBP_state: explicit input box, weight margin 0.5 sigma around the posterior mean (verifiers.py:97-123)
+    pm.model.set_weights(pm.posterior_mean)
+    s0, s1 = np.clip(x - 0.01, 0, 1).astype(np.float32), np.clip(x + 0.01, 0, 1).astype(np.float32)
+    lo, hi = verifiers.IBP_state(pm, s0, s1, pm.model.get_weights(), weight_margin=0.5)
+    out["state_s0"], out["state_s1"], out["state_l"], out["state_u"] = s0, s1, np.asarray(lo), np.asarray(hi)
     np.savez_compressed(os.path.join(HERE, "reference_ibp.npz"), **out)
     print("wrote reference_ibp.npz:", {k: v.shape for k, v in out.items()})
 

@@ -856,3 +856,28 @@ def test_bbb_step_fgsm_adversarial_training_matches_oracle(oracle):
     got = opt._last_loss.cpu().numpy()
     np.testing.assert_allclose(got[0], loss, rtol=5e-5)
     np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
+
+
+def test_ibp_state_weight_margin_matches_reference_run(oracle, golden_dir):
+    """dbx_ibp_state (explicit input box, weight margin in units of sigma) against the committed output of the
+    reference's own verifiers.IBP_state on the VOGN tutorial posterior, and against the oracle on a synthetic model."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.analyzers import verifiers
+    ref = np.load(os.path.join(golden_dir, "reference_ibp.npz"))
+    pm = db.PosteriorModel(os.path.join(golden_dir, "posteriors", "VOGN_MNIST_Posterior"), mode="fp32")
+    lo, hi = verifiers.IBP_state(pm, ref["state_s0"], ref["state_s1"], pm.posterior_mean, weight_margin=0.5)
+    scale = np.abs(ref["state_u"]).max()
+    np.testing.assert_allclose(lo, ref["state_l"], rtol=1e-5, atol=3e-6 * scale)
+    np.testing.assert_allclose(hi, ref["state_u"], rtol=1e-5, atol=3e-6 * scale)
+    assert verifiers.IBP_prob is verifiers.IBP_state
+    dims, B = [50, 36, 20, 6], 23
+    L, eng, mean, std = _mlp_engine(dims, oracle, seed=7, sigma_scale=1.5)
+    x = oracle.synthetic_x((B, 50), seed=3)
+    s0, s1 = (x - 0.02).astype(np.float32), (x + 0.03).astype(np.float32)
+    w = oracle.flatten_list(mean).astype(np.float32)
+    for marg in (0.0, 0.7):
+        glo, ghi = eng.ibp_state(s0, s1, w, marg)
+        wlo, whi = oracle.ibp_state(L, mean, s0, s1, std, marg)
+        sc = max(np.abs(wlo).max(), np.abs(whi).max())
+        np.testing.assert_allclose(glo.cpu().numpy(), wlo, rtol=1e-5, atol=3e-6 * sc)
+        np.testing.assert_allclose(ghi.cpu().numpy(), whi, rtol=1e-5, atol=3e-6 * sc)

@@ -386,3 +386,16 @@ def test_bbb_step_fgsm_mode_gradient_by_finite_differences(oracle):
         wg = (f(bump(W, 1), mean64, rho) - f(bump(W, -1), mean64, rho)) / (2 * h)
         mg = (f(W, bump(mean64, 1), rho) - f(W, bump(mean64, -1), rho)) / (2 * h)
         np.testing.assert_allclose((mean64[i][idx] - nm[i][idx]) / lr, wg + mg, rtol=2e-5, atol=2e-8)
+
+
+def test_oracle_matches_reference_ibp_state_run(oracle, golden_dir):
+    """oracle.ibp_state against the reference's own verifiers.IBP_state (weight margin 0.5 sigma, explicit input box)."""
+    ref = np.load(os.path.join(golden_dir, "reference_ibp.npz"))
+    mean, var = _vogn(golden_dir)
+    L = oracle.mlp([784, 128, 10])
+    w = [np.asarray(t, np.float32) for t in mean]
+    lo, hi = oracle.ibp_state(L, w, ref["state_s0"], ref["state_s1"], var, 0.5)
+    np.testing.assert_allclose(lo, ref["state_l"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(hi, ref["state_u"], rtol=1e-12, atol=1e-12)
+    lo0, hi0 = oracle.ibp_state(L, w, ref["state_s0"], ref["state_s1"], var, 0.0)
+    assert (lo <= lo0 + 1e-12).all() and (hi0 <= hi + 1e-12).all()
