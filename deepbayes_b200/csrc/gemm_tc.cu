@@ -155,6 +155,149 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
+
+// =======================================================================================
+// Persistent variant of dense_tc_kernel for NARROW layers (N <= 64: conv kernels with few output channels, run
+// through an im2col matrix).  Their tiles have one to five k-blocks, so a CTA per tile spent most of its life in
+// the serial chain TMEM alloc -> barrier init -> TMA -> MMA -> epilogue (config 4's first conv: 6 us per
+// 128 x 32 tile).  Here 2 CTAs per SM walk the (sample, m tile) list; the TMA ring, the two TMEM accumulators and
+// the epilogue of tile i overlap the loads and MMAs of tile i+1.
+// =======================================================================================
+constexpr int kPStages = 4;
+constexpr int kPStageB = 24576;      // A block [128 x 64] 16 KB + W block [64 k x 64 n] 8 KB
+
+struct __align__(8) PBarriers {
+  uint64_t full[kPStages], empty[kPStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
+
+template <int kAct>
+__global__ void __launch_bounds__(kGThreads, 2)
+dense_tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p, int ns,
+                       int tiles_m) {
+  __shared__ float s_bias[64];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  PBarriers* bars = (PBarriers*)(smem + kPStages * kPStageB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kb_n = (p.K + 63) / 64;
+  const long long total = (long long)ns * tiles_m;
+  // contiguous tile range per CTA: consecutive tiles are neighbouring row blocks of the same sample
+  const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < kPStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<128>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    uint32_t g = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const int s = (int)(t / tiles_m), m0 = (int)(t - (long long)s * tiles_m) * 128;
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kPStages, ph = (g / kPStages) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          const uint32_t base = s_stage + st * kPStageB;
+          mbar_expect_tx(fb, kPStageB);
+          if (p.a_shared) tma_load_2d(base, &tmA, fb, kb * 64, m0);
+          else tma_load_3d(base, &tmA, fb, kb * 64, m0, s);
+          tma_load_3d(base + 16384, &tmW, fb, 0, kb * 64, s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+    uint32_t g = 0, it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
+      fence_after_sync();
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kPStages, ph = (g / kPStages) & 1;
+        mbar_wait(smem_u32(&bars->full[st]), ph);
+        if (elect_one()) {
+          const uint32_t a16 = ((s_stage + st * kPStageB) & 0x3FFFF) >> 4;
+          const uint32_t a_lo = a16 | (1u << 16);
+          const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
+          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+          for (int kk = 0; kk < ksteps; ++kk)
+            mma_ss_lh(tmem + ab * 64, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+          mma_commit(smem_u32(&bars->empty[st]));
+          if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int gq = warp & 3;
+    const int row = gq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    uint32_t it = 0;
+    int cur_s = -1;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int s = (int)(t / tiles_m), m0 = (int)(t - (long long)s * tiles_m) * 128;
+      const int gm = m0 + row;
+      const uint32_t ab = it & 1;
+      if (s != cur_s) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int te = tid - 64;
+        if (te < 64) s_bias[te] = te < p.N ? p.bias[(long long)s * p.b_sstride + p.b_off + te] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_s = s;
+      }
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+      uint32_t v[64];
+      tmem_ld32(tmem + lane_base + ab * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem + lane_base + ab * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      wait_ld();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+      if (gm < p.M) {
+        if (p.out16) {
+          __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16;
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8) {
+            const int c = q8 * 8;
+            if (c + 8 <= p.N) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[c + 2 * i]) + s_bias[c + 2 * i]),
+                                   act_fixed<kAct>(p.act, __uint_as_float(v[c + 2 * i + 1]) + s_bias[c + 2 * i + 1]));
+              *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              for (int i = 0; i < 8; ++i)
+                if (c + i < p.N) dst[c + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[c + i]) + s_bias[c + i]));
+            }
+          }
+        } else {
+          float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < p.N) dst[i] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + s_bias[i]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem);
+}
+
 // =======================================================================================
 // Stored posteriors (BASELINE config 3) at batch sizes above the streaming kernel's 16 rows: the SAME per-sample
 // GEMM, but the weights are read by TMA straight from the fp32 `[S,P]` slab -- once, 4 B per parameter, which is
@@ -686,6 +829,29 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
   p.M = M; p.N = N; p.K = K; p.NT = (int)std::min<int64_t>(256, round_up(N, 64));
   p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
+  const int ka = act_class(act);
+  // narrow layer with many tiles: persistent kernel (DBX_NO_NARROW=1 disables)
+  const long long tiles = (long long)ns * cdiv(M, 128);
+  long long min_tiles = 1024;
+  if (const char* e = getenv("DBX_NARROW_MIN_TILES")) min_tiles = atoll(e);      // tests lower it to reach the kernel with small shapes
+  if (N <= 64 && tiles >= min_tiles && !(getenv("DBX_NO_NARROW") && getenv("DBX_NO_NARROW")[0] == '1')) {
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+    }
+    const int smem = kPStages * kPStageB + (int)sizeof(PBarriers) + 1024;
+    const int tiles_m = (int)cdiv(M, 128);
+    dim3 pgrid((unsigned)std::min<long long>(tiles, 2LL * num_sms));
+    auto gop = [&](auto kern) -> int {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+      kern<<<pgrid, kGThreads, smem, st>>>(tmA, tmW, p, ns, tiles_m);
+      return 0;
+    };
+    if (ka == 1 ? gop(dense_tc_narrow_kernel<1>) : ka == 0 ? gop(dense_tc_narrow_kernel<0>) : gop(dense_tc_narrow_kernel<-1>)) return 1;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
   dim3 grid((unsigned)cdiv(N, p.NT), (unsigned)cdiv(M, 128), (unsigned)ns);
   auto go = [&](auto kern, int ntmax) -> int {
     const int smem = (ntmax == 64 ? 3 : kGStages) * (16384 + (ntmax / 64) * 8192) + (int)sizeof(GBarriers) + 1024;
@@ -694,7 +860,6 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
     return 0;
   };
   int rc;
-  const int ka = act_class(act);
 #define DBX_GO(NTM) (ka == 1 ? go(dense_tc_kernel<NTM, 1>, NTM) : ka == 0 ? go(dense_tc_kernel<NTM, 0>, NTM) : go(dense_tc_kernel<NTM, -1>, NTM))
   if (p.NT <= 64) rc = DBX_GO(64);
   else if (p.NT <= 128) rc = DBX_GO(128);
