@@ -157,41 +157,44 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 
 // =======================================================================================
-// Persistent variant of dense_tc_kernel for NARROW layers (N <= 64: conv kernels with few output channels, run
-// through an im2col matrix).  Their tiles have one to five k-blocks, so a CTA per tile spent most of its life in
-// the serial chain TMEM alloc -> barrier init -> TMA -> MMA -> epilogue (config 4's first conv: 6 us per
-// 128 x 32 tile).  Here 2 CTAs per SM walk the (sample, m tile) list; the TMA ring, the two TMEM accumulators and
-// the epilogue of tile i overlap the loads and MMAs of tile i+1.
+// Persistent variant of dense_tc_kernel.  A CTA per tile spends most of a short tile's life in the serial chain
+// TMEM alloc -> barrier init -> TMA -> MMA -> epilogue (config 4's first conv: 6 us per 128 x 32 tile with one
+// k-block; the IBP GEMMs at B = 128: 50 us per CTA at 1.1 TB/s).  Here the CTAs (1 or 2 per SM) walk a contiguous range
+// of the (sample, m tile, n tile) list; the TMA ring, the two TMEM accumulators and the epilogue of tile i overlap the
+// loads and MMAs of tile i+1.  kNT = column tile (64 / 128 / 256).
 // =======================================================================================
-constexpr int kPStages = 4;
-constexpr int kPStageB = 24576;      // A block [128 x 64] 16 KB + W block [64 k x 64 n] 8 KB
-
 struct __align__(8) PBarriers {
-  uint64_t full[kPStages], empty[kPStages];
+  uint64_t full[4], empty[4];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
 
-template <int kAct>
-__global__ void __launch_bounds__(kGThreads, 2)
-dense_tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p, int ns,
-                       int tiles_m) {
-  __shared__ float s_bias[64];
+template <int kNT, int kAct>
+__global__ void __launch_bounds__(kGThreads, kNT == 256 ? 1 : 2)
+dense_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p, int ns,
+                        int tiles_m, int tiles_n) {
+  constexpr int kStB = 16384 + (kNT / 64) * 8192;
+  constexpr int kSt = kNT == 128 ? 3 : 4;
+  __shared__ float s_bias[kNT];
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  PBarriers* bars = (PBarriers*)(smem + kPStages * kPStageB);
+  PBarriers* bars = (PBarriers*)(smem + kSt * kStB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kb_n = (p.K + 63) / 64;
-  const long long total = (long long)ns * tiles_m;
-  // contiguous tile range per CTA: consecutive tiles are neighbouring row blocks of the same sample
+  const long long total = (long long)ns * tiles_m * tiles_n;
   const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
+  auto decode = [&](long long t, int& n0, int& m0, int& s) {
+    const int nt_i = (int)(t % tiles_n);
+    const long long r = t / tiles_n;
+    n0 = nt_i * kNT; m0 = (int)(r % tiles_m) * 128; s = (int)(r / tiles_m);
+  };
 
   if (tid == 0) {
-    for (int i = 0; i < kPStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < kSt; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<128>(smem_u32(&bars->tmem_slot));
+  if (warp == 1) tmem_alloc<2 * kNT>(smem_u32(&bars->tmem_slot));
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
   fence_before_sync();
   __syncthreads();
@@ -201,39 +204,44 @@ dense_tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0) {
     uint32_t g = 0;
     for (long long t = t_begin; t < t_end; ++t) {
-      const int s = (int)(t / tiles_m), m0 = (int)(t - (long long)s * tiles_m) * 128;
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int nblk = min(kNT, ((p.N - n0 + 63) / 64) * 64) / 64;
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
-        const uint32_t st = g % kPStages, ph = (g / kPStages) & 1;
+        const uint32_t st = g % kSt, ph = (g / kSt) & 1;
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->full[st]);
-          const uint32_t base = s_stage + st * kPStageB;
-          mbar_expect_tx(fb, kPStageB);
+          const uint32_t base = s_stage + st * kStB;
+          mbar_expect_tx(fb, 16384 + nblk * 8192);
           if (p.a_shared) tma_load_2d(base, &tmA, fb, kb * 64, m0);
           else tma_load_3d(base, &tmA, fb, kb * 64, m0, s);
-          tma_load_3d(base + 16384, &tmW, fb, 0, kb * 64, s);
+          for (int nb = 0; nb < nblk; ++nb) tma_load_3d(base + 16384 + nb * 8192, &tmW, fb, n0 + nb * 64, kb * 64, s);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
     uint32_t g = 0, it = 0;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
+      const uint32_t idesc = make_idesc_bf16(128, nt, 0, 1);
       const uint32_t ab = it & 1;
       mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
       fence_after_sync();
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
-        const uint32_t st = g % kPStages, ph = (g / kPStages) & 1;
+        const uint32_t st = g % kSt, ph = (g / kSt) & 1;
         mbar_wait(smem_u32(&bars->full[st]), ph);
         if (elect_one()) {
-          const uint32_t a16 = ((s_stage + st * kPStageB) & 0x3FFFF) >> 4;
+          const uint32_t a16 = ((s_stage + st * kStB) & 0x3FFFF) >> 4;
           const uint32_t a_lo = a16 | (1u << 16);
           const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
           const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
           for (int kk = 0; kk < ksteps; ++kk)
-            mma_ss_lh(tmem + ab * 64, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+            mma_ss_lh(tmem + ab * kNT, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
           mma_commit(smem_u32(&bars->empty[st]));
           if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
         }
@@ -245,57 +253,63 @@ dense_tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int row = gq * 32 + lane;
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
     uint32_t it = 0;
-    int cur_s = -1;
+    int cur_s = -1, cur_n0 = -1;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
-      const int s = (int)(t / tiles_m), m0 = (int)(t - (long long)s * tiles_m) * 128;
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
       const int gm = m0 + row;
       const uint32_t ab = it & 1;
-      if (s != cur_s) {
+      if (s != cur_s || n0 != cur_n0) {      // this (sample, column tile)'s bias -> smem (per-column global loads stall the epilogue)
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int te = tid - 64;
-        if (te < 64) s_bias[te] = te < p.N ? p.bias[(long long)s * p.b_sstride + p.b_off + te] : 0.f;
+        for (int c = tid - 64; c < kNT; c += 128) s_bias[c] = (n0 + c < p.N) ? p.bias[(long long)s * p.b_sstride + p.b_off + n0 + c] : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        cur_s = s;
+        cur_s = s; cur_n0 = n0;
       }
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
-      uint32_t v[64];
-      tmem_ld32(tmem + lane_base + ab * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld32(tmem + lane_base + ab * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-      wait_ld();
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
-      if (gm < p.M) {
-        if (p.out16) {
-          __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16;
+      for (int c0 = 0; c0 < nt; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + ab * kNT + c0, v);
+        wait_ld();
+        if (c0 + 32 >= nt) {   // the whole accumulator is in registers / stored: the MMA warp may reuse it
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+        }
+        if (gm < p.M) {
+          if (p.out16) {
+            __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0 + c0;
 #pragma unroll
-          for (int q8 = 0; q8 < 8; ++q8) {
-            const int c = q8 * 8;
-            if (c + 8 <= p.N) {
-              uint32_t w[4];
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int c = n0 + c0 + q4 * 8;
+              if (c + 8 <= p.N) {
+                uint32_t w[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[c + 2 * i]) + s_bias[c + 2 * i]),
-                                   act_fixed<kAct>(p.act, __uint_as_float(v[c + 2 * i + 1]) + s_bias[c + 2 * i + 1]));
-              *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
-            } else {
-              for (int i = 0; i < 8; ++i)
-                if (c + i < p.N) dst[c + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[c + i]) + s_bias[c + i]));
+                for (int i = 0; i < 4; ++i)
+                  w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + s_bias[c0 + q4 * 8 + 2 * i]),
+                                     act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + s_bias[c0 + q4 * 8 + 2 * i + 1]));
+                *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              } else {
+                for (int i = 0; i < 8; ++i)
+                  if (c + i < p.N) dst[q4 * 8 + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + i]) + s_bias[c0 + q4 * 8 + i]));
+              }
+            }
+          } else {
+            float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = n0 + c0 + i;
+              if (c < p.N) dst[c] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + s_bias[c0 + i]);
             }
           }
-        } else {
-          float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i < p.N) dst[i] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + s_bias[i]);
         }
       }
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<128>(tmem);
+  if (warp == 1) tmem_dealloc<2 * kNT>(tmem);
 }
 
 // =======================================================================================
@@ -830,27 +844,34 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
   p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
   const int ka = act_class(act);
-  // narrow layer with many tiles: persistent kernel (DBX_NO_NARROW=1 disables)
-  const long long tiles = (long long)ns * cdiv(M, 128);
-  long long min_tiles = 1024;
-  if (const char* e = getenv("DBX_NARROW_MIN_TILES")) min_tiles = atoll(e);      // tests lower it to reach the kernel with small shapes
-  if (N <= 64 && tiles >= min_tiles && !(getenv("DBX_NO_NARROW") && getenv("DBX_NO_NARROW")[0] == '1')) {
-    static int num_sms = 0;
-    if (!num_sms) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+  // enough tiles to keep persistent CTAs busy: dense_tc_persist_kernel (DBX_NO_PERSIST=1 disables; DBX_PERSIST_MIN_TILES
+  // lowers the threshold so that tests reach it with small shapes)
+  {
+    const int tiles_m = (int)cdiv(M, 128), tiles_n = (int)cdiv(N, p.NT);
+    const long long tiles = (long long)ns * tiles_m * tiles_n;
+    long long min_tiles = 296;
+    if (const char* e = getenv("DBX_PERSIST_MIN_TILES")) min_tiles = atoll(e);
+    if (tiles >= min_tiles && !(getenv("DBX_NO_PERSIST") && getenv("DBX_NO_PERSIST")[0] == '1')) {
+      static int num_sms = 0;
+      if (!num_sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+      }
+      const int ntc = p.NT <= 64 ? 64 : (p.NT <= 128 ? 128 : 256);
+      const int smem = (ntc == 128 ? 3 : 4) * (16384 + (ntc / 64) * 8192) + (int)sizeof(PBarriers) + 1024;
+      dim3 pgrid((unsigned)std::min<long long>(tiles, (ntc == 256 ? 1LL : 2LL) * num_sms));
+      auto gop = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+        kern<<<pgrid, kGThreads, smem, st>>>(tmA, tmW, p, ns, tiles_m, tiles_n);
+        return 0;
+      };
+#define DBX_GOP(NTM) (ka == 1 ? gop(dense_tc_persist_kernel<NTM, 1>) : ka == 0 ? gop(dense_tc_persist_kernel<NTM, 0>) : gop(dense_tc_persist_kernel<NTM, -1>))
+      const int prc = ntc == 64 ? DBX_GOP(64) : (ntc == 128 ? DBX_GOP(128) : DBX_GOP(256));
+#undef DBX_GOP
+      if (prc) return 1;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
-    const int smem = kPStages * kPStageB + (int)sizeof(PBarriers) + 1024;
-    const int tiles_m = (int)cdiv(M, 128);
-    dim3 pgrid((unsigned)std::min<long long>(tiles, 2LL * num_sms));
-    auto gop = [&](auto kern) -> int {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
-      kern<<<pgrid, kGThreads, smem, st>>>(tmA, tmW, p, ns, tiles_m);
-      return 0;
-    };
-    if (ka == 1 ? gop(dense_tc_narrow_kernel<1>) : ka == 0 ? gop(dense_tc_narrow_kernel<0>) : gop(dense_tc_narrow_kernel<-1>)) return 1;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
   }
   dim3 grid((unsigned)cdiv(N, p.NT), (unsigned)cdiv(M, 128), (unsigned)ns);
   auto go = [&](auto kern, int ntmax) -> int {

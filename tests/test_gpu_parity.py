@@ -684,10 +684,10 @@ def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
     np.testing.assert_allclose(d2.cpu().numpy() / n, i2.cpu().numpy() / n, rtol=0, atol=1.5e-3)
     np.testing.assert_allclose(d1.cpu().numpy() / n, f1.cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
     assert _lib_launches() - launches_direct > 0
-    # the persistent narrow-layer GEMM (N <= 64; normally only for >= 1024 tiles) on the im2col'd convs of this model
-    monkeypatch.setenv("DBX_NARROW_MIN_TILES", "1")
+    # the persistent GEMM kernel (normally only for >= 296 tiles) on every GEMM of this model
+    monkeypatch.setenv("DBX_PERSIST_MIN_TILES", "1")
     p1, p2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
-    monkeypatch.setenv("DBX_NO_NARROW", "1")
+    monkeypatch.setenv("DBX_NO_PERSIST", "1")
     q1, q2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     np.testing.assert_allclose(p1.cpu().numpy() / n, q1.cpu().numpy() / n, rtol=0, atol=2e-4)
     np.testing.assert_allclose(p2.cpu().numpy() / n, q2.cpu().numpy() / n, rtol=0, atol=2e-4)
