@@ -129,6 +129,10 @@ bool conv_tc_eligible(const Layer& L);
 int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared, const __nv_bfloat16* W16, long long w_sstride_elems,
                    int ldw, int ns, int NB, const Layer& L, const float* bias, long long b_sstride, long long b_off, int act,
                    __nv_bfloat16* out, long long o_sstride, cudaStream_t st);
+bool ibp_tc_eligible(int N, int K);
+int ibp_tc_launch(const __nv_bfloat16* Amu, const __nv_bfloat16* Ar, long long a_sstride, int a_shared, const __nv_bfloat16* Wbase,
+                  long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride, long long b_off,
+                  int act, __nv_bfloat16* n_mu, __nv_bfloat16* n_r, long long n_sstride, cudaStream_t st);
 int im2col_launch(const __nv_bfloat16* in, long long in_sstride, __nv_bfloat16* out, long long out_sstride, int ns, int NB,
                   const Layer& L, int Kp, cudaStream_t st);
 

@@ -767,6 +767,201 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
+
+// =======================================================================================
+// One hidden Dense layer of the interval forward (ibp.cuh) in ONE kernel: centre MU = A_mu W + b and radius
+// R = A_r |W| accumulate side by side in TMEM (2 x 128 columns per buffer, two buffers), |W| is formed INSIDE the SM
+// from the W block TMA delivered (sign bits cleared, same swizzled layout) by four converter warps, and the epilogue
+// combines them (u = act(MU + R), l = act(MU - R) -> next centre (u + l)/2 and radius (u - l)/2, bf16).  Before: a
+// pass that wrote |W16| for the whole chunk, two GEMM launches writing fp32 MU / R, and a combine pass.
+//   warp 0 producer (A_mu, A_r, W blocks), warp 1 MMA issuer (8 MMAs per k-block), warps 2-5 converter, warps 6-9 epilogue
+// Persistent, one CTA per SM (3 stages x 64 KB), tiles = (sample, m tile, 128-column tile).
+// =======================================================================================
+constexpr int kIStages = 3;
+constexpr int kIStageB = 65536;      // A_mu 16 KB | A_r 16 KB | W [64 k x 128 n] 16 KB | |W| 16 KB
+constexpr int kINT = 128;
+constexpr int kIThreads = 320;
+
+struct __align__(8) IBarriers {
+  uint64_t full[kIStages], conv[kIStages], empty[kIStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
+
+struct IbpGemmParams {
+  int M, N, K, ns, tiles_m, tiles_n, a_shared, act;
+  const float* bias; long long b_sstride, b_off;
+  __nv_bfloat16* n_mu; __nv_bfloat16* n_r; long long n_sstride;
+};
+
+__global__ void __launch_bounds__(kIThreads, 1)
+ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__ CUtensorMap tmAr, const __grid_constant__ CUtensorMap tmW,
+              const IbpGemmParams p) {
+  __shared__ float s_bias[kINT];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  IBarriers* bars = (IBarriers*)(smem + kIStages * kIStageB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kb_n = (p.K + 63) / 64;
+  const long long total = (long long)p.ns * p.tiles_m * p.tiles_n;
+  const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
+  auto decode = [&](long long t, int& n0, int& m0, int& s) {
+    const int nt_i = (int)(t % p.tiles_n);
+    const long long r = t / p.tiles_n;
+    n0 = nt_i * kINT; m0 = (int)(r % p.tiles_m) * 128; s = (int)(r / p.tiles_m);
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < kIStages; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->conv[i]), 4); mbar_init(smem_u32(&bars->empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmAmu); prefetch_tmap(&tmAr); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    uint32_t g = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kIStages, ph = (g / kIStages) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          const uint32_t base = s_stage + st * kIStageB;
+          mbar_expect_tx(fb, 3 * 16384);
+          if (p.a_shared) { tma_load_2d(base, &tmAmu, fb, kb * 64, m0); tma_load_2d(base + 16384, &tmAr, fb, kb * 64, m0); }
+          else { tma_load_3d(base, &tmAmu, fb, kb * 64, m0, s); tma_load_3d(base + 16384, &tmAr, fb, kb * 64, m0, s); }
+          for (int nb = 0; nb < 2; ++nb) tma_load_3d(base + 32768 + nb * 8192, &tmW, fb, n0 + nb * 64, kb * 64, s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t idesc = make_idesc_bf16(128, kINT, 0, 1);
+    uint32_t g = 0, it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
+      fence_after_sync();
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kIStages, ph = (g / kIStages) & 1;
+        mbar_wait(smem_u32(&bars->full[st]), ph);
+        mbar_wait(smem_u32(&bars->conv[st]), ph);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a16 = ((s_stage + st * kIStageB) & 0x3FFFF) >> 4;
+          const uint32_t amu = a16 | (1u << 16), ar = (a16 + (16384 >> 4)) | (1u << 16);
+          const uint32_t bw = (a16 + (32768 >> 4)) | ((8192u >> 4) << 16), babs = (a16 + (49152 >> 4)) | ((8192u >> 4) << 16);
+          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+          for (int kk = 0; kk < ksteps; ++kk) {
+            mma_ss_lh(tmem + ab * 256, amu + kk * 2, kDescHi128, bw + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+            mma_ss_lh(tmem + ab * 256 + kINT, ar + kk * 2, kDescHi128, babs + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+          }
+          mma_commit(smem_u32(&bars->empty[st]));
+          if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ---- converter: |W| block = W block with the sign bits cleared (identical layout)
+    const int tc = tid - 64;
+    uint32_t g = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kIStages, ph = (g / kIStages) & 1;
+        mbar_wait(smem_u32(&bars->full[st]), ph);      // the stage's `empty` wait was the producer's: the |W| slot is free too
+        const uint4* src = reinterpret_cast<const uint4*>(smem + st * kIStageB + 32768);
+        uint4* dst = reinterpret_cast<uint4*>(smem + st * kIStageB + 49152);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 v = src[i * 128 + tc];
+          v.x &= 0x7FFF7FFFu; v.y &= 0x7FFF7FFFu; v.z &= 0x7FFF7FFFu; v.w &= 0x7FFF7FFFu;
+          dst[i * 128 + tc] = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->conv[st]));
+      }
+    }
+  } else {
+    // ---- epilogue
+    const int gq = warp & 3;
+    const int row = gq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    uint32_t it = 0;
+    int cur_s = -1, cur_n0 = -1;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int gm = m0 + row;
+      const uint32_t ab = it & 1;
+      if (s != cur_s || n0 != cur_n0) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int te = tid - 192;
+        if (te < kINT) s_bias[te] = (n0 + te < p.N) ? p.bias[(long long)s * p.b_sstride + p.b_off + n0 + te] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_s = s; cur_n0 = n0;
+      }
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+      __nv_bfloat16* dmu = p.n_mu + (long long)s * p.n_sstride + (long long)gm * p.N + n0;
+      __nv_bfloat16* dr = p.n_r + (long long)s * p.n_sstride + (long long)gm * p.N + n0;
+      for (int c0 = 0; c0 < kINT; c0 += 32) {
+        uint32_t vm[32], vr[32];
+        tmem_ld32(tmem + lane_base + ab * 256 + c0, vm);
+        tmem_ld32(tmem + lane_base + ab * 256 + kINT + c0, vr);
+        wait_ld();
+        if (c0 + 32 >= kINT) {
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+        }
+        if (gm < p.M) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int c = n0 + c0 + q4 * 8;
+            uint32_t wm[4], wr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float cm[2], cr[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float mu = __uint_as_float(vm[q4 * 8 + 2 * i + h]) + s_bias[c0 + q4 * 8 + 2 * i + h];
+                const float rr = __uint_as_float(vr[q4 * 8 + 2 * i + h]);
+                const float au = apply_act(p.act, mu + rr), al = apply_act(p.act, mu - rr);
+                cm[h] = (au + al) / 2.f; cr[h] = (au - al) / 2.f;
+              }
+              wm[i] = pack_bf16x2(cm[0], cm[1]); wr[i] = pack_bf16x2(cr[0], cr[1]);
+            }
+            if (c + 8 <= p.N) {
+              *reinterpret_cast<uint4*>(dmu + c0 + q4 * 8) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+              *reinterpret_cast<uint4*>(dr + c0 + q4 * 8) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+            } else {
+              const __nv_bfloat16* hm = reinterpret_cast<const __nv_bfloat16*>(wm);
+              const __nv_bfloat16* hr = reinterpret_cast<const __nv_bfloat16*>(wr);
+              for (int i = 0; i < 8; ++i)
+                if (c + i < p.N) { dmu[c0 + q4 * 8 + i] = hm[i]; dr[c0 + q4 * 8 + i] = hr[i]; }
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 // NHWC bf16 activations -> im2col rows [n*Ho*Wo][kh*kw*C (padded to Kp)] so that Conv2D becomes the GEMM above
 // (same (kh, kw, cin) ordering as the HWIO kernel flattened to [kh*kw*cin, cout]).
 __global__ void im2col_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long in_sstride, __nv_bfloat16* __restrict__ out,
@@ -1012,6 +1207,55 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
   };
   const int ka = act_class(act);
   if (ka == 1 ? go(conv_tc_kernel<1>) : ka == 0 ? go(conv_tc_kernel<0>) : go(conv_tc_kernel<-1>)) return 1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+bool ibp_tc_eligible(int N, int K) {
+  if (!g_tc_ok || !get_encode_fn()) return false;
+  if ((K & 7) || (N & 7)) return false;
+  if (const char* e = getenv("DBX_NO_IBP_TC")) if (e[0] == '1') return false;
+  return true;
+}
+
+// One hidden layer of the interval forward on tensor cores (see ibp_tc_kernel).  A_mu / A_r: bf16 [ns or 1][M][K] (K % 8 == 0);
+// outputs bf16 [ns][M][N] (N % 8 == 0) at n_sstride.  Returns 1 when not applicable.
+int ibp_tc_launch(const __nv_bfloat16* Amu, const __nv_bfloat16* Ar, long long a_sstride, int a_shared, const __nv_bfloat16* Wbase,
+                  long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride, long long b_off,
+                  int act, __nv_bfloat16* n_mu, __nv_bfloat16* n_r, long long n_sstride, cudaStream_t st) {
+  if (!ibp_tc_eligible(N, K) || (a_sstride & 7) || (n_sstride & 7)) return 1;
+  CUtensorMap tmAmu, tmAr, tmW;
+  for (int which = 0; which < 2; ++which) {
+    const __nv_bfloat16* A = which ? Ar : Amu;
+    CUtensorMap* tm = which ? &tmAr : &tmAmu;
+    if (a_shared) {
+      uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, sb[1] = {(uint64_t)K * 2};
+      uint32_t b[2] = {64, 128};
+      if (!make_tmap_bf16(tm, (void*)A, 2, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    } else {
+      uint64_t d[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)K * 2, (uint64_t)a_sstride * 2};
+      uint32_t b[3] = {64, 128, 1};
+      if (!make_tmap_bf16(tm, (void*)A, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+  }
+  {
+    uint64_t d[3] = {(uint64_t)N, (uint64_t)K, (uint64_t)ns}, sb[2] = {(uint64_t)ldw * 2, (uint64_t)w_sstride_elems * 2};
+    uint32_t b[3] = {64, 64, 1};
+    if (!make_tmap_bf16(&tmW, (void*)Wbase, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  IbpGemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.ns = ns; p.tiles_m = (int)cdiv(M, 128); p.tiles_n = (int)cdiv(N, kINT); p.a_shared = a_shared; p.act = act;
+  p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.n_mu = n_mu; p.n_r = n_r; p.n_sstride = n_sstride;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+  }
+  const int smem = kIStages * kIStageB + (int)sizeof(IBarriers) + 1024;
+  if (cudaFuncSetAttribute(ibp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  const long long total = (long long)ns * p.tiles_m * p.tiles_n;
+  dim3 grid((unsigned)std::min<long long>(total, (long long)num_sms));
+  ibp_tc_kernel<<<grid, kIThreads, smem, st>>>(tmAmu, tmAr, tmW, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -145,6 +145,16 @@ ibp_dense_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_
   }
 }
 
+// |W16| of one parameter range [off, off + len) of every sample (units of 8 bf16)
+__global__ void abs_bf16_range_kernel(const uint4* __restrict__ W, uint4* __restrict__ Wabs, int64_t sstride8, int64_t off8, int64_t len8) {
+  const int64_t base = (int64_t)blockIdx.y * sstride8 + off8;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < len8; e += (int64_t)gridDim.x * blockDim.x) {
+    uint4 v = W[base + e];
+    v.x &= 0x7FFF7FFFu; v.y &= 0x7FFF7FFFu; v.z &= 0x7FFF7FFFu; v.w &= 0x7FFF7FFFu;
+    Wabs[base + e] = v;
+  }
+}
+
 // tensor-core back end: MU (bias added) and R come from two dense_tc_kernel launches as fp32 [s][M][N]
 __global__ void ibp_combine_kernel(const float* __restrict__ MU, const float* __restrict__ R, int64_t total_per_s, int M, int N,
                                    __nv_bfloat16* __restrict__ n_mu, __nv_bfloat16* __restrict__ n_r, int64_t n_sstride, IbpOut o) {
@@ -214,6 +224,20 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   DBX_CUDA(cudaMemsetAsync(zero_bias, 0, zb_b, st));
   if (sink.counts && !sink.accumulate) DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, sink.counts, B);
 
+  // hidden layers that the fused interval kernel takes need no |W16| copy
+  int64_t abs_off = 0, abs_len = kBf16 ? m->P16 : 0;
+  std::vector<char> fused_layer(m->layers.size(), 0);
+  if (use_tc) {
+    bool all_hidden = true;
+    for (int li = 0; li < (int)m->layers.size(); ++li) {
+      const Layer& L = m->layers[li];
+      if (!L.has_w || li == m->last_weighted) continue;
+      fused_layer[li] = ibp_tc_eligible(L.units, (int)L.in_feat) && (act_b / sizeof(T)) % 8 == 0;
+      all_hidden = all_hidden && fused_layer[li];
+    }
+    const Layer& LL = m->layers[m->last_weighted];
+    if (all_hidden && LL.w16_off % 8 == 0 && (LL.w_rows * LL.w_cols_pad) % 8 == 0) { abs_off = LL.w16_off; abs_len = LL.w_rows * LL.w_cols_pad; }
+  }
   for (int64_t c0 = 0; c0 < n; c0 += ns) {
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
@@ -221,8 +245,13 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     if (kBf16) {
       if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
       Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
-      if (use_tc)
-        DBX_LAUNCH(abs_bf16_kernel, grid_for((int64_t)nc * m->P16 / 8), 256, 0, st, (const uint4*)Wc, (uint4*)Wabs, (int64_t)nc * m->P16 / 8);
+      if (use_tc) {  // |W16| for the layers that run as two GEMMs: all of them, or (hidden layers fused) the output layer alone
+        if (abs_len == m->P16)
+          DBX_LAUNCH(abs_bf16_kernel, grid_for((int64_t)nc * m->P16 / 8), 256, 0, st, (const uint4*)Wc, (uint4*)Wabs, (int64_t)nc * m->P16 / 8);
+        else if (abs_len > 0)
+          DBX_LAUNCH(abs_bf16_range_kernel, dim3((unsigned)std::min<int64_t>(cdiv(abs_len / 8, 256), 1024), (unsigned)nc), 256, 0, st,
+                     (const uint4*)Wc, (uint4*)Wabs, m->P16 / 8, abs_off / 8, abs_len / 8);
+      }
     } else if (src.stored) {
       Wbase = (const T*)m->slab; w_sstride = m->slab_stride; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
       Bbase = m->slab; b_sstride = m->slab_stride;
@@ -247,7 +276,14 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
       T* n_mu = abuf[2 * bi]; T* n_r = abuf[2 * bi + 1];
       prof_begin(st);
       bool done = false;
-      if (kBf16 && use_tc && L.in_feat % 8 == 0 && (last || L.units % 8 == 0) && (size_t)L.units * 4 <= zb_b) {
+      if (kBf16 && use_tc && !last && fused_layer[li]) {
+        // hidden layer: centre + radius + combine in one kernel, |W| formed in the SM (no fallback: |W16| was not written for it)
+        DBX_CHECK(ibp_tc_launch((const __nv_bfloat16*)cur_mu, (const __nv_bfloat16*)cur_r, cur_ss, cur_ss == 0 ? 1 : 0,
+                                (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff,
+                                L.act, (__nv_bfloat16*)n_mu, (__nv_bfloat16*)n_r, act_ss, st) == 0,
+                  "fused interval layer %d failed to launch", li);
+        done = true; g_used_tc = true;
+      } else if (kBf16 && use_tc && L.in_feat % 8 == 0 && (last || L.units % 8 == 0) && (size_t)L.units * 4 <= zb_b) {
         const int shared = cur_ss == 0 ? 1 : 0;
         const int rc1 = dense_tc_launch((const __nv_bfloat16*)cur_mu, cur_ss, (int)L.in_feat, shared, (const __nv_bfloat16*)Wbase + woff,
                                         w_sstride, ldw, nc, (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff, DBX_ACT_LINEAR,

@@ -612,6 +612,27 @@ def test_ibp_properties_and_bf16(oracle, monkeypatch):
     np.testing.assert_allclose(s["lower"].cpu().numpy(), f["lower"].cpu().numpy(), rtol=1e-6, atol=1e-5)
 
 
+@pytest.mark.parametrize("dims,B,n", [([784, 256, 256, 10], 200, 12), ([784, 512, 10], 128, 300), ([104, 72, 200, 136, 10], 130, 5),
+                                        ([64, 1024, 10], 1, 3)])
+def test_ibp_fused_layer_is_bit_identical_to_two_gemms(oracle, monkeypatch, dims, B, n):
+    """ibp_tc_kernel (centre, radius and the interval combine of a hidden layer in one launch, |W| formed in the SM) against
+    the two dense_tc launches + ibp_combine_kernel it replaces: same MMA order, same epilogue arithmetic -> same bits.
+    Ragged M / N / K tails and the 256-sample chunk boundary (n = 300) included."""
+    L, eng, mean, std = _mlp_engine(dims, oracle, sigma_scale=0.3)
+    x = oracle.synthetic_x((B, dims[0]), seed=16)
+    labels = np.random.Generator(np.random.Philox(18)).integers(0, dims[-1], size=B).astype(np.int32)
+    want = ("worst", "lower", "upper", "counts")
+    monkeypatch.setenv("DBX_NO_IBP_TC", "1")
+    a = eng.ibp_predict(x, 0.004, labels, n, seed=9, mode="bf16", want=want)
+    monkeypatch.setenv("DBX_NO_IBP_TC", "0")
+    k0 = _lib_launches()
+    b = eng.ibp_predict(x, 0.004, labels, n, seed=9, mode="bf16", want=want)
+    assert _lib_launches() - k0 > 0
+    assert eng.last_path() == "generic_tc"
+    for k in want:
+        np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy())
+
+
 def test_massart_with_ibp(tmp_path, oracle):
     import deepbayes_b200 as db
     from deepbayes_b200.analyzers import verifiers
