@@ -975,6 +975,8 @@ int dbx_destroy(dbx_handle h) {
   cudaFree(h->d_x); cudaFree(h->d_s1); cudaFree(h->d_s2);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_posterior) cudaEventDestroy(h->ev_posterior);
+  if (h->ibp_side) cudaStreamDestroy(h->ibp_side);
+  for (cudaEvent_t e : h->ibp_ev) if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }

@@ -76,6 +76,8 @@ struct dbx_model {
   float* d_s1 = nullptr; float* d_s2 = nullptr; size_t d_s_bytes = 0;
   cudaStream_t own_stream = nullptr;
   void* fused_state = nullptr;  // owned by fused_mlp.cu
+  cudaStream_t ibp_side = nullptr;  // interval forward: weights of chunk c+1 are drawn here while chunk c is in the GEMMs
+  cudaEvent_t ibp_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // entry, sampled[2], consumed[2]
 };
 
 namespace dbx {

@@ -774,16 +774,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // from the W block TMA delivered (sign bits cleared, same swizzled layout) by four converter warps, and the epilogue
 // combines them (u = act(MU + R), l = act(MU - R) -> next centre (u + l)/2 and radius (u - l)/2, bf16).  Before: a
 // pass that wrote |W16| for the whole chunk, two GEMM launches writing fp32 MU / R, and a combine pass.
-//   warp 0 producer (A_mu, A_r, W blocks), warp 1 MMA issuer (8 MMAs per k-block), warps 2-5 converter, warps 6-9 epilogue
-// Persistent, one CTA per SM (3 stages x 64 KB), tiles = (sample, m tile, 128-column tile).
+//   warp 0 producer (A_mu, A_r, W blocks), warp 1 MMA issuer (8 MMAs per k-block), warps 2-5 converter, warps 6.. epilogue
+// Persistent, one CTA per SM (TMA ring 4 x 48 KB + |W| ring 2 x 16 KB), tiles = (sample, m tile, 128-column tile).
 // =======================================================================================
-constexpr int kIStages = 3;
-constexpr int kIStageB = 65536;      // A_mu 16 KB | A_r 16 KB | W [64 k x 128 n] 16 KB | |W| 16 KB
+constexpr int kIStages = 3;          // TMA ring (4 measured no faster; the space is the epilogue's staging)
+constexpr int kIStageB = 49152;      // A_mu 16 KB | A_r 16 KB | W [64 k x 128 n] 16 KB
+constexpr int kIAbs = 2;             // |W| ring (16 KB slots): written by the converter warps, separate so that the TMA ring is 4 deep
+constexpr int kIAbsB = 16384;
+constexpr int kIOutB = 4 * 8192;     // per epilogue warp: [32 rows x 64 columns] bf16 boxes of the next centre and radius, for the TMA stores
 constexpr int kINT = 128;
-constexpr int kIThreads = 320;
+constexpr int kIEpiWarps = 4;      // one per TMEM lane quarter
+constexpr int kIThreads = 192 + 32 * kIEpiWarps;
 
 struct __align__(8) IBarriers {
-  uint64_t full[kIStages], conv[kIStages], empty[kIStages];
+  uint64_t full[kIStages], empty[kIStages], conv[kIAbs], abs_empty[kIAbs];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
@@ -794,13 +798,16 @@ struct IbpGemmParams {
   __nv_bfloat16* n_mu; __nv_bfloat16* n_r; long long n_sstride;
 };
 
+template <int kAct>
 __global__ void __launch_bounds__(kIThreads, 1)
 ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__ CUtensorMap tmAr, const __grid_constant__ CUtensorMap tmW,
-              const IbpGemmParams p) {
-  __shared__ float s_bias[kINT];
+              const __grid_constant__ CUtensorMap tmOmu, const __grid_constant__ CUtensorMap tmOr, const IbpGemmParams p) {
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  IBarriers* bars = (IBarriers*)(smem + kIStages * kIStageB);
+  uint8_t* abs_ring = smem + kIStages * kIStageB;
+  uint8_t* stage_out = abs_ring + kIAbs * kIAbsB;
+  float* s_bias = (float*)(stage_out + kIOutB);
+  IBarriers* bars = (IBarriers*)(s_bias + kINT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kb_n = (p.K + 63) / 64;
   const long long total = (long long)p.ns * p.tiles_m * p.tiles_n;
@@ -812,14 +819,13 @@ ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__
   };
 
   if (tid == 0) {
-    for (int i = 0; i < kIStages; ++i) {
-      mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->conv[i]), 4); mbar_init(smem_u32(&bars->empty[i]), 1);
-    }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    for (int i = 0; i < kIStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < kIAbs; ++i) { mbar_init(smem_u32(&bars->conv[i]), 4); mbar_init(smem_u32(&bars->abs_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kIEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem_slot));
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmAmu); prefetch_tmap(&tmAr); prefetch_tmap(&tmW); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmAmu); prefetch_tmap(&tmAr); prefetch_tmap(&tmW); prefetch_tmap(&tmOmu); prefetch_tmap(&tmOr); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -854,19 +860,26 @@ ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__
       fence_after_sync();
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
         const uint32_t st = g % kIStages, ph = (g / kIStages) & 1;
+        const uint32_t aj = g % kIAbs, aph = (g / kIAbs) & 1;
         mbar_wait(smem_u32(&bars->full[st]), ph);
-        mbar_wait(smem_u32(&bars->conv[st]), ph);
+        fence_after_sync();
+        const uint32_t a16 = ((s_stage + st * kIStageB) & 0x3FFFF) >> 4;
+        const uint32_t amu = a16 | (1u << 16), ar = (a16 + (16384 >> 4)) | (1u << 16);
+        const uint32_t bw = (a16 + (32768 >> 4)) | ((8192u >> 4) << 16);
+        const uint32_t babs = (((s_stage + kIStages * kIStageB + aj * kIAbsB) & 0x3FFFF) >> 4) | ((8192u >> 4) << 16);
+        const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+        // the centre product needs only what TMA delivered: issue it first, the |W| conversion runs meanwhile
+        if (elect_one())
+          for (int kk = 0; kk < ksteps; ++kk)
+            mma_ss_lh(tmem + ab * 256, amu + kk * 2, kDescHi128, bw + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+        __syncwarp();
+        mbar_wait(smem_u32(&bars->conv[aj]), aph);
         fence_after_sync();
         if (elect_one()) {
-          const uint32_t a16 = ((s_stage + st * kIStageB) & 0x3FFFF) >> 4;
-          const uint32_t amu = a16 | (1u << 16), ar = (a16 + (16384 >> 4)) | (1u << 16);
-          const uint32_t bw = (a16 + (32768 >> 4)) | ((8192u >> 4) << 16), babs = (a16 + (49152 >> 4)) | ((8192u >> 4) << 16);
-          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
-          for (int kk = 0; kk < ksteps; ++kk) {
-            mma_ss_lh(tmem + ab * 256, amu + kk * 2, kDescHi128, bw + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+          for (int kk = 0; kk < ksteps; ++kk)
             mma_ss_lh(tmem + ab * 256 + kINT, ar + kk * 2, kDescHi128, babs + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
-          }
           mma_commit(smem_u32(&bars->empty[st]));
+          mma_commit(smem_u32(&bars->abs_empty[aj]));
           if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
         }
         __syncwarp();
@@ -879,9 +892,11 @@ ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__
     for (long long t = t_begin; t < t_end; ++t) {
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
         const uint32_t st = g % kIStages, ph = (g / kIStages) & 1;
-        mbar_wait(smem_u32(&bars->full[st]), ph);      // the stage's `empty` wait was the producer's: the |W| slot is free too
+        const uint32_t aj = g % kIAbs, aph = (g / kIAbs) & 1;
+        mbar_wait(smem_u32(&bars->abs_empty[aj]), aph ^ 1);   // the radius MMAs that read this |W| slot have completed
+        mbar_wait(smem_u32(&bars->full[st]), ph);
         const uint4* src = reinterpret_cast<const uint4*>(smem + st * kIStageB + 32768);
-        uint4* dst = reinterpret_cast<uint4*>(smem + st * kIStageB + 49152);
+        uint4* dst = reinterpret_cast<uint4*>(abs_ring + aj * kIAbsB);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint4 v = src[i * 128 + tc];
@@ -890,46 +905,50 @@ ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->conv[st]));
+        if (lane == 0) mbar_arrive(smem_u32(&bars->conv[aj]));
       }
     }
   } else {
     // ---- epilogue
-    const int gq = warp & 3;
-    const int row = gq * 32 + lane;
+    const int gq = warp & 3;      // TMEM lane quarter
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
     uint32_t it = 0;
     int cur_s = -1, cur_n0 = -1;
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       int n0, m0, s;
       decode(t, n0, m0, s);
-      const int gm = m0 + row;
       const uint32_t ab = it & 1;
       if (s != cur_s || n0 != cur_n0) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int te = tid - 192;
-        if (te < kINT) s_bias[te] = (n0 + te < p.N) ? p.bias[(long long)s * p.b_sstride + p.b_off + n0 + te] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kIEpiWarps) : "memory");
+        for (int te = tid - 192; te < kINT; te += 32 * kIEpiWarps) s_bias[te] = (n0 + te < p.N) ? p.bias[(long long)s * p.b_sstride + p.b_off + n0 + te] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kIEpiWarps) : "memory");
         cur_s = s; cur_n0 = n0;
       }
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
-      __nv_bfloat16* dmu = p.n_mu + (long long)s * p.n_sstride + (long long)gm * p.N + n0;
-      __nv_bfloat16* dr = p.n_r + (long long)s * p.n_sstride + (long long)gm * p.N + n0;
-      for (int c0 = 0; c0 < kINT; c0 += 32) {
-        uint32_t vm[32], vr[32];
-        tmem_ld32(tmem + lane_base + ab * 256 + c0, vm);
-        tmem_ld32(tmem + lane_base + ab * 256 + kINT + c0, vr);
-        wait_ld();
-        if (c0 + 32 >= kINT) {
-          fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
-        }
-        if (gm < p.M) {
+      // 64 columns at a time: the warp's 32 rows x 64 columns of next centre / radius go to its staging boxes in shared memory
+      // (128-byte rows, 16-byte chunks XOR-swizzled by row so that the 32 row-wise writes of a warp spread over all banks),
+      // and one lane hands both boxes to TMA: full-line writes, M / N tails clipped by the tensor map.  (One 16-byte store per
+      // lane straight to global put 32 half-sectors of 32 different rows into every store instruction: 27 % of the kernel.)
+      uint8_t* stg_mu = stage_out + (warp - 6) * 8192;
+      uint8_t* stg_r = stg_mu + 4096;
+      for (int h0 = 0; h0 < kINT; h0 += 64) {
+        for (int c0 = h0; c0 < h0 + 64; c0 += 32) {
+          uint32_t vm[32], vr[32];
+          tmem_ld32(tmem + lane_base + ab * 256 + c0, vm);
+          tmem_ld32(tmem + lane_base + ab * 256 + kINT + c0, vr);
+          wait_ld();
+          if (c0 + 32 >= kINT) {
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+          }
+          if (c0 == h0) {      // the previous boxes have been read by TMA
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const int c = n0 + c0 + q4 * 8;
             uint32_t wm[4], wr[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -938,24 +957,26 @@ ibp_tc_kernel(const __grid_constant__ CUtensorMap tmAmu, const __grid_constant__
               for (int h = 0; h < 2; ++h) {
                 const float mu = __uint_as_float(vm[q4 * 8 + 2 * i + h]) + s_bias[c0 + q4 * 8 + 2 * i + h];
                 const float rr = __uint_as_float(vr[q4 * 8 + 2 * i + h]);
-                const float au = apply_act(p.act, mu + rr), al = apply_act(p.act, mu - rr);
+                const float au = act_fixed<kAct>(p.act, mu + rr), al = act_fixed<kAct>(p.act, mu - rr);
                 cm[h] = (au + al) / 2.f; cr[h] = (au - al) / 2.f;
               }
               wm[i] = pack_bf16x2(cm[0], cm[1]); wr[i] = pack_bf16x2(cr[0], cr[1]);
             }
-            if (c + 8 <= p.N) {
-              *reinterpret_cast<uint4*>(dmu + c0 + q4 * 8) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
-              *reinterpret_cast<uint4*>(dr + c0 + q4 * 8) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
-            } else {
-              const __nv_bfloat16* hm = reinterpret_cast<const __nv_bfloat16*>(wm);
-              const __nv_bfloat16* hr = reinterpret_cast<const __nv_bfloat16*>(wr);
-              for (int i = 0; i < 8; ++i)
-                if (c + i < p.N) { dmu[c0 + q4 * 8 + i] = hm[i]; dr[c0 + q4 * 8 + i] = hr[i]; }
-            }
+            const int chunk = (((c0 - h0) >> 3) + q4) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(stg_mu + lane * 128 + chunk * 16) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+            *reinterpret_cast<uint4*>(stg_r + lane * 128 + chunk * 16) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
           }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && n0 + h0 < p.N && m0 + gq * 32 < p.M) {
+          tma_store_3d(&tmOmu, smem_u32(stg_mu), n0 + h0, m0 + gq * 32, s);
+          tma_store_3d(&tmOr, smem_u32(stg_r), n0 + h0, m0 + gq * 32, s);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   fence_before_sync();
   __syncthreads();
@@ -1243,6 +1264,12 @@ int ibp_tc_launch(const __nv_bfloat16* Amu, const __nv_bfloat16* Ar, long long a
     uint32_t b[3] = {64, 64, 1};
     if (!make_tmap_bf16(&tmW, (void*)Wbase, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
+  CUtensorMap tmOmu, tmOr;
+  for (int which = 0; which < 2; ++which) {
+    uint64_t d[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)N * 2, (uint64_t)n_sstride * 2};
+    uint32_t b[3] = {64, 32, 1};
+    if (!make_tmap_bf16(which ? &tmOr : &tmOmu, (void*)(which ? n_r : n_mu), 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
   IbpGemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.ns = ns; p.tiles_m = (int)cdiv(M, 128); p.tiles_n = (int)cdiv(N, kINT); p.a_shared = a_shared; p.act = act;
   p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.n_mu = n_mu; p.n_r = n_r; p.n_sstride = n_sstride;
@@ -1251,11 +1278,13 @@ int ibp_tc_launch(const __nv_bfloat16* Amu, const __nv_bfloat16* Ar, long long a
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
   }
-  const int smem = kIStages * kIStageB + (int)sizeof(IBarriers) + 1024;
-  if (cudaFuncSetAttribute(ibp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+  const int smem = kIStages * kIStageB + kIAbs * kIAbsB + kIOutB + kINT * 4 + (int)sizeof(IBarriers) + 1024;
+  const int ka = act_class(act);
+  auto kern = ka == 1 ? ibp_tc_kernel<1> : (ka == 0 ? ibp_tc_kernel<0> : ibp_tc_kernel<-1>);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
   const long long total = (long long)ns * p.tiles_m * p.tiles_n;
   dim3 grid((unsigned)std::min<long long>(total, (long long)num_sms));
-  ibp_tc_kernel<<<grid, kIThreads, smem, st>>>(tmAmu, tmAr, tmW, p);
+  kern<<<grid, kIThreads, smem, st>>>(tmAmu, tmAr, tmW, tmOmu, tmOr, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -196,7 +196,13 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   const size_t out_b = (size_t)B * C * 4;                     // lower / upper / worst stay dense [s][B][C] for the sink kernels
   const size_t w16_b = (size_t)m->P16 * 2;
   DBX_CHECK(!kBf16 || m->P16 % 8 == 0, "bf16 parameter pitch %lld is not a multiple of 8", (long long)m->P16);
-  const size_t w_b = kBf16 ? (w16_b * (use_tc ? 2 : 1) + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
+  // bf16: the weights of chunk c + 1 are drawn on a side stream while chunk c is in the GEMMs (two W16 / bias buffers;
+  // the sampler is ALU work, the GEMMs tensor-pipe work); DBX_IBP_OVERLAP=0 serialises them
+  bool overlap = kBf16;
+  if (const char* e = getenv("DBX_IBP_OVERLAP")) overlap = overlap && atoi(e) != 0;
+  const int nwb = overlap ? 2 : 1;
+  const size_t pb_b = round_up((size_t)m->PB * 4, 16);
+  const size_t w_b = kBf16 ? (w16_b * (nwb + (use_tc ? 1 : 0)) + nwb * pb_b) : (src.stored ? 0 : (size_t)m->P * 4);
   const size_t per = 4 * act_b + 2 * f32_b + 3 * out_b + w_b + 64;
   const size_t zb_b = round_up(std::max<size_t>(4096, (size_t)m->max_feat * 4), 256);
   const size_t in_b = 2 * round_up((size_t)B * m->in_feat * sizeof(T), 256) + zb_b + 4096;
@@ -215,8 +221,37 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   float* upper = (float*)p; p += round_up((size_t)ns * out_b, 256);
   float* worst = (float*)p; p += round_up((size_t)ns * out_b, 256);
   T* Wc = (T*)p;
-  __nv_bfloat16* Wabs = (__nv_bfloat16*)(p + round_up((size_t)ns * w16_b, 256));
-  float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * w16_b, 256) * (use_tc ? 2 : 1)) : nullptr;
+  T* Wc2[2] = {Wc, Wc}; float* B32b[2] = {nullptr, nullptr}; __nv_bfloat16* Wabs = nullptr;
+  if (kBf16) {
+    const size_t wslab = round_up((size_t)ns * w16_b, 256);
+    char* q = p;
+    for (int i = 0; i < nwb; ++i) { Wc2[i] = (T*)q; q += wslab; }
+    if (nwb == 1) Wc2[1] = Wc2[0];
+    Wabs = (__nv_bfloat16*)q; if (use_tc) q += wslab;
+    for (int i = 0; i < nwb; ++i) { B32b[i] = (float*)q; q += round_up((size_t)ns * pb_b, 256); }
+    if (nwb == 1) B32b[1] = B32b[0];
+  }
+  cudaStream_t sst = st;
+  if (overlap) {
+    if (!m->ibp_side) {
+      DBX_CUDA(cudaStreamCreateWithFlags(&m->ibp_side, cudaStreamNonBlocking));
+      for (cudaEvent_t& e : m->ibp_ev) DBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    sst = m->ibp_side;
+    // everything enqueued on `st` before this call (previous users of the workspace, the posterior upload, a slab or
+    // injected noise written just before) is ordered before the first draw
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], st));
+    DBX_CUDA(cudaStreamWaitEvent(sst, m->ibp_ev[0], 0));
+  }
+  auto draw_chunk = [&](int64_t ci) -> int {     // bf16 only
+    const int b = (int)(ci & 1) % nwb;
+    const int64_t c0 = ci * ns;
+    const int nc = (int)std::min<int64_t>(ns, n - c0);
+    if (overlap && ci >= 2) DBX_CUDA(cudaStreamWaitEvent(sst, m->ibp_ev[3 + b], 0));
+    if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc2[b], B32b[b], sst)) return 1;
+    if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[1 + b], sst));
+    return 0;
+  };
   const int64_t act_ss = (int64_t)(act_b / sizeof(T)), out_ss = B * C;
 
   if (box_hi_dev) DBX_LAUNCH(ibp_box_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, box_hi_dev, in_mu, in_r, B * m->in_feat);
@@ -242,9 +277,16 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
     const float* Bbase; int64_t b_sstride;
+    const int64_t ci = c0 / ns;
+    const int wb = (int)(ci & 1) % nwb;
     if (kBf16) {
-      if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st)) return 1;
-      Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
+      if (ci == 0 || !overlap) { if (draw_chunk(ci)) return 1; }
+      if (overlap) {
+        if (c0 + ns < n && draw_chunk(ci + 1)) return 1;       // next chunk's weights, concurrently
+        DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[1 + wb], 0));
+      }
+      Wc = Wc2[wb];
+      Wbase = Wc; w_sstride = m->P16; Bbase = B32b[wb]; b_sstride = m->PB;
       if (use_tc) {  // |W16| for the layers that run as two GEMMs: all of them, or (hidden layers fused) the output layer alone
         if (abs_len == m->P16)
           DBX_LAUNCH(abs_bf16_kernel, grid_for((int64_t)nc * m->P16 / 8), 256, 0, st, (const uint4*)Wc, (uint4*)Wabs, (int64_t)nc * m->P16 / 8);
@@ -307,6 +349,7 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
       if (last) break;
       cur_mu = n_mu; cur_r = n_r; cur_ss = act_ss; bi ^= 1;
     }
+    if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[3 + wb], st));     // this chunk's weights are free again
     // ---- sinks
     const int act_last = m->layers[m->last_weighted].act;
     const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
