@@ -1,6 +1,6 @@
 // Bayes-by-Backprop training step on the device (included by engine.cu).
 //
-// Reference: deepbayes/optimizers/bayesbybackprop.py:46-170 (robust_train == 0) + losses.py:10-45.  One mini-batch:
+// Reference: deepbayes/optimizers/bayesbybackprop.py:46-170 (robust_train 0, 1, 2) + losses.py:10-45.  One mini-batch:
 //   noise ~ N(0,1) per weight (Philox, or injected), W = mean + softplus(rho) * noise            (:50-59)
 //   predictions = model_W(features)                                                               (:65)
 //   loss = loss_fn(labels, predictions) + kl_weight * (log_q(W; mean, rho) - log_q(W; prior))    (losses.py:40-45)
@@ -184,6 +184,158 @@ __global__ void mix_ce_kernel(const float* __restrict__ logits, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// robust_train == 1 (bayesbybackprop.py:73-90): the interval forward of verifiers.IBP (:68-95) through the step's own
+// weights, kept in (upper, lower) form per layer, and its backward.  With mu = (u + l)/2, r = (u - l)/2 of a layer's
+// input: MU = mu W + b, R = r |W| (propagate_interval, :23-41), z_u = MU + R, z_l = MU - R.
+// ---------------------------------------------------------------------------------------
+__global__ void ibp_train_box_kernel(const float* __restrict__ x, int64_t n, float eps, float* __restrict__ U, float* __restrict__ L) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[o];
+    U[o] = fminf(fmaxf(v + eps, 0.f), 1.f);          // tf.clip_by_value(inp + eps, 0, 1), verifiers.py:70-71
+    L[o] = fminf(fmaxf(v - eps, 0.f), 1.f);
+  }
+}
+
+// U / L [B, N] = act(MU +- R); 32 x 32 output tiles, ascending k
+__global__ void __launch_bounds__(256)
+ibp_train_fwd_kernel(const float* __restrict__ Up, const float* __restrict__ Lp, const float* __restrict__ W, const float* __restrict__ bias,
+                     int B, int K, int N, int act, float* __restrict__ U, float* __restrict__ L) {
+  __shared__ float Ms[32][33];
+  __shared__ float Rs[32][33];
+  __shared__ float Ws[32][33];
+  const int b0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float am[4] = {0.f, 0.f, 0.f, 0.f}, ar[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = ty; i < 32; i += 8) {
+      const bool in = b0 + i < B && k0 + tx < K;
+      const float u = in ? Up[(int64_t)(b0 + i) * K + k0 + tx] : 0.f, l = in ? Lp[(int64_t)(b0 + i) * K + k0 + tx] : 0.f;
+      Ms[i][tx] = (u + l) / 2.f; Rs[i][tx] = (u - l) / 2.f;
+      Ws[i][tx] = (k0 + i < K && n0 + tx < N) ? W[(int64_t)(k0 + i) * N + n0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float w = Ws[k][tx], wa = fabsf(w);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { am[r] = fmaf(Ms[ty + 8 * r][k], w, am[r]); ar[r] = fmaf(Rs[ty + 8 * r][k], wa, ar[r]); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + ty + 8 * r, n = n0 + tx;
+    if (b < B && n < N) {
+      const float mu = am[r] + bias[n];
+      U[(int64_t)b * N + n] = apply_act(act, mu + ar[r]);
+      L[(int64_t)b * N + n] = apply_act(act, mu - ar[r]);
+    }
+  }
+}
+
+// worst[b][c] = lower on the label, upper elsewhere (:78-82)
+__global__ void ibp_worst_kernel(const float* __restrict__ U, const float* __restrict__ L, const int32_t* __restrict__ labels, int B, int C,
+                                 float* __restrict__ worst) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= B * C) return;
+  worst[o] = (labels[o / C] == o % C) ? L[o] : U[o];
+}
+// gradient at the worst-case logits -> gradients at the upper / lower logits
+__global__ void ibp_split_kernel(const float* __restrict__ dzw, const int32_t* __restrict__ labels, int B, int C, float* __restrict__ dzu,
+                                 float* __restrict__ dzl) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= B * C) return;
+  const bool lab = labels[o / C] == o % C;
+  dzu[o] = lab ? 0.f : dzw[o];
+  dzl[o] = lab ? dzw[o] : 0.f;
+}
+
+// dW[k, n] (+)= sum_b mu[b, k] dMU[b, n] + sign(W[k, n]) sum_b r[b, k] dR[b, n],  dMU = dzu + dzl, dR = dzu - dzl
+__global__ void __launch_bounds__(256)
+ibp_grad_w_kernel(const float* __restrict__ Up, const float* __restrict__ Lp, const float* __restrict__ dzu, const float* __restrict__ dzl,
+                  const float* __restrict__ W, int B, int K, int N, float* __restrict__ dW, int accumulate) {
+  __shared__ float Ms[32][33];
+  __shared__ float Rs[32][33];
+  __shared__ float Zm[32][33];
+  __shared__ float Zr[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float am[4] = {0.f, 0.f, 0.f, 0.f}, ar[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    for (int i = ty; i < 32; i += 8) {
+      const int b = b0 + i;
+      const bool ia = b < B && k0 + tx < K, iz = b < B && n0 + tx < N;
+      const float u = ia ? Up[(int64_t)b * K + k0 + tx] : 0.f, l = ia ? Lp[(int64_t)b * K + k0 + tx] : 0.f;
+      const float zu = iz ? dzu[(int64_t)b * N + n0 + tx] : 0.f, zl = iz ? dzl[(int64_t)b * N + n0 + tx] : 0.f;
+      Ms[i][tx] = (u + l) / 2.f; Rs[i][tx] = (u - l) / 2.f;
+      Zm[i][tx] = zu + zl; Zr[i][tx] = zu - zl;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const float zm = Zm[i][tx], zr = Zr[i][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { am[r] = fmaf(Ms[i][ty + 8 * r], zm, am[r]); ar[r] = fmaf(Rs[i][ty + 8 * r], zr, ar[r]); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = k0 + ty + 8 * r, n = n0 + tx;
+    if (k < K && n < N) {
+      const float w = W[(int64_t)k * N + n];
+      const float g = am[r] + (w > 0.f ? ar[r] : (w < 0.f ? -ar[r] : 0.f));      // d|w|/dw = sign(w)
+      dW[(int64_t)k * N + n] = accumulate ? dW[(int64_t)k * N + n] + g : g;
+    }
+  }
+}
+
+// gradients at the previous layer's pre-activation bounds: dmu = dMU W^T, dr = dR |W|^T, du = (dmu + dr)/2, dl = (dmu - dr)/2,
+// each times act' evaluated from the previous layer's OUTPUT bound (Up / Lp)
+__global__ void __launch_bounds__(256)
+ibp_grad_a_kernel(const float* __restrict__ dzu, const float* __restrict__ dzl, const float* __restrict__ W, const float* __restrict__ Up,
+                  const float* __restrict__ Lp, int B, int K, int N, int act, float* __restrict__ dzu_prev, float* __restrict__ dzl_prev) {
+  __shared__ float Zm[32][33];
+  __shared__ float Zr[32][33];
+  __shared__ float Ws[32][33];
+  const int b0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float am[4] = {0.f, 0.f, 0.f, 0.f}, ar[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    for (int i = ty; i < 32; i += 8) {
+      const bool iz = b0 + i < B && n0 + tx < N;
+      const float zu = iz ? dzu[(int64_t)(b0 + i) * N + n0 + tx] : 0.f, zl = iz ? dzl[(int64_t)(b0 + i) * N + n0 + tx] : 0.f;
+      Zm[i][tx] = zu + zl; Zr[i][tx] = zu - zl;
+      Ws[i][tx] = (k0 + i < K && n0 + tx < N) ? W[(int64_t)(k0 + i) * N + n0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < 32; ++n) {
+      const float w = Ws[tx][n], wa = fabsf(w);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { am[r] = fmaf(Zm[ty + 8 * r][n], w, am[r]); ar[r] = fmaf(Zr[ty + 8 * r][n], wa, ar[r]); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + ty + 8 * r, k = k0 + tx;
+    if (b < B && k < K) {
+      const float u = Up[(int64_t)b * K + k], l = Lp[(int64_t)b * K + k];
+      float du, dl;
+      switch (act) {
+        case DBX_ACT_RELU: du = u > 0.f ? 1.f : 0.f; dl = l > 0.f ? 1.f : 0.f; break;
+        case DBX_ACT_TANH: du = 1.f - u * u; dl = 1.f - l * l; break;
+        case DBX_ACT_SIGMOID: du = u * (1.f - u); dl = l * (1.f - l); break;
+        default: du = 1.f; dl = 1.f;
+      }
+      dzu_prev[(int64_t)b * K + k] = (am[r] + ar[r]) / 2.f * du;
+      dzl_prev[(int64_t)b * K + k] = (am[r] - ar[r]) / 2.f * dl;
+    }
+  }
+}
+
 struct TrainTensors {
   int n;
   int32_t off[DBX_MAX_TENSORS], end[DBX_MAX_TENSORS];
@@ -243,7 +395,7 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
                         float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
                         float robust_lambda, float in_lower, float in_upper, cudaStream_t st) {
   DBX_CHECK(m->is_mlp, "the device training step covers Dense MLPs (bayesbybackprop.py:46-170)");
-  DBX_CHECK(robust_mode == 0 || robust_mode == 2, "robust_train %d is not built (0 = standard, 2 = FGSM adversarial training)", robust_mode);
+  DBX_CHECK(robust_mode >= 0 && robust_mode <= 2, "robust_train %d is not built (0 = standard, 1 = IBP, 2 = FGSM adversarial training)", robust_mode);
   const Layer& Lout = m->layers[m->last_weighted];
   DBX_CHECK(Lout.act == DBX_ACT_SOFTMAX, "the device training step needs a softmax output (sparse categorical cross-entropy)");
   const int64_t P = m->P, C = m->out_feat, K0 = m->in_feat;
@@ -256,7 +408,7 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   const size_t pb = round_up((size_t)P * 4, 256), dzb = round_up((size_t)B * std::max<int64_t>(m->max_feat, K0) * 4, 256);
   const size_t xb = round_up((size_t)B * K0 * 4, 256), ob = round_up((size_t)B * C * 4, 256);
   const int ublocks = 148 * 4;
-  const size_t need = 3 * pb + 2 * act_total + xb + 2 * dzb + 2 * ob + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
+  const size_t need = 3 * pb + 3 * act_total + 2 * xb + 4 * dzb + 3 * ob + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
   if (ensure_ws(m->ws, need)) return 1;
   char* p = (char*)m->ws.ptr;
   float* W = (float*)p; p += pb;            // (dbx_bbb_step copies the sampled weights out of this first block)
@@ -265,8 +417,13 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   std::vector<float*> acts(nl), acts_adv(nl);
   for (int i = 0; i < nl; ++i) { acts[i] = (float*)p; p += round_up((size_t)B * dl[i]->units * 4, 256); }
   for (int i = 0; i < nl; ++i) { acts_adv[i] = (float*)p; p += round_up((size_t)B * dl[i]->units * 4, 256); }
-  float* x_adv = (float*)p; p += xb;
+  std::vector<float*> acts_low(nl);     // robust_train == 1: acts_adv holds the upper bounds, acts_low the lower ones
+  for (int i = 0; i < nl; ++i) { acts_low[i] = (float*)p; p += round_up((size_t)B * dl[i]->units * 4, 256); }
+  float* x_adv = (float*)p; p += xb;      // robust_train == 1: upper input bound
+  float* x_low = (float*)p; p += xb;
   float* dz[2]; dz[0] = (float*)p; p += dzb; dz[1] = (float*)p; p += dzb;
+  float* dzl[2]; dzl[0] = (float*)p; p += dzb; dzl[1] = (float*)p; p += dzb;
+  float* worst = (float*)p; p += ob;
   float* probs_scratch = (float*)p; p += ob;
   float* dz_adv = (float*)p; p += ob;
   float* row_loss = (float*)p; p += round_up((size_t)B * 4, 256);
@@ -313,6 +470,40 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   if (robust_mode == 0) {
     DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], labels_dev, (int)B, (int)C, probs, dz[0], row_loss);
     backward(x_dev, acts, false, 0);
+  } else if (robust_mode == 1) {
+    // robust_train == 1: IBP through the step's own weights; the worst-case logits take the adversarial pass's place
+    DBX_LAUNCH(ibp_train_box_kernel, grid_for(B * K0), 256, 0, st, x_dev, B * K0, epsilon, x_adv, x_low);
+    for (int i = 0; i < nl; ++i) {
+      const Layer& L = *dl[i];
+      dim3 grid((unsigned)cdiv(L.units, 32), (unsigned)cdiv(B, 32));
+      DBX_LAUNCH(ibp_train_fwd_kernel, grid, 256, 0, st, (const float*)(i ? acts_adv[i - 1] : x_adv), (const float*)(i ? acts_low[i - 1] : x_low),
+                 (const float*)W + L.w_off, (const float*)W + L.b_off, (int)B, (int)L.in_feat, L.units, i == nl - 1 ? DBX_ACT_LINEAR : L.act,
+                 acts_adv[i], acts_low[i]);
+    }
+    DBX_LAUNCH(ibp_worst_kernel, (int)cdiv(B * C, 256), 256, 0, st, (const float*)acts_adv[nl - 1], (const float*)acts_low[nl - 1], labels_dev,
+               (int)B, (int)C, worst);
+    DBX_LAUNCH(mix_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (const float*)worst, labels_dev, (int)B, (int)C,
+               robust_lambda, probs, dz[0], dz_adv, row_loss);
+    backward(x_dev, acts, false, 0);
+    DBX_LAUNCH(ibp_split_kernel, (int)cdiv(B * C, 256), 256, 0, st, (const float*)dz_adv, labels_dev, (int)B, (int)C, dz[0], dzl[0]);
+    int zi = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      const Layer& L = *dl[i];
+      const float* up = i ? acts_adv[i - 1] : x_adv;
+      const float* lp = i ? acts_low[i - 1] : x_low;
+      const int K = (int)L.in_feat, N = L.units;
+      dim3 gw((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
+      DBX_LAUNCH(ibp_grad_w_kernel, gw, 256, 0, st, up, lp, (const float*)dz[zi], (const float*)dzl[zi], (const float*)W + L.w_off, (int)B, K, N,
+                 gdata + L.w_off, 1);
+      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, 1);
+      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dzl[zi], (int)B, N, gdata + L.b_off, 1);
+      if (i > 0) {
+        dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32));
+        DBX_LAUNCH(ibp_grad_a_kernel, ga, 256, 0, st, (const float*)dz[zi], (const float*)dzl[zi], (const float*)W + L.w_off, up, lp, (int)B, K, N,
+                   dl[i - 1]->act, dz[zi ^ 1], dzl[zi ^ 1]);
+        zi ^= 1;
+      }
+    }
   } else {
     // robust_train == 2: FGSM against the step's own weights (attacks.py:81-102 with num_models = 1 -> current weights, :57-58)
     DBX_LAUNCH(attack_upstream_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (int)B, (int)C, dz[0]);

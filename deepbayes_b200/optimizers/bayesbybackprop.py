@@ -1,7 +1,7 @@
 """BayesByBackprop -- hot-path part of deepbayes/optimizers/bayesbybackprop.py:
 ``compile`` (:31-44, rho = log(exp(std)-1)), the sampling + forward half of ``step``
 (:46-65, W = mu + softplus(rho)*eps then model(features)), ``sample`` (:176-181) and ``save``
-(:184-195), and the full training step (:46-170, robust_train == 0) as one device call (`dbx_bbb_step`).
+(:184-195), and the full training step (:46-170, robust_train 0 / 1 / 2) as one device call (`dbx_bbb_step`).
 """
 from __future__ import annotations
 
@@ -69,9 +69,9 @@ class BayesByBackprop(optimizer.Optimizer):
         set on the object and returned like the reference does (:169-170), and the sampled weights are left in the model
         (:59).  Other data losses / robust_train modes raise NotImplementedError."""
         rt = int(getattr(self, "robust_train", 0))
-        if rt not in (0, 2):
-            raise NotImplementedError("robust_train = %d (bayesbybackprop.py:73-136): only 0 (standard) and 2 (FGSM adversarial training, "
-                                      ":91-101) are built; the IBP modes need a backward through the interval forward" % rt)
+        if rt not in (0, 1, 2):
+            raise NotImplementedError("robust_train = %d (bayesbybackprop.py:102-136): 0 (standard), 1 (IBP, :73-90) and 2 (FGSM adversarial "
+                                      "training, :91-101) are built; the Monte-Carlo-over-epsilon modes 3 / 4 are not" % rt)
         name = getattr(self.loss_func, "__name__", type(self.loss_func).__name__).lower() if self.loss_func is not None else "sparse_categorical_crossentropy"
         if "sparse" not in name or "crossentropy" not in name:
             raise NotImplementedError("the device step builds the sparse categorical cross-entropy data term only (got %r)" % name)

@@ -138,6 +138,9 @@ int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32
  * rho -= lrate * (noise * sigmoid(rho) * gW + grho).  All parameter vectors are flat fp32 [P] in Keras order, on the
  * device, owned by the caller.  Optional outputs: loss_out_dev[2] = (loss, kl component), probs_out_dev [B,C] = the
  * predictions of this step, W_out_dev [P] = the sampled weights (the reference leaves them in the model, :59).
+ * robust_mode = 1 (bayesbybackprop.py:73-90): (logit_l, logit_u) = IBP(features, W, eps = epsilon) (verifiers.py:68-95, input box
+ * clip(features -+ epsilon, 0, 1)), worst = softmax(logit_l on the label, logit_u elsewhere), the data term is evaluated on
+ * robust_lambda * predictions + (1 - robust_lambda) * worst and differentiated through the interval forward as well.
  * robust_mode = 2 (bayesbybackprop.py:91-101): features_adv = FGSM(features, eps = epsilon) against the step's own
  * weights towards the predicted class, clipped to [in_lower, in_upper], and the data term is evaluated on
  * robust_lambda * predictions + (1 - robust_lambda) * model(features_adv); robust_mode = 0 ignores those arguments.

@@ -644,12 +644,63 @@ def _mlp_backward_weights(dense, W, acts, dz):
     return gW
 
 
+def _act_grad(name, a):
+    """Derivative of an element-wise activation written in terms of its OUTPUT a."""
+    if name == "relu":
+        return (a > 0).astype(a.dtype)
+    if name == "tanh":
+        return 1 - a * a
+    if name == "sigmoid":
+        return a * (1 - a)
+    if name in ("linear", None):
+        return np.ones_like(a)
+    raise NotImplementedError(name)
+
+
+def _ibp_forward_bounds(dense, W, x, eps):
+    """verifiers.IBP (:68-95, predict=False) on a Dense MLP keeping every layer's bounds: U[i] / Lo[i] = upper / lower
+    input of layer i (after the previous activation), U[-1] / Lo[-1] = the logit interval.  Also returns the pre-activation
+    bounds.  The input box is clip(x -+ eps, 0, 1) (:70-71)."""
+    hu, hl = np.clip(x + eps, 0.0, 1.0), np.clip(x - eps, 0.0, 1.0)
+    U, Lo, Z = [hu], [hl], []
+    for li, l in enumerate(dense):
+        zl, zu = propagate_interval(W[2 * li], W[2 * li + 1], hl, hu)
+        Z.append((zl, zu))
+        if li < len(dense) - 1:
+            hl, hu = _act(l.activation, zl), _act(l.activation, zu)
+        else:
+            hl, hu = zl, zu
+        U.append(hu); Lo.append(hl)
+    return U, Lo, Z
+
+
+def _ibp_backward_weights(dense, W, U, Lo, dzu, dzl):
+    """dLoss/dW through the interval forward, given dLoss/d(upper logits) = dzu and dLoss/d(lower logits) = dzl.
+    With mu = (u + l)/2, r = (u - l)/2 of a layer's input and MU = mu W + b, R = r |W| (propagate_interval,
+    verifiers.py:23-41): z_u = MU + R, z_l = MU - R, so dMU = dzu + dzl, dR = dzu - dzl,
+    dW = mu^T dMU + sign(W) * (r^T dR), db = sum_b dMU, dmu = dMU W^T, dr = dR |W|^T, du = (dmu + dr)/2, dl = (dmu - dr)/2."""
+    gW = [None] * len(W)
+    for li in range(len(dense) - 1, -1, -1):
+        mu, r = (U[li] + Lo[li]) / 2, (U[li] - Lo[li]) / 2
+        dMU, dR = dzu + dzl, dzu - dzl
+        gW[2 * li] = mu.T @ dMU + np.sign(W[2 * li]) * (r.T @ dR)
+        gW[2 * li + 1] = dMU.sum(0)
+        if li > 0:
+            dmu, dr = dMU @ W[2 * li].T, dR @ np.abs(W[2 * li]).T
+            name = dense[li - 1].activation
+            dzu = (dmu + dr) / 2 * _act_grad(name, U[li])
+            dzl = (dmu - dr) / 2 * _act_grad(name, Lo[li])
+    return gW
+
+
 def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64,
              robust_train=0, epsilon=0.0, robust_lambda=1.0, lower=-np.inf, upper=np.inf):
     """`BayesByBackprop.step` (bayesbybackprop.py:46-170) for Dense MLPs with a softmax output and the sparse categorical
     cross-entropy, gradients written out by hand (the reference gets them from tf.GradientTape):
       W = mean + softplus(rho) * noise                                                    (:50-59)
       robust_train == 0: output = model_W(x)                                               (:65-72)
+      robust_train == 1: (l, u) = IBP(x, W, eps), worst = softmax(u off the label, l on it),
+                         output = lambda * model_W(x) + (1 - lambda) * worst                (:73-90)
       robust_train == 2: x_adv = FGSM(x, eps) against W towards argmax model_W(x) (:92, attacks.py:81-102 with the
                          model's current weights), output = lambda * model_W(x) + (1 - lambda) * model_W(x_adv)   (:93-95)
       weight_gradient = dLoss/dW       (data term + kl_weight * d(log_q - log_prior)/dW)  (:138)
@@ -697,8 +748,20 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
         g1 = _mlp_backward_weights(dense, W, acts, dz)
         g2 = _mlp_backward_weights(dense, W, acts_adv, dza)
         gW = [a + b for a, b in zip(g1, g2)]
+    elif robust_train == 1:
+        U, Lo, _ = _ibp_forward_bounds(dense, W, x, epsilon)
+        worst = (1 - onehot) * U[-1] + onehot * Lo[-1]                     # :78-82 (v2 * logit_u + v1 * logit_l)
+        pw = _act("softmax", worst)                                        # :84
+        out = d(robust_lambda) * pred + d(1 - robust_lambda) * pw          # :85
+        oy = out[np.arange(B), lab]
+        g = np.where((oy > 1e-7) & (oy < 1 - 1e-7), -1.0 / (B * oy), 0.0)
+        dz = (d(robust_lambda) * g * pred[np.arange(B), lab])[:, None] * (onehot - pred)
+        dzw = (d(1 - robust_lambda) * g * pw[np.arange(B), lab])[:, None] * (onehot - pw)
+        g1 = _mlp_backward_weights(dense, W, acts, dz)
+        g2 = _ibp_backward_weights(dense, W, U, Lo, dzw * (1 - onehot), dzw * onehot)
+        gW = [a + b for a, b in zip(g1, g2)]
     else:
-        raise NotImplementedError("oracle bbb_step: robust_train 0 and 2")
+        raise NotImplementedError("oracle bbb_step: robust_train 0, 1 and 2")
     data = sparse_categorical_crossentropy(lab, out, d)
     klc = log_q(W, mean, rho, d) - log_q(W, pm, [np.asarray(t, d) for t in prior_var], d)
     loss = data + d(kl_weight) * klc

@@ -756,7 +756,7 @@ def test_bbb_step_matches_oracle(oracle, dims, B):
     np.testing.assert_allclose(got[1], klc, rtol=2e-5)
     np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
     with pytest.raises(NotImplementedError):
-        db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, robust_train=1).step(x, lab, lr)
+        db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, robust_train=3).step(x, lab, lr)
 
 
 def test_bbb_training_learns(oracle):
@@ -885,6 +885,75 @@ def test_bbb_step_fgsm_adversarial_training_matches_oracle(oracle):
     got = opt._last_loss.cpu().numpy()
     np.testing.assert_allclose(got[0], loss, rtol=5e-5)
     np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("hidden_act", ["relu", "tanh"])
+def test_bbb_step_ibp_training_matches_oracle(oracle, hidden_act):
+    """robust_train = 1 (bayesbybackprop.py:73-90): interval forward through the step's own weights, softmax of the
+    worst-case logits mixed with the clean prediction, backward through BOTH the plain and the interval forward --
+    device vs oracle (float64, gradients checked by finite differences in test_oracle.py) with injected noise."""
+    import deepbayes_b200 as db
+    dims, B = [40, 24, 16, 6], 21
+    L = oracle.mlp(dims, hidden_act=hidden_act)
+    layers = [db.Dense(24, activation=hidden_act, input_shape=(40,)), db.Dense(16, activation=hidden_act), db.Dense(6, activation="softmax")]
+    opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.5,
+                                                  robust_train=1, epsilon=0.02, rob_lam=0.3)
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    opt.posterior_mean = [m.copy() for m in mean]
+    opt.posterior_var = [oracle.inverse_softplus(s) for s in std]
+    rho0 = [r.copy() for r in opt.posterior_var]
+    x = oracle.synthetic_x((B, 40), seed=0)
+    lab = np.random.Generator(np.random.Philox(3)).integers(0, 6, size=B)
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr = 0.1
+    nm, nr = opt.step(x, lab, lr, noise=noise)
+    wm, wr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.5,
+                                                 robust_train=1, epsilon=0.02, robust_lambda=0.3)
+    for i in range(len(nm)):
+        dm, dr = np.abs(wm[i] - mean[i]).max() + 1e-12, np.abs(wr[i] - rho0[i]).max() + 1e-12
+        np.testing.assert_allclose(nm[i], wm[i], rtol=0, atol=5e-4 * dm + 1e-7)
+        np.testing.assert_allclose(nr[i], wr[i], rtol=0, atol=5e-4 * dr + 1e-7)
+    got = opt._last_loss.cpu().numpy()
+    np.testing.assert_allclose(got[0], loss, rtol=5e-5)
+    np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
+    # lambda = 1 switches the interval term off: same update as the standard step
+    opt1 = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.5,
+                                                   robust_train=1, epsilon=0.02, rob_lam=1.0, linear_schedule=False)
+    opt0 = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.5)
+    for o in (opt0, opt1):
+        o.posterior_mean = [m.copy() for m in mean]
+        o.posterior_var = [r.copy() for r in rho0]
+    if float(getattr(opt1, "robust_lambda", 1.0)) == 1.0:
+        a, _ = opt0.step(x, lab, lr, noise=noise)
+        b, _ = opt1.step(x, lab, lr, noise=noise)
+        for i in range(len(a)):
+            np.testing.assert_allclose(a[i], b[i], rtol=0, atol=1e-7)
+
+
+def test_bbb_ibp_training_tightens_the_bounds(oracle):
+    """A few hundred robust_train = 1 steps on a separable toy problem: the clean accuracy stays high and the certified
+    (IBP) worst-case probability of the true class ends above what standard training reaches."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.analyzers import verifiers
+    g = np.random.Generator(np.random.Philox(11))
+    n, d = 512, 20
+    lab = g.integers(0, 2, size=n)
+    x = np.clip(0.5 + 0.25 * (2 * lab[:, None] - 1) * np.ones((1, d)) + 0.05 * g.standard_normal((n, d)), 0, 1).astype(np.float32)
+    res = {}
+    for rt in (0, 1):
+        layers = [db.Dense(32, activation="relu", input_shape=(d,)), db.Dense(2, activation="softmax")]
+        opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=128, learning_rate=0.3, epochs=1, inflate_prior=1.0,
+                                                      kl_weight=0.01, robust_train=rt, epsilon=0.1, rob_lam=0.5, linear_schedule=False, seed=5)
+        for it in range(300):
+            sel = g.integers(0, n, size=128)
+            opt.step(x[sel], lab[sel], 0.3, sync=(it == 299))
+        w = opt.posterior_mean
+        acc = (np.argmax(opt.predict(x), 1) == lab).mean()
+        lo, hi = verifiers.IBP(opt, x, w, 0.1)
+        worst = np.where(np.eye(2)[lab] > 0, lo, hi)
+        cert = (np.argmax(worst, 1) == lab).mean()
+        res[rt] = (acc, cert)
+    assert res[1][0] > 0.95 and res[1][1] >= res[0][1] - 0.02 and res[1][1] > 0.9, res
 
 
 def test_ibp_state_weight_margin_matches_reference_run(oracle, golden_dir):
