@@ -1107,12 +1107,29 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
                  float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
   DBX_CHECK(h && x_dev && labels_dev && mean_dev && rho_dev && prior_mean_dev && prior_var_dev, "null argument");
   DBX_CHECK(B > 0, "B must be positive");
+  DBX_CHECK(robust_mode >= 0 && robust_mode <= 2, "robust_mode %d: 0, 1, 2 here; the epsilon-draw mode 3 is dbx_bbb_step_ibp_mc", robust_mode);
   DBX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (run_bbb_step(h, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
                    loss_out_dev, probs_out_dev, robust_mode, epsilon, robust_lambda, in_lower, in_upper, st))
     return 1;
   if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));   // W is the first workspace block
+  return 0;
+}
+
+int dbx_bbb_step_ibp_mc(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                        const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                        float lrate, float kl_weight, int32_t n_eps, const float* eps_host, float* loss_out_dev, float* probs_out_dev,
+                        float* W_out_dev, void* stream) {
+  DBX_CHECK(h && x_dev && labels_dev && mean_dev && rho_dev && prior_mean_dev && prior_var_dev && eps_host, "null argument");
+  DBX_CHECK(B > 0 && n_eps >= 1 && n_eps <= 64, "B must be positive and 1 <= n_eps <= 64");
+  for (int k = 0; k < n_eps; ++k) DBX_CHECK(eps_host[k] >= 0.f, "epsilon draw %d is negative", k);
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (run_bbb_step(h, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
+                   loss_out_dev, probs_out_dev, 3, 0.f, 0.f, 0.f, 0.f, st, n_eps, eps_host))
+    return 1;
+  if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -336,6 +336,43 @@ ibp_grad_a_kernel(const float* __restrict__ dzu, const float* __restrict__ dzl, 
   }
 }
 
+// robust_train == 3 (bayesbybackprop.py:102-121): output = sum_k (1/K) softmax(worst_k), worst_k the worst-case IBP logits at
+// the k-th draw of epsilon; loss row, the clean probabilities (train_metric, :166) and the gradient at every worst_k
+__global__ void mc_ce_kernel(const float* __restrict__ logits, const float* __restrict__ worstK, int K, const int32_t* __restrict__ labels, int B,
+                             int C, float* __restrict__ probs, float* __restrict__ dzwK, float* __restrict__ row_loss) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int y = labels[b];
+  const float invK = 1.f / (float)K;
+  float oy = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float* z = worstK + ((int64_t)k * B + b) * C;
+    float m = z[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(z[c] - m);
+    oy += invK * (expf(z[y] - m) / den);
+  }
+  const float g = (oy > 1e-7f && oy < 1.f - 1e-7f) ? -1.f / ((float)B * oy) : 0.f;
+  row_loss[b] = -logf(fminf(fmaxf(oy, 1e-7f), 1.f - 1e-7f));
+  for (int k = 0; k < K; ++k) {
+    const float* z = worstK + ((int64_t)k * B + b) * C;
+    float m = z[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(z[c] - m);
+    const float py = expf(z[y] - m) / den;
+    for (int c = 0; c < C; ++c)
+      dzwK[((int64_t)k * B + b) * C + c] = invK * g * py * ((c == y ? 1.f : 0.f) - expf(z[c] - m) / den);
+  }
+  const float* z = logits + (int64_t)b * C;
+  float m = z[0];
+  for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) den += expf(z[c] - m);
+  for (int c = 0; c < C; ++c) probs[(int64_t)b * C + c] = expf(z[c] - m) / den;
+}
+
 struct TrainTensors {
   int n;
   int32_t off[DBX_MAX_TENSORS], end[DBX_MAX_TENSORS];
@@ -393,9 +430,10 @@ __global__ void bbb_loss_kernel(const float* __restrict__ row_loss, int B, const
 static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                         float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
-                        float robust_lambda, float in_lower, float in_upper, cudaStream_t st) {
+                        float robust_lambda, float in_lower, float in_upper, cudaStream_t st, int n_eps = 0, const float* eps_list = nullptr) {
   DBX_CHECK(m->is_mlp, "the device training step covers Dense MLPs (bayesbybackprop.py:46-170)");
-  DBX_CHECK(robust_mode >= 0 && robust_mode <= 2, "robust_train %d is not built (0 = standard, 1 = IBP, 2 = FGSM adversarial training)", robust_mode);
+  DBX_CHECK(robust_mode >= 0 && robust_mode <= 3, "robust_train %d is not built (0 = standard, 1 = IBP, 2 = FGSM adversarial training, 3 = IBP over draws of epsilon)", robust_mode);
+  DBX_CHECK(robust_mode != 3 || (n_eps >= 1 && n_eps <= 64 && eps_list), "robust_train 3 needs 1..64 epsilon draws");
   const Layer& Lout = m->layers[m->last_weighted];
   DBX_CHECK(Lout.act == DBX_ACT_SOFTMAX, "the device training step needs a softmax output (sparse categorical cross-entropy)");
   const int64_t P = m->P, C = m->out_feat, K0 = m->in_feat;
@@ -408,7 +446,7 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   const size_t pb = round_up((size_t)P * 4, 256), dzb = round_up((size_t)B * std::max<int64_t>(m->max_feat, K0) * 4, 256);
   const size_t xb = round_up((size_t)B * K0 * 4, 256), ob = round_up((size_t)B * C * 4, 256);
   const int ublocks = 148 * 4;
-  const size_t need = 3 * pb + 3 * act_total + 2 * xb + 4 * dzb + 3 * ob + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
+  const size_t need = 3 * pb + 3 * act_total + 2 * xb + 4 * dzb + (3 + 2 * (size_t)std::max(n_eps, 0)) * ob + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
   if (ensure_ws(m->ws, need)) return 1;
   char* p = (char*)m->ws.ptr;
   float* W = (float*)p; p += pb;            // (dbx_bbb_step copies the sampled weights out of this first block)
@@ -424,6 +462,8 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   float* dz[2]; dz[0] = (float*)p; p += dzb; dz[1] = (float*)p; p += dzb;
   float* dzl[2]; dzl[0] = (float*)p; p += dzb; dzl[1] = (float*)p; p += dzb;
   float* worst = (float*)p; p += ob;
+  float* worstK = (float*)p; p += (size_t)std::max(n_eps, 0) * ob;       // robust_train == 3: [K][B][C] (ob-pitched)
+  float* dzwK = (float*)p; p += (size_t)std::max(n_eps, 0) * ob;
   float* probs_scratch = (float*)p; p += ob;
   float* dz_adv = (float*)p; p += ob;
   float* row_loss = (float*)p; p += round_up((size_t)B * 4, 256);
@@ -470,22 +510,25 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   if (robust_mode == 0) {
     DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], labels_dev, (int)B, (int)C, probs, dz[0], row_loss);
     backward(x_dev, acts, false, 0);
-  } else if (robust_mode == 1) {
-    // robust_train == 1: IBP through the step's own weights; the worst-case logits take the adversarial pass's place
-    DBX_LAUNCH(ibp_train_box_kernel, grid_for(B * K0), 256, 0, st, x_dev, B * K0, epsilon, x_adv, x_low);
-    for (int i = 0; i < nl; ++i) {
-      const Layer& L = *dl[i];
-      dim3 grid((unsigned)cdiv(L.units, 32), (unsigned)cdiv(B, 32));
-      DBX_LAUNCH(ibp_train_fwd_kernel, grid, 256, 0, st, (const float*)(i ? acts_adv[i - 1] : x_adv), (const float*)(i ? acts_low[i - 1] : x_low),
-                 (const float*)W + L.w_off, (const float*)W + L.b_off, (int)B, (int)L.in_feat, L.units, i == nl - 1 ? DBX_ACT_LINEAR : L.act,
-                 acts_adv[i], acts_low[i]);
-    }
-    DBX_LAUNCH(ibp_worst_kernel, (int)cdiv(B * C, 256), 256, 0, st, (const float*)acts_adv[nl - 1], (const float*)acts_low[nl - 1], labels_dev,
-               (int)B, (int)C, worst);
-    DBX_LAUNCH(mix_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (const float*)worst, labels_dev, (int)B, (int)C,
-               robust_lambda, probs, dz[0], dz_adv, row_loss);
-    backward(x_dev, acts, false, 0);
-    DBX_LAUNCH(ibp_split_kernel, (int)cdiv(B * C, 256), 256, 0, st, (const float*)dz_adv, labels_dev, (int)B, (int)C, dz[0], dzl[0]);
+  } else if (robust_mode == 1 || robust_mode == 3) {
+    // interval forward through the step's own weights at one epsilon: bounds per layer in acts_adv (upper) / acts_low (lower),
+    // worst-case logits into `wdst`
+    auto ibp_forward = [&](float eps_k, float* wdst) -> int {
+      DBX_LAUNCH(ibp_train_box_kernel, grid_for(B * K0), 256, 0, st, x_dev, B * K0, eps_k, x_adv, x_low);
+      for (int i = 0; i < nl; ++i) {
+        const Layer& L = *dl[i];
+        dim3 grid((unsigned)cdiv(L.units, 32), (unsigned)cdiv(B, 32));
+        DBX_LAUNCH(ibp_train_fwd_kernel, grid, 256, 0, st, (const float*)(i ? acts_adv[i - 1] : x_adv), (const float*)(i ? acts_low[i - 1] : x_low),
+                   (const float*)W + L.w_off, (const float*)W + L.b_off, (int)B, (int)L.in_feat, L.units, i == nl - 1 ? DBX_ACT_LINEAR : L.act,
+                   acts_adv[i], acts_low[i]);
+      }
+      DBX_LAUNCH(ibp_worst_kernel, (int)cdiv(B * C, 256), 256, 0, st, (const float*)acts_adv[nl - 1], (const float*)acts_low[nl - 1], labels_dev,
+                 (int)B, (int)C, wdst);
+      return 0;
+    };
+    // backward through the interval forward from the gradient at the worst-case logits
+    auto ibp_backward = [&](const float* dzw, int accumulate) -> int {
+    DBX_LAUNCH(ibp_split_kernel, (int)cdiv(B * C, 256), 256, 0, st, dzw, labels_dev, (int)B, (int)C, dz[0], dzl[0]);
     int zi = 0;
     for (int i = nl - 1; i >= 0; --i) {
       const Layer& L = *dl[i];
@@ -494,14 +537,34 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
       const int K = (int)L.in_feat, N = L.units;
       dim3 gw((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
       DBX_LAUNCH(ibp_grad_w_kernel, gw, 256, 0, st, up, lp, (const float*)dz[zi], (const float*)dzl[zi], (const float*)W + L.w_off, (int)B, K, N,
-                 gdata + L.w_off, 1);
-      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, 1);
+                 gdata + L.w_off, accumulate);
+      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, accumulate);
       DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dzl[zi], (int)B, N, gdata + L.b_off, 1);
       if (i > 0) {
         dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32));
         DBX_LAUNCH(ibp_grad_a_kernel, ga, 256, 0, st, (const float*)dz[zi], (const float*)dzl[zi], (const float*)W + L.w_off, up, lp, (int)B, K, N,
                    dl[i - 1]->act, dz[zi ^ 1], dzl[zi ^ 1]);
         zi ^= 1;
+      }
+    }
+    return 0;
+    };
+    if (robust_mode == 1) {
+      // the worst-case logits take the adversarial pass's place in the mixed loss
+      if (ibp_forward(epsilon, worst)) return 1;
+      DBX_LAUNCH(mix_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (const float*)worst, labels_dev, (int)B, (int)C,
+                 robust_lambda, probs, dz[0], dz_adv, row_loss);
+      backward(x_dev, acts, false, 0);
+      if (ibp_backward(dz_adv, 1)) return 1;
+    } else {
+      // robust_train == 3: the mean over the epsilon draws of softmax(worst_k); the clean prediction is not part of the loss.
+      // Pass 1 keeps only the worst-case logits of every draw; pass 2 repeats each interval forward right before its backward.
+      for (int k = 0; k < n_eps; ++k) if (ibp_forward(eps_list[k], worstK + (int64_t)k * B * C)) return 1;
+      DBX_LAUNCH(mc_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)acts[nl - 1], (const float*)worstK, n_eps, labels_dev, (int)B, (int)C,
+                 probs, dzwK, row_loss);
+      for (int k = 0; k < n_eps; ++k) {
+        if (n_eps > 1 || k > 0) { if (ibp_forward(eps_list[k], worst)) return 1; }
+        if (ibp_backward(dzwK + (int64_t)k * B * C, k > 0 ? 1 : 0)) return 1;
       }
     }
   } else {

@@ -236,9 +236,11 @@ class Engine:
         return (counts, flags) if return_flags else counts
 
     def bbb_step(self, x, labels, mean_t, rho_t, prior_mean_t, prior_var_t, lrate, kl_weight=1.0, seed=0, step=0, noise=None,
-                 want_probs=True, want_weights=False, robust_mode=0, epsilon=0.0, robust_lambda=1.0, in_lower=-3.0e38, in_upper=3.0e38):
+                 want_probs=True, want_weights=False, robust_mode=0, epsilon=0.0, robust_lambda=1.0, in_lower=-3.0e38, in_upper=3.0e38,
+                 eps_draws=None):
         """One Bayes-by-Backprop step (bayesbybackprop.py:46-170) updating the flat device tensors ``mean_t`` / ``rho_t`` in
-        place.  Returns dict(loss=[loss, kl] device tensor, probs=[B,C] | None, W=[P] | None)."""
+        place.  robust_mode 3 (IBP averaged over the epsilon draws ``eps_draws``, :102-121) goes through `dbx_bbb_step_ibp_mc`.
+        Returns dict(loss=[loss, kl] device tensor, probs=[B,C] | None, W=[P] | None)."""
         torch = self.torch
         xt = self._x2d(x)
         B = xt.shape[0]
@@ -252,6 +254,13 @@ class Engine:
         probs = torch.empty((B, self.C), dtype=torch.float32, device=self.device) if want_probs else None
         W = torch.empty(self.P, dtype=torch.float32, device=self.device) if want_weights else None
         e = None if noise is None else self._dev_f32(noise).reshape(-1)
+        if int(robust_mode) == 3:
+            import ctypes
+            d = np.ascontiguousarray(np.asarray(eps_draws, np.float32).reshape(-1))
+            _lib.check(self.lib.dbx_bbb_step_ibp_mc(self.h, _ptr(xt), B, _ptr(lab), _ptr(mean_t), _ptr(rho_t), _ptr(prior_mean_t), _ptr(prior_var_t),
+                                                    _ptr(e), seed, step, float(lrate), float(kl_weight), int(d.size),
+                                                    d.ctypes.data_as(ctypes.c_void_p), _ptr(loss), _ptr(probs), _ptr(W), _stream()))
+            return {"loss": loss, "probs": probs, "W": W}
         _lib.check(self.lib.dbx_bbb_step(self.h, _ptr(xt), B, _ptr(lab), _ptr(mean_t), _ptr(rho_t), _ptr(prior_mean_t), _ptr(prior_var_t),
                                          _ptr(e), seed, step, float(lrate), float(kl_weight), int(robust_mode), float(epsilon),
                                          float(robust_lambda), float(max(in_lower, -3.0e38)), float(min(in_upper, 3.0e38)), _ptr(loss),

@@ -61,17 +61,31 @@ class BayesByBackprop(optimizer.Optimizer):
             o += k
         return out
 
-    def step(self, features, labels, lrate, noise=None, sync=True):
-        """bayesbybackprop.py:46-170 (robust_train == 0) in ONE device call (`dbx_bbb_step`): draw noise, W = mean +
+    def step(self, features, labels, lrate, noise=None, sync=True, eps_draws=None):
+        """bayesbybackprop.py:46-170 (robust_train 0 - 4) in ONE device call (`dbx_bbb_step`): draw noise, W = mean +
         softplus(rho) * noise, forward, KL loss (losses.py:40-45) with the sparse categorical cross-entropy as the data
         term, the reference's three gradients and its SGD update.  ``noise`` (list / flat vector) injects the N(0,1) draw.
         The parameters live on the device between steps; with sync=True (default) the updated lists are copied back,
         set on the object and returned like the reference does (:169-170), and the sampled weights are left in the model
-        (:59).  Other data losses / robust_train modes raise NotImplementedError."""
+        (:59).  robust_train: 1 = IBP (:73-90), 2 = FGSM (:91-101), 3 = IBP averaged over ``loss_mc`` draws of epsilon from
+        Exponential(rate = 1 / epsilon) (:102-121; ``eps_draws`` injects them, otherwise they come from a NumPy generator
+        seeded with the optimizer's seed), 4 = the FGSM pass repeated loss_mc times with the SAME epsilon (:123-136: the
+        drawn eps is not used, :131), i.e. mode 2 with lambda = 0.  Other data losses raise NotImplementedError."""
         rt = int(getattr(self, "robust_train", 0))
-        if rt not in (0, 1, 2):
-            raise NotImplementedError("robust_train = %d (bayesbybackprop.py:102-136): 0 (standard), 1 (IBP, :73-90) and 2 (FGSM adversarial "
-                                      "training, :91-101) are built; the Monte-Carlo-over-epsilon modes 3 / 4 are not" % rt)
+        if rt not in (0, 1, 2, 3, 4):
+            raise NotImplementedError("robust_train = %d (bayesbybackprop.py:68-136 knows 0 - 4)" % rt)
+        epsilon, lam, mode, draws = float(getattr(self, "epsilon", 0.0)), float(getattr(self, "robust_lambda", 1.0)), rt, None
+        if rt in (3, 4):
+            self.epsilon = epsilon = max(0.0001, epsilon)       # :104, :125
+            k = int(getattr(self, "loss_monte_carlo", 2))
+            if rt == 3:
+                if eps_draws is None:
+                    if getattr(self, "_eps_rng", None) is None:
+                        self._eps_rng = np.random.Generator(np.random.Philox(int(self.seed) + 0x3E95))
+                    eps_draws = self._eps_rng.exponential(scale=epsilon, size=k)      # Exponential(rate 1 / epsilon): mean epsilon
+                draws = np.asarray(eps_draws, np.float32).reshape(-1)
+            else:
+                mode, lam = 2, 0.0
         name = getattr(self.loss_func, "__name__", type(self.loss_func).__name__).lower() if self.loss_func is not None else "sparse_categorical_crossentropy"
         if "sparse" not in name or "crossentropy" not in name:
             raise NotImplementedError("the device step builds the sparse categorical cross-entropy data term only (got %r)" % name)
@@ -84,9 +98,8 @@ class BayesByBackprop(optimizer.Optimizer):
             self._d_pv = self._flat_dev(self.prior_var).clone()
         e = None if noise is None else eng._as_flat(noise)
         res = eng.bbb_step(features, labels, self._d_mean, self._d_rho, self._d_pm, self._d_pv, lrate, self.kl_weight, self.seed,
-                           self._take_ids(1), e, want_probs=True, want_weights=sync, robust_mode=rt,
-                           epsilon=float(getattr(self, "epsilon", 0.0)), robust_lambda=float(getattr(self, "robust_lambda", 1.0)),
-                           in_lower=self.input_lower, in_upper=self.input_upper)
+                           self._take_ids(1), e, want_probs=True, want_weights=sync, robust_mode=mode,
+                           epsilon=epsilon, robust_lambda=lam, in_lower=self.input_lower, in_upper=self.input_upper, eps_draws=draws)
         self._last_loss, self._last_probs = res["loss"], res["probs"]
         if sync:
             self.posterior_mean = self._unflat(self._d_mean.cpu().numpy())

@@ -150,6 +150,17 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
                  float lrate, float kl_weight, int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper,
                  float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
 
+/* robust_train == 3 of the same step (bayesbybackprop.py:102-121): the data term is evaluated on
+ * output = sum_k (1 / n_eps) * softmax(worst-case IBP logits at eps_host[k]) -- the clean prediction is NOT part of the loss
+ * (it is still returned in probs_out_dev for the train metric, :166).  eps_host[n_eps] is HOST memory: the reference draws
+ * every eps from Exponential(rate = 1 / epsilon) (:106-109); the caller draws them.  Everything else as dbx_bbb_step.
+ * (robust_train == 4, :123-136, repeats the SAME FGSM pass loss_mc times -- the drawn eps is not used, :131 -- and is
+ * dbx_bbb_step with robust_mode = 2 and robust_lambda = 0.) */
+int dbx_bbb_step_ibp_mc(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                        const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                        float lrate, float kl_weight, int32_t n_eps, const float* eps_host, float* loss_out_dev, float* probs_out_dev,
+                        float* W_out_dev, void* stream);
+
 /* `IBP_state(model, s0, s1, weights, weight_margin)` (verifiers.py:97-123; probverification.py IBP_prob :84-110): the
  * input box [lo, hi] itself is given, the weights are one explicit flat vector, and every weight / bias is widened by
  * weight_margin * sigma (sigma = the Gaussian posterior's scale set with dbx_set_gaussian): the |x_mu| W_r and

@@ -694,13 +694,14 @@ def _ibp_backward_weights(dense, W, U, Lo, dzu, dzl):
 
 
 def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64,
-             robust_train=0, epsilon=0.0, robust_lambda=1.0, lower=-np.inf, upper=np.inf):
+             robust_train=0, epsilon=0.0, robust_lambda=1.0, lower=-np.inf, upper=np.inf, eps_draws=None):
     """`BayesByBackprop.step` (bayesbybackprop.py:46-170) for Dense MLPs with a softmax output and the sparse categorical
     cross-entropy, gradients written out by hand (the reference gets them from tf.GradientTape):
       W = mean + softplus(rho) * noise                                                    (:50-59)
       robust_train == 0: output = model_W(x)                                               (:65-72)
       robust_train == 1: (l, u) = IBP(x, W, eps), worst = softmax(u off the label, l on it),
                          output = lambda * model_W(x) + (1 - lambda) * worst                (:73-90)
+      robust_train == 3: output = mean over eps_draws of softmax(worst-case IBP logits at that eps)      (:102-121)
       robust_train == 2: x_adv = FGSM(x, eps) against W towards argmax model_W(x) (:92, attacks.py:81-102 with the
                          model's current weights), output = lambda * model_W(x) + (1 - lambda) * model_W(x_adv)   (:93-95)
       weight_gradient = dLoss/dW       (data term + kl_weight * d(log_q - log_prior)/dW)  (:138)
@@ -760,8 +761,26 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
         g1 = _mlp_backward_weights(dense, W, acts, dz)
         g2 = _ibp_backward_weights(dense, W, U, Lo, dzw * (1 - onehot), dzw * onehot)
         gW = [a + b for a, b in zip(g1, g2)]
+    elif robust_train == 3:
+        # :102-121 -- output = sum_k (1/K) softmax(worst-case IBP logits at eps_k); eps_k ~ Exponential(1 / epsilon) in the
+        # reference, injected here (eps_draws); the clean prediction is not part of the loss
+        K = len(eps_draws)
+        bounds, pws = [], []
+        out = np.zeros_like(pred)
+        for ek in eps_draws:
+            U, Lo, _ = _ibp_forward_bounds(dense, W, x, d(ek))
+            pw = _act("softmax", (1 - onehot) * U[-1] + onehot * Lo[-1])
+            bounds.append((U, Lo)); pws.append(pw)
+            out = out + d(1.0 / K) * pw
+        oy = out[np.arange(B), lab]
+        g = np.where((oy > 1e-7) & (oy < 1 - 1e-7), -1.0 / (B * oy), 0.0)
+        gW = None
+        for (U, Lo), pw in zip(bounds, pws):
+            dzw = (d(1.0 / K) * g * pw[np.arange(B), lab])[:, None] * (onehot - pw)
+            gk = _ibp_backward_weights(dense, W, U, Lo, dzw * (1 - onehot), dzw * onehot)
+            gW = gk if gW is None else [a + b for a, b in zip(gW, gk)]
     else:
-        raise NotImplementedError("oracle bbb_step: robust_train 0, 1 and 2")
+        raise NotImplementedError("oracle bbb_step: robust_train 0, 1, 2 and 3")
     data = sparse_categorical_crossentropy(lab, out, d)
     klc = log_q(W, mean, rho, d) - log_q(W, pm, [np.asarray(t, d) for t in prior_var], d)
     loss = data + d(kl_weight) * klc

@@ -756,7 +756,7 @@ def test_bbb_step_matches_oracle(oracle, dims, B):
     np.testing.assert_allclose(got[1], klc, rtol=2e-5)
     np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
     with pytest.raises(NotImplementedError):
-        db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, robust_train=3).step(x, lab, lr)
+        db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, robust_train=5).step(x, lab, lr)
 
 
 def test_bbb_training_learns(oracle):
@@ -928,6 +928,43 @@ def test_bbb_step_ibp_training_matches_oracle(oracle, hidden_act):
         b, _ = opt1.step(x, lab, lr, noise=noise)
         for i in range(len(a)):
             np.testing.assert_allclose(a[i], b[i], rtol=0, atol=1e-7)
+
+
+def test_bbb_step_ibp_mc_and_fgsm_mc_modes(oracle):
+    """robust_train = 3 (IBP averaged over injected epsilon draws, `dbx_bbb_step_ibp_mc`) against the oracle, and
+    robust_train = 4 (the same FGSM pass loss_mc times, :123-136) against the oracle's mode 2 at lambda = 0."""
+    import deepbayes_b200 as db
+    dims, B = [40, 24, 16, 6], 21
+    L = oracle.mlp(dims)
+    layers = [db.Dense(24, activation="relu", input_shape=(40,)), db.Dense(16, activation="relu"), db.Dense(6, activation="softmax")]
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    x = oracle.synthetic_x((B, 40), seed=0)
+    lab = np.random.Generator(np.random.Philox(3)).integers(0, 6, size=B)
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr, draws = 0.1, [0.03, 0.004, 0.011]
+    for rt in (3, 4):
+        opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.5,
+                                                      robust_train=rt, epsilon=0.05, rob_lam=0.3, loss_mc=3)
+        opt.posterior_mean = [m.copy() for m in mean]
+        opt.posterior_var = [oracle.inverse_softplus(s) for s in std]
+        rho0 = [r.copy() for r in opt.posterior_var]
+        nm, nr = opt.step(x, lab, lr, noise=noise, eps_draws=draws if rt == 3 else None)
+        if rt == 3:
+            want = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.5, robust_train=3, eps_draws=draws)
+        else:
+            want = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.5, robust_train=2,
+                                   epsilon=0.05, robust_lambda=0.0)
+        wm, wr, loss, klc, pred, W = want
+        for i in range(len(nm)):
+            dm, dr = np.abs(wm[i] - mean[i]).max() + 1e-12, np.abs(wr[i] - rho0[i]).max() + 1e-12
+            np.testing.assert_allclose(nm[i], wm[i], rtol=0, atol=5e-4 * dm + 1e-7)
+            np.testing.assert_allclose(nr[i], wr[i], rtol=0, atol=5e-4 * dr + 1e-7)
+        np.testing.assert_allclose(opt._last_loss.cpu().numpy()[0], loss, rtol=5e-5)
+        np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=2e-5, atol=1e-7)
+    # un-injected draws: Exponential with mean epsilon from the optimizer's own generator, one device call per step
+    opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, robust_train=3, epsilon=0.02, loss_mc=2)
+    opt.step(x, lab, lr)
+    assert np.isfinite(opt._last_loss.cpu().numpy()).all()
 
 
 def test_bbb_ibp_training_tightens_the_bounds(oracle):

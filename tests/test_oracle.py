@@ -424,6 +424,43 @@ def test_bbb_step_ibp_mode_gradient_by_finite_differences(oracle):
             np.testing.assert_allclose((mean64[i][idx] - nm[i][idx]) / lr, wg + mg, rtol=2e-5, atol=2e-8)
 
 
+def test_bbb_step_ibp_mc_mode_gradient_by_finite_differences(oracle):
+    """robust_train = 3 (bayesbybackprop.py:102-121): CE on the mean over epsilon draws of the worst-case softmax."""
+    L = oracle.mlp([12, 9, 7, 5])
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    rho = [oracle.inverse_softplus(s, np.float64) for s in std]
+    pm, pv = oracle.implicit_prior(L, 2.0)
+    x = oracle.synthetic_x((6, 12), seed=0).astype(np.float64)
+    lab = np.array([0, 1, 2, 3, 4, 0])
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr, kw, draws = 0.1, 0.7, [0.03, 0.004, 0.011]
+    nm, nr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho, pm, pv, x, lab, noise, lr, kl_weight=kw, robust_train=3, eps_draws=draws)
+    mean64 = [np.asarray(m, np.float64) for m in mean]
+
+    def f(W_, m_, r_):
+        out = 0
+        for ek in draws:
+            lo, hi = oracle.ibp_forward(L, W_, x, ek)
+            worst = oracle.worst_case_logits(lo, hi, lab, depth=5)
+            e = np.exp(worst - worst.max(1, keepdims=True))
+            out = out + e / e.sum(1, keepdims=True) / len(draws)
+        return oracle.sparse_categorical_crossentropy(lab, out) + kw * (oracle.log_q(W_, m_, r_) - oracle.log_q(W_, pm, pv))
+    assert abs(f(W, mean64, rho) - loss) < 1e-12
+    g = np.random.Generator(np.random.Philox(1))
+    h = 1e-6
+    for i in range(len(W)):
+        for _ in range(2):
+            idx = tuple(g.integers(0, d) for d in W[i].shape)
+
+            def bump(lst, sign):
+                out = [np.array(t, np.float64) for t in lst]
+                out[i][idx] += sign * h
+                return out
+            wg = (f(bump(W, 1), mean64, rho) - f(bump(W, -1), mean64, rho)) / (2 * h)
+            mg = (f(W, bump(mean64, 1), rho) - f(W, bump(mean64, -1), rho)) / (2 * h)
+            np.testing.assert_allclose((mean64[i][idx] - nm[i][idx]) / lr, wg + mg, rtol=2e-5, atol=2e-8)
+
+
 def test_oracle_matches_reference_ibp_state_run(oracle, golden_dir):
     """oracle.ibp_state against the reference's own verifiers.IBP_state (weight margin 0.5 sigma, explicit input box)."""
     ref = np.load(os.path.join(golden_dir, "reference_ibp.npz"))
