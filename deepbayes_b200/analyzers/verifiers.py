@@ -87,10 +87,19 @@ def _flat(weights):
 def IBP(model, inp, weights, eps, predict=False):
     """`IBP(model, inp, weights, eps, predict=False)` (verifiers.py:68-95) on the device: the logit interval
     (h_l, h_u) of the eps-ball around ``inp`` (clipped to [0,1]) under the explicit weight list ``weights``.
-    predict=True (un-clipped box, last activation applied to the bounds) is the regression branch and is not built.
-    Dense / Flatten models; fp32 arithmetic (the reference uses float64)."""
+    predict=True (:73-74, :92-94; the regression branch): the box inp -+ eps is NOT clipped and the last layer's
+    activation is applied to both bounds.  Dense / Conv2D (`propagate_conv2d`, :11-21) / pooling / Flatten layers; fp32
+    arithmetic (the reference's Dense part uses float64)."""
     if predict:
-        raise NotImplementedError("IBP(predict=True) (verifiers.py:73-74, :92-94) is not built")
+        eng = _engine_of(model)
+        a = np.asarray(inp, np.float32)
+        x2 = a.reshape(-1, eng.K)
+        e = np.float32(eps)
+        lo, hi = eng.ibp_state(x2 - e, x2 + e, _flat(weights), 0.0)
+        name = [l for l in eng.model.layers if l.kind in ("dense", "conv2d")][-1].activation.name
+        shape = a.shape[:-1] + (eng.C,)
+        from ..engine import device_activation
+        return (device_activation(name, lo.cpu().numpy()).reshape(shape), device_activation(name, hi.cpu().numpy()).reshape(shape))
     eng = _engine_of(model)
     a = np.asarray(inp, np.float32)
     lo, hi = eng.ibp_one(a.reshape(-1, eng.K), eps, _flat(weights), mode="fp32")

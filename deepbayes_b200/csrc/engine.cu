@@ -138,8 +138,9 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
     if (jb + 1024 > tab.src_end[ti])
       for (int i = ti; i + 1 < tab.n; ++i) ti += (j0 >= tab.src_end[i]) ? 1 : 0;
     const int rel = j0 - tab.src_off[ti];
-    if (!tab.is_bias[ti] && !tab.blocked8[ti] && tab.cols_pad[ti] == tab.cols[ti] && rel + 4 <= tab.size[ti]) {
-      // fast path: 4 elements of an unpadded kernel tensor -> one 8-byte store
+    if (!tab.is_bias[ti] && !tab.blocked8[ti] && tab.cols_pad[ti] == tab.cols[ti] && rel + 4 <= tab.size[ti] && ((tab.dst_off[ti] + rel) & 3) == 0) {
+      // fast path: 4 elements of an unpadded kernel tensor -> one 8-byte store (the tensor's flat offset need not be a
+      // multiple of 4 -- bias vectors of 5 or 6 entries before it -- in which case the store would be misaligned)
       uint2 v;
       v.x = tc_pack_bf16x2(w[0], w[1]);
       v.y = tc_pack_bf16x2(w[2], w[3]);

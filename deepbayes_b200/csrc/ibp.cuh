@@ -145,6 +145,71 @@ ibp_dense_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_
   }
 }
 
+// propagate_conv2d (verifiers.py:11-21).  Two quirks of the reference are kept: tf.nn.convolution is called with its defaults
+// (VALID padding, stride 1 -- the layer's own settings are not passed), and the nominal convolution is ADDED to both interval
+// sums: h_l = conv(mid, W) + [conv(x_l, W+) + conv(x_u, W-)] + b = 2 conv(mid, W) - conv(rad, |W|) + b, h_u likewise with +.
+// One thread per output element (NHWC x HWIO), centre and radius sums side by side.
+template <typename T>
+__global__ void ibp_conv_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_sstride, const T* __restrict__ Wbase,
+                                int64_t w_sstride, const int32_t* __restrict__ rows, int64_t row0, int64_t w_off, int ldw,
+                                const float* __restrict__ Bbase, int64_t b_sstride, int64_t b_off, T* __restrict__ n_mu,
+                                T* __restrict__ n_r, int64_t n_sstride, int NB, int H, int Wd, int Cin, int Ho, int Wo, int Cout,
+                                int kh, int kw, IbpOut o) {
+  const int s = blockIdx.y;
+  const int64_t wrow = rows ? (int64_t)rows[s] : (row0 + s);
+  const T* Mp = Amu + (int64_t)s * a_sstride;
+  const T* Rp = Ar + (int64_t)s * a_sstride;
+  const T* Wp = Wbase + wrow * w_sstride + w_off;
+  const float* bp = Bbase + wrow * b_sstride + b_off;
+  const int64_t total = (int64_t)NB * Ho * Wo * Cout;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(e % Cout);
+    int64_t r = e / Cout;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int nb = (int)(r / Ho);
+    float am = 0.f, ar = 0.f;
+    for (int i = 0; i < kh; ++i)
+      for (int j = 0; j < kw; ++j) {
+        const int64_t at = (((int64_t)nb * H + ho + i) * Wd + wo + j) * Cin;
+        const T* wp = Wp + ((int64_t)(i * kw + j) * Cin) * ldw + co;
+        for (int c = 0; c < Cin; ++c) {
+          const float w = to_f32<T>(wp[(int64_t)c * ldw]);
+          am = fmaf(to_f32<T>(Mp[at + c]), w, am);
+          ar = fmaf(to_f32<T>(Rp[at + c]), fabsf(w), ar);
+        }
+      }
+    ibp_store<T>(o, n_mu, n_r, n_sstride, s, (int)(e / Cout), co, Cout, 2.f * am + bp[co], ar);
+  }
+}
+
+// a weightless pooling layer is applied to each bound (verifiers.py:78-81): max-pool the upper and the lower bound
+template <typename T>
+__global__ void ibp_pool_kernel(const T* __restrict__ Amu, const T* __restrict__ Ar, int64_t a_sstride, T* __restrict__ n_mu,
+                                T* __restrict__ n_r, int64_t n_sstride, int NB, int H, int Wd, int C, int Ho, int Wo, int ph, int pw,
+                                int sh, int sw) {
+  const int s = blockIdx.y;
+  const T* Mp = Amu + (int64_t)s * a_sstride;
+  const T* Rp = Ar + (int64_t)s * a_sstride;
+  const int64_t total = (int64_t)NB * Ho * Wo * C;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    int64_t r = e / C;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int nb = (int)(r / Ho);
+    float hi = -INFINITY, lo = -INFINITY;
+    for (int i = 0; i < ph; ++i)
+      for (int j = 0; j < pw; ++j) {
+        const int64_t at = (((int64_t)nb * H + ho * sh + i) * Wd + wo * sw + j) * C + c;
+        const float m = to_f32<T>(Mp[at]), rr = to_f32<T>(Rp[at]);
+        hi = fmaxf(hi, m + rr); lo = fmaxf(lo, m - rr);
+      }
+    n_mu[(int64_t)s * n_sstride + e] = from_f32<T>((hi + lo) / 2.f);
+    n_r[(int64_t)s * n_sstride + e] = from_f32<T>((hi - lo) / 2.f);
+  }
+}
+
 // |W16| of one parameter range [off, off + len) of every sample (units of 8 bf16)
 __global__ void abs_bf16_range_kernel(const uint4* __restrict__ W, uint4* __restrict__ Wabs, int64_t sstride8, int64_t off8, int64_t len8) {
   const int64_t base = (int64_t)blockIdx.y * sstride8 + off8;
@@ -179,7 +244,15 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   // box_hi_dev != nullptr: x_dev / box_hi_dev are the lower / upper input bounds themselves (IBP_state); weight_margin > 0
   // widens every weight by margin * sigma (needs the Gaussian posterior's sigma; CUDA-core back end)
   constexpr bool kBf16 = !std::is_same<T, float>::value;
-  DBX_CHECK(m->is_mlp, "IBP on the device covers Dense / Flatten models (propagate_conv2d, verifiers.py:11-21, is not built)");
+  for (size_t li = 0; li < m->layers.size(); ++li) {
+    const Layer& L = m->layers[li];
+    if (L.kind != DBX_CONV2D) continue;
+    // tf.nn.convolution(x, w) in propagate_conv2d runs VALID / stride 1 whatever the layer says: any other layer would leave the
+    // reference with shapes that do not match its own next layer
+    DBX_CHECK(L.pad == DBX_PAD_VALID && L.sh == 1 && L.sw == 1, "IBP through Conv2D needs padding='valid' and strides 1 (propagate_conv2d, verifiers.py:11-21, calls tf.nn.convolution with its defaults)");
+    DBX_CHECK((int)li != m->last_weighted, "IBP: the output layer must be Dense");
+    DBX_CHECK(!(weight_margin > 0.f), "weight margins through Conv2D are not built");
+  }
   for (size_t li = 0; li + 1 < m->layers.size(); ++li) {
     const Layer& L = m->layers[li];
     DBX_CHECK(!L.has_w || (int)li == m->last_weighted || L.act != DBX_ACT_SOFTMAX,
@@ -266,7 +339,7 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     bool all_hidden = true;
     for (int li = 0; li < (int)m->layers.size(); ++li) {
       const Layer& L = m->layers[li];
-      if (!L.has_w || li == m->last_weighted) continue;
+      if (!L.has_w || li == m->last_weighted || L.kind != DBX_DENSE) continue;
       fused_layer[li] = ibp_tc_eligible(L.units, (int)L.in_feat) && (act_b / sizeof(T)) % 8 == 0;
       all_hidden = all_hidden && fused_layer[li];
     }
@@ -308,7 +381,15 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     int bi = 0;
     for (int li = 0; li < (int)m->layers.size(); ++li) {
       const Layer& L = m->layers[li];
-      if (!L.has_w) continue;    // Flatten
+      if (L.kind == DBX_MAXPOOL2D) {
+        T* p_mu = abuf[2 * bi]; T* p_r = abuf[2 * bi + 1];
+        dim3 grid((unsigned)grid_for(B * L.out_feat), (unsigned)nc);
+        DBX_LAUNCH(ibp_pool_kernel<T>, grid, 256, 0, st, cur_mu, cur_r, cur_ss, p_mu, p_r, act_ss, (int)B, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w,
+                   L.kh, L.kw, L.sh, L.sw);
+        cur_mu = p_mu; cur_r = p_r; cur_ss = act_ss; bi ^= 1;
+        continue;
+      }
+      if (!L.has_w) continue;    // Flatten (NHWC order is the flat order already)
       const bool last = (li == m->last_weighted);
       const int64_t woff = kBf16 ? L.w16_off : L.w_off;
       const int64_t boff = kBf16 ? L.b32_off : L.b_off;
@@ -318,7 +399,12 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
       T* n_mu = abuf[2 * bi]; T* n_r = abuf[2 * bi + 1];
       prof_begin(st);
       bool done = false;
-      if (kBf16 && use_tc && !last && fused_layer[li]) {
+      if (L.kind == DBX_CONV2D) {
+        dim3 grid((unsigned)grid_for(B * L.out_feat), (unsigned)nc);
+        DBX_LAUNCH(ibp_conv_kernel<T>, grid, 256, 0, st, cur_mu, cur_r, cur_ss, Wbase, w_sstride, rows, row0, woff, ldw, Bbase, b_sstride, boff,
+                   n_mu, n_r, act_ss, (int)B, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w, L.out_c, L.kh, L.kw, o);
+        done = true;
+      } else if (kBf16 && use_tc && !last && fused_layer[li]) {
         // hidden layer: centre + radius + combine in one kernel, |W| formed in the SM (no fallback: |W16| was not written for it)
         DBX_CHECK(ibp_tc_launch((const __nv_bfloat16*)cur_mu, (const __nv_bfloat16*)cur_r, cur_ss, cur_ss == 0 ? 1 : 0,
                                 (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff,

@@ -21,7 +21,8 @@ network).  The oracle is therefore pinned two ways, both weaker than a real gold
   (2) the two saved posteriors under Tutorials/PosteriorModels pin real inputs (mu, sigma,
       architecture).
   (3) the widened rows: make_reference_ibp_fixtures.py runs analyzers/verifiers.py (IBP,
-      chernoff_bound_verification) and make_reference_bbb_fixtures.py runs optimizers/losses.py
+      chernoff_bound_verification), make_reference_conv_ibp_fixtures.py runs its propagate_conv2d (with a NumPy
+      VALID / stride-1 loop for tf.nn.convolution) and make_reference_bbb_fixtures.py runs optimizers/losses.py
       (log_q, KL_Loss) the same way; the GRADIENTS of bbb_step / input_gradient replace
       tf.GradientTape, which cannot run on the stand-in, and are checked against finite
       differences of those pinned losses -- parity unpinned by a reference run for them.
@@ -504,8 +505,37 @@ def propagate_interval(W, b, x_l, x_u, marg=0.0, b_marg=0.0):
     return h_l, h_u
 
 
+def _conv_valid(x, k):
+    """tf.nn.convolution(x, k) with its defaults: NHWC x HWIO, VALID padding, stride 1."""
+    kh, kw, cin, cout = k.shape
+    n, h, w, c = x.shape
+    ho, wo = h - kh + 1, w - kw + 1
+    cols = np.empty((n, ho, wo, kh, kw, c), dtype=np.result_type(x.dtype, k.dtype))
+    for i in range(kh):
+        for j in range(kw):
+            cols[:, :, :, i, j, :] = x[:, i:i + ho, j:j + wo, :]
+    return (cols.reshape(n * ho * wo, kh * kw * c) @ k.reshape(kh * kw * c, cout)).reshape(n, ho, wo, cout)
+
+
+def propagate_conv2d(W, b, x_l, x_u, marg=0, b_marg=0):
+    """One Conv2D layer on an interval, exactly as verifiers.py:11-21 writes it:
+      w_pos = max(W + marg, 0), w_neg = min(W - marg, 0)
+      h_l = conv(x_l, w_pos) + conv(x_u, w_neg);  h_u = conv(x_u, w_pos) + conv(x_l, w_neg)
+      nom = conv((x_l + x_u) / 2, W);  h_l = nom + h_l + (b - b_marg);  h_u = nom + h_u + (b + b_marg)
+    i.e. the nominal response is ADDED to both interval sums (kept: it is what the reference computes), and
+    tf.nn.convolution runs with its defaults (VALID, stride 1) whatever the layer's padding / strides are.
+    Arithmetic in float64 here; TensorFlow computes it in the inputs' float32."""
+    W = np.asarray(W, np.float64)
+    x_l, x_u = np.asarray(x_l, np.float64), np.asarray(x_u, np.float64)
+    w_pos, w_neg = np.maximum(W + marg, 0), np.minimum(W - marg, 0)
+    h_l = _conv_valid(x_l, w_pos) + _conv_valid(x_u, w_neg)
+    h_u = _conv_valid(x_u, w_pos) + _conv_valid(x_l, w_neg)
+    nom = _conv_valid((x_l + x_u) / 2, W)
+    return nom + h_l + (np.asarray(b, np.float64) - b_marg), nom + h_u + (np.asarray(b, np.float64) + b_marg)
+
+
 def ibp_forward(layers, weights, x, eps, predict=False):
-    """`IBP(model, inp, weights, eps, predict)` (verifiers.py:68-95) for Dense / weightless layers:
+    """`IBP(model, inp, weights, eps, predict)` (verifiers.py:68-95) for Dense / Conv2D / weightless layers:
     input box clip(x -+ eps, 0, 1) (predict=False) or x -+ eps; every Dense through
     propagate_interval; the layer's activation on both bounds, except that with predict=False
     the LAST layer's activation is skipped (:90-91), i.e. the result is a logit interval.
@@ -521,9 +551,13 @@ def ibp_forward(layers, weights, x, eps, predict=False):
         if l.kind == "flatten":
             h_u, h_l = h_u.reshape(h_u.shape[0], -1), h_l.reshape(h_l.shape[0], -1)
             continue
-        if l.kind != "dense":
-            raise NotImplementedError("oracle IBP covers Dense / Flatten (propagate_conv2d, verifiers.py:11-21, is not restated)")
-        h_l, h_u = propagate_interval(weights[wi], weights[wi + 1], h_l, h_u)
+        if l.kind == "maxpool2d":          # a weightless layer is applied to each bound (:78-81)
+            h_u, h_l = _maxpool(h_u, l), _maxpool(h_l, l)
+            continue
+        if l.kind == "conv2d":
+            h_l, h_u = propagate_conv2d(weights[wi], weights[wi + 1], h_l, h_u)
+        else:
+            h_l, h_u = propagate_interval(weights[wi], weights[wi + 1], h_l, h_u)
         wi += 2
         if (not predict) and i >= len(layers) - 1:
             continue

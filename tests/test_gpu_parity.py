@@ -573,8 +573,13 @@ def test_ibp_matches_reference_run(oracle, golden_dir):
     # API shape and sample count of the drop-in function (device Philox noise: same distribution, other draws)
     got = verifiers.chernoff_bound_verification(pm, x[:1], eps, cls, confidence=0.75, delta=0.3)
     assert got.shape == (1, 10) and abs(got.sum() - n) < 1e-3
-    with pytest.raises(NotImplementedError):
-        verifiers.IBP(pm, x, pm.posterior_mean, eps, predict=True)
+    # predict=True (regression branch): un-clipped box, last activation on both bounds -- against the oracle restatement
+    lo_p, hi_p = verifiers.IBP(pm, x, pm.posterior_mean, eps, predict=True)
+    wl, wu = oracle.ibp_forward(oracle.mlp([784, 128, 10]), [np.asarray(t, np.float32) for t in pm.posterior_mean], x, eps, predict=True)
+    np.testing.assert_allclose(lo_p, wl, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(hi_p, wu, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(lo_p, ref["ibp_mean_predict_l"], rtol=1e-5, atol=2e-6)     # the reference's own run
+    np.testing.assert_allclose(hi_p, ref["ibp_mean_predict_u"], rtol=1e-5, atol=2e-6)
 
 
 def test_ibp_properties_and_bf16(oracle, monkeypatch):
@@ -631,6 +636,64 @@ def test_ibp_fused_layer_is_bit_identical_to_two_gemms(oracle, monkeypatch, dims
     assert eng.last_path() == "generic_tc"
     for k in want:
         np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_ibp_through_conv_layers_matches_oracle(oracle, mode):
+    """propagate_conv2d (verifiers.py:11-21) + pooling applied per bound (:78-81) + Dense on the device against
+    oracle.ibp_forward (whose conv part is pinned on a run of the reference's own function): sampled weights injected."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    m = db.Sequential([db.Conv2D(8, 3, activation="relu", input_shape=(12, 10, 2)), db.Conv2D(6, (2, 3), activation="tanh"),
+                       db.MaxPooling2D(2), db.Flatten(), db.Dense(24, activation="relu"), db.Dense(5, activation="softmax")])
+    L = [oracle.Conv2D(3, 3, 2, 8, "relu"), oracle.Conv2D(2, 3, 8, 6, "tanh"), oracle.MaxPool2D((2, 2)), oracle.Flatten(),
+         oracle.Dense(4 * 3 * 6, 24, "relu"), oracle.Dense(24, 5, "softmax")]
+    eng = Engine(m)
+    mean, std = oracle.synthetic_posterior(L, seed=5, sigma_scale=0.3)
+    eng.set_gaussian(mean, std)
+    B, n, eps = 7, 3, 0.01
+    x = oracle.synthetic_x((B, 12, 10, 2), seed=2)
+    labels = np.random.Generator(np.random.Philox(3)).integers(0, 5, size=B).astype(np.int32)
+    noise = oracle.synthetic_eps(L, n, seed=2)
+    nf = np.stack([oracle.flatten_list(e) for e in noise])
+    out = eng.ibp_predict(x, eps, labels, n, noise=nf, mode=mode, want=("worst", "lower", "upper", "counts"))
+    want_l = np.zeros((B, 5)); want_u = np.zeros((B, 5))
+    for s in range(n):
+        w = oracle.sample_gaussian(mean, std, noise[s], order="f32")
+        lo, hi = oracle.ibp_forward(L, w, x, eps)
+        want_l += lo; want_u += hi
+    scale = max(np.abs(want_l).max(), np.abs(want_u).max())
+    tol = dict(rtol=1e-5, atol=3e-6 * scale) if mode == "fp32" else dict(rtol=0, atol=3e-2 * scale)
+    np.testing.assert_allclose(out["lower"].cpu().numpy(), want_l, **tol)
+    np.testing.assert_allclose(out["upper"].cpu().numpy(), want_u, **tol)
+    assert (out["lower"] <= out["upper"]).all()
+    if mode == "fp32":
+        # explicit weights through the drop-in function; SAME padding is refused loudly (the reference's call ignores it)
+        lo1, hi1 = eng.ibp_one(x.reshape(B, -1), eps, oracle.flatten_list(mean), mode="fp32")
+        wl, wu = oracle.ibp_forward(L, mean, x, eps)
+        np.testing.assert_allclose(lo1.cpu().numpy(), wl, rtol=1e-5, atol=3e-6 * scale)
+        np.testing.assert_allclose(hi1.cpu().numpy(), wu, rtol=1e-5, atol=3e-6 * scale)
+        m2 = db.Sequential([db.Conv2D(4, 3, padding="same", activation="relu", input_shape=(6, 6, 1)), db.Flatten(), db.Dense(3, activation="softmax")])
+        e2 = Engine(m2)
+        e2.set_gaussian(np.zeros(e2.P, np.float32), np.ones(e2.P, np.float32))
+        with pytest.raises(Exception, match="valid"):
+            e2.ibp_predict(np.zeros((1, 6, 6, 1), np.float32), 0.1, [0], 2, mode="fp32", want=("worst",))
+
+
+def test_bf16_sampler_with_tensors_at_odd_offsets(oracle):
+    """Kernel tensors whose flat Keras offset is not a multiple of 4 (bias vectors of 5 / 6 entries in front of them): the
+    bf16 sampler's 8-byte store path must not be taken for them (it was: misaligned address).  bf16 vs fp32 predict."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    m = db.Sequential([db.Conv2D(6, 3, activation="relu", input_shape=(9, 9, 2)), db.Flatten(), db.Dense(24, activation="relu"),
+                       db.Dense(5, activation="relu"), db.Dense(8, activation="softmax")])
+    eng = Engine(m)
+    g = np.random.Generator(np.random.Philox(5))
+    eng.set_gaussian((g.standard_normal(eng.P) * 0.1).astype(np.float32), np.full(eng.P, 0.02, np.float32))
+    x = oracle.synthetic_x((11, 9, 9, 2), seed=3)
+    a, _ = eng.predict_sums(x, 6, seed=2, mode="bf16")
+    b, _ = eng.predict_sums(x, 6, seed=2, mode="fp32")
+    np.testing.assert_allclose(a.cpu().numpy() / 6, b.cpu().numpy() / 6, rtol=0, atol=BF16_ATOL)
 
 
 def test_massart_with_ibp(tmp_path, oracle):

@@ -461,6 +461,29 @@ def test_bbb_step_ibp_mc_mode_gradient_by_finite_differences(oracle):
             np.testing.assert_allclose((mean64[i][idx] - nm[i][idx]) / lr, wg + mg, rtol=2e-5, atol=2e-8)
 
 
+def test_oracle_propagate_conv2d_matches_reference_run(oracle, golden_dir):
+    """oracle.propagate_conv2d against the reference's own verifiers.propagate_conv2d (:11-21) executed on NumPy stand-ins
+    (tests/golden/make_reference_conv_ibp_fixtures.py), and its algebra: the reference ADDS the nominal convolution to both
+    interval sums, so centre = 2 conv(mid, W) + b and radius = conv(rad, |W|)."""
+    ref = np.load(os.path.join(golden_dir, "reference_conv_ibp.npz"))
+    for tag in ("a", "b"):
+        W, b, xl, xu = ref[tag + "_W"], ref[tag + "_b"], ref[tag + "_xl"], ref[tag + "_xu"]
+        lo, hi = oracle.propagate_conv2d(W, b, xl, xu)
+        np.testing.assert_allclose(lo, ref[tag + "_l"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(hi, ref[tag + "_u"], rtol=1e-12, atol=1e-12)
+        mid, rad = (xl + xu) / 2, (xu - xl) / 2
+        np.testing.assert_allclose((hi + lo) / 2, 2 * oracle._conv_valid(mid, W) + b, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose((hi - lo) / 2, oracle._conv_valid(rad, np.abs(W)), rtol=1e-10, atol=1e-12)
+    # IBP through a small conv net: eps = 0 collapses the interval (onto the quirk's doubled-conv network, not the forward)
+    L = [oracle.Conv2D(3, 3, 2, 4, "relu"), oracle.MaxPool2D((2, 2)), oracle.Flatten(), oracle.Dense(36, 5, "softmax")]
+    mean, _ = oracle.synthetic_posterior(L, seed=3)
+    x = oracle.synthetic_x((3, 8, 8, 2), seed=1)
+    lo, hi = oracle.ibp_forward(L, mean, x, 0.0)
+    np.testing.assert_allclose(lo, hi, rtol=0, atol=1e-12)
+    lo2, hi2 = oracle.ibp_forward(L, mean, x, 0.01)
+    assert (lo2 <= lo + 1e-12).all() and (hi <= hi2 + 1e-12).all()
+
+
 def test_oracle_matches_reference_ibp_state_run(oracle, golden_dir):
     """oracle.ibp_state against the reference's own verifiers.IBP_state (weight margin 0.5 sigma, explicit input box)."""
     ref = np.load(os.path.join(golden_dir, "reference_ibp.npz"))
