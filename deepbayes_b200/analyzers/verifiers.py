@@ -137,8 +137,18 @@ def chernoff_bound_verification(model, inp, eps, cls, **kwargs):
     x2 = a.reshape(-1, eng.K)
     labels = np.broadcast_to(np.asarray(cls, np.int32).reshape(-1), (x2.shape[0],))
     s0 = model._take_ids(n)
-    out = eng.ibp_predict(x2, eps, labels, n, model.seed, s0, None, 1.0, mode, want=("worst",))
-    return out["worst"].cpu().numpy().reshape(a.shape[:-1] + (eng.C,))
+    # samples are independent: with model.shard the n global sample ids are split over the torch.distributed ranks and ONE
+    # all-reduce(SUM) of the [B,C] buffer combines them (same ids for every world size)
+    from .. import distributed as _dd
+    rank, ws = _dd.world() if getattr(model, "shard", False) else (0, 1)
+    off, cnt = _dd.shard_range(n, rank, ws)
+    if cnt > 0:
+        worst = eng.ibp_predict(x2, eps, labels, cnt, model.seed, s0 + off, None, 1.0, mode, want=("worst",))["worst"]
+    else:
+        worst = eng.torch.zeros((x2.shape[0], eng.C), dtype=eng.torch.float32, device=eng.device)
+    if ws > 1:
+        _dd.allreduce_sum_(worst)
+    return worst.cpu().numpy().reshape(a.shape[:-1] + (eng.C,))
 
 
 def massart_bound_check(model, inp, eps, predicate=None, **kwargs):

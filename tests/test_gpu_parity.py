@@ -243,6 +243,13 @@ def test_sample_split_independence(ctx):
         b1, _ = eng.predict_sums(c["x"], 4, seed=5, s0=100, mode=mode)
         b2, _ = eng.predict_sums(c["x"], 6, seed=5, s0=104, mode=mode)
         np.testing.assert_allclose(a.cpu().numpy(), (b1 + b2).cpu().numpy(), rtol=1e-5, atol=tol)
+    # the interval forward shards the same way (chernoff_bound_verification with model.shard)
+    for mode in ("fp32", "bf16"):
+        a = eng.ibp_predict(c["x"], 0.01, c["labels"], 10, seed=5, s0=100, mode=mode, want=("worst", "counts"))
+        b1 = eng.ibp_predict(c["x"], 0.01, c["labels"], 4, seed=5, s0=100, mode=mode, want=("worst", "counts"))
+        b2 = eng.ibp_predict(c["x"], 0.01, c["labels"], 6, seed=5, s0=104, mode=mode, want=("worst", "counts"))
+        np.testing.assert_allclose(a["worst"].cpu().numpy(), (b1["worst"] + b2["worst"]).cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(a["counts"].cpu().numpy(), (b1["counts"] + b2["counts"]).cpu().numpy())
     cnt = eng.count_predicate(c["x"], c["labels"], 64, seed=5, s0=0, mode="bf16").cpu().numpy()
     c1 = eng.count_predicate(c["x"], c["labels"], 24, seed=5, s0=0, mode="bf16").cpu().numpy()
     c2 = eng.count_predicate(c["x"], c["labels"], 40, seed=5, s0=24, mode="bf16").cpu().numpy()
