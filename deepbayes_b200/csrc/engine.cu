@@ -708,9 +708,11 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
     // ---- layers
     const T* cur = x_in; int64_t cur_ss = 0;  // layer-0 input is shared by all samples
     T* bufs[2] = {act0, act1}; int bi = 0;
+    bool pooled_next = false;
     for (int li = 0; li < (int)m->layers.size(); ++li) {
       const Layer& L = m->layers[li];
       if (L.kind == DBX_FLATTEN) continue;
+      if (pooled_next) { pooled_next = false; continue; }      // this MaxPool ran in the previous convolution's epilogue
       const bool last = (li == m->last_weighted);
       const int64_t woff = kBf16 ? L.w16_off : L.w_off;
       const int64_t boff = kBf16 ? L.b32_off : L.b_off;
@@ -735,6 +737,12 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
                                     (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff, act,
                                     last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units, last ? logits : nullptr,
                                     B * C, st) == 0;
+        } else if (L.kind == DBX_CONV2D && !last && !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1') &&
+                   li + 1 < (int)m->layers.size() && conv_tc_pool_eligible(L, m->layers[li + 1]) && (B * m->layers[li + 1].out_feat) % 8 == 0 &&
+                   conv_tc_launch(A16, cur_ss, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L, Bbase, b_sstride,
+                                  boff, act, (__nv_bfloat16*)bufs[bi], B * m->layers[li + 1].out_feat, st, 1) == 0) {
+          done_tc = true;      // direct convolution with the following 2x2 max-pool done in its epilogue: the full-resolution map
+          pooled_next = true;  // (4x the bytes) is never written
         } else if (L.kind == DBX_CONV2D && !last && !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1') &&
                    conv_tc_launch(A16, cur_ss, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L, Bbase, b_sstride,
                                   boff, act, (__nv_bfloat16*)bufs[bi], B * L.out_feat, st) == 0) {
@@ -790,7 +798,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
       if (L.has_w)
         prof_end(st, 2.0 * (double)L.w_rows * L.w_cols * (L.kind == DBX_CONV2D ? (double)L.out_h * L.out_w : 1.0) * (double)B * nc);
       if (last) break;
-      cur = bufs[bi]; cur_ss = B * L.out_feat; bi ^= 1;
+      cur = bufs[bi]; cur_ss = B * (pooled_next ? m->layers[li + 1].out_feat : L.out_feat); bi ^= 1;
     }
     // ---- sink
     const int act_last = m->layers[m->last_weighted].act;

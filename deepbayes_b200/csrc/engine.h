@@ -128,9 +128,10 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
                          const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
                          long long o16_sstride, int ld16, float* out32, long long o32_sstride, cudaStream_t st);
 bool conv_tc_eligible(const Layer& L);
+bool conv_tc_pool_eligible(const Layer& L, const Layer& P);
 int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared, const __nv_bfloat16* W16, long long w_sstride_elems,
                    int ldw, int ns, int NB, const Layer& L, const float* bias, long long b_sstride, long long b_off, int act,
-                   __nv_bfloat16* out, long long o_sstride, cudaStream_t st);
+                   __nv_bfloat16* out, long long o_sstride, cudaStream_t st, int pool = 0);
 bool ibp_tc_eligible(int N, int K);
 int ibp_tc_launch(const __nv_bfloat16* Amu, const __nv_bfloat16* Ar, long long a_sstride, int a_shared, const __nv_bfloat16* Wbase,
                   long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride, long long b_off,

@@ -546,6 +546,8 @@ struct ConvParams {
   int patch;   // one input patch [R+kh-1][Wo+kw-1][Cin] per tile serves all taps (see conv_tc_kernel); implies w_res
   int PW, base_off;
   int w_res;   // the whole kernel tensor of a sample stays in shared memory while the CTA works on that sample
+  int stages;  // A-ring depth (<= kCStages; fewer when the pooled epilogue needs its staging tile)
+  int pool;    // 1: the layer is followed by MaxPool 2x2 / stride 2 and the epilogue writes the POOLED map [ns][NB][Ho/2][Wo/2][Cout]
   const float* bias; long long b_sstride, b_off;
   __nv_bfloat16* out; long long o_sstride;
 };
@@ -575,7 +577,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stage_b = a_bytes + (p.w_res ? 0 : w_tap_b);
   const uint32_t s_wres = s_stage;
   const uint32_t s_ring = s_stage + w_res_b;
-  CBarriers* bars = (CBarriers*)(smem + w_res_b + kCStages * stage_b);
+  CBarriers* bars = (CBarriers*)(smem + w_res_b + p.stages * stage_b);
+  uint8_t* pool_stage = (uint8_t*)bars + ((sizeof(CBarriers) + 15) / 16) * 16;      // pool mode: [128 accumulator rows][Cout] bf16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = (long long)p.ns * p.NB * p.tiles_per_img;
   const int NT = nblk * 64;
@@ -612,7 +615,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode(t, ho0, nb, s);
       if (p.w_res && s != cur_s) {
         // new sample: every MMA that read the old weights has retired once the last tap's commit has arrived
-        if (g > 0) mbar_wait(smem_u32(&bars->empty[(g - 1) % kCStages]), ((g - 1) / kCStages) & 1);
+        if (g > 0) mbar_wait(smem_u32(&bars->empty[(g - 1) % p.stages]), ((g - 1) / p.stages) & 1);
         if (elect_one()) {
           const uint32_t wf = smem_u32(&bars->w_full);
           mbar_expect_tx(wf, (uint32_t)w_res_b);
@@ -626,7 +629,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ONE box per tile: input rows ho0-pad_t .. +R+kh-2, columns -pad_l .. +PW-1 (zeros outside the image); the taps
         // are address offsets into it.  (Per-tap boxes cost 9 x 112 TMA rows of 64 B per tile, and the TMA row rate, not
         // bandwidth or latency, bounded the kernel.)
-        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        const uint32_t st = g % p.stages, ph = (g / p.stages) & 1;
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->full[st]);
@@ -638,7 +641,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         continue;
       }
       for (int tap = 0; tap < taps; ++tap, ++g) {
-        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        const uint32_t st = g % p.stages, ph = (g / p.stages) & 1;
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->full[st]);
@@ -671,7 +674,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
       fence_after_sync();
       if (p.patch) {
-        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        const uint32_t st = g % p.stages, ph = (g / p.stages) & 1;
         mbar_wait(smem_u32(&bars->full[st]), ph);
         if (elect_one()) {
           const uint32_t base = (s_ring + st * stage_b) & 0x3FFFF;
@@ -694,7 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         continue;
       }
       for (int tap = 0; tap < taps; ++tap, ++g) {
-        const uint32_t st = g % kCStages, ph = (g / kCStages) & 1;
+        const uint32_t st = g % p.stages, ph = (g / p.stages) & 1;
         mbar_wait(smem_u32(&bars->full[st]), ph);
         if (elect_one()) {
           const uint32_t a16 = ((s_ring + st * stage_b) & 0x3FFFF) >> 4;
@@ -731,6 +734,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const bool valid = r < p.R && wo < p.Wo && ho0 + r < p.Ho;
       __nv_bfloat16* dst = p.out + (long long)s * p.o_sstride + ((((long long)nb * p.Ho + ho0 + r) * p.Wo + wo) * p.Cout);
+      // pool mode: the activated bf16 row goes to the staging tile instead (16-byte chunks XOR-swizzled so that the 32 row-wise
+      // writes of a warp spread over all banks: rows of Cout * 2 <= 128 bytes)
+      const int nchunk = p.Cout >> 3;                                   // 16-byte chunks per row (1, 2, 4 or 8 in pool mode)
+      const int swz = p.pool ? ((row / (8 / nchunk)) & (nchunk - 1)) : 0;
+      uint8_t* srow = pool_stage + row * (p.Cout * 2);
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
       for (int c0 = 0; c0 < NT; c0 += 32) {
@@ -742,7 +750,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
         }
-        if (valid) {
+        if (valid || p.pool) {
 #pragma unroll
           for (int q8 = 0; q8 < 4; ++q8) {
             const int c = c0 + q8 * 8;
@@ -752,13 +760,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 4; ++i)
                 w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
                                    act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
-              *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
-            } else {
+              if (p.pool) *reinterpret_cast<uint4*>(srow + (((c >> 3) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              else *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else if (!p.pool) {
               for (int i = 0; i < 8; ++i)
                 if (c + i < p.Cout) dst[c + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
             }
           }
         }
+      }
+      if (p.pool) {
+        // 2x2 / stride-2 max over the staged tile: R (even) output rows x Wo columns -> R/2 x Wo/2 pooled pixels, one 16-byte
+        // channel chunk per task, written as full NHWC rows of the pooled map (packed bf16x2 max, like maxpool_bf16_vec8_kernel)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int pw_n = p.Wo >> 1, PHo = p.Ho >> 1;
+        const int tasks = (p.R >> 1) * pw_n * nchunk;
+        const int pitch = p.Cout * 2;
+        for (int j = tid - 64; j < tasks; j += 128) {
+          const int q = j % nchunk, pp = j / nchunk;
+          const int pr = pp / pw_n, pc = pp - pr * pw_n;
+          const int prow = (ho0 >> 1) + pr;
+          if (prow >= PHo) continue;
+          const int a0 = (2 * pr) * rw + 2 * pc;
+          uint4 m4;
+          {
+            const int rws[4] = {a0, a0 + 1, a0 + rw, a0 + rw + 1};
+            __nv_bfloat162 acc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int rr = rws[e];
+              const int sz = (rr / (8 / nchunk)) & (nchunk - 1);
+              const uint4 t4 = *reinterpret_cast<const uint4*>(pool_stage + rr * pitch + ((q ^ sz) << 4));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = e == 0 ? h[i] : __hmax2(acc[i], h[i]);
+            }
+            m4 = *reinterpret_cast<const uint4*>(acc);
+          }
+          __nv_bfloat16* po = p.out + (long long)s * p.o_sstride + ((((long long)nb * PHo + prow) * pw_n + pc) * p.Cout) + q * 8;
+          *reinterpret_cast<uint4*>(po) = m4;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the staging tile is free for the next tile
       }
     }
   }
@@ -1158,19 +1200,25 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
 
 // dynamic shared memory of conv_tc_kernel.  The kernel tensor stays resident when it is at most 40 KB; then, if
 // R = 128 / (Wo + kw - 1) >= 1 output rows fit the 128 accumulator rows, one input patch per tile serves all taps.
-static int conv_tc_smem(const Layer& L, int* w_res, int* patch, int* R_out) {
+static int conv_tc_smem(const Layer& L, int* w_res, int* patch, int* R_out, int pool = 0, int* stages_out = nullptr) {
   const int Cin = L.in_c, taps = L.kh * L.kw, nblk = (L.out_c + 63) / 64;
   const int w_tap_b = nblk * Cin * 128;
   const int res = taps * w_tap_b <= 40 * 1024 ? 1 : 0;
   const int PW = L.out_w + L.kw - 1;
   int pm = (res && PW <= 128) ? 1 : 0;
   if (const char* e = getenv("DBX_CONV_PATCH")) pm = pm && atoi(e) != 0;
-  const int R = std::min(pm ? 128 / PW : 128 / L.out_w, L.out_h);
+  int R = std::min(pm ? 128 / PW : 128 / L.out_w, L.out_h);
+  if (pool) R &= ~1;                                   // pooling windows must not straddle tiles
   const int a_bytes = pm ? (((L.kh - 1) * PW + L.kw - 1 + 128) * Cin * 2 + 1023) / 1024 * 1024 : 128 * Cin * 2;
   if (w_res) *w_res = res;
   if (patch) *patch = pm;
   if (R_out) *R_out = R;
-  return (res ? taps * w_tap_b + kCStages * a_bytes : kCStages * (a_bytes + w_tap_b)) + (int)sizeof(CBarriers) + 1024;
+  const int fixed = (res ? taps * w_tap_b : 0) + ((int)sizeof(CBarriers) + 15) / 16 * 16 + 1024 + (pool ? 128 * L.out_c * 2 : 0);
+  const int per_stage = res ? a_bytes : a_bytes + w_tap_b;
+  int stages = kCStages;
+  if (pool) while (stages > 2 && fixed + stages * per_stage > 110 * 1024) --stages;      // two CTAs per SM
+  if (stages_out) *stages_out = stages;
+  return fixed + stages * per_stage;
 }
 
 // layer-level part of conv_tc_launch's scope test (the executor sizes its im2col buffer with it)
@@ -1184,15 +1232,26 @@ bool conv_tc_eligible(const Layer& L) {
 // Direct convolution launch.  in: bf16 NHWC [ns or 1][NB][H][W][Cin]; W16: the sample's HWIO kernel as [kh*kw*Cin][ldw] bf16
 // rows; out: bf16 NHWC [ns][NB][Ho][Wo][Cout].  Returns 1 when the layer is outside the kernel's scope (the caller then
 // uses im2col + dense_tc_kernel).
+// Can the 2x2 / stride-2 MaxPool behind this convolution be done in its epilogue?
+bool conv_tc_pool_eligible(const Layer& L, const Layer& P) {
+  if (!conv_tc_eligible(L) || P.kind != DBX_MAXPOOL2D || P.kh != 2 || P.kw != 2 || P.sh != 2 || P.sw != 2) return false;
+  if (const char* e = getenv("DBX_NO_POOL_FUSE")) if (e[0] == '1') return false;
+  const int Cout = L.out_c;
+  if (!(Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64) || L.out_h < 2 || L.out_w < 2) return false;
+  int R = 0, stages = 0;
+  const int smem = conv_tc_smem(L, nullptr, nullptr, &R, 1, &stages);
+  return R >= 2 && stages >= 3 && smem <= 110 * 1024;
+}
+
 int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared, const __nv_bfloat16* W16, long long w_sstride_elems,
                    int ldw, int ns, int NB, const Layer& L, const float* bias, long long b_sstride, long long b_off, int act,
-                   __nv_bfloat16* out, long long o_sstride, cudaStream_t st) {
+                   __nv_bfloat16* out, long long o_sstride, cudaStream_t st, int pool) {
   if (!g_tc_ok || !get_encode_fn()) return 1;
   const int Cin = L.in_c, Cout = L.out_c, Wo = L.out_w, Ho = L.out_h;
   if (!conv_tc_eligible(L)) return 1;
   if ((in_sstride & 7) || (o_sstride & 7) || (ldw & 7) || ((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return 1;
-  int w_res = 0, patch = 0, R = 1;
-  const int smem = conv_tc_smem(L, &w_res, &patch, &R);
+  int w_res = 0, patch = 0, R = 1, stages = kCStages;
+  const int smem = conv_tc_smem(L, &w_res, &patch, &R, pool, &stages);
   const int PW = Wo + L.kw - 1;
   CUtensorMap tmA, tmW;
   {
@@ -1211,7 +1270,7 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
   ConvParams p = {};
   p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.kh = L.kh; p.kw = L.kw; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
   p.R = R; p.tiles_per_img = (int)cdiv(Ho, R); p.ns = ns; p.a_shared = in_shared; p.act = act; p.w_res = w_res;
-  p.patch = patch; p.PW = PW; p.base_off = 0;
+  p.patch = patch; p.PW = PW; p.base_off = 0; p.stages = stages; p.pool = pool;
   if (const char* e = getenv("DBX_CONV_BASEOFF")) p.base_off = atoi(e);
   p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.out = out; p.o_sstride = o_sstride;
   static int num_sms = 0;

@@ -785,6 +785,37 @@ def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
     np.testing.assert_allclose(p1.cpu().numpy() / n, i1.cpu().numpy() / n, rtol=0, atol=1.5e-3)
 
 
+@pytest.mark.parametrize("shape,c1,c2,pad", [((13, 11, 3), 16, 32, "valid"), ((20, 18, 3), 32, 64, "same"), ((9, 30, 3), 16, 8, "valid"),
+                                            ((32, 32, 3), 32, 64, "valid")])
+def test_conv_with_fused_maxpool_is_bit_identical(oracle, monkeypatch, shape, c1, c2, pad):
+    """conv_tc_kernel with the following 2x2 / stride-2 MaxPool done in its epilogue (staged tile in shared memory, packed
+    bf16x2 max, pooled NHWC rows out) against the same kernel + maxpool_bf16_vec8_kernel: same bf16 values before the max,
+    so the same bits after it.  Odd output heights / widths (the last row / column is dropped), SAME padding, Cout = 8 .. 64."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    m = db.Sequential([db.Conv2D(c1, 3, activation="relu", input_shape=shape), db.Conv2D(c2, 3, padding=pad, activation="relu"),
+                       db.MaxPooling2D(2), db.Flatten(), db.Dense(16, activation="relu"), db.Dense(10, activation="softmax")])
+    eng = Engine(m)
+    g = np.random.Generator(np.random.Philox(23))
+    eng.set_gaussian((g.standard_normal(eng.P) * 0.08).astype(np.float32), np.full(eng.P, 0.01, np.float32))
+    B, n = 19, 30
+    x = oracle.synthetic_x((B,) + shape, seed=4)
+    monkeypatch.setenv("DBX_NO_POOL_FUSE", "1")
+    a1, a2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
+    k0 = _lib_launches()
+    monkeypatch.setenv("DBX_NO_POOL_FUSE", "0")
+    b1, b2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
+    k1 = _lib_launches()
+    monkeypatch.setenv("DBX_NO_POOL_FUSE", "1")
+    eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
+    k2 = _lib_launches()
+    assert k1 - k0 < k2 - k1          # the pooling launches are gone
+    np.testing.assert_array_equal(a1.cpu().numpy(), b1.cpu().numpy())
+    np.testing.assert_array_equal(a2.cpu().numpy(), b2.cpu().numpy())
+    f1, _ = eng.predict_sums(x, n, seed=9, mode="fp32")
+    np.testing.assert_allclose(b1.cpu().numpy() / n, f1.cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
+
+
 def _lib_launches():
     from deepbayes_b200 import _lib
     return _lib.launch_count()
