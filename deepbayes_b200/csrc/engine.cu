@@ -985,6 +985,7 @@ int dbx_destroy(dbx_handle h) {
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_posterior) cudaEventDestroy(h->ev_posterior);
   if (h->ibp_side) cudaStreamDestroy(h->ibp_side);
+  if (h->ibp_main) cudaStreamDestroy(h->ibp_main);
   for (cudaEvent_t e : h->ibp_ev) if (e) cudaEventDestroy(e);
   delete h;
   return 0;

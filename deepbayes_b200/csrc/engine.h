@@ -77,7 +77,8 @@ struct dbx_model {
   cudaStream_t own_stream = nullptr;
   void* fused_state = nullptr;  // owned by fused_mlp.cu
   cudaStream_t ibp_side = nullptr;  // interval forward: weights of chunk c+1 are drawn here while chunk c is in the GEMMs
-  cudaEvent_t ibp_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // entry, sampled[2], consumed[2]
+  cudaStream_t ibp_main = nullptr;  // ... and the GEMM chain here (high priority)
+  cudaEvent_t ibp_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // entry, sampled[2], consumed[2], done
 };
 
 namespace dbx {

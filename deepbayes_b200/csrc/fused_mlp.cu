@@ -1525,6 +1525,8 @@ struct FusedState {
   int num_sms = 0;
   // weight sampling of chunk c+1 runs on a side stream while chunk c is in the fused kernel
   cudaStream_t side = nullptr;
+  cudaStream_t main = nullptr;   // high priority: the fused kernels (see fused_mlp_run)
+  cudaEvent_t ev_join = nullptr, ev_done = nullptr;
   bool used = false;   // ev_entry holds the end of the previous call's device work
   bool consumed_rec[2] = {false, false};          // ev_consumed[b] was recorded by a previous call ...
   size_t lay_x = 0, lay_w = 0, lay_b = 0;         // ... whose workspace layout was this
@@ -1621,24 +1623,55 @@ static inline int grid_for2(int64_t total, int block = 256) {
   return (int)std::min<int64_t>(std::max<int64_t>(cdiv(total, block), 1), 148 * 16);
 }
 
-int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
-                  cudaStream_t st) {
-  if (!shape_supported(m)) return 0;
-  if (!get_encode_fn()) return 0;
+static FusedState* fused_state_of(dbx_model* m) {
   FusedState* fs = (FusedState*)m->fused_state;
   if (!fs) {
     fs = new FusedState();
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete fs; return -1; }
+    if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete fs; return nullptr; }
     fs->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&fs->side, cudaStreamNonBlocking) != cudaSuccess) { delete fs; return -1; }
+    if (cudaStreamCreateWithFlags(&fs->side, cudaStreamNonBlocking) != cudaSuccess) { delete fs; return nullptr; }
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&fs->main, cudaStreamNonBlocking, hi) != cudaSuccess) { delete fs; return nullptr; }
     cudaEventCreateWithFlags(&fs->ev_entry, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&fs->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&fs->ev_done, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) {
       cudaEventCreateWithFlags(&fs->ev_sampled[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&fs->ev_consumed[i], cudaEventDisableTiming);
     }
     m->fused_state = fs;
   }
+  return fs;
+}
+
+static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink, cudaStream_t st);
+
+// The fused kernels run on a HIGH-priority stream of the engine's own, joined with the caller's stream at both ends: the
+// sampler of the next chunk shares the SMs with them from a default-priority side stream, and at every chunk boundary the
+// next fused launch's CTA pairs then get SM slots ahead of the sampler's queued blocks (DBX_FUSED_PRIO=0: caller's stream).
+int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
+                  cudaStream_t st_user) {
+  if (!shape_supported(m)) return 0;
+  if (!get_encode_fn()) return 0;
+  FusedState* fs = fused_state_of(m);
+  if (!fs) return -1;
+  bool prio = true;
+  if (const char* e = getenv("DBX_FUSED_PRIO")) prio = atoi(e) != 0;
+  if (!prio) return fused_mlp_run_on(m, x_dev, B, n, src, sink, st_user);
+  if (cudaEventRecord(fs->ev_join, st_user) != cudaSuccess || cudaStreamWaitEvent(fs->main, fs->ev_join, 0) != cudaSuccess) return -1;
+  const int rc = fused_mlp_run_on(m, x_dev, B, n, src, sink, fs->main);
+  if (cudaEventRecord(fs->ev_done, fs->main) != cudaSuccess || cudaStreamWaitEvent(st_user, fs->ev_done, 0) != cudaSuccess) return -1;
+  return rc;
+}
+
+static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
+                            cudaStream_t st) {
+  if (!shape_supported(m)) return 0;
+  if (!get_encode_fn()) return 0;
+  FusedState* fs = fused_state_of(m);
+  if (!fs) return -1;
   std::vector<const Layer*> dl;
   for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
   const int NH = (int)dl.size() - 1, H = dl[0]->units, K0 = (int)m->in_feat, C = (int)m->out_feat;
@@ -1868,6 +1901,9 @@ void fused_mlp_free(dbx_model* m) {
     FusedState* fs = (FusedState*)m->fused_state;
     if (fs->side) cudaStreamDestroy(fs->side);
     if (fs->ev_entry) cudaEventDestroy(fs->ev_entry);
+    if (fs->main) cudaStreamDestroy(fs->main);
+    if (fs->ev_join) cudaEventDestroy(fs->ev_join);
+    if (fs->ev_done) cudaEventDestroy(fs->ev_done);
     for (int i = 0; i < 2; ++i) { if (fs->ev_sampled[i]) cudaEventDestroy(fs->ev_sampled[i]); if (fs->ev_consumed[i]) cudaEventDestroy(fs->ev_consumed[i]); }
     delete fs; m->fused_state = nullptr;
   }

@@ -240,7 +240,8 @@ struct IbpSink {
 
 template <typename T>
 static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int clip01, int64_t n, const Source& src,
-                   const IbpSink& sink, cudaStream_t st, const float* box_hi_dev = nullptr, float weight_margin = 0.f) {
+                   const IbpSink& sink, cudaStream_t st_user, const float* box_hi_dev = nullptr, float weight_margin = 0.f) {
+  cudaStream_t st = st_user;
   // box_hi_dev != nullptr: x_dev / box_hi_dev are the lower / upper input bounds themselves (IBP_state); weight_margin > 0
   // widens every weight by margin * sigma (needs the Gaussian posterior's sigma; CUDA-core back end)
   constexpr bool kBf16 = !std::is_same<T, float>::value;
@@ -311,10 +312,24 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
       for (cudaEvent_t& e : m->ibp_ev) DBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     sst = m->ibp_side;
-    // everything enqueued on `st` before this call (previous users of the workspace, the posterior upload, a slab or
-    // injected noise written just before) is ordered before the first draw
-    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], st));
+    // everything enqueued on the caller's stream before this call (previous users of the workspace, the posterior upload, a
+    // slab or injected noise written just before) is ordered before the first draw
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], st_user));
     DBX_CUDA(cudaStreamWaitEvent(sst, m->ibp_ev[0], 0));
+    // the GEMM chain runs on a HIGH-priority stream of our own (joined with the caller's stream at both ends): its short
+    // persistent kernels then get SM slots ahead of the sampler's queued blocks instead of waiting for the sampler grid to
+    // drain (DBX_IBP_PRIO=0: run it on the caller's stream)
+    bool prio = true;
+    if (const char* e = getenv("DBX_IBP_PRIO")) prio = atoi(e) != 0;
+    if (prio) {
+      if (!m->ibp_main) {
+        int lo = 0, hi = 0;
+        DBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        DBX_CUDA(cudaStreamCreateWithPriority(&m->ibp_main, cudaStreamNonBlocking, hi));
+      }
+      st = m->ibp_main;
+      DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[0], 0));
+    }
   }
   auto draw_chunk = [&](int64_t ci) -> int {     // bf16 only
     const int b = (int)(ci & 1) % nwb;
@@ -448,6 +463,10 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     if (sink.counts)
       DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, worst, nc, B, (int)C, sink.labels,
                  sink.flags ? sink.flags + c0 * B : nullptr, sink.counts);
+  }
+  if (st != st_user) {       // hand the results back to the caller's stream
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[5], st));
+    DBX_CUDA(cudaStreamWaitEvent(st_user, m->ibp_ev[5], 0));
   }
   return 0;
 }
