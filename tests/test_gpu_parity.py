@@ -310,6 +310,25 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     np.testing.assert_array_equal(cf.cpu().numpy(), ff.sum(0).cpu().numpy())
 
 
+def test_fused_long_run_chunking(oracle, monkeypatch):
+    """Small batches with many samples run the fused kernel in launches of up to 1024 samples (instead of 256): same
+    predicate counts, same sums up to the accumulation order."""
+    L, eng, mean, std = _mlp_engine([784, 512, 512, 10], oracle, sigma_scale=0.3)
+    B, n = 100, 2304 + 37
+    x = oracle.synthetic_x((B, 784), seed=12)
+    labels = np.random.Generator(np.random.Philox(8)).integers(0, 10, size=B).astype(np.int32)
+    monkeypatch.setenv("DBX_FUSED_NS", "256")
+    c0 = eng.count_predicate(x, labels, n, seed=5, mode="bf16").cpu().numpy()
+    s0, q0 = eng.predict_sums(x, n, seed=5, mode="bf16", second_moment=True)
+    monkeypatch.delenv("DBX_FUSED_NS")
+    c1 = eng.count_predicate(x, labels, n, seed=5, mode="bf16").cpu().numpy()
+    s1, q1 = eng.predict_sums(x, n, seed=5, mode="bf16", second_moment=True)
+    assert eng.last_path() == "fused_tcgen05"
+    np.testing.assert_array_equal(c0, c1)
+    np.testing.assert_allclose(s0.cpu().numpy() / n, s1.cpu().numpy() / n, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(q0.cpu().numpy() / n, q1.cpu().numpy() / n, rtol=0, atol=2e-6)
+
+
 @pytest.mark.parametrize("dims,B", [([784, 1024, 1024, 10], 16), ([784, 1024, 1024, 10], 1), ([784, 512, 10], 5),
                                     ([37, 50, 10], 7), ([13, 24, 16, 3], 9), ([64, 40, 12], 2)])
 def test_stream_vs_generic_device_crosscheck(oracle, monkeypatch, dims, B):
