@@ -39,6 +39,7 @@ _SIGS = {
     "dbx_last_path": (C.c_int, []),
     "dbx_profile": (C.c_int, [C.c_int]),
     "dbx_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "dbx_debug_trace": (C.c_int, [_p, C.c_int]),
     "dbx_create": (C.c_int, [C.POINTER(LayerDesc), _i32, C.POINTER(_i32), _i32, _i32, C.POINTER(_p)]),
     "dbx_destroy": (C.c_int, [_p]),
     "dbx_param_count": (C.c_int, [_p, C.POINTER(_i64)]),

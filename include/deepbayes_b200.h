@@ -225,6 +225,9 @@ int dbx_profile_read(double* ms_total, double* flops_total, int64_t* launches);
 /* which kernels served the last compute call: 0 generic (CUDA cores), 1 fused tcgen05 MLP,
  * 2 small-batch streaming, 3 generic with per-layer tcgen05 GEMMs (bf16 mode). */
 int dbx_last_path(void);
+/* Development hook (tools/trace_fused.py): with DBX_FUSED_TRACE=1 the fused kernel records (probe id, clock) pairs of one
+ * cluster; this copies up to max_pairs of them to host memory and returns the count. */
+int dbx_debug_trace(long long* out_host, int max_pairs);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
