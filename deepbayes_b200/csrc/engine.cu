@@ -678,9 +678,10 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   bool skip_tensor[DBX_MAX_TENSORS] = {};
   bool layer_f32w[64] = {};
   bool any_f32w = false;
-  // (Batches of 768 rows and more: every 128-row tile converts the same fp32 block again, and one conversion pass to bf16 +
-  // dense_tc_persist_kernel wins -- 9.4 vs 11.2 ms at B = 1024, equal at 512, 4.1 vs 3.1 ms at 256 for 1000 samples of config 3.)
-  if (kBf16 && use_tc && src.stored && m->layers.size() <= 64 && B < 768) {
+  // (Batches above 384 rows: every 128-row tile converts the same fp32 block again, and one conversion pass to bf16 + the
+  // CTA-pair GEMM wins -- 7.6 vs 11.2 ms at B = 1024, 4.9 vs 5.9 ms at 512, equal at 384, 3.6 vs 3.1 ms at 256 for 1000
+  // samples of config 3.)
+  if (kBf16 && use_tc && src.stored && m->layers.size() <= 64 && B <= 384) {
     for (int li = 0; li < (int)m->layers.size(); ++li) {
       if (!f32w_layer_ok(m, li)) continue;
       const Layer& L = m->layers[li];

@@ -313,6 +313,170 @@ dense_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 }
 
 // =======================================================================================
+// CTA-pair GEMM (cta_group::2) for big per-sample GEMMs: tile = 256 rows x 256 columns on the two SMs of a cluster.  CTA r of
+// the pair owns rows [r*128, r*128+128) of the tile (its A block, its TMEM lanes, its epilogue) and stages columns
+// [r*128, r*128+128) of the weight block; one tcgen05.mma issued by the leader reads both halves.  Per k-block a CTA now
+// pulls 16 KB (A) + 16 KB (half of W) through its L2 port for 2 x the MMA work of the single-CTA 128 x 256 tile, which pulled
+// 48 KB: that kernel was bound by the ~42 B/clk/SM L2 -> SM rate (0.5 PFLOP/s at B >= 512), not by the tensor pipe.
+// Persistent clusters, 6 x 32 KB TMA ring, two TMEM accumulators, epilogue overlapped with the next tile.
+// =======================================================================================
+constexpr int kPrStages = 6;
+constexpr int kPrStageB = 32768;
+struct __align__(8) PairBarriers {
+  uint64_t full[kPrStages], empty[kPrStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
+
+template <int kAct>
+__global__ void __launch_bounds__(kGThreads, 1)
+dense_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p, int ns,
+                     int tiles_m, int tiles_n) {
+  __shared__ float s_bias[256];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  PairBarriers* bars = (PairBarriers*)(smem + kPrStages * kPrStageB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr uint16_t kBoth = 0x3;
+  const int kb_n = (p.K + 63) / 64;
+  const long long total = (long long)ns * tiles_m * tiles_n;
+  const long long ncl = gridDim.x / 2, cl = blockIdx.x / 2;
+  const long long t_begin = (total * cl) / ncl, t_end = (total * (cl + 1)) / ncl;
+  auto decode = [&](long long t, int& n0, int& m0, int& s) {
+    const int nt_i = (int)(t % tiles_n);
+    const long long r = t / tiles_n;
+    n0 = nt_i * 256; m0 = (int)(r % tiles_m) * 256 + (int)rank * 128; s = (int)(r / tiles_m);
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < kPrStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 8); }   // 4 epilogue warps of each CTA
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc2<512>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer (both CTAs): own A rows, own half of the W block; complete_tx goes to the LEADER's barrier
+    uint32_t g = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kPrStages, ph = (g / kPrStages) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          const uint32_t base = s_stage + st * kPrStageB;
+          if (leader) mbar_expect_tx(fb, 2u * kPrStageB);
+          if (p.a_shared) tma2_load_2d(base, &tmA, fb, kb * 64, m0);
+          else tma2_load_3d(base, &tmA, fb, kb * 64, m0, s);
+          for (int nb = 0; nb < 2; ++nb) tma2_load_3d(base + 16384 + nb * 8192, &tmW, fb, n0 + (int)rank * 128 + nb * 64, kb * 64, s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t idesc = make_idesc_bf16(256, 256, 0, 1);
+      uint32_t g = 0, it = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const uint32_t ab = it & 1;
+        mbar_wait_cluster(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
+        fence_after_sync();
+        for (int kb = 0; kb < kb_n; ++kb, ++g) {
+          const uint32_t st = g % kPrStages, ph = (g / kPrStages) & 1;
+          mbar_wait(smem_u32(&bars->full[st]), ph);
+          fence_after_sync();
+          if (elect_one()) {
+            const uint32_t a16 = ((s_stage + st * kPrStageB) & 0x3FFFF) >> 4;
+            const uint32_t a_lo = a16 | (1u << 16);
+            const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
+            const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+            for (int kk = 0; kk < ksteps; ++kk)
+              mma2_ss_lh(tmem + ab * 256, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+            mma2_commit_mc(smem_u32(&bars->empty[st]), kBoth);
+            if (kb == kb_n - 1) mma2_commit_mc(smem_u32(&bars->acc_full[ab]), kBoth);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue (both CTAs): this CTA's 128 rows x 256 columns
+    const int gq = warp & 3;
+    const int row = gq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    uint32_t it = 0;
+    int cur_s = -1, cur_n0 = -1;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int gm = m0 + row;
+      const uint32_t ab = it & 1;
+      if (s != cur_s || n0 != cur_n0) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = tid - 64; c < 256; c += 128) s_bias[c] = (n0 + c < p.N) ? p.bias[(long long)s * p.b_sstride + p.b_off + n0 + c] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_s = s; cur_n0 = n0;
+      }
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+      const int nt = min(256, ((p.N - n0 + 31) / 32) * 32);
+      for (int c0 = 0; c0 < nt; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + ab * 256 + c0, v);
+        wait_ld();
+        if (c0 + 32 >= nt) {   // the accumulator is in registers: tell the leader's MMA warp
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_release(smem_u32(&bars->acc_empty[ab]), 0);
+        }
+        if (gm < p.M) {
+          if (p.out16) {
+            __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0 + c0;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int c = n0 + c0 + q4 * 8;
+              if (c + 8 <= p.N) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + s_bias[c0 + q4 * 8 + 2 * i]),
+                                     act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + s_bias[c0 + q4 * 8 + 2 * i + 1]));
+                *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              } else {
+                for (int i = 0; i < 8; ++i)
+                  if (c + i < p.N) dst[q4 * 8 + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + i]) + s_bias[c0 + q4 * 8 + i]));
+              }
+            }
+          } else {
+            float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = n0 + c0 + i;
+              if (c < p.N) dst[c] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + s_bias[c0 + i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync();          // the peer's smem / barriers are in use until the leader's last MMA and commit have completed
+  if (warp == 1) tmem_dealloc2<512>(tmem);
+}
+
+// =======================================================================================
 // Stored posteriors (BASELINE config 3) at batch sizes above the streaming kernel's 16 rows: the SAME per-sample
 // GEMM, but the weights are read by TMA straight from the fp32 `[S,P]` slab -- once, 4 B per parameter, which is
 // the algorithmic traffic of that path -- and rounded to bf16 INSIDE the SM: the four epilogue warps spend the
@@ -1105,6 +1269,34 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
   // enough tiles to keep persistent CTAs busy: dense_tc_persist_kernel (DBX_NO_PERSIST=1 disables; DBX_PERSIST_MIN_TILES
   // lowers the threshold so that tests reach it with small shapes)
   {
+    // big GEMMs: CTA pairs on 256 x 256 tiles (dense_tc_pair_kernel; DBX_NO_PAIR_GEMM=1 disables)
+    if (M >= 256 && N >= 256 && K >= 256 && !(getenv("DBX_NO_PAIR_GEMM") && getenv("DBX_NO_PAIR_GEMM")[0] == '1')) {
+      static int num_sms2 = 0;
+      if (!num_sms2) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms2, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+      }
+      const int ptm = (int)cdiv(M, 256), ptn = (int)cdiv(N, 256);
+      const long long ptiles = (long long)ns * ptm * ptn;
+      if (ptiles >= num_sms2 / 2) {
+        const int smem = kPrStages * kPrStageB + (int)sizeof(PairBarriers) + 1024;
+        auto gpair = [&](auto kern) -> int {
+          if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(2u * (unsigned)std::min<long long>(ptiles, num_sms2 / 2)); cfg.blockDim = dim3(kGThreads);
+          cfg.dynamicSmemBytes = smem; cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          return cudaLaunchKernelEx(&cfg, kern, tmA, tmW, p, ns, ptm, ptn) == cudaSuccess ? 0 : 1;
+        };
+        const int prc = ka == 1 ? gpair(dense_tc_pair_kernel<1>) : ka == 0 ? gpair(dense_tc_pair_kernel<0>) : gpair(dense_tc_pair_kernel<-1>);
+        if (prc) return 1;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+      }
+    }
     const int tiles_m = (int)cdiv(M, 128), tiles_n = (int)cdiv(N, p.NT);
     const long long tiles = (long long)ns * tiles_m * tiles_n;
     long long min_tiles = 296;

@@ -835,6 +835,25 @@ def test_conv_with_fused_maxpool_is_bit_identical(oracle, monkeypatch, shape, c1
     np.testing.assert_allclose(b1.cpu().numpy() / n, f1.cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
 
 
+@pytest.mark.parametrize("dims,B,n", [([784, 1024, 1024, 10], 600, 40), ([512, 640, 10], 300, 70), ([256, 1000, 328, 10], 257, 90)])
+def test_pair_gemm_is_bit_identical_to_single_cta_gemm(oracle, monkeypatch, dims, B, n):
+    """dense_tc_pair_kernel (cta_group::2, 256 x 256 tiles, each CTA staging half of the weight block) against the single-CTA
+    tensor-core GEMMs on the same sampled weights: same products in the same k order -> same bits.  Ragged row / column
+    tiles (600 = 2 x 256 + 88 rows, 640 = 2.5 x 256 columns, 1000 and 328 columns) included."""
+    L, eng, mean, std = _mlp_engine(dims, oracle, sigma_scale=0.3)
+    x = oracle.synthetic_x((B, dims[0]), seed=21)
+    monkeypatch.setenv("DBX_NO_FUSED", "1")
+    monkeypatch.setenv("DBX_NO_PAIR_GEMM", "1")
+    a1, a2 = eng.predict_sums(x, n, seed=3, mode="bf16", second_moment=True)
+    assert eng.last_path() == "generic_tc"
+    monkeypatch.setenv("DBX_NO_PAIR_GEMM", "0")
+    b1, b2 = eng.predict_sums(x, n, seed=3, mode="bf16", second_moment=True)
+    np.testing.assert_array_equal(a1.cpu().numpy(), b1.cpu().numpy())
+    np.testing.assert_array_equal(a2.cpu().numpy(), b2.cpu().numpy())
+    f1, _ = eng.predict_sums(x, n, seed=3, mode="fp32")
+    np.testing.assert_allclose(b1.cpu().numpy() / n, f1.cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
+
+
 def _lib_launches():
     from deepbayes_b200 import _lib
     return _lib.launch_count()
