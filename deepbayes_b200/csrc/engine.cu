@@ -619,12 +619,18 @@ static bool f32w_model_ok(const dbx_model* m) {
 
 template <typename T>
 static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
-                       cudaStream_t st) {
+                       cudaStream_t st, cudaStream_t sst = nullptr) {
+  // sst != nullptr (bf16 mode): the weights of chunk c + 1 are drawn / converted on that side stream while chunk c is in the
+  // layers (two weight buffers; events gen_ev[1..4] = sampled[2], consumed[2]); the caller has ordered both streams after
+  // everything that was enqueued before the call and joins them afterwards (see run())
   constexpr bool kBf16 = !std::is_same<T, float>::value;
   const int64_t C = m->out_feat;
+  const bool overlap = kBf16 && sst != nullptr;
+  const int nwb = overlap ? 2 : 1;
   // per-sample workspace bytes
   const size_t act_b = (size_t)B * m->max_feat * sizeof(T);
-  const size_t w_b = kBf16 ? ((size_t)m->P16 * 2 + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
+  const size_t w1_b = kBf16 ? ((size_t)m->P16 * 2 + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
+  const size_t w_b = w1_b * nwb;
   // bf16 mode: Conv2D layers run as im2col + tcgen05 GEMM and need a column buffer
   size_t col_b = 0;
   bool use_tc = kBf16;
@@ -649,7 +655,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   const size_t xin_b = xin1_b * ((kBf16 && src.stored) ? kXRep : 1) + col0_b;
   int64_t ns = (int64_t)std::max<size_t>(1, (ws_budget_bytes() - std::min(ws_budget_bytes(), xin_b)) / per);
   ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
-  if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 8192)) return 1;
+  if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 16384)) return 1;
   char* p = (char*)m->ws.ptr;
   T* xin = (T*)p; p += xin_b - col0_b;
   __nv_bfloat16* col0 = (__nv_bfloat16*)p; p += col0_b;
@@ -659,7 +665,12 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   float* logits = (float*)p; p += round_up((size_t)ns * B * C * 4, 256);
   T* Wc = (T*)p;
   float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * m->P16 * 2, 256)) : nullptr;
-  __nv_bfloat16* colbuf = (__nv_bfloat16*)(p + round_up((size_t)ns * w_b, 256) + 512);
+  T* Wc2[2] = {Wc, Wc}; float* B32b[2] = {B32, B32};
+  if (overlap) {
+    const size_t one = round_up((size_t)ns * m->P16 * 2, 256) + round_up((size_t)ns * m->PB * 4, 256);
+    Wc2[1] = (T*)(p + one); B32b[1] = (float*)(p + one + round_up((size_t)ns * m->P16 * 2, 256));
+  }
+  __nv_bfloat16* colbuf = (__nv_bfloat16*)(p + round_up((size_t)ns * w_b, 256) + 1024);
 
   const T* x_in;
   if (kBf16) {
@@ -695,8 +706,25 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
     // ---- weights of this chunk
     const T* Wbase; int64_t w_sstride; const int32_t* rows = nullptr; int64_t row0 = 0;
     const float* Bbase; int64_t b_sstride;
+    const int64_t ci = c0 / ns;
+    const int wb = (int)(ci & 1) % nwb;
     if (kBf16) {
-      if (launch_sample_bf16(m, m->table, src, c0, nc, (__nv_bfloat16*)Wc, B32, st, 0, any_f32w ? skip_tensor : nullptr)) return 1;
+      auto draw_chunk = [&](int64_t cj) -> int {
+        const int b = (int)(cj & 1) % nwb;
+        const int64_t d0 = cj * ns;
+        const int dn = (int)std::min<int64_t>(ns, n - d0);
+        cudaStream_t ds = overlap ? sst : st;
+        if (overlap && cj >= 2) DBX_CUDA(cudaStreamWaitEvent(ds, m->ibp_ev[3 + b], 0));
+        if (launch_sample_bf16(m, m->table, src, d0, dn, (__nv_bfloat16*)Wc2[b], B32b[b], ds, 0, any_f32w ? skip_tensor : nullptr)) return 1;
+        if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[1 + b], ds));
+        return 0;
+      };
+      if (ci == 0 || !overlap) { if (draw_chunk(ci)) return 1; }
+      if (overlap) {
+        if (c0 + ns < n && draw_chunk(ci + 1)) return 1;       // next chunk's weights, concurrently
+        DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[1 + wb], 0));
+      }
+      Wc = Wc2[wb]; B32 = B32b[wb];
       Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
     } else if (src.stored) {
       Wbase = (const T*)m->slab; w_sstride = m->slab_stride; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
@@ -803,6 +831,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
       if (last) break;
       cur = bufs[bi]; cur_ss = B * (pooled_next ? m->layers[li + 1].out_feat : L.out_feat); bi ^= 1;
     }
+    if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[3 + wb], st));      // this chunk's weights are free again
     // ---- sink
     const int act_last = m->layers[m->last_weighted].act;
     if (sink.kind == 0) {
@@ -843,7 +872,33 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
       if (r < 0) return 1;
       if (r == 1) { g_last_path = 1; return 0; }
     }
-    const int rg = run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
+    // generic executor: the layers on a high-priority stream of the engine's own, the sampling / conversion of the next chunk
+    // on a default-priority side stream, both joined with the caller's stream here (DBX_GENERIC_OVERLAP=0: all on `st`)
+    bool overlap = true;
+    if (const char* e = getenv("DBX_GENERIC_OVERLAP")) overlap = atoi(e) != 0;
+    if (!overlap) {
+      const int rg0 = run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
+      if (g_used_tc) g_last_path = 3;
+      return rg0;
+    }
+    if (!m->ibp_side) {
+      DBX_CUDA(cudaStreamCreateWithFlags(&m->ibp_side, cudaStreamNonBlocking));
+      for (cudaEvent_t& e : m->ibp_ev) DBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!m->ibp_main) {
+      int lo = 0, hi = 0;
+      DBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      DBX_CUDA(cudaStreamCreateWithPriority(&m->ibp_main, cudaStreamNonBlocking, hi));
+    }
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], st));
+    DBX_CUDA(cudaStreamWaitEvent(m->ibp_side, m->ibp_ev[0], 0));
+    DBX_CUDA(cudaStreamWaitEvent(m->ibp_main, m->ibp_ev[0], 0));
+    const int rg = run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, m->ibp_main, m->ibp_side);
+    // join: the side stream's last work was consumed by the main stream already, but an error path may have left some
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[5], m->ibp_main));
+    DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[5], 0));
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], m->ibp_side));
+    DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[0], 0));
     if (g_used_tc) g_last_path = 3;
     return rg;
   }
