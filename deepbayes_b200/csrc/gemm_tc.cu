@@ -330,12 +330,13 @@ struct __align__(8) PairBarriers {
 
 template <int kAct>
 __global__ void __launch_bounds__(kGThreads, 1)
-dense_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p, int ns,
-                     int tiles_m, int tiles_n) {
+dense_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+                     const GemmParams p, int ns, int tiles_m, int tiles_n, int tma_out) {
   __shared__ float s_bias[256];
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  PairBarriers* bars = (PairBarriers*)(smem + kPrStages * kPrStageB);
+  uint8_t* stage_out = smem + kPrStages * kPrStageB;            // per epilogue warp: a [32 rows x 64 columns] bf16 box for the TMA store
+  PairBarriers* bars = (PairBarriers*)(stage_out + 4 * 4096);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -440,7 +441,33 @@ dense_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_release(smem_u32(&bars->acc_empty[ab]), 0);
         }
-        if (gm < p.M) {
+        if (tma_out) {
+          // bf16 output through a swizzled staging box and a TMA store per 64 columns: full-line writes, M / N tails clipped by
+          // the tensor map (one 16-byte store per lane put 32 half-used sectors of 32 different rows into every instruction)
+          uint8_t* stg = stage_out + (warp - 2) * 4096;
+          if ((c0 & 63) == 0) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i]) + s_bias[c0 + q4 * 8 + 2 * i]),
+                                 act_fixed<kAct>(p.act, __uint_as_float(v[q4 * 8 + 2 * i + 1]) + s_bias[c0 + q4 * 8 + 2 * i + 1]));
+            const int chunk = (((c0 & 63) >> 3) + q4) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if ((c0 & 63) == 32 || c0 + 32 >= nt) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m0 + gq * 32 < p.M) {
+              tma_store_3d(&tmO, smem_u32(stg), n0 + (c0 & ~63), m0 + gq * 32, s);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        } else if (gm < p.M) {
           if (p.out16) {
             __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0 + c0;
 #pragma unroll
@@ -470,6 +497,7 @@ dense_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   }
+  if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   fence_before_sync();
   __syncthreads();
   cluster_sync();          // the peer's smem / barriers are in use until the leader's last MMA and commit have completed
@@ -1279,7 +1307,16 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
       const int ptm = (int)cdiv(M, 256), ptn = (int)cdiv(N, 256);
       const long long ptiles = (long long)ns * ptm * ptn;
       if (ptiles >= num_sms2 / 2) {
-        const int smem = kPrStages * kPrStageB + (int)sizeof(PairBarriers) + 1024;
+        const int smem = kPrStages * kPrStageB + 4 * 4096 + (int)sizeof(PairBarriers) + 1024;
+        // bf16 output: TMA stores from a staging box (needs 16-byte pitches; otherwise the kernel stores directly)
+        CUtensorMap tmO = tmW;
+        int tma_out = 0;
+        if (out16 && !(getenv("DBX_NO_TMA_STORE") && getenv("DBX_NO_TMA_STORE")[0] == '1') && (ld16 & 7) == 0 && (o16_sstride & 7) == 0 &&
+            ((uintptr_t)out16 & 15) == 0) {
+          uint64_t d[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)ld16 * 2, (uint64_t)o16_sstride * 2};
+          uint32_t b[3] = {64, 32, 1};
+          tma_out = make_tmap_bf16(&tmO, (void*)out16, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B) ? 1 : 0;
+        }
         auto gpair = [&](auto kern) -> int {
           if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
           cudaLaunchConfig_t cfg = {};
@@ -1289,7 +1326,7 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
           attr[0].id = cudaLaunchAttributeClusterDimension;
           attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
           cfg.attrs = attr; cfg.numAttrs = 1;
-          return cudaLaunchKernelEx(&cfg, kern, tmA, tmW, p, ns, ptm, ptn) == cudaSuccess ? 0 : 1;
+          return cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmO, p, ns, ptm, ptn, tma_out) == cudaSuccess ? 0 : 1;
         };
         const int prc = ka == 1 ? gpair(dense_tc_pair_kernel<1>) : ka == 0 ? gpair(dense_tc_pair_kernel<0>) : gpair(dense_tc_pair_kernel<-1>);
         if (prc) return 1;
