@@ -32,6 +32,51 @@ def _worker(rank, world, port, q):
     dd.allreduce_sum_(t1, t2)
     f1, f2 = o.predict_moments(L, mean, std, x, n, eps)
     ok = np.allclose(t1.numpy(), f1, rtol=1e-6, atol=1e-7) and np.allclose(t2.numpy(), f2, rtol=1e-6, atol=1e-7)
+    # the drop-in chernoff_bound_verification with model.shard: the host logic (global sample ids split over the ranks, one
+    # all-reduce of the [B,C] buffer) around a stand-in engine that evaluates each rank's ids with the oracle
+    from deepbayes_b200.analyzers import verifiers
+
+    class _Eng:
+        K, C, device = 11, 4, torch.device("cpu")
+        calls = []
+
+        def __init__(self):
+            self.torch = torch
+
+        def ibp_predict(self, x2, e, labels, cnt_, seed, s0, noise, inflate, mode, want=("worst",)):
+            _Eng.calls.append((int(s0), int(cnt_)))
+            tot = np.zeros((x2.shape[0], 4))
+            for sid in range(s0, s0 + cnt_):
+                w = o.sample_gaussian(mean, std, o.split_flat(L, o.philox_normals(seed, sid, o.param_count(L))), order="f32")
+                lo, hi = o.ibp_forward(L, w, x2, e)
+                worst = o.worst_case_logits(lo, hi, labels)
+                ex = np.exp(worst - worst.max(1, keepdims=True))
+                tot += ex / ex.sum(1, keepdims=True)
+            return {"worst": torch.from_numpy(tot.astype(np.float32))}
+
+    class _Model:
+        seed, shard, mode = 5, True, "fp32"
+        _next = 100
+
+        def __init__(self):
+            self._e = _Eng()
+
+        def engine(self):
+            return self._e
+
+        def _take_ids(self, k):
+            v = _Model._next
+            _Model._next += k
+            return v
+
+    mdl = _Model()
+    cls = np.array([0, 1, 2, 3, 0])
+    got = verifiers.chernoff_bound_verification(mdl, x, 0.01, cls, confidence=0.6, delta=0.3)       # n = 6 samples
+    nver = verifiers.chernoff_sample_bound(0.6, 0.3)
+    mdl2 = _Model(); mdl2.shard = False; _Model._next = 100
+    full = verifiers.chernoff_bound_verification(mdl2, x, 0.01, cls, confidence=0.6, delta=0.3)
+    offv, cntv = dd.shard_range(nver, rank, world)
+    ok = ok and np.allclose(got, full, rtol=1e-5, atol=1e-6) and _Eng.calls[0] == (100 + offv, cntv) and _Eng.calls[1] == (100, nver)
     q.put((rank, bool(ok), off, cnt))
     dist.destroy_process_group()
 
