@@ -40,6 +40,9 @@ _SIGS = {
     "dbx_profile": (C.c_int, [C.c_int]),
     "dbx_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
     "dbx_debug_trace": (C.c_int, [_p, C.c_int]),
+    "dbx_set_option": (C.c_int, [C.c_char_p, _i64]),
+    "dbx_get_option": (C.c_int, [C.c_char_p, C.POINTER(_i64)]),
+    "dbx_reset_options": (C.c_int, []),
     "dbx_create": (C.c_int, [C.POINTER(LayerDesc), _i32, C.POINTER(_i32), _i32, _i32, C.POINTER(_p)]),
     "dbx_destroy": (C.c_int, [_p]),
     "dbx_param_count": (C.c_int, [_p, C.POINTER(_i64)]),
@@ -101,6 +104,21 @@ def load():
 def check(rc: int):
     if rc != 0:
         raise DbxError(load().dbx_last_error().decode("utf-8", "replace"))
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide dispatch switch (`name` without the DBX_ prefix); see include/deepbayes_b200.h."""
+    check(load().dbx_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = _i64()
+    check(load().dbx_get_option(name.encode(), C.byref(v)))
+    return int(v.value)
+
+
+def reset_options() -> None:
+    check(load().dbx_reset_options())
 
 
 def launch_count() -> int:

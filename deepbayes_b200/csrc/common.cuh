@@ -13,6 +13,30 @@ extern std::atomic<long long> g_launches;
 
 int set_err(const char* fmt, ...);
 
+// Process-wide A/B switches.  Read ONCE from the DBX_* environment (first use), afterwards only changed through
+// dbx_set_option / dbx_reset_options (tests, tools/): nothing on a call path touches getenv().  None of them selects a
+// CPU or library fallback -- every value still runs this library's own kernels.
+struct Options {
+  long long no_fused = 0;           // skip fused_mlp*_kernel, use the generic executor
+  long long no_stream = 0;          // skip stream_mlp_kernel
+  long long no_tc = 0;              // generic executor / IBP on the CUDA-core kernels only
+  long long no_pair_gemm = 0;       // big per-sample GEMMs on the single-CTA kernels instead of dense_tc_pair_kernel
+  long long no_tma_store = 0;       // dense_tc_pair_kernel stores its bf16 output directly
+  long long no_persist = 0;         // one CTA per tile (dense_tc_kernel)
+  long long persist_min_tiles = 296;
+  long long no_f32w = 0;            // stored posteriors: convert the slab chunk to bf16 first
+  long long no_direct_conv = 0;     // Conv2D as im2col + GEMM
+  long long no_pool_fuse = 0;       // separate max-pool launch
+  long long no_ibp_tc = 0;          // interval forward: two GEMMs + combine per hidden layer
+  long long ibp_overlap = 1, ibp_prio = 1, generic_overlap = 1, fused_overlap = 1, fused_prio = 1;
+  long long fused_kernel = 0;       // 0 = by shape; 1 = single-CTA kernel; 2 = CTA-pair kernel
+  long long fused_order = -1;       // -1 = by shape; 0 = [q][s] contiguous ranges; 1 = [s][q] round-robin
+  long long fused_ns = 0;           // samples per fused launch (0 = by shape)
+  long long fused_trace = 0, fused_trace_only = 0;   // in-kernel clock probes of one cluster (tools/trace_fused.py)
+  long long ws_mb = 2048;           // workspace budget of the generic executor / IBP
+};
+Options& opt();
+
 #define DBX_CUDA(expr)                                                                      \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

@@ -32,6 +32,31 @@ int set_err(const char* fmt, ...) {
   return 1;
 }
 
+// ---- process-wide options (see common.cuh) ------------------------------------------------------
+struct OptEntry { const char* name; long long Options::*field; };
+static const OptEntry kOptTable[] = {
+  {"NO_FUSED", &Options::no_fused}, {"NO_STREAM", &Options::no_stream}, {"NO_TC", &Options::no_tc},
+  {"NO_PAIR_GEMM", &Options::no_pair_gemm}, {"NO_TMA_STORE", &Options::no_tma_store}, {"NO_PERSIST", &Options::no_persist},
+  {"PERSIST_MIN_TILES", &Options::persist_min_tiles}, {"NO_F32W", &Options::no_f32w},
+  {"NO_DIRECT_CONV", &Options::no_direct_conv}, {"NO_POOL_FUSE", &Options::no_pool_fuse}, {"NO_IBP_TC", &Options::no_ibp_tc},
+  {"IBP_OVERLAP", &Options::ibp_overlap}, {"IBP_PRIO", &Options::ibp_prio}, {"GENERIC_OVERLAP", &Options::generic_overlap},
+  {"FUSED_OVERLAP", &Options::fused_overlap}, {"FUSED_PRIO", &Options::fused_prio}, {"FUSED_KERNEL", &Options::fused_kernel},
+  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
+};
+static void options_from_env(Options& o) {
+  o = Options();
+  for (const OptEntry& e : kOptTable) {
+    const std::string var = std::string("DBX_") + e.name;
+    if (const char* v = getenv(var.c_str())) o.*(e.field) = atoll(v);
+  }
+}
+Options& opt() {
+  static Options o;
+  static bool init = false;
+  if (!init) { options_from_env(o); init = true; }
+  return o;
+}
+
 struct ProfRec { cudaEvent_t a, b; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -592,17 +617,12 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
   return 0;
 }
 
-static size_t ws_budget_bytes() {
-  const char* e = getenv("DBX_WS_MB");
-  size_t mb = e ? (size_t)atoll(e) : 2048;
-  return mb << 20;
-}
+static size_t ws_budget_bytes() { return (size_t)std::max<long long>(1, opt().ws_mb) << 20; }
 
 // Can dense_tc_f32w_kernel take this layer's kernel straight from the fp32 slab?  (16-byte TMA strides and offsets; small
 // kernels are not worth a launch of their own.)  DBX_NO_F32W=1 restores the two-pass path.
 static bool f32w_layer_ok(const dbx_model* m, int li) {
-  if (const char* e = getenv("DBX_NO_F32W")) if (e[0] == '1') return false;
-  if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') return false;
+  if (opt().no_f32w || opt().no_tc) return false;
   const Layer& L = m->layers[li];
   if (L.kind != DBX_DENSE || !L.has_w || !m->slab) return false;
   if ((L.in_feat & 7) || (L.w_cols & 3) || (L.w_off & 3) || (m->slab_stride & 3) || ((uintptr_t)m->slab & 15)) return false;
@@ -634,10 +654,10 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   // bf16 mode: Conv2D layers run as im2col + tcgen05 GEMM and need a column buffer
   size_t col_b = 0;
   bool use_tc = kBf16;
-  if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') use_tc = false;
+  if (opt().no_tc) use_tc = false;
   // (not the layers conv_tc_kernel takes directly; a conv on the call's input, which every sample shares, needs ONE
   // column matrix per call, built before the chunk loop)
-  const bool direct_conv = !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1');
+  const bool direct_conv = !opt().no_direct_conv;
   size_t col0_b = 0;
   int first_w = -1;
   for (int li = 0; li < (int)m->layers.size(); ++li) if (m->layers[li].has_w) { first_w = li; break; }
@@ -768,13 +788,13 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
                                     (int)B, L.units, (int)L.in_feat, Bbase, b_sstride, boff, act,
                                     last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units, last ? logits : nullptr,
                                     B * C, st) == 0;
-        } else if (L.kind == DBX_CONV2D && !last && !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1') &&
+        } else if (L.kind == DBX_CONV2D && !last && !opt().no_direct_conv &&
                    li + 1 < (int)m->layers.size() && conv_tc_pool_eligible(L, m->layers[li + 1]) && (B * m->layers[li + 1].out_feat) % 8 == 0 &&
                    conv_tc_launch(A16, cur_ss, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L, Bbase, b_sstride,
                                   boff, act, (__nv_bfloat16*)bufs[bi], B * m->layers[li + 1].out_feat, st, 1) == 0) {
           done_tc = true;      // direct convolution with the following 2x2 max-pool done in its epilogue: the full-resolution map
           pooled_next = true;  // (4x the bytes) is never written
-        } else if (L.kind == DBX_CONV2D && !last && !(getenv("DBX_NO_DIRECT_CONV") && getenv("DBX_NO_DIRECT_CONV")[0] == '1') &&
+        } else if (L.kind == DBX_CONV2D && !last && !opt().no_direct_conv &&
                    conv_tc_launch(A16, cur_ss, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)B, L, Bbase, b_sstride,
                                   boff, act, (__nv_bfloat16*)bufs[bi], B * L.out_feat, st) == 0) {
           done_tc = true;      // direct convolution: per-tap TMA boxes of the NHWC input, no im2col matrix
@@ -866,16 +886,14 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
     if (r == 1) { g_last_path = 2; return 0; }
   }
   if (mode == DBX_MODE_BF16) {
-    const char* nf = getenv("DBX_NO_FUSED");
-    if (!(nf && nf[0] == '1')) {
+    if (!opt().no_fused) {
       const int r = fused_mlp_run(m, x_dev, B, n, src, sink, st);
       if (r < 0) return 1;
       if (r == 1) { g_last_path = 1; return 0; }
     }
     // generic executor: the layers on a high-priority stream of the engine's own, the sampling / conversion of the next chunk
     // on a default-priority side stream, both joined with the caller's stream here (DBX_GENERIC_OVERLAP=0: all on `st`)
-    bool overlap = true;
-    if (const char* e = getenv("DBX_GENERIC_OVERLAP")) overlap = atoi(e) != 0;
+    const bool overlap = opt().generic_overlap != 0;
     if (!overlap) {
       const int rg0 = run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
       if (g_used_tc) g_last_path = 3;
@@ -919,6 +937,20 @@ const char* dbx_last_error(void) { return g_err.c_str(); }
 int dbx_version(void) { return 100; }
 int64_t dbx_launch_count(void) { return (int64_t)g_launches.load(); }
 int dbx_last_path(void) { return g_last_path; }
+
+int dbx_set_option(const char* name, int64_t value) {
+  DBX_CHECK(name != nullptr, "dbx_set_option: null name");
+  for (const OptEntry& e : kOptTable)
+    if (strcmp(e.name, name) == 0) { opt().*(e.field) = (long long)value; return 0; }
+  return set_err("dbx_set_option: unknown option '%s'", name);
+}
+int dbx_get_option(const char* name, int64_t* value) {
+  DBX_CHECK(name != nullptr && value != nullptr, "dbx_get_option: null argument");
+  for (const OptEntry& e : kOptTable)
+    if (strcmp(e.name, name) == 0) { *value = (int64_t)(opt().*(e.field)); return 0; }
+  return set_err("dbx_get_option: unknown option '%s'", name);
+}
+int dbx_reset_options(void) { options_from_env(opt()); return 0; }
 
 int dbx_profile(int enable) {
   g_prof_on = enable != 0;

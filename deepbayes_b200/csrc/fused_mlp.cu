@@ -532,8 +532,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #define DBX_K2STAGES 6
 #endif
 constexpr int k2Stages = DBX_K2STAGES;
-constexpr int k2StagesS1 = 4;         // S1 variant: 64 KB of the ring hold the second half of H1
-constexpr int k2H1Bytes = 65536;
 constexpr int k2StageBytes = 32768;   // X block 16 KB + this CTA's half of the weight block 16 KB
 
 struct __align__(8) Barriers2 {
@@ -546,12 +544,6 @@ struct __align__(8) Barriers2 {
   uint32_t tmem_slot;
 };
 
-// S1 = true (opt-in experiment; two hidden layers, H > 256): the second half of H1 (layer-1 chunk 1) is packed into
-// SHARED memory (K-major SWIZZLE_128B, 64 KB) instead of TMEM, and the layer-2 MMAs over k >= 256 read it as an SS
-// operand; the 64 KB come out of the TMA ring (4 stages instead of 6; measured cost of the shorter ring: 1 %).
-// Built to test whether the TMEM read port limits layer 2 -- it does not (tools/mma_rate2.cu: tcgen05.ld streams do
-// not slow .ts MMAs), and the SS form is the slower MMA, so this is a measured negative result.
-template <bool S1>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
@@ -559,12 +551,9 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int CM = 2;
   uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  constexpr int NST = S1 ? k2StagesS1 : k2Stages;
-  constexpr int kH1Smem = S1 ? k2H1Bytes : 0;
-  uint8_t* h1_smem = smem + NST * k2StageBytes;
-  const uint32_t s_h1 = s_stage + NST * k2StageBytes;
-  const uint32_t s_w3 = s_h1 + kH1Smem;
-  float* bias_smem = (float*)(h1_smem + kH1Smem + kW3Bytes / 2);
+  constexpr int NST = k2Stages;
+  const uint32_t s_w3 = s_stage + NST * k2StageBytes;
+  float* bias_smem = (float*)(smem + NST * k2StageBytes + kW3Bytes / 2);
   const uint32_t s_bias = smem_u32(bias_smem);
   Barriers2* bars = (Barriers2*)((uint8_t*)bias_smem + 2 * kBiasFloats * 4);
 
@@ -700,7 +689,6 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t idesc_l2 = make_idesc_bf16(256, 128, 0, 1);
       // W3: one 8-column core-matrix block per CTA, k-groups 128 B apart
       const uint64_t w3desc0 = make_smem_desc(s_w3, 128, (uint32_t)(H * 16), SW_NONE);
-      const uint32_t h1_16 = (s_h1 & 0x3FFFF) >> 4;
 
       auto pump = [&](bool force) -> bool {
         if (pn == 0) return false;
@@ -803,8 +791,7 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0;
                 nsg = min(2, l2_stages);
               } else {
-                if (S1) mbar_wait_cluster(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1);   // peer's smem stores
-                else mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1);
+                mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1);
                 ++ph_act1_1;
                 nsg = l2_stages - sg;
               }
@@ -822,19 +809,10 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               for (int t = 0; t < nsg; ++t) {
                 const int g = sg + t;
                 const uint32_t b_lo = (a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
-                if (S1 && g >= 2) {
-                  // k >= 256: A = H1 chunk 1 in shared memory, 64-wide k-block (g - 2) * 2 + kblk, 32 B per k-step
-                  const uint32_t a_lo = (h1_16 + (uint32_t)(g - 2) * (2u * 16384u >> 4)) | (1u << 16);
+                const uint32_t a0 = tmem + (uint32_t)(g >> 1) * 256 + (uint32_t)(g & 1) * 64;
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    mma2_ss_lh(dbuf, a_lo + (i >> 2) * (16384u >> 4) + (i & 3) * 2, kDescHi128,
-                               b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, 1);
-                } else {
-                  const uint32_t a0 = tmem + (uint32_t)(g >> 1) * 256 + (uint32_t)(g & 1) * 64;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
-                    mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (g | i) > 0);
-                }
+                for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
+                  mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (g | i) > 0);
                 mma2_commit_mc(e, kBoth);
                 if (++i2 == NST) { i2 = 0; e = empty0; a16 = a16_0; } else { e += 8; a16 += k2StageBytes >> 4; }
               }
@@ -904,33 +882,6 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       fence_before_sync();
     };
 
-    // S1: relu(acc + b) -> bf16 -> this row of the H1 chunk-1 operand in shared memory (8-row groups of 1024 B,
-    // 128 B per row, 16-byte chunks XOR-swizzled by row & 7 = SWIZZLE_128B K-major)
-    uint8_t* h1_row = h1_smem + (row >> 3) * 1024 + (row & 7) * 128;
-    const int sw = row & 7;
-    auto store_h1 = [&](uint32_t src, int ncols, const float* bias) {
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(src + c0, v);
-        wait_ld();
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * i);
-          const float lo = fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f);
-          const float hi = fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f);
-          w[i] = pack_bf16x2(lo, hi);
-        }
-        uint8_t* blk = h1_row + (c0 >> 6) * 16384;
-        const int j0 = (c0 & 63) >> 3;            // first 16-byte chunk (0 or 4)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(blk + (((j0 + i) ^ sw) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-      }
-      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      fence_before_sync();
-    };
-
     for (long long u = u0; u < u1; u += u_step, ++unit_n) {
       int q, s;
       decode(u, q, s);
@@ -962,15 +913,9 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ++ph_acc[c];
         fence_after_sync();
         if (warp == 2) DBX_TRACE(200 + c);
-        if (S1 && c == 1) {
-          store_h1(tmem + lane_base + 256, ncols, bias + p.b1_off + 256);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_release(smem_u32(&bars->act1_ready[1]), 0);
-        } else {
-          pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
-        }
+        pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
         if (warp == 2) DBX_TRACE(210 + c);
         if (NH == 1) drain_l3(c, tmem + lane_base + c * 256 + 128);
       }
@@ -1058,424 +1003,26 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1) tmem_dealloc2<512>(tmem);
 }
 
-// =======================================================================================
-// CTA-pair kernel, version 3: as fused_mlp2_kernel, but the tiny output layer (C <= 12) leaves
-// the tensor pipe.  Measured (tools/mma_rate.cu, timeline traces): a tcgen05.mma costs the
-// issuing thread >= ~63 cycles whatever its N, so the 32 N=16 output-layer MMAs per unit took
-// as long as a quarter of layer 2 and sat on the critical path together with their drain
-// round-trips.  Here the epilogue applies W3 with FFMA while it already holds relu(H2) in
-// registers: H2 is never packed or written back, and the MMA warp only ever issues full-rate
-// layer-1/2 MMAs.  Two epilogue warpgroups (8 warps) split the chunks (WG0: L1 chunk 0 + L2
-// chunks 0,2; WG1: L1 chunk 1 + L2 chunks 1,3) and hand the partial logits over in smem.
-// W3_s arrives as fp32 [H][12] (bf16-rounded values) right behind the biases in B32.
-// =======================================================================================
-constexpr int k3Stages = 5;
-constexpr int k3StageBytes = 32768;
-constexpr int k3Threads = 320;       // producer, issuer, 2 x 4 epilogue warps
-constexpr int kW3Pitch = 12;
 
-struct __align__(8) Barriers3 {
-  uint64_t full[k3Stages], empty[k3Stages];
-  uint64_t w3_full, w3_empty;
-  uint64_t bias_full[2], bias_empty[2];
-  uint64_t acc_full[2], act1_ready[2];
-  uint64_t acc2_full[2], buf_free[2];
-  uint64_t logit_full[2], logit_empty[2];
-  uint32_t tmem_slot;
-};
-
-__global__ void __launch_bounds__(k3Threads, 1)
-fused_mlp3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                  const __grid_constant__ CUtensorMap tmW2, const FusedParams p) {
-  constexpr int CM = 2;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t s_stage = smem_u32(smem);
-  float* w3f = (float*)(smem + k3Stages * k3StageBytes);                       // [H][12] fp32
-  float* bias_smem = w3f + 512 * kW3Pitch;                                     // 2 x kBiasFloats
-  float* lslot = bias_smem + 2 * kBiasFloats;                                  // 2 x [128][12] partial logits (WG1 -> WG0)
-  Barriers3* bars = (Barriers3*)(lslot + 2 * 128 * kW3Pitch);
-  const uint32_t s_w3f = smem_u32(w3f), s_bias = smem_u32(bias_smem);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int trace_n = 0;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = (rank == 0);
-  const int cluster_id = blockIdx.x / CM;
-  constexpr uint16_t kBoth = 0x3;
-
-  const int H = p.H, NH = p.NH, K0 = p.K0;
-  const int n_l1 = (H + 255) / 256;
-  const int n_l2 = (NH == 2) ? H / 128 : 0;
-  const int kb1 = (K0 + 63) / 64;
-  const int l2_stages = H / 128;
-
-  if (tid == 0) {
-    for (int i = 0; i < k3Stages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
-    mbar_init(smem_u32(&bars->w3_full), 1); mbar_init(smem_u32(&bars->w3_empty), 8);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->bias_full[i]), 1); mbar_init(smem_u32(&bars->bias_empty[i]), 8);
-      mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->act1_ready[i]), 8);   // 4 warps x 2 CTAs
-      mbar_init(smem_u32(&bars->acc2_full[i]), 1); mbar_init(smem_u32(&bars->buf_free[i]), 8);
-      mbar_init(smem_u32(&bars->logit_full[i]), 4); mbar_init(smem_u32(&bars->logit_empty[i]), 4);
+// order 1: adds the per-(cluster, q) running sums in cluster order
+__global__ void finish4_kernel(const float* __restrict__ partial, const unsigned long long* __restrict__ visited, int NC, int Q,
+                               int CM, int B, int C, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
+  const long long total = (long long)B * C;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(o / C), c = (int)(o - (long long)b * C);
+    const int tile = b / 128, row = b % 128, q = tile / CM, rank = tile % CM;
+    float a1 = overwrite ? 0.f : sum1[o];
+    float a2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
+    for (int k = 0; k < NC; ++k) {
+      if (!((visited[k] >> q) & 1ull)) continue;
+      const float* src = partial + ((((long long)k * Q + q) * CM + rank) * 128 + row) * 32;
+      a1 += src[c];
+      if (sum2) a2 += src[16 + c];
     }
-    fence_mbar_init();
+    sum1[o] = a1;
+    if (sum2) sum2[o] = a2;
   }
-  if (warp == 1) tmem_alloc2<512>(smem_u32(&bars->tmem_slot));
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmX); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2); }
-  fence_before_sync();
-  __syncthreads();
-  cluster_sync();
-  fence_after_sync();
-  const uint32_t tmem = bars->tmem_slot;
-
-  const long long u0 = ((long long)cluster_id * p.U) / p.NC;
-  const long long u1 = ((long long)(cluster_id + 1) * p.U) / p.NC;
-
-  if (warp == 0) {
-    // =========================== TMA producer (both CTAs) ===========================
-    uint32_t it = 0, w3_n = 0, unit_n = 0;
-    for (long long u = u0; u < u1; ++u, ++unit_n) {
-      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
-      const int m0 = (q * CM + (int)rank) * 128;
-      {
-        const uint32_t b = unit_n & 1;
-        mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(smem_u32(&bars->bias_full[b]), (uint32_t)(p.w3f_off * 4));
-          bulk_load(s_bias + b * kBiasFloats * 4, p.bias + (long long)s * p.PB, (uint32_t)(p.w3f_off * 4), smem_u32(&bars->bias_full[b]));
-        }
-        __syncwarp();
-      }
-      for (int c = 0; c < n_l1; ++c) {
-        const int ncols = min(256, H - c * 256);
-        const int nhalf = ncols / 128;
-        for (int kb = 0; kb < kb1; ++kb, ++it) {
-          const uint32_t st = it % k3Stages, ph = (it / k3Stages) & 1;
-          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
-          if (elect_one()) {
-            const uint32_t fb = smem_u32(&bars->full[st]);
-            const uint32_t base = s_stage + st * k3StageBytes;
-            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)(kXBytes + nhalf * kBlkBytes));
-            tma2_load_2d(base, &tmX, fb, kb * 64, m0);
-#pragma unroll
-            for (int nb = 0; nb < 2; ++nb)
-              if (nb < nhalf)
-                tma2_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + ((int)rank * nhalf + nb) * 64, kb * 64, s);
-          }
-          __syncwarp();
-        }
-        if (c == 0) {
-          // output-layer kernel of this sample (fp32 [H][12], single buffer): free once both
-          // warpgroups finished the previous unit's last chunk
-          mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
-          if (elect_one()) {
-            const uint32_t wf = smem_u32(&bars->w3_full);
-            mbar_expect_tx(wf, (uint32_t)(H * kW3Pitch * 4));
-            bulk_load(s_w3f, p.bias + (long long)s * p.PB + p.w3f_off, (uint32_t)(H * kW3Pitch * 4), wf);
-          }
-          __syncwarp();
-          ++w3_n;
-        }
-      }
-      for (int j = 0; j < n_l2; ++j) {
-        for (int sg = 0; sg < l2_stages; ++sg, ++it) {
-          const uint32_t st = it % k3Stages, ph = (it / k3Stages) & 1;
-          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
-          if (elect_one()) {
-            const uint32_t fb = smem_u32(&bars->full[st]);
-            const uint32_t base = s_stage + st * k3StageBytes + kXBytes;
-            if (leader) mbar_expect_tx(fb, 2u * 2u * kBlkBytes);
-#pragma unroll
-            for (int kblk = 0; kblk < 2; ++kblk)
-              tma2_load_3d(base + kblk * kBlkBytes, &tmW2, fb, j * 128 + (int)rank * 64, (sg * 2 + kblk) * 64, s);
-          }
-          __syncwarp();
-        }
-      }
-    }
-    for (int k = 0; k < k3Stages; ++k, ++it) {
-      const uint32_t st = it % k3Stages, ph = (it / k3Stages) & 1;
-      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer (leader CTA only) ===========================
-    if (leader) {
-      uint32_t st_i = 0, st_ph = 0;
-      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
-      const uint32_t a16_0 = (s_stage & 0x3FFFF) >> 4;
-      uint32_t st_full = full0, st_empty = empty0, st_a16 = a16_0;
-      auto advance = [&]() {
-        if (++st_i == k3Stages) { st_i = 0; st_ph ^= 1; st_full = full0; st_empty = empty0; st_a16 = a16_0; }
-        else { st_full += 8; st_empty += 8; st_a16 += k3StageBytes >> 4; }
-      };
-      constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-      uint32_t ph_act1_0 = 0, ph_act1_1 = 0;
-      uint32_t issued0 = 0, issued1 = 0, waited0 = 0, waited1 = 0;   // accumulator hand-offs per buffer
-      const uint32_t idesc_l2 = make_idesc_bf16(256, 128, 0, 1);
-      // buffer / region b may be overwritten once every accumulator handed to its warpgroup was read
-      auto wait_free = [&](int b) {
-        if (b == 0) { while (waited0 < issued0) { mbar_wait(smem_u32(&bars->buf_free[0]), waited0 & 1); ++waited0; } }
-        else { while (waited1 < issued1) { mbar_wait(smem_u32(&bars->buf_free[1]), waited1 & 1); ++waited1; } }
-        fence_after_sync();
-      };
-
-      for (long long u = u0; u < u1; ++u) {
-        for (int c = 0; c < n_l1; ++c) {
-          const int ncols = min(256, H - c * 256);
-          const uint32_t idesc = make_idesc_bf16(256, ncols, 0, 1);
-          const uint32_t dreg = tmem + c * 256;
-          wait_free(c);
-          if (n_l1 == 1) wait_free(1);     // H <= 256: buffer 1 lives in the otherwise unused region 1
-          DBX_TRACE(100 + c);
-          for (int kb = 0; kb < kb1; ++kb) {
-            mbar_wait(st_full, st_ph);
-            DBX_STAGE_FENCE();
-            if (elect_one()) {
-              const uint32_t a_lo = st_a16 | (1u << 16);
-              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
-              if (kb + 1 < kb1 || (K0 & 63) == 0) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  mma2_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
-              } else {
-                const int ksteps = ((K0 & 63) + 15) >> 4;
-                for (int kk = 0; kk < ksteps; ++kk)
-                  mma2_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
-              }
-              mma2_commit_mc(st_empty, kBoth);
-            }
-            __syncwarp();
-            advance();
-          }
-          if (elect_one()) mma2_commit_mc(smem_u32(&bars->acc_full[c]), kBoth);
-          __syncwarp();
-          if (NH == 1) { if (c == 0) ++issued0; else ++issued1; }
-          DBX_TRACE(110 + c);
-        }
-        for (int j = 0; j < n_l2; ++j) {
-          const int b = j & 1;
-          const uint32_t dbuf = tmem + b * 256 + 128;
-          wait_free(b);
-          DBX_TRACE(120 + j);
-          for (int sg = 0; sg < l2_stages; ++sg) {
-            if (j == 0 && (sg & 1) == 0) {   // first touch of packed H1 region sg>>1 (also frees its upper half)
-              if ((sg >> 1) == 0) { mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0; }
-              else { mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1; }
-            }
-            mbar_wait(st_full, st_ph);
-            DBX_STAGE_FENCE();
-            if (elect_one()) {
-              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
-              const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (sg | i) > 0);
-              mma2_commit_mc(st_empty, kBoth);
-            }
-            __syncwarp();
-            advance();
-          }
-          if (elect_one()) mma2_commit_mc(smem_u32(&bars->acc2_full[b]), kBoth);
-          __syncwarp();
-          if (b == 0) ++issued0; else ++issued1;
-          DBX_TRACE(130 + j);
-        }
-        // H <= 256 with two hidden layers: region 1 is never packed, but chunk 1 of layer 2 used its upper
-        // half as buffer 1 -- nothing else to do, wait_free(1) above covers it.
-      }
-    }
-  } else {
-    // =========================== epilogue: warpgroup 0 = warps 2-5, warpgroup 1 = warps 6-9 ===========================
-    const int wg = (warp - 2) >> 2;
-    const int g = warp & 3;                       // TMEM lane group of this warp
-    const int row = g * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
-    uint32_t ph_acc = 0, ph_acc2 = 0, unit_n = 0;
-    float acc1[kMaxC], acc2[kMaxC];
-#pragma unroll
-    for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
-    unsigned int cnt = 0;
-    int cur_q = (u0 < u1) ? (int)(u0 / p.ns) : -1;
-    const int q_first = cur_q;
-
-    auto flush_segment = [&](int q) {
-      const int seg = q - q_first;
-      const int grow = (q * CM + (int)rank) * 128 + row;
-      if (p.sink_kind == 0) {
-        float* dst = p.partial + ((((long long)cluster_id * p.maxseg + seg) * CM + rank) * 128 + row) * 32;
-#pragma unroll
-        for (int i = 0; i < kMaxC; i += 4) {
-          *reinterpret_cast<float4*>(dst + i) = make_float4(acc1[i], acc1[i + 1], acc1[i + 2], acc1[i + 3]);
-          *reinterpret_cast<float4*>(dst + 16 + i) = make_float4(acc2[i], acc2[i + 1], acc2[i + 2], acc2[i + 3]);
-        }
-      } else if (grow < p.B && cnt) {
-        atomicAdd(p.counts + grow, (unsigned long long)cnt);
-      }
-#pragma unroll
-      for (int i = 0; i < kMaxC; ++i) { acc1[i] = 0.f; acc2[i] = 0.f; }
-      cnt = 0;
-    };
-    // relu(acc + bias) as packed bf16 in place (next layer's A operand)
-    auto pack_chunk = [&](uint32_t src, int ncols, const float* bias) {
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(src + c0, v);
-        wait_ld();
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * i);
-          w[i] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
-        }
-        tmem_st16(src + c0 / 2, w);
-      }
-      wait_st();
-      fence_before_sync();
-    };
-
-    for (long long u = u0; u < u1; ++u, ++unit_n) {
-      const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
-      if (wg == 0 && q != cur_q) { flush_segment(cur_q); cur_q = q; }
-      const uint32_t bb = unit_n & 1;
-      const float* bias = bias_smem + bb * kBiasFloats;
-      mbar_wait(smem_u32(&bars->bias_full[bb]), (unit_n >> 1) & 1);
-      float logit[kW3Pitch];
-#pragma unroll
-      for (int i = 0; i < kW3Pitch; ++i) logit[i] = 0.f;
-
-      // logit += bf16(relu(acc + bias)) * W3[k0 .. k0+ncols), accumulators read from TMEM at `src`
-      auto out_layer_chunk = [&](uint32_t src, int ncols, const float* bvec, int k0) {
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(src + c0, v);
-          wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 b2 = *reinterpret_cast<const float2*>(bvec + c0 + i);
-            // round to bf16 exactly as the packed tensor-core operand would be
-            const uint32_t pk = pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b2.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b2.y, 0.f));
-            const float h0 = __uint_as_float(pk << 16), h1 = __uint_as_float(pk & 0xFFFF0000u);
-            const float4* w0 = reinterpret_cast<const float4*>(w3f + (size_t)(k0 + c0 + i) * kW3Pitch);
-            const float4 a0 = w0[0], a1 = w0[1], a2 = w0[2], c0v = w0[3], c1v = w0[4], c2v = w0[5];
-            logit[0] = fmaf(h0, a0.x, logit[0]); logit[1] = fmaf(h0, a0.y, logit[1]); logit[2] = fmaf(h0, a0.z, logit[2]); logit[3] = fmaf(h0, a0.w, logit[3]);
-            logit[4] = fmaf(h0, a1.x, logit[4]); logit[5] = fmaf(h0, a1.y, logit[5]); logit[6] = fmaf(h0, a1.z, logit[6]); logit[7] = fmaf(h0, a1.w, logit[7]);
-            logit[8] = fmaf(h0, a2.x, logit[8]); logit[9] = fmaf(h0, a2.y, logit[9]); logit[10] = fmaf(h0, a2.z, logit[10]); logit[11] = fmaf(h0, a2.w, logit[11]);
-            logit[0] = fmaf(h1, c0v.x, logit[0]); logit[1] = fmaf(h1, c0v.y, logit[1]); logit[2] = fmaf(h1, c0v.z, logit[2]); logit[3] = fmaf(h1, c0v.w, logit[3]);
-            logit[4] = fmaf(h1, c1v.x, logit[4]); logit[5] = fmaf(h1, c1v.y, logit[5]); logit[6] = fmaf(h1, c1v.z, logit[6]); logit[7] = fmaf(h1, c1v.w, logit[7]);
-            logit[8] = fmaf(h1, c2v.x, logit[8]); logit[9] = fmaf(h1, c2v.y, logit[9]); logit[10] = fmaf(h1, c2v.z, logit[10]); logit[11] = fmaf(h1, c2v.w, logit[11]);
-          }
-        }
-        fence_before_sync();
-      };
-
-      bool w3_waited = false;
-      auto wait_w3 = [&]() { if (!w3_waited) { mbar_wait(smem_u32(&bars->w3_full), unit_n & 1); w3_waited = true; } };
-
-      // ---- layer-1 chunk of this warpgroup
-      if (wg < n_l1) {
-        const int c = wg;
-        const int ncols = min(256, H - c * 256);
-        mbar_wait(smem_u32(&bars->acc_full[c]), ph_acc & 1);
-        ++ph_acc;
-        fence_after_sync();
-        if (warp == 2) DBX_TRACE(200 + c);
-        if (NH == 2) {
-          pack_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->act1_ready[c]), 0);
-        } else {
-          wait_w3();
-          out_layer_chunk(tmem + lane_base + c * 256, ncols, bias + p.b1_off + c * 256, c * 256);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->buf_free[c]), 0);
-        }
-        if (warp == 2) DBX_TRACE(210 + c);
-      }
-      // ---- layer-2 chunks of this warpgroup (buffer == warpgroup)
-      for (int j = wg; j < n_l2; j += 2) {
-        mbar_wait(smem_u32(&bars->acc2_full[wg]), ph_acc2 & 1);
-        ++ph_acc2;
-        fence_after_sync();
-        if (warp == 2) DBX_TRACE(220 + j);
-        wait_w3();
-        out_layer_chunk(tmem + lane_base + wg * 256 + 128, 128, bias + p.b2_off + j * 128, j * 128);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->buf_free[wg]), 0);
-        if (warp == 2) DBX_TRACE(230 + j);
-      }
-      // this warpgroup is done with W3 (and, for WG1, with the biases) of this unit
-      wait_w3();   // keeps the w3 phase in step even if this warpgroup had no chunk
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->w3_empty));
-      if (wg == 1) {
-        // hand the partial logits to warpgroup 0
-        mbar_wait(smem_u32(&bars->logit_empty[bb]), ((unit_n >> 1) & 1) ^ 1);
-        float4* dst = reinterpret_cast<float4*>(lslot + ((size_t)bb * 128 + row) * kW3Pitch);
-        dst[0] = make_float4(logit[0], logit[1], logit[2], logit[3]);
-        dst[1] = make_float4(logit[4], logit[5], logit[6], logit[7]);
-        dst[2] = make_float4(logit[8], logit[9], logit[10], logit[11]);
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(smem_u32(&bars->logit_full[bb])); mbar_arrive(smem_u32(&bars->bias_empty[bb])); }
-        continue;
-      }
-      // ---- warpgroup 0: total logits, output activation, running sums
-      mbar_wait(smem_u32(&bars->logit_full[bb]), (unit_n >> 1) & 1);
-      {
-        const float4* src = reinterpret_cast<const float4*>(lslot + ((size_t)bb * 128 + row) * kW3Pitch);
-        const float4 x0 = src[0], x1 = src[1], x2 = src[2];
-        logit[0] += x0.x; logit[1] += x0.y; logit[2] += x0.z; logit[3] += x0.w;
-        logit[4] += x1.x; logit[5] += x1.y; logit[6] += x1.z; logit[7] += x1.w;
-        logit[8] += x2.x; logit[9] += x2.y; logit[10] += x2.z; logit[11] += x2.w;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->logit_empty[bb]));
-      const float* b3 = bias + p.b3_off;
-      float z[kW3Pitch];
-#pragma unroll
-      for (int i = 0; i < kW3Pitch; ++i) z[i] = (i < p.C) ? logit[i] + b3[i] : -INFINITY;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->bias_empty[bb]));
-      const int grow = (q * CM + (int)rank) * 128 + row;
-      if (p.sink_kind == 0) {
-        const float w = p.wts ? p.wts[s] : 1.f;
-        if (p.out_kind == DBX_OUT_LOGITS) {
-#pragma unroll
-          for (int i = 0; i < kW3Pitch; ++i) if (i < p.C) { acc1[i] = fmaf(w, z[i], acc1[i]); acc2[i] = fmaf(w * z[i], z[i], acc2[i]); }
-        } else if (p.act_last == DBX_ACT_SOFTMAX) {
-          float mx = z[0];
-#pragma unroll
-          for (int i = 1; i < kW3Pitch; ++i) mx = fmaxf(mx, z[i]);
-          float e[kW3Pitch], den = 0.f;
-#pragma unroll
-          for (int i = 0; i < kW3Pitch; ++i) { e[i] = (i < p.C) ? expf(z[i] - mx) : 0.f; den += e[i]; }
-          const float inv = 1.f / den;
-#pragma unroll
-          for (int i = 0; i < kW3Pitch; ++i) { const float pr = e[i] * inv; acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
-        } else {
-#pragma unroll
-          for (int i = 0; i < kW3Pitch; ++i) if (i < p.C) { const float pr = apply_act(p.act_last, z[i]); acc1[i] = fmaf(w, pr, acc1[i]); acc2[i] = fmaf(w * pr, pr, acc2[i]); }
-        }
-      } else {
-        int best = 0; float bv = z[0];
-#pragma unroll
-        for (int i = 1; i < kW3Pitch; ++i) if (z[i] > bv) { bv = z[i]; best = i; }
-        if (grow < p.B) {
-          const int ok = (best == p.labels[grow]);
-          if (p.flags) p.flags[(long long)s * p.B + grow] = (uint8_t)ok;
-          cnt += ok;
-        }
-      }
-    }
-    if (wg == 0 && cur_q >= 0) flush_segment(cur_q);
-  }
-
-  fence_before_sync();
-  __syncthreads();
-  cluster_sync();
-  if (warp == 1) tmem_dealloc2<512>(tmem);
 }
-
-#include "fused_mlp4.cuh"
 
 // Adds the per-(cluster, segment) partial sums in sample order.
 __global__ void finish_kernel(const float* __restrict__ partial, int NC, int maxseg, int CM, long long U, int ns, int B,
@@ -1521,6 +1068,14 @@ __global__ void zero_counts_kernel(unsigned long long* p, int64_t n) {
 
 long long* g_trace_buf = nullptr;
 
+// Tensor maps of one (workspace, batch, chunk size, kernel) combination: encoded once, reused by every later call
+// with the same key (a repeated predict call encodes nothing).
+struct FusedPlan {
+  const void* ws = nullptr; size_t ws_bytes = 0;
+  int64_t B = -1, ns = -1; int variant = 0;
+  CUtensorMap tmX, tmW1[2], tmW2[2], tmW3[2];
+};
+
 struct FusedState {
   int num_sms = 0;
   // weight sampling of chunk c+1 runs on a side stream while chunk c is in the fused kernel
@@ -1531,6 +1086,9 @@ struct FusedState {
   bool consumed_rec[2] = {false, false};          // ev_consumed[b] was recorded by a previous call ...
   size_t lay_x = 0, lay_w = 0, lay_b = 0;         // ... whose workspace layout was this
   cudaEvent_t ev_entry = nullptr, ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in = nullptr;
+  FusedPlan plan;
+  bool attr_set[2] = {false, false};
 };
 
 static bool shape_supported(const dbx_model* m) {
@@ -1547,89 +1105,52 @@ static bool shape_supported(const dbx_model* m) {
   return true;
 }
 
-template <int CM>
-static int launch_fused(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
-                        const FusedParams& p, int smem, cudaStream_t st) {
-  DBX_CUDA(cudaFuncSetAttribute(fused_mlp_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.NC * CM));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = (size_t)smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp_kernel<CM>, tmX, tmW1, tmW2, tmW3, p));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
-}
+constexpr int kSmem1 = kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024;
+constexpr int kSmem2 = k2Stages * k2StageBytes + kW3Bytes / 2 + 2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024;
 
-template <bool S1>
-static int launch_fused2(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
+// single-CTA kernel (a lone 128-row tile: a CTA pair would idle its second half)
+static int launch_fused1(FusedState* fs, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
                          const FusedParams& p, cudaStream_t st) {
-  constexpr int smem = (S1 ? k2StagesS1 * k2StageBytes + k2H1Bytes : k2Stages * k2StageBytes) + kW3Bytes / 2 +
-                       2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024;
-  DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<S1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (!fs->attr_set[0]) {
+    DBX_CUDA(cudaFuncSetAttribute(fused_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1));
+    fs->attr_set[0] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p.NC);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)kSmem1;
+  cfg.stream = st;
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp_kernel<1>, tmX, tmW1, tmW2, tmW2, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// CTA-pair kernel (cta_group::2): the default
+static int launch_fused2(FusedState* fs, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
+                         const CUtensorMap& tmW3, const FusedParams& p, cudaStream_t st) {
+  if (!fs->attr_set[1]) {
+    DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    fs->attr_set[1] = true;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.NC * 2));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.dynamicSmemBytes = (size_t)kSmem2;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<S1>, tmX, tmW1, tmW2, tmW3, p));
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel, tmX, tmW1, tmW2, tmW3, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
-}
-
-static int launch_fused3(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const FusedParams& p,
-                         int smem, cudaStream_t st) {
-  DBX_CUDA(cudaFuncSetAttribute(fused_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.NC * 2));
-  cfg.blockDim = dim3(k3Threads);
-  cfg.dynamicSmemBytes = (size_t)smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp3_kernel, tmX, tmW1, tmW2, p));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
-}
-
-static int launch_fused4(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmW3,
-                         const FusedParams& p, cudaStream_t st) {
-  DBX_CUDA(cudaFuncSetAttribute(fused_mlp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k4SmemBytes));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.NC * 2));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = (size_t)k4SmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp4_kernel, tmX, tmW1, tmW2, tmW3, p));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
-}
-
-static inline int grid_for2(int64_t total, int block = 256) {
-  return (int)std::min<int64_t>(std::max<int64_t>(cdiv(total, block), 1), 148 * 16);
 }
 
 static FusedState* fused_state_of(dbx_model* m) {
   FusedState* fs = (FusedState*)m->fused_state;
   if (!fs) {
     fs = new FusedState();
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) { delete fs; return nullptr; }
-    fs->num_sms = prop.multiProcessorCount;
+    if (cudaDeviceGetAttribute(&fs->num_sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess) { delete fs; return nullptr; }
     if (cudaStreamCreateWithFlags(&fs->side, cudaStreamNonBlocking) != cudaSuccess) { delete fs; return nullptr; }
     int lo = 0, hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
@@ -1637,6 +1158,7 @@ static FusedState* fused_state_of(dbx_model* m) {
     cudaEventCreateWithFlags(&fs->ev_entry, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&fs->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&fs->ev_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&fs->ev_in, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) {
       cudaEventCreateWithFlags(&fs->ev_sampled[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&fs->ev_consumed[i], cudaEventDisableTiming);
@@ -1646,86 +1168,79 @@ static FusedState* fused_state_of(dbx_model* m) {
   return fs;
 }
 
-static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink, cudaStream_t st);
+static inline int grid_for2(const FusedState* fs, int64_t total, int block = 256) {
+  return (int)std::min<int64_t>(std::max<int64_t>(cdiv(total, block), 1), (int64_t)fs->num_sms * 16);
+}
+
+static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, int64_t B, int64_t n, const Source& src,
+                            const Sink& sink, cudaStream_t st);
 
 // The fused kernels run on a HIGH-priority stream of the engine's own, joined with the caller's stream at both ends: the
 // sampler of the next chunk shares the SMs with them from a default-priority side stream, and at every chunk boundary the
-// next fused launch's CTA pairs then get SM slots ahead of the sampler's queued blocks (DBX_FUSED_PRIO=0: caller's stream).
+// next fused launch's CTA pairs then get SM slots ahead of the sampler's queued blocks (option FUSED_PRIO=0: caller's stream).
 int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
                   cudaStream_t st_user) {
   if (!shape_supported(m)) return 0;
   if (!get_encode_fn()) return 0;
   FusedState* fs = fused_state_of(m);
   if (!fs) return -1;
-  bool prio = true;
-  if (const char* e = getenv("DBX_FUSED_PRIO")) prio = atoi(e) != 0;
-  if (!prio) return fused_mlp_run_on(m, x_dev, B, n, src, sink, st_user);
+  if (!opt().fused_prio) return fused_mlp_run_on(m, fs, x_dev, B, n, src, sink, st_user);
   if (cudaEventRecord(fs->ev_join, st_user) != cudaSuccess || cudaStreamWaitEvent(fs->main, fs->ev_join, 0) != cudaSuccess) return -1;
-  const int rc = fused_mlp_run_on(m, x_dev, B, n, src, sink, fs->main);
+  const int rc = fused_mlp_run_on(m, fs, x_dev, B, n, src, sink, fs->main);
   if (cudaEventRecord(fs->ev_done, fs->main) != cudaSuccess || cudaStreamWaitEvent(st_user, fs->ev_done, 0) != cudaSuccess) return -1;
   return rc;
 }
 
-static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
-                            cudaStream_t st) {
-  if (!shape_supported(m)) return 0;
-  if (!get_encode_fn()) return 0;
-  FusedState* fs = fused_state_of(m);
-  if (!fs) return -1;
+// Samples per fused launch.  256 x Q row-tile pairs keep every cluster busy for large batches.  With one or two row tiles
+// per sample (config 5: 128 inputs x 100k samples) a launch of 256 samples is over before its pipeline has filled, so
+// long runs use up to 1024 (still >= 4 chunks, so that sampling keeps overlapping).  SHORT calls (n <= 256: the per-rank
+// share of a sample-sharded predict) are cut into 2-4 launches so that only the first quarter of the
+// sampling is exposed before the first fused launch; each launch keeps >= 4 units per cluster.
+static int64_t samples_per_launch(const FusedState* fs, int64_t n, int Q, int CM) {
+  if (opt().fused_ns > 0) return std::min<int64_t>(n, opt().fused_ns);
+  int64_t ns_max = 256;
+  if (Q <= 4 && n >= 2048) ns_max = std::min<int64_t>(1024, (n / 4) / 256 * 256);
+  if (n > ns_max) return ns_max;
+  const int64_t NC = std::max(1, fs->num_sms / CM);
+  const int64_t min_ns = cdiv(4 * NC, Q);                  // >= 4 units per cluster and launch
+  int64_t parts = std::min<int64_t>(4, std::max<int64_t>(1, n / std::max<int64_t>(min_ns, 1)));
+  return cdiv(n, parts);
+}
+
+static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, int64_t B, int64_t n, const Source& src,
+                            const Sink& sink, cudaStream_t st) {
   std::vector<const Layer*> dl;
   for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
   const int NH = (int)dl.size() - 1, H = dl[0]->units, K0 = (int)m->in_feat, C = (int)m->out_feat;
   const Layer* Lout = dl.back();
 
-  int CM = 1;
-  if (const char* e = getenv("DBX_FUSED_CM")) CM = atoi(e);
-  if (CM != 1 && CM != 2 && CM != 4) CM = 1;
-  // kernel variant: 1 = single-CTA (clusters only multicast); 2 = CTA pair (cta_group::2), output layer on the
-  // tensor cores -- the default; 3 = CTA pair with the output layer on FFMA in two epilogue warpgroups (kept as
-  // a measured negative result: broadcasting W3 to every row-thread is shared-memory-bandwidth bound)
-  int variant = 2;
-  if (const char* e = getenv("DBX_FUSED_KERNEL")) variant = atoi(e);
-  if (const char* e = getenv("DBX_FUSED_2CTA")) variant = atoi(e) ? 2 : 1;
-  if (variant == 3 && C > kW3Pitch) variant = 1;
-  if (variant >= 2 && B <= 128 && !getenv("DBX_FUSED_KERNEL")) variant = 1;   // a single 128-row tile: a CTA pair would idle its second half
-  if (variant < 1 || variant > 4) variant = 1;
-  if (variant == 4 && !(NH == 2 && H == k4H)) variant = 2;   // v4 is the 2-hidden-layer H = 512 kernel
-  const bool two_cta = variant >= 2;
-  // v2 only, opt-in (DBX_FUSED_H1SMEM=1): second half of H1 in shared memory.  Measured slower (5.84 vs 5.59 ms per
-  // config-2 step): the SS N=128 pair MMA costs 106 cycles against 73.5 for the .ts form (tools/mma_rate2.cu).
-  bool h1_smem = false;
-  if (const char* e = getenv("DBX_FUSED_H1SMEM")) h1_smem = variant == 2 && NH == 2 && H > 256 && atoi(e) != 0;
-  if (two_cta) CM = 2;
-  // v3 keeps the output-layer kernel as fp32 [H][12] behind the biases of each sample
-  const int64_t pbs = round_up(m->PB, 4);
-  const int64_t PBx = (variant == 3) ? pbs + (int64_t)H * kW3Pitch : m->PB;
+  // kernel: 2 = CTA pair (cta_group::2), the default; 1 = single-CTA kernel for a lone 128-row tile (option FUSED_KERNEL forces one)
+  int variant = (B <= 128) ? 1 : 2;
+  if (opt().fused_kernel == 1 || opt().fused_kernel == 2) variant = (int)opt().fused_kernel;
+  const bool two_cta = variant == 2;
+  const int CM = two_cta ? 2 : 1;
   const int T = (int)cdiv(B, 128);
   const int Q = (int)cdiv(T, CM);
-  // samples per launch: 256 x Q row tiles keeps every cluster busy for large batches; with one or two row tiles per sample
-  // (config 5: 128 inputs x 100k samples) a launch of 256 samples is over before its pipeline has filled, so long runs use
-  // up to 1024 (still >= 4 chunks, so that sampling keeps overlapping): 235 -> 219 us per 256 samples
-  int64_t ns_max = 256;
-  if (Q <= 4 && n >= 2048) ns_max = std::min<int64_t>(1024, (n / 4) / 256 * 256);
-  if (const char* e = getenv("DBX_FUSED_NS")) ns_max = std::max(1, atoi(e));
-  const int64_t ns = std::min<int64_t>(n, ns_max);
+  const int64_t ns = samples_per_launch(fs, n, Q, CM);
 
   // ---- workspace: X bf16 | W16 [ns,P16] | B32 [ns,PB] | partials
   const int K0p = (int)round_up(K0, 8);
   const size_t x_b = round_up((size_t)B * K0p * 2, 1024);
   const size_t w_b = round_up((size_t)ns * m->P16 * 2, 1024);
-  const size_t b_b = round_up((size_t)ns * PBx * 4, 1024);
+  const size_t b_b = round_up((size_t)ns * m->PB * 4, 1024);
   const int NCmax = std::max(1, fs->num_sms / CM);
   const int maxseg = (int)cdiv(Q, NCmax) + 2;
-  // v4 work order: 1 = [s][q] round-robin (L2-friendly), needs Q <= 64 for the visited mask
-  const bool order_ok = (variant == 2 || variant == 4) && Q <= 64;
+  // work order: 1 = [s][q] round-robin (L2-friendly; CTA-pair kernel, needs Q <= 64 for the visited mask), 0 = [q][s] ranges
+  const bool order_ok = two_cta && Q <= 64;
   int order = order_ok ? 1 : 0;
-  if (const char* e = getenv("DBX_FUSED_ORDER")) order = (order_ok && atoi(e) != 0) ? 1 : 0;
+  if (opt().fused_order >= 0) order = (order_ok && opt().fused_order != 0) ? 1 : 0;
   const size_t part_b = round_up(std::max((size_t)NCmax * maxseg * CM * 128 * 32 * 4,
                                           order ? (size_t)NCmax * Q * CM * 128 * 32 * 4 + (size_t)NCmax * 8 : (size_t)0), 1024);
   const size_t need = x_b + 2 * (w_b + b_b) + part_b;
   if (m->fused_ws.bytes < need) {
     if (ensure_ws(m->fused_ws, need)) return -1;
     if (cudaMemsetAsync(m->fused_ws.ptr, 0, need, st) != cudaSuccess) return -1;  // pad columns stay zero
+    fs->plan.ws = nullptr;
   }
   char* wp = (char*)m->fused_ws.ptr;
   __nv_bfloat16* X16 = (__nv_bfloat16*)wp; wp += x_b;
@@ -1733,58 +1248,47 @@ static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t
   for (int i = 0; i < 2; ++i) { W16buf[i] = (__nv_bfloat16*)wp; wp += w_b; B32buf[i] = (float*)wp; wp += b_b; }
   float* partial = (float*)wp;
 
-  cast_rows_bf16_kernel<<<grid_for2(B * K0p), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
+  cast_rows_bf16_kernel<<<grid_for2(fs, B * K0p), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
   g_launches.fetch_add(1);
   if (cudaGetLastError() != cudaSuccess) { set_err("cast launch failed"); return -1; }
 
-  // ---- tensor maps
-  CUtensorMap tmX, tmW1, tmW2, tmW3;
-  {
-    uint64_t d[2] = {(uint64_t)K0, (uint64_t)B}, s[1] = {(uint64_t)K0p * 2};
-    uint32_t b[2] = {variant == 4 ? 32u : 64u, 128};
-    if (!make_tmap_bf16(&tmX, X16, 2, d, s, b, variant == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
-  }
-  CUtensorMap tmW1b[2], tmW2b[2];
-  for (int i = 0; i < 2; ++i) {
-    auto make_w = [&](CUtensorMap* tm, const Layer* L, uint32_t bn, uint32_t bk, CUtensorMapSwizzle swz) {
-      uint64_t d[3] = {(uint64_t)L->w_cols_pad, (uint64_t)L->w_rows, (uint64_t)ns};
-      uint64_t sb[2] = {(uint64_t)L->w_cols_pad * 2, (uint64_t)m->P16 * 2};
-      uint32_t b[3] = {bn, bk, 1};
-      return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 3, d, sb, b, swz);
-    };
-    const uint32_t bk = variant == 4 ? 32 : 64;
-    if (!make_w(&tmW1b[i], dl[0], 64, bk, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W1 failed"); return -1; }
-    if (!make_w(&tmW2b[i], NH == 2 ? dl[1] : dl[0], 64, bk, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map W2 failed"); return -1; }
-  }
-  (void)tmW1; (void)tmW2; (void)tmW3;
-  CUtensorMap tmW3b[2];
-  for (int i = 0; i < 2; ++i) {
-    // last layer's kernel in blocked8 order viewed as rows of 64 bf16: CTA r of a pair fetches rows [r*H/8, (r+1)*H/8)
-    uint64_t d[3] = {64, (uint64_t)(Lout->w_rows * Lout->w_cols_pad / 64), (uint64_t)ns};
-    uint64_t sb[2] = {128, (uint64_t)m->P16 * 2};
-    uint32_t b[3] = {64, (uint32_t)(H / 8), 1};
-    if (!make_tmap_bf16(&tmW3b[i], W16buf[i] + Lout->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
+  // ---- tensor maps (cached: the workspace layout is a function of B and ns)
+  FusedPlan& pl = fs->plan;
+  if (pl.ws != m->fused_ws.ptr || pl.ws_bytes != m->fused_ws.bytes || pl.B != B || pl.ns != ns || pl.variant != variant) {
+    {
+      uint64_t d[2] = {(uint64_t)K0, (uint64_t)B}, s[1] = {(uint64_t)K0p * 2};
+      uint32_t b[2] = {64u, 128};
+      if (!make_tmap_bf16(&pl.tmX, X16, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
+    }
+    for (int i = 0; i < 2; ++i) {
+      auto make_w = [&](CUtensorMap* tm, const Layer* L) {
+        uint64_t d[3] = {(uint64_t)L->w_cols_pad, (uint64_t)L->w_rows, (uint64_t)ns};
+        uint64_t sb[2] = {(uint64_t)L->w_cols_pad * 2, (uint64_t)m->P16 * 2};
+        uint32_t b[3] = {64, 64, 1};
+        return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B);
+      };
+      if (!make_w(&pl.tmW1[i], dl[0])) { set_err("tensor map W1 failed"); return -1; }
+      if (!make_w(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0])) { set_err("tensor map W2 failed"); return -1; }
+      // last layer's kernel in blocked8 order viewed as rows of 64 bf16: CTA r of a pair fetches rows [r*H/8, (r+1)*H/8)
+      uint64_t d[3] = {64, (uint64_t)(Lout->w_rows * Lout->w_cols_pad / 64), (uint64_t)ns};
+      uint64_t sb[2] = {128, (uint64_t)m->P16 * 2};
+      uint32_t b[3] = {64, (uint32_t)(H / 8), 1};
+      if (!make_tmap_bf16(&pl.tmW3[i], W16buf[i] + Lout->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
+    }
+    pl.ws = m->fused_ws.ptr; pl.ws_bytes = m->fused_ws.bytes; pl.B = B; pl.ns = ns; pl.variant = variant;
   }
   // the last layer's kernel goes out in tcgen05 core-matrix order (one bulk copy per sample)
   TensorTable tab = m->table;
   for (int i = 0; i < tab.n; ++i)
-    if (!tab.is_bias[i] && tab.src_off[i] == (int32_t)Lout->w_off) {
-      if (variant == 3) { tab.is_bias[i] = 2; tab.dst_off[i] = (int32_t)pbs; }   // fp32 [H][12] in the bias array
-      else tab.blocked8[i] = 1;
-    }
-
-  const int smem = (variant == 3) ? (k3Stages * k3StageBytes + 512 * kW3Pitch * 4 + 2 * kBiasFloats * 4 + 2 * 128 * kW3Pitch * 4 + (int)sizeof(Barriers3) + 1024)
-                 : two_cta ? (k2Stages * k2StageBytes + kW3Bytes / 2 + 2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024)
-                           : (kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024);
+    if (!tab.is_bias[i] && tab.src_off[i] == (int32_t)Lout->w_off) tab.blocked8[i] = 1;
 
   if (sink.kind == 1 && !sink.accumulate) {
-    zero_counts_kernel<<<grid_for2(B), 256, 0, st>>>(sink.counts, B);
+    zero_counts_kernel<<<grid_for2(fs, B), 256, 0, st>>>(sink.counts, B);
     g_launches.fetch_add(1);
   }
 
-  // overlap: sampling runs one chunk ahead on the side stream (env DBX_FUSED_OVERLAP=0 disables)
-  bool overlap = true;
-  if (const char* e = getenv("DBX_FUSED_OVERLAP")) overlap = atoi(e) != 0;
+  // overlap: sampling runs one chunk ahead on the side stream (option FUSED_OVERLAP=0 disables)
+  const bool overlap = opt().fused_overlap != 0;
   cudaStream_t sst = overlap ? fs->side : st;
   if (overlap) {
     // Sampling does not depend on this call's input, only on the previous call having finished with the weight
@@ -1800,9 +1304,7 @@ static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t
     } else if (fs->used && cudaStreamWaitEvent(sst, fs->ev_entry, 0) != cudaSuccess) return -1;
     if (m->ev_posterior && cudaStreamWaitEvent(sst, m->ev_posterior, 0) != cudaSuccess) return -1;
     if (src.stored || src.eps) {   // slab / injected eps may have been produced on `st` just before this call
-      static thread_local cudaEvent_t ev_in = nullptr;
-      if (!ev_in) cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
-      if (cudaEventRecord(ev_in, st) != cudaSuccess || cudaStreamWaitEvent(sst, ev_in, 0) != cudaSuccess) return -1;
+      if (cudaEventRecord(fs->ev_in, st) != cudaSuccess || cudaStreamWaitEvent(sst, fs->ev_in, 0) != cudaSuccess) return -1;
     }
   }
   const int64_t nchunks = cdiv(n, ns);
@@ -1812,7 +1314,7 @@ static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t
     const int64_t c0 = ci * ns;
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     if (overlap && ci >= 2 && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
-    if (launch_sample_bf16(m, tab, src, c0, nc, W16buf[b], B32buf[b], sst, PBx)) return -1;
+    if (launch_sample_bf16(m, tab, src, c0, nc, W16buf[b], B32buf[b], sst, m->PB)) return -1;
     if (overlap && cudaEventRecord(fs->ev_sampled[b], sst) != cudaSuccess) return -1;
     return 0;
   };
@@ -1824,36 +1326,31 @@ static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t
     if (ci + 1 < nchunks && sample_chunk(ci + 1)) return -1;   // next chunk's weights, concurrently
     if (overlap && cudaStreamWaitEvent(st, fs->ev_sampled[bsel], 0) != cudaSuccess) return -1;
     __nv_bfloat16* W16 = W16buf[bsel];
-    float* B32 = B32buf[bsel];
-    const CUtensorMap& tmW1c = tmW1b[bsel];
-    const CUtensorMap& tmW2c = tmW2b[bsel];
 
     FusedParams p = {};
     p.K0 = K0; p.H = H; p.NH = NH; p.C = C; p.B = (int)B; p.ns = nc; p.CM = CM;
-    p.mc = 1; if (const char* e = getenv("DBX_FUSED_MC")) p.mc = atoi(e);
+    p.mc = 0;
     p.Q = Q; p.U = (long long)Q * nc;
     p.NC = (int)std::min<long long>(NCmax, std::max<long long>(1, p.U));
     p.maxseg = maxseg;
     p.sink_kind = sink.kind; p.out_kind = sink.out_kind; p.act_last = Lout->act; p.want_sum2 = sink.sum2 != nullptr;
-    p.bias = B32; p.PB = PBx; p.w3f_off = (int)pbs;
+    p.bias = B32buf[bsel]; p.PB = m->PB; p.w3f_off = 0;
     p.b1_off = (int)dl[0]->b32_off; p.b2_off = (int)(NH == 2 ? dl[1]->b32_off : 0); p.b3_off = (int)Lout->b32_off;
     p.wts = sink.wts ? sink.wts + c0 : nullptr;
     p.labels = sink.labels; p.flags = sink.flags ? sink.flags + c0 * B : nullptr; p.counts = sink.counts;
     p.partial = partial;
     p.w3 = W16 + Lout->w16_off; p.P16 = m->P16; p.w3_bytes = (int)(Lout->w_rows * Lout->w_cols_pad * 2);
     p.chunk = (int)ci; p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
-    p.trace = nullptr; p.trace_only = 0;
-    if (const char* e = getenv("DBX_FUSED_TRACE_ONLY")) p.trace_only = (unsigned)strtoul(e, nullptr, 10);
-    if (const char* e = getenv("DBX_FUSED_TRACE")) { if (atoi(e)) { static long long* tb = nullptr; if (!tb) { cudaMalloc(&tb, 8 * 31208); } cudaMemsetAsync(tb, 0, 8 * 31208, st); p.trace = tb; g_trace_buf = tb; } }
+    p.trace = nullptr; p.trace_only = (unsigned)opt().fused_trace_only;
+    if (opt().fused_trace) {
+      static long long* tb = nullptr;
+      if (!tb) cudaMalloc(&tb, 8 * 31208);
+      cudaMemsetAsync(tb, 0, 8 * 31208, st);
+      p.trace = tb; g_trace_buf = tb;
+    }
     prof_begin(st);
-    int rc = 0;
-    if (variant == 4) rc = launch_fused4(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st);
-    else if (variant == 3) rc = launch_fused3(tmX, tmW1c, tmW2c, p, smem, st);
-    else if (two_cta) rc = h1_smem ? launch_fused2<true>(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st)
-                             : launch_fused2<false>(tmX, tmW1c, tmW2c, tmW3b[bsel], p, st);
-    else if (CM == 1) rc = launch_fused<1>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
-    else if (CM == 2) rc = launch_fused<2>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
-    else rc = launch_fused<4>(tmX, tmW1c, tmW2c, tmW2c, p, smem, st);
+    const int rc = two_cta ? launch_fused2(fs, pl.tmX, pl.tmW1[bsel], pl.tmW2[bsel], pl.tmW3[bsel], p, st)
+                           : launch_fused1(fs, pl.tmX, pl.tmW1[bsel], pl.tmW2[bsel], p, st);
     if (rc) return -1;
     prof_end(st, (double)m->flops * (double)B * nc);
     if (sink.kind == 0) {
@@ -1861,13 +1358,13 @@ static int fused_mlp_run_on(dbx_model* m, const float* x_dev, int64_t B, int64_t
       if (order) {
         if (ci == 0) nc_first = p.NC;
         if (ci + 1 == nchunks) {   // the slices carried the sums of every chunk
-          finish4_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.visited, nc_first, Q, CM, (int)B, C, sink.accumulate ? 0 : 1,
-                                                           sink.sum1, sink.sum2);
+          finish4_kernel<<<grid_for2(fs, B * C), 256, 0, st>>>(partial, p.visited, nc_first, Q, CM, (int)B, C, sink.accumulate ? 0 : 1,
+                                                               sink.sum1, sink.sum2);
           g_launches.fetch_add(1);
         }
       } else {
-        finish_kernel<<<grid_for2(B * C), 256, 0, st>>>(partial, p.NC, maxseg, CM, p.U, nc, (int)B, C, overwrite, sink.sum1,
-                                                         sink.sum2);
+        finish_kernel<<<grid_for2(fs, B * C), 256, 0, st>>>(partial, p.NC, maxseg, CM, p.U, nc, (int)B, C, overwrite, sink.sum1,
+                                                             sink.sum2);
         g_launches.fetch_add(1);
       }
       if (cudaGetLastError() != cudaSuccess) { set_err("finish launch failed"); return -1; }
@@ -1908,6 +1405,7 @@ void fused_mlp_free(dbx_model* m) {
     if (fs->main) cudaStreamDestroy(fs->main);
     if (fs->ev_join) cudaEventDestroy(fs->ev_join);
     if (fs->ev_done) cudaEventDestroy(fs->ev_done);
+    if (fs->ev_in) cudaEventDestroy(fs->ev_in);
     for (int i = 0; i < 2; ++i) { if (fs->ev_sampled[i]) cudaEventDestroy(fs->ev_sampled[i]); if (fs->ev_consumed[i]) cudaEventDestroy(fs->ev_consumed[i]); }
     delete fs; m->fused_state = nullptr;
   }

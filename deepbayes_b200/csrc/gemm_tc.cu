@@ -1298,7 +1298,7 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
   // lowers the threshold so that tests reach it with small shapes)
   {
     // big GEMMs: CTA pairs on 256 x 256 tiles (dense_tc_pair_kernel; DBX_NO_PAIR_GEMM=1 disables)
-    if (M >= 256 && N >= 256 && K >= 256 && !(getenv("DBX_NO_PAIR_GEMM") && getenv("DBX_NO_PAIR_GEMM")[0] == '1')) {
+    if (M >= 256 && N >= 256 && K >= 256 && !opt().no_pair_gemm) {
       static int num_sms2 = 0;
       if (!num_sms2) {
         int dev = 0;
@@ -1311,7 +1311,7 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
         // bf16 output: TMA stores from a staging box (needs 16-byte pitches; otherwise the kernel stores directly)
         CUtensorMap tmO = tmW;
         int tma_out = 0;
-        if (out16 && !(getenv("DBX_NO_TMA_STORE") && getenv("DBX_NO_TMA_STORE")[0] == '1') && (ld16 & 7) == 0 && (o16_sstride & 7) == 0 &&
+        if (out16 && !opt().no_tma_store && (ld16 & 7) == 0 && (o16_sstride & 7) == 0 &&
             ((uintptr_t)out16 & 15) == 0) {
           uint64_t d[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)ld16 * 2, (uint64_t)o16_sstride * 2};
           uint32_t b[3] = {64, 32, 1};
@@ -1336,9 +1336,7 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
     }
     const int tiles_m = (int)cdiv(M, 128), tiles_n = (int)cdiv(N, p.NT);
     const long long tiles = (long long)ns * tiles_m * tiles_n;
-    long long min_tiles = 296;
-    if (const char* e = getenv("DBX_PERSIST_MIN_TILES")) min_tiles = atoll(e);
-    if (tiles >= min_tiles && !(getenv("DBX_NO_PERSIST") && getenv("DBX_NO_PERSIST")[0] == '1')) {
+    if (tiles >= opt().persist_min_tiles && !opt().no_persist) {
       static int num_sms = 0;
       if (!num_sms) {
         int dev = 0;
@@ -1434,8 +1432,7 @@ static int conv_tc_smem(const Layer& L, int* w_res, int* patch, int* R_out, int 
   const int w_tap_b = nblk * Cin * 128;
   const int res = taps * w_tap_b <= 40 * 1024 ? 1 : 0;
   const int PW = L.out_w + L.kw - 1;
-  int pm = (res && PW <= 128) ? 1 : 0;
-  if (const char* e = getenv("DBX_CONV_PATCH")) pm = pm && atoi(e) != 0;
+  const int pm = (res && PW <= 128) ? 1 : 0;
   int R = std::min(pm ? 128 / PW : 128 / L.out_w, L.out_h);
   if (pool) R &= ~1;                                   // pooling windows must not straddle tiles
   const int a_bytes = pm ? (((L.kh - 1) * PW + L.kw - 1 + 128) * Cin * 2 + 1023) / 1024 * 1024 : 128 * Cin * 2;
@@ -1464,7 +1461,7 @@ bool conv_tc_eligible(const Layer& L) {
 // Can the 2x2 / stride-2 MaxPool behind this convolution be done in its epilogue?
 bool conv_tc_pool_eligible(const Layer& L, const Layer& P) {
   if (!conv_tc_eligible(L) || P.kind != DBX_MAXPOOL2D || P.kh != 2 || P.kw != 2 || P.sh != 2 || P.sw != 2) return false;
-  if (const char* e = getenv("DBX_NO_POOL_FUSE")) if (e[0] == '1') return false;
+  if (opt().no_pool_fuse) return false;
   const int Cout = L.out_c;
   if (!(Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64) || L.out_h < 2 || L.out_w < 2) return false;
   int R = 0, stages = 0;
@@ -1500,7 +1497,6 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
   p.NB = NB; p.Ho = Ho; p.Wo = Wo; p.Cin = Cin; p.Cout = Cout; p.kh = L.kh; p.kw = L.kw; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
   p.R = R; p.tiles_per_img = (int)cdiv(Ho, R); p.ns = ns; p.a_shared = in_shared; p.act = act; p.w_res = w_res;
   p.patch = patch; p.PW = PW; p.base_off = 0; p.stages = stages; p.pool = pool;
-  if (const char* e = getenv("DBX_CONV_BASEOFF")) p.base_off = atoi(e);
   p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.out = out; p.o_sstride = o_sstride;
   static int num_sms = 0;
   if (!num_sms) {
@@ -1523,7 +1519,7 @@ int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared,
 bool ibp_tc_eligible(int N, int K) {
   if (!g_tc_ok || !get_encode_fn()) return false;
   if ((K & 7) || (N & 7)) return false;
-  if (const char* e = getenv("DBX_NO_IBP_TC")) if (e[0] == '1') return false;
+  if (opt().no_ibp_tc) return false;
   return true;
 }
 

@@ -261,7 +261,7 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   }
   const int64_t C = m->out_feat;
   bool use_tc = kBf16 && !(weight_margin > 0.f);
-  if (const char* e = getenv("DBX_NO_TC")) if (e[0] == '1') use_tc = false;
+  if (opt().no_tc) use_tc = false;
   DBX_CHECK(!(weight_margin > 0.f) || (m->have_gaussian && !kBf16), "weight margins need a Gaussian posterior's sigma and the fp32 mode");
   // ---- workspace per sample: 4 activation buffers (centre/radius, ping-pong), fp32 MU/R (tensor-core back end),
   //      lower/upper/worst, weights (+ |W16|)
@@ -272,8 +272,7 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
   DBX_CHECK(!kBf16 || m->P16 % 8 == 0, "bf16 parameter pitch %lld is not a multiple of 8", (long long)m->P16);
   // bf16: the weights of chunk c + 1 are drawn on a side stream while chunk c is in the GEMMs (two W16 / bias buffers;
   // the sampler is ALU work, the GEMMs tensor-pipe work); DBX_IBP_OVERLAP=0 serialises them
-  bool overlap = kBf16;
-  if (const char* e = getenv("DBX_IBP_OVERLAP")) overlap = overlap && atoi(e) != 0;
+  const bool overlap = kBf16 && opt().ibp_overlap != 0;
   const int nwb = overlap ? 2 : 1;
   const size_t pb_b = round_up((size_t)m->PB * 4, 16);
   const size_t w_b = kBf16 ? (w16_b * (nwb + (use_tc ? 1 : 0)) + nwb * pb_b) : (src.stored ? 0 : (size_t)m->P * 4);
@@ -319,8 +318,7 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
     // the GEMM chain runs on a HIGH-priority stream of our own (joined with the caller's stream at both ends): its short
     // persistent kernels then get SM slots ahead of the sampler's queued blocks instead of waiting for the sampler grid to
     // drain (DBX_IBP_PRIO=0: run it on the caller's stream)
-    bool prio = true;
-    if (const char* e = getenv("DBX_IBP_PRIO")) prio = atoi(e) != 0;
+    const bool prio = opt().ibp_prio != 0;
     if (prio) {
       if (!m->ibp_main) {
         int lo = 0, hi = 0;

@@ -311,7 +311,7 @@ static int launch_stream(StreamParams& p, int num_sms, size_t smem, cudaStream_t
 int stream_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
                    cudaStream_t st) {
   if (!m->is_mlp || B > 16 || B < 1) return 0;
-  if (const char* e = getenv("DBX_NO_STREAM")) if (e[0] == '1') return 0;
+  if (opt().no_stream) return 0;
   StreamParams p = {};
   int nl = 0;
   int maxw = 1;

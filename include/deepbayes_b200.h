@@ -225,7 +225,14 @@ int dbx_profile_read(double* ms_total, double* flops_total, int64_t* launches);
 /* which kernels served the last compute call: 0 generic (CUDA cores), 1 fused tcgen05 MLP,
  * 2 small-batch streaming, 3 generic with per-layer tcgen05 GEMMs (bf16 mode). */
 int dbx_last_path(void);
-/* Development hook (tools/trace_fused.py): with DBX_FUSED_TRACE=1 the fused kernel records (probe id, clock) pairs of one
+/* Process-wide A/B switches of the kernel dispatch (DESIGN.md section 5 lists them; none selects a CPU or library
+ * fallback).  Their defaults are read ONCE from the DBX_<NAME> environment variables; afterwards only these calls change
+ * them (the parity tests compare one kernel against another this way).  `name` without the DBX_ prefix, e.g. "NO_FUSED".
+ * dbx_reset_options re-reads the environment defaults. */
+int dbx_set_option(const char* name, int64_t value);
+int dbx_get_option(const char* name, int64_t* value);
+int dbx_reset_options(void);
+/* Development hook (tools/trace_fused.py): with option FUSED_TRACE=1 the fused kernel records (probe id, clock) pairs of one
  * cluster; this copies up to max_pairs of them to host memory and returns the count. */
 int dbx_debug_trace(long long* out_host, int max_pairs);
 

@@ -40,3 +40,24 @@ def oracle():
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def dbx_opt():
+    """Setter for the library's process-wide dispatch switches (include/deepbayes_b200.h: dbx_set_option); every switch is
+    back at its default after the test.  ``dbx_opt("NO_FUSED", 1)``; value None = that option's default."""
+    from deepbayes_b200 import _lib
+    touched = {}
+
+    def set_(name, value):
+        if value is None:
+            touched.pop(name, None)
+            _lib.reset_options()
+            for k, v in touched.items():
+                _lib.set_option(k, v)
+        else:
+            touched[name] = int(value)
+            _lib.set_option(name, int(value))
+
+    yield set_
+    _lib.reset_options()

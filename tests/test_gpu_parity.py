@@ -127,9 +127,9 @@ def test_predict_fp32(ctx, golden, oracle, name):
 
 @pytest.mark.parametrize("name", cases.NAMES)
 @pytest.mark.parametrize("fused", [True, False])
-def test_predict_bf16(ctx, golden, oracle, name, fused, monkeypatch):
+def test_predict_bf16(ctx, golden, oracle, name, fused, dbx_opt):
     c, m, eng = ctx(name)
-    monkeypatch.setenv("DBX_NO_FUSED", "0" if fused else "1")
+    dbx_opt("NO_FUSED", "0" if fused else "1")
     n = c["n"]
     s1, _ = eng.predict_sums(c["x"], n, eps=c["eps_flat"], mode="bf16")
     got = (s1 / float(n)).cpu().numpy()
@@ -256,11 +256,11 @@ def test_sample_split_independence(ctx):
     np.testing.assert_array_equal(cnt, c1 + c2)
 
 
-@pytest.mark.parametrize("cm", ["1", "2", "4", "pair", "pair_qs", "pair_h1half", "pair_ffma", "pair_smem", "pair_smem_qs"])
+@pytest.mark.parametrize("cm", ["single", "pair", "pair_qs"])
 @pytest.mark.parametrize("dims,B,n", [([784, 512, 512, 10], 1000, 70), ([300, 512, 512, 16], 5000, 9), ([784, 512, 10], 700, 33), ([784, 128, 10], 300, 20),
                                        ([100, 256, 256, 7], 513, 40), ([784, 384, 384, 10], 260, 12)])
-def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n):
-    """The tcgen05 fused kernel (cluster multicast widths 1/2/4, ragged row tiles, several chunks
+def test_fused_vs_generic_device_crosscheck(oracle, dbx_opt, cm, dims, B, n):
+    """The tcgen05 fused kernels (single-CTA and CTA-pair, both work orders, ragged row tiles, several chunks
     and work segments) against the plain CUDA-core bf16 path on the same Philox draws: both round
     the GEMM operands to bf16 and accumulate in fp32, so they agree to accumulation order."""
     import deepbayes_b200 as db
@@ -274,25 +274,20 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
     mean, std = oracle.synthetic_posterior(L, seed=5, sigma_scale=0.5)
     eng.set_gaussian(mean, std)
     x = oracle.synthetic_x((B, dims[0]), seed=6)
-    monkeypatch.setenv("DBX_NO_FUSED", "1")
-    monkeypatch.setenv("DBX_NO_TC", "1")     # reference = plain CUDA-core bf16 kernels
+    dbx_opt("NO_FUSED", "1")
+    dbx_opt("NO_TC", "1")     # reference = plain CUDA-core bf16 kernels
     g1, g2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
     assert eng.last_path() == "generic"
-    monkeypatch.setenv("DBX_NO_TC", "0")
+    dbx_opt("NO_TC", "0")
     t1, t2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)   # per-layer tcgen05 GEMMs
     assert eng.last_path() == "generic_tc"   # at least the hidden layers are GEMM-eligible (widths % 8 == 0)
     np.testing.assert_allclose((t1 / n).cpu().numpy(), (g1 / n).cpu().numpy(), rtol=0, atol=1.5e-3)
-    monkeypatch.setenv("DBX_NO_FUSED", "0")
-    if cm.startswith("pair"):   # cta_group::2 kernels (the default is "pair")
-        # pair = v2 (the default: H1 packed in TMEM), pair_h1half = v2 with the second half of H1 in smem, pair_ffma = v3,
-        # pair_smem = v4 (all of H1 in smem); default work order [s][q], *_qs = [q][s]
-        monkeypatch.setenv("DBX_FUSED_KERNEL", {"pair": "2", "pair_qs": "2", "pair_h1half": "2", "pair_ffma": "3", "pair_smem": "4", "pair_smem_qs": "4"}[cm])
-        monkeypatch.setenv("DBX_FUSED_H1SMEM", "1" if cm == "pair_h1half" else "0")
-        monkeypatch.setenv("DBX_FUSED_ORDER", "0" if cm.endswith("_qs") else "1")
-    else:
-        monkeypatch.setenv("DBX_FUSED_KERNEL", "1")
-        monkeypatch.setenv("DBX_FUSED_CM", cm)
-    monkeypatch.setenv("DBX_FUSED_NS", "16")   # several chunks -> accumulate path of finish_kernel
+    dbx_opt("NO_FUSED", "0")
+    # pair = fused_mlp2_kernel (cta_group::2, the default for B > 128), work order [s][q]; pair_qs = the same kernel with the
+    # [q][s] contiguous-range order; single = fused_mlp_kernel<1> (the kernel a lone 128-row tile gets) forced on every shape
+    dbx_opt("FUSED_KERNEL", 1 if cm == "single" else 2)
+    dbx_opt("FUSED_ORDER", 0 if cm.endswith("_qs") else 1)
+    dbx_opt("FUSED_NS", "16")   # several chunks -> accumulate path of finish_kernel
     for rep in range(3):
         f1, f2 = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16", second_moment=True)
         assert eng.last_path() == "fused_tcgen05"
@@ -304,23 +299,23 @@ def test_fused_vs_generic_device_crosscheck(oracle, monkeypatch, cm, dims, B, n)
             assert bool((f1 == first).all())
     lab = np.random.Generator(np.random.Philox(1)).integers(0, dims[-1], size=B).astype(np.int32)
     cf, ff = eng.count_predicate(x, lab, n, seed=17, s0=3, mode="bf16", return_flags=True)
-    monkeypatch.setenv("DBX_NO_FUSED", "1")
+    dbx_opt("NO_FUSED", "1")
     cg, fg = eng.count_predicate(x, lab, n, seed=17, s0=3, mode="bf16", return_flags=True)
     assert (ff != fg).float().mean().item() < 5e-3
     np.testing.assert_array_equal(cf.cpu().numpy(), ff.sum(0).cpu().numpy())
 
 
-def test_fused_long_run_chunking(oracle, monkeypatch):
+def test_fused_long_run_chunking(oracle, dbx_opt):
     """Small batches with many samples run the fused kernel in launches of up to 1024 samples (instead of 256): same
     predicate counts, same sums up to the accumulation order."""
     L, eng, mean, std = _mlp_engine([784, 512, 512, 10], oracle, sigma_scale=0.3)
     B, n = 100, 2304 + 37
     x = oracle.synthetic_x((B, 784), seed=12)
     labels = np.random.Generator(np.random.Philox(8)).integers(0, 10, size=B).astype(np.int32)
-    monkeypatch.setenv("DBX_FUSED_NS", "256")
+    dbx_opt("FUSED_NS", "256")
     c0 = eng.count_predicate(x, labels, n, seed=5, mode="bf16").cpu().numpy()
     s0, q0 = eng.predict_sums(x, n, seed=5, mode="bf16", second_moment=True)
-    monkeypatch.delenv("DBX_FUSED_NS")
+    dbx_opt("FUSED_NS", None)
     c1 = eng.count_predicate(x, labels, n, seed=5, mode="bf16").cpu().numpy()
     s1, q1 = eng.predict_sums(x, n, seed=5, mode="bf16", second_moment=True)
     assert eng.last_path() == "fused_tcgen05"
@@ -331,7 +326,7 @@ def test_fused_long_run_chunking(oracle, monkeypatch):
 
 @pytest.mark.parametrize("dims,B", [([784, 1024, 1024, 10], 16), ([784, 1024, 1024, 10], 1), ([784, 512, 10], 5),
                                     ([37, 50, 10], 7), ([13, 24, 16, 3], 9), ([64, 40, 12], 2)])
-def test_stream_vs_generic_device_crosscheck(oracle, monkeypatch, dims, B):
+def test_stream_vs_generic_device_crosscheck(oracle, dbx_opt, dims, B):
     """Small-batch streaming kernel (weights read / generated once, fp32) against the generic fp32
     kernels: Philox draws, injected eps, stored samples with index list and weights, count sink."""
     import deepbayes_b200 as db
@@ -354,8 +349,8 @@ def test_stream_vs_generic_device_crosscheck(oracle, monkeypatch, dims, B):
     lab = np.random.Generator(np.random.Philox(1)).integers(0, dims[-1], size=B).astype(np.int32)
     res = {}
     for tag, env in (("generic", "1"), ("stream", "0")):
-        monkeypatch.setenv("DBX_NO_STREAM", env)
-        monkeypatch.setenv("DBX_NO_FUSED", "1")
+        dbx_opt("NO_STREAM", env)
+        dbx_opt("NO_FUSED", "1")
         r = {}
         r["philox"] = eng.predict_sums(x, n, seed=17, s0=3, mode="fp32", second_moment=True)
         assert eng.last_path() == tag
@@ -371,7 +366,7 @@ def test_stream_vs_generic_device_crosscheck(oracle, monkeypatch, dims, B):
     assert (res["stream"]["count"][1] != res["generic"]["count"][1]).float().mean().item() < 0.02
     np.testing.assert_array_equal(res["stream"]["count"][0].cpu().numpy(), res["stream"]["count"][1].sum(0).cpu().numpy())
     # bf16 mode at small B is served by the same fp32 streaming kernel
-    monkeypatch.setenv("DBX_NO_STREAM", "0")
+    dbx_opt("NO_STREAM", "0")
     b1, _ = eng.predict_sums(x, n, seed=17, s0=3, mode="bf16")
     assert eng.last_path() == "stream"
     np.testing.assert_array_equal(b1.cpu().numpy(), res["stream"]["philox"][0].cpu().numpy())
@@ -608,7 +603,7 @@ def test_ibp_matches_reference_run(oracle, golden_dir):
     np.testing.assert_allclose(hi_p, ref["ibp_mean_predict_u"], rtol=1e-5, atol=2e-6)
 
 
-def test_ibp_properties_and_bf16(oracle, monkeypatch):
+def test_ibp_properties_and_bf16(oracle, dbx_opt):
     """eps = 0 collapses the interval onto the plain forward; the bf16 tensor-core back end agrees with the
     bf16 CUDA-core back end and stays within the bf16 tolerance of fp32; stored-sample source; Massart loop."""
     dims, B, n = [784, 256, 256, 10], 200, 12
@@ -621,10 +616,10 @@ def test_ibp_properties_and_bf16(oracle, monkeypatch):
     np.testing.assert_allclose(z["lower"].cpu().numpy(), lg.cpu().numpy(), rtol=1e-4, atol=1e-3)
     eps = 0.004
     f = eng.ibp_predict(x, eps, labels, n, seed=5, mode="fp32", want=("worst", "lower", "upper", "counts"))
-    monkeypatch.setenv("DBX_NO_TC", "1")
+    dbx_opt("NO_TC", "1")
     c = eng.ibp_predict(x, eps, labels, n, seed=5, mode="bf16", want=("worst", "lower", "upper", "counts"))
     assert eng.last_path() == "generic"
-    monkeypatch.setenv("DBX_NO_TC", "0")
+    dbx_opt("NO_TC", "0")
     t = eng.ibp_predict(x, eps, labels, n, seed=5, mode="bf16", want=("worst", "lower", "upper", "counts"))
     assert eng.last_path() == "generic_tc"
     for k in ("lower", "upper"):
@@ -645,7 +640,7 @@ def test_ibp_properties_and_bf16(oracle, monkeypatch):
 
 @pytest.mark.parametrize("dims,B,n", [([784, 256, 256, 10], 200, 12), ([784, 512, 10], 128, 300), ([104, 72, 200, 136, 10], 130, 5),
                                         ([64, 1024, 10], 1, 3)])
-def test_ibp_fused_layer_is_bit_identical_to_two_gemms(oracle, monkeypatch, dims, B, n):
+def test_ibp_fused_layer_is_bit_identical_to_two_gemms(oracle, dbx_opt, dims, B, n):
     """ibp_tc_kernel (centre, radius and the interval combine of a hidden layer in one launch, |W| formed in the SM) against
     the two dense_tc launches + ibp_combine_kernel it replaces: same MMA order, same epilogue arithmetic -> same bits.
     Ragged M / N / K tails and the 256-sample chunk boundary (n = 300) included."""
@@ -653,9 +648,9 @@ def test_ibp_fused_layer_is_bit_identical_to_two_gemms(oracle, monkeypatch, dims
     x = oracle.synthetic_x((B, dims[0]), seed=16)
     labels = np.random.Generator(np.random.Philox(18)).integers(0, dims[-1], size=B).astype(np.int32)
     want = ("worst", "lower", "upper", "counts")
-    monkeypatch.setenv("DBX_NO_IBP_TC", "1")
+    dbx_opt("NO_IBP_TC", "1")
     a = eng.ibp_predict(x, 0.004, labels, n, seed=9, mode="bf16", want=want)
-    monkeypatch.setenv("DBX_NO_IBP_TC", "0")
+    dbx_opt("NO_IBP_TC", "0")
     k0 = _lib_launches()
     b = eng.ibp_predict(x, 0.004, labels, n, seed=9, mode="bf16", want=want)
     assert _lib_launches() - k0 > 0
@@ -737,7 +732,7 @@ def test_massart_with_ibp(tmp_path, oracle):
 
 
 @pytest.mark.parametrize("dims,B,S", [([784, 1024, 1024, 10], 64, 20), ([200, 512, 384, 12], 150, 9), ([784, 640, 10], 40, 7)])
-def test_stored_posterior_f32_slab_on_tensor_cores(oracle, monkeypatch, dims, B, S):
+def test_stored_posterior_f32_slab_on_tensor_cores(oracle, dbx_opt, dims, B, S):
     """Stored posteriors at B > 16 in bf16 mode: dense_tc_f32w_kernel reads the Dense kernels from the fp32 slab by TMA and
     rounds them to bf16 inside the SM.  Same arithmetic as the two-pass path (bf16 copy of the slab chunk, then
     dense_tc_kernel), so the two agree to accumulation order; both stay within the bf16 tolerance of the fp32 mode."""
@@ -751,9 +746,9 @@ def test_stored_posterior_f32_slab_on_tensor_cores(oracle, monkeypatch, dims, B,
     f1, f2 = eng.predict_stored_sums(x, 2 * S, idx=idx, wts=wts, mode="fp32", second_moment=True)
     t1, t2 = eng.predict_stored_sums(x, 2 * S, idx=idx, wts=wts, mode="bf16", second_moment=True)
     assert eng.last_path() == "generic_tc"
-    monkeypatch.setenv("DBX_NO_F32W", "1")
+    dbx_opt("NO_F32W", "1")
     c1, c2 = eng.predict_stored_sums(x, 2 * S, idx=idx, wts=wts, mode="bf16", second_moment=True)
-    monkeypatch.setenv("DBX_NO_F32W", "0")
+    dbx_opt("NO_F32W", "0")
     tot = float(wts.sum())
     np.testing.assert_allclose(t1.cpu().numpy() / tot, c1.cpu().numpy() / tot, rtol=0, atol=2e-4)
     np.testing.assert_allclose(t2.cpu().numpy() / tot, c2.cpu().numpy() / tot, rtol=0, atol=2e-4)
@@ -761,12 +756,12 @@ def test_stored_posterior_f32_slab_on_tensor_cores(oracle, monkeypatch, dims, B,
     assert (t1.argmax(1) == f1.argmax(1)).float().mean().item() > 0.97
     # contiguous rows j0.. (no index list)
     a1, _ = eng.predict_stored_sums(x, S - 2, j0=2, mode="bf16")
-    monkeypatch.setenv("DBX_NO_F32W", "1")
+    dbx_opt("NO_F32W", "1")
     b1, _ = eng.predict_stored_sums(x, S - 2, j0=2, mode="bf16")
     np.testing.assert_allclose(a1.cpu().numpy() / (S - 2), b1.cpu().numpy() / (S - 2), rtol=0, atol=2e-4)
 
 
-def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
+def test_direct_conv_on_tensor_cores(oracle, dbx_opt):
     """conv_tc_kernel (per-tap TMA boxes of the NHWC input, no im2col matrix) against the im2col + GEMM path on the same
     sampled weights, and against the fp32 mode: VALID and SAME padding, Cin = 16 / 32 / 64, ragged row groups, Cout
     that is not a multiple of 64."""
@@ -788,16 +783,16 @@ def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
     d1, d2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     assert eng.last_path() == "generic_tc"
     launches_direct = _lib_launches()
-    monkeypatch.setenv("DBX_NO_DIRECT_CONV", "1")
+    dbx_opt("NO_DIRECT_CONV", "1")
     i1, i2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     np.testing.assert_allclose(d1.cpu().numpy() / n, i1.cpu().numpy() / n, rtol=0, atol=1.5e-3)
     np.testing.assert_allclose(d2.cpu().numpy() / n, i2.cpu().numpy() / n, rtol=0, atol=1.5e-3)
     np.testing.assert_allclose(d1.cpu().numpy() / n, f1.cpu().numpy() / n, rtol=0, atol=BF16_ATOL)
     assert _lib_launches() - launches_direct > 0
     # the persistent GEMM kernel (normally only for >= 296 tiles) on every GEMM of this model
-    monkeypatch.setenv("DBX_PERSIST_MIN_TILES", "1")
+    dbx_opt("PERSIST_MIN_TILES", "1")
     p1, p2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
-    monkeypatch.setenv("DBX_NO_PERSIST", "1")
+    dbx_opt("NO_PERSIST", "1")
     q1, q2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     np.testing.assert_allclose(p1.cpu().numpy() / n, q1.cpu().numpy() / n, rtol=0, atol=2e-4)
     np.testing.assert_allclose(p2.cpu().numpy() / n, q2.cpu().numpy() / n, rtol=0, atol=2e-4)
@@ -806,7 +801,7 @@ def test_direct_conv_on_tensor_cores(oracle, monkeypatch):
 
 @pytest.mark.parametrize("shape,c1,c2,pad", [((13, 11, 3), 16, 32, "valid"), ((20, 18, 3), 32, 64, "same"), ((9, 30, 3), 16, 8, "valid"),
                                             ((32, 32, 3), 32, 64, "valid")])
-def test_conv_with_fused_maxpool_is_bit_identical(oracle, monkeypatch, shape, c1, c2, pad):
+def test_conv_with_fused_maxpool_is_bit_identical(oracle, dbx_opt, shape, c1, c2, pad):
     """conv_tc_kernel with the following 2x2 / stride-2 MaxPool done in its epilogue (staged tile in shared memory, packed
     bf16x2 max, pooled NHWC rows out) against the same kernel + maxpool_bf16_vec8_kernel: same bf16 values before the max,
     so the same bits after it.  Odd output heights / widths (the last row / column is dropped), SAME padding, Cout = 8 .. 64."""
@@ -819,13 +814,13 @@ def test_conv_with_fused_maxpool_is_bit_identical(oracle, monkeypatch, shape, c1
     eng.set_gaussian((g.standard_normal(eng.P) * 0.08).astype(np.float32), np.full(eng.P, 0.01, np.float32))
     B, n = 19, 30
     x = oracle.synthetic_x((B,) + shape, seed=4)
-    monkeypatch.setenv("DBX_NO_POOL_FUSE", "1")
+    dbx_opt("NO_POOL_FUSE", "1")
     a1, a2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     k0 = _lib_launches()
-    monkeypatch.setenv("DBX_NO_POOL_FUSE", "0")
+    dbx_opt("NO_POOL_FUSE", "0")
     b1, b2 = eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     k1 = _lib_launches()
-    monkeypatch.setenv("DBX_NO_POOL_FUSE", "1")
+    dbx_opt("NO_POOL_FUSE", "1")
     eng.predict_sums(x, n, seed=9, mode="bf16", second_moment=True)
     k2 = _lib_launches()
     assert k1 - k0 < k2 - k1          # the pooling launches are gone
@@ -836,17 +831,17 @@ def test_conv_with_fused_maxpool_is_bit_identical(oracle, monkeypatch, shape, c1
 
 
 @pytest.mark.parametrize("dims,B,n", [([784, 1024, 1024, 10], 600, 40), ([512, 640, 10], 300, 70), ([256, 1000, 328, 10], 257, 90)])
-def test_pair_gemm_is_bit_identical_to_single_cta_gemm(oracle, monkeypatch, dims, B, n):
+def test_pair_gemm_is_bit_identical_to_single_cta_gemm(oracle, dbx_opt, dims, B, n):
     """dense_tc_pair_kernel (cta_group::2, 256 x 256 tiles, each CTA staging half of the weight block) against the single-CTA
     tensor-core GEMMs on the same sampled weights: same products in the same k order -> same bits.  Ragged row / column
     tiles (600 = 2 x 256 + 88 rows, 640 = 2.5 x 256 columns, 1000 and 328 columns) included."""
     L, eng, mean, std = _mlp_engine(dims, oracle, sigma_scale=0.3)
     x = oracle.synthetic_x((B, dims[0]), seed=21)
-    monkeypatch.setenv("DBX_NO_FUSED", "1")
-    monkeypatch.setenv("DBX_NO_PAIR_GEMM", "1")
+    dbx_opt("NO_FUSED", "1")
+    dbx_opt("NO_PAIR_GEMM", "1")
     a1, a2 = eng.predict_sums(x, n, seed=3, mode="bf16", second_moment=True)
     assert eng.last_path() == "generic_tc"
-    monkeypatch.setenv("DBX_NO_PAIR_GEMM", "0")
+    dbx_opt("NO_PAIR_GEMM", "0")
     b1, b2 = eng.predict_sums(x, n, seed=3, mode="bf16", second_moment=True)
     np.testing.assert_array_equal(a1.cpu().numpy(), b1.cpu().numpy())
     np.testing.assert_array_equal(a2.cpu().numpy(), b2.cpu().numpy())

@@ -1,3 +1,6 @@
+// NOT BUILT.  Round-1 experiment kept for the record (measured negative result): CTA-pair fused
+// MLP kernel with all of H1 in SHARED memory and N=256 SS layer-2 MMAs -- 17 % slower than fused_mlp2_kernel.  It was
+// #included by deepbayes_b200/csrc/fused_mlp.cu until round 2; finish4_kernel now lives in that file.
 // CTA-pair kernel, version 4 (included by fused_mlp.cu): 784-H-H-C MLPs with H = 512.
 //
 // What limited version 2 (profiles/r1_timeline_pair_kernel.log): the hidden activations H1 were
@@ -24,7 +27,7 @@
 //      from HBM once and then served by L2 to the other tile groups.  The running sums live in
 //      a per-(cluster, q) slice of `partial` (read-modify-write by the owning thread, L2
 //      resident); finish4_kernel adds the slices in cluster order -- still no float atomics.
-#pragma once
+#if 0
 
 constexpr int k4Stages = 5;
 constexpr int k4StageBytes = 16384;   // X block 8 KB + this CTA's half of the weight block 8 KB
@@ -496,3 +499,5 @@ __global__ void finish4_kernel(const float* __restrict__ partial, const unsigned
     if (sum2) sum2[o] = a2;
   }
 }
+
+#endif

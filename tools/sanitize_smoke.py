@@ -19,15 +19,15 @@ def mlp(dims):
 for dims, B, n in (([784, 512, 512, 10], 300, 5), ([784, 256, 10], 130, 3), ([784, 384, 384, 10], 260, 3)):
     eng = mlp(dims)
     x = o.synthetic_x((B, dims[0]), seed=6)
-    for kern in ("1", "2", "3"):
-        os.environ["DBX_FUSED_KERNEL"] = kern
+    for kern in (1, 2):
+        db._lib.set_option("FUSED_KERNEL", kern)
         s1, s2 = eng.predict_sums(x, n, seed=1, mode="bf16", second_moment=True)
         print(dims, "kernel", kern, eng.last_path(), float(s1.sum()))
-    os.environ.pop("DBX_FUSED_KERNEL")
-    os.environ["DBX_NO_FUSED"] = "1"
+    db._lib.set_option("FUSED_KERNEL", 0)
+    db._lib.set_option("NO_FUSED", 1)
     s1, _ = eng.predict_sums(x, n, seed=1, mode="bf16"); print("generic_tc", eng.last_path(), float(s1.sum()))
     s1, _ = eng.predict_sums(x, n, seed=1, mode="fp32"); print("generic fp32", eng.last_path(), float(s1.sum()))
-    os.environ["DBX_NO_FUSED"] = "0"
+    db._lib.set_option("NO_FUSED", 0)
     s1, _ = eng.predict_sums(x[:7], n, seed=1, mode="bf16"); print("stream", eng.last_path(), float(s1.sum()))
     lab = np.zeros(B, np.int32)
     c = eng.count_predicate(x, lab, n, seed=1, mode="bf16"); print("count", eng.last_path(), int(c.sum()))
