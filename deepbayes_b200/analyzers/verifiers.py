@@ -2,8 +2,9 @@
 (:517-653): Chernoff / Okamoto sample bound, Massart sequential halting, Clopper-Pearson
 interval, and the per-sample "forward on perturbed inputs -> predicate -> count" evaluated
 for ALL samples in one device call (dbx_count_predicate) instead of one Python iteration per
-posterior sample.  The IBP worst-case evaluation (verify=True, :593-619) and the FGSM inner
-attack (:622-625) are SURVEY.md 8(f) ranks 1 and 3: callers pass the perturbed inputs.
+posterior sample.  The IBP worst-case evaluation (verify=True, :593-619: `dbx_ibp_predict` / `dbx_ibp_samples`) and the FGSM
+inner attack (:622-625: `dbx_count_predicate_fgsm` / `dbx_fgsm_samples`) run on the device too; interval bounds default to
+fp32 arithmetic (bf16 is opt-in and not sound).
 """
 from __future__ import annotations
 
@@ -46,8 +47,9 @@ def chernoff_sample_bound(confidence=0.95, delta=0.3):
 
 
 def _mode_of(model, override=None):
-    """Arithmetic mode of the device path: PosteriorModel.mode / Optimizer.compute_mode (an optimizer's own
-    `.mode` is the reference's "classification" / "regression" switch, optimizer.py:60)."""
+    """Arithmetic mode of the device FORWARD path: PosteriorModel.mode / Optimizer.compute_mode (an optimizer's own
+    `.mode` is the reference's "classification" / "regression" switch, optimizer.py:60).  Interval bounds do not use this:
+    they default to fp32 (see chernoff_bound_verification / massart_bound_check)."""
     for m in (override, getattr(model, "compute_mode", None), getattr(model, "mode", None)):
         if m in ("bf16", "fp32"):
             return m
@@ -127,12 +129,13 @@ def chernoff_bound_verification(model, inp, eps, cls, **kwargs):
     samples; for each, IBP logits of the eps-ball, worst case w.r.t. ``cls`` (lower bound of the true class, upper
     bound of the others), the last layer's activation; returns the SUM over samples, like the reference (:556-557).
     ``inp`` may hold several rows, with one class per row (the reference takes one input).  All n samples run in one
-    device call; kwarg mode="fp32"|"bf16" (default: the model's)."""
+    device call.  The interval arithmetic runs in fp32 by default (the reference uses float64, verifiers.py:26-33);
+    mode="bf16" (tensor cores) is opt-in and NOT a sound bound: its operands are rounded to bf16, to nearest."""
     delta = kwargs.get('delta', 0.3)
     confidence = kwargs.get('confidence', 0.95)
     eng = _engine_of(model)
     n = chernoff_sample_bound(confidence, delta)
-    mode = _mode_of(model, kwargs.get('mode'))
+    mode = kwargs.get('mode') or "fp32"
     a = np.asarray(inp, np.float32)
     x2 = a.reshape(-1, eng.K)
     labels = np.broadcast_to(np.asarray(cls, np.int32).reshape(-1), (x2.shape[0],))
@@ -151,70 +154,130 @@ def chernoff_bound_verification(model, inp, eps, cls, **kwargs):
     return worst.cpu().numpy().reshape(a.shape[:-1] + (eng.C,))
 
 
-def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
-    """verifiers.py:563-653: each iteration draws one posterior sample, evaluates the worst case and applies the
-    predicate; the loop stops at the Massart halting bound (or the Chernoff bound).  The device evaluates the 0/1
-    outcomes for whole blocks of samples at once and the halting rule walks them in order, so the result equals the
-    sequential loop on the same sample sequence.
+def _softmax_rows(z):
+    z = np.asarray(z, np.float64)
+    e = np.exp(z - z.max(axis=-1, keepdims=True))
+    return e / e.sum(axis=-1, keepdims=True)
 
-    verify=True, classification=True (:588-603): the worst case comes from IBP over the eps-ball (`dbx_ibp_predict`).
-    verify=False (:622-625): every posterior sample gets its own FGSM step against that sample's weights, then the sample
-    is evaluated at the adversarial input (`dbx_count_predicate_fgsm`; attack direction = argmax of model.predict(inp), as
-    FGSM's default direction=-1).  For a PosteriorModel the reference's FGSM differentiates through the 35 fresh samples of
-    predict() instead of the iteration's own weights; the per-sample form used here is what it does for an optimizer object.
-    Passing ``adv=`` (a pre-perturbed input) skips the attack.  In all cases the predicate is ``argmax == cls`` (``cls=`` kwarg; the tutorials'
-    predicate).  Returns (successes/iterations, iterations, mean/iterations) like :653 (mean is zero unless chernoff
-    override, as in the reference)."""
+
+def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
+    """verifiers.py:563-653, same signature and defaults (``verify=True``, ``classification=False``, ``chernoff=False``):
+    every iteration draws one posterior sample, builds its ``worst_case`` and calls ``predicate(worst_case)``; the loop stops
+    at the Massart halting bound (or, with chernoff=True, after the Chernoff bound).  Here the device evaluates whole BLOCKS
+    of posterior samples per call and hands back every sample's own output (`dbx_ibp_samples`, `dbx_fgsm_samples`,
+    `dbx_predict_samples`); the predicate and the halting rule then walk the block in sample order, so the result equals the
+    sequential loop on the same sample sequence (samples past the halting point are discarded).
+
+    worst_case per branch, as in the reference:
+      verify and classification (:593-608)  softmax of (upper logit bound everywhere, lower bound at ``cls``), one-hot depth 10
+                                            (depth 2 when that does not broadcast), shape like the model output
+      verify and not classification (:609-619)  IBP(..., predict=True) on the UN-clipped box, last activation applied to the
+                                            bounds; per output the bound that lies farther from ``cls``
+      not verify (:621-625)                 model._predict(FGSM(model, inp, loss, eps, samples=1)): each posterior sample
+                                            attacked with its own gradient (for a PosteriorModel the reference's FGSM
+                                            differentiates through 35 fresh samples of predict(); the per-sample form is what
+                                            it does for an optimizer object); ``adv=`` (not in the reference) skips the attack
+    ``predicate=None`` (not in the reference) selects the device predicate ``argmax == cls`` (the tutorials' predicate)
+    without materialising the per-sample outputs.  chernoff=True also returns the mean of model._predict(glob_adv) over the
+    iterations, glob_adv = FGSM(..., samples=35) (:585, :647-648).  Returns (successes/iterations, iterations,
+    mean/iterations)."""
     delta = kwargs.get('delta', 0.3)
     alpha = kwargs.get('alpha', 0.05)
     confidence = kwargs.get('confidence', 0.95)
-    verify = kwargs.get('verify', False)
+    verify = kwargs.get('verify', True)                       # :568
+    classification = kwargs.get('classification', False)      # :569
+    chernoff_override = kwargs.get('chernoff', False)         # :576
     cls = kwargs.get('cls', None)
     adv = kwargs.get('adv', None)
+    loss_fn = kwargs.get('loss_fn', None)
     block = int(kwargs.get('block', 4096))
-    if verify and not kwargs.get('classification', False):
-        raise NotImplementedError("verify=True for regression (verifiers.py:605-620, IBP predict=True) is not built")
-    if cls is None:
-        raise ValueError("pass cls=<true class>: the device predicate is argmax == cls")
+    if predicate is None and cls is None:
+        raise ValueError("pass a predicate (verifiers.py:563) or cls=<true class> for the device predicate argmax == cls")
+    if verify and cls is None:
+        raise ValueError("verify=True needs cls= (verifiers.py:596-603 / :607-608 build the worst case around it)")
     eng = _engine_of(model)
-    mode = _mode_of(model, kwargs.get('mode'))
+    # bounds are computed in fp32 unless the caller opts into bf16 (narrower arithmetic than the reference's float64: not sound)
+    mode = kwargs.get('mode') or ("fp32" if verify else _mode_of(model))
+    a = np.asarray(inp, np.float32)
+    x1 = a.reshape(1, -1)
+    _, oshape = eng.model.rows_and_outshape(a)
+    C = eng.C
     epsilon = 1 - confidence
     chernoff_bound = math.ceil((1 / (2 * epsilon ** 2)) * math.log(2 / delta))
     successes, iterations = 0.0, 0.0
     halting_bound = chernoff_bound
-    flags = np.zeros(0, np.uint8)
-    pos = 0
-    done = False
+    mean = 0.0 * np.asarray(model.predict(inp))               # :583 (consumes posterior samples like the reference)
+    glob_adv = None
+    if chernoff_override:                                     # :584-585
+        from . import attacks
+        glob_adv = attacks.FGSM(model, inp, loss_fn, eps, samples=35)
     direc = None
+    fast = predicate is None and (classification or not verify)
+    done = False
     while not done:
         nb = int(min(block, chernoff_bound + 1 - iterations))
         s0 = model._take_ids(nb)
-        if verify:
-            fl = eng.ibp_predict(np.asarray(inp).reshape(1, -1), eps, [int(cls)], nb, model.seed, s0, None, 1.0, mode,
-                                 want=(), return_flags=True)["flags"]
-        elif adv is None:
-            if direc is None:
-                direc = int(np.argmax(np.asarray(model.predict(inp)).reshape(-1)))
-            _, fl = eng.count_predicate_fgsm(np.asarray(inp).reshape(1, -1), [direc], [int(cls)], eps, nb, model.seed, s0,
-                                             lower=getattr(model, "input_lower", -np.inf), upper=getattr(model, "input_upper", np.inf),
-                                             return_flags=True)
+        outcomes = None
+        if verify and classification:
+            if fast:
+                outcomes = eng.ibp_predict(x1, eps, [int(cls)], nb, model.seed, s0, None, 1.0, mode, want=(),
+                                           return_flags=True)["flags"].cpu().numpy().reshape(-1)
+            else:
+                lo, hi = eng.ibp_samples(x1, eps, nb, model.seed, s0, mode=mode)
+                lo, hi = lo.cpu().numpy().reshape(nb, C), hi.cpu().numpy().reshape(nb, C)
+                depth = 10 if C == 10 else 2                   # :596-603 (one_hot depth 10, else the depth-2 retry)
+                if depth != C:
+                    raise ValueError("verifiers.py:596-603 builds its one-hot with depth 10 or 2; the model has %d outputs" % C)
+                v1 = np.zeros(C, np.float32); v1[int(cls)] = 1.0
+                worst = _softmax_rows((1.0 - v1) * hi + v1 * lo).astype(np.float32)
+        elif verify:
+            e = np.float32(eps)
+            lo, hi = eng.ibp_samples(x1 - e, 0.0, nb, model.seed, s0, mode=mode, clip=False, box_hi=x1 + e)
+            from ..engine import device_activation
+            name = [l for l in eng.model.layers if l.kind in ("dense", "conv2d")][-1].activation.name
+            lo = device_activation(name, lo.cpu().numpy().reshape(nb, C)); hi = device_activation(name, hi.cpu().numpy().reshape(nb, C))
+            target = np.asarray(cls, np.float32)
+            above, below = np.abs(hi - target), np.abs(lo - target)
+            worst = np.where(above > below, hi, lo)            # :610-618
+        elif adv is not None:
+            if fast:
+                _, fl = eng.count_predicate(np.asarray(adv).reshape(1, -1), [int(cls)], nb, model.seed, s0, None, 1.0, mode, True)
+                outcomes = fl.cpu().numpy().reshape(-1)
+            else:
+                worst = eng.predict_samples(np.asarray(adv).reshape(1, -1), nb, model.seed, s0, mode=mode).cpu().numpy().reshape(nb, C)
         else:
-            _, fl = eng.count_predicate(np.asarray(adv).reshape(1, -1), [int(cls)], nb, model.seed, s0, None, 1.0, mode, True)
-        flags = fl.cpu().numpy().reshape(-1)
+            if direc is None:                                  # FGSM's default direction=-1: the model's own prediction
+                direc = int(np.argmax(np.asarray(model.predict(inp)).reshape(-1)))
+            lower, upper = getattr(model, "input_lower", -np.inf), getattr(model, "input_upper", np.inf)
+            if fast:
+                _, fl = eng.count_predicate_fgsm(x1, [direc], [int(cls)], eps, nb, model.seed, s0, lower=lower, upper=upper,
+                                                 return_flags=True)
+                outcomes = fl.cpu().numpy().reshape(-1)
+            else:
+                worst = eng.fgsm_samples(x1, [direc], eps, nb, model.seed, s0, lower=lower, upper=upper).cpu().numpy().reshape(nb, C)
+        gl = None
+        if chernoff_override:                                  # model._predict(glob_adv) under the same posterior samples (:648)
+            gl = eng.predict_samples(np.asarray(glob_adv, np.float32).reshape(1, -1), nb, model.seed, s0,
+                                     mode=_mode_of(model, kwargs.get('mode'))).cpu().numpy().reshape(nb, C)
         pos = 0
-        while pos < len(flags):
+        while pos < nb:
             if not (iterations <= halting_bound):
                 done = True
                 break
-            successes += float(flags[pos])
+            if outcomes is not None:
+                result = float(outcomes[pos])
+            else:
+                result = 1.0 if predicate(worst[pos].reshape(oshape)) else 0.0    # :628
+            successes += result
             iterations += 1
-            pos += 1
             lb, ub = proportion_confint_beta(successes, iterations)
             lb = 0.0 if math.isnan(lb) else lb
             ub = 1.0 if math.isnan(ub) else ub
             hb = absolute_massart_halting(successes, iterations, [lb, ub], epsilon, delta, alpha)
-            halting_bound = chernoff_bound if hb == -1 else min(hb, chernoff_bound)
+            halting_bound = chernoff_bound if (hb == -1 or chernoff_override) else min(hb, chernoff_bound)   # :643-646
+            if chernoff_override:
+                mean = mean + gl[pos].reshape(oshape)          # :647-648
+            pos += 1
         if not (iterations <= halting_bound):
             done = True
-    mean = 0.0 * np.asarray(model.predict(inp)) if hasattr(model, "predict") else 0.0
     return successes / iterations, iterations, mean / iterations

@@ -204,7 +204,7 @@ __global__ void fgsm_adv_kernel(const float* __restrict__ x, float* __restrict__
 // sample's weights, then the predicate argmax == label on the sample's output at the adversarial input.
 static int run_count_fgsm(dbx_model* m, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, const int32_t* labels_dev,
                           float eps, float lower, float upper, int64_t n, const Source& src0, int accumulate, uint8_t* flags_dev,
-                          unsigned long long* counts_dev, cudaStream_t st) {
+                          unsigned long long* counts_dev, cudaStream_t st, float* probs_out = nullptr) {
   DBX_CHECK(m->is_mlp, "the device FGSM loop covers Dense MLPs");
   DBX_CHECK(m->layers[m->last_weighted].act == DBX_ACT_SOFTMAX, "the device FGSM loop needs a softmax output");
   std::vector<const Layer*> dl;
@@ -227,7 +227,7 @@ static int run_count_fgsm(dbx_model* m, const float* x_dev, int64_t B, const int
   float* dz[2];
   dz[0] = (float*)p; p += (size_t)ns * dzb; dz[1] = (float*)p; p += (size_t)ns * dzb;
   float* Wc = (float*)p;
-  if (!accumulate) DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, counts_dev, B);
+  if (!accumulate && counts_dev) DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, counts_dev, B);
 
   for (int64_t c0 = 0; c0 < n; c0 += ns) {
     const int nc = (int)std::min<int64_t>(ns, n - c0);
@@ -264,8 +264,14 @@ static int run_count_fgsm(dbx_model* m, const float* x_dev, int64_t B, const int
     }
     DBX_LAUNCH(fgsm_adv_kernel, grid_for((int64_t)nc * B * K0), 256, 0, st, x_dev, dz[zi], nc, B * K0, eps, lower, upper);
     if (forward(dz[zi], B * K0)) return 1;
-    DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, (const float*)acts[nl - 1], nc, B, (int)C, labels_dev,
-               flags_dev ? flags_dev + c0 * B : nullptr, counts_dev);
+    if (counts_dev)
+      DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, (const float*)acts[nl - 1], nc, B, (int)C, labels_dev,
+                 flags_dev ? flags_dev + c0 * B : nullptr, counts_dev);
+    if (probs_out) {   // every sample's own output at its adversarial input (model._predict(adv), verifiers.py:624-625)
+      float* dst = probs_out + c0 * B * C;
+      DBX_CUDA(cudaMemcpyAsync(dst, acts[nl - 1], (size_t)nc * B * C * 4, cudaMemcpyDeviceToDevice, st));
+      DBX_LAUNCH(act_rows_kernel, grid_for((int64_t)nc * B), 256, 0, st, (int)DBX_ACT_SOFTMAX, dst, (int64_t)nc * B, C);
+    }
   }
   return 0;
 }

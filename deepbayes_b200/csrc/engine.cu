@@ -858,6 +858,11 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
       const int overwrite = (c0 == 0 && !sink.accumulate) ? 1 : 0;
       launch_accum(logits, nc, B, (int)C, act_last, sink.out_kind, sink.wts ? sink.wts + c0 : nullptr, overwrite, sink.sum1, sink.sum2, st);
       DBX_CUDA(cudaGetLastError());
+    } else if (sink.kind == 2) {   // every sample's own output (what the reference's loops look at one sample at a time)
+      float* dst = sink.sum1 + c0 * B * C;
+      DBX_CUDA(cudaMemcpyAsync(dst, logits, (size_t)nc * B * C * 4, cudaMemcpyDeviceToDevice, st));
+      if (sink.out_kind == DBX_OUT_PROBS && act_last != DBX_ACT_LINEAR)
+        DBX_LAUNCH(act_rows_kernel, grid_for((int64_t)nc * B), 256, 0, st, act_last, dst, (int64_t)nc * B, C);
     } else {
       DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, logits, nc, B, (int)C, sink.labels,
                  sink.flags ? sink.flags + c0 * B : nullptr, sink.counts);
@@ -880,6 +885,12 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
   DBX_CUDA(cudaSetDevice(m->device));
   g_last_path = 0; g_used_tc = false;
   DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
+  if (sink.kind == 2) {
+    if (mode == DBX_MODE_FP32) return run_generic<float>(m, x_dev, B, n, src, sink, st);
+    const int rg2 = run_generic<__nv_bfloat16>(m, x_dev, B, n, src, sink, st);
+    if (g_used_tc) g_last_path = 3;
+    return rg2;
+  }
   if (!(mode == DBX_MODE_BF16 && src.stored && B > 8 && f32w_model_ok(m))) {
     const int r = stream_mlp_run(m, x_dev, B, n, src, sink, st);
     if (r < 0) return 1;
@@ -1071,6 +1082,7 @@ int dbx_destroy(dbx_handle h) {
   fused_mlp_free(h);
   cudaFree(h->mu); cudaFree(h->sigma); cudaFree(h->ws.ptr); cudaFree(h->fused_ws.ptr);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  for (int i = 0; i < 2; ++i) { if (h->up_stage[i]) cudaFreeHost(h->up_stage[i]); if (h->up_ev[i]) cudaEventDestroy(h->up_ev[i]); }
   cudaFree(h->d_x); cudaFree(h->d_s1); cudaFree(h->d_s2);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_posterior) cudaEventDestroy(h->ev_posterior);
@@ -1299,6 +1311,41 @@ int dbx_ibp_predict(dbx_handle h, const float* x_dev, int64_t B, float eps, int3
   return rc;
 }
 
+int dbx_predict_samples(dbx_handle h, const float* x_dev, int64_t B, int64_t n, uint64_t seed, int64_t s0, const float* eps_dev,
+                        float inflate, int32_t mode, int32_t out_kind, float* out_dev, void* stream) {
+  DBX_CHECK(h && x_dev && out_dev, "null argument");
+  Source src; src.eps = eps_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  Sink sink; sink.kind = 2; sink.out_kind = out_kind; sink.sum1 = out_dev;
+  return run(h, x_dev, B, n, src, sink, mode, (cudaStream_t)stream);
+}
+
+int dbx_fgsm_samples(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, float eps, float lower, float upper,
+                     int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate, float* probs_dev, void* stream) {
+  DBX_CHECK(h && x_dev && attack_labels_dev && probs_dev, "null argument");
+  DBX_CHECK(B > 0 && n > 0 && eps >= 0.f, "B, n must be positive and eps >= 0");
+  DBX_CHECK(h->have_gaussian, "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  Source src; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  return run_count_fgsm(h, x_dev, B, attack_labels_dev, nullptr, eps, lower, upper, n, src, 1, nullptr, nullptr, (cudaStream_t)stream,
+                        probs_dev);
+}
+
+int dbx_ibp_samples(dbx_handle h, const float* x_dev, const float* box_hi_dev, int64_t B, float eps, int32_t clip01, int64_t n,
+                    uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t mode, float* lower_dev, float* upper_dev,
+                    void* stream) {
+  DBX_CHECK(h && x_dev && lower_dev && upper_dev, "null argument");
+  DBX_CHECK(B > 0 && n > 0 && eps >= 0.f, "B, n must be positive and eps >= 0");
+  DBX_CHECK(h->have_gaussian, "no Gaussian posterior set (dbx_set_gaussian)");
+  DBX_CUDA(cudaSetDevice(h->device));
+  Source src; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  IbpSink sink; sink.per_lower = lower_dev; sink.per_upper = upper_dev;
+  g_last_path = 0; g_used_tc = false;
+  int rc;
+  if (mode == DBX_MODE_BF16) { rc = run_ibp<__nv_bfloat16>(h, x_dev, B, eps, clip01, n, src, sink, (cudaStream_t)stream, box_hi_dev); if (g_used_tc) g_last_path = 3; }
+  else { DBX_CHECK(mode == DBX_MODE_FP32, "unknown mode %d", mode); rc = run_ibp<float>(h, x_dev, B, eps, clip01, n, src, sink, (cudaStream_t)stream, box_hi_dev); }
+  return rc;
+}
+
 int dbx_ibp_one(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const float* W_dev, int32_t mode,
                 float* lower_dev, float* upper_dev, void* stream) {
   DBX_CHECK(h && x_dev && W_dev && lower_dev && upper_dev, "null argument");
@@ -1325,6 +1372,43 @@ int dbx_ibp_state(dbx_handle h, const float* lo_dev, const float* hi_dev, int64_
   return rc;
 }
 
+static bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+constexpr size_t kUpPiece = 4u << 20;
+
+int dbx_upload_f32(dbx_handle h, const float* src_host, float* dst_dev, int64_t count, void* stream) {
+  DBX_CHECK(h && src_host && dst_dev && count >= 0, "dbx_upload_f32: bad argument");
+  DBX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)count * 4;
+  if (bytes == 0) return 0;
+  if (host_ptr_is_pinned(src_host)) {   // page-locked by the caller: one DMA, nothing staged; the caller keeps it alive until the stream has passed
+    DBX_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (!h->up_stage[i]) {
+      DBX_CUDA(cudaMallocHost(&h->up_stage[i], kUpPiece));
+      DBX_CUDA(cudaEventCreateWithFlags(&h->up_ev[i], cudaEventDisableTiming));
+      DBX_CUDA(cudaEventRecord(h->up_ev[i], st));
+    }
+  // pageable memory: pieces of 4 MB through two pinned buffers, the host memcpy of piece i+1 under the DMA of piece i; a
+  // buffer is rewritten only after the event of its previous copy has completed
+  for (size_t off = 0; off < bytes; off += kUpPiece) {
+    const int b = h->up_next; h->up_next ^= 1;
+    const size_t nb = std::min(kUpPiece, bytes - off);
+    DBX_CUDA(cudaEventSynchronize(h->up_ev[b]));
+    memcpy(h->up_stage[b], (const char*)src_host + off, nb);
+    DBX_CUDA(cudaMemcpyAsync((char*)dst_dev + off, h->up_stage[b], nb, cudaMemcpyHostToDevice, st));
+    DBX_CUDA(cudaEventRecord(h->up_ev[b], st));
+  }
+  return 0;
+}
+
 int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, uint64_t seed, int64_t s0, float inflate,
                      int32_t mode, int32_t out_kind, float* mean_host, float* var_host) {
   DBX_CHECK(h && x_host && mean_host, "null argument");
@@ -1332,11 +1416,11 @@ int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, ui
   if (!h->own_stream) DBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   cudaStream_t st = h->own_stream;
   const size_t xb = (size_t)B * h->in_feat * 4, ob = (size_t)B * h->out_feat * 4;
-  if (h->h_pin_bytes < xb + 2 * ob) {
+  if (h->h_pin_bytes < 2 * ob) {
     if (h->h_pin) DBX_CUDA(cudaFreeHost(h->h_pin));
     h->h_pin = nullptr; h->h_pin_bytes = 0;
-    DBX_CUDA(cudaMallocHost(&h->h_pin, xb + 2 * ob));
-    h->h_pin_bytes = xb + 2 * ob;
+    DBX_CUDA(cudaMallocHost(&h->h_pin, 2 * ob));
+    h->h_pin_bytes = 2 * ob;
   }
   if (h->d_x_bytes < xb) {
     cudaFree(h->d_x); h->d_x = nullptr; h->d_x_bytes = 0;
@@ -1346,19 +1430,21 @@ int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, ui
     cudaFree(h->d_s1); cudaFree(h->d_s2); h->d_s1 = h->d_s2 = nullptr; h->d_s_bytes = 0;
     DBX_CUDA(cudaMalloc(&h->d_s1, ob)); DBX_CUDA(cudaMalloc(&h->d_s2, ob)); h->d_s_bytes = ob;
   }
-  memcpy(h->h_pin, x_host, xb);
-  DBX_CUDA(cudaMemcpyAsync(h->d_x, h->h_pin, xb, cudaMemcpyHostToDevice, st));
+  if (dbx_upload_f32(h, x_host, h->d_x, B * h->in_feat, st)) return 1;
   if (dbx_predict(h, h->d_x, B, n, seed, s0, nullptr, inflate, mode, out_kind, 0, h->d_s1, var_host ? h->d_s2 : nullptr, st))
     return 1;
   DBX_LAUNCH(finalize_kernel, grid_for(B * h->out_feat), 256, 0, st, h->d_s1, var_host ? h->d_s2 : nullptr,
              1.0f / (float)n, B * h->out_feat, h->d_s1, var_host ? h->d_s2 : nullptr);
-  float* om = (float*)((char*)h->h_pin + xb);
-  float* ov = (float*)((char*)h->h_pin + xb + ob);
+  const bool direct = host_ptr_is_pinned(mean_host) && (!var_host || host_ptr_is_pinned(var_host));
+  float* om = direct ? mean_host : (float*)h->h_pin;
+  float* ov = direct ? var_host : (float*)((char*)h->h_pin + ob);
   DBX_CUDA(cudaMemcpyAsync(om, h->d_s1, ob, cudaMemcpyDeviceToHost, st));
   if (var_host) DBX_CUDA(cudaMemcpyAsync(ov, h->d_s2, ob, cudaMemcpyDeviceToHost, st));
   DBX_CUDA(cudaStreamSynchronize(st));
-  memcpy(mean_host, om, ob);
-  if (var_host) memcpy(var_host, ov, ob);
+  if (!direct) {
+    memcpy(mean_host, om, ob);
+    if (var_host) memcpy(var_host, ov, ob);
+  }
   return 0;
 }
 

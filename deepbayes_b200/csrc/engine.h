@@ -75,6 +75,8 @@ struct dbx_model {
   float* d_x = nullptr; size_t d_x_bytes = 0;
   float* d_s1 = nullptr; float* d_s2 = nullptr; size_t d_s_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  // pageable host -> device uploads: two pinned staging pieces, each guarded by the event of its last copy (dbx_upload_f32)
+  void* up_stage[2] = {nullptr, nullptr}; cudaEvent_t up_ev[2] = {nullptr, nullptr}; int up_next = 0;
   void* fused_state = nullptr;  // owned by fused_mlp.cu
   cudaStream_t ibp_side = nullptr;  // interval forward: weights of chunk c+1 are drawn here while chunk c is in the GEMMs
   cudaStream_t ibp_main = nullptr;  // ... and the GEMM chain here (high priority)
@@ -94,7 +96,7 @@ struct Source {
 
 // What happens to each sample's output.
 struct Sink {
-  int kind = 0;  // 0 accumulate moments, 1 count predicate
+  int kind = 0;  // 0 accumulate moments, 1 count predicate, 2 per-sample outputs [n,B,C] into `sum1` (generic executor only)
   int out_kind = 0; int accumulate = 0;
   float* sum1 = nullptr; float* sum2 = nullptr; const float* wts = nullptr;
   const int32_t* labels = nullptr; uint8_t* flags = nullptr; unsigned long long* counts = nullptr;

@@ -235,6 +235,7 @@ struct IbpSink {
   const int32_t* labels = nullptr;
   float* sum_worst = nullptr; float* sum_lower = nullptr; float* sum_upper = nullptr;   // [B,C] each, optional
   unsigned long long* counts = nullptr; uint8_t* flags = nullptr;                        // optional
+  float* per_lower = nullptr; float* per_upper = nullptr;                                // [n,B,C] each: every sample's own logit bounds, optional
   int accumulate = 0;
 };
 
@@ -458,6 +459,8 @@ static int run_ibp(dbx_model* m, const float* x_dev, int64_t B, float eps, int c
       launch_accum(lower, nc, B, (int)C, act_last, DBX_OUT_LOGITS, nullptr, overwrite, sink.sum_lower, nullptr, st);
     if (sink.sum_upper)
       launch_accum(upper, nc, B, (int)C, act_last, DBX_OUT_LOGITS, nullptr, overwrite, sink.sum_upper, nullptr, st);
+    if (sink.per_lower) DBX_CUDA(cudaMemcpyAsync(sink.per_lower + c0 * out_ss, lower, (size_t)nc * out_ss * 4, cudaMemcpyDeviceToDevice, st));
+    if (sink.per_upper) DBX_CUDA(cudaMemcpyAsync(sink.per_upper + c0 * out_ss, upper, (size_t)nc * out_ss * 4, cudaMemcpyDeviceToDevice, st));
     if (sink.counts)
       DBX_LAUNCH(count_kernel, grid_for((int64_t)nc * B), 256, 0, st, worst, nc, B, (int)C, sink.labels,
                  sink.flags ? sink.flags + c0 * B : nullptr, sink.counts);

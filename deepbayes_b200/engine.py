@@ -91,7 +91,7 @@ class Engine:
         _lib.check(self.lib.dbx_input_dim(h, C.byref(v))); self.K = v.value
         _lib.check(self.lib.dbx_flops_per_forward(h, C.byref(v))); self.flops_per_forward = v.value
         self._slab = None
-        self._pin = None
+        self._keep = None
 
     def __del__(self):
         try:
@@ -103,18 +103,20 @@ class Engine:
 
     # ---- helpers ----------------------------------------------------------------------
     def _dev_f32(self, a):
+        """fp32 device tensor of `a`.  Host arrays go through dbx_upload_f32: one DMA when the array is page-locked (e.g. the
+        .numpy() view of a pinned torch tensor), otherwise pieces through the handle's pinned staging ring, each piece
+        guarded by the event of its previous copy -- back-to-back uploads never overwrite data still in flight."""
         torch = self.torch
         if isinstance(a, torch.Tensor):
-            return a.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()   # async when the source is pinned
+            if a.is_cuda:
+                return a.to(device=self.device, dtype=torch.float32).contiguous()
+            a = a.detach().to(torch.float32).contiguous().numpy()
         a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
-        if a.nbytes < (1 << 16):
-            return torch.from_numpy(a).to(self.device)
-        # large host arrays go through a cached pinned staging buffer (async H2D)
-        if self._pin is None or self._pin.numel() < a.size:
-            self._pin = torch.empty(a.size, dtype=torch.float32, pin_memory=True)
-        stage = self._pin[:a.size]
-        stage.numpy()[:] = a.reshape(-1)
-        return stage.to(self.device, non_blocking=True).reshape(a.shape)
+        t = torch.empty(a.shape, dtype=torch.float32, device=self.device)
+        if a.size:
+            _lib.check(self.lib.dbx_upload_f32(self.h, a.ctypes.data_as(C.c_void_p), _ptr(t), a.size, _stream()))
+            self._keep = a      # a pinned source must outlive its DMA: keep the latest one referenced
+        return t
 
     def _as_flat(self, a):
         if isinstance(a, self.torch.Tensor):
@@ -146,16 +148,18 @@ class Engine:
         return mu, sg
 
     def set_samples(self, slab):
-        """slab: [S,P] fp32 (numpy or torch); kept alive here, borrowed by the library."""
+        """slab: [S,P] fp32 (numpy or torch), or [S,pitch] with pitch = P rounded up to 4 (16-byte rows: 128-bit streaming
+        loads and TMA without a padded copy -- what a 74.5 GB slab needs); kept alive here, borrowed by the library."""
         t = self._dev_f32(slab)
-        if t.ndim != 2 or t.shape[1] != self.P:
-            raise ValueError("slab must be [S,%d], got %r" % (self.P, tuple(t.shape)))
         pitch = (self.P + 3) // 4 * 4          # 16-byte aligned rows -> 128-bit streaming loads
-        if pitch != self.P:
+        if t.ndim != 2 or t.shape[1] not in (self.P, pitch):
+            raise ValueError("slab must be [S,%d] (or [S,%d] padded), got %r" % (self.P, pitch, tuple(t.shape)))
+        if t.shape[1] != pitch:
             padded = self.torch.zeros((t.shape[0], pitch), dtype=self.torch.float32, device=self.device)
             padded[:, :self.P] = t
             t = padded
         self._slab = t
+        self.S = int(t.shape[0])
         _lib.check(self.lib.dbx_set_samples_strided(self.h, _ptr(t), t.shape[0], self.P, pitch))
 
     # ---- hot path ---------------------------------------------------------------------
@@ -186,7 +190,15 @@ class Engine:
         B = xt.shape[0]
         s1 = torch.empty((B, self.C), dtype=torch.float32, device=self.device)
         s2 = torch.empty_like(s1) if second_moment else None
-        it = None if idx is None else torch.as_tensor(np.asarray(idx, dtype=np.int32)).to(self.device)
+        it = None
+        if idx is not None:
+            ia = np.asarray(idx, dtype=np.int32).reshape(-1)
+            S = getattr(self, "S", 0)
+            if ia.size < n or (ia.size and (ia.min() < 0 or ia.max() >= S)):   # the device gathers rows of the slab by these
+                raise ValueError("stored-sample indices must be %d values in [0, %d)" % (n, S))
+            it = torch.as_tensor(ia).to(self.device)
+        elif j0 < 0 or j0 + n > getattr(self, "S", 0):
+            raise ValueError("stored-sample range [%d, %d) outside the slab of %d samples" % (j0, j0 + n, getattr(self, "S", 0)))
         wt = None if wts is None else self._dev_f32(wts).reshape(-1)
         _lib.check(self.lib.dbx_predict_stored(self.h, _ptr(xt), B, j0, n, _ptr(it), _ptr(wt), _lib.MODE[mode],
                                                _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, 0, _ptr(s1),
@@ -337,6 +349,46 @@ class Engine:
             out["flags"] = flags
         return out
 
+    # ---- every sample's own output (callers that apply their own predicate per iteration, verifiers.py:563-653) -------
+    def predict_samples(self, x, n, seed=0, s0=0, eps=None, inflate=1.0, mode="fp32", out_kind="probs"):
+        """[n,B,C] device tensor: output of posterior sample s0+i at x (what uncertainty.py:15-36 stacks)."""
+        torch = self.torch
+        xt = self._x2d(x)
+        out = torch.empty((n, xt.shape[0], self.C), dtype=torch.float32, device=self.device)
+        e = None if eps is None else self._dev_f32(eps).reshape(n, self.P)
+        _lib.check(self.lib.dbx_predict_samples(self.h, _ptr(xt), xt.shape[0], n, seed, s0, _ptr(e), float(inflate), _lib.MODE[mode],
+                                                _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, _ptr(out), _stream()))
+        return out
+
+    def fgsm_samples(self, x, attack_labels, eps, n, seed=0, s0=0, noise=None, inflate=1.0, lower=-3.0e38, upper=3.0e38):
+        """[n,B,C] device tensor: softmax output of sample i at ITS OWN FGSM input (verifiers.py:622-625)."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        al = torch.as_tensor(np.asarray(attack_labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
+        if al.numel() != B:
+            raise ValueError("need one attack label per input row")
+        out = torch.empty((n, B, self.C), dtype=torch.float32, device=self.device)
+        e = None if noise is None else self._dev_f32(noise).reshape(n, self.P)
+        lo = float(max(lower, -3.0e38)); hi = float(min(upper, 3.0e38))
+        _lib.check(self.lib.dbx_fgsm_samples(self.h, _ptr(xt), B, _ptr(al), float(eps), lo, hi, n, seed, s0, _ptr(e), float(inflate),
+                                             _ptr(out), _stream()))
+        return out
+
+    def ibp_samples(self, x, eps, n, seed=0, s0=0, noise=None, inflate=1.0, mode="fp32", clip=True, box_hi=None):
+        """(lower, upper) [n,B,C] device tensors: logit bounds of sample i over the eps-ball around x (verifiers.py:593), or over
+        the explicit box [x, box_hi] (the un-clipped box of IBP(..., predict=True), :605-606)."""
+        torch = self.torch
+        xt = self._x2d(x)
+        B = xt.shape[0]
+        ht = None if box_hi is None else self._x2d(box_hi)
+        lo = torch.empty((n, B, self.C), dtype=torch.float32, device=self.device)
+        hi = torch.empty_like(lo)
+        e = None if noise is None else self._dev_f32(noise).reshape(n, self.P)
+        _lib.check(self.lib.dbx_ibp_samples(self.h, _ptr(xt), _ptr(ht), B, float(eps), 1 if clip else 0, n, seed, s0, _ptr(e),
+                                            float(inflate), _lib.MODE[mode], _ptr(lo), _ptr(hi), _stream()))
+        return lo, hi
+
     def ibp_one(self, x, eps, weights_flat, mode="fp32", clip=True):
         """`IBP(model, inp, weights, eps)` with explicit weights (verifiers.py:68-95): (lower, upper) logits [B,C]."""
         torch = self.torch
@@ -365,8 +417,8 @@ class Engine:
         return lo_o, hi_o
 
     def predict_host(self, x: np.ndarray, n, seed=0, s0=0, inflate=1.0, mode="bf16", out_kind="probs", variance=False):
-        """Host buffers in, host buffers out: the H2D copy of x and the D2H copy of the mean
-        happen inside the C call (this is the bench's `e2e` path)."""
+        """Host buffers in, host buffers out (`dbx_predict_host`): the H2D copy of x and the D2H copy of the mean happen inside
+        the C call on the handle's own stream."""
         a = np.ascontiguousarray(np.asarray(x, dtype=np.float32)).reshape(-1, self.K)
         B = a.shape[0]
         mean = np.empty((B, self.C), np.float32)

@@ -106,6 +106,8 @@ def load_slab(path: str, P: int, S: Optional[int] = None) -> np.ndarray:
         slab = np.load(f, mmap_mode="r")
         if slab.ndim != 2 or slab.shape[1] != P:
             raise ValueError("slab.npy has shape %r, expected [S,%d]" % (slab.shape, P))
+        if S is not None and slab.shape[0] != S:   # a stale / short slab would be indexed out of bounds on the device
+            raise ValueError("slab.npy holds %d samples but freq.npy lists %d: delete the stale slab.npy" % (slab.shape[0], S))
         return np.ascontiguousarray(slab, dtype=np.float32)
     S = count_samples(path) if S is None else S
     if S == 0:

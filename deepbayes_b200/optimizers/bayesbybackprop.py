@@ -32,6 +32,7 @@ class BayesByBackprop(optimizer.Optimizer):
         injected, a list [eps_W0, eps_b0, ...] / flat vector), W = mean + softplus(rho)*noise
         formed in fp32 exactly in that order, forward of the mini-batch.  Returns predictions
         (and, if asked, the sampled weights and ``noise_used``, :57)."""
+        self.sync_from_device()     # steps taken with sync=False left the live parameters on the device only
         eng = self.engine()
         _, oshape = self.model.rows_and_outshape(np.asarray(features))
         e = None if eps is None else eng._as_flat(eps)
@@ -122,13 +123,18 @@ class BayesByBackprop(optimizer.Optimizer):
         """optimizer.py:100-133: epochs x mini-batches of `step`, learning rate lr / (1 + decay * epoch), Gaussian input
         noise (input_noise), per-epoch logging of the running loss / accuracy and of the validation pass with the weights
         the last step left in the model (model_validate, :139-141).  The reference's `shuffle(100)` windowed shuffle is
-        replaced by a seeded permutation per epoch."""
+        replaced by a seeded permutation per epoch.  With linear_schedule (the default, optimizer.py:75) epsilon starts at 0 and
+        grows by max_eps / epochs after every epoch (:105-108, :131-132) -- also when robust_train = 0, where it is unused."""
         X_train = np.asarray(X_train, np.float32)
         y_train = np.asarray(y_train).reshape(-1)
         self.N = len(X_train)
         rng = np.random.Generator(np.random.Philox(self.seed))
         bs = int(self.batch_size)
         self.loss_log, self.acc_log, self.val_log = [], [], []
+        if self.robust_linear:      # optimizer.py:105-108: the attack / verification radius ramps up linearly from 0
+            self.max_eps = self.epsilon
+            self.epsilon = 0.0
+            self.max_robust_lambda = self.robust_lambda
         for epoch in range(self.epochs):
             lrate = self.learning_rate * (1 / (1 + self.decay * epoch))
             perm = rng.permutation(self.N)
@@ -153,14 +159,18 @@ class BayesByBackprop(optimizer.Optimizer):
                 val_loss = float(-np.mean(np.log(np.clip(pv[np.arange(len(yt)), yt], 1e-7, 1 - 1e-7))))
             self.loss_log.append(loss); self.acc_log.append(acc); self.val_log.append((val_loss, val_acc))
             print("Epoch {}, loss: {:.3f}, acc: {:.3f}, val_loss: {:.3f}, val_acc: {:.3f}".format(epoch + 1, loss, acc, val_loss, val_acc))
+            if self.robust_linear:  # optimizer.py:131-132 (epochs already holds the extra epoch compile() added, :77-79)
+                self.epsilon += self.max_eps / self.epochs
         return self
 
     def sample(self):
         """bayesbybackprop.py:176-181: N(mean, scale=softplus(rho)) -- the device holds
         sigma = softplus(rho) (dbx_set_gaussian_rho)."""
+        self.sync_from_device()
         return super().sample()
 
     def save(self, path):
         """bayesbybackprop.py:184-195: var.npy = softplus(rho) (a std); no info.pkl."""
+        self.sync_from_device()
         var = [softplus(v) for v in self.posterior_var]
         formats.save_gaussian_posterior(path, self.model, self.posterior_mean, var, None)

@@ -193,14 +193,34 @@ int dbx_count_predicate_fgsm(dbx_handle h, const float* x_dev, int64_t B, const 
  * the input box clip(x -+ eps, 0, 1) (clip01 = 0: x -+ eps) goes through the Dense layers in centre/radius form;
  * outputs, all optional: sum over samples of softmax(worst case) [B,C] (worst case = lower logit of labels[b], upper
  * logit of every other class), of the lower / upper logits [B,C], and per input the number of samples (and the
- * per-sample flags [n,B]) whose worst case still has argmax == labels[b].  Dense / Flatten models only. */
+ * per-sample flags [n,B]) whose worst case still has argmax == labels[b].  Dense / Conv2D (VALID, stride 1) / MaxPool / Flatten models. */
 int dbx_ibp_predict(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const int32_t* labels_dev, int64_t n,
                     uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, int32_t mode,
                     int32_t accumulate, float* sum_worst_dev, float* sum_lower_dev, float* sum_upper_dev, uint8_t* flags_dev,
                     int64_t* counts_dev, void* stream);
+/* The same loops with EVERY SAMPLE'S OWN OUTPUT returned instead of sums / flags, for callers that apply their own predicate
+ * to each iteration's `worst_case` like massart_bound_check does (verifiers.py:563-653: `predicate(worst_case)`, :628):
+ *   dbx_predict_samples  out [n,B,C] = model output (or logits) of posterior sample s0+i at x          (adv given, :625)
+ *   dbx_fgsm_samples     probs [n,B,C] = output of sample i at ITS OWN FGSM input (attack label per row)  (:622-625)
+ *   dbx_ibp_samples      lower / upper [n,B,C] = logit bounds of sample i over the eps-ball (clip01) or, when box_hi_dev is
+ *                        given, over the explicit box [x_dev, box_hi_dev] (IBP(..., predict=True), :605-606)  (:593, :606)
+ * also what analyzers/uncertainty.py:15-36 stacks (per-sample predictions). */
+int dbx_predict_samples(dbx_handle h, const float* x_dev, int64_t B, int64_t n, uint64_t seed, int64_t s0, const float* eps_dev,
+                        float inflate, int32_t mode, int32_t out_kind, float* out_dev, void* stream);
+int dbx_fgsm_samples(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, float eps, float lower, float upper,
+                     int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate, float* probs_dev, void* stream);
+int dbx_ibp_samples(dbx_handle h, const float* x_dev, const float* box_hi_dev, int64_t B, float eps, int32_t clip01, int64_t n,
+                    uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t mode, float* lower_dev, float* upper_dev,
+                    void* stream);
 /* `IBP(model, inp, weights, eps)` with one explicit flat weight vector (verifiers.py:68-95): logit bounds [B,C]. */
 int dbx_ibp_one(dbx_handle h, const float* x_dev, int64_t B, float eps, int32_t clip01, const float* W_dev, int32_t mode,
                 float* lower_dev, float* upper_dev, void* stream);
+
+/* Host -> device upload of `count` fp32 values on `stream` (the input of predict: posteriormodel.py:81 takes any host array).
+ * Page-locked sources are copied with one DMA (the caller keeps them alive until the stream has passed the copy); pageable
+ * sources go through two pinned staging pieces owned by the handle, each reused only after the event of its previous copy,
+ * so the call returns with `src_host` free to be modified. */
+int dbx_upload_f32(dbx_handle h, const float* src_host, float* dst_dev, int64_t count, void* stream);
 
 /* Host-buffer form of dbx_predict, the call PosteriorModel.predict(x, n) binds to: copies x
  * (host, [B,K] fp32) to the device, runs the loop, writes mean = sum1/n ([B,C]) and, if

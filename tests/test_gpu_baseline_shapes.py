@@ -1,0 +1,204 @@
+"""GPU parity at the BASELINE.json shapes: the tensor-core kernels against the CPU ORACLE (not
+against another device path) on identical seeded inputs with the oracle's eps injected, through
+the C ABI.
+
+  config 2  784-512-512-10, B = 4096 (Q = 16 row-tile pairs, [s][q] work order, 74 clusters, running
+            sums persisting over several chunk launches, finish4_kernel)       -> fused_mlp2_kernel
+  config 3  784-1024-1024-10 stored posterior, B = 64 / B = 512                -> dense_tc_f32w_kernel /
+                                                                                  dense_tc_pair_kernel
+  config 4  CNN of SURVEY 8(d) on [B,32,32,3]                                   -> conv_tc_kernel + pooled epilogue
+  config 5  784-512-512-10, K = 128 fixed inputs, argmax predicate              -> fused_mlp_kernel<1>
+  config 1  784-512-10 at B = 10000 rows                                         -> fused_mlp2_kernel, one hidden layer
+
+Tolerances (BASELINE.json north_star): bf16 mode <= 2e-2 absolute on predictive probabilities
+against the fp32 oracle, <= 2e-3 against the oracle that rounds the GEMM operands to bf16 (only
+the accumulation order differs), argmax identical; fp32 mode <= 1e-5 relative.
+Reference loop: deepbayes/posteriormodel.py:81-101; stored posteriors hmc.py:308-322;
+verification loop analyzers/verifiers.py:588-634."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BF16_ATOL = 2e-2
+BF16_VS_BF16_ORACLE = 2e-3
+
+
+def _mlp(dims, oracle, seed=1, sigma_scale=0.1):
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    L = oracle.mlp(dims)
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    eng = Engine(db.Sequential(layers))
+    mean, std = oracle.synthetic_posterior(L, seed=seed, sigma_scale=sigma_scale)
+    return L, eng, mean, std
+
+
+def _check_probs(got, want_bf, want_32):
+    assert np.isfinite(got).all()
+    assert np.abs(got - want_32).max() <= BF16_ATOL
+    np.testing.assert_allclose(got, want_bf, rtol=0, atol=BF16_VS_BF16_ORACLE)
+    assert (got.argmax(-1) == want_bf.argmax(-1)).all(), "argmax differs from the bf16 oracle"
+    margin = np.sort(want_32, axis=-1)
+    clear = (margin[:, -1] - margin[:, -2]) > 2 * BF16_ATOL
+    assert (got.argmax(-1) == want_32.argmax(-1))[clear].all()
+
+
+@pytest.mark.parametrize("fused_ns", [None, 4, 3])
+def test_config2_full_batch_fused_kernel_vs_oracle(oracle, dbx_opt, fused_ns):
+    """BASELINE config 2 at its real batch: B = 4096 rows = 16 row-tile pairs per sample.  fused_ns = 4 / 3 cut the 8 samples
+    into 2 / 3 launches, so the per-(cluster, q) running sums persist across launches and the last chunk is ragged."""
+    dims, B, n = [784, 512, 512, 10], 4096, 8
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    eps = oracle.synthetic_eps(L, n, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    if fused_ns is not None:
+        dbx_opt("FUSED_NS", fused_ns)
+    s1, s2 = eng.predict_sums(x, n, eps=eps_flat, mode="bf16", second_moment=True)
+    assert eng.last_path() == "fused_tcgen05"
+    got = (s1 / float(n)).cpu().numpy()
+    w1, w2 = oracle.predict_moments(L, mean, std, x, n, eps, bf16=True)
+    want_32 = oracle.predict(L, mean, std, x, n, eps)
+    _check_probs(got, w1 / np.float32(n), want_32)
+    np.testing.assert_allclose((s2 / float(n)).cpu().numpy(), w2 / np.float32(n), rtol=0, atol=BF16_VS_BF16_ORACLE)
+    # mean logits (predict_logits, posteriormodel.py:114-139) through the same kernel
+    lg, _ = eng.predict_sums(x, n, eps=eps_flat, mode="bf16", out_kind="logits")
+    want_lg = oracle.predict(L, mean, std, x, n, eps, out="logits", bf16=True)
+    np.testing.assert_allclose((lg / float(n)).cpu().numpy(), want_lg, rtol=0, atol=5e-3)
+
+
+def test_config2_full_batch_fp32_mode_vs_oracle(oracle):
+    dims, B, n = [784, 512, 512, 10], 4096, 3
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    eps = oracle.synthetic_eps(L, n, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    s1, _ = eng.predict_sums(x, n, eps=eps_flat, mode="fp32")
+    want = oracle.predict(L, mean, std, x, n, eps)
+    np.testing.assert_allclose((s1 / float(n)).cpu().numpy(), want, rtol=1e-5, atol=2e-7)
+
+
+def test_config1_full_batch_vs_oracle(oracle):
+    """BASELINE config 1 (784-512-10) at the MNIST-test-shaped batch of SURVEY 8(d): B = 10,000 (79 row tiles: the last pair is
+    half empty and the last tile ragged)."""
+    dims, B, n = [784, 512, 10], 10000, 5
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    eps = oracle.synthetic_eps(L, n, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    s1, _ = eng.predict_sums(x, n, eps=eps_flat, mode="bf16")
+    assert eng.last_path() == "fused_tcgen05"
+    _check_probs((s1 / float(n)).cpu().numpy(), oracle.predict(L, mean, std, x, n, eps, bf16=True),
+                 oracle.predict(L, mean, std, x, n, eps))
+
+
+@pytest.mark.parametrize("B", [64, 512])
+def test_config3_stored_posterior_vs_oracle(oracle, B):
+    """BASELINE config 3 architecture (784-1024-1024-10), stored fp32 samples resident in HBM: B = 64 runs
+    dense_tc_f32w_kernel (weights by TMA straight from the fp32 slab), B = 512 the conversion pass + dense_tc_pair_kernel."""
+    dims, S = [784, 1024, 1024, 10], 8
+    L, eng, mean, std = _mlp(dims, oracle, sigma_scale=0.3)
+    eps = oracle.synthetic_eps(L, S, seed=2)
+    samples = [oracle.sample_gaussian(mean, std, e) for e in eps]
+    slab = np.stack([oracle.flatten_list(s) for s in samples])
+    eng.set_samples(slab)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    g = np.random.Generator(np.random.Philox(5))
+    idx = g.integers(0, S, size=12).astype(np.int32)          # the n draws of posteriormodel.py:77, with replacement
+    s1, _ = eng.predict_stored_sums(x, len(idx), idx=idx, mode="bf16")
+    assert eng.last_path() == "generic_tc"
+    want_bf = oracle.predict_stored(L, samples, x, list(idx), bf16=True) / np.float32(len(idx))
+    want_32 = oracle.predict_stored(L, samples, x, list(idx)) / np.float32(len(idx))
+    _check_probs((s1 / float(len(idx))).cpu().numpy(), want_bf, want_32)
+    # deterministic expectation sum_i freq_i f(W_i) (probverification.py:619-650), contiguous rows
+    freq = oracle.normalise_freq(np.arange(1, S + 1))
+    e1, _ = eng.predict_stored_sums(x, S, j0=0, wts=freq, mode="bf16")
+    want_e = oracle.predict_stored(L, samples, x, list(range(S)), weights=freq, bf16=True)
+    np.testing.assert_allclose(e1.cpu().numpy(), want_e, rtol=0, atol=BF16_VS_BF16_ORACLE)
+    # fp32 mode: the reference's arithmetic
+    f1, _ = eng.predict_stored_sums(x[:16], S, j0=0, wts=freq, mode="fp32")
+    np.testing.assert_allclose(f1.cpu().numpy(), oracle.predict_stored(L, samples, x[:16], list(range(S)), weights=freq),
+                               rtol=1e-5, atol=2e-7)
+
+
+def test_config4_cnn_vs_oracle(oracle):
+    """BASELINE config 4: Conv2D(32,3x3) -> Conv2D(64,3x3) -> MaxPool(2) -> Flatten -> Dense(128) -> Dense(10) on [B,32,32,3]
+    (SURVEY 8(d)): first conv through the shared im2col + GEMM, second through conv_tc_kernel with the pooled epilogue."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.engine import Engine
+    L = oracle.cnn_cfg4()
+    m = db.Sequential([db.Conv2D(32, 3, activation="relu", input_shape=(32, 32, 3)), db.Conv2D(64, 3, activation="relu"),
+                       db.MaxPooling2D(2), db.Flatten(), db.Dense(128, activation="relu"), db.Dense(10, activation="softmax")])
+    eng = Engine(m)
+    assert eng.P == oracle.param_count(L) == 1626442
+    mean, std = oracle.synthetic_posterior(L, seed=1)
+    eng.set_gaussian(mean, std)
+    B, n = 4, 2
+    x = oracle.synthetic_x((B, 32, 32, 3), seed=0)
+    eps = oracle.synthetic_eps(L, n, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    s1, _ = eng.predict_sums(x, n, eps=eps_flat, mode="bf16")
+    assert eng.last_path() == "generic_tc"
+    _check_probs((s1 / float(n)).cpu().numpy(), oracle.predict(L, mean, std, x, n, eps, bf16=True),
+                 oracle.predict(L, mean, std, x, n, eps))
+    f1, _ = eng.predict_sums(x, n, eps=eps_flat, mode="fp32")
+    np.testing.assert_allclose((f1 / float(n)).cpu().numpy(), oracle.predict(L, mean, std, x, n, eps), rtol=1e-5, atol=2e-7)
+
+
+def test_config5_predicate_flags_vs_oracle(oracle):
+    """BASELINE config 5: K = 128 fixed (pre-perturbed) inputs through config 2's MLP, per-sample predicate argmax == label
+    (verifiers.py:628-634 with the tutorial predicate).  Flags must equal the bf16 oracle's wherever its top-2 logits are not
+    within accumulation-order noise of each other."""
+    dims, K, n = [784, 512, 512, 10], 128, 16
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    g = np.random.Generator(np.random.Philox(3))
+    x = np.clip(oracle.synthetic_x((K, dims[0]), seed=0) + g.uniform(-0.1, 0.1, size=(K, dims[0])).astype(np.float32), 0, 1)
+    eps = oracle.synthetic_eps(L, n, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    # labels = the deterministic prediction, so that the predicate is not trivially false
+    labels = oracle.forward(L, mean, x).argmax(-1).astype(np.int32)
+    counts, flags = eng.count_predicate(x, labels, n, eps=eps_flat, mode="bf16", return_flags=True)
+    assert eng.last_path() == "fused_tcgen05"
+    flags, counts = flags.cpu().numpy(), counts.cpu().numpy()
+    np.testing.assert_array_equal(counts, flags.sum(0))
+    want_flags = np.zeros((n, K), np.uint8)
+    clear = np.zeros((n, K), bool)
+    for s in range(n):
+        w = oracle.sample_gaussian(mean, std, eps[s])
+        z = oracle.forward(L, w, x, np.float32, "logits", True)
+        want_flags[s] = (z.argmax(-1) == labels)
+        top = np.sort(z, axis=-1)
+        clear[s] = (top[:, -1] - top[:, -2]) > 5e-3
+    assert clear.mean() > 0.9
+    np.testing.assert_array_equal(flags[clear], want_flags[clear])
+    assert (flags != want_flags).mean() <= 0.01
+    assert 0 < counts.sum() <= n * K
+
+
+def test_rank_shards_equal_one_rank(oracle):
+    """SURVEY 8(e) on one GPU: the n samples of one predict split into G contiguous global-id ranges (what rank g of G
+    evaluates) and summed equal the single-rank result, for G = 2, 4, 8 (bench.py repeats this across real ranks under
+    torchrun and prints "shard_check")."""
+    from deepbayes_b200 import distributed as dd
+    dims, B, n = [784, 512, 512, 10], 1024, 64
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    one1, one2 = eng.predict_sums(x, n, seed=11, s0=1000, mode="bf16", second_moment=True)
+    one1, one2 = one1.cpu().numpy(), one2.cpu().numpy()
+    for G in (2, 4, 8):
+        t1 = np.zeros_like(one1); t2 = np.zeros_like(one2)
+        for g in range(G):
+            off, cnt = dd.shard_range(n, g, G)
+            a, b = eng.predict_sums(x, cnt, seed=11, s0=1000 + off, mode="bf16", second_moment=True)
+            t1 += a.cpu().numpy(); t2 += b.cpu().numpy()
+        np.testing.assert_allclose(t1 / n, one1 / n, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(t2 / n, one2 / n, rtol=1e-5, atol=1e-6)
