@@ -74,6 +74,12 @@ _SIGS = {
     "dbx_ibp_state": (C.c_int, [_p, _p, _p, _i64, _p, C.c_float, _p, _p, _p]),
     "dbx_ibp_one": (C.c_int, [_p, _p, _i64, C.c_float, C.c_int32, _p, C.c_int32, _p, _p, _p]),
     "dbx_upload_f32": (C.c_int, [_p, _p, _p, _i64, _p]),
+    "dbx_comm_create": (C.c_int, [_i32, _i32, _i32, _i64, C.POINTER(_p)]),
+    "dbx_comm_handle": (C.c_int, [_p, _p]),
+    "dbx_comm_connect": (C.c_int, [_p, _p]),
+    "dbx_comm_allreduce": (C.c_int, [_p, _p, _i64, _p, _i64, _p]),
+    "dbx_comm_status": (C.c_int, [_p, C.POINTER(_i32), C.POINTER(_i64)]),
+    "dbx_comm_destroy": (C.c_int, [_p]),
     "dbx_predict_host": (C.c_int, [_p, _p, _i64, _i64, _u64, _i64, _f, _i32, _i32, _p, _p]),
     "dbx_activation": (C.c_int, [_i32, _p, _i64, _i64, _p]),
     "dbx_philox_raw": (C.c_int, [_u64, _i64, _i64, _p, _p]),

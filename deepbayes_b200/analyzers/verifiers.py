@@ -195,6 +195,9 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
         raise ValueError("pass a predicate (verifiers.py:563) or cls=<true class> for the device predicate argmax == cls")
     if verify and cls is None:
         raise ValueError("verify=True needs cls= (verifiers.py:596-603 / :607-608 build the worst case around it)")
+    if predicate is None and verify and not classification:
+        raise ValueError("verify=True with classification=False (verifiers.py:609-619) needs a predicate: cls is a regression target "
+                         "there, not a class index; pass classification=True or verify=False for the device predicate argmax == cls")
     eng = _engine_of(model)
     # bounds are computed in fp32 unless the caller opts into bf16 (narrower arithmetic than the reference's float64: not sound)
     mode = kwargs.get('mode') or ("fp32" if verify else _mode_of(model))

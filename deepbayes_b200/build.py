@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libdeepbayes_b200.so")
-SOURCES = ["engine.cu", "fused_mlp.cu", "stream_mlp.cu", "gemm_tc.cu"]
+SOURCES = ["engine.cu", "fused_mlp.cu", "stream_mlp.cu", "gemm_tc.cu", "collective.cu"]
 HEADERS = ["common.cuh", "engine.h", "tc05.cuh", "ibp.cuh", "train.cuh", "attack.cuh", os.path.join("..", "..", "include", "deepbayes_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

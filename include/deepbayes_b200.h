@@ -228,6 +228,26 @@ int dbx_upload_f32(dbx_handle h, const float* src_host, float* dst_dev, int64_t 
 int dbx_predict_host(dbx_handle h, const float* x_host, int64_t B, int64_t n, uint64_t seed, int64_t s0,
                      float inflate, int32_t mode, int32_t out_kind, float* mean_host, float* var_host);
 
+/* ---- multi-GPU: the one exchange of the path -------------------------------------------------------
+ * Posterior samples shard over ranks (posteriormodel.py:94-101: the iterations of the loop are independent); the only
+ * collective is the SUM over ranks of the [B,C] sample-sums.  A communicator owns a window in its GPU's HBM that every
+ * peer rank of the node maps through CUDA IPC; dbx_comm_allreduce is ONE kernel on `stream`: local sums -> own window,
+ * release-flag to every peer over NVLink, wait for all peers' flags, read all windows in rank order and write the sum in
+ * place (bit-identical on every rank, independent of arrival order).  One process per GPU:
+ *   dbx_comm_create   allocate the window (max_floats = largest na + nb of a later call)
+ *   dbx_comm_handle   64-byte IPC handle of the own window; the host side all-gathers these (torch.distributed / MPI)
+ *   dbx_comm_connect  map the `world` windows (handles in rank order, world x 64 bytes)
+ *   dbx_comm_allreduce  a_dev[na] (and b_dev[nb], optional) += the same buffers of every other rank; calls on one
+ *                     communicator must be issued in the same order on every rank; na, nb multiples of 4, 16-byte aligned
+ *   dbx_comm_status   timed_out != 0 after a peer failed to arrive within 10 s (the communicator is then unusable) */
+typedef struct dbx_comm_s* dbx_comm;
+int dbx_comm_create(int32_t rank, int32_t world, int32_t device, int64_t max_floats, dbx_comm* out);
+int dbx_comm_handle(dbx_comm c, void* handle64);
+int dbx_comm_connect(dbx_comm c, const void* handles);
+int dbx_comm_allreduce(dbx_comm c, float* a_dev, int64_t na, float* b_dev, int64_t nb, void* stream);
+int dbx_comm_status(dbx_comm c, int32_t* timed_out, int64_t* calls);
+int dbx_comm_destroy(dbx_comm c);
+
 /* Elementwise activation on a device buffer [rows, cols] (model.layers[-1].activation(...),
  * verifiers.py:552-555). */
 int dbx_activation(int32_t act, float* x_dev, int64_t rows, int64_t cols, void* stream);

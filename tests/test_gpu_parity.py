@@ -166,7 +166,7 @@ def test_stored_posterior(ctx, golden, oracle, name):
     assert np.abs((s1b / float(len(idx))).cpu().numpy() - golden[name + "/stored_mc_fp32"]).max() <= BF16_ATOL
     # range check: asking past the slab fails loudly
     from deepbayes_b200._lib import DbxError
-    with pytest.raises(DbxError):
+    with pytest.raises((DbxError, ValueError)):
         eng.predict_stored_sums(c["x"], n + 1, j0=0, mode="fp32")
 
 
@@ -479,7 +479,7 @@ def test_statistical_verification(ctx, oracle):
     res = db.analyzers.statistical_robustness(pm, x, cls, return_flags=True)
     assert res["n"] == 380 and res["flags"].shape == (380, 4)
     assert (res["p"] > 0.9).all()
-    frac, iters, _ = db.analyzers.massart_bound_check(pm, x[:1], 0.0, cls=int(cls[0]), adv=x[:1])
+    frac, iters, _ = db.analyzers.massart_bound_check(pm, x[:1], 0.0, cls=int(cls[0]), adv=x[:1], verify=False)
     flags = np.ones(1000, np.uint8)
     want_frac, want_iters = oracle.massart_loop(flags)
     if frac == 1.0:
@@ -727,8 +727,69 @@ def test_massart_with_ibp(tmp_path, oracle):
     cls = int(np.argmax(opt.predict(x)))
     p, it, _ = verifiers.massart_bound_check(opt, x, 1e-4, None, cls=cls, verify=True, classification=True, confidence=0.8, delta=0.3)
     assert 0.0 <= p <= 1.0 and 1 <= it <= verifiers.chernoff_sample_bound(0.8, 0.3) + 1
-    with pytest.raises(NotImplementedError):
-        verifiers.massart_bound_check(opt, x, 1e-4, None, cls=cls, verify=True, classification=False)
+    # a Python predicate (verifiers.py:628) on every sample's worst case == the device predicate on the same sample ids
+    opt._next_sample = 0
+    seen = []
+    pa = verifiers.massart_bound_check(opt, x, 1e-4, None, cls=cls, classification=True, confidence=0.8, delta=0.3)
+    opt._next_sample = 0
+    pb = verifiers.massart_bound_check(opt, x, 1e-4, lambda wc: (seen.append(np.asarray(wc)), np.argmax(np.squeeze(wc)) == cls)[1],
+                                       cls=cls, classification=True, confidence=0.8, delta=0.3)
+    assert pa[:2] == pb[:2]
+    assert len(seen) == int(pb[1]) and seen[0].shape == (1, 10) and np.allclose(seen[0].sum(), 1, rtol=1e-5)
+    with pytest.raises(ValueError):   # no predicate and nothing to build the device predicate from
+        verifiers.massart_bound_check(opt, x, 1e-4, None, classification=True)
+
+
+def test_massart_regression_branch_and_chernoff_override_vs_oracle(tmp_path, oracle):
+    """verifiers.py:609-619 (verify=True, classification=False: IBP(predict=True) on the un-clipped box, per output the bound
+    farther from ``cls``) and the chernoff=True override (:585, :643-648) walked against the oracle on the SAME posterior
+    samples (Philox ids 35.. -- the first 35 go to the `mean = 0.0 * model.predict(inp)` line, :583)."""
+    import deepbayes_b200 as db
+    from deepbayes_b200 import formats
+    from deepbayes_b200.analyzers import verifiers
+    dims = [12, 16, 3]
+    L = oracle.mlp(dims, out_act="linear")
+    m = db.Sequential([db.Dense(16, activation="relu", input_shape=(12,)), db.Dense(3, activation="linear")])
+    mean, std = oracle.synthetic_posterior(L, seed=4, sigma_scale=0.3)
+    pdir = str(tmp_path / "post")
+    formats.save_gaussian_posterior(pdir, m, mean, std, {"input_upper": 1.0, "input_lower": 0.0})
+    seed = 21
+    pm = db.PosteriorModel(pdir, mode="fp32", seed=seed)
+    x = oracle.synthetic_x((1, 12), seed=3)
+    eps = 0.05
+    target = oracle.forward(L, mean, x, out="logits").reshape(-1)
+    tol = 0.35
+    pred = lambda wc: bool(np.abs(np.squeeze(wc) - target).max() < tol)
+    seen = []
+    frac, iters, mz = verifiers.massart_bound_check(pm, x, eps, lambda wc: (seen.append(np.array(wc)), pred(wc))[1], cls=target,
+                                                    confidence=0.8, delta=0.3)
+    P = oracle.param_count(L)
+    outcomes, worsts = [], []
+    for i in range(verifiers.chernoff_sample_bound(0.8, 0.3) + 2):
+        w = oracle.sample_gaussian(mean, std, oracle.split_flat(L, oracle.philox_normals(seed, 35 + i, P)))
+        lo, hi = oracle.ibp_forward(L, w, x, eps, predict=True)
+        wc = np.where(np.abs(hi - target) > np.abs(lo - target), hi, lo)
+        worsts.append(wc); outcomes.append(pred(wc))
+    want_frac, want_iters = oracle.massart_loop(np.asarray(outcomes, np.uint8), confidence=0.8, delta=0.3)
+    for got, want in zip(seen, worsts):
+        np.testing.assert_allclose(np.squeeze(got), np.squeeze(want), rtol=2e-5, atol=2e-5)
+    margins = [abs(np.abs(np.squeeze(wc) - target).max() - tol) for wc in worsts[:int(want_iters)]]
+    if min(margins) > 1e-3:
+        assert (frac, iters) == (want_frac, want_iters)
+    assert np.all(np.asarray(mz) == 0)
+    assert 0.0 < want_frac < 1.0 or len(set(outcomes)) == 1
+    # chernoff=True (:585, :643-648) on a classifier: the walk runs to the Chernoff bound whatever the halting rule says, and the
+    # mean of model._predict(glob_adv) over the iterations comes back (rows of softmax outputs: they sum to 1)
+    Lc = oracle.mlp([12, 16, 3])
+    mc = db.Sequential([db.Dense(16, activation="relu", input_shape=(12,)), db.Dense(3, activation="softmax")])
+    cdir = str(tmp_path / "post_c")
+    formats.save_gaussian_posterior(cdir, mc, mean, std, {"input_upper": 1.0, "input_lower": 0.0})
+    pm2 = db.PosteriorModel(cdir, mode="fp32", seed=seed)
+    c0 = int(np.argmax(pm2.predict(x)))
+    f2, it2, mean2 = verifiers.massart_bound_check(pm2, x, eps, lambda wc: np.argmax(np.squeeze(wc)) == c0, cls=c0, confidence=0.8,
+                                                   delta=0.3, chernoff=True, verify=False)
+    assert it2 == verifiers.chernoff_sample_bound(0.8, 0.3) + 1
+    assert np.asarray(mean2).shape == (1, 3) and np.allclose(np.asarray(mean2).sum(), 1.0, rtol=1e-4)
 
 
 @pytest.mark.parametrize("dims,B,S", [([784, 1024, 1024, 10], 64, 20), ([200, 512, 384, 12], 150, 9), ([784, 640, 10], 40, 7)])
