@@ -32,6 +32,9 @@ struct Options {
   long long fused_kernel = 0;       // 0 = by shape; 1 = single-CTA kernel; 2 = CTA-pair kernel
   long long fused_order = -1;       // -1 = by shape; 0 = [q][s] contiguous ranges; 1 = [s][q] round-robin
   long long fused_ns = 0;           // samples per fused launch (0 = by shape)
+  long long fused_l3at = 16;        // CTA-pair kernel: layer-2 k-step at which the previous chunk's output-layer MMAs are slipped in (0 = after the chunk)
+  long long fused_np = 1;           // CTA-pair kernel: TMA producer warps (2 = even / odd stages from two threads)
+  long long fused_kd = 128;         // CTA-pair kernel: k-depth of a layer-1 TMA stage (128 = 3 x 64 KB stages, 64 = 6 x 32 KB)
   long long fused_trace = 0, fused_trace_only = 0;   // in-kernel clock probes of one cluster (tools/trace_fused.py)
   long long ws_mb = 2048;           // workspace budget of the generic executor / IBP
 };

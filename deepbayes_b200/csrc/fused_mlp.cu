@@ -66,6 +66,7 @@ struct FusedParams {
   int chunk;                   // index of this launch within the call (order 1 keeps its running sums across launches)
   int order;                   // v4: 0 = [q][s] contiguous ranges, 1 = [s][q] round-robin with running sums in `partial`
   unsigned long long* visited; // v4 order 1: per cluster, bit q set when the cluster wrote its (cluster, q) slice
+  int l3_at;                   // pair kernel: k-step of a layer-2 chunk at which the previous chunk's output-layer MMAs may be slipped in (0 = never)
   unsigned trace_only;            // 0 = all probes, else up to four probe ids, one per byte (a probe costs ~180 cycles on the warp that takes it)
   long long* trace;            // debug timeline of block 0 (null in production): [0]=count, then (id, clock) pairs
 };
@@ -528,14 +529,27 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 // is what limits the single-CTA SS MMA to ~77 % of the tensor peak (tools/mma_rate.cu).
 // Same TMEM plan, same epilogue and same work split as fused_mlp_kernel<2>.
 // =======================================================================================
-#ifndef DBX_K2STAGES
-#define DBX_K2STAGES 6
-#endif
-constexpr int k2Stages = DBX_K2STAGES;
-constexpr int k2StageBytes = 32768;   // X block 16 KB + this CTA's half of the weight block 16 KB
+// Stage geometry of the CTA-pair kernel.  KD = k-depth of one layer-1 stage.  What bounds the TMA ring is not bytes in
+// flight but the PRODUCER THREAD: every stage costs it ~400 cycles of barrier handshake plus ~95 cycles per bulk-tensor
+// copy it issues (tools/tma_rate.cu, profiles/r2_tma_rate.log: one thread sustains 54 B/clk/SM with 2 x 16 KB copies per
+// 32 KB stage, 41 with 4 x 8 KB, 82-87 with 64 KB stages -- the same for 2, 3 or 6 stages in flight).  With 32 KB stages
+// and three copies per stage the layer-1 loop needed a stage per 512 MMA cycles from a thread that could not deliver one
+// in under ~700.  So: KD = 128 -> 64 KB stages (3 of them), ONE copy for the X block (box 64k x 128 rows x 2 k-blocks through
+// a 3-D view of X) and ONE for the CTA's weight half (box 64n x 128k x 2 n-blocks through a 4-D view of the Keras kernel);
+// a layer-2 chunk's whole [64n x 512k] weight half is one stage (two copies).  KD = 64 keeps 6 x 32 KB stages with the
+// same merged copies (option FUSED_KD=64, for A/B runs).
+template <int KD> struct K2 {
+  static constexpr int XB = KD * 256;                  // X block: 128 rows x KD x bf16
+  static constexpr int WB = KD * 128;                  // one [64 n x KD k] MN-major weight block
+  static constexpr int STAGE = XB + 2 * WB;            // 32 KB / 64 KB
+  static constexpr int NST = 196608 / STAGE;           // 6 / 3
+  static constexpr int L2K = KD == 128 ? 512 : 128;    // k per layer-2 stage
+  static constexpr int L2BOXK = KD == 128 ? 256 : 128; // k rows of one layer-2 copy (box dims are <= 256)
+};
+constexpr int k2MaxStages = 6;
 
 struct __align__(8) Barriers2 {
-  uint64_t full[k2Stages], empty[k2Stages];
+  uint64_t full[k2MaxStages], empty[k2MaxStages];
   uint64_t w3_full, w3_empty;
   uint64_t bias_full[2], bias_empty[2];
   uint64_t acc_full[2], act1_ready[2];
@@ -544,14 +558,18 @@ struct __align__(8) Barriers2 {
   uint32_t tmem_slot;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int k2Threads = 224;   // warp 0 producer, 1 MMA issuer, 2-5 epilogue, 6 second producer (NP = 2)
+template <int KD, int NP>
+__global__ void __launch_bounds__(k2Threads, 1)
 fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3,
                   const FusedParams p) {
+  using G = K2<KD>;
+  constexpr int k2StageBytes = G::STAGE;
   constexpr int CM = 2;
   uint8_t* smem = (uint8_t*)(((uintptr_t)fused_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
-  constexpr int NST = k2Stages;
+  constexpr int NST = G::NST;
   const uint32_t s_w3 = s_stage + NST * k2StageBytes;
   float* bias_smem = (float*)(smem + NST * k2StageBytes + kW3Bytes / 2);
   const uint32_t s_bias = smem_u32(bias_smem);
@@ -567,8 +585,8 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int H = p.H, NH = p.NH, K0 = p.K0;
   const int n_l1 = (H + 255) / 256;
   const int n_l2 = (NH == 2) ? H / 128 : 0;
-  const int kb1 = (K0 + 63) / 64;
-  const int l2_stages = H / 128;                // 2 k-blocks per stage
+  const int kb1 = (K0 + KD - 1) / KD;
+  const int l2_stages = (H + G::L2K - 1) / G::L2K;
 
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
@@ -599,16 +617,18 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     else { q = (int)(u / p.ns); s = (int)(u - (long long)q * p.ns); }
   };
 
-  if (warp == 0) {
-    // =========================== TMA producer (both CTAs) ===========================
+  if (warp == 0 || (NP == 2 && warp == 6)) {
+    // =========================== TMA producer(s) (both CTAs) ===========================
     // Every copy lands in the issuing CTA's smem and signals the LEADER's `full` barrier; only
-    // the leader arms it (expect_tx of the pair's total bytes).
+    // the leader arms it (expect_tx of the pair's total bytes).  NP = 2: warp 0 fills the even stages of the sequence,
+    // warp 6 the odd ones (a stage costs the issuing thread ~600 cycles, see K2; two threads keep a ring of 32 KB stages fed).
+    const uint32_t pi = warp == 0 ? 0u : 1u;
     uint32_t it = 0, w3_n = 0, unit_n = 0;
     for (long long u = u0; u < u1; u += u_step, ++unit_n) {
       int q, s;
       decode(u, q, s);
       const int m0 = (q * CM + (int)rank) * 128;
-      {
+      if (pi == 0) {
         const uint32_t b = unit_n & 1;
         mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
         if (elect_one()) {
@@ -621,21 +641,20 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int ncols = min(256, H - c * 256);
         const int nhalf = ncols / 128;            // n-blocks (64 cols) per CTA
         for (int kb = 0; kb < kb1; ++kb, ++it) {
+          if (NP == 2 && (it & 1u) != pi) continue;
           const uint32_t st = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
           if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
             const uint32_t base = s_stage + st * k2StageBytes;
-            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)(kXBytes + nhalf * kBlkBytes));
-            tma2_load_2d(base, &tmX, fb, kb * 64, m0);
-#pragma unroll
-            for (int nb = 0; nb < 2; ++nb)
-              if (nb < nhalf)
-                tma2_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + ((int)rank * nhalf + nb) * 64, kb * 64, s);
+            // full boxes always: what lies beyond K0 (k) or beyond the kernel's columns is zero-filled and counted
+            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)G::STAGE);
+            tma2_load_3d(base, &tmX, fb, 0, m0, kb * (KD / 64));
+            tma2_load_4d(base + G::XB, &tmW1, fb, 0, kb * KD, c * 4 + (int)rank * nhalf, s);
           }
           __syncwarp();
         }
-        if (c == 0) {
+        if (c == 0 && pi == 0) {
           mbar_wait(smem_u32(&bars->w3_empty), (w3_n & 1) ^ 1);
           if (elect_one()) {
             const uint32_t wf = smem_u32(&bars->w3_full);
@@ -649,24 +668,28 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       for (int j = 0; j < n_l2; ++j) {
         for (int sg = 0; sg < l2_stages; ++sg, ++it) {
+          if (NP == 2 && (it & 1u) != pi) continue;
           const uint32_t st = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
           if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
-            const uint32_t base = s_stage + st * k2StageBytes + kXBytes;
-            if (leader) mbar_expect_tx(fb, 2u * 2u * kBlkBytes);
-#pragma unroll
-            for (int kblk = 0; kblk < 2; ++kblk)   // this CTA's 64 of the chunk's 128 columns, two 64-wide k-blocks
-              tma2_load_3d(base + kblk * kBlkBytes, &tmW2, fb, j * 128 + (int)rank * 64, (sg * 2 + kblk) * 64, s);
+            const uint32_t base = s_stage + st * k2StageBytes;
+            // this CTA's 64 of the chunk's 128 columns, k rows [sg * L2K, ...): one or two [64 n x L2BOXK k] boxes
+            const int krem = H - sg * G::L2K;
+            const int nops = krem > G::L2BOXK && G::L2K > G::L2BOXK ? 2 : 1;
+            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)(nops * G::L2BOXK * 128));
+            for (int o = 0; o < nops; ++o)
+              tma2_load_4d(base + o * (G::L2BOXK * 128), &tmW2, fb, 0, sg * G::L2K + o * G::L2BOXK, j * 2 + (int)rank, s);
           }
           __syncwarp();
         }
       }
     }
-    for (int k = 0; k < NST; ++k, ++it) {   // tail: the leader's last commits must have landed here
-      const uint32_t st = it % NST, ph = (it / NST) & 1;
-      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
-    }
+    if (pi == 0)
+      for (int k = 0; k < NST; ++k, ++it) {   // tail: the leader's last commits must have landed here
+        const uint32_t st = it % NST, ph = (it / NST) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA only) ===========================
     if (leader) {
@@ -702,9 +725,9 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         DBX_TRACE(140);
         if (elect_one()) {
           const uint64_t bd = w3desc0 + (uint64_t)(pw0 >> 4);
-          for (int kk = 0; kk < pk0; ++kk) {
+          for (int kk = 0; kk < pk0; ++kk) {   // four independent accumulator chains (see drain_l3)
             const uint64_t d = bd + (uint64_t)(kk * 16);
-            mma2_ts_lh(pd0, pa0 + kk * 8, (uint32_t)d, (uint32_t)(d >> 32), idesc_l3, kk > 0);
+            mma2_ts_lh(pd0 + (uint32_t)(kk & 3) * 16, pa0 + kk * 8, (uint32_t)d, (uint32_t)(d >> 32), idesc_l3, kk > 3);
           }
           mma2_commit_mc(smem_u32(&bars->l3_full[pb0]), kBoth);
           if (pl0) mma2_commit_mc(smem_u32(&bars->w3_empty), kBoth);
@@ -743,16 +766,18 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             mbar_wait(st_full, st_ph);
             DBX_STAGE_FENCE();
             if (elect_one()) {
+              // A: [64 k x 128 rows] K-major SW128 tiles, 16 KB apart; B: [KD k x 64 n] MN-major SW128 blocks, WB apart
               const uint32_t a_lo = st_a16 | (1u << 16);
-              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
-              if (kb + 1 < kb1 || (K0 & 63) == 0) {
+              const uint32_t b_lo = (st_a16 + (G::XB >> 4)) | ((G::WB >> 4) << 16);
+              const int kleft = K0 - kb * KD;
+              if (kleft >= KD) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  mma2_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+                for (int kk = 0; kk < KD / 16; ++kk)
+                  mma2_ss_lh(dreg, a_lo + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
               } else {
-                const int ksteps = ((K0 & 63) + 15) >> 4;
+                const int ksteps = (kleft + 15) >> 4;
                 for (int kk = 0; kk < ksteps; ++kk)
-                  mma2_ss_lh(dreg, a_lo + kk * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+                  mma2_ss_lh(dreg, a_lo + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
               }
               mma2_commit_mc(st_empty, kBoth);
             }
@@ -783,53 +808,90 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           flush_buf(b);
           wait_drained(b);
           DBX_TRACE(120 + j);
-          int sg = 0;
-          while (sg < l2_stages) {
-            int nsg = l2_stages;
+          // k-steps [0, KS) of this chunk; chunk 0 is cut at k-step 16 (the features of layer-1 chunk 1 follow there,
+          // and their epilogue may still be running); each piece is issued as ONE block after all its stages have landed
+          const int KS = H >> 4;
+          constexpr int SPS = G::L2K / 16;   // k-steps per stage
+          const int l3_at = (p.l3_at > 0 && p.l3_at < KS) ? p.l3_at : KS + 1;   // k-step at which the previous chunk's output-layer MMAs may be slipped in
+          int ks = 0, waited = 0;
+          while (ks < KS) {
+            int ke = KS;
             if (j == 0) {
-              if (sg == 0) {
+              if (ks == 0) {
                 mbar_wait(smem_u32(&bars->act1_ready[0]), ph_act1_0 & 1); ++ph_act1_0;
-                nsg = min(2, l2_stages);
+                ke = min(16, KS);
               } else {
-                mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1);
-                ++ph_act1_1;
-                nsg = l2_stages - sg;
+                mbar_wait(smem_u32(&bars->act1_ready[1]), ph_act1_1 & 1); ++ph_act1_1;
               }
               fence_after_sync();
             }
-            {   // every stage of the block has landed (normally long ago: the producer runs ahead)
-              uint32_t f = st_full, i2 = st_i, ph = st_ph;
-              for (int t = 0; t < nsg; ++t) {
-                mbar_wait(f, ph);
-                if (++i2 == NST) { i2 = 0; ph ^= 1; f = full0; } else f += 8;
+            {   // every stage of the piece has landed (normally long ago: the producer runs ahead)
+              const int hi = (ke - 1) / SPS;
+              for (; waited <= hi; ++waited) {
+                uint32_t i2 = st_i + (uint32_t)waited, ph = st_ph;
+                while (i2 >= (uint32_t)NST) { i2 -= NST; ph ^= 1; }
+                mbar_wait(full0 + 8 * i2, ph);
               }
             }
+            // The piece is issued as ONE block by the elected thread: a gap of even ~20 cycles between dependent MMAs costs
+            // ~330 cycles (the accumulator chain restarts; splitting the 32 MMAs into 4 groups with a barrier probe between
+            // them measured 2350 -> 4000 cycles per chunk).  The pending output-layer MMAs of the PREVIOUS chunk are slipped
+            // in ONCE, at k-step `l3_at`, if its packed H2 is there by then (one in-thread non-blocking probe): issued
+            // only after this chunk, they, the drain of their 16 columns and with it the start of the chunk after next
+            // came ~1300 cycles late.
+            bool slipped = false;
             if (elect_one()) {
-              uint32_t e = st_empty, a16 = st_a16, i2 = st_i;
-              for (int t = 0; t < nsg; ++t) {
-                const int g = sg + t;
-                const uint32_t b_lo = (a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
-                const uint32_t a0 = tmem + (uint32_t)(g >> 1) * 256 + (uint32_t)(g & 1) * 64;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
-                  mma2_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2, (g | i) > 0);
-                mma2_commit_mc(e, kBoth);
-                if (++i2 == NST) { i2 = 0; e = empty0; a16 = a16_0; } else { e += 8; a16 += k2StageBytes >> 4; }
+              int g = ks;
+              while (g < ke) {
+                const int t = g / SPS, kk0 = g - t * SPS;
+                int kk1 = min(SPS, ke - t * SPS);
+                uint32_t i2 = st_i + (uint32_t)t;
+                while (i2 >= (uint32_t)NST) i2 -= NST;
+                const uint32_t b_base = (a16_0 + i2 * (k2StageBytes >> 4)) | ((G::WB >> 4) << 16);
+                if (j > 0 && !slipped && pn > 0 && g < l3_at && t * SPS + kk1 > l3_at) kk1 = l3_at - t * SPS;   // stop at the probe point
+#pragma unroll 8
+                for (int kk = kk0; kk < kk1; ++kk) {
+                  const int gg = t * SPS + kk;
+                  mma2_ts_lh(dbuf, tmem + (uint32_t)(gg >> 4) * 256 + (uint32_t)(gg & 15) * 8, b_base + kk * 128, kDescHi128, idesc_l2, gg > 0);
+                }
+                g = t * SPS + kk1;
+                if (kk1 == SPS || g == KS) mma2_commit_mc(empty0 + 8 * i2, kBoth);
+                if (j > 0 && !slipped && pn > 0 && g == l3_at) {
+                  const uint32_t bar = smem_u32(&bars->act2_ready[pb0]);
+                  const uint32_t ph = pb0 ? ph_act2_1 : ph_act2_0;
+                  if (pkind0 == 2 && mbar_test_wait(bar, ph & 1)) {
+                    fence_after_sync();
+                    const uint64_t bd = w3desc0 + (uint64_t)(pw0 >> 4);
+                    for (int kk = 0; kk < pk0; ++kk) {
+                      const uint64_t d = bd + (uint64_t)(kk * 16);
+                      mma2_ts_lh(pd0 + (uint32_t)(kk & 3) * 16, pa0 + kk * 8, (uint32_t)d, (uint32_t)(d >> 32), idesc_l3, kk > 3);
+                    }
+                    mma2_commit_mc(smem_u32(&bars->l3_full[pb0]), kBoth);
+                    if (pl0) mma2_commit_mc(smem_u32(&bars->w3_empty), kBoth);
+                    slipped = true;
+                  }
+                }
               }
-              if (sg + nsg == l2_stages) mma2_commit_mc(smem_u32(&bars->acc2_full[b]), kBoth);
+              if (ke == KS) mma2_commit_mc(smem_u32(&bars->acc2_full[b]), kBoth);
+            }
+            slipped = __any_sync(0xffffffffu, slipped);
+            if (slipped) {   // book-keeping of pump(), warp-uniform
+              if (pb0) { ++ph_act2_1; ++l3_issued1; } else { ++ph_act2_0; ++l3_issued0; }
+              pb0 = pb1; pk0 = pk1; pl0 = pl1; pkind0 = pkind1; pa0 = pa1; pd0 = pd1; pw0 = pw1;
+              --pn;
             }
             __syncwarp();
-            for (int t = 0; t < nsg; ++t) advance();
-            sg += nsg;
+            ks = ke;
             pump(false);
           }
+          for (int t = 0; t < l2_stages; ++t) advance();
           DBX_TRACE(130 + j);
           push(b, dbuf, dbuf + 64, (uint32_t)(j * 128 * 16), 8, j == n_l2 - 1, 2);
         }
       }
       flush_all();
     }
-  } else {
+  } else if (warp >= 2 && warp < 6) {
     // =========================== epilogue (warps 2..5, both CTAs) ===========================
     const int g = warp & 3;
     const int row = g * 32 + lane;
@@ -897,14 +959,19 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(smem_u32(&bars->l3_full[b]), ph_l3[b] & 1);
         ++ph_l3[b];
         fence_after_sync();
-        uint32_t v[16];
-        tmem_ld16(daddr, v);
+        // The output layer's k-steps accumulate round-robin into FOUR 16-column accumulators: an N = 16 MMA lasts a few
+        // cycles, so a single dependent chain of 8 (16) of them ran at the pipe's accumulate latency (~100 cycles each,
+        // ~900 cycles of an in-order tensor pipe per chunk); the four partial sums are added here.
+        uint32_t v[32], v2[32];
+        tmem_ld32(daddr, v);
+        tmem_ld32(daddr + 32, v2);
         wait_ld();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(smem_u32(&bars->l3_drained[b]), 0);   // the leader's MMA warp waits for both CTAs
 #pragma unroll
-        for (int i = 0; i < kMaxC; ++i) logit[i] += __uint_as_float(v[i]);
+        for (int i = 0; i < kMaxC; ++i)
+          logit[i] += (__uint_as_float(v[i]) + __uint_as_float(v[16 + i])) + (__uint_as_float(v2[i]) + __uint_as_float(v2[16 + i]));
       };
 
       for (int c = 0; c < n_l1; ++c) {
@@ -1072,7 +1139,7 @@ long long* g_trace_buf = nullptr;
 // with the same key (a repeated predict call encodes nothing).
 struct FusedPlan {
   const void* ws = nullptr; size_t ws_bytes = 0;
-  int64_t B = -1, ns = -1; int variant = 0;
+  int64_t B = -1, ns = -1; int variant = 0, kd = 0;
   CUtensorMap tmX, tmW1[2], tmW2[2], tmW3[2];
 };
 
@@ -1106,7 +1173,7 @@ static bool shape_supported(const dbx_model* m) {
 }
 
 constexpr int kSmem1 = kStages * kStageBytes + kW3Bytes + 2 * kBiasFloats * 4 + (int)sizeof(Barriers) + 1024;
-constexpr int kSmem2 = k2Stages * k2StageBytes + kW3Bytes / 2 + 2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024;
+constexpr int kSmem2 = 196608 + kW3Bytes / 2 + 2 * kBiasFloats * 4 + (int)sizeof(Barriers2) + 1024;   // 3 x 64 KB or 6 x 32 KB of stages
 
 // single-CTA kernel (a lone 128-row tile: a CTA pair would idle its second half)
 static int launch_fused1(FusedState* fs, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
@@ -1126,22 +1193,29 @@ static int launch_fused1(FusedState* fs, const CUtensorMap& tmX, const CUtensorM
 }
 
 // CTA-pair kernel (cta_group::2): the default
-static int launch_fused2(FusedState* fs, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
+static int launch_fused2(FusedState* fs, int kd, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
                          const CUtensorMap& tmW3, const FusedParams& p, cudaStream_t st) {
+  const int np = opt().fused_np == 2 ? 2 : 1;
   if (!fs->attr_set[1]) {
-    DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
     fs->attr_set[1] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.NC * 2));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(k2Threads);
   cfg.dynamicSmemBytes = (size_t)kSmem2;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel, tmX, tmW1, tmW2, tmW3, p));
+  if (kd == 128 && np == 1) DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<128, 1>, tmX, tmW1, tmW2, tmW3, p));
+  else if (kd == 128) DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<128, 2>, tmX, tmW1, tmW2, tmW3, p));
+  else if (np == 1) DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<64, 1>, tmX, tmW1, tmW2, tmW3, p));
+  else DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<64, 2>, tmX, tmW1, tmW2, tmW3, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -1224,7 +1298,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   const int64_t ns = samples_per_launch(fs, n, Q, CM);
 
   // ---- workspace: X bf16 | W16 [ns,P16] | B32 [ns,PB] | partials
-  const int K0p = (int)round_up(K0, 8);
+  const int K0p = (int)round_up(K0, 64);   // whole 64-wide k-blocks: the pad columns hold zeros (the pair kernel reads X through a 3-D view)
   const size_t x_b = round_up((size_t)B * K0p * 2, 1024);
   const size_t w_b = round_up((size_t)ns * m->P16 * 2, 1024);
   const size_t b_b = round_up((size_t)ns * m->PB * 4, 1024);
@@ -1254,8 +1328,14 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
 
   // ---- tensor maps (cached: the workspace layout is a function of B and ns)
   FusedPlan& pl = fs->plan;
-  if (pl.ws != m->fused_ws.ptr || pl.ws_bytes != m->fused_ws.bytes || pl.B != B || pl.ns != ns || pl.variant != variant) {
-    {
+  const int kd = (two_cta && opt().fused_kd == 64) ? 64 : 128;
+  if (pl.ws != m->fused_ws.ptr || pl.ws_bytes != m->fused_ws.bytes || pl.B != B || pl.ns != ns || pl.variant != variant || pl.kd != kd) {
+    if (two_cta) {
+      // X [B, K0p] seen as (64 k, rows, k-block): one box = KD/64 K-major SW128 tiles of 128 rows
+      uint64_t d[3] = {64, (uint64_t)B, (uint64_t)(K0p / 64)}, s[2] = {(uint64_t)K0p * 2, 128};
+      uint32_t b[3] = {64u, 128u, (uint32_t)(kd / 64)};
+      if (!make_tmap_bf16(&pl.tmX, X16, 3, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X (3-D view) failed"); return -1; }
+    } else {
       uint64_t d[2] = {(uint64_t)K0, (uint64_t)B}, s[1] = {(uint64_t)K0p * 2};
       uint32_t b[2] = {64u, 128};
       if (!make_tmap_bf16(&pl.tmX, X16, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
@@ -1267,15 +1347,27 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
         uint32_t b[3] = {64, 64, 1};
         return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B);
       };
-      if (!make_w(&pl.tmW1[i], dl[0])) { set_err("tensor map W1 failed"); return -1; }
-      if (!make_w(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0])) { set_err("tensor map W2 failed"); return -1; }
+      // pair kernel: the Keras (fan_in, fan_out) kernel seen as (64 n, k, n-block, sample); a box spans `kbox` k rows of `nblk` n-blocks
+      auto make_w4 = [&](CUtensorMap* tm, const Layer* L, uint32_t kbox, uint32_t nblk) {
+        uint64_t d[4] = {64, (uint64_t)L->w_rows, (uint64_t)cdiv(L->w_cols_pad, 64), (uint64_t)ns};
+        uint64_t sb[3] = {(uint64_t)L->w_cols_pad * 2, 128, (uint64_t)m->P16 * 2};
+        uint32_t b[4] = {64, kbox, nblk, 1};
+        return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 4, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B);
+      };
+      if (two_cta) {
+        if (!make_w4(&pl.tmW1[i], dl[0], (uint32_t)kd, 2)) { set_err("tensor map W1 (4-D view) failed"); return -1; }
+        if (!make_w4(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0], kd == 128 ? 256u : 128u, 1)) { set_err("tensor map W2 (4-D view) failed"); return -1; }
+      } else {
+        if (!make_w(&pl.tmW1[i], dl[0])) { set_err("tensor map W1 failed"); return -1; }
+        if (!make_w(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0])) { set_err("tensor map W2 failed"); return -1; }
+      }
       // last layer's kernel in blocked8 order viewed as rows of 64 bf16: CTA r of a pair fetches rows [r*H/8, (r+1)*H/8)
       uint64_t d[3] = {64, (uint64_t)(Lout->w_rows * Lout->w_cols_pad / 64), (uint64_t)ns};
       uint64_t sb[2] = {128, (uint64_t)m->P16 * 2};
       uint32_t b[3] = {64, (uint32_t)(H / 8), 1};
       if (!make_tmap_bf16(&pl.tmW3[i], W16buf[i] + Lout->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_NONE)) { set_err("tensor map W3 failed"); return -1; }
     }
-    pl.ws = m->fused_ws.ptr; pl.ws_bytes = m->fused_ws.bytes; pl.B = B; pl.ns = ns; pl.variant = variant;
+    pl.ws = m->fused_ws.ptr; pl.ws_bytes = m->fused_ws.bytes; pl.B = B; pl.ns = ns; pl.variant = variant; pl.kd = kd;
   }
   // the last layer's kernel goes out in tcgen05 core-matrix order (one bulk copy per sample)
   TensorTable tab = m->table;
@@ -1342,6 +1434,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
     p.w3 = W16 + Lout->w16_off; p.P16 = m->P16; p.w3_bytes = (int)(Lout->w_rows * Lout->w_cols_pad * 2);
     p.chunk = (int)ci; p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
     p.trace = nullptr; p.trace_only = (unsigned)opt().fused_trace_only;
+    p.l3_at = (int)opt().fused_l3at;
     if (opt().fused_trace) {
       static long long* tb = nullptr;
       if (!tb) cudaMalloc(&tb, 8 * 31208);
@@ -1349,7 +1442,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
       p.trace = tb; g_trace_buf = tb;
     }
     prof_begin(st);
-    const int rc = two_cta ? launch_fused2(fs, pl.tmX, pl.tmW1[bsel], pl.tmW2[bsel], pl.tmW3[bsel], p, st)
+    const int rc = two_cta ? launch_fused2(fs, kd, pl.tmX, pl.tmW1[bsel], pl.tmW2[bsel], pl.tmW3[bsel], p, st)
                            : launch_fused1(fs, pl.tmX, pl.tmW1[bsel], pl.tmW2[bsel], p, st);
     if (rc) return -1;
     prof_end(st, (double)m->flops * (double)B * nc);
