@@ -33,6 +33,7 @@ struct Options {
   long long fused_order = -1;       // -1 = by shape; 0 = [q][s] contiguous ranges; 1 = [s][q] round-robin
   long long fused_ns = 0;           // samples per fused launch (0 = by shape)
   long long fused_l3at = 16;        // CTA-pair kernel: layer-2 k-step at which the previous chunk's output-layer MMAs are slipped in (0 = after the chunk)
+  long long fused_stream = 1;       // fused path: sampler and fused kernel of a chunk run concurrently, gated by ready flags (0 = one event per chunk)
   long long fused_np = 1;           // CTA-pair kernel: TMA producer warps (2 = even / odd stages from two threads)
   long long fused_kd = 128;         // CTA-pair kernel: k-depth of a layer-1 TMA stage (128 = 3 x 64 KB stages, 64 = 6 x 32 KB)
   long long fused_trace = 0, fused_trace_only = 0;   // in-kernel clock probes of one cluster (tools/trace_fused.py)

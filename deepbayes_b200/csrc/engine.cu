@@ -41,7 +41,7 @@ static const OptEntry kOptTable[] = {
   {"NO_DIRECT_CONV", &Options::no_direct_conv}, {"NO_POOL_FUSE", &Options::no_pool_fuse}, {"NO_IBP_TC", &Options::no_ibp_tc},
   {"IBP_OVERLAP", &Options::ibp_overlap}, {"IBP_PRIO", &Options::ibp_prio}, {"GENERIC_OVERLAP", &Options::generic_overlap},
   {"FUSED_OVERLAP", &Options::fused_overlap}, {"FUSED_PRIO", &Options::fused_prio}, {"FUSED_KERNEL", &Options::fused_kernel},
-  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
+  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"FUSED_STREAM", &Options::fused_stream}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
 };
 static void options_from_env(Options& o) {
   o = Options();

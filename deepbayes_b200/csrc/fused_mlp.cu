@@ -66,6 +66,8 @@ struct FusedParams {
   int chunk;                   // index of this launch within the call (order 1 keeps its running sums across launches)
   int order;                   // v4: 0 = [q][s] contiguous ranges, 1 = [s][q] round-robin with running sums in `partial`
   unsigned long long* visited; // v4 order 1: per cluster, bit q set when the cluster wrote its (cluster, q) slice
+  const unsigned int* ready;   // stream mode: ready[k] != 0 once sub-chunk k of the launch's samples has been drawn (null: all drawn before the launch)
+  int sub0, subc;              // sub-chunk 0 holds samples [0, sub0), sub-chunk k >= 1 samples [sub0 + (k-1)*subc, sub0 + k*subc)
   int l3_at;                   // pair kernel: k-step of a layer-2 chunk at which the previous chunk's output-layer MMAs may be slipped in (0 = never)
   unsigned trace_only;            // 0 = all probes, else up to four probe ids, one per byte (a probe costs ~180 cycles on the warp that takes it)
   long long* trace;            // debug timeline of block 0 (null in production): [0]=count, then (id, clock) pairs
@@ -92,6 +94,31 @@ extern __shared__ __align__(1024) uint8_t fused_smem_raw[];
 #else
 #define DBX_STAGE_FENCE() do {} while (0)
 #endif
+
+// Stream mode: the sampler of a chunk runs CONCURRENTLY with the fused kernel that consumes it (side stream, launched
+// first); after each sub-chunk of samples a one-thread kernel publishes ready[k] (the kernel boundary before it makes the
+// sampler's writes visible).  A producer warp acquires the flag of a unit's sample before its first copy of that sample's
+// weights; the copies read global memory through the async proxy, hence the proxy fence after the acquire.
+__device__ __forceinline__ void wait_sample_ready(const FusedParams& p, int s, int& ready_upto, int lane) {
+  if (p.ready == nullptr) return;
+  const int sub = s < p.sub0 ? 0 : 1 + (s - p.sub0) / p.subc;
+  if (sub <= ready_upto) return;
+  const unsigned int* f = p.ready + sub;
+  unsigned int v = 0, spins = 0;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v == 0) {
+      __nanosleep(200);
+      if (++spins > (1u << 24)) { if (lane == 0) printf("fused kernel: sample %d never became ready (block %d)\n", s, blockIdx.x); __trap(); }
+    }
+  } while (v == 0);
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  __syncwarp();
+  ready_upto = sub;
+}
+__global__ void flag_set_kernel(unsigned int* flag) {
+  if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory"); }
+}
 
 // debug timeline (block 0 only): each traced warp appends (id, clock) to its own lane of the
 // buffer with a private counter -- no atomics, so the probe costs a clock read and two stores.
@@ -155,9 +182,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // in uniform registers); one elected lane issues the copies.
     uint32_t it = 0;
     uint32_t w3_n = 0, unit_n = 0;
+    int ready_upto = -1;
     for (long long u = u0; u < u1; ++u, ++unit_n) {
       const int q = (int)(u / p.ns), s = (int)(u - (long long)q * p.ns);
       const int m0 = (q * CM + (int)rank) * 128;
+      wait_sample_ready(p, s, ready_upto, lane);
       {
         const uint32_t b = unit_n & 1;
         mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
@@ -624,10 +653,12 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // warp 6 the odd ones (a stage costs the issuing thread ~600 cycles, see K2; two threads keep a ring of 32 KB stages fed).
     const uint32_t pi = warp == 0 ? 0u : 1u;
     uint32_t it = 0, w3_n = 0, unit_n = 0;
+    int ready_upto = -1;
     for (long long u = u0; u < u1; u += u_step, ++unit_n) {
       int q, s;
       decode(u, q, s);
       const int m0 = (q * CM + (int)rank) * 128;
+      wait_sample_ready(p, s, ready_upto, lane);
       if (pi == 0) {
         const uint32_t b = unit_n & 1;
         mbar_wait(smem_u32(&bars->bias_empty[b]), ((unit_n >> 1) & 1) ^ 1);
@@ -1152,6 +1183,7 @@ struct FusedState {
   bool used = false;   // ev_entry holds the end of the previous call's device work
   bool consumed_rec[2] = {false, false};          // ev_consumed[b] was recorded by a previous call ...
   size_t lay_x = 0, lay_w = 0, lay_b = 0;         // ... whose workspace layout was this
+  bool lay_stream = false;
   cudaEvent_t ev_entry = nullptr, ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr;
   FusedPlan plan;
@@ -1295,7 +1327,17 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   const int CM = two_cta ? 2 : 1;
   const int T = (int)cdiv(B, 128);
   const int Q = (int)cdiv(T, CM);
-  const int64_t ns = samples_per_launch(fs, n, Q, CM);
+  // stream mode (default): ONE fused launch per chunk of up to 1024 samples runs concurrently with the sampler that feeds
+  // it, gated by per-sub-chunk flags (wait_sample_ready) -- a short call (the per-rank share of a sample-sharded predict,
+  // SURVEY 8(e)) exposes only its first 16 samples of sampling and has no launch boundaries inside
+  const bool overlap = opt().fused_overlap != 0;
+  const bool stream = overlap && opt().fused_stream != 0 && opt().fused_ns == 0;
+  const int64_t per_sample_b = (int64_t)m->P16 * 2 + (int64_t)m->PB * 4;
+  const int64_t ns = stream ? std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 1024), ((int64_t)3 << 29) / per_sample_b))
+                            : samples_per_launch(fs, n, Q, CM);
+  constexpr int kMaxSub = 72;
+  const int sub0 = (int)std::min<int64_t>(ns, 16);
+  const int subc = (int)std::min<int64_t>(128, std::max<int64_t>(32, round_up(cdiv(ns, 8), 4)));
 
   // ---- workspace: X bf16 | W16 [ns,P16] | B32 [ns,PB] | partials
   const int K0p = (int)round_up(K0, 64);   // whole 64-wide k-blocks: the pad columns hold zeros (the pair kernel reads X through a 3-D view)
@@ -1310,13 +1352,20 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   if (opt().fused_order >= 0) order = (order_ok && opt().fused_order != 0) ? 1 : 0;
   const size_t part_b = round_up(std::max((size_t)NCmax * maxseg * CM * 128 * 32 * 4,
                                           order ? (size_t)NCmax * Q * CM * 128 * 32 * 4 + (size_t)NCmax * 8 : (size_t)0), 1024);
-  const size_t need = x_b + 2 * (w_b + b_b) + part_b;
+  const size_t flag_b = 1024;   // 2 x kMaxSub flags, keeps the 1024-byte alignment of what follows
+  const size_t need = x_b + 2 * (w_b + b_b) + part_b + flag_b;
   if (m->fused_ws.bytes < need) {
+    if (fs->used) cudaDeviceSynchronize();   // the old workspace may still be in use by a side stream
     if (ensure_ws(m->fused_ws, need)) return -1;
-    if (cudaMemsetAsync(m->fused_ws.ptr, 0, need, st) != cudaSuccess) return -1;  // pad columns stay zero
+    if (cudaMemsetAsync(m->fused_ws.ptr, 0, m->fused_ws.bytes, st) != cudaSuccess) return -1;  // pad columns and ready flags start at zero
+    if (cudaEventRecord(fs->ev_in, st) != cudaSuccess || cudaStreamWaitEvent(fs->side, fs->ev_in, 0) != cudaSuccess) return -1;
     fs->plan.ws = nullptr;
+    fs->used = false; fs->consumed_rec[0] = fs->consumed_rec[1] = false;
   }
+  // ready flags FIRST: their place must not depend on the call's sizes (they are zero whenever no chunk is in flight)
   char* wp = (char*)m->fused_ws.ptr;
+  unsigned int* flags[2] = {(unsigned int*)wp, (unsigned int*)wp + kMaxSub};
+  wp += flag_b;
   __nv_bfloat16* X16 = (__nv_bfloat16*)wp; wp += x_b;
   __nv_bfloat16* W16buf[2]; float* B32buf[2];
   for (int i = 0; i < 2; ++i) { W16buf[i] = (__nv_bfloat16*)wp; wp += w_b; B32buf[i] = (float*)wp; wp += b_b; }
@@ -1380,7 +1429,6 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   }
 
   // overlap: sampling runs one chunk ahead on the side stream (option FUSED_OVERLAP=0 disables)
-  const bool overlap = opt().fused_overlap != 0;
   cudaStream_t sst = overlap ? fs->side : st;
   if (overlap) {
     // Sampling does not depend on this call's input, only on the previous call having finished with the weight
@@ -1389,7 +1437,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
     // Same workspace layout as the previous call: each weight buffer only has to wait for ITS last consumer, so the
     // first chunk of this call is drawn while the previous call's last chunk is still in the fused kernel
     // (back-to-back predict calls pipeline; a call that ends with a device->host read does not see this).
-    const bool same_layout = fs->used && fs->lay_x == x_b && fs->lay_w == w_b && fs->lay_b == b_b;
+    const bool same_layout = fs->used && fs->lay_x == x_b && fs->lay_w == w_b && fs->lay_b == b_b && fs->lay_stream == stream;
     if (same_layout) {
       for (int b = 0; b < 2; ++b)
         if (fs->consumed_rec[b] && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
@@ -1406,7 +1454,21 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
     const int64_t c0 = ci * ns;
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     if (overlap && ci >= 2 && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
-    if (launch_sample_bf16(m, tab, src, c0, nc, W16buf[b], B32buf[b], sst, m->PB)) return -1;
+    if (!stream) {
+      if (launch_sample_bf16(m, tab, src, c0, nc, W16buf[b], B32buf[b], sst, m->PB)) return -1;
+    } else {
+      // sub-chunks in sample order, each followed by its ready flag (the fused kernel of this chunk is launched AFTER these,
+      // so even if the two streams shared one hardware queue the flags would be set before it could spin on them)
+      int k = 0;
+      for (int o = 0; o < nc; ++k) {
+        const int cnt = std::min(nc - o, k == 0 ? sub0 : subc);
+        if (launch_sample_bf16(m, tab, src, c0 + o, cnt, W16buf[b] + (int64_t)o * m->P16, B32buf[b] + (int64_t)o * m->PB, sst, m->PB)) return -1;
+        flag_set_kernel<<<1, 32, 0, sst>>>(flags[b] + k);
+        g_launches.fetch_add(1);
+        o += cnt;
+      }
+      if (cudaGetLastError() != cudaSuccess) { set_err("flag launch failed"); return -1; }
+    }
     if (overlap && cudaEventRecord(fs->ev_sampled[b], sst) != cudaSuccess) return -1;
     return 0;
   };
@@ -1416,7 +1478,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
     const int bsel = (int)(ci & 1);
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     if (ci + 1 < nchunks && sample_chunk(ci + 1)) return -1;   // next chunk's weights, concurrently
-    if (overlap && cudaStreamWaitEvent(st, fs->ev_sampled[bsel], 0) != cudaSuccess) return -1;
+    if (overlap && !stream && cudaStreamWaitEvent(st, fs->ev_sampled[bsel], 0) != cudaSuccess) return -1;
     __nv_bfloat16* W16 = W16buf[bsel];
 
     FusedParams p = {};
@@ -1435,6 +1497,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
     p.chunk = (int)ci; p.order = order; p.visited = (unsigned long long*)((char*)partial + (size_t)NCmax * Q * CM * 128 * 32 * 4);
     p.trace = nullptr; p.trace_only = (unsigned)opt().fused_trace_only;
     p.l3_at = (int)opt().fused_l3at;
+    p.ready = stream ? flags[bsel] : nullptr; p.sub0 = sub0; p.subc = subc;
     if (opt().fused_trace) {
       static long long* tb = nullptr;
       if (!tb) cudaMalloc(&tb, 8 * 31208);
@@ -1463,13 +1526,14 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
       if (cudaGetLastError() != cudaSuccess) { set_err("finish launch failed"); return -1; }
     }
     if (overlap) {
+      if (stream && cudaMemsetAsync(flags[bsel], 0, kMaxSub * sizeof(unsigned int), st) != cudaSuccess) return -1;   // for the buffer's next user
       if (cudaEventRecord(fs->ev_consumed[bsel], st) != cudaSuccess) return -1;
       fs->consumed_rec[bsel] = true;
     }
   }
   if (cudaEventRecord(fs->ev_entry, st) != cudaSuccess) return -1;
   fs->used = true;
-  fs->lay_x = x_b; fs->lay_w = w_b; fs->lay_b = b_b;
+  fs->lay_x = x_b; fs->lay_w = w_b; fs->lay_b = b_b; fs->lay_stream = stream;
   if (!overlap) fs->consumed_rec[0] = fs->consumed_rec[1] = false;
   return 1;
 }
