@@ -88,12 +88,15 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs ~100 ms before its first row
+    and samples every 20 ms, while K steps of the 8-GPU strong split last ~15 ms -- so the sampler is started during the
+    pre-heat (the same steps, back to back with the timed ones) and `mark()` notes where the timed region begins; if fewer
+    than 3 rows fall inside it, the rows of the last second of pre-heat are used as well (`window` says which)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_mark, self.t_end = [], None, index, None, None
 
     def start(self):
         try:
@@ -107,29 +110,42 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t_mark = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t_end is None:
+            self.end()
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(2)
         except Exception:
             self.proc.kill()
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        inside = [r for (t, r) in self.rows if t0 <= t <= self.t_end + 0.03]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [r for (t, r) in self.rows if t0 - 1.0 <= t <= self.t_end + 0.03]
+            window = "timed region + the last second of pre-heat (identical steps, back to back)"
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in inside:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        busy = sm[len(sm) // 4:] or sm   # skip the ramp at the start of the timed region
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -341,14 +357,15 @@ def run_config2(args, c):
         _barrier(c)
         est = _max_over_ranks(c, [a.elapsed_time(b) / warm])[0]
         pre = int(min(20000, math.ceil(args.preheat * 1e3 / max(est, 1e-3)))) if args.preheat > 0 else 0
+        clocks.start()
         for _ in range(pre):
             step(i); i += 1
         _barrier(c)
         evs = [torch_.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        clocks.start()
         launches0 = _lib.launch_count()
         lib.dbx_profile(1)
         _barrier(c)
+        clocks.mark()
         t0 = time.perf_counter()
         for k in range(args.steps):
             evs[k].record()
@@ -356,6 +373,7 @@ def run_config2(args, c):
         evs[args.steps].record()
         host_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         _barrier(c)
+        clocks.end()
         res["ms"] = evs[0].elapsed_time(evs[args.steps]) / args.steps
         per = np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)])
         res["quart"] = {"min": float(per.min()), "median": float(np.median(per)), "max": float(per.max()),
@@ -592,17 +610,19 @@ def run_other(args, c):
     path = eng.last_path()
     # warm-up / pre-heat without the profiler, then the timed steps with it
     steps = args.steps
-    ms_w, _, _, pre, nxt = timed_steps(c, step, 1, warm, args.preheat, first_index=1)
     clocks = ClockSampler(torch.cuda.current_device()); clocks.start()
+    ms_w, _, _, pre, nxt = timed_steps(c, step, 1, warm, args.preheat, first_index=1)
     launches0 = _lib.launch_count()
     lib.dbx_profile(1)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     _barrier(c)
+    clocks.mark()
     for k in range(steps):
         evs[k].record()
         step(nxt + k)
     evs[steps].record()
     _barrier(c)
+    clocks.end()
     ms = _max_over_ranks(c, [evs[0].elapsed_time(evs[steps]) / steps])[0]
     pms, pfl, pn = _profile_read(lib)
     lib.dbx_profile(0)
