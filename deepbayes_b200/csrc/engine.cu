@@ -41,7 +41,7 @@ static const OptEntry kOptTable[] = {
   {"NO_DIRECT_CONV", &Options::no_direct_conv}, {"NO_POOL_FUSE", &Options::no_pool_fuse}, {"NO_IBP_TC", &Options::no_ibp_tc},
   {"IBP_OVERLAP", &Options::ibp_overlap}, {"IBP_PRIO", &Options::ibp_prio}, {"GENERIC_OVERLAP", &Options::generic_overlap},
   {"FUSED_OVERLAP", &Options::fused_overlap}, {"FUSED_PRIO", &Options::fused_prio}, {"FUSED_KERNEL", &Options::fused_kernel},
-  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"FUSED_STREAM", &Options::fused_stream}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
+  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"NO_F32W_WIDE", &Options::no_f32w_wide}, {"FUSED_STREAM", &Options::fused_stream}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
 };
 static void options_from_env(Options& o) {
   o = Options();
@@ -573,8 +573,9 @@ static inline int grid_for(int64_t total, int block = 256) {
 // ---------------------------------------------------------------------------------------
 
 int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
-                       float* B32, cudaStream_t st, int64_t pb_stride, const bool* skip) {
+                       float* B32, cudaStream_t st, int64_t pb_stride, const bool* skip, int64_t w16_stride) {
   if (pb_stride <= 0) pb_stride = m->PB;
+  if (w16_stride <= 0) w16_stride = m->P16;
   const int nblk = (int)((m->P + 3) / 4);
   BlockRanges rg; rg.n = 0;
   const bool philox = !src.stored && !src.eps;
@@ -589,7 +590,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
       if (lo > cursor) { rg.lo[rg.n] = cursor; rg.hi[rg.n] = lo; ++rg.n; }
       dim3 grid((unsigned)std::min<int64_t>(cdiv((hi - lo + 1) / 2, 256), 148 * 4), (unsigned)cdiv(nc, kSamplesPerThread));
       DBX_LAUNCH(sample_bf16_fast_kernel, grid, 256, 0, st, m->mu, m->sigma, src.inflate, src.seed, src.s0 + c0, nc, lo, hi,
-                 tab.dst_off[i] - tab.src_off[i], W16, m->P16);
+                 tab.dst_off[i] - tab.src_off[i], W16, w16_stride);
       cursor = hi;
     }
   }
@@ -612,7 +613,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
     DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
                (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
                src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, m->slab_stride, tab, rg, W16,
-               m->P16, B32, pb_stride);
+               w16_stride, B32, pb_stride);
   }
   return 0;
 }
@@ -647,9 +648,43 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   const int64_t C = m->out_feat;
   const bool overlap = kBf16 && sst != nullptr;
   const int nwb = overlap ? 2 : 1;
+  // Stored posteriors in bf16 mode: large Dense kernels are NOT copied to bf16 first -- dense_tc_f32w_kernel reads them
+  // from the fp32 slab by TMA and rounds them inside the SM (gemm_tc.cu).  DBX_NO_F32W=1 restores the two-pass path.
+  // (Batches above 384 rows: every 128-row tile converts the same fp32 block again, and one conversion pass to bf16 + the
+  // CTA-pair GEMM wins -- 7.6 vs 11.2 ms at B = 1024, 4.9 vs 5.9 ms at 512, equal at 384, 3.6 vs 3.1 ms at 256 for 1000
+  // samples of config 3.)
+  bool skip_tensor[DBX_MAX_TENSORS] = {};
+  bool layer_f32w[64] = {};
+  bool any_f32w = false;
+  if (kBf16 && !opt().no_tc && src.stored && m->layers.size() <= 64 && B <= 384) {
+    for (int li = 0; li < (int)m->layers.size(); ++li) {
+      if (!f32w_layer_ok(m, li)) continue;
+      const Layer& L = m->layers[li];
+      for (int ti = 0; ti < m->table.n; ++ti)
+        if (!m->table.is_bias[ti] && m->table.src_off[ti] == (int32_t)L.w_off) { skip_tensor[ti] = true; layer_f32w[li] = true; any_f32w = true; }
+    }
+  }
+  // ... and then the bf16 copy of a sample holds only the remaining (small) kernels: a compact layout, so that a chunk
+  // can span thousands of samples (launch boundaries drain the HBM pipeline: 40 chunks x 3 launches cost config 3 ~8 %)
+  TensorTable tabc = m->table;
+  int64_t p16_eff = m->P16;
+  int64_t w16_off_c[64];
+  for (int li = 0; li < (int)m->layers.size() && li < 64; ++li) w16_off_c[li] = m->layers[li].w16_off;
+  if (any_f32w) {
+    int64_t off = 0;
+    for (int ti = 0; ti < tabc.n; ++ti) {
+      if (tabc.is_bias[ti]) continue;
+      if (skip_tensor[ti]) continue;
+      for (int li = 0; li < (int)m->layers.size() && li < 64; ++li)
+        if (m->layers[li].has_w && m->table.src_off[ti] == (int32_t)m->layers[li].w_off) w16_off_c[li] = off;
+      tabc.dst_off[ti] = (int32_t)off;
+      off += round_up((int64_t)tabc.rows[ti] * tabc.cols_pad[ti], 64);
+    }
+    p16_eff = std::max<int64_t>(round_up(off, 64), 64);
+  }
   // per-sample workspace bytes
   const size_t act_b = (size_t)B * m->max_feat * sizeof(T);
-  const size_t w1_b = kBf16 ? ((size_t)m->P16 * 2 + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
+  const size_t w1_b = kBf16 ? ((size_t)p16_eff * 2 + (size_t)m->PB * 4) : (src.stored ? 0 : (size_t)m->P * 4);
   const size_t w_b = w1_b * nwb;
   // bf16 mode: Conv2D layers run as im2col + tcgen05 GEMM and need a column buffer
   size_t col_b = 0;
@@ -674,7 +709,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   const size_t xin1_b = kBf16 ? round_up((size_t)B * m->in_feat * 2, 256) : 0;
   const size_t xin_b = xin1_b * ((kBf16 && src.stored) ? kXRep : 1) + col0_b;
   int64_t ns = (int64_t)std::max<size_t>(1, (ws_budget_bytes() - std::min(ws_budget_bytes(), xin_b)) / per);
-  ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
+  ns = std::min<int64_t>(std::min<int64_t>(ns, n), any_f32w ? 2048 : 256);
   if (ensure_ws(m->ws, xin_b + (size_t)ns * per + 16384)) return 1;
   char* p = (char*)m->ws.ptr;
   T* xin = (T*)p; p += xin_b - col0_b;
@@ -684,11 +719,11 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   T* act1 = (T*)p; p += round_up((size_t)ns * act_b, 256);
   float* logits = (float*)p; p += round_up((size_t)ns * B * C * 4, 256);
   T* Wc = (T*)p;
-  float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * m->P16 * 2, 256)) : nullptr;
+  float* B32 = kBf16 ? (float*)(p + round_up((size_t)ns * p16_eff * 2, 256)) : nullptr;
   T* Wc2[2] = {Wc, Wc}; float* B32b[2] = {B32, B32};
   if (overlap) {
-    const size_t one = round_up((size_t)ns * m->P16 * 2, 256) + round_up((size_t)ns * m->PB * 4, 256);
-    Wc2[1] = (T*)(p + one); B32b[1] = (float*)(p + one + round_up((size_t)ns * m->P16 * 2, 256));
+    const size_t one = round_up((size_t)ns * p16_eff * 2, 256) + round_up((size_t)ns * m->PB * 4, 256);
+    Wc2[1] = (T*)(p + one); B32b[1] = (float*)(p + one + round_up((size_t)ns * p16_eff * 2, 256));
   }
   __nv_bfloat16* colbuf = (__nv_bfloat16*)(p + round_up((size_t)ns * w_b, 256) + 1024);
 
@@ -704,23 +739,6 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
   if (sink.kind == 1 && !sink.accumulate)
     DBX_LAUNCH(zero_u64_kernel, grid_for(B), 256, 0, st, sink.counts, B);
 
-  // Stored posteriors in bf16 mode: large Dense kernels are NOT copied to bf16 first -- dense_tc_f32w_kernel reads them
-  // from the fp32 slab by TMA and rounds them inside the SM (gemm_tc.cu).  DBX_NO_F32W=1 restores the two-pass path.
-  bool skip_tensor[DBX_MAX_TENSORS] = {};
-  bool layer_f32w[64] = {};
-  bool any_f32w = false;
-  // (Batches above 384 rows: every 128-row tile converts the same fp32 block again, and one conversion pass to bf16 + the
-  // CTA-pair GEMM wins -- 7.6 vs 11.2 ms at B = 1024, 4.9 vs 5.9 ms at 512, equal at 384, 3.6 vs 3.1 ms at 256 for 1000
-  // samples of config 3.)
-  if (kBf16 && use_tc && src.stored && m->layers.size() <= 64 && B <= 384) {
-    for (int li = 0; li < (int)m->layers.size(); ++li) {
-      if (!f32w_layer_ok(m, li)) continue;
-      const Layer& L = m->layers[li];
-      for (int ti = 0; ti < m->table.n; ++ti)
-        if (!m->table.is_bias[ti] && m->table.src_off[ti] == (int32_t)L.w_off) { skip_tensor[ti] = true; layer_f32w[li] = true; any_f32w = true; }
-    }
-  }
-
   for (int64_t c0 = 0; c0 < n; c0 += ns) {
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     // ---- weights of this chunk
@@ -735,7 +753,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
         const int dn = (int)std::min<int64_t>(ns, n - d0);
         cudaStream_t ds = overlap ? sst : st;
         if (overlap && cj >= 2) DBX_CUDA(cudaStreamWaitEvent(ds, m->ibp_ev[3 + b], 0));
-        if (launch_sample_bf16(m, m->table, src, d0, dn, (__nv_bfloat16*)Wc2[b], B32b[b], ds, 0, any_f32w ? skip_tensor : nullptr)) return 1;
+        if (launch_sample_bf16(m, tabc, src, d0, dn, (__nv_bfloat16*)Wc2[b], B32b[b], ds, 0, any_f32w ? skip_tensor : nullptr, p16_eff)) return 1;
         if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[1 + b], ds));
         return 0;
       };
@@ -745,7 +763,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
         DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[1 + wb], 0));
       }
       Wc = Wc2[wb]; B32 = B32b[wb];
-      Wbase = Wc; w_sstride = m->P16; Bbase = B32; b_sstride = m->PB;
+      Wbase = Wc; w_sstride = p16_eff; Bbase = B32; b_sstride = m->PB;
     } else if (src.stored) {
       Wbase = (const T*)m->slab; w_sstride = m->slab_stride; rows = src.idx ? src.idx + c0 : nullptr; row0 = src.j0 + c0;
       Bbase = m->slab; b_sstride = m->slab_stride;
@@ -765,7 +783,7 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
       if (L.kind == DBX_FLATTEN) continue;
       if (pooled_next) { pooled_next = false; continue; }      // this MaxPool ran in the previous convolution's epilogue
       const bool last = (li == m->last_weighted);
-      const int64_t woff = kBf16 ? L.w16_off : L.w_off;
+      const int64_t woff = kBf16 ? w16_off_c[std::min(li, 63)] : L.w_off;
       const int64_t boff = kBf16 ? L.b32_off : L.b_off;
       const int ldw = (int)(kBf16 ? L.w_cols_pad : L.w_cols);
       const int act = last ? DBX_ACT_LINEAR : L.act;  // last activation applied by the sink

@@ -113,7 +113,7 @@ void prof_end(cudaStream_t st, double flops);
 // padded bf16, biases -> B32 [nc,PB] fp32): Gaussian draw (injected eps or Philox) or conversion
 // of stored samples.  Defined in engine.cu.
 int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, int64_t c0, int nc, __nv_bfloat16* W16,
-                       float* B32, cudaStream_t st, int64_t pb_stride = 0, const bool* skip = nullptr);
+                       float* B32, cudaStream_t st, int64_t pb_stride = 0, const bool* skip = nullptr, int64_t w16_stride = 0);
 
 // fused_mlp.cu: returns 1 if the tcgen05 fused path handled the request, 0 if the shape is
 // not supported by it (caller uses the generic kernels), <0 on error.

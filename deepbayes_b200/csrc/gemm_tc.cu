@@ -517,14 +517,26 @@ dense_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 //   warps 6-9  epilogue of tile i (bias, activation, stores) while the main loop of tile i+1 runs
 // 97 KB of shared memory per CTA -> two persistent CTAs per SM.
 // =======================================================================================
-constexpr int kFLand = 3, kFOp = 2;
-constexpr int kFLandBytes = 16384;   // [64 k][64 n] fp32, as TMA delivers it (no swizzle, 256 B rows)
-constexpr int kFOpBytes = 24576;     // A block 16 KB + converted W block 8 KB
-constexpr int kFNT = 64;
+// What bounds the kernel is SHARED-MEMORY bandwidth, not HBM: per fp32 byte of W the SM moved 1 B (TMA landing) + 1 B
+// (converter read) + 0.5 B (converter write) + 0.5 B (MMA B read) + 1 B (TMA write of the [128 x 64] A block, re-fetched
+// for every 64-column tile) + 1 B (MMA A read) = 5 B; at 5.6 TB/s and the 1.48 GHz the power cap leaves that is the
+// 128 B/clk/SM limit (bench: 0.78 of the HBM peak; ncu at full clock saw 0.89).  Hence NT = 128: 128-column tiles
+// (512-byte slab rows per TMA box, A traffic per W byte halved) and A boxes of 64 rows when the batch has at most 64
+// (the other 64 rows of the tile are never written; their accumulator rows are never read): 3.75 B per W byte.
+template <int NT> struct FCfg {
+  static constexpr int LandBytes = 64 * NT * 4;      // [64 k][NT n] fp32, as TMA delivers it (no swizzle, NT*4-byte rows)
+  static constexpr int WopBytes = NT * 128;          // converted [64 k x NT n] bf16: NT/64 MN-major SW128 blocks of 8 KB
+  static constexpr int OpBytes = 16384 + WopBytes;   // A block 16 KB + converted W
+  static constexpr int Land = NT == 128 ? 4 : 3;
+  static constexpr int Op = 2;
+  static constexpr int CtasPerSm = NT == 128 ? 1 : 2;
+  static constexpr int Smem = Land * LandBytes + Op * OpBytes;
+};
+constexpr int kFLandMax = 4, kFOp = 2;
 constexpr int kFThreads = 320;       // producer, issuer, 4 converter warps, 4 epilogue warps
 
 struct __align__(8) FBarriers {
-  uint64_t land_full[kFLand], land_empty[kFLand];
+  uint64_t land_full[kFLandMax], land_empty[kFLandMax];
   uint64_t op_full[kFOp], op_empty[kFOp];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
@@ -535,14 +547,20 @@ struct FGemmParams {
   const int32_t* w_rows; long long w_row0;   // sample -> slab row (third TMA coordinate)
   int ns, tiles_n, tiles_m;
   int a_rep;                                 // > 0: A is the same for every sample and exists a_rep times (copy s % a_rep is read)
+  int a_box_bytes;                           // bytes one A box delivers (64 or 128 rows of 128 B)
 };
 
 // PERSISTENT: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened (sample, m tile, n tile)
-// list (n fastest: CTAs running side by side read neighbouring 256-byte segments of the same slab rows), and all three
+// list (n fastest: CTAs running side by side read neighbouring segments of the same slab rows), and all three
 // rings run across tile boundaries, so the HBM stream never drains between tiles.
-template <int kAct>
-__global__ void __launch_bounds__(kFThreads, 2)
+template <int kAct, int NT>
+__global__ void __launch_bounds__(kFThreads, FCfg<NT>::CtasPerSm)
 dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const FGemmParams fp) {
+  using C = FCfg<NT>;
+  constexpr int kFLand = C::Land;
+  constexpr int kFLandBytes = C::LandBytes;
+  constexpr int kFOpBytes = C::OpBytes;
+  constexpr int kFNT = NT;
   const GemmParams& p = fp.g;
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_land = smem_u32(smem);
@@ -564,7 +582,7 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<128>(smem_u32(&bars->tmem_slot));
+  if (warp == 1) tmem_alloc<2 * NT>(smem_u32(&bars->tmem_slot));
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
   fence_before_sync();
   __syncthreads();
@@ -602,7 +620,7 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(smem_u32(&bars->op_empty[o]), oph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->op_full[o]);
-          mbar_expect_tx(fb, 16384);
+          mbar_expect_tx(fb, (uint32_t)fp.a_box_bytes);
           tma_load_3d(s_op + o * kFOpBytes, &tmA, fb, kb * 64, m0, fp.a_rep ? s % fp.a_rep : s);
         }
         __syncwarp();
@@ -636,8 +654,9 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp < 6) {
-    // ---- converter: landed fp32 block -> bf16 B operand (row k = 128 B, 16-byte chunk c stored at c ^ (k & 7))
+    // ---- converter: landed fp32 block -> bf16 B operand: 64-column blocks of 8 KB, row k = 128 B, 16-byte chunk c at c ^ (k & 7)
     const int tc = tid - 64;                      // 0..127
+    constexpr int kChunks = NT / 8;               // 16-byte bf16 chunks per k row
     uint32_t g = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
@@ -647,13 +666,13 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint8_t* src = smem + l * kFLandBytes;
         uint8_t* dst = op_smem + o * kFOpBytes + 16384;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 64 * kChunks / 128; ++i) {
           const int u = i * 128 + tc;
-          const int k = u >> 3, c = u & 7;        // row k, 16-byte bf16 chunk c = columns 8c..8c+7
-          const float4 a = *reinterpret_cast<const float4*>(src + k * 256 + c * 32);
-          const float4 b = *reinterpret_cast<const float4*>(src + k * 256 + c * 32 + 16);
+          const int k = u / kChunks, c = u % kChunks;        // row k, 16-byte bf16 chunk c = columns 8c..8c+7
+          const float4 a = *reinterpret_cast<const float4*>(src + k * (NT * 4) + c * 32);
+          const float4 b = *reinterpret_cast<const float4*>(src + k * (NT * 4) + c * 32 + 16);
           const uint4 v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-          *reinterpret_cast<uint4*>(dst + (k >> 3) * 1024 + (k & 7) * 128 + ((c ^ (k & 7)) << 4)) = v;
+          *reinterpret_cast<uint4*>(dst + (c >> 3) * 8192 + (k >> 3) * 1024 + (k & 7) * 128 + (((c & 7) ^ (k & 7)) << 4)) = v;
         }
         fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
         __syncwarp();
@@ -675,37 +694,43 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const float* bias = p.bias + brow * p.b_sstride + p.b_off;
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
-      uint32_t v[kFNT];
-      tmem_ld32(tmem + lane_base + ab * kFNT, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld32(tmem + lane_base + ab * kFNT + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-      wait_ld();
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));   // the accumulator is in registers: the next tile may start
-      if (gm < p.M) {
-        if (p.out16) {
-          __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + n0;
 #pragma unroll
-          for (int q8 = 0; q8 < kFNT / 8; ++q8) {
-            const int c = n0 + q8 * 8;
-            if (c + 8 <= p.N) {
-              uint32_t w[4];
+      for (int hb = 0; hb < NT / 64; ++hb) {
+        uint32_t v[64];
+        tmem_ld32(tmem + lane_base + ab * kFNT + hb * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(tmem + lane_base + ab * kFNT + hb * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        wait_ld();
+        if (hb == NT / 64 - 1) {
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));   // the accumulator is in registers: the next tile may start
+        }
+        const int nh = n0 + hb * 64;
+        if (gm < p.M) {
+          if (p.out16) {
+            __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + nh;
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
-                                   act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
-              *reinterpret_cast<uint4*>(dst + q8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-            } else {
-              for (int i = 0; i < 8; ++i)
-                if (c + i < p.N) dst[q8 * 8 + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
+            for (int q8 = 0; q8 < 8; ++q8) {
+              const int c = nh + q8 * 8;
+              if (c + 8 <= p.N) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
+                                     act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+                *reinterpret_cast<uint4*>(dst + q8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              } else {
+                for (int i = 0; i < 8; ++i)
+                  if (c + i < p.N) dst[q8 * 8 + i] = __float2bfloat16_rn(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + i]) + bias[c + i]));
+              }
             }
-          }
-        } else {
-          float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
+          } else {
+            float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N;
 #pragma unroll
-          for (int i = 0; i < kFNT; ++i) {
-            const int c = n0 + i;
-            if (c < p.N) dst[c] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + bias[c]);
+            for (int i = 0; i < 64; ++i) {
+              const int c = nh + i;
+              if (c < p.N) dst[c] = act_fixed<kAct>(p.act, __uint_as_float(v[i]) + bias[c]);
+            }
           }
         }
       }
@@ -713,7 +738,7 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<128>(tmem);
+  if (warp == 1) tmem_dealloc<2 * NT>(tmem);
 }
 
 
@@ -1385,42 +1410,51 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
                          long long o16_sstride, int ld16, float* out32, long long o32_sstride, cudaStream_t st) {
   if (!g_tc_ok || !get_encode_fn()) return 1;
   if ((N & 3) || (w_off & 3) || (slab_stride & 3) || (lda & 7) || ((uintptr_t)slab & 15)) return 1;
+  const bool wide = (N % 128 == 0) && !opt().no_f32w_wide;   // 128-column tiles (see FCfg)
+  const int NT = wide ? 128 : 64;
+  const int a_rows = (M <= 64) ? 64 : 128;                    // rows one A box delivers
   CUtensorMap tmA, tmW;
   {
     // a_rep > 0: the layer input is shared by all samples and replicated a_rep times a_sstride apart, so that the CTAs
     // of different samples do not all pull the same L2 lines; a_rep == 0: one input per sample
     uint64_t d[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(a_rep ? a_rep : ns)}, sb[2] = {(uint64_t)lda * 2, (uint64_t)a_sstride * 2};
-    uint32_t b[3] = {64, 128, 1};
+    uint32_t b[3] = {64, (uint32_t)a_rows, 1};
     if (!make_tmap_bf16(&tmA, (void*)A, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
     uint64_t d[3] = {(uint64_t)N, (uint64_t)K, (uint64_t)slab_rows}, sb[2] = {(uint64_t)N * 4, (uint64_t)slab_stride * 4};
-    uint32_t b[3] = {64, 64, 1};
+    uint32_t b[3] = {(uint32_t)NT, 64, 1};
     if (!make_tmap_f32(&tmW, (void*)(slab + w_off), 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   }
   FGemmParams fp = {};
   GemmParams& p = fp.g;
-  p.M = M; p.N = N; p.K = K; p.NT = kFNT;
+  p.M = M; p.N = N; p.K = K; p.NT = NT;
   p.a_shared = a_rep ? 1 : 0; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
   fp.a_rep = a_rep;
+  fp.a_box_bytes = a_rows * 128;
   fp.w_rows = w_rows; fp.w_row0 = w_row0;
-  fp.ns = ns; fp.tiles_n = (int)cdiv(N, kFNT); fp.tiles_m = (int)cdiv(M, 128);
-  const int smem = kFLand * kFLandBytes + kFOp * kFOpBytes + (int)sizeof(FBarriers) + 1024;
+  fp.ns = ns; fp.tiles_n = (int)cdiv(N, NT); fp.tiles_m = (int)cdiv(M, 128);
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
   }
   const long long total = (long long)ns * fp.tiles_m * fp.tiles_n;
-  dim3 grid((unsigned)std::min<long long>(total, 2LL * num_sms));   // two resident CTAs per SM
-  auto go = [&](auto kern) -> int {
+  auto go = [&](auto kern, int smem_b, int ctas_per_sm) -> int {
+    const int smem = smem_b + (int)sizeof(FBarriers) + 1024;
+    dim3 grid((unsigned)std::min<long long>(total, (long long)ctas_per_sm * num_sms));   // persistent: the resident CTAs
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
     kern<<<grid, kFThreads, smem, st>>>(tmA, tmW, fp);
     return 0;
   };
   const int ka = act_class(act);
-  if (ka == 1 ? go(dense_tc_f32w_kernel<1>) : ka == 0 ? go(dense_tc_f32w_kernel<0>) : go(dense_tc_f32w_kernel<-1>)) return 1;
+  int rc;
+  if (wide) rc = ka == 1 ? go(dense_tc_f32w_kernel<1, 128>, FCfg<128>::Smem, 1) : ka == 0 ? go(dense_tc_f32w_kernel<0, 128>, FCfg<128>::Smem, 1)
+                                                                                         : go(dense_tc_f32w_kernel<-1, 128>, FCfg<128>::Smem, 1);
+  else rc = ka == 1 ? go(dense_tc_f32w_kernel<1, 64>, FCfg<64>::Smem, 2) : ka == 0 ? go(dense_tc_f32w_kernel<0, 64>, FCfg<64>::Smem, 2)
+                                                                                   : go(dense_tc_f32w_kernel<-1, 64>, FCfg<64>::Smem, 2);
+  if (rc) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
