@@ -199,7 +199,10 @@ sample_bf16_kernel(const float* __restrict__ mu, const float* __restrict__ sigma
 // pairs in registers for kSamplesPerThread consecutive samples (blockIdx.y covers that many), so the fp32 posterior is
 // read from L2 once per group instead of once per sample (8 B/parameter/sample was 4x the bf16 bytes written).
 constexpr int kSamplesPerThread = 4;
-__global__ void __launch_bounds__(256)
+#ifndef DBX_SAMPLER_MIN_BLOCKS
+#define DBX_SAMPLER_MIN_BLOCKS 1   // (6 = a 40-register cap so that three blocks fit beside a fused CTA: it spills 88 bytes and config 5 went 86 -> 130 ms)
+#endif
+__global__ void __launch_bounds__(256, DBX_SAMPLER_MIN_BLOCKS)
 sample_bf16_fast_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, float inflate, uint64_t seed,
                         int64_t s0, int nc, int blk_lo, int blk_hi, int dst_delta, __nv_bfloat16* __restrict__ W16,
                         int64_t P16) {

@@ -1331,7 +1331,10 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   // it, gated by per-sub-chunk flags (wait_sample_ready) -- a short call (the per-rank share of a sample-sharded predict,
   // SURVEY 8(e)) exposes only its first 16 samples of sampling and has no launch boundaries inside
   const bool overlap = opt().fused_overlap != 0;
-  const bool stream = overlap && opt().fused_stream != 0 && opt().fused_ns == 0;
+  // ... when the fused kernel is the bulk of the work (>= 6 row-tile groups per sample).  With one or two tiles per sample
+  // (config 5: 128 inputs) the SAMPLER is the bottleneck, and a fused kernel that sits on every SM for the whole chunk,
+  // waiting for samples, leaves it two resident blocks per SM instead of eight: 119 ms against 86 ms for 100k samples.
+  const bool stream = overlap && opt().fused_stream != 0 && opt().fused_ns == 0 && (Q >= 6 || opt().fused_stream == 2);
   const int64_t per_sample_b = (int64_t)m->P16 * 2 + (int64_t)m->PB * 4;
   const int64_t ns = stream ? std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 1024), ((int64_t)3 << 29) / per_sample_b))
                             : samples_per_launch(fs, n, Q, CM);

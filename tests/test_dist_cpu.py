@@ -1,7 +1,8 @@
 """world_size-2 gloo test of the sharding logic: each rank evaluates its
 contiguous range of global sample ids, ONE all-reduce combines the moment buffers, and the
 result equals the unsharded sum.  The per-rank compute is stood in for by the oracle here
-(CPU container); the GPU version of the same test is tests/test_gpu_parity.py::test_sharded."""
+(CPU container); on GPUs the same split is checked by tests/test_gpu_baseline_shapes.py::test_rank_shards_equal_one_rank
+(one GPU) and by bench.py under torchrun ("shard_check": N ranks == 1 rank on the same global sample ids)."""
 import os
 import sys
 

@@ -202,3 +202,76 @@ def test_rank_shards_equal_one_rank(oracle):
             t1 += a.cpu().numpy(); t2 += b.cpu().numpy()
         np.testing.assert_allclose(t1 / n, one1 / n, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(t2 / n, one2 / n, rtol=1e-5, atol=1e-6)
+
+
+def test_stream_mode_equals_chunked_launches(oracle, dbx_opt):
+    """Stream mode (one fused launch per chunk, sampler running concurrently behind per-sub-chunk ready flags) against the
+    event-ordered path (FUSED_STREAM=0: sampler of a chunk finished before its fused launch), the CTA-pair kernel's 64 KB
+    TMA stages against the 32 KB ones, and one / two producer warps: the same sums up to the order the per-cluster
+    slices are added in."""
+    dims, B, n = [784, 512, 512, 10], 2048, 96      # 8 row-tile pairs per sample: stream mode is the default from 6 up
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    ref1, ref2 = eng.predict_sums(x, n, seed=5, s0=40, mode="bf16", second_moment=True)
+    assert eng.last_path() == "fused_tcgen05"
+    ref1, ref2 = ref1.cpu().numpy() / n, ref2.cpu().numpy() / n
+    for opts in ({"FUSED_STREAM": 0}, {"FUSED_KD": 64}, {"FUSED_NP": 2}, {"FUSED_KD": 64, "FUSED_NP": 2}, {"FUSED_L3AT": 0}):
+        for k, v in opts.items():
+            dbx_opt(k, v)
+        a1, a2 = eng.predict_sums(x, n, seed=5, s0=40, mode="bf16", second_moment=True)
+        for k in opts:
+            dbx_opt(k, None)
+        np.testing.assert_allclose(a1.cpu().numpy() / n, ref1, rtol=2e-6, atol=2e-7, err_msg=str(opts))
+        np.testing.assert_allclose(a2.cpu().numpy() / n, ref2, rtol=2e-6, atol=2e-7, err_msg=str(opts))
+    # back-to-back calls reuse the weight buffers and their ready flags: results must not depend on what ran before
+    for n2 in (8, 200, 17):
+        dbx_opt("FUSED_STREAM", 2)      # forced also for a batch this small (2 row-tile pairs)
+        b1, _ = eng.predict_sums(x[:300], n2, seed=9, s0=3, mode="bf16")
+        dbx_opt("FUSED_STREAM", 0)
+        c1, _ = eng.predict_sums(x[:300], n2, seed=9, s0=3, mode="bf16")
+        dbx_opt("FUSED_STREAM", None)
+        np.testing.assert_allclose(b1.cpu().numpy() / n2, c1.cpu().numpy() / n2, rtol=2e-6, atol=2e-7)
+
+
+def test_f32w_wide_tiles_equal_narrow(oracle, dbx_opt):
+    """dense_tc_f32w_kernel with 128-column tiles / 64-row A boxes against its 64-column form: the same MMAs in the same k
+    order, so the sums are bit-identical."""
+    dims, S = [784, 1024, 1024, 10], 6
+    L, eng, mean, std = _mlp(dims, oracle, sigma_scale=0.3)
+    eng.set_gaussian(mean, std)
+    eng.set_samples(eng.sample(S, seed=3, s0=0))
+    for B in (64, 100, 33):
+        x = oracle.synthetic_x((B, dims[0]), seed=B)
+        a1, a2 = eng.predict_stored_sums(x, S, j0=0, mode="bf16", second_moment=True)
+        assert eng.last_path() == "generic_tc"
+        dbx_opt("NO_F32W_WIDE", 1)
+        b1, b2 = eng.predict_stored_sums(x, S, j0=0, mode="bf16", second_moment=True)
+        dbx_opt("NO_F32W_WIDE", None)
+        np.testing.assert_array_equal(a1.cpu().numpy(), b1.cpu().numpy())
+        np.testing.assert_array_equal(a2.cpu().numpy(), b2.cpu().numpy())
+
+
+def test_peer_window_allreduce_one_rank():
+    """dbx_comm_* on a world of one rank: the kernel's copy-in / flag / rank-ordered sum path with a single window (the
+    N-rank exchange is exercised by bench.py under torchrun, which asserts it against a one-rank recomputation)."""
+    import torch
+    from deepbayes_b200 import distributed as dd
+    c = dd.PeerComm(0, 1, torch.cuda.current_device(), 1 << 17)
+    try:
+        c.connect([c.handle()])
+        a = torch.arange(4096 * 10, dtype=torch.float32, device="cuda") * 0.5
+        b = torch.full((4096 * 10,), 3.0, dtype=torch.float32, device="cuda")
+        wa, wb = a.clone(), b.clone()
+        for _ in range(5):      # epochs alternate the two slots of the window
+            c.allreduce(a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(a, wa) and torch.equal(b, wb) and not c.timed_out()
+        c.allreduce(a)
+        torch.cuda.synchronize()
+        assert torch.equal(a, wa)
+        from deepbayes_b200._lib import DbxError
+        with pytest.raises(DbxError):
+            c.allreduce(torch.zeros(1 << 18, dtype=torch.float32, device="cuda"))   # larger than the window
+    finally:
+        c.close()
