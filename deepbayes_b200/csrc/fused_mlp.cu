@@ -130,6 +130,8 @@ __global__ void flag_set_kernel(unsigned int* flag) {
     }                                                                                         \
   } while (0)
 
+// (a register cap of 128 -- no spills -- would let a third sampler block run beside this CTA: measured SLOWER, config 5
+// 85.1 -> 88.5 ms; the extra sampler warps take issue slots from the epilogue)
 template <int CM>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
