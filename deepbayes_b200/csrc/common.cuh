@@ -26,6 +26,7 @@ struct Options {
   long long persist_min_tiles = 296;
   long long no_f32w = 0;            // stored posteriors: convert the slab chunk to bf16 first
   long long no_f32w_wide = 0;       // dense_tc_f32w_kernel: 64-column tiles, two CTAs per SM (the round-1 shape) instead of 128-column tiles
+  long long no_shared_a = 0;        // a small layer on the call's shared input: per-sample GEMMs instead of dense_tc_shareda_kernel (8 samples per tile)
   long long no_direct_conv = 0;     // Conv2D as im2col + GEMM
   long long no_pool_fuse = 0;       // separate max-pool launch
   long long no_ibp_tc = 0;          // interval forward: two GEMMs + combine per hidden layer

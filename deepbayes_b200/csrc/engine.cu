@@ -41,7 +41,7 @@ static const OptEntry kOptTable[] = {
   {"NO_DIRECT_CONV", &Options::no_direct_conv}, {"NO_POOL_FUSE", &Options::no_pool_fuse}, {"NO_IBP_TC", &Options::no_ibp_tc},
   {"IBP_OVERLAP", &Options::ibp_overlap}, {"IBP_PRIO", &Options::ibp_prio}, {"GENERIC_OVERLAP", &Options::generic_overlap},
   {"FUSED_OVERLAP", &Options::fused_overlap}, {"FUSED_PRIO", &Options::fused_prio}, {"FUSED_KERNEL", &Options::fused_kernel},
-  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"NO_F32W_WIDE", &Options::no_f32w_wide}, {"FUSED_STREAM", &Options::fused_stream}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
+  {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"NO_SHARED_A", &Options::no_shared_a}, {"NO_F32W_WIDE", &Options::no_f32w_wide}, {"FUSED_STREAM", &Options::fused_stream}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
 };
 static void options_from_env(Options& o) {
   o = Options();
@@ -827,7 +827,12 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
           bool col_ok = true;
           if (!(cb == col0 && col0_done)) col_ok = im2col_launch(A16, cur_ss, cb, col_ss, shared ? 1 : nc, (int)B, L, Kp, st) == 0;
           if (cb == col0 && col_ok) col0_done = true;      // the input is the same for every chunk of this call
-          if (col_ok)
+          // the call's own input under eight samples' kernels at a time (config 4's first convolution)
+          if (col_ok && shared && !last &&
+              dense_tc_shareda_launch(cb, Kp, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc, (int)Mrows, L.units, (int)L.w_rows,
+                                      Bbase, b_sstride, boff, act, (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units, st) == 0)
+            done_tc = true;
+          else if (col_ok)
             done_tc = dense_tc_launch(cb, col_ss, Kp, shared, (const __nv_bfloat16*)Wbase + woff, w_sstride, ldw, nc,
                                       (int)Mrows, L.units, (int)L.w_rows, Bbase, b_sstride, boff, act,
                                       last ? nullptr : (__nv_bfloat16*)bufs[bi], B * L.out_feat, L.units,

@@ -130,6 +130,9 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
                          long long slab_rows, long long w_off, const int32_t* w_rows, long long w_row0, int ns, int M, int N, int K,
                          const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
                          long long o16_sstride, int ld16, float* out32, long long o32_sstride, cudaStream_t st);
+int dense_tc_shareda_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wbase, long long w_sstride_elems, int ldw, int ns, int M,
+                            int N, int K, const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
+                            long long o16_sstride, int ld16, cudaStream_t st);
 bool conv_tc_eligible(const Layer& L);
 bool conv_tc_pool_eligible(const Layer& L, const Layer& P);
 int conv_tc_launch(const __nv_bfloat16* in, long long in_sstride, int in_shared, const __nv_bfloat16* W16, long long w_sstride_elems,

@@ -1459,6 +1459,211 @@ int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, i
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// =======================================================================================
+// A layer whose INPUT is shared by all posterior samples and whose GEMM is tiny in K and N (config 4's first convolution:
+// im2col of the call's input, K = 27, N = 32 output channels): run per sample it is one 128 x 32 x 32 tile per 1.5 us of
+// barrier round trips and reads the im2col rows once per SAMPLE (7.7 us per sample, 27 % of config 4).  Here EIGHT samples
+// share a tile: their kernels sit side by side as the N dimension, B = [K x (8 x 32)], so a 128-row block of A is read once
+// for eight samples and feeds one M = 128, N = 256 MMA per 16 k; what remains is the write of the outputs
+// (M x 32 bf16 per sample), eight 64-byte row segments per thread and tile.
+//   warp 0  producer: W box [32 n x 32 k x 8 samples] per sample group (SWIZZLE_64B, lands as eight MN-major blocks of
+//           2 KB = the N = 256 operand with LBO 2048), A boxes [32 k x 128 rows] (SWIZZLE_64B K-major) through a 4-deep ring
+//   warp 1  MMA issuer: two K = 16 steps per tile, two 256-column TMEM accumulators
+//   warps 2-5 epilogue: bias + activation + bf16 pack, 4 x 16-byte stores per (row, sample)
+// Persistent CTAs over contiguous ranges of the [group][m tile] list (a group's kernels are loaded once per CTA).
+// =======================================================================================
+constexpr int kSAStages = 4, kSAThreads = 192, kSAGroup = 8;
+struct SAParams {
+  int M, K, ns, tiles_m, groups, act;
+  const float* bias; long long b_sstride, b_off;
+  __nv_bfloat16* out; long long o_sstride;   // [s][M][32]
+};
+struct __align__(8) SABarriers {
+  uint64_t full[kSAStages], empty[kSAStages];
+  uint64_t b_full[2], b_empty[2];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
+
+template <int kAct>
+__global__ void __launch_bounds__(kSAThreads, 1)
+dense_tc_shareda_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const SAParams p) {
+  __shared__ float s_bias[2][kSAGroup * 32];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_a = smem_u32(smem);                       // kSAStages x 8 KB
+  const uint32_t s_b = s_a + kSAStages * 8192;               // 2 x 16 KB
+  SABarriers* bars = (SABarriers*)(smem + kSAStages * 8192 + 2 * 16384);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long total = (long long)p.groups * p.tiles_m;
+  const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < kSAStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1);
+      mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    uint32_t it = 0, gn = 0;
+    int cur_g = -1;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int g = (int)(t / p.tiles_m), mt = (int)(t - (long long)g * p.tiles_m);
+      if (g != cur_g) {
+        const uint32_t gb = gn & 1;
+        mbar_wait(smem_u32(&bars->b_empty[gb]), ((gn >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->b_full[gb]);
+          mbar_expect_tx(fb, 16384);                          // samples past ns / rows past K arrive as zeros, counted
+          tma_load_3d(s_b + gb * 16384, &tmW, fb, 0, 0, g * kSAGroup);
+        }
+        __syncwarp();
+        cur_g = g; ++gn;
+      }
+      const uint32_t st = it % kSAStages, ph = (it / kSAStages) & 1;
+      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&bars->full[st]);
+        mbar_expect_tx(fb, 8192);
+        tma_load_2d(s_a + st * 8192, &tmA, fb, 0, mt * 128);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kHi64 = (512u >> 4) | (1u << 14) | (4u << 29);      // 8-row / 8-k groups 512 B apart, SWIZZLE_64B
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 1);
+    uint32_t it = 0, gn = 0;
+    int cur_g = -1;
+    uint32_t gb = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int g = (int)(t / p.tiles_m);
+      if (g != cur_g) {
+        gb = gn & 1;
+        mbar_wait(smem_u32(&bars->b_full[gb]), (gn >> 1) & 1);
+        cur_g = g; ++gn;
+      }
+      const bool last_of_group = (t + 1 == t_end) || ((int)((t + 1) / p.tiles_m) != g);
+      const uint32_t ab = it & 1, st = it % kSAStages, ph = (it / kSAStages) & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a_lo = (((s_a + st * 8192) & 0x3FFFF) >> 4) | (1u << 16);
+        const uint32_t b_lo = (((s_b + gb * 16384) & 0x3FFFF) >> 4) | ((2048u >> 4) << 16);   // n-blocks (samples) 2 KB apart
+        mma_ss_lh(tmem + ab * 256, a_lo, kHi64, b_lo, kHi64, idesc, 0);
+        if (p.K > 16) mma_ss_lh(tmem + ab * 256, a_lo + 2, kHi64, b_lo + 64, kHi64, idesc, 1);
+        mma_commit(smem_u32(&bars->empty[st]));
+        mma_commit(smem_u32(&bars->acc_full[ab]));
+        if (last_of_group) mma_commit(smem_u32(&bars->b_empty[gb]));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int gq = warp & 3;
+    const int row = gq * 32 + lane;
+    const int et = tid - 64;                                  // 0..127 among the epilogue threads
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    uint32_t it = 0, gn = 0;
+    int cur_g = -1;
+    uint32_t gb = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int g = (int)(t / p.tiles_m), mt = (int)(t - (long long)g * p.tiles_m);
+      if (g != cur_g) {
+        gb = gn & 1;
+        // this group's biases (the previous user of s_bias[gb] was two groups ago: every warp has passed it)
+        for (int i = et; i < kSAGroup * 32; i += 128) {
+          const int sI = g * kSAGroup + (i >> 5);
+          s_bias[gb][i] = sI < p.ns ? p.bias[(long long)sI * p.b_sstride + p.b_off + (i & 31)] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_g = g; ++gn;
+      }
+      const uint32_t ab = it & 1;
+      const int gm = mt * 128 + row;
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+#pragma unroll 2
+      for (int q = 0; q < kSAGroup; ++q) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + ab * 256 + q * 32, v);
+        wait_ld();
+        if (q == kSAGroup - 1) {
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+        }
+        const int sI = g * kSAGroup + q;
+        if (sI < p.ns && gm < p.M) {
+          const float* bq = &s_bias[gb][q * 32];
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)sI * p.o_sstride + (long long)gm * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[c4 * 8 + 2 * i]) + bq[c4 * 8 + 2 * i]),
+                                 act_fixed<kAct>(p.act, __uint_as_float(v[c4 * 8 + 2 * i + 1]) + bq[c4 * 8 + 2 * i + 1]));
+            dst[c4] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// returns 0 when the layer was launched, 1 when the shape does not fit (the caller uses the per-sample GEMM)
+int dense_tc_shareda_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wbase, long long w_sstride_elems, int ldw, int ns, int M,
+                            int N, int K, const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,
+                            long long o16_sstride, int ld16, cudaStream_t st) {
+  if (!g_tc_ok || !get_encode_fn() || opt().no_shared_a) return 1;
+  if (N != 32 || K > 32 || K < 1 || ldw != 32 || ld16 != 32 || ns < 2 || (lda & 7) || (o16_sstride & 7) || ((uintptr_t)out16 & 15) ||
+      (w_sstride_elems & 7) || ((uintptr_t)Wbase & 15) || M < 128)
+    return 1;
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, sb[1] = {(uint64_t)lda * 2};
+    uint32_t b[2] = {32, 128};
+    if (!make_tmap_bf16(&tmA, (void*)A, 2, d, sb, b, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
+  {
+    uint64_t d[3] = {32, (uint64_t)K, (uint64_t)ns}, sb[2] = {(uint64_t)ldw * 2, (uint64_t)w_sstride_elems * 2};
+    uint32_t b[3] = {32, 32, (uint32_t)kSAGroup};
+    if (!make_tmap_bf16(&tmW, (void*)Wbase, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
+  SAParams p = {};
+  p.M = M; p.K = K; p.ns = ns; p.tiles_m = (int)cdiv(M, 128); p.groups = (int)cdiv(ns, kSAGroup); p.act = act;
+  p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.out = out16; p.o_sstride = o16_sstride;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+  }
+  // (asks for more than half an SM's shared memory: the kernel allocates all 512 TMEM columns, so two CTAs must never share an SM)
+  const int smem = std::max(kSAStages * 8192 + 2 * 16384 + (int)sizeof(SABarriers) + 1024, 118 * 1024);
+  const long long total = (long long)p.groups * p.tiles_m;
+  dim3 grid((unsigned)std::min<long long>(total, num_sms));
+  auto go = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+    kern<<<grid, kSAThreads, smem, st>>>(tmA, tmW, p);
+    return 0;
+  };
+  const int ka = act_class(act);
+  if (ka == 1 ? go(dense_tc_shareda_kernel<1>) : ka == 0 ? go(dense_tc_shareda_kernel<0>) : go(dense_tc_shareda_kernel<-1>)) return 1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 // dynamic shared memory of conv_tc_kernel.  The kernel tensor stays resident when it is at most 40 KB; then, if
 // R = 128 / (Wo + kw - 1) >= 1 output rows fit the 128 accumulator rows, one input patch per tile serves all taps.
 static int conv_tc_smem(const Layer& L, int* w_res, int* patch, int* R_out, int pool = 0, int* stages_out = nullptr) {
