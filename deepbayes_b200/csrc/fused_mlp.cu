@@ -1104,23 +1104,42 @@ fused_mlp2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 
-// order 1: adds the per-(cluster, q) running sums in cluster order
-__global__ void finish4_kernel(const float* __restrict__ partial, const unsigned long long* __restrict__ visited, int NC, int Q,
-                               int CM, int B, int C, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
-  const long long total = (long long)B * C;
+// order 1: adds the per-(cluster, q) running sums in cluster order.  One thread per (input row, group of 4 floats of the
+// row's 32-float slice: sum p in [0,16), sum p^2 in [16,32)); the row's 8 threads read one 128-byte line per cluster, eight
+// independent 128-bit loads in flight per thread.  (The element-per-thread form took 27 us for B = 4096 -- 4 % of the
+// per-rank step of the 8-GPU strong split.)
+__global__ void __launch_bounds__(256)
+finish4_kernel(const float* __restrict__ partial, const unsigned long long* __restrict__ visited, int NC, int Q,
+               int CM, int B, int C, int overwrite, float* __restrict__ sum1, float* __restrict__ sum2) {
+  const long long total = (long long)B * 8;
   for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(o / C), c = (int)(o - (long long)b * C);
+    const int b = (int)(o >> 3), j = (int)(o & 7);
+    const int c0 = (j & 3) * 4;
+    const bool second = j >= 4;
+    if (c0 >= C || (second && !sum2)) continue;
     const int tile = b / 128, row = b % 128, q = tile / CM, rank = tile % CM;
-    float a1 = overwrite ? 0.f : sum1[o];
-    float a2 = (sum2 && !overwrite) ? sum2[o] : 0.f;
-    for (int k = 0; k < NC; ++k) {
-      if (!((visited[k] >> q) & 1ull)) continue;
-      const float* src = partial + ((((long long)k * Q + q) * CM + rank) * 128 + row) * 32;
-      a1 += src[c];
-      if (sum2) a2 += src[16 + c];
+    const float* base = partial + ((((long long)q) * CM + rank) * 128 + row) * 32 + j * 4;
+    const long long kstride = (long long)Q * CM * 128 * 32;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 8 <= NC; k += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[i] = ((visited[k + i] >> q) & 1ull) ? __ldcg(reinterpret_cast<const float4*>(base + (k + i) * kstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }   // cluster order
     }
-    sum1[o] = a1;
-    if (sum2) sum2[o] = a2;
+    for (; k < NC; ++k) {
+      if (!((visited[k] >> q) & 1ull)) continue;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(base + k * kstride));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* dst = (second ? sum2 : sum1) + (long long)b * C + c0;
+    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (c0 + i < C) dst[i] = (overwrite ? 0.f : dst[i]) + a[i];
   }
 }
 
@@ -1162,6 +1181,22 @@ __global__ void cast_rows_bf16_kernel(const float* __restrict__ in, __nv_bfloat1
     out[o] = __float2bfloat16_rn(k < K ? in[r * K + k] : 0.f);
   }
 }
+// K % 8 == 0 and 16-byte aligned rows: 8 elements per thread (two 128-bit loads, one 128-bit store); Kp % 8 == 0 always
+__global__ void __launch_bounds__(256)
+cast_rows_bf16_vec8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows, int K, int Kp) {
+  const int g = Kp >> 3;
+  const int64_t total = rows * g;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = o / g; const int k = (int)(o - r * g) << 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (k < K) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(in + r * K + k));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(in + r * K + k + 4));
+      v = make_uint4(tc_pack_bf16x2(a.x, a.y), tc_pack_bf16x2(a.z, a.w), tc_pack_bf16x2(b.x, b.y), tc_pack_bf16x2(b.z, b.w));
+    }
+    *reinterpret_cast<uint4*>(out + r * Kp + k) = v;
+  }
+}
 __global__ void zero_counts_kernel(unsigned long long* p, int64_t n) {
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) p[o] = 0ULL;
 }
@@ -1186,6 +1221,7 @@ struct FusedState {
   bool consumed_rec[2] = {false, false};          // ev_consumed[b] was recorded by a previous call ...
   size_t lay_x = 0, lay_w = 0, lay_b = 0;         // ... whose workspace layout was this
   bool lay_stream = false;
+  int buf_base = 0;                               // weight buffer of a call's first chunk: alternates from call to call
   cudaEvent_t ev_entry = nullptr, ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr;
   FusedPlan plan;
@@ -1283,6 +1319,16 @@ static inline int grid_for2(const FusedState* fs, int64_t total, int block = 256
 static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, int64_t B, int64_t n, const Source& src,
                             const Sink& sink, cudaStream_t st);
 
+// Stream mode (see fused_mlp_run_on): when the fused kernel is the bulk of the work, i.e. >= 6 row-tile pairs per sample.
+static bool stream_mode_for(int64_t B) {
+  if (!opt().fused_overlap || !opt().fused_stream || opt().fused_ns != 0) return false;
+  int variant = (B <= 128) ? 1 : 2;
+  if (opt().fused_kernel == 1 || opt().fused_kernel == 2) variant = (int)opt().fused_kernel;
+  const int CM = variant == 2 ? 2 : 1;
+  const int64_t Q = cdiv(cdiv(B, 128), CM);
+  return Q >= 6 || opt().fused_stream == 2;
+}
+
 // The fused kernels run on a HIGH-priority stream of the engine's own, joined with the caller's stream at both ends: the
 // sampler of the next chunk shares the SMs with them from a default-priority side stream, and at every chunk boundary the
 // next fused launch's CTA pairs then get SM slots ahead of the sampler's queued blocks (option FUSED_PRIO=0: caller's stream).
@@ -1292,7 +1338,10 @@ int fused_mlp_run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const 
   if (!get_encode_fn()) return 0;
   FusedState* fs = fused_state_of(m);
   if (!fs) return -1;
-  if (!opt().fused_prio) return fused_mlp_run_on(m, fs, x_dev, B, n, src, sink, st_user);
+  // stream mode holds ONE long fused launch per chunk: nothing is queued behind the sampler's blocks at chunk boundaries,
+  // so the priority stream buys nothing there and its two cross-stream joins cost ~10 us per call (1.5 % of the per-rank
+  // step of the 8-GPU strong split)
+  if (!opt().fused_prio || stream_mode_for(B)) return fused_mlp_run_on(m, fs, x_dev, B, n, src, sink, st_user);
   if (cudaEventRecord(fs->ev_join, st_user) != cudaSuccess || cudaStreamWaitEvent(fs->main, fs->ev_join, 0) != cudaSuccess) return -1;
   const int rc = fused_mlp_run_on(m, fs, x_dev, B, n, src, sink, fs->main);
   if (cudaEventRecord(fs->ev_done, fs->main) != cudaSuccess || cudaStreamWaitEvent(st_user, fs->ev_done, 0) != cudaSuccess) return -1;
@@ -1336,7 +1385,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   // ... when the fused kernel is the bulk of the work (>= 6 row-tile groups per sample).  With one or two tiles per sample
   // (config 5: 128 inputs) the SAMPLER is the bottleneck, and a fused kernel that sits on every SM for the whole chunk,
   // waiting for samples, leaves it two resident blocks per SM instead of eight: 119 ms against 86 ms for 100k samples.
-  const bool stream = overlap && opt().fused_stream != 0 && opt().fused_ns == 0 && (Q >= 6 || opt().fused_stream == 2);
+  const bool stream = stream_mode_for(B);
   const int64_t per_sample_b = (int64_t)m->P16 * 2 + (int64_t)m->PB * 4;
   const int64_t ns = stream ? std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 1024), ((int64_t)3 << 29) / per_sample_b))
                             : samples_per_launch(fs, n, Q, CM);
@@ -1376,7 +1425,10 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   for (int i = 0; i < 2; ++i) { W16buf[i] = (__nv_bfloat16*)wp; wp += w_b; B32buf[i] = (float*)wp; wp += b_b; }
   float* partial = (float*)wp;
 
-  cast_rows_bf16_kernel<<<grid_for2(fs, B * K0p), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
+  if ((K0 & 7) == 0 && ((uintptr_t)x_dev & 15) == 0)
+    cast_rows_bf16_vec8_kernel<<<grid_for2(fs, B * (K0p / 8)), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
+  else
+    cast_rows_bf16_kernel<<<grid_for2(fs, B * K0p), 256, 0, st>>>(x_dev, X16, B, K0, K0p);
   g_launches.fetch_add(1);
   if (cudaGetLastError() != cudaSuccess) { set_err("cast launch failed"); return -1; }
 
@@ -1443,10 +1495,8 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
     // first chunk of this call is drawn while the previous call's last chunk is still in the fused kernel
     // (back-to-back predict calls pipeline; a call that ends with a device->host read does not see this).
     const bool same_layout = fs->used && fs->lay_x == x_b && fs->lay_w == w_b && fs->lay_b == b_b && fs->lay_stream == stream;
-    if (same_layout) {
-      for (int b = 0; b < 2; ++b)
-        if (fs->consumed_rec[b] && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
-    } else if (fs->used && cudaStreamWaitEvent(sst, fs->ev_entry, 0) != cudaSuccess) return -1;
+    // (each chunk waits for its own buffer's last consumer in sample_chunk)
+    if (!same_layout && fs->used && cudaStreamWaitEvent(sst, fs->ev_entry, 0) != cudaSuccess) return -1;
     if (m->ev_posterior && cudaStreamWaitEvent(sst, m->ev_posterior, 0) != cudaSuccess) return -1;
     if (src.stored || src.eps) {   // slab / injected eps may have been produced on `st` just before this call
       if (cudaEventRecord(fs->ev_in, st) != cudaSuccess || cudaStreamWaitEvent(sst, fs->ev_in, 0) != cudaSuccess) return -1;
@@ -1454,11 +1504,14 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   }
   const int64_t nchunks = cdiv(n, ns);
   int nc_first = 1;
+  // A call's first chunk takes the buffer the PREVIOUS call's first chunk did not: back-to-back single-chunk calls (the
+  // per-rank share of a sharded predict) then draw call i+1's weights while call i's fused kernel is still reading its own.
+  const int bb = overlap ? fs->buf_base : 0;
   auto sample_chunk = [&](int64_t ci) -> int {
-    const int b = (int)(ci & 1);
+    const int b = (int)((ci + bb) & 1);
     const int64_t c0 = ci * ns;
     const int nc = (int)std::min<int64_t>(ns, n - c0);
-    if (overlap && ci >= 2 && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
+    if (overlap && fs->consumed_rec[b] && cudaStreamWaitEvent(sst, fs->ev_consumed[b], 0) != cudaSuccess) return -1;
     if (!stream) {
       if (launch_sample_bf16(m, tab, src, c0, nc, W16buf[b], B32buf[b], sst, m->PB)) return -1;
     } else {
@@ -1480,7 +1533,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   if (sample_chunk(0)) return -1;
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int64_t c0 = ci * ns;
-    const int bsel = (int)(ci & 1);
+    const int bsel = (int)((ci + bb) & 1);
     const int nc = (int)std::min<int64_t>(ns, n - c0);
     if (ci + 1 < nchunks && sample_chunk(ci + 1)) return -1;   // next chunk's weights, concurrently
     if (overlap && !stream && cudaStreamWaitEvent(st, fs->ev_sampled[bsel], 0) != cudaSuccess) return -1;
@@ -1519,7 +1572,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
       if (order) {
         if (ci == 0) nc_first = p.NC;
         if (ci + 1 == nchunks) {   // the slices carried the sums of every chunk
-          finish4_kernel<<<grid_for2(fs, B * C), 256, 0, st>>>(partial, p.visited, nc_first, Q, CM, (int)B, C, sink.accumulate ? 0 : 1,
+          finish4_kernel<<<grid_for2(fs, B * 8), 256, 0, st>>>(partial, p.visited, nc_first, Q, CM, (int)B, C, sink.accumulate ? 0 : 1,
                                                                sink.sum1, sink.sum2);
           g_launches.fetch_add(1);
         }
@@ -1539,6 +1592,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
   if (cudaEventRecord(fs->ev_entry, st) != cudaSuccess) return -1;
   fs->used = true;
   fs->lay_x = x_b; fs->lay_w = w_b; fs->lay_b = b_b; fs->lay_stream = stream;
+  if (overlap) fs->buf_base = (int)((bb + nchunks) & 1);   // the buffer after this call's last one
   if (!overlap) fs->consumed_rec[0] = fs->consumed_rec[1] = false;
   return 1;
 }
