@@ -143,7 +143,7 @@ class Optimizer(ABC):
         out, o = [], 0
         for s in self.model.weight_shapes():
             k = int(np.prod(s))
-            out.append(W[o:o + k].reshape(s))
+            out.append(W[o:o + k].reshape(s).astype(np.float64))     # np.random.normal returns float64 (optimizer.py:199-201)
             o += k
         return out
 

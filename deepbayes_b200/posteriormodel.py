@@ -78,12 +78,14 @@ class PosteriorModel:
         return s0
 
     def sample(self, inflate=1.0):
-        """posteriormodel.py:60-79.  Returns a fresh list [W0,b0,...]; the model is not touched."""
+        """posteriormodel.py:60-79.  Returns a fresh list [W0,b0,...] (float64 for Gaussian posteriors, like the reference;
+        stored samples come back in their stored dtype); the model is not touched."""
         if self.det:
             return self.model.get_weights()
         if not self.sample_based:
             W = self._engine.sample(1, self.seed, self._take_ids(1), None, inflate)
-            return _split(self.model, W[0].cpu().numpy())
+            # float64 like np.random.normal(loc=..., scale=...) at :74-75 (the values are the device's fp32 draws)
+            return [w.astype(np.float64) for w in _split(self.model, W[0].cpu().numpy())]
         index = np.random.choice(range(self.num_post_samps), p=self.frequency)  # :77
         return _split(self.model, self._slab_host[index])
 

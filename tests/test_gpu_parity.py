@@ -405,6 +405,7 @@ def test_posterior_model_api(golden_dir, oracle):
     assert np.abs(w_after[0] - pm.posterior_mean[0]).max() < 6 * pm.posterior_var[0].max()
     s = pm.sample()
     assert [a.shape for a in s] == [(784, 128), (128,), (128, 10), (10,)]
+    assert all(a.dtype == np.float64 for a in s)          # np.random.normal at posteriormodel.py:74-75 returns float64
     np.testing.assert_array_equal(pm.model.get_weights()[0], w_after[0])
     np.testing.assert_allclose(pm._predict(x), oracle.forward(L, w_after, x.reshape(6, 784)).reshape(6, 1, 10), rtol=FP32_RTOL, atol=FP32_ATOL)
     lg = pm.predict_logits(x, n=5)
@@ -464,6 +465,7 @@ def test_bbb_optimizer_api(oracle):
     np.testing.assert_array_equal(m.get_weights()[0], ws[0])         # step leaves the sample in the model (:59)
     np.testing.assert_allclose(opt.predict(x), want, rtol=FP32_RTOL, atol=FP32_ATOL)  # single forward, no sampling (:293-298)
     s = opt.sample()
+    assert all(a.dtype == np.float64 for a in s)          # optimizer.py:199-201 / bayesbybackprop.py:178-181
     sd = np.sqrt(1 / 30.0)
     assert abs(np.std(s[0]) - sd) < 0.1 * sd                          # N(0, softplus(rho)) = N(0, prior std)
     p2 = opt.forward_sample(x)                                        # Philox noise
