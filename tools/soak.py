@@ -9,7 +9,9 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 g = np.random.Generator(np.random.Philox(99))
 t0 = time.time(); it = 0
 while time.time() - t0 < budget:
-    kind = it % 3
+    kind = it % 4
+    if os.environ.get('SOAK_VERBOSE'):
+        print('it', it, 'kind', kind, 'start', flush=True)
     if kind == 0:      # MLP: IBP (fused layers) + predict (fused / generic)
         K = int(g.integers(1, 40)) * 8
         hs = [int(g.integers(1, 80)) * 8 for _ in range(int(g.integers(1, 4)))]
@@ -36,6 +38,19 @@ while time.time() - t0 < budget:
         x = g.random((B, H, W, 3)).astype(np.float32)
         s1, _ = eng.predict_sums(x, n, seed=it, mode="bf16")
         assert bool(torch.isfinite(s1).all())
+    elif kind == 3:    # stored posterior: fp32 slab through dense_tc_f32w_kernel (64- and 128-column tiles, 64- / 128-row A boxes)
+        K = int(g.integers(2, 30)) * 8
+        hs = [int(g.choice([128, 192, 256, 320, 512, 1024])) for _ in range(int(g.integers(1, 3)))]
+        layers = [db.Dense(hs[0], activation="relu", input_shape=(K,))] + [db.Dense(h, activation="relu") for h in hs[1:]] + [db.Dense(10, activation="softmax")]
+        eng = Engine(db.Sequential(layers))
+        eng.set_gaussian((g.standard_normal(eng.P) * 0.1).astype(np.float32), np.full(eng.P, 0.02, np.float32))
+        S = int(g.integers(2, 40))
+        eng.set_samples(eng.sample(S, seed=it, s0=0))
+        B = int(g.integers(9, 300))
+        x = g.random((B, K)).astype(np.float32)
+        a, _ = eng.predict_stored_sums(x, S, j0=0, mode="bf16")
+        b, _ = eng.predict_stored_sums(x, S, j0=0, mode="fp32")
+        assert float((a - b).abs().max()) / S < 2e-2
     else:              # fused MLP shapes, long runs at small batch
         H = int(g.choice([128, 256, 384, 512]))
         dims = [784, H, H, 10] if g.random() < 0.5 else [784, H, 10]
@@ -48,6 +63,10 @@ while time.time() - t0 < budget:
         c = eng.count_predicate(x, lab, n, seed=it, mode="bf16")
         assert int(c.max()) <= n
     torch.cuda.synchronize()
+    if os.environ.get('SOAK_VERBOSE'):
+        print('it', it, 'kind', kind, 'ok', round(time.time() - t0, 1), flush=True)
     del eng
     it += 1
+    if it % 500 == 0:
+        print('soak:', it, 'iterations', round(time.time() - t0, 1), 's', flush=True)
 print("soak ok:", it, "iterations in", round(time.time() - t0, 1), "s")
