@@ -63,6 +63,9 @@ Options& opt();
     DBX_CUDA(cudaGetLastError());                                          \
   } while (0)
 
+// SM count of the current device (queried once; the grid-stride kernels size their grids as a multiple of it)
+int sm_count();
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 

@@ -50,6 +50,15 @@ static void options_from_env(Options& o) {
     if (const char* v = getenv(var.c_str())) o.*(e.field) = atoll(v);
   }
 }
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 Options& opt() {
   static Options o;
   static bool init = false;
@@ -514,7 +523,7 @@ static inline void launch_accum(const float* logits, int ns, int64_t B, int C, i
   if (C <= kAccumMaxC && ns >= 32 && B <= 65535 * 16) {
     accum_block_kernel<<<(unsigned)B, 256, 0, st>>>(logits, ns, B, C, act, out_kind, wts, overwrite, sum1, sum2);
   } else {
-    accum_kernel<<<(unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(B * C, 256), 1), 148 * 16), 256, 0, st>>>(
+    accum_kernel<<<(unsigned)std::min<int64_t>(std::max<int64_t>(cdiv(B * C, 256), 1), sm_count() * 16), 256, 0, st>>>(
         logits, ns, B, C, act, out_kind, wts, overwrite, sum1, sum2);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -568,7 +577,7 @@ __global__ void zero_u64_kernel(unsigned long long* p, int64_t n) {
 
 static inline int grid_for(int64_t total, int block = 256) {
   int64_t g = cdiv(total, block);
-  return (int)std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 16);
+  return (int)std::min<int64_t>(std::max<int64_t>(g, 1), sm_count() * 16);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -591,7 +600,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
       const int lo = (tab.src_off[i] + 3) >> 2, hi = tab.src_end[i] >> 2;   // whole Philox blocks inside the tensor
       if (hi <= lo || rg.n + 2 > DBX_MAX_RANGES) continue;
       if (lo > cursor) { rg.lo[rg.n] = cursor; rg.hi[rg.n] = lo; ++rg.n; }
-      dim3 grid((unsigned)std::min<int64_t>(cdiv((hi - lo + 1) / 2, 256), 148 * 4), (unsigned)cdiv(nc, kSamplesPerThread));
+      dim3 grid((unsigned)std::min<int64_t>(cdiv((hi - lo + 1) / 2, 256), sm_count() * 4), (unsigned)cdiv(nc, kSamplesPerThread));
       DBX_LAUNCH(sample_bf16_fast_kernel, grid, 256, 0, st, m->mu, m->sigma, src.inflate, src.seed, src.s0 + c0, nc, lo, hi,
                  tab.dst_off[i] - tab.src_off[i], W16, w16_stride);
       cursor = hi;
@@ -612,7 +621,7 @@ int launch_sample_bf16(dbx_model* m, const TensorTable& tab, const Source& src, 
   if (rg.n > 0) {
     int64_t most = 0;
     for (int i = 0; i < rg.n; ++i) most = std::max<int64_t>(most, rg.hi[i] - rg.lo[i]);
-    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(most, 256), 148 * 4)), (unsigned)nc);
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(most, 256), sm_count() * 4)), (unsigned)nc);
     DBX_LAUNCH(sample_bf16_kernel, grid, 256, 0, st, m->mu, m->sigma,
                (!src.stored && src.eps) ? src.eps + c0 * m->P : nullptr, src.inflate, src.seed, src.s0 + c0, (int)m->P,
                src.stored ? m->slab : nullptr, (src.stored && src.idx) ? src.idx + c0 : nullptr, src.j0 + c0, m->slab_stride, tab, rg, W16,

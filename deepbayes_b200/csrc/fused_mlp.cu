@@ -1265,12 +1265,22 @@ static int launch_fused1(FusedState* fs, const CUtensorMap& tmX, const CUtensorM
 // CTA-pair kernel (cta_group::2): the default
 static int launch_fused2(FusedState* fs, int kd, const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
                          const CUtensorMap& tmW3, const FusedParams& p, cudaStream_t st) {
+  // The shipped library holds ONE instantiation: 64 KB stages, one producer warp.  The measured-slower geometries (32 KB
+  // stages: 39 k cycles per unit against 30.8 k; a second producer warp: no gain) are compiled only with
+  // -DDBX_FUSED_VARIANTS (tools/, A/B runs), where options FUSED_KD / FUSED_NP select them.
+#ifdef DBX_FUSED_VARIANTS
   const int np = opt().fused_np == 2 ? 2 : 1;
+#else
+  const int np = 1;
+  (void)kd;
+#endif
   if (!fs->attr_set[1]) {
     DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+#ifdef DBX_FUSED_VARIANTS
     DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
     DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
     DBX_CUDA(cudaFuncSetAttribute(fused_mlp2_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+#endif
     fs->attr_set[1] = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1282,10 +1292,14 @@ static int launch_fused2(FusedState* fs, int kd, const CUtensorMap& tmX, const C
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef DBX_FUSED_VARIANTS
   if (kd == 128 && np == 1) DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<128, 1>, tmX, tmW1, tmW2, tmW3, p));
   else if (kd == 128) DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<128, 2>, tmX, tmW1, tmW2, tmW3, p));
   else if (np == 1) DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<64, 1>, tmX, tmW1, tmW2, tmW3, p));
   else DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<64, 2>, tmX, tmW1, tmW2, tmW3, p));
+#else
+  DBX_CUDA(cudaLaunchKernelEx(&cfg, fused_mlp2_kernel<128, 1>, tmX, tmW1, tmW2, tmW3, p));
+#endif
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -1434,7 +1448,11 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
 
   // ---- tensor maps (cached: the workspace layout is a function of B and ns)
   FusedPlan& pl = fs->plan;
+#ifdef DBX_FUSED_VARIANTS
   const int kd = (two_cta && opt().fused_kd == 64) ? 64 : 128;
+#else
+  const int kd = 128;
+#endif
   if (pl.ws != m->fused_ws.ptr || pl.ws_bytes != m->fused_ws.bytes || pl.B != B || pl.ns != ns || pl.variant != variant || pl.kd != kd) {
     if (two_cta) {
       // X [B, K0p] seen as (64 k, rows, k-block): one box = KD/64 K-major SW128 tiles of 128 rows

@@ -1816,14 +1816,14 @@ int im2col_launch(const __nv_bfloat16* in, long long in_sstride, __nv_bfloat16* 
                   const Layer& L, int Kp, cudaStream_t st) {
   if (L.in_c % 8 == 0 && Kp == L.kh * L.kw * L.in_c && (in_sstride % 8) == 0 && (out_sstride % 8) == 0) {
     const long long total8 = (long long)NB * L.out_h * L.out_w * (Kp / 8);
-    dim3 grid8((unsigned)std::min<long long>(std::max<long long>(cdiv(total8, 256), 1), 148 * 32), (unsigned)ns);
+    dim3 grid8((unsigned)std::min<long long>(std::max<long long>(cdiv(total8, 256), 1), sm_count() * 32), (unsigned)ns);
     im2col_bf16_vec8_kernel<<<grid8, 256, 0, st>>>(in, in_sstride, out, out_sstride, NB, L.in_h, L.in_w, L.in_c, L.out_h,
                                                    L.out_w, L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
   }
   const long long total = (long long)NB * L.out_h * L.out_w * Kp;
-  dim3 grid((unsigned)std::min<long long>(std::max<long long>(cdiv(total, 256), 1), 148 * 32), (unsigned)ns);
+  dim3 grid((unsigned)std::min<long long>(std::max<long long>(cdiv(total, 256), 1), sm_count() * 32), (unsigned)ns);
   im2col_bf16_kernel<<<grid, 256, 0, st>>>(in, in_sstride, out, out_sstride, NB, L.in_h, L.in_w, L.in_c, L.out_h, L.out_w,
                                            L.kh, L.kw, L.sh, L.sw, L.pad_t, L.pad_l, Kp);
   g_launches.fetch_add(1, std::memory_order_relaxed);

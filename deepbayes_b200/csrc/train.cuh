@@ -445,7 +445,7 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
   for (auto* L : dl) act_total += round_up((size_t)B * L->units * 4, 256);
   const size_t pb = round_up((size_t)P * 4, 256), dzb = round_up((size_t)B * std::max<int64_t>(m->max_feat, K0) * 4, 256);
   const size_t xb = round_up((size_t)B * K0 * 4, 256), ob = round_up((size_t)B * C * 4, 256);
-  const int ublocks = 148 * 4;
+  const int ublocks = sm_count() * 4;
   const size_t need = 3 * pb + 3 * act_total + 2 * xb + 4 * dzb + (3 + 2 * (size_t)std::max(n_eps, 0)) * ob + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
   if (ensure_ws(m->ws, need)) return 1;
   char* p = (char*)m->ws.ptr;

@@ -206,8 +206,8 @@ def test_rank_shards_equal_one_rank(oracle):
 
 def test_stream_mode_equals_chunked_launches(oracle, dbx_opt):
     """Stream mode (one fused launch per chunk, sampler running concurrently behind per-sub-chunk ready flags) against the
-    event-ordered path (FUSED_STREAM=0: sampler of a chunk finished before its fused launch), the CTA-pair kernel's 64 KB
-    TMA stages against the 32 KB ones, and one / two producer warps: the same sums up to the order the per-cluster
+    event-ordered path (FUSED_STREAM=0: sampler of a chunk finished before its fused launch), the output-layer MMAs slipped
+    into the next chunk's stream or issued after it, and the two work orders: the same sums up to the order the per-cluster
     slices are added in."""
     dims, B, n = [784, 512, 512, 10], 2048, 96      # 8 row-tile pairs per sample: stream mode is the default from 6 up
     L, eng, mean, std = _mlp(dims, oracle)
@@ -216,7 +216,7 @@ def test_stream_mode_equals_chunked_launches(oracle, dbx_opt):
     ref1, ref2 = eng.predict_sums(x, n, seed=5, s0=40, mode="bf16", second_moment=True)
     assert eng.last_path() == "fused_tcgen05"
     ref1, ref2 = ref1.cpu().numpy() / n, ref2.cpu().numpy() / n
-    for opts in ({"FUSED_STREAM": 0}, {"FUSED_KD": 64}, {"FUSED_NP": 2}, {"FUSED_KD": 64, "FUSED_NP": 2}, {"FUSED_L3AT": 0}):
+    for opts in ({"FUSED_STREAM": 0}, {"FUSED_L3AT": 0}, {"FUSED_L3AT": 24}, {"FUSED_ORDER": 0}, {"FUSED_PRIO": 0, "FUSED_STREAM": 0}):
         for k, v in opts.items():
             dbx_opt(k, v)
         a1, a2 = eng.predict_sums(x, n, seed=5, s0=40, mode="bf16", second_moment=True)
