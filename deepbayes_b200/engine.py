@@ -279,6 +279,29 @@ class Engine:
                                          _ptr(probs), _ptr(W), _stream()))
         return {"loss": loss, "probs": probs, "W": W}
 
+    def bbb_train_epoch(self, x_t, labels_t, batch, mean_t, rho_t, prior_mean_t, prior_var_t, lrate, kl_weight=1.0, seed=0, step0=0,
+                        robust_mode=0, epsilon=0.0, robust_lambda=1.0, in_lower=-3.0e38, in_upper=3.0e38, want_weights=True):
+        """One epoch of Bayes-by-Backprop steps in ONE device call (`dbx_bbb_train_epoch`): ``x_t`` [N,K] fp32 / ``labels_t`` [N]
+        int32 CUDA tensors in visiting order.  Returns dict(loss=[nb,2], probs=[N,C], W=[P] | None) device tensors."""
+        torch = self.torch
+        N = int(x_t.shape[0])
+        if not (x_t.is_cuda and x_t.dtype == torch.float32 and x_t.is_contiguous() and x_t.numel() == N * self.K):
+            raise ValueError("x_t must be a contiguous fp32 CUDA tensor [N,%d]" % self.K)
+        if not (labels_t.is_cuda and labels_t.dtype == torch.int32 and labels_t.is_contiguous() and labels_t.numel() == N):
+            raise ValueError("labels_t must be a contiguous int32 CUDA tensor [N]")
+        for t in (mean_t, rho_t, prior_mean_t, prior_var_t):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.numel() == self.P and t.is_contiguous()):
+                raise ValueError("parameter vectors must be contiguous fp32 CUDA tensors with %d elements" % self.P)
+        nb = (N + int(batch) - 1) // int(batch)
+        loss = torch.empty((nb, 2), dtype=torch.float32, device=self.device)
+        probs = torch.empty((N, self.C), dtype=torch.float32, device=self.device)
+        W = torch.empty(self.P, dtype=torch.float32, device=self.device) if want_weights else None
+        _lib.check(self.lib.dbx_bbb_train_epoch(self.h, _ptr(x_t), _ptr(labels_t), N, int(batch), _ptr(mean_t), _ptr(rho_t), _ptr(prior_mean_t),
+                                                _ptr(prior_var_t), seed, step0, float(lrate), float(kl_weight), int(robust_mode), float(epsilon),
+                                                float(robust_lambda), float(max(in_lower, -3.0e38)), float(min(in_upper, 3.0e38)), _ptr(loss),
+                                                _ptr(probs), _ptr(W), _stream()))
+        return {"loss": loss, "probs": probs, "W": W}
+
     def input_gradient(self, x, labels, n_outer=1, n_inner=1, seed=0, s0=0, noise=None, inflate=1.0, stored=False, j0=0):
         """Sum over n_outer iterations of d CE(labels, mean of n_inner sampled predictions) / d x (attacks.py:49-75): [B,K] device tensor."""
         torch = self.torch

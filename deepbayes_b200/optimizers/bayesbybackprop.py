@@ -135,22 +135,35 @@ class BayesByBackprop(optimizer.Optimizer):
             self.max_eps = self.epsilon
             self.epsilon = 0.0
             self.max_robust_lambda = self.robust_lambda
+        # One device call per EPOCH (`dbx_bbb_train_epoch`): the training set stays in HBM, an epoch's permutation is applied
+        # there, and nothing comes back before the epoch's last step.  The per-step loop remains for what needs the host
+        # between steps: Gaussian input noise (drawn from the NumPy generator) and the epsilon draws of robust_train 3.
+        rt = int(getattr(self, "robust_train", 0))
+        device_epochs = kwargs.get("device_epochs", True) and not getattr(self, "input_noise", 0.0) and rt in (0, 1, 2, 4)
+        if device_epochs:
+            eng = self.engine()
+            torch = eng.torch
+            Xd = torch.from_numpy(np.ascontiguousarray(X_train.reshape(self.N, -1))).to(eng.device)
+            yd = torch.from_numpy(y_train.astype(np.int32)).to(eng.device)
         for epoch in range(self.epochs):
             lrate = self.learning_rate * (1 / (1 + self.decay * epoch))
             perm = rng.permutation(self.N)
-            losses, correct, seen = [], 0, 0
-            starts = list(range(0, self.N, bs))
-            for b0 in starts:
-                idx = perm[b0:b0 + bs]
-                feats = X_train[idx]
-                if getattr(self, "input_noise", 0.0):
-                    feats = feats + rng.normal(0.0, self.input_noise, size=feats.shape).astype(np.float32)
-                self.step(feats, y_train[idx], lrate, sync=(b0 == starts[-1]))   # the epoch's last step leaves its W in the model
-                losses.append(self._last_loss)
-                correct += int((self._last_probs.argmax(1).cpu().numpy() == y_train[idx]).sum())
-                seen += len(idx)
-            loss = float(np.mean([float(l[0]) for l in losses]))
-            acc = correct / max(seen, 1)
+            if device_epochs:
+                loss, acc = self._epoch_on_device(eng, Xd, yd, perm, bs, lrate)
+            else:
+                losses, correct, seen = [], 0, 0
+                starts = list(range(0, self.N, bs))
+                for b0 in starts:
+                    idx = perm[b0:b0 + bs]
+                    feats = X_train[idx]
+                    if getattr(self, "input_noise", 0.0):
+                        feats = feats + rng.normal(0.0, self.input_noise, size=feats.shape).astype(np.float32)
+                    self.step(feats, y_train[idx], lrate, sync=(b0 == starts[-1]))   # the epoch's last step leaves its W in the model
+                    losses.append(self._last_loss)
+                    correct += int((self._last_probs.argmax(1).cpu().numpy() == y_train[idx]).sum())
+                    seen += len(idx)
+                loss = float(np.mean([float(l[0]) for l in losses]))
+                acc = correct / max(seen, 1)
             val_loss = val_acc = float("nan")
             if X_test is not None and y_test is not None:
                 pv = np.asarray(self.model(np.asarray(X_test, np.float32))).reshape(len(X_test), -1)   # model_validate, :139-141
@@ -162,6 +175,40 @@ class BayesByBackprop(optimizer.Optimizer):
             if self.robust_linear:  # optimizer.py:131-132 (epochs already holds the extra epoch compile() added, :77-79)
                 self.epsilon += self.max_eps / self.epochs
         return self
+
+    def _epoch_on_device(self, eng, Xd, yd, perm, bs, lrate):
+        """The mini-batch loop of one epoch (optimizer.py:112-116) as one `dbx_bbb_train_epoch` call; same step ids, same
+        kernels and the same order as `step` per mini-batch, so the parameters come out bit-identical."""
+        torch = eng.torch
+        rt = int(getattr(self, "robust_train", 0))
+        epsilon, lam, mode = float(getattr(self, "epsilon", 0.0)), float(getattr(self, "robust_lambda", 1.0)), rt
+        if rt == 4:
+            self.epsilon = epsilon = max(0.0001, epsilon)       # :125
+            mode, lam = 2, 0.0
+        name = getattr(self.loss_func, "__name__", type(self.loss_func).__name__).lower() if self.loss_func is not None else "sparse_categorical_crossentropy"
+        if "sparse" not in name or "crossentropy" not in name:
+            raise NotImplementedError("the device step builds the sparse categorical cross-entropy data term only (got %r)" % name)
+        key = (id(self.posterior_mean), id(self.posterior_var))
+        if getattr(self, "_train_key", None) != key:
+            self._d_mean = self._flat_dev(self.posterior_mean).clone()
+            self._d_rho = self._flat_dev(self.posterior_var).clone()
+            self._d_pm = self._flat_dev(self.prior_mean).clone()
+            self._d_pv = self._flat_dev(self.prior_var).clone()
+        pd = torch.from_numpy(np.asarray(perm, np.int64)).to(eng.device)
+        xp, yp = Xd.index_select(0, pd).contiguous(), yd.index_select(0, pd).contiguous()
+        nb = (len(perm) + bs - 1) // bs
+        res = eng.bbb_train_epoch(xp, yp, bs, self._d_mean, self._d_rho, self._d_pm, self._d_pv, lrate, self.kl_weight, self.seed,
+                                  self._take_ids(nb), robust_mode=mode, epsilon=epsilon, robust_lambda=lam,
+                                  in_lower=self.input_lower, in_upper=self.input_upper)
+        self._last_loss, self._last_probs = res["loss"][-1], res["probs"][(nb - 1) * bs:]
+        loss = float(res["loss"][:, 0].mean().item())
+        acc = float((res["probs"].argmax(1).to(torch.int32) == yp).float().mean().item())
+        self.posterior_mean = self._unflat(self._d_mean.cpu().numpy())
+        self.posterior_var = self._unflat(self._d_rho.cpu().numpy())
+        self.model.set_weights(self._unflat(res["W"].cpu().numpy()))       # the epoch's last step leaves its W in the model (:59)
+        self._train_key = (id(self.posterior_mean), id(self.posterior_var))
+        self._dirty = False
+        return loss, acc
 
     def sample(self):
         """bayesbybackprop.py:176-181: N(mean, scale=softplus(rho)) -- the device holds

@@ -156,6 +156,17 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
  * every eps from Exponential(rate = 1 / epsilon) (:106-109); the caller draws them.  Everything else as dbx_bbb_step.
  * (robust_train == 4, :123-136, repeats the SAME FGSM pass loss_mc times -- the drawn eps is not used, :131 -- and is
  * dbx_bbb_step with robust_mode = 2 and robust_lambda = 0.) */
+/* One EPOCH of such steps in a single call (optimizer.py:100-133, the mini-batch loop `for (features, labels) in train_ds:
+ * self.step(...)`, :112-116): x_dev [N,K] / labels_dev [N] hold the epoch's examples in visiting order (the caller applies
+ * its shuffle), mini-batch i = rows [i*batch, min(N, (i+1)*batch)) takes Philox step id step0 + i; lrate / epsilon are the
+ * epoch's (the reference changes them per epoch, :102-108, :131-132).  loss_out_dev [ceil(N/batch), 2] and probs_out_dev
+ * [N,C] (optional) receive every step's (loss, KL term) and predictions; W_out_dev (optional) the last step's sampled weights
+ * (what the reference leaves in the model, :59).  The steps are the same kernels in the same order as N/batch calls of
+ * dbx_bbb_step: bit-identical parameters, without a host round trip per mini-batch. */
+int dbx_bbb_train_epoch(dbx_handle h, const float* x_dev, const int32_t* labels_dev, int64_t N, int64_t batch, float* mean_dev, float* rho_dev,
+                        const float* prior_mean_dev, const float* prior_var_dev, uint64_t seed, int64_t step0, float lrate, float kl_weight,
+                        int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper, float* loss_out_dev,
+                        float* probs_out_dev, float* W_out_dev, void* stream);
 int dbx_bbb_step_ibp_mc(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                         float lrate, float kl_weight, int32_t n_eps, const float* eps_host, float* loss_out_dev, float* probs_out_dev,

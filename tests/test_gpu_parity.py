@@ -973,6 +973,37 @@ def test_bbb_training_learns(oracle):
     assert (pm.argmax(1) == y[1536:]).mean() > 0.85
 
 
+@pytest.mark.parametrize("robust_train", [0, 2])
+def test_bbb_epoch_on_device_equals_per_step_loop(oracle, robust_train):
+    """`dbx_bbb_train_epoch` (one device call per epoch, training set resident in HBM) against the per-mini-batch loop of
+    `step` calls (optimizer.py:112-116): the same kernels with the same Philox step ids in the same order, so the trained
+    posterior is bit-identical; ragged last mini-batch included."""
+    import deepbayes_b200 as db
+    g = np.random.Generator(np.random.Philox(12))
+    C, D, N = 5, 24, 1000
+    centers = g.standard_normal((C, D)).astype(np.float32)
+    y = g.integers(0, C, size=N)
+    X = np.clip(0.5 + 0.2 * centers[y] + 0.1 * g.standard_normal((N, D)), 0, 1).astype(np.float32)
+    res = []
+    for dev in (True, False):
+        m = db.Sequential([db.Dense(48, activation="relu", input_shape=(D,)), db.Dense(C, activation="softmax")])
+        if res:
+            m.set_weights(res[0]["w0"])
+        w0 = [np.array(w) for w in m.get_weights()]
+        opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=96, learning_rate=0.2, epochs=2, inflate_prior=1.0, kl_weight=0.1,
+                                                      seed=7, robust_train=robust_train, epsilon=0.02, rob_lam=0.5, linear_schedule=False)
+        opt.train(X, y, device_epochs=dev)
+        res.append({"w0": w0, "mean": opt.posterior_mean, "var": opt.posterior_var, "loss": list(opt.loss_log), "acc": list(opt.acc_log),
+                    "W": opt.model.get_weights()})
+    a, b = res
+    for i in range(len(a["mean"])):
+        np.testing.assert_array_equal(np.asarray(a["mean"][i]), np.asarray(b["mean"][i]))
+        np.testing.assert_array_equal(np.asarray(a["var"][i]), np.asarray(b["var"][i]))
+        np.testing.assert_array_equal(np.asarray(a["W"][i]), np.asarray(b["W"][i]))
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-5)
+    np.testing.assert_allclose(a["acc"], b["acc"], rtol=0, atol=1e-7)
+
+
 @pytest.mark.parametrize("dims,B,n_outer,n_inner", [([10, 8, 6, 4], 3, 2, 5), ([784, 128, 10], 40, 1, 35), ([100, 72, 40, 10], 33, 3, 1)])
 def test_input_gradient_matches_oracle(oracle, dims, B, n_outer, n_inner):
     """dbx_input_gradient (injected weight noise) against oracle.input_gradient, summed over the outer iterations."""

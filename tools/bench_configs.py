@@ -136,6 +136,15 @@ def cfg_train():
         ms = timeit(run, warm=1, reps=3) / 50
         emit(config="train: BayesByBackprop.step, MLP %s, mini-batch 128, fp32" % "-".join(map(str, dims)), B=128, ms=ms,
              value=1e3 / ms, unit="steps/s", path="dbx_bbb_step", note="reference: 8.4 ms per sample-forward on CPU (SURVEY section 6); one step = sample + forward + backward + update")
+        # the same steps as ONE device call per epoch (dbx_bbb_train_epoch): 200 mini-batches of 128 resident examples
+        eng = opt.engine()
+        N = 128 * 200
+        Xd = torch.from_numpy(o.synthetic_x((N, 784), seed=1)).cuda()
+        yd = torch.from_numpy(np.random.Generator(np.random.Philox(4)).integers(0, 10, size=N).astype(np.int32)).cuda()
+        ep = lambda: eng.bbb_train_epoch(Xd, yd, 128, opt._d_mean, opt._d_rho, opt._d_pm, opt._d_pv, 0.01, 1.0, 3, 0, want_weights=False)
+        ms2 = timeit(ep, warm=1, reps=3) / 200
+        emit(config="train: one dbx_bbb_train_epoch call per 200 mini-batches, MLP %s, mini-batch 128, fp32" % "-".join(map(str, dims)), B=128,
+             ms=ms2, value=1e3 / ms2, unit="steps/s", path="dbx_bbb_train_epoch")
 
 
 def cfg_attack():
