@@ -132,3 +132,41 @@ def test_massart_helpers_match_oracle(oracle):
         assert tuple(I) == oracle.clopper_pearson(succ, tr)
         assert verifiers.absolute_massart_halting(succ, tr, I, 0.05, 0.3, 0.05) == \
             oracle.absolute_massart_halting(succ, tr, I, 0.05, 0.3, 0.05)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys,
+    on the default workload, also when torchrun has exported OMP_NUM_THREADS=1 (the arm restores the thread count)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DBX_REF_SAMPLES="1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config",
+              "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "forwards/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "784-512-512-10" in line["config"]["workload"]
+    # ranks other than 0 print nothing and exit 0
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_peer_window_api_refuses_bad_arguments():
+    """The multi-GPU entry points fail with a message (not a crash) before any CUDA work when called wrongly."""
+    import ctypes as C
+    from deepbayes_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.dbx_comm_create(3, 2, 0, 1024, C.byref(h)) != 0          # rank outside the world
+    assert b"rank" in lib.dbx_last_error()
+    assert lib.dbx_comm_create(0, 99, 0, 1024, C.byref(h)) != 0         # more ranks than a window has flags for
+    assert lib.dbx_comm_create(0, 1, 0, 0, C.byref(h)) != 0             # empty window
+    assert lib.dbx_comm_allreduce(None, None, 0, None, 0, None) != 0
+    assert lib.dbx_comm_destroy(None) == 0
