@@ -530,7 +530,7 @@ def run_other(args, c):
     if cfg == 1:
         pm = _mlp_posterior_model(c, [784, 512, 10], args.mode, "cfg1", shard=True)
         eng = pm._engine
-        B, n = 10000, 100
+        B, n = (args.batch if args.batch != B_ROWS else 10000), 100      # MNIST-test-shaped batch; also B = 1 and 128
         x_np = o.synthetic_x((B, 784), seed=0)
         units = n * B
         bound = "tensor"
