@@ -271,6 +271,16 @@ __global__ void philox_raw_kernel(uint64_t seed, uint64_t s, int64_t P, uint32_t
   }
 }
 
+// fp32 -> T into `reps` copies `rep_stride` elements apart (the layer-0 input of the stored-posterior path is read by every
+// CTA of every sample: replicas keep them from all pulling the same L2 lines)
+template <typename T>
+__global__ void cast_rep_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t nelem, int reps, int64_t rep_stride) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nelem; j += (int64_t)gridDim.x * blockDim.x) {
+    const T v = from_f32<T>(in[j]);
+    for (int r = 0; r < reps; ++r) out[r * rep_stride + j] = v;
+  }
+}
+
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t nelem) {
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nelem; j += (int64_t)gridDim.x * blockDim.x)
@@ -741,11 +751,11 @@ static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, c
 
   const T* x_in;
   if (kBf16) {
-    DBX_LAUNCH(cast_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, xin, B * m->in_feat);
+    if (src.stored)   // one launch writes all kXRep replicas (was 31 device-to-device copies per call)
+      DBX_LAUNCH(cast_rep_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, xin, B * m->in_feat, kXRep, (int64_t)(xin1_b / sizeof(T)));
+    else
+      DBX_LAUNCH(cast_kernel<T>, grid_for(B * m->in_feat), 256, 0, st, x_dev, xin, B * m->in_feat);
     x_in = xin;
-    if (src.stored)
-      for (int r = 1; r < kXRep; ++r)
-        DBX_CUDA(cudaMemcpyAsync((char*)xin + (size_t)r * xin1_b, xin, (size_t)B * m->in_feat * 2, cudaMemcpyDeviceToDevice, st));
   } else x_in = (const T*)x_dev;
 
   if (sink.kind == 1 && !sink.accumulate)

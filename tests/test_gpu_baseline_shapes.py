@@ -224,6 +224,20 @@ def test_stream_mode_equals_chunked_launches(oracle, dbx_opt):
             dbx_opt(k, None)
         np.testing.assert_allclose(a1.cpu().numpy() / n, ref1, rtol=2e-6, atol=2e-7, err_msg=str(opts))
         np.testing.assert_allclose(a2.cpu().numpy() / n, ref2, rtol=2e-6, atol=2e-7, err_msg=str(opts))
+    # more than two chunks of 1024 samples: both weight buffers, their flags and the cross-chunk running sums in play
+    big1, big2 = eng.predict_sums(x, 2100, seed=6, s0=7, mode="bf16", second_moment=True)
+    dbx_opt("FUSED_STREAM", 0)
+    ref_b1, ref_b2 = eng.predict_sums(x, 2100, seed=6, s0=7, mode="bf16", second_moment=True)
+    dbx_opt("FUSED_STREAM", None)
+    np.testing.assert_allclose(big1.cpu().numpy() / 2100, ref_b1.cpu().numpy() / 2100, rtol=2e-6, atol=2e-7)
+    np.testing.assert_allclose(big2.cpu().numpy() / 2100, ref_b2.cpu().numpy() / 2100, rtol=2e-6, atol=2e-7)
+    # back-to-back calls of different sizes in the default mode (buffers alternate from call to call)
+    for n2 in (8, 200, 17, 1500):
+        d1, _ = eng.predict_sums(x, n2, seed=9, s0=3, mode="bf16")
+        dbx_opt("FUSED_STREAM", 0)
+        e1, _ = eng.predict_sums(x, n2, seed=9, s0=3, mode="bf16")
+        dbx_opt("FUSED_STREAM", None)
+        np.testing.assert_allclose(d1.cpu().numpy() / n2, e1.cpu().numpy() / n2, rtol=2e-6, atol=2e-7)
     # back-to-back calls reuse the weight buffers and their ready flags: results must not depend on what ran before
     for n2 in (8, 200, 17):
         dbx_opt("FUSED_STREAM", 2)      # forced also for a batch this small (2 row-tile pairs)
