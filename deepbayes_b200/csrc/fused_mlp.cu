@@ -207,15 +207,21 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[st]);
             const uint32_t base = s_stage + st * kStageBytes;
-            mbar_expect_tx(fb, kXBytes + nblk * kBlkBytes);
-            tma_load_2d(base, &tmX, fb, kb * 64, m0);
+            if (CM == 1 || !p.mc) {
+              // ONE copy for the chunk's (up to) four 64-column weight blocks through the 4-D (64 n, k, n-block, sample) view
+              // of the kernel: the issuing thread pays ~95 cycles per copy (tools/tma_rate.cu), and five copies per stage
+              // made it, not the MMAs, the pace of layer 1.  The box always spans four n-blocks (zeros / the next chunk's
+              // columns beyond this one's; all counted).
+              mbar_expect_tx(fb, kXBytes + 4 * kBlkBytes);
+              tma_load_2d(base, &tmX, fb, kb * 64, m0);
+              tma_load_4d(base + kXBytes, &tmW1, fb, 0, kb * 64, c * 4, s);
+            } else {
+              mbar_expect_tx(fb, kXBytes + nblk * kBlkBytes);
+              tma_load_2d(base, &tmX, fb, kb * 64, m0);
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-              if (nb < nblk) {
-                if (CM == 1 || !p.mc) tma_load_3d(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s);
-                else if ((nb % CM) == (int)rank)
+              for (int nb = 0; nb < 4; ++nb)
+                if (nb < nblk && (nb % CM) == (int)rank)
                   tma_load_3d_mc(base + kXBytes + nb * kBlkBytes, &tmW1, fb, c * 256 + nb * 64, kb * 64, s, kMask);
-              }
             }
           }
           __syncwarp();
@@ -241,13 +247,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t fb = smem_u32(&bars->full[st]);
             const uint32_t base = s_stage + st * kStageBytes + kXBytes;
             mbar_expect_tx(fb, 4 * kBlkBytes);
+            if (CM == 1 || !p.mc) {
+              // one copy: [2 n-blocks][128 k][64 n] (n-block stride 16 KB)
+              tma_load_4d(base, &tmW2, fb, 0, sg * 128, j * 2, s);
+            } else {
 #pragma unroll
-            for (int bx = 0; bx < 4; ++bx) {  // (k-block kblk, n-block nb)
-              const int kblk = bx >> 1, nb = bx & 1;
-              const int kabs = sg * 2 + kblk;
-              if (CM == 1 || !p.mc) tma_load_3d(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s);
-              else if ((bx % CM) == (int)rank)
-                tma_load_3d_mc(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s, kMask);
+              for (int bx = 0; bx < 4; ++bx) {  // (k-block kblk, n-block nb)
+                const int kblk = bx >> 1, nb = bx & 1;
+                const int kabs = sg * 2 + kblk;
+                if ((bx % CM) == (int)rank)
+                  tma_load_3d_mc(base + bx * kBlkBytes, &tmW2, fb, j * 128 + nb * 64, kabs * 64, s, kMask);
+              }
             }
           }
           __syncwarp();
@@ -302,7 +312,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       DBX_TRACE(140);
       if (elect_one()) {
         const uint64_t bd = w3desc0 + (uint64_t)(pw0 >> 4);
-        for (int kk = 0; kk < pk0; ++kk) mma_ts(pd0, pa0 + kk * 8, bd + (uint64_t)(kk * 16), idesc_l3, kk > 0);
+        for (int kk = 0; kk < pk0; ++kk)   // four independent accumulator chains (see drain_l3)
+          mma_ts(pd0 + (uint32_t)(kk & 3) * 16, pa0 + kk * 8, bd + (uint64_t)(kk * 16), idesc_l3, kk > 3);
         mma_commit(smem_u32(&bars->l3_full[pb0]));
         if (pl0) mma_commit(smem_u32(&bars->w3_empty));
       }
@@ -387,13 +398,20 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(st_full, st_ph);
           DBX_STAGE_FENCE();
           if (elect_one()) {
-            const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
             // 128 consecutive k of packed H1: region sg>>1, packed column (sg&1)*64
             const uint32_t a0 = tmem + (uint32_t)(sg >> 1) * 256 + (uint32_t)(sg & 1) * 64;
+            if (CM == 1 || !p.mc) {
+              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((2 * kBlkBytes >> 4) << 16);   // [n-block][128 k][64 n]
 #pragma unroll
-            for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk; consecutive 16-wide k-steps are 8 TMEM columns apart
-              mma_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (2 * kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2,
-                        (sg | i) > 0);
+              for (int i = 0; i < 8; ++i)   // consecutive 16-wide k-steps: 8 TMEM columns / 2 KB of the weight block apart
+                mma_ts_lh(dbuf, a0 + i * 8, b_lo + i * 128, kDescHi128, idesc_l2, (sg | i) > 0);
+            } else {
+              const uint32_t b_lo = (st_a16 + (kXBytes >> 4)) | ((kBlkBytes >> 4) << 16);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)   // i = kblk*4 + kk
+                mma_ts_lh(dbuf, a0 + i * 8, b_lo + (i >> 2) * (2 * kBlkBytes / 16) + (i & 3) * 128, kDescHi128, idesc_l2,
+                          (sg | i) > 0);
+            }
             if (CM == 1 || !p.mc) mma_commit(st_empty); else mma_commit_mc(st_empty, kMask);
           }
           __syncwarp();
@@ -473,13 +491,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(smem_u32(&bars->l3_full[b]), ph_l3[b] & 1);
         ++ph_l3[b];
         fence_after_sync();
-        uint32_t v[16];
-        tmem_ld16(daddr, v);
+        // four partial accumulators of 16 columns each (the output layer's k-steps go round-robin into them: a single
+        // dependent chain of N = 16 MMAs runs at the pipe's accumulate latency, 53 cycles each)
+        uint32_t v[32], v2[32];
+        tmem_ld32(daddr, v);
+        tmem_ld32(daddr + 32, v2);
         wait_ld();
         fence_before_sync();
         mbar_arrive(smem_u32(&bars->l3_drained[b]));
 #pragma unroll
-        for (int i = 0; i < kMaxC; ++i) logit[i] += __uint_as_float(v[i]);
+        for (int i = 0; i < kMaxC; ++i)
+          logit[i] += (__uint_as_float(v[i]) + __uint_as_float(v[16 + i])) + (__uint_as_float(v2[i]) + __uint_as_float(v2[16 + i]));
       };
 
       for (int c = 0; c < n_l1; ++c) {
@@ -1465,13 +1487,7 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
       if (!make_tmap_bf16(&pl.tmX, X16, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) { set_err("tensor map X failed"); return -1; }
     }
     for (int i = 0; i < 2; ++i) {
-      auto make_w = [&](CUtensorMap* tm, const Layer* L) {
-        uint64_t d[3] = {(uint64_t)L->w_cols_pad, (uint64_t)L->w_rows, (uint64_t)ns};
-        uint64_t sb[2] = {(uint64_t)L->w_cols_pad * 2, (uint64_t)m->P16 * 2};
-        uint32_t b[3] = {64, 64, 1};
-        return make_tmap_bf16(tm, W16buf[i] + L->w16_off, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B);
-      };
-      // pair kernel: the Keras (fan_in, fan_out) kernel seen as (64 n, k, n-block, sample); a box spans `kbox` k rows of `nblk` n-blocks
+      // the Keras (fan_in, fan_out) kernel seen as (64 n, k, n-block, sample); a box spans `kbox` k rows of `nblk` n-blocks
       auto make_w4 = [&](CUtensorMap* tm, const Layer* L, uint32_t kbox, uint32_t nblk) {
         uint64_t d[4] = {64, (uint64_t)L->w_rows, (uint64_t)cdiv(L->w_cols_pad, 64), (uint64_t)ns};
         uint64_t sb[3] = {(uint64_t)L->w_cols_pad * 2, 128, (uint64_t)m->P16 * 2};
@@ -1482,8 +1498,9 @@ static int fused_mlp_run_on(dbx_model* m, FusedState* fs, const float* x_dev, in
         if (!make_w4(&pl.tmW1[i], dl[0], (uint32_t)kd, 2)) { set_err("tensor map W1 (4-D view) failed"); return -1; }
         if (!make_w4(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0], kd == 128 ? 256u : 128u, 1)) { set_err("tensor map W2 (4-D view) failed"); return -1; }
       } else {
-        if (!make_w(&pl.tmW1[i], dl[0])) { set_err("tensor map W1 failed"); return -1; }
-        if (!make_w(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0])) { set_err("tensor map W2 failed"); return -1; }
+        // single-CTA kernel: all four 64-column blocks of a layer-1 chunk / both blocks x 128 k of a layer-2 stage per copy
+        if (!make_w4(&pl.tmW1[i], dl[0], 64, 4)) { set_err("tensor map W1 (4-D view) failed"); return -1; }
+        if (!make_w4(&pl.tmW2[i], NH == 2 ? dl[1] : dl[0], 128, 2)) { set_err("tensor map W2 (4-D view) failed"); return -1; }
       }
       // last layer's kernel in blocked8 order viewed as rows of 64 bf16: CTA r of a pair fetches rows [r*H/8, (r+1)*H/8)
       uint64_t d[3] = {64, (uint64_t)(Lout->w_rows * Lout->w_cols_pad / 64), (uint64_t)ns};
