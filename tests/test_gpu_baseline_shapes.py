@@ -289,3 +289,21 @@ def test_peer_window_allreduce_one_rank():
             c.allreduce(torch.zeros(1 << 18, dtype=torch.float32, device="cuda"))   # larger than the window
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("dims", [[784, 384, 384, 10], [784, 128, 10], [784, 256, 256, 7], [200, 512, 512, 16]])
+def test_other_fused_shapes_in_stream_mode_vs_oracle(oracle, dims):
+    """The pair kernel's other geometries (hidden width 128 / 256 / 384: a 128-column second layer-1 chunk, one or three
+    layer-2 k-pieces, TMA boxes that reach past the kernel's columns; one hidden layer; K0 not a multiple of 128) at a batch
+    large enough for stream mode (7 row-tile pairs, the last one ragged), against the oracle."""
+    B, n = 1700, 5
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    eps = oracle.synthetic_eps(L, n, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    s1, s2 = eng.predict_sums(x, n, eps=eps_flat, mode="bf16", second_moment=True)
+    assert eng.last_path() == "fused_tcgen05"
+    w1, w2 = oracle.predict_moments(L, mean, std, x, n, eps, bf16=True)
+    _check_probs((s1 / float(n)).cpu().numpy(), w1 / np.float32(n), oracle.predict(L, mean, std, x, n, eps))
+    np.testing.assert_allclose((s2 / float(n)).cpu().numpy(), w2 / np.float32(n), rtol=0, atol=BF16_VS_BF16_ORACLE)
