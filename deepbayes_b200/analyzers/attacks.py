@@ -1,6 +1,7 @@
 """First-order attacks over the posterior -- deepbayes/analyzers/attacks.py: ``gradient_expectation`` (:49-75),
 ``FGSM`` (:81-102), ``PGD`` / ``_PGD`` (:133-182) -- with the input gradient evaluated on the device
-(`dbx_input_gradient`): all samples of one ``model.predict`` side by side, forward and backward in fp32.
+(`dbx_input_gradient`): all samples of one ``model.predict`` side by side; forward and backward run in the model's arithmetic
+mode (PosteriorModel.mode / Optimizer.compute_mode): "bf16" = per-sample tcgen05 GEMMs both ways, "fp32" = FFMA kernels.
 
 Scope: Dense MLPs with a softmax output and the sparse categorical cross-entropy (the tutorials' attack loss); order=1.
 As in the reference the model may be a PosteriorModel (its predict() is the mean of 35 sampled forwards, so each
@@ -10,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .verifiers import _engine_of
+from .verifiers import _engine_of, _mode_of
 
 _PM_PREDICT_N = 35          # PosteriorModel.predict's default n (posteriormodel.py:81)
 
@@ -28,8 +29,9 @@ def _labels_of(model, inp, direction):
     return np.broadcast_to(d, (len(inp),)) if d.size == 1 else d
 
 
-def gradient_expectation(model, inp, direction, loss_fn=None, num_models=10):
-    """attacks.py:49-75.  Returns the gradient SUM over the iterations, shaped like ``inp``."""
+def gradient_expectation(model, inp, direction, loss_fn=None, num_models=10, mode=None):
+    """attacks.py:49-75.  Returns the gradient SUM over the iterations, shaped like ``inp``.  ``mode`` (not in the reference)
+    overrides the model's arithmetic mode for this call."""
     _check_loss(loss_fn)
     eng = _engine_of(model)
     a = np.asarray(inp, np.float32)
@@ -50,8 +52,11 @@ def gradient_expectation(model, inp, direction, loss_fn=None, num_models=10):
     n_inner = _PM_PREDICT_N if is_pm else 1
     s0 = model._take_ids(n_outer * n_inner)
     if is_pm and model.sample_based:
-        raise NotImplementedError("gradient_expectation over a sample-based posterior draws stored samples with replacement (posteriormodel.py:77); not built")
-    g = eng.input_gradient(x2, labels, n_outer, n_inner, model.seed, s0)
+        # every sampled forward of predict() draws one stored sample with replacement (posteriormodel.py:77, :95-97)
+        idx = np.random.choice(model.num_post_samps, size=n_outer * n_inner, p=model.frequency)
+        g = eng.input_gradient(x2, labels, n_outer, n_inner, stored=True, idx=idx, mode=_mode_of(model, mode))
+        return g.cpu().numpy().reshape(a.shape)
+    g = eng.input_gradient(x2, labels, n_outer, n_inner, model.seed, s0, mode=_mode_of(model, mode))
     return g.cpu().numpy().reshape(a.shape)
 
 

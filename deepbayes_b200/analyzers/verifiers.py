@@ -254,10 +254,10 @@ def massart_bound_check(model, inp, eps, predicate=None, **kwargs):
             lower, upper = getattr(model, "input_lower", -np.inf), getattr(model, "input_upper", np.inf)
             if fast:
                 _, fl = eng.count_predicate_fgsm(x1, [direc], [int(cls)], eps, nb, model.seed, s0, lower=lower, upper=upper,
-                                                 return_flags=True)
+                                                 return_flags=True, mode=mode)
                 outcomes = fl.cpu().numpy().reshape(-1)
             else:
-                worst = eng.fgsm_samples(x1, [direc], eps, nb, model.seed, s0, lower=lower, upper=upper).cpu().numpy().reshape(nb, C)
+                worst = eng.fgsm_samples(x1, [direc], eps, nb, model.seed, s0, lower=lower, upper=upper, mode=mode).cpu().numpy().reshape(nb, C)
         gl = None
         if chernoff_override:                                  # model._predict(glob_adv) under the same posterior samples (:648)
             gl = eng.predict_samples(np.asarray(glob_adv, np.float32).reshape(1, -1), nb, model.seed, s0,

@@ -660,6 +660,15 @@ static bool f32w_model_ok(const dbx_model* m) {
   return covered * 10 >= m->P * 9;
 }
 
+// side stream + events of the "weights of the next chunk are drawn ahead" pipelines (generic executor, gradient loops)
+static int ensure_side_streams(dbx_model* m) {
+  if (!m->ibp_side) {
+    DBX_CUDA(cudaStreamCreateWithFlags(&m->ibp_side, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : m->ibp_ev) DBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
 template <typename T>
 static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
                        cudaStream_t st, cudaStream_t sst = nullptr) {
@@ -955,10 +964,7 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
       if (g_used_tc) g_last_path = 3;
       return rg0;
     }
-    if (!m->ibp_side) {
-      DBX_CUDA(cudaStreamCreateWithFlags(&m->ibp_side, cudaStreamNonBlocking));
-      for (cudaEvent_t& e : m->ibp_ev) DBX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    if (ensure_side_streams(m)) return 1;
     if (!m->ibp_main) {
       int lo = 0, hi = 0;
       DBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1312,13 +1318,21 @@ int dbx_bbb_step_ibp_mc(dbx_handle h, const float* x_dev, int64_t B, const int32
 }
 
 int dbx_input_gradient(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, int64_t n_outer, int64_t n_inner, uint64_t seed,
-                       int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, float* grad_dev, void* stream) {
+                       int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, const int32_t* idx_dev, int32_t mode,
+                       float* grad_dev, void* stream) {
   DBX_CHECK(h && x_dev && labels_dev && grad_dev, "null argument");
+  DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
   DBX_CHECK(B > 0 && n_outer > 0 && n_inner > 0 && n_inner <= 4096, "B, n_outer, n_inner must be positive (n_inner <= 4096)");
   Source src; src.stored = stored != 0; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0; src.j0 = j0;
-  DBX_CHECK(src.stored ? (h->slab != nullptr && j0 >= 0 && j0 + n_outer * n_inner <= h->S) : h->have_gaussian,
+  src.idx = src.stored ? idx_dev : nullptr;      // rows in [0, S): checked by the caller (Engine.input_gradient)
+  DBX_CHECK(src.stored ? (h->slab != nullptr && (src.idx || (j0 >= 0 && j0 + n_outer * n_inner <= h->S))) : h->have_gaussian,
             src.stored ? "stored rows out of range / no slab set" : "no Gaussian posterior set (dbx_set_gaussian)");
   DBX_CUDA(cudaSetDevice(h->device));
+  g_last_path = 0;
+  if (mode == DBX_MODE_BF16 && h->is_mlp && grad_tc_ok(h)) {
+    g_last_path = 3;
+    return run_input_gradient_tc(h, x_dev, B, labels_dev, n_outer, n_inner, src, grad_dev, (cudaStream_t)stream);
+  }
   return run_input_gradient(h, x_dev, B, labels_dev, n_outer, n_inner, src, grad_dev, (cudaStream_t)stream);
 }
 
@@ -1327,19 +1341,26 @@ int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const in
   DBX_CHECK(h && W_dev, "null argument");
   const float* keep = h->slab; const int64_t keepS = h->S, keepStride = h->slab_stride;
   h->slab = W_dev; h->S = 1; h->slab_stride = h->P;
-  const int rc = dbx_input_gradient(h, x_dev, B, labels_dev, 1, 1, 0, 0, nullptr, 1.f, 1, 0, grad_dev, stream);
+  const int rc = dbx_input_gradient(h, x_dev, B, labels_dev, 1, 1, 0, 0, nullptr, 1.f, 1, 0, nullptr, DBX_MODE_FP32, grad_dev, stream);
   h->slab = keep; h->S = keepS; h->slab_stride = keepStride;
   return rc;
 }
 
 int dbx_count_predicate_fgsm(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, const int32_t* labels_dev,
                              float eps, float lower, float upper, int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate,
-                             int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream) {
+                             int32_t mode, int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream) {
   DBX_CHECK(h && x_dev && attack_labels_dev && labels_dev && counts_dev, "null argument");
   DBX_CHECK(B > 0 && n > 0 && eps >= 0.f, "B, n must be positive and eps >= 0");
+  DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
   DBX_CHECK(h->have_gaussian, "no Gaussian posterior set (dbx_set_gaussian)");
   DBX_CUDA(cudaSetDevice(h->device));
   Source src; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  g_last_path = 0;
+  if (mode == DBX_MODE_BF16 && h->is_mlp && grad_tc_ok(h)) {
+    g_last_path = 3;
+    return run_count_fgsm_tc(h, x_dev, B, attack_labels_dev, labels_dev, eps, lower, upper, n, src, accumulate, flags_dev,
+                             (unsigned long long*)counts_dev, (cudaStream_t)stream);
+  }
   return run_count_fgsm(h, x_dev, B, attack_labels_dev, labels_dev, eps, lower, upper, n, src, accumulate, flags_dev,
                         (unsigned long long*)counts_dev, (cudaStream_t)stream);
 }
@@ -1386,12 +1407,19 @@ int dbx_predict_samples(dbx_handle h, const float* x_dev, int64_t B, int64_t n, 
 }
 
 int dbx_fgsm_samples(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, float eps, float lower, float upper,
-                     int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate, float* probs_dev, void* stream) {
+                     int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t mode, float* probs_dev, void* stream) {
   DBX_CHECK(h && x_dev && attack_labels_dev && probs_dev, "null argument");
   DBX_CHECK(B > 0 && n > 0 && eps >= 0.f, "B, n must be positive and eps >= 0");
+  DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
   DBX_CHECK(h->have_gaussian, "no Gaussian posterior set (dbx_set_gaussian)");
   DBX_CUDA(cudaSetDevice(h->device));
   Source src; src.eps = noise_dev; src.inflate = inflate; src.seed = seed; src.s0 = s0;
+  g_last_path = 0;
+  if (mode == DBX_MODE_BF16 && h->is_mlp && grad_tc_ok(h)) {
+    g_last_path = 3;
+    return run_count_fgsm_tc(h, x_dev, B, attack_labels_dev, nullptr, eps, lower, upper, n, src, 1, nullptr, nullptr, (cudaStream_t)stream,
+                             probs_dev);
+  }
   return run_count_fgsm(h, x_dev, B, attack_labels_dev, nullptr, eps, lower, upper, n, src, 1, nullptr, nullptr, (cudaStream_t)stream,
                         probs_dev);
 }

@@ -154,7 +154,285 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc<kNTMax>(tmem);
 }
 
+// =======================================================================================
+// Backward-data GEMM of a Dense layer for every sample of a chunk (expected input gradient, attacks.py:49-75; the FGSM step
+// of massart_bound_check, verifiers.py:622-625):
+//     dA[s] (M x Kin) = ( dZ[s] (M x N, bf16, N contiguous)  *  W_s^T ) .* act'(Aprev[s])
+// The reduction runs over the layer's OUTPUT features, so the Keras (fan_in, fan_out) kernel as it lies in the chunk's bf16
+// layout IS the K-major B operand (row = fan_in index = output column of this GEMM, fan_out contiguous): one TMA box
+// [64 fan_out x NT fan_in rows], SWIZZLE_128B, the same canonical layout as the A block -- no transposed copy of W_s exists.
+// Same warp roles as dense_tc_kernel; the epilogue multiplies by the derivative of the previous layer's activation taken
+// from its stored (post-activation, bf16) output and writes bf16 (the next GEMM's dZ) or fp32 (the gradient at the input).
+// =======================================================================================
+struct __align__(8) PBarriers {
+  uint64_t full[4], empty[4];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
 
+struct BwdParams {
+  int M, N, K, NT;          // N = fan_in (output columns), K = fan_out (reduction); NT = output columns per CTA
+  const __nv_bfloat16* aprev; long long ap_sstride; int ld_ap; int act;     // previous layer's output [s][M][ld_ap] or null
+  __nv_bfloat16* out16; long long o16_sstride; int ld16;
+  float* out32; long long o32_sstride;
+  // FGSM epilogue (the gradient at the input is only needed for its sign, attacks.py:94-101): with fgsm_x = the call's input
+  // [M][N] fp32, out16 receives clip(clip(x + eps sign(g), x - eps, x + eps), lower, upper) as bf16 -- the A operand of the
+  // forward pass at every sample's own adversarial input; the fp32 gradient is never written
+  const float* fgsm_x; float fgsm_eps, fgsm_lo, fgsm_hi;
+};
+
+__device__ __forceinline__ float act_deriv(int act, float a) {      // derivative written in terms of the activation's OUTPUT
+  switch (act) {
+    case DBX_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case DBX_ACT_TANH: return 1.f - a * a;
+    case DBX_ACT_SIGMOID: return a * (1.f - a);
+    default: return 1.f;
+  }
+}
+
+// one thread's 32 accumulator columns [c0g, c0g + 32) of row gm, sample s
+__device__ __forceinline__ void bwd_epilogue32(const BwdParams& p, int s, int gm, int c0g, const uint32_t (&v)[32]) {
+  const __nv_bfloat16* ap = p.aprev ? p.aprev + (long long)s * p.ap_sstride + (long long)gm * p.ld_ap : nullptr;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const int c = c0g + q4 * 8;
+    if (c < p.N) {
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(v[q4 * 8 + i]);
+      const bool whole = c + 8 <= p.N;
+      if (ap) {
+        if (whole && (p.ld_ap & 7) == 0) {
+          const uint4 a8 = *reinterpret_cast<const uint4*>(ap + c);
+          const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            d[2 * i] *= act_deriv(p.act, __uint_as_float(aw[i] << 16));
+            d[2 * i + 1] *= act_deriv(p.act, __uint_as_float(aw[i] & 0xFFFF0000u));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (c + i < p.N) d[i] *= act_deriv(p.act, __bfloat162float(ap[c + i]));
+        }
+      }
+      if (p.fgsm_x) {
+        const float* xr = p.fgsm_x + (long long)gm * p.N + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xe = (c + i < p.N) ? xr[i] : 0.f;
+          const float sgn = d[i] > 0.f ? 1.f : (d[i] < 0.f ? -1.f : 0.f);
+          float a = xe + p.fgsm_eps * sgn;
+          a = fminf(fmaxf(a, xe - p.fgsm_eps), xe + p.fgsm_eps);
+          d[i] = fminf(fmaxf(a, p.fgsm_lo), p.fgsm_hi);
+        }
+      }
+      if (p.out16) {
+        __nv_bfloat16* dst = p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + c;
+        if (whole && (p.ld16 & 7) == 0) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]),
+                                                      pack_bf16x2(d[6], d[7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (c + i < p.N) dst[i] = __float2bfloat16_rn(d[i]);
+        }
+      } else {
+        float* dst = p.out32 + (long long)s * p.o32_sstride + (long long)gm * p.N + c;
+        if (whole && (p.N & 3) == 0) {
+          *reinterpret_cast<float4*>(dst) = make_float4(d[0], d[1], d[2], d[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (c + i < p.N) dst[i] = d[i];
+        }
+      }
+    }
+  }
+}
+
+template <int kNTMax>
+__global__ void __launch_bounds__(kGThreads, kNTMax == 256 ? 1 : (kNTMax == 128 ? 2 : 3))
+dense_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const BwdParams p) {
+  constexpr int kStageB = 16384 + kNTMax * 128;
+  constexpr int kSt = kNTMax == 64 ? 3 : kGStages;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  GBarriers* bars = (GBarriers*)(smem + kSt * kStageB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * p.NT, m0 = blockIdx.y * 128, s = blockIdx.z;
+  const int nt = min(p.NT, ((p.N - n0 + 63) / 64) * 64);
+  const int kb_n = (p.K + 63) / 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < kSt; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kNTMax>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmZ); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const uint32_t st = kb % kSt, ph = (kb / kSt) & 1;
+      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&bars->full[st]);
+        const uint32_t base = s_stage + st * kStageB;
+        mbar_expect_tx(fb, 16384 + p.NT * 128);       // a box is written whole; what lies outside the tensor arrives as zeros
+        tma_load_3d(base, &tmZ, fb, kb * 64, m0, s);
+        tma_load_3d(base + 16384, &tmW, fb, kb * 64, n0, s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = make_idesc_bf16(128, nt, 0, 0);
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const uint32_t st = kb % kSt, ph = (kb / kSt) & 1;
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a16 = ((s_stage + st * kStageB) & 0x3FFFF) >> 4;
+        const uint32_t a_lo = a16 | (1u << 16);
+        const uint32_t b_lo = (a16 + (16384 >> 4)) | (1u << 16);
+        const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+        for (int kk = 0; kk < ksteps; ++kk)
+          mma_ss_lh(tmem, a_lo + kk * 2, kDescHi128, b_lo + kk * 2, kDescHi128, idesc, (kb | kk) > 0);
+        mma_commit(smem_u32(&bars->empty[st]));
+        if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int g = warp & 3;
+    const int gm = m0 + g * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    fence_after_sync();
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_base + c0, v);
+      wait_ld();
+      if (gm < p.M) bwd_epilogue32(p, s, gm, n0 + c0, v);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kNTMax>(tmem);
+}
+
+// Persistent form (the launches of the gradient loops have hundreds of (sample, column tile) pairs): CTAs walk a contiguous
+// range of the tile list; TMA ring, two TMEM accumulators and the epilogue of tile i overlap the loads and MMAs of tile i + 1
+// (the structure of dense_tc_persist_kernel).
+template <int kNT>
+__global__ void __launch_bounds__(kGThreads, kNT == 256 ? 1 : 2)
+dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const BwdParams p, int ns,
+                            int tiles_m, int tiles_n) {
+  constexpr int kStB = 16384 + kNT * 128;
+  constexpr int kSt = kNT == 128 ? 3 : 4;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  PBarriers* bars = (PBarriers*)(smem + kSt * kStB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kb_n = (p.K + 63) / 64;
+  const long long total = (long long)ns * tiles_m * tiles_n;
+  const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
+  auto decode = [&](long long t, int& n0, int& m0, int& s) {
+    const int nt_i = (int)(t % tiles_n);
+    const long long r = t / tiles_n;
+    n0 = nt_i * kNT; m0 = (int)(r % tiles_m) * 128; s = (int)(r / tiles_m);
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < kSt; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * kNT>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmZ); prefetch_tmap(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    uint32_t g = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kSt, ph = (g / kSt) & 1;
+        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[st]);
+          const uint32_t base = s_stage + st * kStB;
+          mbar_expect_tx(fb, 16384 + kNT * 128);
+          tma_load_3d(base, &tmZ, fb, kb * 64, m0, s);
+          tma_load_3d(base + 16384, &tmW, fb, kb * 64, n0, s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    uint32_t g = 0, it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
+      const uint32_t idesc = make_idesc_bf16(128, nt, 0, 0);
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
+      fence_after_sync();
+      for (int kb = 0; kb < kb_n; ++kb, ++g) {
+        const uint32_t st = g % kSt, ph = (g / kSt) & 1;
+        mbar_wait(smem_u32(&bars->full[st]), ph);
+        if (elect_one()) {
+          const uint32_t a16 = ((s_stage + st * kStB) & 0x3FFFF) >> 4;
+          const uint32_t a_lo = a16 | (1u << 16);
+          const uint32_t b_lo = (a16 + (16384 >> 4)) | (1u << 16);
+          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+          for (int kk = 0; kk < ksteps; ++kk)
+            mma_ss_lh(tmem + ab * kNT, a_lo + kk * 2, kDescHi128, b_lo + kk * 2, kDescHi128, idesc, (kb | kk) > 0);
+          mma_commit(smem_u32(&bars->empty[st]));
+          if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full[ab]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int gq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
+    uint32_t it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      int n0, m0, s;
+      decode(t, n0, m0, s);
+      const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
+      const int gm = m0 + gq * 32 + lane;
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      fence_after_sync();
+      for (int c0 = 0; c0 < nt; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + ab * kNT + c0, v);
+        wait_ld();
+        if (c0 + 32 >= nt) {   // the whole accumulator is in registers: the MMA warp may reuse it
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+        }
+        if (gm < p.M) bwd_epilogue32(p, s, gm, n0 + c0, v);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * kNT>(tmem);
+}
 
 // =======================================================================================
 // Persistent variant of dense_tc_kernel.  A CTA per tile spends most of a short tile's life in the serial chain
@@ -163,11 +441,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // of the (sample, m tile, n tile) list; the TMA ring, the two TMEM accumulators and the epilogue of tile i overlap the
 // loads and MMAs of tile i+1.  kNT = column tile (64 / 128 / 256).
 // =======================================================================================
-struct __align__(8) PBarriers {
-  uint64_t full[4], empty[4];
-  uint64_t acc_full[2], acc_empty[2];
-  uint32_t tmem_slot;
-};
 
 template <int kNT, int kAct>
 __global__ void __launch_bounds__(kGThreads, kNT == 256 ? 1 : 2)
@@ -1400,6 +1673,61 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
   else if (p.NT <= 128) rc = DBX_GO(128);
   else rc = DBX_GO(256);
 #undef DBX_GO
+  if (rc) return 1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Backward-data pass of one Dense layer (dense_tc_bwd_kernel).  dZ: bf16 [ns][M][ldz] (N_out = layer units = reduction);
+// W16 chunk layout as for dense_tc_launch (kernel [fan_in][ldw]); result [ns][M][fan_in] as bf16 (ld16) or fp32 (dense rows).
+// Needs ldz, ldw multiples of 8 and 16-byte aligned bases (TMA); returns 1 when not applicable.
+int dense_tc_bwd_launch(const __nv_bfloat16* dZ, long long dz_sstride, int ldz, const __nv_bfloat16* Wbase, long long w_sstride_elems,
+                        int ldw, int ns, int M, int fan_in, int fan_out, const __nv_bfloat16* aprev, long long ap_sstride, int ld_ap,
+                        int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32, long long o32_sstride,
+                        cudaStream_t st, const float* fgsm_x, float fgsm_eps, float fgsm_lo, float fgsm_hi) {
+  if (!g_tc_ok || !get_encode_fn()) return 1;
+  if ((ldz & 7) || (ldw & 7) || (dz_sstride & 7) || (w_sstride_elems & 7) || ((uintptr_t)dZ & 15) || ((uintptr_t)Wbase & 15)) return 1;
+  BwdParams p = {};
+  p.M = M; p.N = fan_in; p.K = fan_out;
+  p.aprev = aprev; p.ap_sstride = ap_sstride; p.ld_ap = ld_ap; p.act = act;
+  p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
+  p.fgsm_x = fgsm_x; p.fgsm_eps = fgsm_eps; p.fgsm_lo = fgsm_lo; p.fgsm_hi = fgsm_hi;
+  const int ntc = fan_in <= 64 ? 64 : (fan_in <= 128 ? 128 : 256);      // column tile = template width = rows of the weight box
+  p.NT = ntc;
+  CUtensorMap tmZ, tmW;
+  {
+    uint64_t d[3] = {(uint64_t)fan_out, (uint64_t)M, (uint64_t)ns}, sb[2] = {(uint64_t)ldz * 2, (uint64_t)dz_sstride * 2};
+    uint32_t b[3] = {64, 128, 1};
+    if (!make_tmap_bf16(&tmZ, (void*)dZ, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t d[3] = {(uint64_t)fan_out, (uint64_t)fan_in, (uint64_t)ns}, sb[2] = {(uint64_t)ldw * 2, (uint64_t)w_sstride_elems * 2};
+    uint32_t b[3] = {64, (uint32_t)ntc, 1};
+    if (!make_tmap_bf16(&tmW, (void*)Wbase, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  const int tiles_m = (int)cdiv(M, 128), tiles_n = (int)cdiv(fan_in, ntc);
+  const long long tiles = (long long)ns * tiles_m * tiles_n;
+  if (tiles >= opt().persist_min_tiles && !opt().no_persist) {
+    const int smem = (ntc == 128 ? 3 : 4) * (16384 + ntc * 128) + (int)sizeof(PBarriers) + 1024;
+    dim3 pgrid((unsigned)std::min<long long>(tiles, (ntc == 256 ? 1LL : 2LL) * sm_count()));
+    auto gop = [&](auto kern) -> int {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+      kern<<<pgrid, kGThreads, smem, st>>>(tmZ, tmW, p, ns, tiles_m, tiles_n);
+      return 0;
+    };
+    const int prc = ntc == 64 ? gop(dense_tc_bwd_persist_kernel<64>) : (ntc == 128 ? gop(dense_tc_bwd_persist_kernel<128>) : gop(dense_tc_bwd_persist_kernel<256>));
+    if (prc) return 1;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
+  dim3 grid((unsigned)tiles_n, (unsigned)tiles_m, (unsigned)ns);
+  auto go = [&](auto kern, int ntmax) -> int {
+    const int smem = (ntmax == 64 ? 3 : kGStages) * (16384 + ntmax * 128) + (int)sizeof(GBarriers) + 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+    kern<<<grid, kGThreads, smem, st>>>(tmZ, tmW, p);
+    return 0;
+  };
+  const int rc = ntc == 64 ? go(dense_tc_bwd_kernel<64>, 64) : (ntc == 128 ? go(dense_tc_bwd_kernel<128>, 128) : go(dense_tc_bwd_kernel<256>, 256));
   if (rc) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -302,8 +302,9 @@ class Engine:
                                                 _ptr(probs), _ptr(W), _stream()))
         return {"loss": loss, "probs": probs, "W": W}
 
-    def input_gradient(self, x, labels, n_outer=1, n_inner=1, seed=0, s0=0, noise=None, inflate=1.0, stored=False, j0=0):
-        """Sum over n_outer iterations of d CE(labels, mean of n_inner sampled predictions) / d x (attacks.py:49-75): [B,K] device tensor."""
+    def input_gradient(self, x, labels, n_outer=1, n_inner=1, seed=0, s0=0, noise=None, inflate=1.0, stored=False, j0=0, mode="fp32", idx=None):
+        """Sum over n_outer iterations of d CE(labels, mean of n_inner sampled predictions) / d x (attacks.py:49-75): [B,K] device tensor.
+        mode "bf16": forward and backward GEMMs on the tensor cores (operands rounded to bf16), "fp32": FFMA kernels."""
         torch = self.torch
         xt = self._x2d(x)
         B = xt.shape[0]
@@ -312,8 +313,14 @@ class Engine:
             raise ValueError("need one label per input row (%d rows, %d labels)" % (B, lab.numel()))
         g = torch.empty((B, self.K), dtype=torch.float32, device=self.device)
         e = None if noise is None else self._dev_f32(noise).reshape(n_outer * n_inner, self.P)
+        it = None
+        if idx is not None:                                   # stored rows drawn by the caller (with replacement, posteriormodel.py:77)
+            ia = np.asarray(idx, dtype=np.int64).reshape(-1)
+            if not stored or ia.size != n_outer * n_inner or ia.min() < 0 or ia.max() >= getattr(self, "S", 0):
+                raise ValueError("idx needs stored=True and n_outer * n_inner rows in [0, %d)" % getattr(self, "S", 0))
+            it = torch.as_tensor(ia.astype(np.int32)).to(self.device)
         _lib.check(self.lib.dbx_input_gradient(self.h, _ptr(xt), B, _ptr(lab), n_outer, n_inner, seed, s0, _ptr(e), float(inflate),
-                                               1 if stored else 0, j0, _ptr(g), _stream()))
+                                               1 if stored else 0, j0, _ptr(it), _lib.MODE[mode], _ptr(g), _stream()))
         return g
 
     def input_gradient_one(self, x, labels, weights_flat):
@@ -327,7 +334,7 @@ class Engine:
         return g
 
     def count_predicate_fgsm(self, x, attack_labels, labels, eps, n, seed=0, s0=0, noise=None, inflate=1.0, lower=-3.0e38, upper=3.0e38,
-                             return_flags=False):
+                             return_flags=False, mode="fp32"):
         """Per posterior sample: FGSM against that sample, then argmax == label at the adversarial input (verifiers.py:622-634)."""
         torch = self.torch
         xt = self._x2d(x)
@@ -341,7 +348,7 @@ class Engine:
         e = None if noise is None else self._dev_f32(noise).reshape(n, self.P)
         lo = float(max(lower, -3.0e38)); hi = float(min(upper, 3.0e38))
         _lib.check(self.lib.dbx_count_predicate_fgsm(self.h, _ptr(xt), B, _ptr(al), _ptr(lab), float(eps), lo, hi, n, seed, s0, _ptr(e),
-                                                     float(inflate), 0, _ptr(flags), _ptr(counts), _stream()))
+                                                     float(inflate), _lib.MODE[mode], 0, _ptr(flags), _ptr(counts), _stream()))
         return (counts, flags) if return_flags else counts
 
     def ibp_predict(self, x, eps, labels=None, n=1, seed=0, s0=0, noise=None, inflate=1.0, mode="bf16", clip=True,
@@ -383,7 +390,7 @@ class Engine:
                                                 _lib.OUT_LOGITS if out_kind == "logits" else _lib.OUT_PROBS, _ptr(out), _stream()))
         return out
 
-    def fgsm_samples(self, x, attack_labels, eps, n, seed=0, s0=0, noise=None, inflate=1.0, lower=-3.0e38, upper=3.0e38):
+    def fgsm_samples(self, x, attack_labels, eps, n, seed=0, s0=0, noise=None, inflate=1.0, lower=-3.0e38, upper=3.0e38, mode="fp32"):
         """[n,B,C] device tensor: softmax output of sample i at ITS OWN FGSM input (verifiers.py:622-625)."""
         torch = self.torch
         xt = self._x2d(x)
@@ -395,7 +402,7 @@ class Engine:
         e = None if noise is None else self._dev_f32(noise).reshape(n, self.P)
         lo = float(max(lower, -3.0e38)); hi = float(min(upper, 3.0e38))
         _lib.check(self.lib.dbx_fgsm_samples(self.h, _ptr(xt), B, _ptr(al), float(eps), lo, hi, n, seed, s0, _ptr(e), float(inflate),
-                                             _ptr(out), _stream()))
+                                             _lib.MODE[mode], _ptr(out), _stream()))
         return out
 
     def ibp_samples(self, x, eps, n, seed=0, s0=0, noise=None, inflate=1.0, mode="fp32", clip=True, box_hi=None):

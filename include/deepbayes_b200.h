@@ -182,10 +182,14 @@ int dbx_ibp_state(dbx_handle h, const float* lo_dev, const float* hi_dev, int64_
 /* Expected input gradient (deepbayes/analyzers/attacks.py gradient_expectation :49-75): the sum over n_outer iterations
  * of d CE(labels, mean over n_inner posterior samples of softmax(f_W(x))) / d x, CE = batch-mean sparse categorical
  * cross-entropy.  n_inner = 35 reproduces a PosteriorModel (its predict() averages 35 samples, posteriormodel.py:81),
- * n_inner = 1 an optimizer object.  Sample ids s0 + it * n_inner + s (stored != 0: slab rows j0 + ...).  grad_dev [B,K]
- * fp32.  Dense MLPs with a softmax output. */
+ * n_inner = 1 an optimizer object.  Sample ids s0 + it * n_inner + s (stored != 0: slab rows j0 + ..., or, when idx_dev is
+ * given, the rows idx_dev[it * n_inner + s] -- the draws with replacement of posteriormodel.py:77).  grad_dev [B,K]
+ * fp32.  Dense MLPs with a softmax output.  mode = DBX_MODE_FP32: forward and backward on fp32 FFMA kernels (what the
+ * reference computes); DBX_MODE_BF16: both passes on the tensor cores (per-sample tcgen05 GEMMs, operands rounded to bf16,
+ * fp32 accumulation, softmax / cross-entropy in fp32) when every Dense width is a multiple of 8, the fp32 kernels otherwise. */
 int dbx_input_gradient(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, int64_t n_outer, int64_t n_inner, uint64_t seed,
-                       int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, float* grad_dev, void* stream);
+                       int64_t s0, const float* noise_dev, float inflate, int32_t stored, int64_t j0, const int32_t* idx_dev, int32_t mode,
+                       float* grad_dev, void* stream);
 /* same with one explicit flat weight vector (the det / current-weights branch, attacks.py:57-58) */
 int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, const float* W_dev, float* grad_dev,
                            void* stream);
@@ -193,10 +197,11 @@ int dbx_input_gradient_one(dbx_handle h, const float* x_dev, int64_t B, const in
 /* massart_bound_check / chernoff loop with verify=False (verifiers.py:588-634, :622-625): for each of the n posterior
  * samples, an FGSM step (attacks.py:81-102, first order, sparse categorical cross-entropy towards attack_labels) against
  * THAT sample's weights, then the predicate argmax == labels[b] on the sample's output at the adversarial input.
- * counts_dev [B] (+ per-sample flags [n,B]).  lower / upper = the model's input_lower / input_upper. */
+ * counts_dev [B] (+ per-sample flags [n,B]).  lower / upper = the model's input_lower / input_upper.  mode as for
+ * dbx_input_gradient (bf16: forward, backward and the second forward at each sample's own adversarial input on tcgen05). */
 int dbx_count_predicate_fgsm(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, const int32_t* labels_dev,
                              float eps, float lower, float upper, int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate,
-                             int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream);
+                             int32_t mode, int32_t accumulate, uint8_t* flags_dev, int64_t* counts_dev, void* stream);
 
 /* Interval bound propagation over posterior samples (deepbayes/analyzers/verifiers.py: propagate_interval :23-41,
  * IBP :68-95, and its per-sample use in chernoff_bound_verification :537-557 / massart_bound_check :588-634).
@@ -219,7 +224,8 @@ int dbx_ibp_predict(dbx_handle h, const float* x_dev, int64_t B, float eps, int3
 int dbx_predict_samples(dbx_handle h, const float* x_dev, int64_t B, int64_t n, uint64_t seed, int64_t s0, const float* eps_dev,
                         float inflate, int32_t mode, int32_t out_kind, float* out_dev, void* stream);
 int dbx_fgsm_samples(dbx_handle h, const float* x_dev, int64_t B, const int32_t* attack_labels_dev, float eps, float lower, float upper,
-                     int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate, float* probs_dev, void* stream);
+                     int64_t n, uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t mode, float* probs_dev,
+                     void* stream);
 int dbx_ibp_samples(dbx_handle h, const float* x_dev, const float* box_hi_dev, int64_t B, float eps, int32_t clip01, int64_t n,
                     uint64_t seed, int64_t s0, const float* noise_dev, float inflate, int32_t mode, float* lower_dev, float* upper_dev,
                     void* stream);

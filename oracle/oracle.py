@@ -846,40 +846,47 @@ def mean_prediction_loss(layers, weight_sets, x, labels, dtype=np.float64):
     return sparse_categorical_crossentropy(labels, pbar, dtype), pbar
 
 
-def input_gradient(layers, weight_sets, x, labels, dtype=np.float64):
+def input_gradient(layers, weight_sets, x, labels, dtype=np.float64, bf16=False):
     """d mean_prediction_loss / d x by hand (the reference uses tf.GradientTape, attacks.py:60-67) for Dense MLPs with
     a softmax output: with pbar the mean prediction, dz_s[b, c] = g_b p_s[b, y_b] ([c == y_b] - p_s[b, c]),
-    g_b = -1 / (B n pbar_b[y_b]), back-propagated through each sample's layers and summed over samples."""
-    d = dtype
-    x = np.asarray(x, d)
+    g_b = -1 / (B n pbar_b[y_b]), back-propagated through each sample's layers and summed over samples.
+    ``bf16=True`` emulates the GPU's bf16 mode: every GEMM operand (x, weights, stored hidden activations, the upstream
+    gradients between layers) rounded to bf16, fp32 accumulation, bias / softmax / cross-entropy / sums in fp32."""
+    d = np.float32 if bf16 else dtype
+    rnd = bf16_round if bf16 else (lambda a: a)
+    x = rnd(np.asarray(x, d))
     lab = np.asarray(labels).reshape(-1)
     dense = [l for l in layers if l.kind == "dense"]
     B, n = x.shape[0], len(weight_sets)
     fw = []
     for w in weight_sets:
         W = [np.asarray(t, d) for t in w]
+        if bf16:
+            W = [rnd(t) if i % 2 == 0 else t for i, t in enumerate(W)]
         acts = [x]
         h = x
         for li, l in enumerate(dense):
-            h = _act(l.activation, h @ W[2 * li] + W[2 * li + 1])
+            h = _act(l.activation, (h @ W[2 * li] + W[2 * li + 1]).astype(d))
+            if li + 1 < len(dense):
+                h = rnd(h)
             acts.append(h)
         fw.append((W, acts))
     pbar = sum(a[-1] for _, a in fw) / d(n)
     py = pbar[np.arange(B), lab]
-    g = np.where((py > 1e-7) & (py < 1 - 1e-7), -1.0 / (B * n * py), 0.0)
+    g = np.where((py > 1e-7) & (py < 1 - 1e-7), -1.0 / (B * n * py), 0.0).astype(d)
     grad = np.zeros_like(x)
     for W, acts in fw:
         p = acts[-1]
         onehot = np.zeros_like(p)
         onehot[np.arange(B), lab] = 1
-        dz = (g * p[np.arange(B), lab])[:, None] * (onehot - p)
+        dz = rnd((g * p[np.arange(B), lab])[:, None] * (onehot - p))
         for li in range(len(dense) - 1, -1, -1):
             da = dz @ W[2 * li].T
             if li == 0:
                 grad += da
                 break
             a, name = acts[li], dense[li - 1].activation
-            dz = da * ((a > 0) if name == "relu" else (1 - a * a) if name == "tanh" else a * (1 - a) if name == "sigmoid" else 1.0)
+            dz = rnd(da * ((a > 0) if name == "relu" else (1 - a * a) if name == "tanh" else a * (1 - a) if name == "sigmoid" else 1.0))
     return grad
 
 

@@ -1024,6 +1024,110 @@ def test_input_gradient_matches_oracle(oracle, dims, B, n_outer, n_inner):
     np.testing.assert_allclose(g1, oracle.input_gradient(L, [oracle.split_flat(L, w)], x, lab), rtol=2e-4, atol=2e-6 * np.abs(g1).max() + 1e-12)
 
 
+@pytest.mark.parametrize("dims,B,n_outer,n_inner", [([784, 128, 10], 40, 1, 35), ([784, 512, 512, 10], 130, 2, 4), ([104, 72, 40, 16], 33, 3, 1),
+                                                    ([784, 512, 512, 10], 300, 1, 3)])
+@pytest.mark.parametrize("persist", [False, True])
+def test_input_gradient_bf16_on_tensor_cores_matches_oracle(oracle, dbx_opt, dims, B, n_outer, n_inner, persist):
+    """dbx_input_gradient in bf16 mode (forward = per-sample tcgen05 GEMMs, backward = dense_tc_bwd_kernel: dZ * W_s^T with the
+    K-major view of the Keras kernel, activation derivative in its epilogue) against the oracle with the same roundings
+    (operands to bf16, fp32 accumulation) and against the fp64 oracle of attacks.py:49-75.  persist: every GEMM launch through
+    the persistent kernels (dense_tc_persist_kernel / dense_tc_bwd_persist_kernel), otherwise one CTA per tile at these sizes."""
+    dbx_opt("PERSIST_MIN_TILES", "1" if persist else "1000000")
+    L, eng, mean, std = _mlp_engine(dims, oracle, seed=2, sigma_scale=2.0)
+    x = oracle.synthetic_x((B, dims[0]), seed=4)
+    lab = np.random.Generator(np.random.Philox(9)).integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, n_outer * n_inner, seed=3)
+    nf = np.stack([oracle.flatten_list(e) for e in noise])
+    got = eng.input_gradient(x, lab, n_outer, n_inner, noise=nf, mode="bf16").cpu().numpy()
+    assert eng.last_path() == "generic_tc"
+    want16 = np.zeros((B, dims[0]))
+    want = np.zeros((B, dims[0]))
+    for it in range(n_outer):
+        ws = [oracle.sample_gaussian(mean, std, noise[it * n_inner + s], order="f32") for s in range(n_inner)]
+        want16 += oracle.input_gradient(L, ws, x, lab, bf16=True)
+        want += oracle.input_gradient(L, ws, x, lab)
+    scale = np.abs(want).max()
+    # same roundings: what is left is fp32 summation order, which moves a stored activation across a bf16 tie or a relu
+    # across zero in a few rows (their gradient then differs by that unit's share); most rows agree to fp32 rounding
+    row_err = np.abs(got - want16).max(1)
+    assert np.median(row_err) <= 1e-3 * scale and np.quantile(row_err, 0.75) <= 4e-3 * scale and row_err.max() <= 0.1 * scale, \
+        (np.median(row_err) / scale, np.quantile(row_err, 0.75) / scale, row_err.max() / scale)
+    # against the exact gradient: bf16 operand rounding (2^-9 relative per operand, through two or three layers each way)
+    # (observed: 2-6 % of the gradient's norm at this posterior width)
+    assert np.linalg.norm(got - want) <= 0.1 * np.linalg.norm(want)
+    np.testing.assert_allclose(got, want, rtol=0, atol=0.25 * scale)
+    big = np.abs(want) > 0.5 * scale
+    assert (np.sign(got[big]) == np.sign(want[big])).all()
+    # the fp32 kernels on the same inputs
+    g32 = eng.input_gradient(x, lab, n_outer, n_inner, noise=nf, mode="fp32").cpu().numpy()
+    assert eng.last_path() == "generic"
+    np.testing.assert_allclose(g32, want, rtol=2e-4, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_input_gradient_over_stored_samples_drawn_with_replacement(oracle, mode):
+    """gradient_expectation over a sample-based posterior: each forward of predict() uses a stored sample drawn with
+    replacement (posteriormodel.py:77, :95-97) -- the rows are given as an index list."""
+    dims, B, S = [784, 128, 64, 10], 20, 7
+    L, eng, mean, std = _mlp_engine(dims, oracle, seed=2, sigma_scale=2.0)
+    noise = oracle.synthetic_eps(L, S, seed=3)
+    samples = [oracle.sample_gaussian(mean, std, noise[s], order="f32") for s in range(S)]
+    eng.set_samples(np.stack([oracle.flatten_list(w) for w in samples]).astype(np.float32))
+    x = oracle.synthetic_x((B, dims[0]), seed=4)
+    lab = np.random.Generator(np.random.Philox(9)).integers(0, dims[-1], size=B)
+    idx = np.array([3, 3, 0, 6, 1, 3, 5, 2, 6, 6])
+    got = eng.input_gradient(x, lab, 2, 5, stored=True, idx=idx, mode=mode).cpu().numpy()
+    want = sum(oracle.input_gradient(L, [samples[j] for j in idx[it * 5:it * 5 + 5]], x, lab, bf16=(mode == "bf16")) for it in range(2))
+    scale = np.abs(want).max()
+    if mode == "fp32":
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6 * scale)
+    else:
+        assert eng.last_path() == "generic_tc"
+        row_err = np.abs(got - want).max(1)
+        assert np.median(row_err) <= 1e-3 * scale and row_err.max() <= 0.1 * scale
+    with pytest.raises(ValueError):
+        eng.input_gradient(x, lab, 2, 5, stored=True, idx=[0, 1, 2, 3, 4, 5, 6, 7, 0, 1], mode=mode)      # row 7 does not exist
+
+
+@pytest.mark.parametrize("persist", [False, True])
+def test_count_predicate_fgsm_bf16_on_tensor_cores(oracle, dbx_opt, persist):
+    """dbx_count_predicate_fgsm / dbx_fgsm_samples in bf16 mode (forward, backward, second forward at every sample's own
+    adversarial input on tcgen05) against the oracle's per-sample FGSM walk; entries whose gradient sign or top-2 margin is
+    within bf16 rounding of a tie are left out."""
+    dims, B, n = [784, 256, 128, 10], 70, 9
+    dbx_opt("PERSIST_MIN_TILES", "1" if persist else "1000000")
+    L, eng, mean, std = _mlp_engine(dims, oracle, seed=2, sigma_scale=2.0)
+    x = oracle.synthetic_x((B, dims[0]), seed=4)
+    g = np.random.Generator(np.random.Philox(9))
+    direc = g.integers(0, dims[-1], size=B)
+    lab = g.integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, n, seed=3)
+    nf = np.stack([oracle.flatten_list(e) for e in noise])
+    eps = 0.03
+    counts, flags = eng.count_predicate_fgsm(x, direc, lab, eps, n, noise=nf, lower=0.0, upper=1.0, return_flags=True, mode="bf16")
+    assert eng.last_path() == "generic_tc"
+    probs = eng.fgsm_samples(x, direc, eps, n, noise=nf, lower=0.0, upper=1.0, mode="bf16").cpu().numpy()
+    want = np.zeros((n, B), bool)
+    ok = np.ones((n, B), bool)
+    wprobs = np.zeros((n, B, dims[-1]))
+    for s in range(n):
+        w = oracle.sample_gaussian(mean, std, noise[s], order="f32")
+        gr = oracle.input_gradient(L, [w], x, direc, bf16=True)
+        adv = oracle.fgsm(oracle.bf16_round(x), gr, eps, 0.0, 1.0)
+        z = oracle.forward(L, w, adv, out="logits", bf16=True)
+        wprobs[s] = oracle.forward(L, w, adv, bf16=True)
+        want[s] = z.argmax(1) == lab
+        top2 = np.sort(z, axis=1)[:, -2:]
+        # a sign flip of a small gradient entry moves that input by 2 eps: rows where many entries are near zero are not comparable
+        near_zero = (np.abs(gr) < 2e-2 * np.abs(gr).max(1, keepdims=True)).mean(1)
+        ok[s] = ((top2[:, 1] - top2[:, 0]) > 0.05 * np.abs(z).max()) & (near_zero < 0.5)
+    got = flags.cpu().numpy().astype(bool)
+    assert ok.mean() > 0.5 and (got == want)[ok].mean() > 0.97
+    np.testing.assert_array_equal(counts.cpu().numpy(), got.sum(0))
+    np.testing.assert_array_equal(probs.argmax(2) == lab[None, :], got)
+    assert np.median(np.abs(probs - wprobs).max(2)) < 2e-2
+
+
 def test_fgsm_and_pgd_lower_the_true_class_probability(oracle, golden_dir):
     """FGSM / PGD through the drop-in API on the VOGN tutorial posterior: the adversarial inputs stay in the eps-ball and in
     [input_lower, input_upper], and the posterior-mean probability of the attacked class goes down."""

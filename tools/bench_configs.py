@@ -149,14 +149,21 @@ def cfg_train():
 
 def cfg_attack():
     """Expected input gradient: MLP 784-512-512-10, 128 inputs, one FGSM gradient = 10 iterations x 35
-    posterior samples (a PosteriorModel's predict), all on the device."""
+    posterior samples (a PosteriorModel's predict), all on the device; and config 5 with verify=False (massart_bound_check's
+    FGSM per posterior sample, verifiers.py:622-634): 10,000 samples x 128 inputs.  fp32 kernels and the tensor-core path."""
     eng = mlp_engine([784, 512, 512, 10])
     x = torch.from_numpy(o.synthetic_x((128, 784), seed=0)).cuda()
     y = np.random.Generator(np.random.Philox(3)).integers(0, 10, size=128)
-    ms = timeit(lambda: eng.input_gradient(x, y, 10, 35, seed=5), warm=1, reps=3)
-    fl = 3 * 1337344 * 128 * 350 / (ms * 1e-3) / 1e12     # forward + backward-data
-    emit(config="attack: gradient_expectation, MLP 784-512-512-10, 128 inputs, num_models=10 x 35 samples", B=128, ms=ms,
-         value=350 * 128 / (ms * 1e-3), unit="sample-input gradients/s", path="dbx_input_gradient", tflops=fl)
+    for mode in ("fp32", "bf16"):
+        ms = timeit(lambda: eng.input_gradient(x, y, 10, 35, seed=5, mode=mode), warm=1, reps=3)
+        fl = 2 * 1337344 * 128 * 350 / (ms * 1e-3) / 1e12     # forward + backward-data
+        emit(config="attack: gradient_expectation, MLP 784-512-512-10, 128 inputs, num_models=10 x 35 samples", B=128, ms=ms, mode=mode,
+             value=350 * 128 / (ms * 1e-3), unit="sample-input gradients/s", path="dbx_input_gradient/" + eng.last_path(), tflops=fl)
+    for mode, n in (("fp32", 2000), ("bf16", 10000)):
+        ms = timeit(lambda: eng.count_predicate_fgsm(x, y, y, 0.05, n, seed=5, lower=0.0, upper=1.0, mode=mode), warm=1, reps=2)
+        fl = 3 * 1337344 * 128 * n / (ms * 1e-3) / 1e12       # forward + backward-data + forward at the adversarial input
+        emit(config="config 5 with verify=False: FGSM per posterior sample, MLP 784-512-512-10, %d samples x 128 inputs" % n, B=128, n=n,
+             ms=ms, mode=mode, value=n / (ms * 1e-3), unit="posterior samples/s", path="dbx_count_predicate_fgsm/" + eng.last_path(), tflops=fl)
 
 
 if __name__ == "__main__":
