@@ -190,8 +190,76 @@ __device__ __forceinline__ float act_deriv(int act, float a) {      // derivativ
   }
 }
 
+// What the epilogue reads from global memory for one thread's 32 columns [c0g, c0g + 32) of row gm: the previous layer's
+// output (4 x 16 bytes of bf16) or, for the FGSM epilogue, the call's input (8 x 16 bytes of fp32).  The loads are issued
+// BEFORE the accumulator is waited for and before the previous group's stores (which the compiler cannot move loads across:
+// it does not know the buffers are distinct) -- issued one at a time between the stores, each cost a full memory latency and the
+// epilogue ran at a 32nd of the L2's rate (ncu: long-scoreboard stalls, 9 % warps active).
+struct BwdPre { uint4 q[8]; };
+__device__ __forceinline__ bool bwd_vec_ok(const BwdParams& p) {
+  return p.fgsm_x ? ((p.N & 3) == 0) : (p.aprev == nullptr || (p.ld_ap & 7) == 0);
+}
+__device__ __forceinline__ void bwd_prefetch(const BwdParams& p, int s, int gm, int c0g, BwdPre& pre) {
+  if (!bwd_vec_ok(p)) return;
+  if (p.fgsm_x) {
+    const float* xr = p.fgsm_x + (long long)gm * p.N + c0g;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pre.q[i] = (c0g + i * 4 + 4 <= p.N) ? __ldg(reinterpret_cast<const uint4*>(xr + i * 4)) : make_uint4(0u, 0u, 0u, 0u);
+  } else if (p.aprev) {
+    const __nv_bfloat16* ap = p.aprev + (long long)s * p.ap_sstride + (long long)gm * p.ld_ap + c0g;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pre.q[i] = (c0g + i * 8 + 8 <= p.N) ? __ldg(reinterpret_cast<const uint4*>(ap + i * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // one thread's 32 accumulator columns [c0g, c0g + 32) of row gm, sample s
-__device__ __forceinline__ void bwd_epilogue32(const BwdParams& p, int s, int gm, int c0g, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void bwd_epilogue32(const BwdParams& p, int s, int gm, int c0g, const uint32_t (&v)[32], const BwdPre& pre) {
+  const bool vec = bwd_vec_ok(p);
+  // The epilogue is ONE warp per scheduler walking its rows: its time is instructions x issue latency (ncu: 18 cycles per
+  // instruction, 360 instructions per 32 columns with per-element guards).  Whole groups inside the matrix with 16-byte
+  // pitches take this guard-free form.
+  if (vec && c0g + 32 <= p.N && p.out16 && (p.ld16 & 7) == 0 && !p.fgsm_x && (p.act == DBX_ACT_RELU || p.aprev == nullptr)) {
+    uint4* dst = reinterpret_cast<uint4*>(p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + c0g);
+    const bool mask = p.aprev != nullptr;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint32_t aw[4] = {pre.q[q4].x, pre.q[q4].y, pre.q[q4].z, pre.q[q4].w};
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo = __uint_as_float(v[q4 * 8 + 2 * i]), hi = __uint_as_float(v[q4 * 8 + 2 * i + 1]);
+        if (mask) {      // relu'(a) = [a > 0] on the stored bf16 output
+          lo = __uint_as_float(aw[i] << 16) > 0.f ? lo : 0.f;
+          hi = __uint_as_float(aw[i] & 0xFFFF0000u) > 0.f ? hi : 0.f;
+        }
+        w[i] = pack_bf16x2(lo, hi);
+      }
+      dst[q4] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return;
+  }
+  if (vec && c0g + 32 <= p.N && p.fgsm_x && p.out16 && (p.ld16 & 7) == 0 && p.aprev == nullptr) {
+    uint4* dst = reinterpret_cast<uint4*>(p.out16 + (long long)s * p.o16_sstride + (long long)gm * p.ld16 + c0g);
+    const float e = p.fgsm_eps, lo_b = p.fgsm_lo, hi_b = p.fgsm_hi;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint4 xl = pre.q[2 * q4], xh = pre.q[2 * q4 + 1];
+      const float xe[8] = {__uint_as_float(xl.x), __uint_as_float(xl.y), __uint_as_float(xl.z), __uint_as_float(xl.w),
+                           __uint_as_float(xh.x), __uint_as_float(xh.y), __uint_as_float(xh.z), __uint_as_float(xh.w)};
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float g = __uint_as_float(v[q4 * 8 + i]);
+        // x + eps sign(g) lies in [x - eps, x + eps] already (attacks.py:94-99); only the model's input range clips
+        const float step = g > 0.f ? e : (g < 0.f ? -e : 0.f);
+        a[i] = fminf(fmaxf(fminf(fmaxf(xe[i] + step, xe[i] - e), xe[i] + e), lo_b), hi_b);
+      }
+      dst[q4] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+    }
+    return;
+  }
   const __nv_bfloat16* ap = p.aprev ? p.aprev + (long long)s * p.ap_sstride + (long long)gm * p.ld_ap : nullptr;
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
@@ -202,9 +270,8 @@ __device__ __forceinline__ void bwd_epilogue32(const BwdParams& p, int s, int gm
       for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(v[q4 * 8 + i]);
       const bool whole = c + 8 <= p.N;
       if (ap) {
-        if (whole && (p.ld_ap & 7) == 0) {
-          const uint4 a8 = *reinterpret_cast<const uint4*>(ap + c);
-          const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+        if (whole && vec) {
+          const uint32_t aw[4] = {pre.q[q4].x, pre.q[q4].y, pre.q[q4].z, pre.q[q4].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             d[2 * i] *= act_deriv(p.act, __uint_as_float(aw[i] << 16));
@@ -217,13 +284,21 @@ __device__ __forceinline__ void bwd_epilogue32(const BwdParams& p, int s, int gm
         }
       }
       if (p.fgsm_x) {
-        const float* xr = p.fgsm_x + (long long)gm * p.N + c;
+        float xe[8];
+        if (vec) {      // N % 4 == 0: a float4 is inside the row or outside (then zero, and its columns are not stored)
+          const uint4 lo = pre.q[2 * q4], hi = pre.q[2 * q4 + 1];
+          xe[0] = __uint_as_float(lo.x); xe[1] = __uint_as_float(lo.y); xe[2] = __uint_as_float(lo.z); xe[3] = __uint_as_float(lo.w);
+          xe[4] = __uint_as_float(hi.x); xe[5] = __uint_as_float(hi.y); xe[6] = __uint_as_float(hi.z); xe[7] = __uint_as_float(hi.w);
+        } else {
+          const float* xr = p.fgsm_x + (long long)gm * p.N + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xe[i] = (c + i < p.N) ? xr[i] : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float xe = (c + i < p.N) ? xr[i] : 0.f;
           const float sgn = d[i] > 0.f ? 1.f : (d[i] < 0.f ? -1.f : 0.f);
-          float a = xe + p.fgsm_eps * sgn;
-          a = fminf(fmaxf(a, xe - p.fgsm_eps), xe + p.fgsm_eps);
+          float a = xe[i] + p.fgsm_eps * sgn;
+          a = fminf(fmaxf(a, xe[i] - p.fgsm_eps), xe[i] + p.fgsm_eps);
           d[i] = fminf(fmaxf(a, p.fgsm_lo), p.fgsm_hi);
         }
       }
@@ -251,7 +326,7 @@ __device__ __forceinline__ void bwd_epilogue32(const BwdParams& p, int s, int gm
 }
 
 template <int kNTMax>
-__global__ void __launch_bounds__(kGThreads, kNTMax == 256 ? 1 : (kNTMax == 128 ? 2 : 3))
+__global__ void __launch_bounds__(kGThreads, kNTMax == 256 ? 1 : 2)
 dense_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const BwdParams p) {
   constexpr int kStageB = 16384 + kNTMax * 128;
   constexpr int kSt = kNTMax == 64 ? 3 : kGStages;
@@ -311,13 +386,21 @@ dense_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_consta
     const int g = warp & 3;
     const int gm = m0 + g * 32 + lane;
     const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    const bool live = gm < p.M;
+    BwdPre preA, preB;      // nt is a multiple of 64: column groups go in pairs, each group's loads in flight during the one before
+    if (live) bwd_prefetch(p, s, gm, n0, preA);
     mbar_wait(smem_u32(&bars->acc_full), 0);
     fence_after_sync();
-    for (int c0 = 0; c0 < nt; c0 += 32) {
+    for (int c0 = 0; c0 < nt; c0 += 64) {
       uint32_t v[32];
       tmem_ld32(tmem + lane_base + c0, v);
+      if (live) bwd_prefetch(p, s, gm, n0 + c0 + 32, preB);
       wait_ld();
-      if (gm < p.M) bwd_epilogue32(p, s, gm, n0 + c0, v);
+      if (live) bwd_epilogue32(p, s, gm, n0 + c0, v, preA);
+      tmem_ld32(tmem + lane_base + c0 + 32, v);
+      if (live && c0 + 64 < nt) bwd_prefetch(p, s, gm, n0 + c0 + 64, preA);
+      wait_ld();
+      if (live) bwd_epilogue32(p, s, gm, n0 + c0 + 32, v, preB);
     }
   }
   fence_before_sync();
@@ -414,18 +497,26 @@ dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __gri
       const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
       const int gm = m0 + gq * 32 + lane;
       const uint32_t ab = it & 1;
+      const bool live = gm < p.M;
+      BwdPre preA, preB;      // nt is a multiple of 64: column groups go in pairs, each group's loads in flight during the one before
+      if (live) bwd_prefetch(p, s, gm, n0, preA);
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
-      for (int c0 = 0; c0 < nt; c0 += 32) {
+      for (int c0 = 0; c0 < nt; c0 += 64) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + ab * kNT + c0, v);
+        if (live) bwd_prefetch(p, s, gm, n0 + c0 + 32, preB);
         wait_ld();
-        if (c0 + 32 >= nt) {   // the whole accumulator is in registers: the MMA warp may reuse it
+        if (live) bwd_epilogue32(p, s, gm, n0 + c0, v, preA);
+        tmem_ld32(tmem + lane_base + ab * kNT + c0 + 32, v);
+        if (live && c0 + 64 < nt) bwd_prefetch(p, s, gm, n0 + c0 + 64, preA);
+        wait_ld();
+        if (c0 + 64 >= nt) {   // the whole accumulator is in registers: the MMA warp may reuse it
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
         }
-        if (gm < p.M) bwd_epilogue32(p, s, gm, n0 + c0, v);
+        if (live) bwd_epilogue32(p, s, gm, n0 + c0 + 32, v, preB);
       }
     }
   }
@@ -1692,7 +1783,9 @@ int dense_tc_bwd_launch(const __nv_bfloat16* dZ, long long dz_sstride, int ldz, 
   p.aprev = aprev; p.ap_sstride = ap_sstride; p.ld_ap = ld_ap; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
   p.fgsm_x = fgsm_x; p.fgsm_eps = fgsm_eps; p.fgsm_lo = fgsm_lo; p.fgsm_hi = fgsm_hi;
-  const int ntc = fan_in <= 64 ? 64 : (fan_in <= 128 ? 128 : 256);      // column tile = template width = rows of the weight box
+  // column tile = template width = rows of the weight box.  128 columns even for wide layers: two CTAs per SM = two epilogue
+  // warps per scheduler (these GEMMs have few rows per sample and are bound by their epilogue's instruction latency)
+  const int ntc = fan_in <= 64 ? 64 : 128;
   p.NT = ntc;
   CUtensorMap tmZ, tmW;
   {
