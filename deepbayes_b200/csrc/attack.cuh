@@ -390,7 +390,7 @@ static int grad_tc_forward(dbx_model* m, const GradTcBufs& g, const __nv_bfloat1
     prof_begin(st);
     if (dense_tc_launch(cur, cur_ss, (int)L.in_feat, cur_ss == 0 ? 1 : 0, g.W16 + L.w16_off, m->P16, (int)L.w_cols_pad, nc, (int)B, L.units,
                         (int)L.in_feat, g.B32, m->PB, L.b32_off, last ? DBX_ACT_LINEAR : L.act, last ? nullptr : g.acts[i], B * L.units, L.units,
-                        last ? g.logits : nullptr, B * m->out_feat, st)) {
+                        last ? g.logits : nullptr, B * m->out_feat, st, B <= 128 ? 128 : 256)) {
       set_err("dense_tc launch failed (gradient forward)"); return 1;
     }
     prof_end(st, 2.0 * (double)L.w_rows * L.w_cols * (double)B * nc);
@@ -459,12 +459,14 @@ static int run_count_fgsm_tc(dbx_model* m, const float* x_dev, int64_t B, const 
   ns = std::min<int64_t>(std::min<int64_t>(ns, n), 256);
   if (ensure_ws(m->ws, (size_t)ns * per + fixed)) return 1;
   grad_tc_carve(m, B, (int)ns, true, (char*)m->ws.ptr, g, nwb);
-  cudaStream_t sst = st;
-  if (overlap) {
-    if (ensure_side_streams(m)) return 1;
+  cudaStream_t sst = st, caller = st;
+  if (overlap) {      // GEMM chain on the engine's high-priority stream, sampling on the side stream, both joined with the caller's
+    if (ensure_side_streams(m) || ensure_main_stream(m)) return 1;
     sst = m->ibp_side;
-    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], st));
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], caller));
     DBX_CUDA(cudaStreamWaitEvent(sst, m->ibp_ev[0], 0));
+    DBX_CUDA(cudaStreamWaitEvent(m->ibp_main, m->ibp_ev[0], 0));
+    st = m->ibp_main;
   }
   auto draw_chunk = [&](int64_t cj) -> int {
     const int b = (int)(cj & 1) % nwb;
@@ -502,9 +504,11 @@ static int run_count_fgsm_tc(dbx_model* m, const float* x_dev, int64_t B, const 
       DBX_LAUNCH(act_rows_kernel, grid_for((int64_t)nc * B), 256, 0, st, (int)DBX_ACT_SOFTMAX, dst, (int64_t)nc * B, C);
     }
   }
-  if (overlap) {      // join (an error path may have left work on the side stream)
+  if (overlap) {      // join
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[5], st));
+    DBX_CUDA(cudaStreamWaitEvent(caller, m->ibp_ev[5], 0));
     DBX_CUDA(cudaEventRecord(m->ibp_ev[0], sst));
-    DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[0], 0));
+    DBX_CUDA(cudaStreamWaitEvent(caller, m->ibp_ev[0], 0));
   }
   return 0;
 }

@@ -669,6 +669,16 @@ static int ensure_side_streams(dbx_model* m) {
   return 0;
 }
 
+// high-priority stream of the GEMM chains: their CTAs are placed ahead of the sampler's blocks, which fill what is left
+static int ensure_main_stream(dbx_model* m) {
+  if (!m->ibp_main) {
+    int lo = 0, hi = 0;
+    DBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    DBX_CUDA(cudaStreamCreateWithPriority(&m->ibp_main, cudaStreamNonBlocking, hi));
+  }
+  return 0;
+}
+
 template <typename T>
 static int run_generic(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Source& src, const Sink& sink,
                        cudaStream_t st, cudaStream_t sst = nullptr) {
@@ -965,11 +975,7 @@ static int run(dbx_model* m, const float* x_dev, int64_t B, int64_t n, const Sou
       return rg0;
     }
     if (ensure_side_streams(m)) return 1;
-    if (!m->ibp_main) {
-      int lo = 0, hi = 0;
-      DBX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      DBX_CUDA(cudaStreamCreateWithPriority(&m->ibp_main, cudaStreamNonBlocking, hi));
-    }
+    if (ensure_main_stream(m)) return 1;
     DBX_CUDA(cudaEventRecord(m->ibp_ev[0], st));
     DBX_CUDA(cudaStreamWaitEvent(m->ibp_side, m->ibp_ev[0], 0));
     DBX_CUDA(cudaStreamWaitEvent(m->ibp_main, m->ibp_ev[0], 0));

@@ -125,7 +125,7 @@ void fused_mlp_free(dbx_model* m);
 int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const __nv_bfloat16* Wbase,
                     long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride,
                     long long b_off, int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32,
-                    long long o32_sstride, cudaStream_t st);
+                    long long o32_sstride, cudaStream_t st, int nt_cap = 256);      // nt_cap 128: narrower column tiles, two CTAs per SM
 int dense_tc_bwd_launch(const __nv_bfloat16* dZ, long long dz_sstride, int ldz, const __nv_bfloat16* Wbase, long long w_sstride_elems,
                         int ldw, int ns, int M, int fan_in, int fan_out, const __nv_bfloat16* aprev, long long ap_sstride, int ld_ap,
                         int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32, long long o32_sstride,

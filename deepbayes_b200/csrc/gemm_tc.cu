@@ -1665,7 +1665,7 @@ static bool g_tc_ok = true;
 int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_shared, const __nv_bfloat16* Wbase,
                     long long w_sstride_elems, int ldw, int ns, int M, int N, int K, const float* bias, long long b_sstride,
                     long long b_off, int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32,
-                    long long o32_sstride, cudaStream_t st) {
+                    long long o32_sstride, cudaStream_t st, int nt_cap) {
   if (!g_tc_ok || !get_encode_fn()) return 1;
   CUtensorMap tmA, tmW;
   if (a_shared) {
@@ -1683,7 +1683,7 @@ int dense_tc_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_
     if (!make_tmap_bf16(&tmW, (void*)Wbase, 3, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   GemmParams p = {};
-  p.M = M; p.N = N; p.K = K; p.NT = (int)std::min<int64_t>(256, round_up(N, 64));
+  p.M = M; p.N = N; p.K = K; p.NT = (int)std::min<int64_t>(nt_cap >= 128 ? std::min(nt_cap, 256) : 256, round_up(N, 64));
   p.a_shared = a_shared; p.bias = bias; p.b_sstride = b_sstride; p.b_off = b_off; p.rows = nullptr; p.row0 = 0; p.act = act;
   p.out16 = out16; p.o16_sstride = o16_sstride; p.ld16 = ld16; p.out32 = out32; p.o32_sstride = o32_sstride;
   const int ka = act_class(act);
