@@ -61,9 +61,9 @@ _SIGS = {
     "dbx_bbb_forward": (C.c_int, [_p, _p, _i64, _u64, _i64, _p, _i32, _p, _p, _p, _p]),
     "dbx_count_predicate": (C.c_int, [_p, _p, _i64, _p, _i64, _u64, _i64, _p, _f, _i32, _i32, _p, _p, _p]),
     "dbx_bbb_step": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, C.c_uint64, _i64, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
-                               C.c_float, C.c_float, _p, _p, _p, _p]),
+                               C.c_float, C.c_float, C.c_int32, _p, _p, _p, _p]),
     "dbx_bbb_train_epoch": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, C.c_uint64, _i64, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
-                                      C.c_float, C.c_float, _p, _p, _p, _p]),
+                                      C.c_float, C.c_float, C.c_int32, _p, _p, _p, _p]),
     "dbx_bbb_step_ibp_mc": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, C.c_uint64, _i64, C.c_float, C.c_float, C.c_int32, _p, _p, _p, _p, _p]),
     "dbx_input_gradient": (C.c_int, [_p, _p, _i64, _p, _i64, _i64, C.c_uint64, _i64, _p, C.c_float, C.c_int32, _i64, _p, C.c_int32, _p, _p]),
     "dbx_input_gradient_one": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p]),

@@ -1273,14 +1273,15 @@ int dbx_bbb_forward(dbx_handle h, const float* x_dev, int64_t B, uint64_t seed, 
 int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                  const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                  float lrate, float kl_weight, int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper,
-                 float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
+                 int32_t mode, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
   DBX_CHECK(h && x_dev && labels_dev && mean_dev && rho_dev && prior_mean_dev && prior_var_dev, "null argument");
   DBX_CHECK(B > 0, "B must be positive");
+  DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
   DBX_CHECK(robust_mode >= 0 && robust_mode <= 2, "robust_mode %d: 0, 1, 2 here; the epsilon-draw mode 3 is dbx_bbb_step_ibp_mc", robust_mode);
   DBX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (run_bbb_step(h, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
-                   loss_out_dev, probs_out_dev, robust_mode, epsilon, robust_lambda, in_lower, in_upper, st))
+                   loss_out_dev, probs_out_dev, robust_mode, epsilon, robust_lambda, in_lower, in_upper, st, 0, nullptr, mode))
     return 1;
   if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));   // W is the first workspace block
   return 0;
@@ -1288,10 +1289,11 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
 
 int dbx_bbb_train_epoch(dbx_handle h, const float* x_dev, const int32_t* labels_dev, int64_t N, int64_t batch, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, uint64_t seed, int64_t step0, float lrate, float kl_weight,
-                        int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper, float* loss_out_dev,
-                        float* probs_out_dev, float* W_out_dev, void* stream) {
+                        int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper, int32_t mode,
+                        float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream) {
   DBX_CHECK(h && x_dev && labels_dev && mean_dev && rho_dev && prior_mean_dev && prior_var_dev, "null argument");
   DBX_CHECK(N > 0 && batch > 0, "N and batch must be positive");
+  DBX_CHECK(mode == DBX_MODE_BF16 || mode == DBX_MODE_FP32, "unknown mode %d", mode);
   DBX_CHECK(robust_mode >= 0 && robust_mode <= 2, "robust_mode %d: 0, 1, 2 here (the epsilon-draw mode 3 needs host draws per step: dbx_bbb_step_ibp_mc)", robust_mode);
   DBX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1300,7 +1302,7 @@ int dbx_bbb_train_epoch(dbx_handle h, const float* x_dev, const int32_t* labels_
     const int64_t Bb = std::min(batch, N - b0);
     if (run_bbb_step(h, x_dev + b0 * h->in_feat, Bb, labels_dev + b0, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, nullptr, seed, step0 + i,
                      lrate, kl_weight, loss_out_dev ? loss_out_dev + 2 * i : nullptr, probs_out_dev ? probs_out_dev + b0 * h->out_feat : nullptr,
-                     robust_mode, epsilon, robust_lambda, in_lower, in_upper, st))
+                     robust_mode, epsilon, robust_lambda, in_lower, in_upper, st, 0, nullptr, mode))
       return 1;
   }
   if (W_out_dev) DBX_CUDA(cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, st));   // the last step's sample

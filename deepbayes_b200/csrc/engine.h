@@ -130,6 +130,8 @@ int dense_tc_bwd_launch(const __nv_bfloat16* dZ, long long dz_sstride, int ldz, 
                         int ldw, int ns, int M, int fan_in, int fan_out, const __nv_bfloat16* aprev, long long ap_sstride, int ld_ap,
                         int act, __nv_bfloat16* out16, long long o16_sstride, int ld16, float* out32, long long o32_sstride,
                         cudaStream_t st, const float* fgsm_x = nullptr, float fgsm_eps = 0.f, float fgsm_lo = 0.f, float fgsm_hi = 0.f);
+int dense_tc_wgrad_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* dZ, int ldz, int B, int fan_in, int fan_out, float* out,
+                          int accumulate, cudaStream_t st);
 int dense_tc_f32w_launch(const __nv_bfloat16* A, long long a_sstride, int lda, int a_rep, const float* slab, long long slab_stride,
                          long long slab_rows, long long w_off, const int32_t* w_rows, long long w_row0, int ns, int M, int N, int K,
                          const float* bias, long long b_sstride, long long b_off, int act, __nv_bfloat16* out16,

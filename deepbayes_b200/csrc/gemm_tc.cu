@@ -526,6 +526,112 @@ dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __gri
 }
 
 // =======================================================================================
+// Weight-gradient GEMM of a Dense layer (Bayes-by-Backprop step, bayesbybackprop.py:138-170: dL/dW of the sampled weights):
+//     dW (fan_in x fan_out, fp32, Keras layout)  (+)=  A^T (fan_in x B)  *  dZ (B x fan_out)
+// The reduction runs over the BATCH rows, which is the slow axis of both operands as they lie in memory (A = the layer's
+// bf16 input [B][fan_in], dZ = the bf16 upstream gradient [B][fan_out]): both are MN-major operands -- TMA boxes
+// [64 columns x 64 batch rows], SWIZZLE_128B, 64-column blocks 8 KB apart (LBO), 8-row groups 1 KB apart (SBO), the layout the
+// forward kernels use for the Keras kernel.  No transposed copy of the activations exists.  One CTA per 128 x <=256 tile of dW.
+// =======================================================================================
+struct WgradParams {
+  int Kin, N, B, NT;        // dW is Kin x N; B = reduction length
+  float* out; int accumulate;
+};
+
+template <int kNTMax>
+__global__ void __launch_bounds__(kGThreads, kNTMax == 256 ? 1 : 2)
+dense_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmZ, const WgradParams p) {
+  constexpr int kStageB = 16384 + (kNTMax / 64) * 8192;
+  constexpr int kSt = kNTMax == 64 ? 3 : kGStages;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t s_stage = smem_u32(smem);
+  GBarriers* bars = (GBarriers*)(smem + kSt * kStageB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * p.NT, m0 = blockIdx.y * 128;
+  const int nt = min(p.NT, ((p.N - n0 + 63) / 64) * 64);
+  const int nblk = nt / 64;
+  const int kb_n = (p.B + 63) / 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < kSt; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kNTMax>(smem_u32(&bars->tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmZ); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const uint32_t st = kb % kSt, ph = (kb / kSt) & 1;
+      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&bars->full[st]);
+        const uint32_t base = s_stage + st * kStageB;
+        // (a tile's upper 64 rows may lie wholly outside dW: that block is not fetched, its accumulator rows are never stored)
+        const bool up = m0 + 64 < p.Kin;
+        mbar_expect_tx(fb, (up ? 16384 : 8192) + nblk * 8192);
+        tma_load_2d(base, &tmA, fb, m0, kb * 64);                  // fan_in columns [m0, m0 + 64) of batch rows [kb*64, +64)
+        if (up) tma_load_2d(base + 8192, &tmA, fb, m0 + 64, kb * 64);
+        for (int nb = 0; nb < nblk; ++nb) tma_load_2d(base + 16384 + nb * 8192, &tmZ, fb, n0 + nb * 64, kb * 64);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = make_idesc_bf16(128, nt, 1, 1);
+    for (int kb = 0; kb < kb_n; ++kb) {
+      const uint32_t st = kb % kSt, ph = (kb / kSt) & 1;
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a16 = ((s_stage + st * kStageB) & 0x3FFFF) >> 4;
+        const uint32_t a_lo = a16 | ((8192u >> 4) << 16);
+        const uint32_t b_lo = (a16 + (16384 >> 4)) | ((8192u >> 4) << 16);
+        const int ksteps = min(4, (p.B - kb * 64 + 15) / 16);
+        for (int kk = 0; kk < ksteps; ++kk)
+          mma_ss_lh(tmem, a_lo + kk * 128, kDescHi128, b_lo + kk * 128, kDescHi128, idesc, (kb | kk) > 0);
+        mma_commit(smem_u32(&bars->empty[st]));
+        if (kb == kb_n - 1) mma_commit(smem_u32(&bars->acc_full));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int g = warp & 3;
+    const int gm = m0 + g * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    mbar_wait(smem_u32(&bars->acc_full), 0);
+    fence_after_sync();
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_base + c0, v);
+      wait_ld();
+      if (gm < p.Kin) {
+        float* dst = p.out + (long long)gm * p.N + n0 + c0;
+        if (n0 + c0 + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            if (p.accumulate) { const float4 old = *reinterpret_cast<const float4*>(dst + 4 * q); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            *reinterpret_cast<float4*>(dst + 4 * q) = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + c0 + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(v[i]) : __uint_as_float(v[i]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kNTMax>(tmem);
+}
+
+// =======================================================================================
 // Persistent variant of dense_tc_kernel.  A CTA per tile spends most of a short tile's life in the serial chain
 // TMEM alloc -> barrier init -> TMA -> MMA -> epilogue (config 4's first conv: 6 us per 128 x 32 tile with one
 // k-block; the IBP GEMMs at B = 128: 50 us per CTA at 1.1 TB/s).  Here the CTAs (1 or 2 per SM) walk a contiguous range
@@ -1821,6 +1927,40 @@ int dense_tc_bwd_launch(const __nv_bfloat16* dZ, long long dz_sstride, int ldz, 
     return 0;
   };
   const int rc = ntc == 64 ? go(dense_tc_bwd_kernel<64>, 64) : (ntc == 128 ? go(dense_tc_bwd_kernel<128>, 128) : go(dense_tc_bwd_kernel<256>, 256));
+  if (rc) return 1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// dW (+)= A^T dZ (dense_tc_wgrad_kernel).  A: bf16 [B][lda] (the layer's input), dZ: bf16 [B][ldz]; out fp32 [fan_in][fan_out].
+// lda, ldz multiples of 8, 16-byte aligned bases; returns 1 when not applicable.
+int dense_tc_wgrad_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* dZ, int ldz, int B, int fan_in, int fan_out, float* out,
+                          int accumulate, cudaStream_t st) {
+  if (!g_tc_ok || !get_encode_fn()) return 1;
+  if ((lda & 7) || (ldz & 7) || ((uintptr_t)A & 15) || ((uintptr_t)dZ & 15) || ((uintptr_t)out & 15)) return 1;
+  WgradParams p = {};
+  p.Kin = fan_in; p.N = fan_out; p.B = B; p.out = out; p.accumulate = accumulate;
+  const int ntc = fan_out <= 64 ? 64 : (fan_out <= 128 ? 128 : 256);
+  p.NT = ntc;
+  CUtensorMap tmA, tmZ;
+  {
+    uint64_t d[2] = {(uint64_t)fan_in, (uint64_t)B}, sb[1] = {(uint64_t)lda * 2};
+    uint32_t b[2] = {64, 64};
+    if (!make_tmap_bf16(&tmA, (void*)A, 2, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t d[2] = {(uint64_t)fan_out, (uint64_t)B}, sb[1] = {(uint64_t)ldz * 2};
+    uint32_t b[2] = {64, 64};
+    if (!make_tmap_bf16(&tmZ, (void*)dZ, 2, d, sb, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  dim3 grid((unsigned)cdiv(fan_out, ntc), (unsigned)cdiv(fan_in, 128), 1);
+  auto go = [&](auto kern, int ntmax) -> int {
+    const int smem = (ntmax == 64 ? 3 : kGStages) * (16384 + (ntmax / 64) * 8192) + (int)sizeof(GBarriers) + 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 1;
+    kern<<<grid, kGThreads, smem, st>>>(tmA, tmZ, p);
+    return 0;
+  };
+  const int rc = ntc == 64 ? go(dense_tc_wgrad_kernel<64>, 64) : (ntc == 128 ? go(dense_tc_wgrad_kernel<128>, 128) : go(dense_tc_wgrad_kernel<256>, 256));
   if (rc) return 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

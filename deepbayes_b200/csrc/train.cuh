@@ -427,11 +427,26 @@ __global__ void bbb_loss_kernel(const float* __restrict__ row_loss, int B, const
   out[1] = qp - pr;
 }
 
+static bool grad_tc_ok(const dbx_model* m);      // attack.cuh
+static int run_bbb_step_tc_fwd(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                               const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                               float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
+                               float robust_lambda, float in_lower, float in_upper, cudaStream_t st);
 static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                         float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
-                        float robust_lambda, float in_lower, float in_upper, cudaStream_t st, int n_eps = 0, const float* eps_list = nullptr) {
+                        float robust_lambda, float in_lower, float in_upper, cudaStream_t st, int n_eps = 0, const float* eps_list = nullptr,
+                        int mode = DBX_MODE_FP32) {
   DBX_CHECK(m->is_mlp, "the device training step covers Dense MLPs (bayesbybackprop.py:46-170)");
+  DBX_CHECK(m->layers[m->last_weighted].act == DBX_ACT_SOFTMAX, "the device training step needs a softmax output (sparse categorical cross-entropy)");
+  // bf16 mode: tensor-core GEMMs for the standard and the FGSM step when every Dense width suits TMA; the interval modes and
+  // everything else stay on the fp32 kernels
+  g_last_path = 0;
+  if (mode == DBX_MODE_BF16 && (robust_mode == 0 || robust_mode == 2) && grad_tc_ok(m)) {
+    g_last_path = 3;
+    return run_bbb_step_tc_fwd(m, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
+                               loss_out_dev, probs_out_dev, robust_mode, epsilon, robust_lambda, in_lower, in_upper, st);
+  }
   DBX_CHECK(robust_mode >= 0 && robust_mode <= 3, "robust_train %d is not built (0 = standard, 1 = IBP, 2 = FGSM adversarial training, 3 = IBP over draws of epsilon)", robust_mode);
   DBX_CHECK(robust_mode != 3 || (n_eps >= 1 && n_eps <= 64 && eps_list), "robust_train 3 needs 1..64 epsilon draws");
   const Layer& Lout = m->layers[m->last_weighted];
@@ -588,6 +603,153 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
              prior_mean_dev, prior_var_dev, P, tt, lrate, kl_weight, partial);
   if (loss_out_dev) DBX_LAUNCH(bbb_loss_kernel, 1, 32, 0, st, (const float*)row_loss, (int)B, (const float*)partial, ublocks, kl_weight, loss_out_dev);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// bf16 mode of the training step (robust_train 0 and 2): the three GEMMs of every layer on the tensor cores --
+//   forward   Z = A W + b            dense_tc_kernel (the inference GEMM, one "sample" = the step's own weights)
+//   backward  dA = (dZ W^T) .* act'  dense_tc_bwd_kernel (K-major view of the Keras kernel; FGSM step in its epilogue for mode 2)
+//   weights   dW = A^T dZ            dense_tc_wgrad_kernel (both operands MN-major as they lie in memory)
+// with the sampled weights, the activations and the upstream gradients rounded to bf16 as GEMM operands and everything else
+// (the draw W = mean + softplus(rho) * noise, biases, softmax / cross-entropy, the KL terms, the update of mean and rho) in fp32
+// exactly as in the fp32 step.  The parameters themselves never leave fp32.
+// ---------------------------------------------------------------------------------------
+__global__ void dz_to_bf16_kernel(const float* __restrict__ dz, int B, int C, int Cp, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)B * Cp;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(o % Cp);
+    out[o] = __float2bfloat16_rn(c < C ? dz[(o / Cp) * C + c] : 0.f);
+  }
+}
+
+// db[n] = sum_b dZ[b, n], dZ as the GEMMs see it (bf16), summed in fp32 in row order
+__global__ void grad_b_bf16_kernel(const __nv_bfloat16* __restrict__ dZ, int ldz, int B, int N, float* __restrict__ db, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float a = 0.f;
+  for (int b = 0; b < B; ++b) a += __bfloat162float(dZ[(int64_t)b * ldz + n]);
+  db[n] = accumulate ? db[n] + a : a;
+}
+
+static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                           const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                           float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
+                           float robust_lambda, float in_lower, float in_upper, cudaStream_t st) {
+  const int64_t P = m->P, C = m->out_feat, K0 = m->in_feat;
+  std::vector<const Layer*> dl;
+  for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
+  const int nl = (int)dl.size();
+  const int Cp = (int)round_up(C, 8);
+  int64_t hmax = 8;
+  size_t act16_total = 0;
+  for (int i = 0; i + 1 < nl; ++i) { act16_total += round_up((size_t)B * dl[i]->units * 2, 256); hmax = std::max<int64_t>(hmax, dl[i]->units); }
+  const size_t pb = round_up((size_t)P * 4, 256), ob = round_up((size_t)B * C * 4, 256), x16b = round_up((size_t)B * K0 * 2, 256);
+  const size_t dbb = round_up((size_t)B * hmax * 2, 256);
+  const int ublocks = sm_count() * 4;
+  const size_t need = 3 * pb + round_up((size_t)m->P16 * 2, 256) + round_up((size_t)m->PB * 4, 256) + 2 * x16b + 2 * act16_total + 5 * ob +
+                      round_up((size_t)B * Cp * 2, 256) + 2 * dbb + round_up((size_t)B * 4, 256) + round_up((size_t)ublocks * 8, 256) + 4096;
+  if (ensure_ws(m->ws, need)) return 1;
+  char* p = (char*)m->ws.ptr;
+  auto take = [&](size_t bytes) { char* r = p; p += round_up(bytes, 256); return r; };
+  float* W = (float*)take(pb);              // (dbx_bbb_step copies the sampled weights out of this first block)
+  float* noise = (float*)take(pb);
+  float* gdata = (float*)take(pb);
+  __nv_bfloat16* W16 = (__nv_bfloat16*)take((size_t)m->P16 * 2);
+  float* B32 = (float*)take((size_t)m->PB * 4);
+  __nv_bfloat16* xin = (__nv_bfloat16*)take(x16b);
+  __nv_bfloat16* xadv = (__nv_bfloat16*)take(x16b);
+  std::vector<__nv_bfloat16*> acts(std::max(0, nl - 1)), acts_adv(std::max(0, nl - 1));
+  for (int i = 0; i + 1 < nl; ++i) acts[i] = (__nv_bfloat16*)take((size_t)B * dl[i]->units * 2);
+  for (int i = 0; i + 1 < nl; ++i) acts_adv[i] = (__nv_bfloat16*)take((size_t)B * dl[i]->units * 2);
+  float* logits = (float*)take(ob);
+  float* logits_adv = (float*)take(ob);
+  float* dz32 = (float*)take(ob);
+  float* dz_adv32 = (float*)take(ob);
+  float* probs_scratch = (float*)take(ob);
+  __nv_bfloat16* dz16 = (__nv_bfloat16*)take((size_t)B * Cp * 2);
+  __nv_bfloat16* dbuf[2] = {(__nv_bfloat16*)take(dbb), (__nv_bfloat16*)take(dbb)};
+  float* row_loss = (float*)take((size_t)B * 4);
+  float* partial = (float*)p;
+  float* probs = probs_out_dev ? probs_out_dev : probs_scratch;
+
+  DBX_LAUNCH(bbb_sample_kernel, grid_for((P + 3) / 4), 256, 0, st, mean_dev, rho_dev, noise_dev, seed, step, P, W, noise);
+  {   // the step's weights in the GEMMs' bf16 layout (kernels padded / aligned for TMA, biases fp32): W read as ONE stored sample
+    const float* keep = m->slab; const int64_t keepS = m->S, keepStride = m->slab_stride;
+    m->slab = W; m->S = 1; m->slab_stride = P;
+    Source src; src.stored = true; src.j0 = 0;
+    const int rc = launch_sample_bf16(m, m->table, src, 0, 1, W16, B32, st);
+    m->slab = keep; m->S = keepS; m->slab_stride = keepStride;
+    if (rc) return 1;
+  }
+  DBX_LAUNCH(cast_kernel<__nv_bfloat16>, grid_for(B * K0), 256, 0, st, x_dev, xin, B * K0);
+
+  auto forward = [&](const __nv_bfloat16* in, std::vector<__nv_bfloat16*>& out, float* z) -> int {
+    const __nv_bfloat16* cur = in;
+    for (int i = 0; i < nl; ++i) {
+      const Layer& L = *dl[i];
+      const bool last = i == nl - 1;
+      if (dense_tc_launch(cur, 0, (int)L.in_feat, 1, W16 + L.w16_off, m->P16, (int)L.w_cols_pad, 1, (int)B, L.units, (int)L.in_feat, B32, m->PB,
+                          L.b32_off, last ? DBX_ACT_LINEAR : L.act, last ? nullptr : out[i], B * L.units, L.units, last ? z : nullptr, B * C, st)) {
+        set_err("dense_tc launch failed (training forward)"); return 1;
+      }
+      if (!last) cur = out[i];
+    }
+    return 0;
+  };
+  // from dz16 (bf16 [B][Cp], the gradient at the logits): weight / bias gradients into gdata, or (to_input) the FGSM input
+  auto backward = [&](const __nv_bfloat16* in, std::vector<__nv_bfloat16*>& a, bool to_input, int accumulate) -> int {
+    const __nv_bfloat16* dz = dz16; int ldz = Cp; int zi = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      const Layer& L = *dl[i];
+      const __nv_bfloat16* a_prev = (i == 0) ? in : a[i - 1];
+      const int K = (int)L.in_feat, N = L.units;
+      if (!to_input) {
+        if (dense_tc_wgrad_launch(a_prev, K, dz, ldz, (int)B, K, N, gdata + L.w_off, accumulate, st)) { set_err("dense_tc_wgrad launch failed"); return 1; }
+        DBX_LAUNCH(grad_b_bf16_kernel, (int)cdiv(N, 128), 128, 0, st, dz, ldz, (int)B, N, gdata + L.b_off, accumulate);
+      }
+      if (i > 0) {
+        if (dense_tc_bwd_launch(dz, 0, ldz, W16 + L.w16_off, m->P16, (int)L.w_cols_pad, 1, (int)B, K, N, a[i - 1], 0, dl[i - 1]->units, dl[i - 1]->act,
+                                dbuf[zi], 0, K, nullptr, 0, st)) { set_err("dense_tc_bwd launch failed"); return 1; }
+        dz = dbuf[zi]; ldz = K; zi ^= 1;
+      } else if (to_input) {      // FGSM step against the step's own weights in the epilogue: the adversarial batch as the next A operand
+        if (dense_tc_bwd_launch(dz, 0, ldz, W16 + L.w16_off, m->P16, (int)L.w_cols_pad, 1, (int)B, K, N, nullptr, 0, 0, DBX_ACT_LINEAR, xadv, 0, K,
+                                nullptr, 0, st, x_dev, epsilon, in_lower, in_upper)) { set_err("dense_tc_bwd launch failed"); return 1; }
+      }
+    }
+    return 0;
+  };
+  if (forward(xin, acts, logits)) return 1;
+  if (robust_mode == 0) {
+    DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)logits, labels_dev, (int)B, (int)C, probs, dz32, row_loss);
+    DBX_LAUNCH(dz_to_bf16_kernel, grid_for(B * Cp), 256, 0, st, (const float*)dz32, (int)B, (int)C, Cp, dz16);
+    if (backward(xin, acts, false, 0)) return 1;
+  } else {
+    DBX_LAUNCH(attack_upstream_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)logits, (int)B, (int)C, dz32);
+    DBX_LAUNCH(dz_to_bf16_kernel, grid_for(B * Cp), 256, 0, st, (const float*)dz32, (int)B, (int)C, Cp, dz16);
+    if (backward(xin, acts, true, 0)) return 1;
+    if (forward(xadv, acts_adv, logits_adv)) return 1;
+    DBX_LAUNCH(mix_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)logits, (const float*)logits_adv, labels_dev, (int)B, (int)C,
+               robust_lambda, probs, dz32, dz_adv32, row_loss);
+    DBX_LAUNCH(dz_to_bf16_kernel, grid_for(B * Cp), 256, 0, st, (const float*)dz32, (int)B, (int)C, Cp, dz16);
+    if (backward(xin, acts, false, 0)) return 1;
+    DBX_LAUNCH(dz_to_bf16_kernel, grid_for(B * Cp), 256, 0, st, (const float*)dz_adv32, (int)B, (int)C, Cp, dz16);
+    if (backward(xadv, acts_adv, false, 1)) return 1;
+  }
+  DBX_CUDA(cudaGetLastError());
+  TrainTensors tt; tt.n = m->table.n;
+  for (int i = 0; i < tt.n; ++i) { tt.off[i] = m->table.src_off[i]; tt.end[i] = m->table.src_end[i]; }
+  DBX_LAUNCH(bbb_update_kernel, ublocks, 256, 0, st, mean_dev, rho_dev, (const float*)W, (const float*)noise, (const float*)gdata,
+             prior_mean_dev, prior_var_dev, P, tt, lrate, kl_weight, partial);
+  if (loss_out_dev) DBX_LAUNCH(bbb_loss_kernel, 1, 32, 0, st, (const float*)row_loss, (int)B, (const float*)partial, ublocks, kl_weight, loss_out_dev);
+  return 0;
+}
+
+static int run_bbb_step_tc_fwd(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
+                               const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
+                               float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
+                               float robust_lambda, float in_lower, float in_upper, cudaStream_t st) {
+  return run_bbb_step_tc(m, x_dev, B, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, noise_dev, seed, step, lrate, kl_weight,
+                         loss_out_dev, probs_out_dev, robust_mode, epsilon, robust_lambda, in_lower, in_upper, st);
 }
 
 }  // namespace dbx

@@ -249,9 +249,10 @@ class Engine:
 
     def bbb_step(self, x, labels, mean_t, rho_t, prior_mean_t, prior_var_t, lrate, kl_weight=1.0, seed=0, step=0, noise=None,
                  want_probs=True, want_weights=False, robust_mode=0, epsilon=0.0, robust_lambda=1.0, in_lower=-3.0e38, in_upper=3.0e38,
-                 eps_draws=None):
+                 eps_draws=None, mode="fp32"):
         """One Bayes-by-Backprop step (bayesbybackprop.py:46-170) updating the flat device tensors ``mean_t`` / ``rho_t`` in
         place.  robust_mode 3 (IBP averaged over the epsilon draws ``eps_draws``, :102-121) goes through `dbx_bbb_step_ibp_mc`.
+        mode "bf16" (robust_mode 0 / 2): the step's GEMMs on the tensor cores, parameters and update in fp32.
         Returns dict(loss=[loss, kl] device tensor, probs=[B,C] | None, W=[P] | None)."""
         torch = self.torch
         xt = self._x2d(x)
@@ -275,12 +276,12 @@ class Engine:
             return {"loss": loss, "probs": probs, "W": W}
         _lib.check(self.lib.dbx_bbb_step(self.h, _ptr(xt), B, _ptr(lab), _ptr(mean_t), _ptr(rho_t), _ptr(prior_mean_t), _ptr(prior_var_t),
                                          _ptr(e), seed, step, float(lrate), float(kl_weight), int(robust_mode), float(epsilon),
-                                         float(robust_lambda), float(max(in_lower, -3.0e38)), float(min(in_upper, 3.0e38)), _ptr(loss),
-                                         _ptr(probs), _ptr(W), _stream()))
+                                         float(robust_lambda), float(max(in_lower, -3.0e38)), float(min(in_upper, 3.0e38)), _lib.MODE[mode],
+                                         _ptr(loss), _ptr(probs), _ptr(W), _stream()))
         return {"loss": loss, "probs": probs, "W": W}
 
     def bbb_train_epoch(self, x_t, labels_t, batch, mean_t, rho_t, prior_mean_t, prior_var_t, lrate, kl_weight=1.0, seed=0, step0=0,
-                        robust_mode=0, epsilon=0.0, robust_lambda=1.0, in_lower=-3.0e38, in_upper=3.0e38, want_weights=True):
+                        robust_mode=0, epsilon=0.0, robust_lambda=1.0, in_lower=-3.0e38, in_upper=3.0e38, want_weights=True, mode="fp32"):
         """One epoch of Bayes-by-Backprop steps in ONE device call (`dbx_bbb_train_epoch`): ``x_t`` [N,K] fp32 / ``labels_t`` [N]
         int32 CUDA tensors in visiting order.  Returns dict(loss=[nb,2], probs=[N,C], W=[P] | None) device tensors."""
         torch = self.torch
@@ -298,8 +299,8 @@ class Engine:
         W = torch.empty(self.P, dtype=torch.float32, device=self.device) if want_weights else None
         _lib.check(self.lib.dbx_bbb_train_epoch(self.h, _ptr(x_t), _ptr(labels_t), N, int(batch), _ptr(mean_t), _ptr(rho_t), _ptr(prior_mean_t),
                                                 _ptr(prior_var_t), seed, step0, float(lrate), float(kl_weight), int(robust_mode), float(epsilon),
-                                                float(robust_lambda), float(max(in_lower, -3.0e38)), float(min(in_upper, 3.0e38)), _ptr(loss),
-                                                _ptr(probs), _ptr(W), _stream()))
+                                                float(robust_lambda), float(max(in_lower, -3.0e38)), float(min(in_upper, 3.0e38)), _lib.MODE[mode],
+                                                _ptr(loss), _ptr(probs), _ptr(W), _stream()))
         return {"loss": loss, "probs": probs, "W": W}
 
     def input_gradient(self, x, labels, n_outer=1, n_inner=1, seed=0, s0=0, noise=None, inflate=1.0, stored=False, j0=0, mode="fp32", idx=None):

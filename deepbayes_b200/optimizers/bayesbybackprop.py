@@ -100,7 +100,8 @@ class BayesByBackprop(optimizer.Optimizer):
         e = None if noise is None else eng._as_flat(noise)
         res = eng.bbb_step(features, labels, self._d_mean, self._d_rho, self._d_pm, self._d_pv, lrate, self.kl_weight, self.seed,
                            self._take_ids(1), e, want_probs=True, want_weights=sync, robust_mode=mode,
-                           epsilon=epsilon, robust_lambda=lam, in_lower=self.input_lower, in_upper=self.input_upper, eps_draws=draws)
+                           epsilon=epsilon, robust_lambda=lam, in_lower=self.input_lower, in_upper=self.input_upper, eps_draws=draws,
+                           mode=self._train_mode())
         self._last_loss, self._last_probs = res["loss"], res["probs"]
         if sync:
             self.posterior_mean = self._unflat(self._d_mean.cpu().numpy())
@@ -110,6 +111,14 @@ class BayesByBackprop(optimizer.Optimizer):
             self._dirty = True
         self._train_key = (id(self.posterior_mean), id(self.posterior_var))
         return self.posterior_mean, self.posterior_var
+
+    def _train_mode(self):
+        """Arithmetic of the training step's GEMMs: "fp32" (default, what the reference computes) or "bf16" (compile(...,
+        train_mode="bf16"): tensor cores for robust_train 0 / 2 / 4; parameters, losses and the update stay fp32)."""
+        m = getattr(self, "train_mode", None) or "fp32"
+        if m not in ("fp32", "bf16"):
+            raise ValueError("train_mode must be 'fp32' or 'bf16' (got %r)" % (m,))
+        return m
 
     def sync_from_device(self):
         """Copy the device-resident parameters back into posterior_mean / posterior_var (after steps with sync=False)."""
@@ -199,7 +208,7 @@ class BayesByBackprop(optimizer.Optimizer):
         nb = (len(perm) + bs - 1) // bs
         res = eng.bbb_train_epoch(xp, yp, bs, self._d_mean, self._d_rho, self._d_pm, self._d_pv, lrate, self.kl_weight, self.seed,
                                   self._take_ids(nb), robust_mode=mode, epsilon=epsilon, robust_lambda=lam,
-                                  in_lower=self.input_lower, in_upper=self.input_upper)
+                                  in_lower=self.input_lower, in_upper=self.input_upper, mode=self._train_mode())
         self._last_loss, self._last_probs = res["loss"][-1], res["probs"][(nb - 1) * bs:]
         loss = float(res["loss"][:, 0].mean().item())
         acc = float((res["probs"].argmax(1).to(torch.int32) == yp).float().mean().item())

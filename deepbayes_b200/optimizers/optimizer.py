@@ -65,6 +65,7 @@ class Optimizer(ABC):
         self.acc_log, self.rob_log, self.loss_log = [], [], []
         # device-side extras (not in the reference)
         self.compute_mode = kwargs.get('compute_mode', 'fp32')
+        self.train_mode = kwargs.get('train_mode', 'fp32')    # arithmetic of the training step's GEMMs (not in the reference)
         self.seed = int(kwargs.get('seed', np.random.randint(0, 2 ** 31 - 1)))
         self._next_sample = 0
         self._device = kwargs.get('device', None)

@@ -144,11 +144,14 @@ int dbx_count_predicate(dbx_handle h, const float* x_dev, int64_t K, const int32
  * robust_mode = 2 (bayesbybackprop.py:91-101): features_adv = FGSM(features, eps = epsilon) against the step's own
  * weights towards the predicted class, clipped to [in_lower, in_upper], and the data term is evaluated on
  * robust_lambda * predictions + (1 - robust_lambda) * model(features_adv); robust_mode = 0 ignores those arguments.
- * Dense MLPs with a softmax output; fp32 arithmetic. */
+ * Dense MLPs with a softmax output.  mode = DBX_MODE_FP32: fp32 arithmetic throughout (what the reference computes);
+ * DBX_MODE_BF16 (robust_mode 0 and 2, Dense widths multiples of 8; the fp32 kernels otherwise): the forward, backward-data and
+ * weight-gradient GEMMs on the tensor cores with bf16 operands and fp32 accumulation -- the draw of W, biases, losses, KL terms
+ * and the update of mean / rho stay fp32, the parameters never leave fp32. */
 int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                  const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                  float lrate, float kl_weight, int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper,
-                 float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
+                 int32_t mode, float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
 
 /* robust_train == 3 of the same step (bayesbybackprop.py:102-121): the data term is evaluated on
  * output = sum_k (1 / n_eps) * softmax(worst-case IBP logits at eps_host[k]) -- the clean prediction is NOT part of the loss
@@ -165,8 +168,8 @@ int dbx_bbb_step(dbx_handle h, const float* x_dev, int64_t B, const int32_t* lab
  * dbx_bbb_step: bit-identical parameters, without a host round trip per mini-batch. */
 int dbx_bbb_train_epoch(dbx_handle h, const float* x_dev, const int32_t* labels_dev, int64_t N, int64_t batch, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, uint64_t seed, int64_t step0, float lrate, float kl_weight,
-                        int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper, float* loss_out_dev,
-                        float* probs_out_dev, float* W_out_dev, void* stream);
+                        int32_t robust_mode, float epsilon, float robust_lambda, float in_lower, float in_upper, int32_t mode,
+                        float* loss_out_dev, float* probs_out_dev, float* W_out_dev, void* stream);
 int dbx_bbb_step_ibp_mc(dbx_handle h, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                         const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                         float lrate, float kl_weight, int32_t n_eps, const float* eps_host, float* loss_out_dev, float* probs_out_dev,

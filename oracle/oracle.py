@@ -678,6 +678,32 @@ def _mlp_backward_weights(dense, W, acts, dz):
     return gW
 
 
+def _mlp_forward_acts_bf16(dense, W, x):
+    """_mlp_forward_acts as the GPU's bf16 training step computes it: GEMM operands (input, kernels, stored hidden outputs)
+    rounded to bf16, fp32 accumulation / bias / activation; the last entry (the softmax output) stays fp32."""
+    h = bf16_round(x)
+    acts = [h]
+    for li, l in enumerate(dense):
+        h = _act(l.activation, (h @ bf16_round(W[2 * li]) + W[2 * li + 1]).astype(np.float32))
+        if li + 1 < len(dense):
+            h = bf16_round(h)
+        acts.append(h)
+    return acts
+
+
+def _mlp_backward_weights_bf16(dense, W, acts, dz):
+    """_mlp_backward_weights with the same roundings: the upstream gradient of every layer is a bf16 GEMM operand."""
+    gW = [None] * len(W)
+    dz = bf16_round(dz)
+    for li in range(len(dense) - 1, -1, -1):
+        gW[2 * li] = (acts[li].T.astype(np.float64) @ dz.astype(np.float64)).astype(np.float32)
+        gW[2 * li + 1] = dz.astype(np.float64).sum(0).astype(np.float32)
+        if li > 0:
+            da = (dz.astype(np.float64) @ bf16_round(W[2 * li]).T.astype(np.float64)).astype(np.float32)
+            dz = bf16_round(da * _act_grad(dense[li - 1].activation, acts[li]))
+    return gW
+
+
 def _act_grad(name, a):
     """Derivative of an element-wise activation written in terms of its OUTPUT a."""
     if name == "relu":
@@ -727,7 +753,7 @@ def _ibp_backward_weights(dense, W, U, Lo, dzu, dzl):
     return gW
 
 
-def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64,
+def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, kl_weight=1.0, dtype=np.float64, bf16=False,
              robust_train=0, epsilon=0.0, robust_lambda=1.0, lower=-np.inf, upper=np.inf, eps_draws=None):
     """`BayesByBackprop.step` (bayesbybackprop.py:46-170) for Dense MLPs with a softmax output and the sparse categorical
     cross-entropy, gradients written out by hand (the reference gets them from tf.GradientTape):
@@ -759,7 +785,15 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
     if dense[-1].activation != "softmax":
         raise NotImplementedError("oracle bbb_step: softmax output")
     x = np.asarray(x, d)
-    acts = _mlp_forward_acts(dense, W, x)
+    if bf16:
+        # the GPU's bf16 training mode: the GEMMs see bf16 operands (dtype should be np.float32 so that W is the fp32 draw the
+        # device rounds); draw, losses, KL terms and the update are unchanged
+        if robust_train not in (0, 2):
+            raise NotImplementedError("bf16 emulation: robust_train 0 and 2")
+        fwd, bwd = _mlp_forward_acts_bf16, _mlp_backward_weights_bf16
+    else:
+        fwd, bwd = _mlp_forward_acts, _mlp_backward_weights
+    acts = fwd(dense, W, x)
     pred = acts[-1]
     B = pred.shape[0]
     lab = np.asarray(labels).reshape(-1)
@@ -769,19 +803,19 @@ def bbb_step(layers, mean, rho, prior_mean, prior_var, x, labels, noise, lrate, 
         out = pred
         pl = out[np.arange(B), lab]
         active = ((pl > 1e-7) & (pl < 1 - 1e-7)).astype(d)
-        gW = _mlp_backward_weights(dense, W, acts, (pred - onehot) * active[:, None] / d(B))
+        gW = bwd(dense, W, acts, (pred - onehot) * active[:, None] / d(B))
     elif robust_train == 2:
         direc = pred.argmax(1)
-        x_adv = fgsm(x, input_gradient(layers, [W], x, direc, d), epsilon, lower, upper)
-        acts_adv = _mlp_forward_acts(dense, W, x_adv)
+        x_adv = fgsm(x, input_gradient(layers, [W], x, direc, d, bf16=bf16), epsilon, lower, upper)
+        acts_adv = fwd(dense, W, x_adv)
         pa = acts_adv[-1]
         out = d(robust_lambda) * pred + d(1 - robust_lambda) * pa
         oy = out[np.arange(B), lab]
         g = np.where((oy > 1e-7) & (oy < 1 - 1e-7), -1.0 / (B * oy), 0.0)
         dz = (d(robust_lambda) * g * pred[np.arange(B), lab])[:, None] * (onehot - pred)
         dza = (d(1 - robust_lambda) * g * pa[np.arange(B), lab])[:, None] * (onehot - pa)
-        g1 = _mlp_backward_weights(dense, W, acts, dz)
-        g2 = _mlp_backward_weights(dense, W, acts_adv, dza)
+        g1 = bwd(dense, W, acts, dz)
+        g2 = bwd(dense, W, acts_adv, dza)
         gW = [a + b for a, b in zip(g1, g2)]
     elif robust_train == 1:
         U, Lo, _ = _ibp_forward_bounds(dense, W, x, epsilon)

@@ -956,6 +956,71 @@ def test_bbb_step_matches_oracle(oracle, dims, B):
         db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, robust_train=5).step(x, lab, lr)
 
 
+@pytest.mark.parametrize("dims,B,rt", [([784, 512, 512, 10], 256, 0), ([784, 128, 10], 130, 0), ([104, 72, 40, 16], 64, 0),
+                                       ([784, 256, 128, 10], 300, 2)])
+def test_bbb_step_bf16_on_tensor_cores_matches_oracle(oracle, dims, B, rt):
+    """dbx_bbb_step in bf16 mode (compile(..., train_mode="bf16")): forward = dense_tc_kernel, backward-data =
+    dense_tc_bwd_kernel, weight gradient = dense_tc_wgrad_kernel (A^T dZ with both operands MN-major), everything else fp32 --
+    against the oracle with the same operand roundings and against the exact (fp64) step; the sampled weights, the loss terms
+    and the clean predictions are the fp32 step's to rounding."""
+    import deepbayes_b200 as db
+    L = oracle.mlp(dims)
+    layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+    for h in dims[2:-1]:
+        layers.append(db.Dense(h, activation="relu"))
+    layers.append(db.Dense(dims[-1], activation="softmax"))
+    kw = dict(robust_train=rt, epsilon=0.02, rob_lam=0.5, linear_schedule=False) if rt else {}
+    opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=2.0, kl_weight=0.7, train_mode="bf16", **kw)
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=3.0)
+    opt.posterior_mean = [m.copy() for m in mean]
+    opt.posterior_var = [oracle.inverse_softplus(s) for s in std]
+    rho0 = [r.copy() for r in opt.posterior_var]
+    x = oracle.synthetic_x((B, dims[0]), seed=0)
+    lab = np.random.Generator(np.random.Philox(3)).integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    lr = 0.1
+    nm, nr = opt.step(x, lab, lr, noise=noise)
+    assert opt.engine().last_path() == "generic_tc"
+    okw = dict(robust_train=rt, epsilon=0.02, robust_lambda=0.5) if rt else {}
+    wm16, wr16, loss16, klc16, pred16, W16 = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.7,
+                                                            dtype=np.float32, bf16=True, **okw)
+    wm, wr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, lr, kl_weight=0.7, **okw)
+    tol16, tol64 = (2e-2, 0.1) if rt == 0 else (0.15, 0.25)      # (the FGSM sign of near-zero gradient entries moves whole inputs by 2 eps)
+    for i in range(len(nm)):
+        for got, w16, w64, old in ((nm[i], wm16[i], wm[i], mean[i]), (nr[i], wr16[i], wr[i], rho0[i])):
+            d16, d64, dg = (w16 - old).ravel().astype(np.float64), (w64 - old).ravel().astype(np.float64), (got - old).ravel().astype(np.float64)
+            assert np.linalg.norm(dg - d16) <= tol16 * np.linalg.norm(d16) + 1e-9, (i, np.linalg.norm(dg - d16) / np.linalg.norm(d16))
+            assert np.linalg.norm(dg - d64) <= tol64 * np.linalg.norm(d64) + 1e-9, (i, np.linalg.norm(dg - d64) / np.linalg.norm(d64))
+        np.testing.assert_allclose(opt.model.get_weights()[i], W[i], rtol=1e-6, atol=1e-7)        # the draw itself is fp32
+    got = opt._last_loss.cpu().numpy()
+    np.testing.assert_allclose(got[1], klc, rtol=2e-5)                                              # KL terms: fp32
+    np.testing.assert_allclose(got[0], loss16, rtol=5e-3 if rt == 0 else 5e-2)
+    if rt == 0:
+        np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred16, rtol=0, atol=1e-2)      # (a stored activation across a bf16 tie)
+        # (this posterior is 30x wider than the synthetic posterior of BASELINE, whose bf16 bound on probabilities is BF16_ATOL)
+        np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=0, atol=2.5 * BF16_ATOL)
+
+
+def test_bbb_training_in_bf16_mode_learns(oracle):
+    """A few epochs of BayesByBackprop.train with train_mode="bf16" (one dbx_bbb_train_epoch call per epoch on the tensor-core
+    step) reach the accuracy of the fp32 run on the same data."""
+    import deepbayes_b200 as db
+    g = np.random.Generator(np.random.Philox(11))
+    C, D, N = 4, 24, 2048
+    centers = g.standard_normal((C, D)).astype(np.float32) * 2.0
+    y = g.integers(0, C, size=N)
+    X = (centers[y] + g.standard_normal((N, D)).astype(np.float32) * 0.5).astype(np.float32)
+    accs = {}
+    for tm in ("fp32", "bf16"):
+        m = db.Sequential([db.Dense(32, activation="relu", input_shape=(D,)), db.Dense(C, activation="softmax")])
+        opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=256, learning_rate=0.3, epochs=5, inflate_prior=1.0, kl_weight=0.1, seed=5,
+                                                      train_mode=tm)
+        opt.train(X[:1536], y[:1536], X[1536:], y[1536:])
+        assert opt.loss_log[-1] < opt.loss_log[0]
+        accs[tm] = (opt.acc_log[-1], opt.val_log[-1][1])
+    assert accs["bf16"][0] > 0.9 and accs["bf16"][1] > 0.85 and abs(accs["bf16"][0] - accs["fp32"][0]) < 0.05
+
+
 def test_bbb_training_learns(oracle):
     """End to end: a few epochs of BayesByBackprop.train on a separable synthetic problem drive the loss down and the
     accuracy up, and the trained posterior predicts through the fused / generic inference path."""
