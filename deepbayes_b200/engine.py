@@ -237,7 +237,7 @@ class Engine:
         torch = self.torch
         xt = self._x2d(x)
         K = xt.shape[0]
-        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1)).to(self.device)
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
         if lab.numel() != K:
             raise ValueError("need one label per input row (%d rows, %d labels)" % (K, lab.numel()))
         counts = torch.zeros(K, dtype=torch.int64, device=self.device)
@@ -257,7 +257,7 @@ class Engine:
         torch = self.torch
         xt = self._x2d(x)
         B = xt.shape[0]
-        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1)).to(self.device)
+        lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
         if lab.numel() != B:
             raise ValueError("need one label per input row (%d rows, %d labels)" % (B, lab.numel()))
         for t in (mean_t, rho_t, prior_mean_t, prior_var_t):
@@ -363,7 +363,7 @@ class Engine:
         B = xt.shape[0]
         lab = None
         if labels is not None:
-            lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1)).to(self.device)
+            lab = torch.as_tensor(np.asarray(labels, dtype=np.int32).reshape(-1).copy()).to(self.device)
             if lab.numel() != B:
                 raise ValueError("need one label per input row (%d rows, %d labels)" % (B, lab.numel()))
         z = lambda: torch.zeros((B, self.C), dtype=torch.float32, device=self.device)   # noqa: E731

@@ -147,6 +147,32 @@ def cfg_train():
              ms=ms2, value=1e3 / ms2, unit="steps/s", path="dbx_bbb_train_epoch")
 
 
+def cfg_train_tc():
+    """The training step per mini-batch size, fp32 kernels vs tensor-core GEMMs (train_mode): one dbx_bbb_train_epoch call over 40
+    mini-batches of resident examples, MLP 784-512-512-10."""
+    import deepbayes_b200 as db
+    dims = [784, 512, 512, 10]
+    for bs in (128, 256, 1024, 4096):
+        for tm in ("fp32", "bf16"):
+            layers = [db.Dense(dims[1], activation="relu", input_shape=(dims[0],))]
+            for h in dims[2:-1]:
+                layers.append(db.Dense(h, activation="relu"))
+            layers.append(db.Dense(dims[-1], activation="softmax"))
+            opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=bs, inflate_prior=1.0, seed=3, train_mode=tm)
+            x = torch.from_numpy(o.synthetic_x((bs, 784), seed=0)).cuda()
+            y = np.random.Generator(np.random.Philox(3)).integers(0, 10, size=bs)
+            opt.step(x, y, 0.01, sync=False)
+            eng = opt.engine()
+            nb = 40 if bs <= 1024 else 10
+            N = bs * nb
+            Xd = torch.from_numpy(o.synthetic_x((N, 784), seed=1)).cuda()
+            yd = torch.from_numpy(np.random.Generator(np.random.Philox(4)).integers(0, 10, size=N).astype(np.int32)).cuda()
+            ep = lambda: eng.bbb_train_epoch(Xd, yd, bs, opt._d_mean, opt._d_rho, opt._d_pm, opt._d_pv, 0.01, 1.0, 3, 0, want_weights=False, mode=tm)
+            ms = timeit(ep, warm=1, reps=3) / nb
+            emit(config="train: dbx_bbb_train_epoch, MLP 784-512-512-10, mini-batch %d" % bs, B=bs, mode=tm, ms=ms, value=bs * 1e3 / ms,
+                 unit="examples/s", path="dbx_bbb_train_epoch/" + eng.last_path(), tflops=3 * 1337344 * bs / (ms * 1e-3) / 1e12)
+
+
 def cfg_attack():
     """Expected input gradient: MLP 784-512-512-10, 128 inputs, one FGSM gradient = 10 iterations x 35
     posterior samples (a PosteriorModel's predict), all on the device; and config 5 with verify=False (massart_bound_check's
@@ -172,4 +198,4 @@ if __name__ == "__main__":
     ap.add_argument("--stored", type=int, default=2000)
     a = ap.parse_args()
     for c in a.configs.split(","):
-        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5, "train": cfg_train, "attack": cfg_attack}[c]()
+        {"1": cfg1, "3": lambda: cfg3(a.stored), "4": cfg4, "5": cfg5, "train": cfg_train, "train_tc": cfg_train_tc, "attack": cfg_attack}[c]()
