@@ -9,7 +9,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 g = np.random.Generator(np.random.Philox(99))
 t0 = time.time(); it = 0
 while time.time() - t0 < budget:
-    kind = it % 4
+    kind = it % 6
     if os.environ.get('SOAK_VERBOSE'):
         print('it', it, 'kind', kind, 'start', flush=True)
     if kind == 0:      # MLP: IBP (fused layers) + predict (fused / generic)
@@ -51,6 +51,40 @@ while time.time() - t0 < budget:
         a, _ = eng.predict_stored_sums(x, S, j0=0, mode="bf16")
         b, _ = eng.predict_stored_sums(x, S, j0=0, mode="fp32")
         assert float((a - b).abs().max()) / S < 2e-2
+    elif kind == 4:    # gradient loops on the tensor cores: dense_tc_bwd_kernel (persistent / per-tile), FGSM epilogue
+        K = int(g.integers(1, 110)) * 8
+        hs = [int(g.integers(1, 80)) * 8 for _ in range(int(g.integers(1, 4)))]
+        C = int(g.integers(2, 17))
+        layers = [db.Dense(hs[0], activation="relu", input_shape=(K,))] + [db.Dense(h, activation=str(g.choice(["relu", "tanh", "sigmoid"]))) for h in hs[1:]]
+        layers.append(db.Dense(C, activation="softmax"))
+        eng = Engine(db.Sequential(layers))
+        eng.set_gaussian((g.standard_normal(eng.P) * 0.1).astype(np.float32), np.full(eng.P, 0.02, np.float32))
+        B, n = int(g.integers(1, 300)), int(g.integers(1, 400))
+        x = g.random((B, K)).astype(np.float32)
+        lab = g.integers(0, C, size=B).astype(np.int32)
+        gr = eng.input_gradient(x, lab, int(g.integers(1, 4)), min(n, 64), seed=it, mode="bf16")
+        assert eng.last_path() == "generic_tc" and bool(torch.isfinite(gr).all())
+        c = eng.count_predicate_fgsm(x, lab, lab, 0.02, n, seed=it, lower=0.0, upper=1.0, mode="bf16")
+        assert int(c.max()) <= n
+    elif kind == 5:    # training step on the tensor cores: dense_tc_wgrad_kernel, both robust modes
+        K = int(g.integers(1, 110)) * 8
+        hs = [int(g.integers(1, 80)) * 8 for _ in range(int(g.integers(1, 4)))]
+        C = int(g.integers(2, 17))
+        layers = [db.Dense(hs[0], activation="relu", input_shape=(K,))] + [db.Dense(h, activation=str(g.choice(["relu", "tanh"]))) for h in hs[1:]]
+        layers.append(db.Dense(C, activation="softmax"))
+        rt = int(g.choice([0, 2]))
+        opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=64, inflate_prior=1.0, seed=it, train_mode="bf16",
+                                                      robust_train=rt, epsilon=0.02, linear_schedule=False)
+        B = int(g.integers(1, 700))
+        x = g.random((B, K)).astype(np.float32)
+        lab = g.integers(0, C, size=B).astype(np.int32)
+        for _ in range(3):
+            opt.step(x, lab, 0.05, sync=False)
+        eng = opt.engine()
+        assert eng.last_path() == "generic_tc"
+        opt.sync_from_device()
+        assert all(np.isfinite(np.asarray(t)).all() for t in opt.posterior_mean) and all(np.isfinite(np.asarray(t)).all() for t in opt.posterior_var)
+        del opt
     else:              # fused MLP shapes, long runs at small batch
         H = int(g.choice([128, 256, 384, 512]))
         dims = [784, H, H, 10] if g.random() < 0.5 else [784, H, 10]
