@@ -1253,7 +1253,7 @@ struct __align__(8) CBarriers {
 template <int kAct>
 __global__ void __launch_bounds__(kCThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
-  __shared__ float s_bias[128];                       // the current sample's bias (epilogue warps refill it per sample)
+  __shared__ __align__(16) float s_bias[128];         // the current sample's bias (epilogue warps refill it per sample)
   uint8_t* smem = (uint8_t*)(((uintptr_t)gemm_smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t s_stage = smem_u32(smem);
   const int cin_b = p.Cin * 2;                        // bytes per A row = swizzle span (32 / 64 / 128)
@@ -1291,19 +1291,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   fence_after_sync();
   const uint32_t tmem = bars->tmem_slot;
 
-  auto decode = [&](long long t, int& ho0, int& nb, int& s) {
-    const int rg = (int)(t % p.tiles_per_img);
+  // (row group, image, sample) of a tile: decoded ONCE per role and then advanced (three runtime divisions per tile and thread
+  // were a tenth of the epilogue's instructions, and the epilogue's instruction count is what bounds this kernel)
+  struct TileIt { int rg, nb, s; };
+  auto decode0 = [&](long long t) {
+    TileIt ti;
+    ti.rg = (int)(t % p.tiles_per_img);
     const long long r = t / p.tiles_per_img;
-    ho0 = rg * p.R; nb = (int)(r % p.NB); s = (int)(r / p.NB);
+    ti.nb = (int)(r % p.NB); ti.s = (int)(r / p.NB);
+    return ti;
+  };
+  auto advance = [&](TileIt& ti) {
+    if (++ti.rg == p.tiles_per_img) { ti.rg = 0; if (++ti.nb == p.NB) { ti.nb = 0; ++ti.s; } }
   };
 
   if (warp == 0) {
     uint32_t g = 0;
     const uint32_t tx = (uint32_t)(p.R * p.Wo * cin_b + (p.w_res ? 0 : w_tap_b));
     int cur_s = -1;
-    for (long long t = t_begin; t < t_end; ++t) {
-      int ho0, nb, s;
-      decode(t, ho0, nb, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, advance(ti)) {
+      const int ho0 = ti.rg * p.R, nb = ti.nb, s = ti.s;
       if (p.w_res && s != cur_s) {
         // new sample: every MMA that read the old weights has retired once the last tap's commit has arrived
         if (g > 0) mbar_wait(smem_u32(&bars->empty[(g - 1) % p.stages]), ((g - 1) / p.stages) & 1);
@@ -1355,11 +1363,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ksteps = p.Cin / 16;
     uint32_t g = 0, it = 0, w_n = 0;
     int cur_s = -1;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, ++it, advance(ti)) {
       const uint32_t ab = it & 1;
       if (p.w_res) {
-        int ho0, nb, s;
-        decode(t, ho0, nb, s);
+        const int s = ti.s;
         if (s != cur_s) { mbar_wait(smem_u32(&bars->w_full), w_n & 1); ++w_n; cur_s = s; }
       }
       mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) & 1) ^ 1);
@@ -1412,9 +1420,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t it = 0;
     int cur_s = -1;
     const float* bias = s_bias;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      int ho0, nb, s;
-      decode(t, ho0, nb, s);
+    // pool mode: what a thread does in the pooling pass is the same for every tile -- its (up to two) tasks' four staged
+    // addresses and output offsets are computed here, once (per tile they cost ~150 instructions of divisions and address
+    // arithmetic per task); tasks beyond 256 per tile take the general loop
+    const int nchunk_p = p.Cout >> 3, pw_n = p.Wo >> 1, PHo = p.Ho >> 1;
+    const int tasks = p.pool ? (p.R >> 1) * pw_n * nchunk_p : 0;
+    int pt_off[2][4], pt_out[2], pt_pr[2];
+    bool pt_ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int j = tid - 64 + 128 * k;
+      pt_ok[k] = j < tasks;
+      const int q = pt_ok[k] ? j % nchunk_p : 0, pp = pt_ok[k] ? j / nchunk_p : 0;
+      const int pr = pp / max(pw_n, 1), pc = pp - pr * pw_n;
+      const int a0 = (2 * pr) * rw + 2 * pc;
+      const int rws[4] = {a0, a0 + 1, a0 + rw, a0 + rw + 1};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int sz = p.pool ? ((rws[e] / (8 / nchunk_p)) & (nchunk_p - 1)) : 0;
+        pt_off[k][e] = rws[e] * (p.Cout * 2) + ((q ^ sz) << 4);
+      }
+      pt_out[k] = (pr * pw_n + pc) * p.Cout + q * 8;
+      pt_pr[k] = pr;
+    }
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, ++it, advance(ti)) {
+      const int ho0 = ti.rg * p.R, nb = ti.nb, s = ti.s;
       const uint32_t ab = it & 1;
       if (s != cur_s) {      // per-column global loads in the epilogue were its longest stall (ncu: long scoreboard)
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1447,10 +1478,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int c = c0 + q8 * 8;
             if (c + 8 <= p.Cout) {
               uint32_t w[4];
+              const float4 bl = *reinterpret_cast<const float4*>(bias + c), bh = *reinterpret_cast<const float4*>(bias + c + 4);
+              const float bb[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bias[c + 2 * i]),
-                                   act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bias[c + 2 * i + 1]));
+                w[i] = pack_bf16x2(act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i]) + bb[2 * i]),
+                                   act_fixed<kAct>(p.act, __uint_as_float(v[q8 * 8 + 2 * i + 1]) + bb[2 * i + 1]));
               if (p.pool) *reinterpret_cast<uint4*>(srow + (((c >> 3) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
               else *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
             } else if (!p.pool) {
@@ -1464,10 +1497,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // 2x2 / stride-2 max over the staged tile: R (even) output rows x Wo columns -> R/2 x Wo/2 pooled pixels, one 16-byte
         // channel chunk per task, written as full NHWC rows of the pooled map (packed bf16x2 max, like maxpool_bf16_vec8_kernel)
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int pw_n = p.Wo >> 1, PHo = p.Ho >> 1;
-        const int tasks = (p.R >> 1) * pw_n * nchunk;
         const int pitch = p.Cout * 2;
-        for (int j = tid - 64; j < tasks; j += 128) {
+        __nv_bfloat16* obase = p.out + (long long)s * p.o_sstride + (((long long)nb * PHo + (ho0 >> 1)) * pw_n) * p.Cout;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (!pt_ok[k] || (ho0 >> 1) + pt_pr[k] >= PHo) continue;
+          __nv_bfloat162 acc[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint4 t4 = *reinterpret_cast<const uint4*>(pool_stage + pt_off[k][e]);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = e == 0 ? h[i] : __hmax2(acc[i], h[i]);
+          }
+          *reinterpret_cast<uint4*>(obase + pt_out[k]) = *reinterpret_cast<const uint4*>(acc);
+        }
+        for (int j = tid - 64 + 256; j < tasks; j += 128) {
           const int q = j % nchunk, pp = j / nchunk;
           const int pr = pp / pw_n, pc = pp - pr * pw_n;
           const int prow = (ho0 >> 1) + pr;
