@@ -1230,7 +1230,13 @@ dense_tc_f32w_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #define DBX_CSTAGES 6
 #endif
 constexpr int kCStages = DBX_CSTAGES;
-constexpr int kCThreads = 192;
+#ifndef DBX_CEPI
+#define DBX_CEPI 4
+#endif
+constexpr int kCEpiWarps = DBX_CEPI;      // 4 or 8: with 8, two warps share a TMEM lane quarter and split the tile's columns.  Measured
+                                          // SLOWER (config 4: 6.45 -> 6.77 ms): what bounds the epilogue is the number of instructions
+                                          // issued per tile, and every extra warp repeats the per-tile bookkeeping
+constexpr int kCThreads = 64 + 32 * kCEpiWarps;
 
 struct ConvParams {
   int NB, Ho, Wo, Cin, Cout, kh, kw, pad_t, pad_l, R, tiles_per_img, ns, a_shared, act;
@@ -1280,7 +1286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (tid == 0) {
     for (int i = 0; i < kCStages; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kCEpiWarps); }
     mbar_init(smem_u32(&bars->w_full), 1);
     fence_mbar_init();
   }
@@ -1413,6 +1419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int gq = warp & 3;
+    const int ch = (warp - 2) >> 2;                  // column half of this warp (always 0 with four epilogue warps)
     const int row = gq * 32 + lane;                  // accumulator row = output pixel r * Wo + wo of the tile
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
     const int rw = p.patch ? p.PW : p.Wo;          // accumulator rows per output row (patch mode keeps kw-1 garbage columns)
@@ -1429,7 +1436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     bool pt_ok[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int j = tid - 64 + 128 * k;
+      const int j = tid - 64 + 32 * kCEpiWarps * k;
       pt_ok[k] = j < tasks;
       const int q = pt_ok[k] ? j % nchunk_p : 0, pp = pt_ok[k] ? j / nchunk_p : 0;
       const int pr = pp / max(pw_n, 1), pc = pp - pr * pw_n;
@@ -1448,10 +1455,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ho0 = ti.rg * p.R, nb = ti.nb, s = ti.s;
       const uint32_t ab = it & 1;
       if (s != cur_s) {      // per-column global loads in the epilogue were its longest stall (ncu: long scoreboard)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kCEpiWarps) : "memory");
         const int te = tid - 64;
         if (te < p.Cout) s_bias[te] = p.bias[(long long)s * p.b_sstride + p.b_off + te];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kCEpiWarps) : "memory");
         cur_s = s;
       }
       const bool valid = r < p.R && wo < p.Wo && ho0 + r < p.Ho;
@@ -1463,11 +1470,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* srow = pool_stage + row * (p.Cout * 2);
       mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
       fence_after_sync();
-      for (int c0 = 0; c0 < NT; c0 += 32) {
+      const int c_per = NT / (kCEpiWarps / 4), c_lo = ch * c_per, c_hi = c_lo + c_per;      // NT is a multiple of 64
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + ab * 128 + c0, v);
         wait_ld();
-        if (c0 + 32 >= NT) {   // everything is in registers: hand the accumulator back before the stores
+        if (c0 + 32 >= c_hi) {   // everything is in registers: hand the accumulator back before the stores
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
@@ -1496,7 +1504,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.pool) {
         // 2x2 / stride-2 max over the staged tile: R (even) output rows x Wo columns -> R/2 x Wo/2 pooled pixels, one 16-byte
         // channel chunk per task, written as full NHWC rows of the pooled map (packed bf16x2 max, like maxpool_bf16_vec8_kernel)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kCEpiWarps) : "memory");
         const int pitch = p.Cout * 2;
         __nv_bfloat16* obase = p.out + (long long)s * p.o_sstride + (((long long)nb * PHo + (ho0 >> 1)) * pw_n) * p.Cout;
 #pragma unroll
@@ -1512,7 +1520,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           *reinterpret_cast<uint4*>(obase + pt_out[k]) = *reinterpret_cast<const uint4*>(acc);
         }
-        for (int j = tid - 64 + 256; j < tasks; j += 128) {
+        for (int j = tid - 64 + 2 * 32 * kCEpiWarps; j < tasks; j += 32 * kCEpiWarps) {
           const int q = j % nchunk, pp = j / nchunk;
           const int pr = pp / pw_n, pc = pp - pr * pw_n;
           const int prow = (ho0 >> 1) + pr;
@@ -1536,7 +1544,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __nv_bfloat16* po = p.out + (long long)s * p.o_sstride + ((((long long)nb * PHo + prow) * pw_n + pc) * p.Cout) + q * 8;
           *reinterpret_cast<uint4*>(po) = m4;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // the staging tile is free for the next tile
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kCEpiWarps) : "memory");       // the staging tile is free for the next tile
       }
     }
   }
