@@ -121,7 +121,7 @@ static int run_input_gradient(dbx_model* m, const float* x_dev, int64_t B, const
   std::vector<int64_t> act_ss(nl);
   for (int i = 0; i < nl; ++i) { acts[i] = (float*)p; act_ss[i] = B * dl[i]->units; p += (size_t)nc * act_ss[i] * 4; }
   p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
-  float* dz[2]; const int64_t dz_ss = (int64_t)(dzb / 4);
+  float* dz[2];
   dz[0] = (float*)p; p += (size_t)nc * dzb; dz[1] = (float*)p; p += (size_t)nc * dzb;
   float* pbar = (float*)p; p += round_up((size_t)B * C * 4, 256);
   float* Wc = (float*)p;

@@ -424,10 +424,18 @@ dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __gri
   const int kb_n = (p.K + 63) / 64;
   const long long total = (long long)ns * tiles_m * tiles_n;
   const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
-  auto decode = [&](long long t, int& n0, int& m0, int& s) {
-    const int nt_i = (int)(t % tiles_n);
+  // (column tile, row tile, sample) of a tile: decoded once per role, then advanced -- four 64-bit divisions per tile and warp
+  // were as many instructions as a short tile's whole epilogue
+  struct TileIt { int nt_i, mt_i, s; };
+  auto decode0 = [&](long long t) {
+    TileIt ti;
+    ti.nt_i = (int)(t % tiles_n);
     const long long r = t / tiles_n;
-    n0 = nt_i * kNT; m0 = (int)(r % tiles_m) * 128; s = (int)(r / tiles_m);
+    ti.mt_i = (int)(r % tiles_m); ti.s = (int)(r / tiles_m);
+    return ti;
+  };
+  auto advance = [&](TileIt& ti) {
+    if (++ti.nt_i == tiles_n) { ti.nt_i = 0; if (++ti.mt_i == tiles_m) { ti.mt_i = 0; ++ti.s; } }
   };
 
   if (tid == 0) {
@@ -444,9 +452,9 @@ dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __gri
 
   if (warp == 0) {
     uint32_t g = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
-      int n0, m0, s;
-      decode(t, n0, m0, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, advance(ti)) {
+      const int n0 = ti.nt_i * kNT, m0 = ti.mt_i * 128, s = ti.s;
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
         const uint32_t st = g % kSt, ph = (g / kSt) & 1;
         mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
@@ -463,9 +471,9 @@ dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __gri
   } else if (warp == 1) {
     constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
     uint32_t g = 0, it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      int n0, m0, s;
-      decode(t, n0, m0, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, ++it, advance(ti)) {
+      const int n0 = ti.nt_i * kNT;
       const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
       const uint32_t idesc = make_idesc_bf16(128, nt, 0, 0);
       const uint32_t ab = it & 1;
@@ -491,9 +499,9 @@ dense_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmZ, const __gri
     const int gq = warp & 3;
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
     uint32_t it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      int n0, m0, s;
-      decode(t, n0, m0, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, ++it, advance(ti)) {
+      const int n0 = ti.nt_i * kNT, m0 = ti.mt_i * 128, s = ti.s;
       const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
       const int gm = m0 + gq * 32 + lane;
       const uint32_t ab = it & 1;
@@ -653,10 +661,18 @@ dense_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int kb_n = (p.K + 63) / 64;
   const long long total = (long long)ns * tiles_m * tiles_n;
   const long long t_begin = (total * blockIdx.x) / gridDim.x, t_end = (total * (blockIdx.x + 1)) / gridDim.x;
-  auto decode = [&](long long t, int& n0, int& m0, int& s) {
-    const int nt_i = (int)(t % tiles_n);
+  // (column tile, row tile, sample) of a tile: decoded once per role, then advanced -- four 64-bit divisions per tile and warp
+  // were as many instructions as a short tile's whole epilogue
+  struct TileIt { int nt_i, mt_i, s; };
+  auto decode0 = [&](long long t) {
+    TileIt ti;
+    ti.nt_i = (int)(t % tiles_n);
     const long long r = t / tiles_n;
-    n0 = nt_i * kNT; m0 = (int)(r % tiles_m) * 128; s = (int)(r / tiles_m);
+    ti.mt_i = (int)(r % tiles_m); ti.s = (int)(r / tiles_m);
+    return ti;
+  };
+  auto advance = [&](TileIt& ti) {
+    if (++ti.nt_i == tiles_n) { ti.nt_i = 0; if (++ti.mt_i == tiles_m) { ti.mt_i = 0; ++ti.s; } }
   };
 
   if (tid == 0) {
@@ -673,9 +689,9 @@ dense_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   if (warp == 0) {
     uint32_t g = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
-      int n0, m0, s;
-      decode(t, n0, m0, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, advance(ti)) {
+      const int n0 = ti.nt_i * kNT, m0 = ti.mt_i * 128, s = ti.s;
       const int nblk = min(kNT, ((p.N - n0 + 63) / 64) * 64) / 64;
       for (int kb = 0; kb < kb_n; ++kb, ++g) {
         const uint32_t st = g % kSt, ph = (g / kSt) & 1;
@@ -694,9 +710,9 @@ dense_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   } else if (warp == 1) {
     constexpr uint32_t kDescHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
     uint32_t g = 0, it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      int n0, m0, s;
-      decode(t, n0, m0, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, ++it, advance(ti)) {
+      const int n0 = ti.nt_i * kNT;
       const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
       const uint32_t idesc = make_idesc_bf16(128, nt, 0, 1);
       const uint32_t ab = it & 1;
@@ -724,9 +740,9 @@ dense_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const uint32_t lane_base = (uint32_t)(gq * 32) << 16;
     uint32_t it = 0;
     int cur_s = -1, cur_n0 = -1;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      int n0, m0, s;
-      decode(t, n0, m0, s);
+    TileIt ti = decode0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t, ++it, advance(ti)) {
+      const int n0 = ti.nt_i * kNT, m0 = ti.mt_i * 128, s = ti.s;
       const int nt = min(kNT, ((p.N - n0 + 63) / 64) * 64);
       const int gm = m0 + row;
       const uint32_t ab = it & 1;
