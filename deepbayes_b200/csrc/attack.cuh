@@ -426,20 +426,53 @@ static int run_input_gradient_tc(dbx_model* m, const float* x_dev, int64_t B, co
   GradTcBufs g;
   const int nc = (int)n_inner;
   const int64_t C = m->out_feat, K0 = m->in_feat;
-  const size_t per = grad_tc_per_sample(m, B, false, g);
+  // several iterations: the next iteration's weights are drawn on the side stream while this one's GEMM chain runs on the
+  // engine's high-priority stream (the same pipeline as the FGSM loop below)
+  const bool overlap = opt().generic_overlap != 0 && n_outer > 1;
+  const int nwb = overlap ? 2 : 1;
+  const size_t per = grad_tc_per_sample(m, B, false, g, nwb);
   const size_t need = (size_t)nc * per + round_up((size_t)B * K0 * 2, 256) + round_up((size_t)B * C * 4, 256) + 8192;
   DBX_CHECK(need <= ws_budget_bytes() * 2, "n_inner = %d samples need %zu MB of workspace", nc, need >> 20);
   if (ensure_ws(m->ws, need)) return 1;
-  grad_tc_carve(m, B, nc, false, (char*)m->ws.ptr, g);
+  grad_tc_carve(m, B, nc, false, (char*)m->ws.ptr, g, nwb);
+  cudaStream_t sst = st, caller = st;
+  if (overlap) {
+    if (ensure_side_streams(m) || ensure_main_stream(m)) return 1;
+    sst = m->ibp_side;
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], caller));
+    DBX_CUDA(cudaStreamWaitEvent(sst, m->ibp_ev[0], 0));
+    DBX_CUDA(cudaStreamWaitEvent(m->ibp_main, m->ibp_ev[0], 0));
+    st = m->ibp_main;
+  }
+  auto draw = [&](int64_t it) -> int {
+    const int b = (int)(it & 1) % nwb;
+    if (overlap && it >= 2) DBX_CUDA(cudaStreamWaitEvent(sst, m->ibp_ev[3 + b], 0));
+    if (launch_sample_bf16(m, m->table, src0, it * n_inner, nc, g.W16b[b], g.B32b[b], sst)) return 1;
+    if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[1 + b], sst));
+    return 0;
+  };
   DBX_LAUNCH(cast_kernel<__nv_bfloat16>, grid_for(B * K0), 256, 0, st, x_dev, g.xin, B * K0);
   for (int64_t it = 0; it < n_outer; ++it) {
-    if (launch_sample_bf16(m, m->table, src0, it * n_inner, nc, g.W16, g.B32, st)) return 1;
+    const int wb = (int)(it & 1) % nwb;
+    if (it == 0 || !overlap) { if (draw(it)) return 1; }
+    if (overlap) {
+      if (it + 1 < n_outer && draw(it + 1)) return 1;
+      DBX_CUDA(cudaStreamWaitEvent(st, m->ibp_ev[1 + wb], 0));
+    }
+    g.W16 = g.W16b[wb]; g.B32 = g.B32b[wb];
     if (grad_tc_forward(m, g, g.xin, 0, B, nc, st)) return 1;
     DBX_LAUNCH(softmax_mean_kernel, (int)cdiv(B, 128), 128, 0, st, g.logits, nc, (int)B, (int)C, g.pbar);
     DBX_LAUNCH(ce_mean_upstream_bf16_kernel, grid_for((int64_t)nc * B), 256, 0, st, (const float*)g.logits, (const float*)g.pbar, labels_dev,
                nc, (int)B, (int)C, g.Cp, g.dz16);
     if (grad_tc_backward(m, g, B, nc, st)) return 1;
+    if (overlap) DBX_CUDA(cudaEventRecord(m->ibp_ev[3 + wb], st));
     DBX_LAUNCH(sum_samples_kernel, grid_for(B * K0), 256, 0, st, (const float*)g.dx, nc, B * K0, it > 0 ? 1 : 0, grad_dev);
+  }
+  if (overlap) {      // join
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[5], st));
+    DBX_CUDA(cudaStreamWaitEvent(caller, m->ibp_ev[5], 0));
+    DBX_CUDA(cudaEventRecord(m->ibp_ev[0], sst));
+    DBX_CUDA(cudaStreamWaitEvent(caller, m->ibp_ev[0], 0));
   }
   return 0;
 }
