@@ -2009,7 +2009,8 @@ int dense_tc_wgrad_launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
   if ((lda & 7) || (ldz & 7) || ((uintptr_t)A & 15) || ((uintptr_t)dZ & 15) || ((uintptr_t)out & 15)) return 1;
   WgradParams p = {};
   p.Kin = fan_in; p.N = fan_out; p.B = B; p.out = out; p.accumulate = accumulate;
-  const int ntc = fan_out <= 64 ? 64 : (fan_out <= 128 ? 128 : 256);
+  // 128-column tiles even for wide layers: dW has few tiles (784 x 512: 7 x 4) and every CTA walks the whole batch
+  const int ntc = fan_out <= 64 ? 64 : 128;
   p.NT = ntc;
   CUtensorMap tmA, tmZ;
   {

@@ -9,6 +9,8 @@ the C ABI.
   config 4  CNN of SURVEY 8(d) on [B,32,32,3]                                   -> conv_tc_kernel + pooled epilogue
   config 5  784-512-512-10, K = 128 fixed inputs, argmax predicate              -> fused_mlp_kernel<1>
   config 1  784-512-10 at B = 10000 rows                                         -> fused_mlp2_kernel, one hidden layer
+  config 5 / config 2 shapes through the widened rows in bf16 mode: expected input gradient + per-sample FGSM
+            (dense_tc_bwd_kernel, FGSM epilogue) and one training step (dense_tc_wgrad_kernel)
 
 Tolerances (BASELINE.json north_star): bf16 mode <= 2e-2 absolute on predictive probabilities
 against the fp32 oracle, <= 2e-3 against the oracle that rounds the GEMM operands to bf16 (only
@@ -307,3 +309,86 @@ def test_other_fused_shapes_in_stream_mode_vs_oracle(oracle, dims):
     w1, w2 = oracle.predict_moments(L, mean, std, x, n, eps, bf16=True)
     _check_probs((s1 / float(n)).cpu().numpy(), w1 / np.float32(n), oracle.predict(L, mean, std, x, n, eps))
     np.testing.assert_allclose((s2 / float(n)).cpu().numpy(), w2 / np.float32(n), rtol=0, atol=BF16_VS_BF16_ORACLE)
+
+
+def test_config5_shape_input_gradient_and_fgsm_on_tensor_cores_vs_oracle(oracle):
+    """Config 5's shape (784-512-512-10, K = 128 inputs) through the gradient loops in bf16 mode: the expected input gradient of
+    attacks.py:49-75 (2 iterations x 8 posterior samples) and the per-sample FGSM walk of verifiers.py:622-634 (12 samples),
+    forward / backward on tcgen05 (dense_tc_persist_kernel, dense_tc_bwd_kernel with the FGSM step in its epilogue), against the
+    oracle that rounds the GEMM operands the same way and against the exact (fp64) gradient."""
+    dims, K = [784, 512, 512, 10], 128
+    L, eng, mean, std = _mlp(dims, oracle)
+    eng.set_gaussian(mean, std)
+    x = oracle.synthetic_x((K, dims[0]), seed=0)
+    labels = oracle.forward(L, mean, x).argmax(-1).astype(np.int32)
+    n_outer, n_inner = 2, 8
+    eps = oracle.synthetic_eps(L, n_outer * n_inner, seed=2)
+    eps_flat = np.stack([oracle.flatten_list(e) for e in eps])
+    got = eng.input_gradient(x, labels, n_outer, n_inner, noise=eps_flat, mode="bf16").cpu().numpy()
+    assert eng.last_path() == "generic_tc"
+    want16, want = np.zeros((K, dims[0])), np.zeros((K, dims[0]))
+    for it in range(n_outer):
+        ws = [oracle.sample_gaussian(mean, std, eps[it * n_inner + s], order="f32") for s in range(n_inner)]
+        want16 += oracle.input_gradient(L, ws, x, labels, bf16=True)
+        want += oracle.input_gradient(L, ws, x, labels)
+    scale = np.abs(want).max()
+    row_err = np.abs(got - want16).max(1)
+    assert np.median(row_err) <= 1e-3 * scale and row_err.max() <= 0.1 * scale, (np.median(row_err) / scale, row_err.max() / scale)
+    assert np.linalg.norm(got - want) <= 0.1 * np.linalg.norm(want)
+    # the per-sample FGSM loop: flags against the oracle walk wherever neither the gradient signs nor the top-2 logits are near a tie
+    n, e = 12, 0.05
+    counts, flags = eng.count_predicate_fgsm(x, labels, labels, e, n, noise=eps_flat[:n], lower=0.0, upper=1.0, return_flags=True, mode="bf16")
+    assert eng.last_path() == "generic_tc"
+    flags = flags.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(counts.cpu().numpy(), flags.sum(0))
+    want_flags, clear = np.zeros((n, K), bool), np.zeros((n, K), bool)
+    for s in range(n):
+        w = oracle.sample_gaussian(mean, std, eps[s], order="f32")
+        gr = oracle.input_gradient(L, [w], x, labels, bf16=True)
+        adv = oracle.fgsm(oracle.bf16_round(x), gr, e, 0.0, 1.0)
+        z = oracle.forward(L, w, adv, np.float32, "logits", True)
+        want_flags[s] = z.argmax(-1) == labels
+        top = np.sort(z, axis=-1)
+        near_zero = (np.abs(gr) < 2e-2 * np.abs(gr).max(1, keepdims=True)).mean(1)
+        clear[s] = ((top[:, -1] - top[:, -2]) > 0.05 * np.abs(z).max()) & (near_zero < 0.5)
+    assert clear.mean() > 0.5 and (flags == want_flags)[clear].mean() > 0.97
+
+
+def test_config2_shape_training_step_on_tensor_cores_vs_oracle(oracle):
+    """One Bayes-by-Backprop step (bayesbybackprop.py:46-170) of config 2's MLP at mini-batch 512 in bf16 training mode:
+    dense_tc_kernel / dense_tc_bwd_kernel / dense_tc_wgrad_kernel (dW tiles with a ragged last row block: 784 = 6 x 128 + 16)
+    against the oracle with the same operand roundings and against the exact step."""
+    import deepbayes_b200 as db
+    dims, B = [784, 512, 512, 10], 512
+    L = oracle.mlp(dims)
+    layers = [db.Dense(512, activation="relu", input_shape=(784,)), db.Dense(512, activation="relu"), db.Dense(10, activation="softmax")]
+    opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=B, inflate_prior=1.0, kl_weight=1.0, train_mode="bf16")
+    mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=0.1)
+    opt.posterior_mean = [m.copy() for m in mean]
+    opt.posterior_var = [oracle.inverse_softplus(s) for s in std]
+    rho0 = [r.copy() for r in opt.posterior_var]
+    x = oracle.synthetic_x((B, 784), seed=0)
+    lab = np.random.Generator(np.random.Philox(3)).integers(0, 10, size=B)
+    noise = oracle.synthetic_eps(L, 1, seed=2)[0]
+    nm, nr = opt.step(x, lab, 0.1, noise=noise)
+    assert opt.engine().last_path() == "generic_tc"
+    wm16, wr16, loss16, _, pred16, _ = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, 0.1, dtype=np.float32, bf16=True)
+    wm, wr, loss, klc, pred, W = oracle.bbb_step(L, mean, rho0, opt.prior_mean, opt.prior_var, x, lab, noise, 0.1)
+    for i in range(len(nm)):
+        d16, d64, dg = [(a - mean[i]).ravel().astype(np.float64) for a in (wm16[i], wm[i], nm[i])]
+        # (what is left against the same-rounding oracle: fp32 summation order moving stored activations / upstream gradients across bf16 ties)
+        assert np.linalg.norm(dg - d16) <= 5e-2 * np.linalg.norm(d16) + 1e-9, (i, np.linalg.norm(dg - d16) / np.linalg.norm(d16))
+        assert np.linalg.norm(dg - d64) <= 0.1 * np.linalg.norm(d64) + 1e-9, (i, np.linalg.norm(dg - d64) / np.linalg.norm(d64))
+        # rho = -5.6 here and one step moves it by about one fp32 ulp (4.8e-7): the fp32 step (the reference's arithmetic too) is
+        # compared in ulps, not relative to the update
+        ulp = np.spacing(np.abs(rho0[i]).max().astype(np.float32))
+        assert (np.abs(nr[i] - wr16[i]) <= 2 * ulp).mean() > 0.999 and np.abs(nr[i] - wr16[i]).max() <= 16 * ulp
+        assert np.abs(nr[i].astype(np.float64) - wr[i]).max() <= 16 * ulp
+        np.testing.assert_allclose(opt.model.get_weights()[i], W[i], rtol=1e-6, atol=1e-7)
+    probs = opt._last_probs.cpu().numpy()
+    np.testing.assert_allclose(probs, pred16, rtol=0, atol=BF16_VS_BF16_ORACLE)
+    assert np.abs(probs - pred).max() <= BF16_ATOL
+    top = np.sort(pred, axis=1)
+    clear = (top[:, -1] - top[:, -2]) > 2e-3          # (an untrained model: many rows are near-ties)
+    assert (probs.argmax(1) == pred.argmax(1))[clear].all()
+    np.testing.assert_allclose(opt._last_loss.cpu().numpy()[0], loss16, rtol=2e-3)
