@@ -435,6 +435,20 @@ def run_config2(args, c):
         lo, hi = chk.clone(), chk.clone()
         c.dist.all_reduce(lo, op=c.dist.ReduceOp.MIN); c.dist.all_reduce(hi, op=c.dist.ReduceOp.MAX)
         same_bits = bool((lo == hi).all())
+        # the plugin call with the input rows sharded over the ranks' PCIe links + all-gather == the same call with the whole batch
+        # uploaded by every rank (same sample ids)
+        if strong and dd.sharded_upload_enabled(world):
+            pm._next_sample = 9 * n_total
+            a1, a2 = pm.predict_moments(x_host, n_total)
+            os.environ["DBX_NO_SHARDED_UPLOAD"] = "1"
+            pm._next_sample = 9 * n_total
+            b1, b2 = pm.predict_moments(x_host, n_total)
+            os.environ["DBX_NO_SHARDED_UPLOAD"] = "0"
+            up_ok = bool(np.array_equal(a1, b1) and np.array_equal(a2, b2))
+            if rank == 0:
+                shard_detail["sharded_upload_equals_full_upload"] = up_ok
+                if not up_ok:
+                    shard_check = "FAILED"
         _barrier(c)
 
     # ---- secondary arm under torchrun: weak scaling (n samples per GPU)
@@ -498,7 +512,11 @@ def run_config2(args, c):
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": forwards / (ms_e2e * 1e-3) if ms_e2e > 0 else None, "unit": UNIT, "ms_per_step": ms_e2e if ms_e2e > 0 else None,
                     "call": "PosteriorModel.predict_moments(x_numpy, n): page-locked host array in, (mean, E[p^2]) host arrays out",
-                    "h2d_bytes_per_step": int(x_np.nbytes) * world, "d2h_bytes_per_step": int(2 * B * 10 * 4) * world},
+                    # summed over the ranks.  Sharded predict: every rank uploads 1 / world of the batch's rows and one all-gather
+                    # over NVLink completes it (distributed.sharded_upload; DBX_NO_SHARDED_UPLOAD=1: every rank uploads all of it)
+                    "h2d_bytes_per_step": int(x_np.nbytes) * (1 if (strong and world > 1 and dd.sharded_upload_enabled(world)) else world),
+                    "h2d_split": ("rows sharded over ranks + all-gather" if (strong and world > 1 and dd.sharded_upload_enabled(world)) else "whole batch per rank"),
+                    "d2h_bytes_per_step": int(2 * B * 10 * 4) * world},
             "gpu_launches": int(res["launches"]), "clocks": res["clk"],
         }
         if world > 1:

@@ -78,6 +78,19 @@ def _worker(rank, world, port, q):
     full = verifiers.chernoff_bound_verification(mdl2, x, 0.01, cls, confidence=0.6, delta=0.3)
     offv, cntv = dd.shard_range(nver, rank, world)
     ok = ok and np.allclose(got, full, rtol=1e-5, atol=1e-6) and _Eng.calls[0] == (100 + offv, cntv) and _Eng.calls[1] == (100, nver)
+    # sharded upload of the shared input batch: every rank contributes ceil(B / world) rows, one all-gather completes it (even and
+    # ragged row counts); the "upload" of this CPU stand-in is a host copy
+    for Bx in (6, 5):
+        xs = o.synthetic_x((Bx, 11), seed=3)
+        seen = []
+
+        def up(a):
+            seen.append(a.shape[0])
+            return torch.from_numpy(np.ascontiguousarray(a))
+        full = dd.sharded_upload(xs, up, torch.device("cpu"))
+        per = (Bx + world - 1) // world
+        ok = ok and full.shape == (Bx, 11) and np.array_equal(full.numpy(), xs) and seen == [min(per, max(Bx - rank * per, 0))]
+    ok = ok and dd.sharded_upload(o.synthetic_x((1, 11), seed=3), up, torch.device("cpu")) is None      # fewer rows than ranks
     q.put((rank, bool(ok), off, cnt))
     dist.destroy_process_group()
 
