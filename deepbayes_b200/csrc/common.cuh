@@ -40,6 +40,9 @@ struct Options {
   long long fused_kd = 128;         // CTA-pair kernel: k-depth of a layer-1 TMA stage (128 = 3 x 64 KB stages, 64 = 6 x 32 KB)
   long long fused_trace = 0, fused_trace_only = 0;   // in-kernel clock probes of one cluster (tools/trace_fused.py)
   long long ws_mb = 2048;           // workspace budget of the generic executor / IBP
+  long long train_graph = 0;        // dbx_bbb_train_epoch (bf16 mode): 1 = replay one captured step as a CUDA graph instead of launching every
+                                    // step's kernels (bit-identical; measured SLOWER on this driver -- 0.33 vs 0.17 ms per step of
+                                    // 784-512-512-10 at mini-batch 128 over 400 steps -- so it is off by default)
 };
 Options& opt();
 

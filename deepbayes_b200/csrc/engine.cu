@@ -42,6 +42,7 @@ static const OptEntry kOptTable[] = {
   {"IBP_OVERLAP", &Options::ibp_overlap}, {"IBP_PRIO", &Options::ibp_prio}, {"GENERIC_OVERLAP", &Options::generic_overlap},
   {"FUSED_OVERLAP", &Options::fused_overlap}, {"FUSED_PRIO", &Options::fused_prio}, {"FUSED_KERNEL", &Options::fused_kernel},
   {"FUSED_ORDER", &Options::fused_order}, {"FUSED_NS", &Options::fused_ns}, {"FUSED_KD", &Options::fused_kd}, {"NO_SHARED_A", &Options::no_shared_a}, {"NO_F32W_WIDE", &Options::no_f32w_wide}, {"FUSED_STREAM", &Options::fused_stream}, {"FUSED_NP", &Options::fused_np}, {"FUSED_L3AT", &Options::fused_l3at}, {"FUSED_TRACE", &Options::fused_trace}, {"FUSED_TRACE_ONLY", &Options::fused_trace_only}, {"WS_MB", &Options::ws_mb},
+  {"TRAIN_GRAPH", &Options::train_graph},
 };
 static void options_from_env(Options& o) {
   o = Options();
@@ -1298,6 +1299,65 @@ int dbx_bbb_train_epoch(dbx_handle h, const float* x_dev, const int32_t* labels_
   DBX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   int64_t i = 0;
+  // Option TRAIN_GRAPH=1 (bf16 mode, standard step): the mini-batches after the first are ONE captured step replayed as a CUDA graph --
+  // what differs between them (Philox step id, first row, output slot) lives in a device-side StepCtx that the graph's last node
+  // advances.  Same kernels, same order, same arguments as the step-by-step loop (bit-identical parameters, tested).  It is NOT the
+  // default: measured with tools/time_train_graph.py the replay was slower than the plain launches (784-512-512-10, mini-batch 128:
+  // 0.18 vs 0.165 ms per step over 40 steps, 0.33 vs 0.17 over 400; mini-batch 1024: 0.22 vs 0.25 over 200, 0.59 vs 0.25 over 40),
+  // i.e. the step is bound by its ~20 dependent kernels' own latencies, not by launch gaps.
+  const int64_t nfull = N / batch;
+  if (mode == DBX_MODE_BF16 && robust_mode == 0 && h->is_mlp && grad_tc_ok(h) && nfull >= 4 && opt().train_graph) {
+    if (!h->own_stream) DBX_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t gs = h->own_stream;      // (stream capture is not possible on the legacy default stream a caller may pass)
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    DBX_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    DBX_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    DBX_CUDA(cudaEventRecord(ev_in, st));
+    DBX_CUDA(cudaStreamWaitEvent(gs, ev_in, 0));
+    // step 0 directly: sizes the workspace and sets the kernels' attributes outside the capture
+    int rc = run_bbb_step(h, x_dev, batch, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, nullptr, seed, step0, lrate, kl_weight,
+                          loss_out_dev, probs_out_dev, 0, epsilon, robust_lambda, in_lower, in_upper, gs, 0, nullptr, mode);
+    StepCtx* ctx = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    if (!rc && cudaMalloc((void**)&ctx, sizeof(StepCtx)) != cudaSuccess) rc = set_err("cudaMalloc(StepCtx) failed");
+    int64_t done = 1;
+    if (!rc) {
+      const StepCtx init = {(long long)(step0 + 1), (long long)batch, 1};
+      if (cudaMemcpyAsync(ctx, &init, sizeof init, cudaMemcpyHostToDevice, gs) != cudaSuccess || cudaStreamSynchronize(gs) != cudaSuccess)
+        rc = set_err("StepCtx upload failed");
+    }
+    bool captured = false;
+    if (!rc && cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      int crc = run_bbb_step_tc(h, x_dev, batch, labels_dev, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, nullptr, seed, 0, lrate, kl_weight,
+                                loss_out_dev, probs_out_dev, 0, epsilon, robust_lambda, in_lower, in_upper, gs, ctx);
+      if (!crc) { step_ctx_advance_kernel<<<1, 32, 0, gs>>>(ctx, (long long)batch); g_launches.fetch_add(1, std::memory_order_relaxed); }
+      const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+      if (!crc && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) captured = true;
+      else cudaGetLastError();      // capture not possible here: the remaining steps run one by one below
+    }
+    if (captured) {
+      const long long per_step = g_launches.load(std::memory_order_relaxed);
+      for (; done < nfull && !rc; ++done)
+        if (cudaGraphLaunch(exec, gs) != cudaSuccess) rc = set_err("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      (void)per_step;
+    }
+    for (int64_t b0 = done * batch; b0 < N && !rc; b0 += batch, ++done) {      // what the graph did not cover (a ragged last mini-batch)
+      const int64_t Bb = std::min(batch, N - b0);
+      rc = run_bbb_step(h, x_dev + b0 * h->in_feat, Bb, labels_dev + b0, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, nullptr, seed, step0 + done,
+                        lrate, kl_weight, loss_out_dev ? loss_out_dev + 2 * done : nullptr, probs_out_dev ? probs_out_dev + b0 * h->out_feat : nullptr,
+                        0, epsilon, robust_lambda, in_lower, in_upper, gs, 0, nullptr, mode);
+    }
+    if (!rc && W_out_dev && cudaMemcpyAsync(W_out_dev, h->ws.ptr, (size_t)h->P * 4, cudaMemcpyDeviceToDevice, gs) != cudaSuccess)
+      rc = set_err("copy of the sampled weights failed");
+    cudaEventRecord(ev_out, gs);
+    cudaStreamWaitEvent(st, ev_out, 0);
+    if (exec || ctx) cudaStreamSynchronize(gs);      // the graph and its context are freed below
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (ctx) cudaFree(ctx);
+    cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
+    return rc;
+  }
   for (int64_t b0 = 0; b0 < N; b0 += batch, ++i) {
     const int64_t Bb = std::min(batch, N - b0);
     if (run_bbb_step(h, x_dev + b0 * h->in_feat, Bb, labels_dev + b0, mean_dev, rho_dev, prior_mean_dev, prior_var_dev, nullptr, seed, step0 + i,

@@ -16,9 +16,25 @@
 
 namespace dbx {
 
+// What changes from one mini-batch of an epoch to the next, kept in DEVICE memory so that one captured step can be replayed as a CUDA
+// graph (dbx_bbb_train_epoch): the Philox step id, the first row of the mini-batch in the epoch's arrays, the step's index in the
+// call.  Kernels that get a StepCtx take these from it and treat their pointers as the epoch's base pointers.
+struct StepCtx { long long step, row0, idx; };
+__global__ void step_ctx_advance_kernel(StepCtx* c, long long rows) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { c->step += 1; c->row0 += rows; c->idx += 1; }
+}
+// x[row0 .. row0 + B) of the epoch's [N][K] fp32 array as the bf16 A operand of the first layer
+__global__ void cast_rows_ctx_kernel(const float* __restrict__ x_base, const StepCtx* __restrict__ ctx, int64_t K, __nv_bfloat16* __restrict__ out,
+                                     int64_t nelem) {
+  const float* in = x_base + ctx->row0 * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nelem; i += (int64_t)gridDim.x * blockDim.x) out[i] = __float2bfloat16_rn(in[i]);
+}
+
 // W = mean + softplus(rho) * noise, noise from Philox (counter = flat index / 4, sample id = step) or injected
 __global__ void bbb_sample_kernel(const float* __restrict__ mean, const float* __restrict__ rho, const float* __restrict__ noise_in,
-                                  uint64_t seed, int64_t step, int64_t P, float* __restrict__ W, float* __restrict__ noise_out) {
+                                  uint64_t seed, int64_t step, int64_t P, float* __restrict__ W, float* __restrict__ noise_out,
+                                  const StepCtx* __restrict__ ctx = nullptr) {
+  if (ctx) step = ctx->step;
   const int64_t nblk = (P + 3) >> 2;
   for (int64_t blk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; blk < nblk; blk += (int64_t)gridDim.x * blockDim.x) {
     float z[4];
@@ -36,9 +52,11 @@ __global__ void bbb_sample_kernel(const float* __restrict__ mean, const float* _
 // dlogits = (softmax(z) - onehot) / B (gradient of the batch-mean cross-entropy; zero where Keras' clip of p to
 // [1e-7, 1-1e-7] is active), probabilities out, per-row -log(clip(p[label])) for the loss value
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int C,
-                                  float* __restrict__ probs, float* __restrict__ dz, float* __restrict__ row_loss) {
+                                  float* __restrict__ probs, float* __restrict__ dz, float* __restrict__ row_loss,
+                                  const StepCtx* __restrict__ ctx = nullptr, int probs_epoch = 0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (ctx) { labels += ctx->row0; if (probs_epoch) probs += ctx->row0 * C; }
   const float* z = logits + (int64_t)b * C;
   float m = z[0];
   for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
@@ -416,8 +434,9 @@ bbb_update_kernel(float* __restrict__ mean, float* __restrict__ rho, const float
 
 // out[0] = loss = mean(row_loss) + kl_weight * (lq_post - lq_prior); out[1] = kl component
 __global__ void bbb_loss_kernel(const float* __restrict__ row_loss, int B, const float* __restrict__ partial, int nblocks,
-                                float kl_weight, float* __restrict__ out) {
+                                float kl_weight, float* __restrict__ out, const StepCtx* __restrict__ ctx = nullptr) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (ctx) out += 2 * ctx->idx;
   float data = 0.f;
   for (int b = 0; b < B; ++b) data += row_loss[b];
   data /= (float)B;
@@ -634,7 +653,9 @@ __global__ void grad_b_bf16_kernel(const __nv_bfloat16* __restrict__ dZ, int ldz
 static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
                            const float* prior_mean_dev, const float* prior_var_dev, const float* noise_dev, uint64_t seed, int64_t step,
                            float lrate, float kl_weight, float* loss_out_dev, float* probs_out_dev, int robust_mode, float epsilon,
-                           float robust_lambda, float in_lower, float in_upper, cudaStream_t st) {
+                           float robust_lambda, float in_lower, float in_upper, cudaStream_t st, const StepCtx* ctx = nullptr) {
+  // ctx (device memory, robust_mode 0 only): this is the step a CUDA graph replays -- x_dev / labels_dev / probs_out_dev /
+  // loss_out_dev are then the EPOCH's base pointers and the step id, first row and output slot come from *ctx
   const int64_t P = m->P, C = m->out_feat, K0 = m->in_feat;
   std::vector<const Layer*> dl;
   for (auto& L : m->layers) if (L.kind == DBX_DENSE) dl.push_back(&L);
@@ -672,7 +693,7 @@ static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const in
   float* partial = (float*)p;
   float* probs = probs_out_dev ? probs_out_dev : probs_scratch;
 
-  DBX_LAUNCH(bbb_sample_kernel, grid_for((P + 3) / 4), 256, 0, st, mean_dev, rho_dev, noise_dev, seed, step, P, W, noise);
+  DBX_LAUNCH(bbb_sample_kernel, grid_for((P + 3) / 4), 256, 0, st, mean_dev, rho_dev, noise_dev, seed, step, P, W, noise, ctx);
   {   // the step's weights in the GEMMs' bf16 layout (kernels padded / aligned for TMA, biases fp32): W read as ONE stored sample
     const float* keep = m->slab; const int64_t keepS = m->S, keepStride = m->slab_stride;
     m->slab = W; m->S = 1; m->slab_stride = P;
@@ -681,7 +702,8 @@ static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const in
     m->slab = keep; m->S = keepS; m->slab_stride = keepStride;
     if (rc) return 1;
   }
-  DBX_LAUNCH(cast_kernel<__nv_bfloat16>, grid_for(B * K0), 256, 0, st, x_dev, xin, B * K0);
+  if (ctx) DBX_LAUNCH(cast_rows_ctx_kernel, grid_for(B * K0), 256, 0, st, x_dev, ctx, K0, xin, B * K0);
+  else DBX_LAUNCH(cast_kernel<__nv_bfloat16>, grid_for(B * K0), 256, 0, st, x_dev, xin, B * K0);
 
   auto forward = [&](const __nv_bfloat16* in, std::vector<__nv_bfloat16*>& out, float* z) -> int {
     const __nv_bfloat16* cur = in;
@@ -720,7 +742,9 @@ static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const in
   };
   if (forward(xin, acts, logits)) return 1;
   if (robust_mode == 0) {
-    DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)logits, labels_dev, (int)B, (int)C, probs, dz32, row_loss);
+    // (with ctx, a null probs_out_dev must not be offset: the scratch buffer holds one mini-batch)
+    DBX_LAUNCH(softmax_ce_kernel, (int)cdiv(B, 128), 128, 0, st, (const float*)logits, labels_dev, (int)B, (int)C, probs, dz32, row_loss, ctx,
+               probs_out_dev ? 1 : 0);
     DBX_LAUNCH(dz_to_bf16_kernel, grid_for(B * Cp), 256, 0, st, (const float*)dz32, (int)B, (int)C, Cp, dz16);
     if (backward(xin, acts, false, 0)) return 1;
   } else {
@@ -740,7 +764,7 @@ static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const in
   for (int i = 0; i < tt.n; ++i) { tt.off[i] = m->table.src_off[i]; tt.end[i] = m->table.src_end[i]; }
   DBX_LAUNCH(bbb_update_kernel, ublocks, 256, 0, st, mean_dev, rho_dev, (const float*)W, (const float*)noise, (const float*)gdata,
              prior_mean_dev, prior_var_dev, P, tt, lrate, kl_weight, partial);
-  if (loss_out_dev) DBX_LAUNCH(bbb_loss_kernel, 1, 32, 0, st, (const float*)row_loss, (int)B, (const float*)partial, ublocks, kl_weight, loss_out_dev);
+  if (loss_out_dev) DBX_LAUNCH(bbb_loss_kernel, 1, 32, 0, st, (const float*)row_loss, (int)B, (const float*)partial, ublocks, kl_weight, loss_out_dev, ctx);
   return 0;
 }
 

@@ -1001,6 +1001,37 @@ def test_bbb_step_bf16_on_tensor_cores_matches_oracle(oracle, dims, B, rt):
         np.testing.assert_allclose(opt._last_probs.cpu().numpy(), pred, rtol=0, atol=2.5 * BF16_ATOL)
 
 
+def test_bbb_train_epoch_graph_replay_equals_step_by_step(oracle, dbx_opt):
+    """dbx_bbb_train_epoch in bf16 mode replays ONE captured step as a CUDA graph for the full mini-batches (step id, first row and
+    output slot come from a device-side context the graph advances): parameters, per-step losses, predictions and the last
+    sampled weights must be bit-identical to launching every step's kernels one by one (the default; option TRAIN_GRAPH=1
+    selects the replay, which measured slower), ragged last mini-batch included."""
+    import torch
+    import deepbayes_b200 as db
+    dims, bs, N = [784, 256, 128, 10], 256, 6 * 256 + 100
+    L = oracle.mlp(dims)
+    layers = [db.Dense(256, activation="relu", input_shape=(784,)), db.Dense(128, activation="relu"), db.Dense(10, activation="softmax")]
+    X = oracle.synthetic_x((N, 784), seed=5)
+    y = np.random.Generator(np.random.Philox(6)).integers(0, 10, size=N).astype(np.int32)
+    res = []
+    for graph in (1, 0):
+        dbx_opt("TRAIN_GRAPH", graph)
+        opt = db.optimizers.BayesByBackprop().compile(db.Sequential(layers), None, batch_size=bs, inflate_prior=1.0, seed=3, train_mode="bf16")
+        mean, std = oracle.synthetic_posterior(L, seed=1, sigma_scale=1.0)
+        eng = opt.engine()
+        dm = eng._dev_f32(oracle.flatten_list(mean)).clone()
+        dr = eng._dev_f32(oracle.flatten_list([oracle.inverse_softplus(s_) for s_ in std])).clone()
+        pm_ = eng._dev_f32(oracle.flatten_list(opt.prior_mean)).clone()
+        pv_ = eng._dev_f32(oracle.flatten_list(opt.prior_var)).clone()
+        Xd, yd = torch.from_numpy(X).to(eng.device), torch.from_numpy(y).to(eng.device)
+        out = eng.bbb_train_epoch(Xd, yd, bs, dm, dr, pm_, pv_, 0.05, 0.5, seed=11, step0=40, mode="bf16")
+        assert eng.last_path() == "generic_tc"
+        res.append([t.cpu().numpy() for t in (dm, dr, out["loss"], out["probs"], out["W"])])
+    for a, b in zip(*res):
+        np.testing.assert_array_equal(a, b)
+    assert np.isfinite(res[0][2]).all() and res[0][2].shape == (7, 2)
+
+
 def test_bbb_training_in_bf16_mode_learns(oracle):
     """A few epochs of BayesByBackprop.train with train_mode="bf16" (one dbx_bbb_train_epoch call per epoch on the tensor-core
     step) reach the accuracy of the fp32 run on the same data."""
