@@ -170,3 +170,37 @@ def test_peer_window_api_refuses_bad_arguments():
     assert lib.dbx_comm_create(0, 1, 0, 0, C.byref(h)) != 0             # empty window
     assert lib.dbx_comm_allreduce(None, None, 0, None, 0, None) != 0
     assert lib.dbx_comm_destroy(None) == 0
+
+
+def test_sharded_upload_switches(monkeypatch):
+    """distributed.sharded_upload_enabled: row-sharded upload of the input batch from 4 ranks on (measured: slower at 2), off with
+    DBX_NO_SHARDED_UPLOAD=1, threshold overridable."""
+    from deepbayes_b200 import distributed as dd
+    monkeypatch.delenv("DBX_NO_SHARDED_UPLOAD", raising=False)
+    monkeypatch.delenv("DBX_SHARDED_UPLOAD_MIN_RANKS", raising=False)
+    assert [dd.sharded_upload_enabled(w) for w in (1, 2, 4, 8)] == [False, False, True, True]
+    assert dd.sharded_upload_enabled() is False                       # no process group: one rank
+    monkeypatch.setenv("DBX_SHARDED_UPLOAD_MIN_RANKS", "2")
+    assert dd.sharded_upload_enabled(2)
+    monkeypatch.setenv("DBX_NO_SHARDED_UPLOAD", "1")
+    assert not dd.sharded_upload_enabled(8)
+    # without a process group there is nothing to shard
+    assert dd.sharded_upload(np.zeros((8, 3), np.float32), lambda a: a, "cpu") is None
+
+
+def test_train_mode_and_attack_mode_arguments():
+    """compile(..., train_mode=) is validated where it is used; the attacks' mode argument resolves like the forward path's."""
+    import deepbayes_b200 as db
+    from deepbayes_b200.analyzers import verifiers
+    m = db.Sequential([db.Dense(8, activation="relu", input_shape=(16,)), db.Dense(4, activation="softmax")])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=8)
+    assert opt._train_mode() == "fp32"                                 # the reference's arithmetic unless asked otherwise
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=8, train_mode="bf16")
+    assert opt._train_mode() == "bf16"
+    opt.train_mode = "fp16"
+    with pytest.raises(ValueError):
+        opt._train_mode()
+
+    class _M:
+        mode = "fp32"
+    assert verifiers._mode_of(_M()) == "fp32" and verifiers._mode_of(_M(), "bf16") == "bf16" and verifiers._mode_of(object()) == "bf16"
