@@ -3,8 +3,10 @@
 (`dbx_input_gradient`): all samples of one ``model.predict`` side by side; forward and backward run in the model's arithmetic
 mode (PosteriorModel.mode / Optimizer.compute_mode): "bf16" = per-sample tcgen05 GEMMs both ways, "fp32" = FFMA kernels.
 
-Scope: Dense MLPs with a softmax output and the sparse categorical cross-entropy (the tutorials' attack loss); order=1.
-As in the reference the model may be a PosteriorModel (its predict() is the mean of 35 sampled forwards, so each
+Scope: the sparse categorical cross-entropy (the tutorials' attack loss).  order=1 (the backward pass on the device): Dense MLPs
+with a softmax output.  order=0 (``zeroth_order_gradient``, attacks.py:17-45): central differences of the loss through
+``model.predict`` alone, so ANY model the forward path takes (convolutions included) -- 2 x feature_size perturbed inputs per image
+go through predict as two batches.  As in the reference the model may be a PosteriorModel (its predict() is the mean of 35 sampled forwards, so each
 iteration differentiates through 35 samples) or an optimizer object (predict() = one forward with the model's weights).
 """
 from __future__ import annotations
@@ -27,6 +29,28 @@ def _labels_of(model, inp, direction):
         return np.argmax(np.asarray(model.predict(inp)).reshape(len(inp), -1), axis=1)
     d = np.asarray(direction).reshape(-1)
     return np.broadcast_to(d, (len(inp),)) if d.size == 1 else d
+
+
+def zeroth_order_gradient(model, inp, direction, loss_fn=None, num_models=25, step=0.35):
+    """attacks.py:17-45: for every image, the loss at inp[i] +- step * e_k for each of its feature_size coordinates, evaluated by
+    two ``model.predict(batch, n=num_models)`` calls (each with its own fresh posterior samples, like the reference), and
+    grad[k] = (loss+ - loss-) / (2 step).  Returns an array shaped like ``inp``."""
+    _check_loss(loss_fn)
+    a = np.asarray(inp, np.float32)
+    n_img, fshape = a.shape[0], a.shape[1:]
+    F = int(np.prod(fshape))
+    step_mask = (np.eye(F, dtype=np.float32) * np.float32(step)).reshape((-1,) + tuple(fshape))      # :23-29
+    d = np.asarray(direction).reshape(-1)
+    d = np.broadcast_to(d, (n_img,)) if d.size == 1 else d
+
+    def row_loss(p, y):      # loss_fn(direction[i], prediction_j) for every perturbed input j (:36, :39)
+        return -np.log(np.clip(np.asarray(p, np.float64).reshape(F, -1)[:, int(y)], 1e-7, 1 - 1e-7))
+    grads = []
+    for i in range(n_img):
+        lp = row_loss(model.predict(a[i] + step_mask, n=num_models), d[i])
+        lm = row_loss(model.predict(a[i] - step_mask, n=num_models), d[i])
+        grads.append(((lp - lm) / (2.0 * step)).reshape(fshape))
+    return np.asarray(grads, np.float32)
 
 
 def gradient_expectation(model, inp, direction, loss_fn=None, num_models=10, mode=None):
@@ -61,22 +85,24 @@ def gradient_expectation(model, inp, direction, loss_fn=None, num_models=10, mod
 
 
 def FGSM(model, inp, loss_fn=None, eps=0.1, direction=-1, num_models=1, order=1, samples=1):
-    """attacks.py:81-102 (``samples`` overrides ``num_models``, :82)."""
-    if order != 1:
-        raise NotImplementedError("zeroth-order gradients (attacks.py:17-45) are not built")
+    """attacks.py:81-102 (``samples`` overrides ``num_models``, :82); order 1 = gradient_expectation, order 0 =
+    zeroth_order_gradient (:92-95)."""
+    if order not in (0, 1):
+        raise ValueError("order must be 0 or 1 (attacks.py:92-95)")
     num_models = samples
     inp = np.asarray(inp)
     maxi, mini = inp + eps, inp - eps
     direc = _labels_of(model, inp, direction)
-    grad = np.sign(gradient_expectation(model, inp, direc, loss_fn, num_models))
+    grad = np.sign(gradient_expectation(model, inp, direc, loss_fn, num_models) if order == 1
+                   else zeroth_order_gradient(model, inp, direc, loss_fn, num_models))
     adv = np.clip(inp + eps * grad, mini, maxi)
     return np.clip(adv, getattr(model, "input_lower", -np.inf), getattr(model, "input_upper", np.inf))
 
 
 def _PGD(model, inp, loss_fn=None, eps=0.1, direc=-1, step=0.1, num_steps=15, num_models=35, order=1):
     """attacks.py:133-165: random sign start of size eps/10, num_steps+1 sign-gradient steps of eps/num_steps, final clips."""
-    if order != 1:
-        raise NotImplementedError("zeroth-order gradients (attacks.py:17-45) are not built")
+    if order != 1:      # the reference's loop computes a gradient for order == 1 only (:152-155: the other branch is commented out)
+        raise NotImplementedError("_PGD builds its gradient for order=1 only (attacks.py:152-155)")
     inp = np.asarray(inp)
     direc = _labels_of(model, inp, direc)
     adv = np.asarray(inp, np.float32)

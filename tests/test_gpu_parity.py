@@ -1244,7 +1244,41 @@ def test_fgsm_and_pgd_lower_the_true_class_probability(oracle, golden_dir):
     p2 = np.asarray(pm.predict(adv2, n=35)).reshape(16, 10)
     assert p2[np.arange(16), cls].mean() < base[np.arange(16), cls].mean() - 1e-3
     with pytest.raises(NotImplementedError):
-        analyzers.FGSM(pm, x, None, eps, order=0)
+        analyzers.PGD(pm, x, None, eps, num_steps=1, order=0)      # the reference's _PGD builds a gradient for order=1 only (:152-155)
+
+
+def test_zeroth_order_gradient_and_fgsm_order0(oracle):
+    """attacks.py:17-45: the central-difference gradient through model.predict alone.  On an optimizer object (predict = one forward
+    with the current weights) it must agree with the analytic input gradient of the same weights; a CNN goes through as well
+    (no backward kernels needed), and FGSM(order=0) lowers the attacked class's probability."""
+    import deepbayes_b200 as db
+    from deepbayes_b200 import analyzers
+    dims = [24, 32, 5]
+    L = oracle.mlp(dims, hidden_act="tanh")      # smooth: central differences are second-order accurate everywhere
+    m = db.Sequential([db.Dense(32, activation="tanh", input_shape=(24,)), db.Dense(5, activation="softmax")])
+    mean, _ = oracle.synthetic_posterior(L, seed=3, sigma_scale=1.0)
+    m.set_weights([w * 3.0 for w in mean])
+    opt = db.optimizers.BayesByBackprop().compile(m, None, batch_size=8, inflate_prior=1.0)
+    x = oracle.synthetic_x((3, 24), seed=4)
+    lab = np.array([1, 4, 0])
+    g0 = analyzers.zeroth_order_gradient(opt, x, lab, None, num_models=1, step=0.01)
+    assert g0.shape == x.shape
+    W = [np.asarray(w) for w in opt.model.get_weights()]
+    for i in range(3):      # the reference differences the PER-IMAGE loss: batch of one
+        want = oracle.input_gradient(L, [W], x[i:i + 1], lab[i:i + 1])[0]
+        np.testing.assert_allclose(g0[i], want, rtol=0, atol=0.02 * np.abs(want).max() + 1e-4)
+    base = np.asarray(opt.predict(x)).reshape(3, 5)
+    cls = base.argmax(1)
+    adv = analyzers.FGSM(opt, x, None, 0.1, order=0, samples=1)
+    assert adv.shape == x.shape and (np.abs(adv - x) <= 0.1 + 1e-6).all()
+    pa = np.asarray(opt.predict(adv)).reshape(3, 5)
+    assert pa[np.arange(3), cls].mean() < base[np.arange(3), cls].mean()
+    # a convolutional model: order 0 needs the forward path only
+    cnn = db.Sequential([db.Conv2D(4, 3, activation="relu", input_shape=(6, 6, 1)), db.Flatten(), db.Dense(3, activation="softmax")])
+    copt = db.optimizers.BayesByBackprop().compile(cnn, None, batch_size=4, inflate_prior=1.0)
+    xc = oracle.synthetic_x((2, 6, 6, 1), seed=5)
+    gc = analyzers.zeroth_order_gradient(copt, xc, np.array([0, 2]), None, num_models=1, step=0.05)
+    assert gc.shape == xc.shape and np.isfinite(gc).all() and np.abs(gc).max() > 0
 
 
 def test_count_predicate_fgsm_matches_oracle(oracle):
