@@ -1,5 +1,5 @@
 """First-order attacks over the posterior -- deepbayes/analyzers/attacks.py: ``gradient_expectation`` (:49-75),
-``FGSM`` (:81-102), ``PGD`` / ``_PGD`` (:133-182) -- with the input gradient evaluated on the device
+``FGSM`` (:81-102), ``PGD`` / ``_PGD`` (:133-182), ``CW`` (:179-226) -- with the input gradient evaluated on the device
 (`dbx_input_gradient`): all samples of one ``model.predict`` side by side; forward and backward run in the model's arithmetic
 mode (PosteriorModel.mode / Optimizer.compute_mode): "bf16" = per-sample tcgen05 GEMMs both ways, "fp32" = FFMA kernels.
 
@@ -124,3 +124,31 @@ def PGD(model, inp, loss_fn=None, eps=0.1, direction=-1, step=0.1, num_steps=5, 
         adv = _PGD(model, inp, loss_fn, eps, direc=direction, step=step, num_steps=num_steps, num_models=num_models, order=order)
         advs.append(adv)
     return adv if restarts == 0 else advs
+
+
+def CW(model, inp, loss_fn=None, eps=0.01, num_steps=5, num_models=25, direction=-1, stepsize=None, decay1=0.99, decay2=0.9999,
+       epsilon=1e-04, order=1):
+    """attacks.py:179-226: num_steps sign steps of size eps / num_steps along an Adam-style direction
+    moment1 / (sqrt(moment2) + epsilon) of the expected input gradient, clipped to the model's input range after every step and
+    to the eps-ball at the end.  As written in the reference: the bias-CORRECTED moments are what the next iteration decays
+    (:207-211 overwrite moment1 / moment2), ``stepsize`` is ignored (:189), and only order=1 yields a gradient (:197-200)."""
+    if order != 1:
+        raise NotImplementedError("CW builds its gradient for order=1 only (attacks.py:197-200)")
+    inp = np.asarray(inp)
+    direc = _labels_of(model, inp, direction)
+    moment1, moment2, time = 0.0, 0.0, 0
+    adv = np.asarray(inp, np.float32)
+    maxi, mini = adv + eps, adv - eps
+    lo, hi = getattr(model, "input_lower", -np.inf), getattr(model, "input_upper", np.inf)
+    for _ in range(num_steps):
+        grad = np.asarray(gradient_expectation(model, adv, direc, loss_fn, num_models), np.float64)
+        time += 1
+        moment1 = (moment1 * decay1) + ((1 - decay1) * grad)
+        moment2 = (moment2 * decay2) + ((1 - decay2) * (grad ** 2))
+        moment1 = moment1 / (1 - (decay1 ** time))
+        moment2 = moment2 / (1 - (decay2 ** time))
+        d = np.sign(moment1 / (np.sqrt(moment2) + epsilon)) * (eps / float(num_steps))
+        adv = np.clip(adv + d, lo, hi).astype(np.float32)
+    adv = np.clip(adv, mini, maxi)
+    return np.clip(adv, lo, hi)
+

@@ -1245,6 +1245,13 @@ def test_fgsm_and_pgd_lower_the_true_class_probability(oracle, golden_dir):
     assert p2[np.arange(16), cls].mean() < base[np.arange(16), cls].mean() - 1e-3
     with pytest.raises(NotImplementedError):
         analyzers.PGD(pm, x, None, eps, num_steps=1, order=0)      # the reference's _PGD builds a gradient for order=1 only (:152-155)
+    # CW (attacks.py:179-226): Adam-style sign steps on the same expected gradient
+    adv3 = analyzers.CW(pm, x, None, eps, num_steps=4, num_models=2)
+    assert adv3.shape == x.shape and (np.abs(adv3 - x) <= eps + 1e-6).all()
+    p3 = np.asarray(pm.predict(adv3, n=35)).reshape(16, 10)
+    assert p3[np.arange(16), cls].mean() < base[np.arange(16), cls].mean() - 1e-3
+    with pytest.raises(NotImplementedError):
+        analyzers.CW(pm, x, None, eps, order=0)
 
 
 def test_zeroth_order_gradient_and_fgsm_order0(oracle):
