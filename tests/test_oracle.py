@@ -495,3 +495,39 @@ def test_oracle_matches_reference_ibp_state_run(oracle, golden_dir):
     np.testing.assert_allclose(hi, ref["state_u"], rtol=1e-12, atol=1e-12)
     lo0, hi0 = oracle.ibp_state(L, w, ref["state_s0"], ref["state_s1"], var, 0.0)
     assert (lo <= lo0 + 1e-12).all() and (hi0 <= hi + 1e-12).all()
+
+
+def test_bf16_emulating_gradients_stay_close_to_the_exact_ones(oracle):
+    """The oracle's bf16 emulation of the widened rows (what the tensor-core gradient loops and training step are compared with on
+    the GPU) rounds GEMM operands only: it must stay within bf16 distance of the exact restatement, and be the exact one when no
+    rounding can happen (operands already representable: a linear model with bf16-valued weights and inputs)."""
+    dims, B = [32, 24, 6], 9
+    L = oracle.mlp(dims)
+    mean, std = oracle.synthetic_posterior(L, seed=2, sigma_scale=1.0)
+    x = oracle.synthetic_x((B, dims[0]), seed=4)
+    lab = np.random.Generator(np.random.Philox(9)).integers(0, dims[-1], size=B)
+    noise = oracle.synthetic_eps(L, 3, seed=3)
+    ws = [oracle.sample_gaussian(mean, std, e, order="f32") for e in noise]
+    g64 = oracle.input_gradient(L, ws, x, lab)
+    g16 = oracle.input_gradient(L, ws, x, lab, bf16=True)
+    assert g16.dtype == np.float32 and 0 < np.linalg.norm(g16 - g64) <= 0.05 * np.linalg.norm(g64)
+    # training step: updates of mean within bf16 distance of the exact step, KL component untouched by the emulation
+    rho = [oracle.inverse_softplus(s) for s in std]
+    pm, pv = oracle.implicit_prior(L, 1.0)
+    a = oracle.bbb_step(L, mean, rho, pm, pv, x, lab, noise[0], 0.1, kl_weight=0.5)
+    b = oracle.bbb_step(L, mean, rho, pm, pv, x, lab, noise[0], 0.1, kl_weight=0.5, dtype=np.float32, bf16=True)
+    for i in range(len(mean)):
+        d64, d16 = (a[0][i] - mean[i]).ravel(), (b[0][i] - mean[i]).ravel().astype(np.float64)
+        assert np.linalg.norm(d16 - d64) <= 0.05 * np.linalg.norm(d64) + 1e-9
+    np.testing.assert_allclose(b[3], a[3], rtol=1e-4)
+    with pytest.raises(NotImplementedError):
+        oracle.bbb_step(L, mean, rho, pm, pv, x, lab, noise[0], 0.1, robust_train=1, epsilon=0.01, bf16=True)
+    # nothing to round: one linear layer, weights and inputs on the bf16 grid -> identical gradients
+    L1 = oracle.mlp([16, 4])
+    g = np.random.Generator(np.random.Philox(5))
+    W1 = [oracle.bf16_round(g.standard_normal((16, 4)).astype(np.float32)), g.standard_normal(4).astype(np.float32)]
+    x1 = oracle.bf16_round(g.random((5, 16)).astype(np.float32))
+    y1 = g.integers(0, 4, size=5)
+    e64, e16 = oracle.input_gradient(L1, [W1], x1, y1), oracle.input_gradient(L1, [W1], x1, y1, bf16=True)
+    # (the upstream gradient dz is still rounded to bf16: 2^-9 relative)
+    np.testing.assert_allclose(e16, e64, rtol=0, atol=2 ** -8 * np.abs(e64).max())
