@@ -103,13 +103,29 @@ grad_w_kernel(const float* __restrict__ A, const float* __restrict__ dZ, int B, 
   }
 }
 
-// db[n] = sum_b dZ[b, n]
-__global__ void grad_b_kernel(const float* __restrict__ dZ, int B, int N, float* __restrict__ db, int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// db[n] = sum_b dZ[b, n].  One block per 32 columns, 32 row groups: thread (r, c) adds rows r, r + 32, ... of column c, the 32
+// partial sums are added in row-group order (deterministic).  (One thread per column walking all B rows took 40-70 us at
+// mini-batch 1024 -- more than the step's tensor-core GEMMs together; profiles/r2_train_step_launches.csv.)
+constexpr int kGradBThreads = 1024;
+template <typename T>
+__device__ __forceinline__ void grad_b_body(const T* __restrict__ dZ, int ldz, int B, int N, float* __restrict__ db, int accumulate) {
+  __shared__ float part[32][33];
+  const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float a = 0.f;
-  for (int b = 0; b < B; ++b) a += dZ[(int64_t)b * N + n];
-  db[n] = accumulate ? db[n] + a : a;
+  if (c < N)
+    for (int b = r; b < B; b += 32) a += (float)dZ[(int64_t)b * ldz + c];
+  part[r][cl] = a;
+  __syncthreads();
+  if (r == 0 && c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += part[i][cl];
+    db[c] = accumulate ? db[c] + s : s;
+  }
+}
+__global__ void __launch_bounds__(kGradBThreads) grad_b_kernel(const float* __restrict__ dZ, int B, int N, float* __restrict__ db, int accumulate) {
+  grad_b_body<float>(dZ, N, B, N, db, accumulate);
 }
 
 // dZprev[b, k] = (sum_n dZ[b, n] * W[k, n]) * act'(Aprev[b, k])   (W: [K, N] row-major)
@@ -435,13 +451,22 @@ bbb_update_kernel(float* __restrict__ mean, float* __restrict__ rho, const float
 // out[0] = loss = mean(row_loss) + kl_weight * (lq_post - lq_prior); out[1] = kl component
 __global__ void bbb_loss_kernel(const float* __restrict__ row_loss, int B, const float* __restrict__ partial, int nblocks,
                                 float kl_weight, float* __restrict__ out, const StepCtx* __restrict__ ctx = nullptr) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  // one warp (launched with 32 threads): lane l adds elements l, l + 32, ..., then a fixed butterfly -- deterministic.  (One thread
+  // walking B row losses and the update kernel's ~600 partial pairs took 50 us at mini-batch 1024.)
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  float data = 0.f, qp = 0.f, pr = 0.f;
+  for (int b = lane; b < B; b += 32) data += row_loss[b];
+  for (int i = lane; i < nblocks; i += 32) { qp += partial[2 * i]; pr += partial[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    data += __shfl_xor_sync(0xffffffffu, data, o);
+    qp += __shfl_xor_sync(0xffffffffu, qp, o);
+    pr += __shfl_xor_sync(0xffffffffu, pr, o);
+  }
+  if (lane != 0) return;
   if (ctx) out += 2 * ctx->idx;
-  float data = 0.f;
-  for (int b = 0; b < B; ++b) data += row_loss[b];
   data /= (float)B;
-  float qp = 0.f, pr = 0.f;
-  for (int i = 0; i < nblocks; ++i) { qp += partial[2 * i]; pr += partial[2 * i + 1]; }
   out[0] = data + kl_weight * (qp - pr);
   out[1] = qp - pr;
 }
@@ -529,7 +554,7 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
       if (!to_input) {
         dim3 gw((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
         DBX_LAUNCH(grad_w_kernel, gw, 256, 0, st, a_prev, (const float*)dz[zi], (int)B, K, N, gdata + L.w_off, accumulate);
-        DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, accumulate);
+        DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 32), kGradBThreads, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, accumulate);
       }
       if (i > 0 || to_input) {
         dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32));
@@ -572,8 +597,8 @@ static int run_bbb_step(dbx_model* m, const float* x_dev, int64_t B, const int32
       dim3 gw((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
       DBX_LAUNCH(ibp_grad_w_kernel, gw, 256, 0, st, up, lp, (const float*)dz[zi], (const float*)dzl[zi], (const float*)W + L.w_off, (int)B, K, N,
                  gdata + L.w_off, accumulate);
-      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, accumulate);
-      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 128), 128, 0, st, (const float*)dzl[zi], (int)B, N, gdata + L.b_off, 1);
+      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 32), kGradBThreads, 0, st, (const float*)dz[zi], (int)B, N, gdata + L.b_off, accumulate);
+      DBX_LAUNCH(grad_b_kernel, (int)cdiv(N, 32), kGradBThreads, 0, st, (const float*)dzl[zi], (int)B, N, gdata + L.b_off, 1);
       if (i > 0) {
         dim3 ga((unsigned)cdiv(K, 32), (unsigned)cdiv(B, 32));
         DBX_LAUNCH(ibp_grad_a_kernel, ga, 256, 0, st, (const float*)dz[zi], (const float*)dzl[zi], (const float*)W + L.w_off, up, lp, (int)B, K, N,
@@ -642,12 +667,9 @@ __global__ void dz_to_bf16_kernel(const float* __restrict__ dz, int B, int C, in
 }
 
 // db[n] = sum_b dZ[b, n], dZ as the GEMMs see it (bf16), summed in fp32 in row order
-__global__ void grad_b_bf16_kernel(const __nv_bfloat16* __restrict__ dZ, int ldz, int B, int N, float* __restrict__ db, int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float a = 0.f;
-  for (int b = 0; b < B; ++b) a += __bfloat162float(dZ[(int64_t)b * ldz + n]);
-  db[n] = accumulate ? db[n] + a : a;
+__global__ void __launch_bounds__(kGradBThreads) grad_b_bf16_kernel(const __nv_bfloat16* __restrict__ dZ, int ldz, int B, int N,
+                                                                    float* __restrict__ db, int accumulate) {
+  grad_b_body<__nv_bfloat16>(dZ, ldz, B, N, db, accumulate);
 }
 
 static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const int32_t* labels_dev, float* mean_dev, float* rho_dev,
@@ -727,7 +749,7 @@ static int run_bbb_step_tc(dbx_model* m, const float* x_dev, int64_t B, const in
       const int K = (int)L.in_feat, N = L.units;
       if (!to_input) {
         if (dense_tc_wgrad_launch(a_prev, K, dz, ldz, (int)B, K, N, gdata + L.w_off, accumulate, st)) { set_err("dense_tc_wgrad launch failed"); return 1; }
-        DBX_LAUNCH(grad_b_bf16_kernel, (int)cdiv(N, 128), 128, 0, st, dz, ldz, (int)B, N, gdata + L.b_off, accumulate);
+        DBX_LAUNCH(grad_b_bf16_kernel, (int)cdiv(N, 32), kGradBThreads, 0, st, dz, ldz, (int)B, N, gdata + L.b_off, accumulate);
       }
       if (i > 0) {
         if (dense_tc_bwd_launch(dz, 0, ldz, W16 + L.w16_off, m->P16, (int)L.w_cols_pad, 1, (int)B, K, N, a[i - 1], 0, dl[i - 1]->units, dl[i - 1]->act,
