@@ -531,3 +531,30 @@ def test_bf16_emulating_gradients_stay_close_to_the_exact_ones(oracle):
     e64, e16 = oracle.input_gradient(L1, [W1], x1, y1), oracle.input_gradient(L1, [W1], x1, y1, bf16=True)
     # (the upstream gradient dz is still rounded to bf16: 2^-9 relative)
     np.testing.assert_allclose(e16, e64, rtol=0, atol=2 ** -8 * np.abs(e64).max())
+
+
+def test_zeroth_order_attack_matches_a_run_of_the_reference_source(oracle, golden_dir):
+    """tests/golden/reference_attacks.npz holds what the reference's own attacks.zeroth_order_gradient (:17-45) and
+    FGSM(order=0) (:81-102) return on the NumPy stand-in for TensorFlow (make_reference_attack_fixtures.py).  The drop-in
+    functions need nothing but model.predict, so they are checked against it here on the CPU with the same model object."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_reference_attack_fixtures import FixtureModel
+    from deepbayes_b200 import analyzers
+    g = np.load(os.path.join(golden_dir, "reference_attacks.npz"))
+    L = oracle.mlp([int(v) for v in g["dims"]], hidden_act="tanh")
+    model = FixtureModel(oracle, L, oracle.split_flat(L, g["W_flat"]))
+    step = float(g["step"][0])
+    got = analyzers.zeroth_order_gradient(model, g["x"], g["labels"], None, num_models=1, step=step)
+    assert got.shape == g["zog"].shape
+    np.testing.assert_allclose(got, g["zog"], rtol=0, atol=2e-5 * np.abs(g["zog"]).max() + 2e-6)
+    got3 = analyzers.zeroth_order_gradient(model, g["x3"], np.array([2, 3]), None, num_models=1, step=step)
+    assert got3.shape == g["zog3"].shape
+    np.testing.assert_allclose(got3, g["zog3"], rtol=0, atol=2e-5 * np.abs(g["zog3"]).max() + 2e-6)
+    adv = analyzers.FGSM(model, g["x"], None, float(g["fgsm_eps"][0]), direction=-1, order=0, samples=1)
+    np.testing.assert_allclose(adv, g["fgsm0_adv"], rtol=0, atol=1e-6)
+    # and the analytic input gradient of the same weights agrees with the reference's central differences (step 0.05, tanh net)
+    W = oracle.split_flat(L, g["W_flat"])
+    for i in range(g["x"].shape[0]):
+        want = oracle.input_gradient(L, [W], g["x"][i:i + 1], g["labels"][i:i + 1])[0]
+        np.testing.assert_allclose(g["zog"][i], want, rtol=0, atol=0.03 * np.abs(want).max() + 1e-4)
