@@ -24,11 +24,12 @@ def predictive_entropy(model, input, num_models=35):
 
 
 def likelihood_ratio(model, input_indist, input_outdist, labels=-1, num_models=35):
-    """uncertainty.py:57-71."""
+    """uncertainty.py:57-71.  As in the reference the loop runs over the IN-distribution predictions' indices (:61-68): only the
+    first len(input_indist) out-of-distribution predictions enter (fewer raise IndexError there too)."""
     indist_pred = np.asarray(model.predict(input_indist, n=num_models))
     outdist_pred = np.asarray(model.predict(input_outdist, n=num_models))
-    in_like = np.asarray([np.max(p) for p in indist_pred])
-    out_like = np.asarray([np.max(p) for p in outdist_pred])
+    in_like = np.asarray([np.max(indist_pred[i]) for i in range(len(indist_pred))])
+    out_like = np.asarray([np.max(outdist_pred[i]) for i in range(len(indist_pred))])
     return np.mean(out_like) / np.mean(in_like)
 
 

@@ -558,3 +558,25 @@ def test_zeroth_order_attack_matches_a_run_of_the_reference_source(oracle, golde
     for i in range(g["x"].shape[0]):
         want = oracle.input_gradient(L, [W], g["x"][i:i + 1], g["labels"][i:i + 1])[0]
         np.testing.assert_allclose(g["zog"][i], want, rtol=0, atol=0.03 * np.abs(want).max() + 1e-4)
+
+
+def test_uncertainty_helpers_match_a_run_of_the_reference_source(oracle, golden_dir):
+    """tests/golden/reference_uncertainty.npz = the reference's own uncertainty.py (:15-71) on a model object whose predict is the
+    oracle's Monte-Carlo mean over Philox-keyed posterior samples.  The drop-in helpers get the same numbers from ONE pass of
+    moments (E[p], E[p^2]) instead of n stacked single-sample predictions."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_reference_uncertainty_fixtures import McModel
+    from deepbayes_b200.analyzers import uncertainty
+    g = np.load(os.path.join(golden_dir, "reference_uncertainty.npz"))
+    L = oracle.mlp([20, 16, 6])
+    mean, std = oracle.synthetic_posterior(L, seed=5, sigma_scale=4.0)
+    n = int(g["n"][0])
+    epi, ale = uncertainty.variational_uncertainty(McModel(oracle, L, mean, std), g["x"], num_samples=n)
+    np.testing.assert_allclose(epi, g["epistemic"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ale, g["aleatoric"], rtol=0, atol=2e-6)
+    assert (g["epistemic"] > 1e-4).any()                                       # the posterior is wide enough for the test to mean something
+    ent = uncertainty.predictive_entropy(McModel(oracle, L, mean, std), g["x"], num_models=n)
+    np.testing.assert_allclose(ent, g["entropy"], rtol=1e-5)
+    lr = uncertainty.likelihood_ratio(McModel(oracle, L, mean, std), g["x"], g["x_out"], num_models=n)
+    np.testing.assert_allclose(lr, g["likelihood_ratio"][0], rtol=1e-6)
