@@ -204,3 +204,72 @@ def test_train_mode_and_attack_mode_arguments():
     class _M:
         mode = "fp32"
     assert verifiers._mode_of(_M()) == "fp32" and verifiers._mode_of(_M(), "bf16") == "bf16" and verifiers._mode_of(object()) == "bf16"
+
+
+def test_massart_bound_check_replays_a_run_of_the_reference_loop(golden_dir):
+    """tests/golden/reference_massart.npz = the reference's own massart_bound_check (verifiers.py:563-653, verify=True,
+    classification=True) on the VOGN tutorial posterior, with the interval bounds every iteration saw.  The drop-in loop evaluates
+    posterior samples in BLOCKS and walks the predicate / Clopper-Pearson / Massart halting rule over them on the host: fed the
+    same per-sample bounds (a stand-in engine), it must stop after the same number of iterations with the same estimate -- all
+    passes, all failures (the I[1] < 0.5 branch) and a mixed run.  okamoto_bound / absolute_massart_halting against the
+    reference's values as well."""
+    import torch
+    from deepbayes_b200.analyzers import verifiers
+    g = np.load(os.path.join(golden_dir, "reference_massart.npz"))
+    for (e, d), want in zip(((0.1, 0.3), (0.05, 0.1), (0.25, 0.3)), g["okamoto"]):
+        assert verifiers.okamoto_bound(e, d) == pytest.approx(want, rel=1e-12)
+    for a, want in zip(g["halting_args"], g["halting"]):
+        assert verifiers.absolute_massart_halting(int(a[0]), int(a[1]), [a[2], a[3]], a[4], a[5], a[6]) == int(want)
+
+    class _Seq:
+        def rows_and_outshape(self, a):
+            return 1, (1, 10)
+
+    class _Eng:
+        C, K = 10, 784
+        model = _Seq()
+
+        def __init__(self, lo, hi):
+            self.lo, self.hi, self.asked = lo, hi, []
+
+        def ibp_samples(self, x, eps, nb, seed, s0, mode="fp32", **kw):
+            self.asked.append((int(s0), int(nb), mode))
+            idx = np.minimum(np.arange(s0, s0 + nb), len(self.lo) - 1)      # samples past the halting point are never looked at
+            return torch.from_numpy(self.lo[idx].reshape(nb, 1, 10).astype(np.float32)), torch.from_numpy(self.hi[idx].reshape(nb, 1, 10).astype(np.float32))
+
+    class _Model:
+        seed, mode, det = 3, "bf16", False
+
+        def __init__(self, eng):
+            self._e, self._next = eng, 0
+
+        def engine(self):
+            return self._e
+
+        def _take_ids(self, k):
+            v = self._next
+            self._next += k
+            return v
+
+        def predict(self, x, n=35):
+            return np.zeros((1, 10), np.float32)
+
+    for name in ("all_pass", "all_fail", "mixed"):
+        eps, cls, conf, delta = g[name + "_params"]
+        cls = int(cls)
+        seen = []
+
+        def predicate(worst, _cls=cls):
+            assert np.asarray(worst).shape == (1, 10) and abs(float(np.sum(worst)) - 1.0) < 1e-5      # softmax of the worst-case logits
+            ok = bool(np.argmax(np.squeeze(worst)) == _cls)
+            seen.append(ok)
+            return ok
+        for block in (4096, 7):
+            del seen[:]
+            eng = _Eng(g[name + "_lo"], g[name + "_hi"])
+            p, it, _ = verifiers.massart_bound_check(_Model(eng), g["x"], float(eps), predicate, cls=cls, classification=True, verify=True,
+                                                     confidence=float(conf), delta=float(delta), block=block)
+            want_p, want_it = g[name + "_result"]
+            assert it == want_it and p == pytest.approx(want_p, rel=1e-12), (name, block, p, it)
+            np.testing.assert_array_equal(np.asarray(seen, np.uint8), g[name + "_outcomes"])
+            assert all(m == "fp32" for _, _, m in eng.asked)          # interval bounds default to fp32 whatever the model's forward mode
