@@ -273,3 +273,36 @@ def test_massart_bound_check_replays_a_run_of_the_reference_loop(golden_dir):
             assert it == want_it and p == pytest.approx(want_p, rel=1e-12), (name, block, p, it)
             np.testing.assert_array_equal(np.asarray(seen, np.uint8), g[name + "_outcomes"])
             assert all(m == "fp32" for _, _, m in eng.asked)          # interval bounds default to fp32 whatever the model's forward mode
+
+
+def test_train_learning_rate_decay_and_linear_epsilon_schedule():
+    """optimizer.py:100-133: lrate_e = learning_rate / (1 + decay * e) and, with linear_schedule (the default, which also adds an
+    epoch, :77-79), epsilon starts at 0 and grows by max_eps / epochs after every epoch (:105-108, :131-132).  The mini-batch
+    loop of BayesByBackprop.train is driven with a recording `step` (no device work)."""
+    import torch
+    import deepbayes_b200 as db
+
+    class Rec(db.optimizers.BayesByBackprop):
+        def step(self, features, labels, lrate, noise=None, sync=True, eps_draws=None):
+            self.rec.append((float(lrate), float(self.epsilon), len(features)))
+            self._last_loss = [0.0, 0.0]
+            self._last_probs = torch.zeros((len(features), 3))
+            return self.posterior_mean, self.posterior_var
+
+    m = db.Sequential([db.Dense(4, activation="relu", input_shape=(5,)), db.Dense(3, activation="softmax")])
+    opt = Rec().compile(m, None, batch_size=4, learning_rate=0.2, decay=0.5, epochs=3, robust_train=2, epsilon=0.08)
+    assert opt.epochs == 4 and opt.robust_linear
+    opt.rec = []
+    X = np.zeros((10, 5), np.float32)
+    y = np.zeros(10, np.int64)
+    opt.train(X, y, device_epochs=False)
+    assert len(opt.rec) == 4 * 3 and [r[2] for r in opt.rec[:3]] == [4, 4, 2]                 # 3 mini-batches per epoch, ragged last one
+    for e in range(4):
+        for lr, eps, _ in opt.rec[3 * e:3 * e + 3]:
+            assert lr == pytest.approx(0.2 / (1 + 0.5 * e)) and eps == pytest.approx(e * 0.08 / 4)
+    assert opt.max_eps == pytest.approx(0.08) and opt.epsilon == pytest.approx(0.08)          # back at max_eps after the last epoch
+    # without the schedule: epsilon constant, no extra epoch
+    opt2 = Rec().compile(m, None, batch_size=4, learning_rate=0.2, epochs=2, robust_train=2, epsilon=0.08, linear_schedule=False)
+    opt2.rec = []
+    opt2.train(X, y, device_epochs=False)
+    assert opt2.epochs == 2 and {r[1] for r in opt2.rec} == {0.08} and {r[0] for r in opt2.rec} == {0.2}
