@@ -26,6 +26,11 @@ network).  The oracle is therefore pinned two ways, both weaker than a real gold
       (log_q, KL_Loss) the same way; the GRADIENTS of bbb_step / input_gradient replace
       tf.GradientTape, which cannot run on the stand-in, and are checked against finite
       differences of those pinned losses -- parity unpinned by a reference run for them.
+  (4) make_reference_attack_fixtures.py runs attacks.zeroth_order_gradient / FGSM(order=0) (they need only tf.eye,
+      tf.reshape and model.predict): the analytic input_gradient below agrees with those reference-run central
+      differences; make_reference_uncertainty_fixtures.py runs analyzers/uncertainty.py;
+      make_reference_massart_fixtures.py runs verifiers.massart_bound_check / okamoto_bound / absolute_massart_halting
+      and records every iteration's interval bounds, which the drop-in loop replays (tests/test_host.py).
 The third-party arithmetic itself (TensorFlow's Eigen matmul rounding, tf.random.normal's
 bit stream) is NOT pinned by anything the reference holds: **parity unpinned** for those,
 as DESIGN.md says.
