@@ -306,3 +306,19 @@ def test_train_learning_rate_decay_and_linear_epsilon_schedule():
     opt2.rec = []
     opt2.train(X, y, device_epochs=False)
     assert opt2.epochs == 2 and {r[1] for r in opt2.rec} == {0.08} and {r[0] for r in opt2.rec} == {0.2}
+
+
+def test_stored_sample_draws_consume_the_numpy_stream_like_the_reference_loop():
+    """posteriormodel.py:77 draws ONE index per loop iteration (`np.random.choice(range(S), p=frequency)`); the drop-in
+    PosteriorModel draws the n indices of a predict in one call (`np.random.choice(S, size=n, p=frequency)`).  Under the same
+    global seed both give the same index sequence and leave the stream in the same state."""
+    S, n = 17, 40
+    f = np.random.Generator(np.random.Philox(1)).random(S)
+    f = f / f.sum()
+    np.random.seed(123)
+    one_by_one = [int(np.random.choice(range(S), p=f)) for _ in range(n)]
+    after_a = np.random.random()
+    np.random.seed(123)
+    at_once = np.random.choice(S, size=n, p=f).astype(np.int32)
+    after_b = np.random.random()
+    assert one_by_one == at_once.tolist() and after_a == after_b
